@@ -1,0 +1,256 @@
+// TEST INFRASTRUCTURE — not part of the product.
+//
+// Thin C-ABI shim over the UNMODIFIED reference (VTM 9.3) built by oracle/Makefile.ref from the
+// sources under /root/reference.  It lets tests/ and bench.py's cpu_baseline / --impl reference leg
+// call the reference's own functions for the motion-search hot path:
+//
+//   RdCost::setDistParam + DistParam::distFunc          (CommonLib/RdCost.cpp:238-324, x86/RdCostX86.h)
+//   InterpolationFilter::filterHor / filterVer          (CommonLib/InterpolationFilter.cpp:749-895)
+//   InterSearch::xPatternSearch                         (EncoderLib/InterSearch.cpp:3566-3608)
+//   InterSearch::xExtDIFUpSamplingH/Q, xPatternRefinement (InterSearch.cpp:5840-6050, 707-761)
+//
+// xPatternSearchFracDIF itself needs a PredictionUnit with a slice; its PU-independent body
+// (InterSearch.cpp:4296-4338) is driven here by calling the three reference functions it calls.
+// Compiled with -fno-access-control so the protected members can be reached without touching
+// the reference sources.  Output: oracle/_ref/libvtmref.so
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+#include <chrono>
+#include <atomic>
+
+#include "CommonLib/CommonDef.h"
+#include "CommonLib/RdCost.h"
+#include "CommonLib/InterpolationFilter.h"
+#include "CommonLib/InterPrediction.h"
+#include "CommonLib/Buffer.h"
+#include "EncoderLib/EncCfg.h"
+#include "EncoderLib/InterSearch.h"
+
+namespace {
+
+struct Probe : public InterSearch
+{
+  RdCost rd;
+  EncCfg cfg;
+  Probe()
+  {
+    InterPrediction::init(&rd, CHROMA_420, 128);
+    m_pcEncCfg = &cfg;
+    m_skipFracME = false;
+    m_useCompositeRef = false;
+  }
+};
+
+ClpRng makeClp(int bd)
+{
+  ClpRng c;
+  c.min = 0;
+  c.max = (1 << bd) - 1;
+  c.bd = bd;
+  c.n = 0;
+  return c;
+}
+
+thread_local Probe* t_probe = nullptr;
+Probe& probe()
+{
+  if (!t_probe) t_probe = new Probe();   // leaked on purpose: InterSearch::destroy() wants a full init
+  return *t_probe;
+}
+
+}   // namespace
+
+extern "C" {
+
+// 0 SCALAR, 1 SSE41, 2 SSE42, 3 AVX, 4 AVX2, 5 AVX512 (CommonDef.h:609-617)
+int ref_simd_level() { return (int) read_x86_extension_flags(); }
+
+// ME-flavour setDistParam (RdCost.cpp:238-324) + call through the dispatch table.
+uint64_t ref_dist(const int16_t* org, int orgStride, const int16_t* cur, int curStride, int w, int h,
+                  int bitDepth, int subShiftMode, int useHad)
+{
+  Probe& p = probe();
+  DistParam dp;
+  CPelBuf o(org, orgStride, w, h);
+  p.rd.setDistParam(dp, o, cur, curStride, bitDepth, COMPONENT_Y, subShiftMode, 1, useHad != 0);
+  return dp.distFunc(dp);
+}
+
+// subShift the reference picks for (mode,w,h)
+int ref_subshift(int subShiftMode, int w, int h)
+{
+  Probe& p = probe();
+  DistParam dp;
+  static int16_t dummy[4];
+  CPelBuf o(dummy, w, w, h);
+  p.rd.setDistParam(dp, o, dummy, w, 10, COMPONENT_Y, subShiftMode, 1, false);
+  return dp.subShift;
+}
+
+uint32_t ref_mv_bits(int x, int y, int predX, int predY, int costScale, int imvShift)
+{
+  Probe& p = probe();
+  p.rd.setPredictor(Mv(predX, predY));
+  p.rd.setCostScale(costScale);
+  return p.rd.getBitsOfVectorWithPredictor(x, y, imvShift);
+}
+
+uint64_t ref_mv_cost(double lambdaMotion, uint32_t bits)
+{
+  Probe& p = probe();
+  p.rd.m_motionLambda = lambdaMotion;
+  return p.rd.getCost(bits);
+}
+
+void ref_filter_hor(int comp, const int16_t* src, int srcStride, int16_t* dst, int dstStride, int w, int h,
+                    int frac, int isLast, int bd, int useAltHpel)
+{
+  Probe& p = probe();
+  p.m_if.filterHor(ComponentID(comp), src, srcStride, dst, dstStride, w, h, frac, isLast != 0, CHROMA_420,
+                   makeClp(bd), 0, false, useAltHpel != 0);
+}
+
+void ref_filter_ver(int comp, const int16_t* src, int srcStride, int16_t* dst, int dstStride, int w, int h,
+                    int frac, int isFirst, int isLast, int bd, int useAltHpel)
+{
+  Probe& p = probe();
+  p.m_if.filterVer(ComponentID(comp), src, srcStride, dst, dstStride, w, h, frac, isFirst != 0, isLast != 0,
+                   CHROMA_420, makeClp(bd), 0, false, useAltHpel != 0);
+}
+
+struct RefSearchJob
+{
+  const int16_t* org;      // original block (uni-pred: in the original picture)
+  int            orgStride;
+  int            w, h;
+  const int16_t* refAtPU;  // reference picture plane at the PU position (piRefY)
+  int            refStride;
+  int            srLeft, srRight, srTop, srBottom;   // integer-pel window (cStruct.searchRange)
+  int            predQx, predQy;                     // AMVP predictor in quarter-pel (RdCost::setPredictor)
+  int            imvShift;                           // 0 qpel, 1 hpel, 2 fpel, 4 4pel
+  int            subShiftMode;                       // 0 or 2 (FEN)
+  int            bitDepth;
+  int            useHad;                             // HadamardME && !DisableSATDForRD
+  int            useAltHpel;
+  int            doFrac;                             // 0: integer only, 1: run the xPatternSearchFracDIF body
+  double         lambdaMotion;
+};
+
+struct RefSearchResult
+{
+  int      mvX, mvY;         // best integer MV
+  uint64_t intSad;           // ruiSAD of xPatternSearch (best − mv cost)
+  int      halfX, halfY;     // rcMvHalf
+  int      qterX, qterY;     // rcMvQter
+  uint64_t fracCost;         // ruiCost after xPatternSearchFracDIF (SATD + mv cost)
+};
+
+// xPatternSearch (+ the PU-independent body of xPatternSearchFracDIF, InterSearch.cpp:4296-4338)
+void ref_search(const RefSearchJob* j, RefSearchResult* r)
+{
+  Probe& p = probe();
+  p.rd.m_motionLambda = j->lambdaMotion;
+  p.rd.setPredictor(Mv(j->predQx, j->predQy));
+  p.rd.setCostScale(2);
+  p.cfg.setUseHADME(j->useHad != 0);
+  p.m_lumaClpRng = makeClp(j->bitDepth);
+
+  CPelBuf pattern(j->org, j->orgStride, j->w, j->h);
+  InterSearch::IntTZSearchStruct cs;
+  memset(&cs, 0, sizeof(cs));
+  cs.pcPatternKey = &pattern;
+  cs.piRefY       = j->refAtPU;
+  cs.iRefStride   = j->refStride;
+  cs.imvShift     = j->imvShift;
+  cs.useAltHpelIf = j->useAltHpel != 0;
+  cs.subShiftMode = j->subShiftMode;
+  cs.searchRange.left   = j->srLeft;
+  cs.searchRange.right  = j->srRight;
+  cs.searchRange.top    = j->srTop;
+  cs.searchRange.bottom = j->srBottom;
+
+  Mv         mv;
+  Distortion cost = 0;
+  p.xPatternSearch(cs, mv, cost);
+  r->mvX    = mv.hor;
+  r->mvY    = mv.ver;
+  r->intSad = cost;
+  r->halfX = r->halfY = r->qterX = r->qterY = 0;
+  r->fracCost = cost;
+  if (!j->doFrac) return;
+
+  // ---- body of xPatternSearchFracDIF (InterSearch.cpp:4296-4338), calling the reference's own helpers
+  Mv  mvHalf, mvQter;
+  int iOffset = mv.getHor() + mv.getVer() * cs.iRefStride;
+  CPelBuf roi(cs.piRefY + iOffset, cs.iRefStride, *cs.pcPatternKey);
+  if (cs.imvShift > IMV_FPEL)
+  {
+    p.rd.setDistParam(p.m_cDistParam, *cs.pcPatternKey, cs.piRefY + iOffset, cs.iRefStride, p.m_lumaClpRng.bd,
+                      COMPONENT_Y, 0, 1, j->useHad != 0);
+    cost = p.m_cDistParam.distFunc(p.m_cDistParam);
+    cost += p.rd.getCostOfVectorWithPredictor(mv.getHor(), mv.getVer(), cs.imvShift);
+    r->fracCost = cost;
+    return;
+  }
+  p.rd.setCostScale(1);
+  p.xExtDIFUpSamplingH(&roi, cs.useAltHpelIf);
+  mvHalf = mv;
+  mvHalf <<= 1;
+  Mv baseRefMv(0, 0);
+  cost = p.xPatternRefinement(cs.pcPatternKey, baseRefMv, 2, mvHalf, true);
+  if (cs.imvShift == IMV_OFF)
+  {
+    p.rd.setCostScale(0);
+    p.xExtDIFUpSamplingQ(&roi, mvHalf);
+    baseRefMv = mvHalf;
+    baseRefMv <<= 1;
+    mvQter = mv;
+    mvQter <<= 1;
+    mvQter += mvHalf;
+    mvQter <<= 1;
+    cost = p.xPatternRefinement(cs.pcPatternKey, baseRefMv, 1, mvQter, true);
+  }
+  else
+  {
+    mvQter.setZero();
+  }
+  r->halfX    = mvHalf.hor;
+  r->halfY    = mvHalf.ver;
+  r->qterX    = mvQter.hor;
+  r->qterY    = mvQter.ver;
+  r->fracCost = cost;
+}
+
+// Batch driver used as the CPU baseline: nThreads workers over disjoint job ranges.
+// Returns wall seconds spent in the searches (steady_clock around the work only).
+double ref_search_batch(const RefSearchJob* jobs, RefSearchResult* res, int n, int nThreads)
+{
+  if (nThreads < 1) nThreads = 1;
+  std::atomic<int> next(0);
+  auto t0 = std::chrono::steady_clock::now();
+  auto worker = [&]() {
+    for (;;)
+    {
+      int i = next.fetch_add(16);
+      if (i >= n) break;
+      int e = i + 16 < n ? i + 16 : n;
+      for (; i < e; i++) ref_search(&jobs[i], &res[i]);
+    }
+  };
+  if (nThreads == 1)
+  {
+    worker();
+  }
+  else
+  {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nThreads; t++) th.emplace_back(worker);
+    for (auto& t : th) t.join();
+  }
+  auto t1 = std::chrono::steady_clock::now();
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
+}   // extern "C"

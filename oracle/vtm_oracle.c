@@ -1,0 +1,644 @@
+/* TEST INFRASTRUCTURE — CPU oracle, not part of the product (see vtm_oracle.h for the rules and the
+ * parity status: PINNED against the compiled reference, oracle/_ref/libvtmref.so).
+ *
+ * Every function cites the VTM 9.3 file:line it restates (paths relative to /root/reference/source/Lib).
+ */
+#include "vtm_oracle.h"
+
+#include <limits.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#define VO_MAX_CU 128
+#define VO_NTAPS_LUMA 8
+#define VO_IF_INTERNAL_PREC 14 /* InterpolationFilter.h:48 */
+#define VO_IF_FILTER_PREC 6    /* :49 */
+#define VO_IF_INTERNAL_OFFS (1 << (VO_IF_INTERNAL_PREC - 1))
+
+static int vo_floor_log2(uint32_t x) /* CommonDef.h:640-648 */
+{
+  int r = -1;
+  while (x)
+  {
+    x >>= 1;
+    r++;
+  }
+  return r;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Distortion
+ * ---------------------------------------------------------------------------------------------- */
+
+/* RdCost::setDistParam, sub-sampling choice — CommonLib/RdCost.cpp:289-323 */
+int vo_subshift(int subShiftMode, int w, int h)
+{
+  int s = 0;
+  if (subShiftMode == 1)
+  {
+    if (h > 32 && (h & 15) == 0)
+      s = 4;
+    else if (h > 16 && (h & 7) == 0)
+      s = 3;
+    else if (h > 8 && (h & 3) == 0)
+      s = 2;
+    else if ((h & 1) == 0)
+      s = 1;
+  }
+  else if (subShiftMode == 2)
+  {
+    if (h > 8 && w <= 64) s = 1;
+  }
+  else if (subShiftMode == 3)
+  {
+    if (h > 8) s = 1;
+  }
+  return s;
+}
+
+/* RdCost::xGetSAD — CommonLib/RdCost.cpp:493-528 (the SIMD versions x86/RdCostX86.h:210-456 compute the
+ * same sum; the scalar early exit on maximumDistortionForEarlyExit :518-521 never changes an argmin and
+ * is not restated).  DISTORTION_PRECISION_ADJUSTMENT is 0 (TypeDef.h:228-233). */
+uint64_t vo_sad(const vo_pel* org, int orgStride, const vo_pel* cur, int curStride, int w, int h, int subShift)
+{
+  const int step = 1 << subShift;
+  uint64_t  sum  = 0;
+  for (int rows = h; rows != 0; rows -= step)
+  {
+    for (int n = 0; n < w; n++) sum += (uint64_t) abs(org[n] - cur[n]);
+    org += orgStride * step;
+    cur += curStride * step;
+  }
+  return sum << subShift;
+}
+
+/* One Hadamard tile: Σ|coef| with the DC term scaled >>2 (JVET_R0164_MEAN_SCALED_SATD, TypeDef.h:62).
+ * Restates the butterflies of xCalcHADs{2x2,4x4,8x8,16x8,8x16,4x8,8x4} — CommonLib/RdCost.cpp:2140-2817.
+ * The reference's fixed butterfly networks are Walsh-Hadamard transforms along rows and columns; the
+ * sum of absolute coefficients does not depend on the output ordering, only the DC position matters
+ * (index [0][0] in every reference variant). */
+static int64_t vo_had_tile_raw(const vo_pel* org, int orgStride, const vo_pel* cur, int curStride, int tw, int th)
+{
+  int m[16][16];
+  for (int y = 0; y < th; y++)
+    for (int x = 0; x < tw; x++) m[y][x] = org[y * orgStride + x] - cur[y * curStride + x];
+  for (int y = 0; y < th; y++) /* horizontal */
+    for (int len = 1; len < tw; len <<= 1)
+      for (int i = 0; i < tw; i += len << 1)
+        for (int k = i; k < i + len; k++)
+        {
+          int a = m[y][k], b = m[y][k + len];
+          m[y][k]       = a + b;
+          m[y][k + len] = a - b;
+        }
+  for (int x = 0; x < tw; x++) /* vertical */
+    for (int len = 1; len < th; len <<= 1)
+      for (int i = 0; i < th; i += len << 1)
+        for (int k = i; k < i + len; k++)
+        {
+          int a = m[k][x], b = m[k + len][x];
+          m[k][x]       = a + b;
+          m[k + len][x] = a - b;
+        }
+  int64_t s = 0;
+  for (int y = 0; y < th; y++)
+    for (int x = 0; x < tw; x++) s += abs(m[y][x]);
+  s -= abs(m[0][0]);
+  s += abs(m[0][0]) >> 2;
+  return s;
+}
+
+static uint64_t vo_had_tile(const vo_pel* org, int os, const vo_pel* cur, int cs, int tw, int th)
+{
+  int64_t s = vo_had_tile_raw(org, os, cur, cs, tw, th);
+  if (tw == 2 && th == 2) return (uint64_t) s;                 /* RdCost.cpp:2154-2163 */
+  if (tw == 4 && th == 4) return (uint64_t) ((s + 1) >> 1);    /* :2262 */
+  if (tw == 8 && th == 8) return (uint64_t) ((s + 2) >> 2);    /* :2363 */
+  if (tw * th == 128) return (uint64_t) (int) ((int) s / sqrt(16.0 * 8) * 2); /* :2513, :2654 */
+  return (uint64_t) (int) ((int) s / sqrt(4.0 * 8) * 2);       /* :2731, :2814 */
+}
+
+/* RdCost::xGetHADs — CommonLib/RdCost.cpp:2819-2934 (same tiling as xGetHADs_SIMD,
+ * x86/RdCostX86.h:2154-2291; its AVX2 16x16 tile is four 8x8 tiles). */
+uint64_t vo_satd(const vo_pel* org, int os, const vo_pel* cur, int cs, int w, int h)
+{
+  int tw, th;
+  if (w > h && (h & 7) == 0 && (w & 15) == 0)
+    tw = 16, th = 8;
+  else if (w < h && (w & 7) == 0 && (h & 15) == 0)
+    tw = 8, th = 16;
+  else if (w > h && (h & 3) == 0 && (w & 7) == 0)
+    tw = 8, th = 4;
+  else if (w < h && (w & 3) == 0 && (h & 7) == 0)
+    tw = 4, th = 8;
+  else if ((h % 8 == 0) && (w % 8 == 0))
+    tw = 8, th = 8;
+  else if ((h % 4 == 0) && (w % 4 == 0))
+    tw = 4, th = 4;
+  else
+    tw = 2, th = 2;
+  uint64_t sum = 0;
+  for (int y = 0; y < h; y += th)
+    for (int x = 0; x < w; x += tw) sum += vo_had_tile(org + y * os + x, os, cur + y * cs + x, cs, tw, th);
+  return sum;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Motion-vector rate
+ * ---------------------------------------------------------------------------------------------- */
+
+/* RdCost::xGetExpGolombNumberOfBits — CommonLib/RdCost.h:301-313 (MAX_CU_SIZE 128, MAX_CU_DEPTH 7) */
+uint32_t vo_eg_bits(int v)
+{
+  unsigned len = 1, t = (v <= 0) ? ((unsigned) (-v) << 1) + 1 : (unsigned) (v << 1);
+  while (t > 128)
+  {
+    len += 14;
+    t >>= 7;
+  }
+  return len + ((unsigned) vo_floor_log2(t) << 1);
+}
+
+/* RdCost::getBitsOfVectorWithPredictor — CommonLib/RdCost.h:315 */
+uint32_t vo_mv_bits(int x, int y, int predX, int predY, int costScale, int imvShift)
+{
+  return vo_eg_bits(((x << costScale) - predX) >> imvShift) + vo_eg_bits(((y << costScale) - predY) >> imvShift);
+}
+
+/* RdCost::getCost — CommonLib/RdCost.h:191 */
+uint64_t vo_mv_cost(double lambdaMotion, uint32_t bits) { return (uint64_t) (lambdaMotion * bits); }
+
+/* ------------------------------------------------------------------------------------------------
+ * Interpolation
+ * ---------------------------------------------------------------------------------------------- */
+
+/* CommonLib/InterpolationFilter.cpp:57-95, 181-216 */
+static const int16_t vo_luma4x4[16][8] = {
+  { 0, 0, 0, 64, 0, 0, 0, 0 },     { 0, 1, -3, 63, 4, -2, 1, 0 },   { 0, 1, -5, 62, 8, -3, 1, 0 },
+  { 0, 2, -8, 60, 13, -4, 1, 0 },  { 0, 3, -10, 58, 17, -5, 1, 0 }, { 0, 3, -11, 52, 26, -8, 2, 0 },
+  { 0, 2, -9, 47, 31, -10, 3, 0 }, { 0, 3, -11, 45, 34, -10, 3, 0 }, { 0, 3, -11, 40, 40, -11, 3, 0 },
+  { 0, 3, -10, 34, 45, -11, 3, 0 }, { 0, 3, -10, 31, 47, -9, 2, 0 }, { 0, 2, -8, 26, 52, -11, 3, 0 },
+  { 0, 1, -5, 17, 58, -10, 3, 0 }, { 0, 1, -4, 13, 60, -8, 2, 0 },  { 0, 1, -3, 8, 62, -5, 1, 0 },
+  { 0, 1, -2, 4, 63, -3, 1, 0 }
+};
+static const int16_t vo_luma[16][8] = {
+  { 0, 0, 0, 64, 0, 0, 0, 0 },       { 0, 1, -3, 63, 4, -2, 1, 0 },     { -1, 2, -5, 62, 8, -3, 1, 0 },
+  { -1, 3, -8, 60, 13, -4, 1, 0 },   { -1, 4, -10, 58, 17, -5, 1, 0 },  { -1, 4, -11, 52, 26, -8, 3, -1 },
+  { -1, 3, -9, 47, 31, -10, 4, -1 }, { -1, 4, -11, 45, 34, -10, 4, -1 }, { -1, 4, -11, 40, 40, -11, 4, -1 },
+  { -1, 4, -10, 34, 45, -11, 4, -1 }, { -1, 4, -10, 31, 47, -9, 3, -1 }, { -1, 3, -8, 26, 52, -11, 4, -1 },
+  { 0, 1, -5, 17, 58, -10, 4, -1 },  { 0, 1, -4, 13, 60, -8, 3, -1 },   { 0, 1, -3, 8, 62, -5, 2, -1 },
+  { 0, 1, -2, 4, 63, -3, 1, 0 }
+};
+static const int16_t vo_luma_alt_hpel[8] = { 0, 3, 9, 20, 20, 9, 3, 0 };
+static const int16_t vo_chroma[32][4]    = {
+  { 0, 64, 0, 0 },    { -1, 63, 2, 0 },   { -2, 62, 4, 0 },   { -2, 60, 7, -1 },  { -2, 58, 10, -2 }, { -3, 57, 12, -2 },
+  { -4, 56, 14, -2 }, { -4, 55, 15, -2 }, { -4, 54, 16, -2 }, { -5, 53, 18, -2 }, { -6, 52, 20, -2 }, { -6, 49, 24, -3 },
+  { -6, 46, 28, -4 }, { -5, 44, 29, -4 }, { -4, 42, 30, -4 }, { -4, 39, 33, -4 }, { -4, 36, 36, -4 }, { -4, 33, 39, -4 },
+  { -4, 30, 42, -4 }, { -4, 29, 44, -5 }, { -4, 28, 46, -6 }, { -3, 24, 49, -6 }, { -2, 20, 52, -6 }, { -2, 18, 53, -5 },
+  { -2, 16, 54, -4 }, { -2, 15, 55, -4 }, { -2, 14, 56, -4 }, { -2, 12, 57, -3 }, { -2, 10, 58, -2 }, { -1, 7, 60, -2 },
+  { 0, 4, 62, -2 },   { 0, 2, 63, -1 }
+};
+
+static int vo_clip(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* InterpolationFilter::filterCopy<isFirst,isLast> — CommonLib/InterpolationFilter.cpp:397-524 (biMCForDMVR=false) */
+static void vo_filter_copy(int isFirst, int isLast, int bd, const vo_pel* src, int ss, vo_pel* dst, int ds, int w, int h)
+{
+  const int shift = (VO_IF_INTERNAL_PREC - bd) > 2 ? (VO_IF_INTERNAL_PREC - bd) : 2;
+  const int maxv  = (1 << bd) - 1;
+  for (int row = 0; row < h; row++)
+  {
+    for (int col = 0; col < w; col++)
+    {
+      if (isFirst == isLast)
+        dst[col] = src[col];
+      else if (isFirst)
+      {
+        vo_pel val = (vo_pel) (src[col] << shift);
+        dst[col]   = (vo_pel) (val - (vo_pel) VO_IF_INTERNAL_OFFS);
+      }
+      else
+      {
+        vo_pel val = src[col];
+        val        = (vo_pel) ((val + VO_IF_INTERNAL_OFFS + (1 << (shift - 1))) >> shift);
+        dst[col]   = (vo_pel) vo_clip(val, 0, maxv);
+      }
+    }
+    src += ss;
+    dst += ds;
+  }
+}
+
+/* InterpolationFilter::filter<N,isVertical,isFirst,isLast> — CommonLib/InterpolationFilter.cpp:550-656 */
+static void vo_filter(int N, int isVertical, int isFirst, int isLast, int bd, const vo_pel* src, int ss, vo_pel* dst,
+                      int ds, int w, int h, const int16_t* coeff)
+{
+  const int cStride = isVertical ? ss : 1;
+  src -= (N / 2 - 1) * cStride;
+  const int headRoom = (VO_IF_INTERNAL_PREC - bd) > 2 ? (VO_IF_INTERNAL_PREC - bd) : 2;
+  int       shift    = VO_IF_FILTER_PREC;
+  int       offset;
+  const int maxv = (1 << bd) - 1;
+  if (isLast)
+  {
+    shift += isFirst ? 0 : headRoom;
+    offset = 1 << (shift - 1);
+    offset += isFirst ? 0 : VO_IF_INTERNAL_OFFS << VO_IF_FILTER_PREC;
+  }
+  else
+  {
+    shift -= isFirst ? headRoom : 0;
+    offset = isFirst ? -(VO_IF_INTERNAL_OFFS << shift) : 0;
+  }
+  for (int row = 0; row < h; row++)
+  {
+    for (int col = 0; col < w; col++)
+    {
+      int sum = 0;
+      for (int k = 0; k < N; k++) sum += src[col + k * cStride] * coeff[k];
+      vo_pel val = (vo_pel) ((sum + offset) >> shift);
+      if (isLast) val = (vo_pel) vo_clip(val, 0, maxv);
+      dst[col] = val;
+    }
+    src += ss;
+    dst += ds;
+  }
+}
+
+/* InterpolationFilter::filterHor (public dispatch) — CommonLib/InterpolationFilter.cpp:749-810, nFilterIdx 0 */
+void vo_filter_hor(int comp, const vo_pel* src, int ss, vo_pel* dst, int ds, int w, int h, int frac, int isLast, int bd,
+                   int useAltHpel)
+{
+  if (frac == 0)
+    vo_filter_copy(1, isLast, bd, src, ss, dst, ds, w, h);
+  else if (comp == 0)
+  {
+    const int16_t* c;
+    if (frac == 8 && useAltHpel)
+      c = vo_luma_alt_hpel;
+    else if ((w == 4 && h == 4) || (w == 4 && h == (4 + VO_NTAPS_LUMA - 1)))
+      c = vo_luma4x4[frac];
+    else
+      c = vo_luma[frac];
+    vo_filter(8, 0, 1, isLast, bd, src, ss, dst, ds, w, h, c);
+  }
+  else
+    vo_filter(4, 0, 1, isLast, bd, src, ss, dst, ds, w, h, vo_chroma[frac]); /* 4:2:0: frac << (1-csx), csx = 1 */
+}
+
+/* InterpolationFilter::filterVer (public dispatch) — CommonLib/InterpolationFilter.cpp:829-895 */
+void vo_filter_ver(int comp, const vo_pel* src, int ss, vo_pel* dst, int ds, int w, int h, int frac, int isFirst,
+                   int isLast, int bd, int useAltHpel)
+{
+  if (frac == 0)
+    vo_filter_copy(isFirst, isLast, bd, src, ss, dst, ds, w, h);
+  else if (comp == 0)
+  {
+    const int16_t* c;
+    if (frac == 8 && useAltHpel)
+      c = vo_luma_alt_hpel;
+    else if (w == 4 && h == 4)
+      c = vo_luma4x4[frac];
+    else
+      c = vo_luma[frac];
+    vo_filter(8, 1, isFirst, isLast, bd, src, ss, dst, ds, w, h, c);
+  }
+  else
+    vo_filter(4, 1, isFirst, isLast, bd, src, ss, dst, ds, w, h, vo_chroma[frac]);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Search window
+ * ---------------------------------------------------------------------------------------------- */
+
+/* clipMvInPic — CommonLib/Mv.cpp:53-71; InterSearch::xClipMv — EncoderLib/InterSearch.cpp:7735-7764
+ * (no wrap-around, no sub-pictures: identical bounds) */
+void vo_clip_mv(int* mvx, int* mvy, int posX, int posY, int picW, int picH, int maxCuW, int maxCuH)
+{
+  const int mvShift = 4, offset = 8;
+  int       horMax = (picW + offset - posX - 1) << mvShift;
+  int       horMin = (-maxCuW - offset - posX + 1) * (1 << mvShift);
+  int       verMax = (picH + offset - posY - 1) << mvShift;
+  int       verMin = (-maxCuH - offset - posY + 1) * (1 << mvShift);
+  *mvx             = *mvx > horMax ? horMax : (*mvx < horMin ? horMin : *mvx);
+  *mvy             = *mvy > verMax ? verMax : (*mvy < verMin ? verMin : *mvy);
+}
+
+static int vo_div_pow2(int v, int i) /* Mv::divideByPowerOf2 — CommonLib/Mv.h:128-136 */
+{
+  const int offset = 1 << (i - 1);
+  return (v + offset - (v >= 0)) >> i;
+}
+
+/* InterSearch::xSetSearchRange — EncoderLib/InterSearch.cpp:3496-3535 */
+void vo_set_search_range(int predX16, int predY16, int posX, int posY, int picW, int picH, int maxCuW, int maxCuH,
+                         int searchRange, int* left, int* right, int* top, int* bottom)
+{
+  int px = predX16, py = predY16;
+  vo_clip_mv(&px, &py, posX, posY, picW, picH, maxCuW, maxCuH);
+  int tlx = px - (searchRange << 4), tly = py - (searchRange << 4);
+  int brx = px + (searchRange << 4), bry = py + (searchRange << 4);
+  vo_clip_mv(&tlx, &tly, posX, posY, picW, picH, maxCuW, maxCuH);
+  vo_clip_mv(&brx, &bry, posX, posY, picW, picH, maxCuW, maxCuH);
+  *left   = vo_div_pow2(tlx, 4);
+  *top    = vo_div_pow2(tly, 4);
+  *right  = vo_div_pow2(brx, 4);
+  *bottom = vo_div_pow2(bry, 4);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Integer full search
+ * ---------------------------------------------------------------------------------------------- */
+
+/* InterSearch::xPatternSearch — EncoderLib/InterSearch.cpp:3566-3608 */
+void vo_pattern_search(const vo_job* j, int* mvx, int* mvy, uint64_t* sadOut)
+{
+  uint64_t  best     = UINT64_MAX;
+  int       bx = 0, by = 0;
+  const int subShift = vo_subshift(j->subShiftMode, j->w, j->h);
+  for (int y = j->srTop; y <= j->srBottom; y++)
+    for (int x = j->srLeft; x <= j->srRight; x++)
+    {
+      uint64_t sad = vo_sad(j->org, j->orgStride, j->refAtPU + y * j->refStride + x, j->refStride, j->w, j->h, subShift);
+      sad += vo_mv_cost(j->lambdaMotion, vo_mv_bits(x, y, j->predQx, j->predQy, 2, j->imvShift));
+      if (sad < best)
+      {
+        best = sad;
+        bx   = x;
+        by   = y;
+      }
+    }
+  *mvx    = bx;
+  *mvy    = by;
+  *sadOut = best - vo_mv_cost(j->lambdaMotion, vo_mv_bits(bx, by, j->predQx, j->predQy, 2, j->imvShift));
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Fractional refinement
+ * ---------------------------------------------------------------------------------------------- */
+
+static const int vo_refine_h[9][2] = { { 0, 0 },  { 0, -1 }, { 0, 1 },  { -1, 0 }, { 1, 0 },
+                                       { -1, -1 }, { 1, -1 }, { -1, 1 }, { 1, 1 } }; /* InterSearch.cpp:59-70 */
+static const int vo_refine_q[9][2] = { { 0, 0 },  { 0, -1 }, { 0, 1 },  { -1, -1 }, { 1, -1 },
+                                       { -1, 0 }, { 1, 0 },  { -1, 1 }, { 1, 1 } }; /* :72-83 */
+
+static uint64_t vo_dist(const vo_job* j, const vo_pel* cur, int curStride)
+{
+  return j->useHad ? vo_satd(j->org, j->orgStride, cur, curStride, j->w, j->h)
+                   : vo_sad(j->org, j->orgStride, cur, curStride, j->w, j->h, 0);
+}
+
+#define VO_FB_STRIDE (VO_MAX_CU + 1)
+#define VO_FB_SIZE ((VO_MAX_CU + 1 + 16) * (VO_MAX_CU + 8 + 8))
+typedef struct
+{
+  vo_pel tmp[4][VO_FB_SIZE];    /* m_filteredBlockTmp[i][COMPONENT_Y] */
+  vo_pel blk[4][4][VO_FB_SIZE]; /* m_filteredBlock[ver][hor][COMPONENT_Y] */
+} vo_fb;
+
+/* InterSearch::xExtDIFUpSamplingH — EncoderLib/InterSearch.cpp:5840-5882 */
+static void vo_upsample_h(vo_fb* fb, const vo_pel* roi, int srcStride, int w, int h, int bd, int alt)
+{
+  const int     intStride = w + 1, dstStride = w + 1, half = 4;
+  const vo_pel* srcPtr = roi - half * srcStride - 1;
+  vo_filter_hor(0, srcPtr, srcStride, fb->tmp[0], intStride, w + 1, h + 8, 0, 0, bd, alt);
+  vo_filter_hor(0, srcPtr, srcStride, fb->tmp[2], intStride, w + 1, h + 8, 8, 0, bd, alt);
+  vo_filter_ver(0, fb->tmp[0] + half * intStride + 1, intStride, fb->blk[0][0], dstStride, w, h, 0, 0, 1, bd, alt);
+  vo_filter_ver(0, fb->tmp[0] + (half - 1) * intStride + 1, intStride, fb->blk[2][0], dstStride, w, h + 1, 8, 0, 1, bd, alt);
+  vo_filter_ver(0, fb->tmp[2] + half * intStride, intStride, fb->blk[0][2], dstStride, w + 1, h, 0, 0, 1, bd, alt);
+  vo_filter_ver(0, fb->tmp[2] + (half - 1) * intStride, intStride, fb->blk[2][2], dstStride, w + 1, h + 1, 8, 0, 1, bd, alt);
+}
+
+/* InterSearch::xExtDIFUpSamplingQ — EncoderLib/InterSearch.cpp:5895-6050 */
+static void vo_upsample_q(vo_fb* fb, const vo_pel* roi, int srcStride, int w, int h, int bd, int hx, int hy)
+{
+  const int     intStride = w + 1, dstStride = w + 1, half = 4;
+  const int     extHeight = (hy == 0) ? h + 8 : h + 7;
+  const vo_pel* srcPtr;
+  vo_pel*       intPtr;
+
+  srcPtr = roi - half * srcStride - 1; /* horizontal 1/4 */
+  if (hy > 0) srcPtr += srcStride;
+  if (hx >= 0) srcPtr += 1;
+  vo_filter_hor(0, srcPtr, srcStride, fb->tmp[1], intStride, w, extHeight, 4, 0, bd, 0);
+
+  srcPtr = roi - half * srcStride - 1; /* horizontal 3/4 */
+  if (hy > 0) srcPtr += srcStride;
+  if (hx > 0) srcPtr += 1;
+  vo_filter_hor(0, srcPtr, srcStride, fb->tmp[3], intStride, w, extHeight, 12, 0, bd, 0);
+
+  intPtr = fb->tmp[1] + (half - 1) * intStride; /* @1,1 */
+  if (hy == 0) intPtr += intStride;
+  vo_filter_ver(0, intPtr, intStride, fb->blk[1][1], dstStride, w, h, 4, 0, 1, bd, 0);
+
+  intPtr = fb->tmp[1] + (half - 1) * intStride; /* @3,1 */
+  vo_filter_ver(0, intPtr, intStride, fb->blk[3][1], dstStride, w, h, 12, 0, 1, bd, 0);
+
+  if (hy != 0)
+  {
+    intPtr = fb->tmp[1] + (half - 1) * intStride; /* @2,1 */
+    vo_filter_ver(0, intPtr, intStride, fb->blk[2][1], dstStride, w, h, 8, 0, 1, bd, 0);
+    intPtr = fb->tmp[3] + (half - 1) * intStride; /* @2,3 */
+    vo_filter_ver(0, intPtr, intStride, fb->blk[2][3], dstStride, w, h, 8, 0, 1, bd, 0);
+  }
+  else
+  {
+    intPtr = fb->tmp[1] + half * intStride; /* @0,1 */
+    vo_filter_ver(0, intPtr, intStride, fb->blk[0][1], dstStride, w, h, 0, 0, 1, bd, 0);
+    intPtr = fb->tmp[3] + half * intStride; /* @0,3 */
+    vo_filter_ver(0, intPtr, intStride, fb->blk[0][3], dstStride, w, h, 0, 0, 1, bd, 0);
+  }
+
+  if (hx != 0)
+  {
+    intPtr = fb->tmp[2] + (half - 1) * intStride; /* @1,2 */
+    if (hx > 0) intPtr += 1;
+    if (hy >= 0) intPtr += intStride;
+    vo_filter_ver(0, intPtr, intStride, fb->blk[1][2], dstStride, w, h, 4, 0, 1, bd, 0);
+    intPtr = fb->tmp[2] + (half - 1) * intStride; /* @3,2 */
+    if (hx > 0) intPtr += 1;
+    if (hy > 0) intPtr += intStride;
+    vo_filter_ver(0, intPtr, intStride, fb->blk[3][2], dstStride, w, h, 12, 0, 1, bd, 0);
+  }
+  else
+  {
+    intPtr = fb->tmp[0] + (half - 1) * intStride + 1; /* @1,0 */
+    if (hy >= 0) intPtr += intStride;
+    vo_filter_ver(0, intPtr, intStride, fb->blk[1][0], dstStride, w, h, 4, 0, 1, bd, 0);
+    intPtr = fb->tmp[0] + (half - 1) * intStride + 1; /* @3,0 */
+    if (hy > 0) intPtr += intStride;
+    vo_filter_ver(0, intPtr, intStride, fb->blk[3][0], dstStride, w, h, 12, 0, 1, bd, 0);
+  }
+
+  intPtr = fb->tmp[3] + (half - 1) * intStride; /* @1,3 */
+  if (hy == 0) intPtr += intStride;
+  vo_filter_ver(0, intPtr, intStride, fb->blk[1][3], dstStride, w, h, 4, 0, 1, bd, 0);
+
+  intPtr = fb->tmp[3] + (half - 1) * intStride; /* @3,3 */
+  vo_filter_ver(0, intPtr, intStride, fb->blk[3][3], dstStride, w, h, 12, 0, 1, bd, 0);
+}
+
+/* InterSearch::xPatternRefinement — EncoderLib/InterSearch.cpp:707-761
+ * (baseX,baseY) = baseRefMv, (*fx,*fy) in: MV for the rate term, out: best offset */
+static uint64_t vo_refine_literal(const vo_job* j, vo_fb* fb, int baseX, int baseY, int iFrac, int* fx, int* fy)
+{
+  uint64_t best = UINT64_MAX;
+  int      bestDir = 0;
+  const int refStride = j->w + 1;
+  const int (*tab)[2] = (iFrac == 2) ? vo_refine_h : vo_refine_q;
+  const int costScale = (iFrac == 2) ? 1 : 0; /* set by the caller: InterSearch.cpp:4319, 4330 */
+  for (int i = 0; i < 9; i++)
+  {
+    int horVal = (tab[i][0] + baseX) * iFrac;
+    int verVal = (tab[i][1] + baseY) * iFrac;
+    const vo_pel* p = fb->blk[verVal & 3][horVal & 3];
+    if (horVal == 2 && (verVal & 1) == 0) p += 1;
+    if ((horVal & 1) == 0 && verVal == 2) p += refStride;
+    int      tx = tab[i][0] + *fx, ty = tab[i][1] + *fy;
+    uint64_t d  = vo_dist(j, p, refStride);
+    d += vo_mv_cost(j->lambdaMotion, vo_mv_bits(tx, ty, j->predQx, j->predQy, costScale, 0));
+    if (d < best)
+    {
+      best    = d;
+      bestDir = i;
+    }
+  }
+  *fx = tab[bestDir][0];
+  *fy = tab[bestDir][1];
+  return best;
+}
+
+/* Body of InterSearch::xPatternSearchFracDIF — EncoderLib/InterSearch.cpp:4296-4338, literal buffers */
+void vo_frac_literal(const vo_job* j, int mvx, int mvy, int* hx, int* hy, int* qx, int* qy, uint64_t* cost)
+{
+  const vo_pel* roi = j->refAtPU + mvx + mvy * j->refStride;
+  *hx = *hy = *qx = *qy = 0;
+  if (j->imvShift > 1) /* :4311-4317 */
+  {
+    *cost = vo_dist(j, roi, j->refStride) + vo_mv_cost(j->lambdaMotion, vo_mv_bits(mvx, mvy, j->predQx, j->predQy, 2, j->imvShift));
+    return;
+  }
+  vo_fb* fb = (vo_fb*) malloc(sizeof(vo_fb));
+  memset(fb, 0, sizeof(vo_fb));
+  vo_upsample_h(fb, roi, j->refStride, j->w, j->h, j->bitDepth, j->useAltHpel);
+  int fx = mvx << 1, fy = mvy << 1;
+  *cost = vo_refine_literal(j, fb, 0, 0, 2, &fx, &fy);
+  *hx   = fx;
+  *hy   = fy;
+  if (j->imvShift == 0)
+  {
+    vo_upsample_q(fb, roi, j->refStride, j->w, j->h, j->bitDepth, *hx, *hy);
+    fx    = ((mvx << 1) + *hx) << 1;
+    fy    = ((mvy << 1) + *hy) << 1;
+    *cost = vo_refine_literal(j, fb, *hx << 1, *hy << 1, 1, &fx, &fy);
+    *qx   = fx;
+    *qy   = fy;
+  }
+  free(fb);
+}
+
+/* Direct form: the prediction block at quarter-pel offset (dqx,dqy) ∈ [-3,3]² from the integer MV is the
+ * two-stage separable interpolation at integer base floor(d/4), phase d&3: horizontal pass
+ * (isFirst,!isLast) to 14-bit intermediates over H+7 rows, vertical pass (!isFirst,isLast).  This is what
+ * the m_filteredBlock planes of xExtDIFUpSamplingH/Q hold at the positions xPatternRefinement reads
+ * (InterSearch.cpp:728-739); tests/test_oracle.py checks literal == direct. */
+void vo_pred_qpel(const vo_job* j, int mvx, int mvy, int dqx, int dqy, int useAltHpel, vo_pel* dst, int dstStride)
+{
+  const int     ix = dqx >> 2, iy = dqy >> 2, px = dqx & 3, py = dqy & 3;
+  const vo_pel* src = j->refAtPU + (mvx + ix) + (mvy + iy) * j->refStride;
+  vo_pel        tmp[(VO_MAX_CU + 8) * VO_MAX_CU];
+  const int     w = j->w, h = j->h;
+  /* the 4x4 coefficient quirk (InterpolationFilter.cpp:786,869) keys on the (w,h) the reference passes:
+   * never hit for inter CUs (no 4x4); the direct form uses the regular table. */
+  const int16_t* ch = (px == 2 && useAltHpel) ? vo_luma_alt_hpel : vo_luma[px * 4];
+  const int16_t* cv = (py == 2 && useAltHpel) ? vo_luma_alt_hpel : vo_luma[py * 4];
+  if (px == 0)
+    vo_filter_copy(1, 0, j->bitDepth, src - 3 * j->refStride, j->refStride, tmp, w, w, h + 7);
+  else
+    vo_filter(8, 0, 1, 0, j->bitDepth, src - 3 * j->refStride, j->refStride, tmp, w, w, h + 7, ch);
+  if (py == 0)
+    vo_filter_copy(0, 1, j->bitDepth, tmp + 3 * w, w, dst, dstStride, w, h);
+  else
+    vo_filter(8, 1, 0, 1, j->bitDepth, tmp + 3 * w, w, dst, dstStride, w, h, cv);
+}
+
+void vo_frac_direct(const vo_job* j, int mvx, int mvy, int* hx, int* hy, int* qx, int* qy, uint64_t* cost)
+{
+  const vo_pel* roi = j->refAtPU + mvx + mvy * j->refStride;
+  vo_pel        pred[VO_MAX_CU * VO_MAX_CU];
+  *hx = *hy = *qx = *qy = 0;
+  if (j->imvShift > 1)
+  {
+    *cost = vo_dist(j, roi, j->refStride) + vo_mv_cost(j->lambdaMotion, vo_mv_bits(mvx, mvy, j->predQx, j->predQy, 2, j->imvShift));
+    return;
+  }
+  uint64_t best = UINT64_MAX;
+  int      dir  = 0;
+  for (int i = 0; i < 9; i++) /* half-pel, cost scale 1 */
+  {
+    vo_pred_qpel(j, mvx, mvy, vo_refine_h[i][0] * 2, vo_refine_h[i][1] * 2, j->useAltHpel, pred, j->w);
+    uint64_t d = vo_dist(j, pred, j->w);
+    d += vo_mv_cost(j->lambdaMotion,
+                    vo_mv_bits((mvx << 1) + vo_refine_h[i][0], (mvy << 1) + vo_refine_h[i][1], j->predQx, j->predQy, 1, 0));
+    if (d < best) best = d, dir = i;
+  }
+  *hx   = vo_refine_h[dir][0];
+  *hy   = vo_refine_h[dir][1];
+  *cost = best;
+  if (j->imvShift == 0)
+  {
+    best = UINT64_MAX;
+    dir  = 0;
+    for (int i = 0; i < 9; i++) /* quarter-pel, cost scale 0 */
+    {
+      int dqx = *hx * 2 + vo_refine_q[i][0], dqy = *hy * 2 + vo_refine_q[i][1];
+      vo_pred_qpel(j, mvx, mvy, dqx, dqy, 0, pred, j->w);
+      uint64_t d = vo_dist(j, pred, j->w);
+      d += vo_mv_cost(j->lambdaMotion, vo_mv_bits((mvx << 2) + dqx, (mvy << 2) + dqy, j->predQx, j->predQy, 0, 0));
+      if (d < best) best = d, dir = i;
+    }
+    *qx   = vo_refine_q[dir][0];
+    *qy   = vo_refine_q[dir][1];
+    *cost = best;
+  }
+}
+
+/* xPatternSearch followed by the xPatternSearchFracDIF body, as xMotionEstimation chains them
+ * (EncoderLib/InterSearch.cpp:3432, 3476) */
+void vo_search(const vo_job* j, vo_result* r, int literal)
+{
+  vo_pattern_search(j, &r->mvX, &r->mvY, &r->intSad);
+  r->halfX = r->halfY = r->qterX = r->qterY = 0;
+  r->fracCost = r->intSad;
+  if (!j->doFrac) return;
+  if (literal)
+    vo_frac_literal(j, r->mvX, r->mvY, &r->halfX, &r->halfY, &r->qterX, &r->qterY, &r->fracCost);
+  else
+    vo_frac_direct(j, r->mvX, r->mvY, &r->halfX, &r->halfY, &r->qterX, &r->qterY, &r->fracCost);
+}
+
+double vo_search_batch(const vo_job* jobs, vo_result* res, int n, int literal)
+{
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (int i = 0; i < n; i++) vo_search(&jobs[i], &res[i], literal);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  return (double) (t1.tv_sec - t0.tv_sec) + 1e-9 * (double) (t1.tv_nsec - t0.tv_nsec);
+}
+
+/* Tail of xMotionEstimation — EncoderLib/InterSearch.cpp:3477-3484 */
+void vo_me_finish(const vo_job* j, const vo_result* r, double fWeight, uint32_t bitsIn, int* mvQx, int* mvQy,
+                  uint32_t* bitsOut, uint64_t* costOut)
+{
+  int      mx = (r->mvX << 2) + (r->halfX << 1) + r->qterX;
+  int      my = (r->mvY << 2) + (r->halfY << 1) + r->qterY;
+  uint32_t mvBits = vo_mv_bits(mx, my, j->predQx, j->predQy, 0, j->imvShift);
+  uint32_t bits   = bitsIn + mvBits;
+  *mvQx    = mx;
+  *mvQy    = my;
+  *bitsOut = bits;
+  *costOut = (uint64_t) (floor(fWeight * ((double) r->fracCost - (double) vo_mv_cost(j->lambdaMotion, mvBits))) +
+                         (double) vo_mv_cost(j->lambdaMotion, bits));
+}

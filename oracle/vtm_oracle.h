@@ -1,0 +1,91 @@
+/* TEST INFRASTRUCTURE — CPU oracle, not part of the product.
+ *
+ * Plain-C restatement of the arithmetic of VTM 9.3's inter motion-search hot path.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may use it;
+ * the product (libvtmme.so) never links or calls anything in oracle/.
+ *
+ * Parity status: PINNED.  The reference has no tests or golden vectors of its own, so the
+ * oracle is pinned against outputs of the UNMODIFIED reference compiled here (oracle/_ref/libvtmref.so,
+ * built by oracle/Makefile.ref from /root/reference) in tests/test_oracle_vs_ref.py, and against
+ * committed fixtures generated from it (tests/golden/, generator tests/golden/make_golden.py).
+ */
+#ifndef VTM_ORACLE_H
+#define VTM_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int16_t vo_pel; /* Pel, TypeDef.h:259 */
+
+/* Same field layout as RefSearchJob / RefSearchResult in oracle/ref_harness.cpp. */
+typedef struct
+{
+  const vo_pel* org;
+  int           orgStride;
+  int           w, h;
+  const vo_pel* refAtPU; /* cStruct.piRefY: reference plane at the PU position */
+  int           refStride;
+  int           srLeft, srRight, srTop, srBottom;
+  int           predQx, predQy; /* quarter-pel AMVP predictor */
+  int           imvShift;
+  int           subShiftMode;
+  int           bitDepth;
+  int           useHad;
+  int           useAltHpel;
+  int           doFrac;
+  double        lambdaMotion;
+} vo_job;
+
+typedef struct
+{
+  int      mvX, mvY;
+  uint64_t intSad;
+  int      halfX, halfY;
+  int      qterX, qterY;
+  uint64_t fracCost;
+} vo_result;
+
+/* distortion */
+int      vo_subshift(int subShiftMode, int w, int h);
+uint64_t vo_sad(const vo_pel* org, int orgStride, const vo_pel* cur, int curStride, int w, int h, int subShift);
+uint64_t vo_satd(const vo_pel* org, int orgStride, const vo_pel* cur, int curStride, int w, int h);
+
+/* motion-vector rate */
+uint32_t vo_eg_bits(int v);
+uint32_t vo_mv_bits(int x, int y, int predX, int predY, int costScale, int imvShift);
+uint64_t vo_mv_cost(double lambdaMotion, uint32_t bits);
+
+/* interpolation (comp: 0 luma, 1/2 chroma of 4:2:0); frac in 1/16 (luma) or 1/32 (chroma) units */
+void vo_filter_hor(int comp, const vo_pel* src, int srcStride, vo_pel* dst, int dstStride, int w, int h, int frac,
+                   int isLast, int bd, int useAltHpel);
+void vo_filter_ver(int comp, const vo_pel* src, int srcStride, vo_pel* dst, int dstStride, int w, int h, int frac,
+                   int isFirst, int isLast, int bd, int useAltHpel);
+
+/* search window (xSetSearchRange) — pred in 1/16-pel internal units */
+void vo_clip_mv(int* mvx, int* mvy, int posX, int posY, int picW, int picH, int maxCuW, int maxCuH);
+void vo_set_search_range(int predX16, int predY16, int posX, int posY, int picW, int picH, int maxCuW, int maxCuH,
+                         int searchRange, int* left, int* right, int* top, int* bottom);
+
+/* integer full search (xPatternSearch) */
+void vo_pattern_search(const vo_job* j, int* mvx, int* mvy, uint64_t* sad);
+
+/* fractional refinement (xPatternSearchFracDIF): literal buffers and direct form */
+void vo_frac_literal(const vo_job* j, int mvx, int mvy, int* hx, int* hy, int* qx, int* qy, uint64_t* cost);
+void vo_frac_direct(const vo_job* j, int mvx, int mvy, int* hx, int* hy, int* qx, int* qy, uint64_t* cost);
+/* one prediction block at quarter-pel offset (dqx,dqy) from integer MV (mvx,mvy), direct form */
+void vo_pred_qpel(const vo_job* j, int mvx, int mvy, int dqx, int dqy, int useAltHpel, vo_pel* dst, int dstStride);
+
+/* xPatternSearch + xPatternSearchFracDIF body; literal!=0 picks the literal fractional path */
+void vo_search(const vo_job* j, vo_result* r, int literal);
+double vo_search_batch(const vo_job* jobs, vo_result* res, int n, int literal);
+
+/* tail of xMotionEstimation (InterSearch.cpp:3477-3484): final MV (quarter-pel), bits and cost */
+void vo_me_finish(const vo_job* j, const vo_result* r, double fWeight, uint32_t bitsIn, int* mvQx, int* mvQy,
+                  uint32_t* bitsOut, uint64_t* costOut);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,196 @@
+"""Pins the C oracle (oracle/vtm_oracle.c) against the UNMODIFIED reference compiled here
+(oracle/_ref/libvtmref.so = VTM 9.3 built by oracle/Makefile.ref).  CPU only."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import bindings as B
+
+SIZES = [4, 8, 16, 32, 64, 128]
+SHAPES = [(w, h) for w in SIZES for h in SIZES]
+
+
+def blocks(rng, w, h, bd=10, kind="uniform", signed_org=False):
+    hi = 1 << bd
+    cur = rng.integers(0, hi, (h + 3, w + 5), dtype=np.int16)
+    if kind == "uniform":
+        org = rng.integers(0, hi, (h, w + 2), dtype=np.int16)
+    else:
+        org = np.clip(cur[:h, :w + 2].astype(np.int32) + np.rint(rng.normal(0, 16, (h, w + 2))).astype(np.int32), 0, hi - 1).astype(np.int16)
+    if signed_org:   # bi-pred "2*org - otherPred" range (SURVEY hard part 5)
+        org = (2 * org.astype(np.int32) - rng.integers(0, hi, org.shape)).astype(np.int16)
+    return np.ascontiguousarray(org), np.ascontiguousarray(cur)
+
+
+@pytest.mark.ref
+def test_ref_uses_simd(ref_lib):
+    assert ref_lib.ref_simd_level() >= 1   # SSE4.1 or better: the SIMD tables are the ones pinned here
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_subshift(oracle_lib, ref_lib, mode):
+    for w, h in SHAPES:
+        assert oracle_lib.vo_subshift(mode, w, h) == ref_lib.ref_subshift(mode, w, h)
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("kind,signed_org", [("uniform", False), ("residual", False), ("uniform", True)])
+def test_sad_satd_all_shapes(oracle_lib, ref_lib, kind, signed_org):
+    rng = np.random.default_rng(7)
+    for w, h in SHAPES:
+        for rep in range(4):
+            org, cur = blocks(rng, w, h, 10, kind, signed_org)
+            os_, cs = org.shape[1], cur.shape[1]
+            for mode in (0, 2):
+                ss = oracle_lib.vo_subshift(mode, w, h)
+                a = oracle_lib.vo_sad(B.ptr(org), os_, B.ptr(cur, 1), cs, w, h, ss)
+                b = ref_lib.ref_dist(B.ptr(org), os_, B.ptr(cur, 1), cs, w, h, 10, mode, 0)
+                assert a == b, (w, h, mode)
+            a = oracle_lib.vo_satd(B.ptr(org), os_, B.ptr(cur, 1), cs, w, h)
+            b = ref_lib.ref_dist(B.ptr(org), os_, B.ptr(cur, 1), cs, w, h, 10, 0, 1)
+            assert a == b, (w, h, "satd")
+
+
+@pytest.mark.ref
+def test_sad_satd_8bit(oracle_lib, ref_lib):
+    rng = np.random.default_rng(8)
+    for w, h in SHAPES:
+        org, cur = blocks(rng, w, h, 8)
+        os_, cs = org.shape[1], cur.shape[1]
+        assert oracle_lib.vo_sad(B.ptr(org), os_, B.ptr(cur), cs, w, h, 0) == ref_lib.ref_dist(B.ptr(org), os_, B.ptr(cur), cs, w, h, 8, 0, 0)
+        assert oracle_lib.vo_satd(B.ptr(org), os_, B.ptr(cur), cs, w, h) == ref_lib.ref_dist(B.ptr(org), os_, B.ptr(cur), cs, w, h, 8, 0, 1)
+
+
+@pytest.mark.ref
+def test_mv_bits_and_cost(oracle_lib, ref_lib):
+    rng = np.random.default_rng(9)
+    for _ in range(20000):
+        x, y = (int(v) for v in rng.integers(-600, 600, 2))
+        px, py = (int(v) for v in rng.integers(-2400, 2400, 2))
+        scale = int(rng.integers(0, 3))
+        imv = int(rng.choice([0, 1, 2, 4]))
+        assert oracle_lib.vo_mv_bits(x, y, px, py, scale, imv) == ref_lib.ref_mv_bits(x, y, px, py, scale, imv)
+    for lam in (31.33, 4.7, 57.908, 123.456789):
+        for bits in range(0, 140):
+            assert oracle_lib.vo_mv_cost(lam, bits) == ref_lib.ref_mv_cost(lam, bits)
+
+
+def _filt_case(oracle_lib, ref_lib, rng, comp, w, h, frac, bd, first, last, alt, vertical):
+    taps = 8 if comp == 0 else 4
+    hi = 1 << bd
+    sh, sw = h + taps + 2, w + taps + 2
+    if first:
+        src = rng.integers(0, hi, (sh, sw), dtype=np.int16)
+    else:   # 14-bit intermediates as a first stage would produce
+        src = rng.integers(-8192, 8192, (sh, sw), dtype=np.int16)
+    off = (taps // 2) * sw + taps // 2
+    d0 = np.zeros((h, w), np.int16)
+    d1 = np.zeros((h, w), np.int16)
+    if vertical:
+        oracle_lib.vo_filter_ver(comp, B.ptr(src, off), sw, B.ptr(d0), w, w, h, frac, first, last, bd, alt)
+        ref_lib.ref_filter_ver(comp, B.ptr(src, off), sw, B.ptr(d1), w, w, h, frac, first, last, bd, alt)
+    else:
+        oracle_lib.vo_filter_hor(comp, B.ptr(src, off), sw, B.ptr(d0), w, w, h, frac, last, bd, alt)
+        ref_lib.ref_filter_hor(comp, B.ptr(src, off), sw, B.ptr(d1), w, w, h, frac, last, bd, alt)
+    assert np.array_equal(d0, d1), (comp, w, h, frac, bd, first, last, alt, vertical)
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("bd", [8, 10])
+def test_interpolation_luma(oracle_lib, ref_lib, bd):
+    rng = np.random.default_rng(10)
+    for (w, h) in [(4, 4), (4, 11), (4, 8), (8, 4), (5, 12), (9, 16), (17, 24), (16, 16), (33, 40), (64, 64), (128, 128), (129, 136)]:
+        for frac in range(16):
+            for alt in (0, 1):
+                if alt and frac != 8:
+                    continue
+                _filt_case(oracle_lib, ref_lib, rng, 0, w, h, frac, bd, 1, 0, alt, False)
+                _filt_case(oracle_lib, ref_lib, rng, 0, w, h, frac, bd, 1, 1, alt, False)
+                _filt_case(oracle_lib, ref_lib, rng, 0, w, h, frac, bd, 1, 0, alt, True)
+                _filt_case(oracle_lib, ref_lib, rng, 0, w, h, frac, bd, 1, 1, alt, True)
+                _filt_case(oracle_lib, ref_lib, rng, 0, w, h, frac, bd, 0, 1, alt, True)
+                _filt_case(oracle_lib, ref_lib, rng, 0, w, h, frac, bd, 0, 0, alt, True)
+
+
+@pytest.mark.ref
+def test_interpolation_chroma(oracle_lib, ref_lib):
+    rng = np.random.default_rng(11)
+    for (w, h) in [(2, 2), (4, 4), (2, 8), (8, 2), (16, 16), (64, 64), (3, 7)]:
+        for frac in range(32):
+            _filt_case(oracle_lib, ref_lib, rng, 1, w, h, frac, 10, 1, 0, 0, False)
+            _filt_case(oracle_lib, ref_lib, rng, 1, w, h, frac, 10, 1, 1, 0, False)
+            _filt_case(oracle_lib, ref_lib, rng, 2, w, h, frac, 10, 1, 1, 0, True)
+            _filt_case(oracle_lib, ref_lib, rng, 2, w, h, frac, 10, 0, 1, 0, True)
+
+
+def planted(rng, w, h, sr, smooth=True):
+    """Reference plane with margin and an original block = displaced + noisy copy of it."""
+    m = sr + 16
+    H, W = h + 2 * m, w + 2 * m
+    ref = rng.integers(0, 1024, (H + 2, W + 2)).astype(np.float64)
+    if smooth:
+        ref = (ref[:-2, :-2] + ref[:-2, 1:-1] + ref[:-2, 2:] + ref[1:-1, :-2] + ref[1:-1, 1:-1] + ref[1:-1, 2:] + ref[2:, :-2] + ref[2:, 1:-1] + ref[2:, 2:]) / 9
+    else:
+        ref = ref[:H, :W]
+    ref = np.ascontiguousarray(np.clip(np.rint(ref), 0, 1023).astype(np.int16))
+    dx, dy = (int(v) for v in rng.integers(-sr + 2, sr - 1, 2))
+    org = ref[m + dy:m + dy + h, m + dx:m + dx + w].astype(np.int32)
+    org = np.clip(org + np.rint(rng.normal(0, 6, org.shape)).astype(np.int32), 0, 1023).astype(np.int16)
+    return ref, np.ascontiguousarray(org), m * W + m, W, (dx, dy)
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("w,h", [(8, 8), (16, 16), (8, 4), (4, 8), (16, 8), (8, 16), (32, 8), (8, 32), (32, 32), (64, 16), (16, 64), (64, 64), (128, 64), (128, 128)])
+def test_search_matches_reference(oracle_lib, ref_lib, w, h):
+    rng = np.random.default_rng(100 * w + h)
+    nrep = 3 if w * h <= 1024 else 1
+    for rep in range(nrep):
+        sr = 24 if w * h > 4096 else 40
+        ref, org, off, stride, _ = planted(rng, w, h, sr)
+        for imv, alt, ssm in [(0, 0, 0), (0, 0, 2), (1, 1, 0), (2, 0, 2)]:
+            pred = (int(rng.integers(-40, 40)), int(rng.integers(-40, 40)))
+            win = (-sr + int(rng.integers(0, 5)), sr - int(rng.integers(0, 5)), -sr + int(rng.integers(0, 5)), sr - int(rng.integers(0, 5)))
+            do_frac = 0 if imv > 1 else 1
+            j = B.make_job(org, ref, stride, off, w, h, win, pred, imv, ssm, 10, 1, alt, do_frac, 31.33 + rep)
+            r0, r1, r2 = B.Result(), B.Result(), B.Result()
+            ref_lib.ref_search(C.byref(j), C.byref(r0))
+            oracle_lib.vo_search(C.byref(j), C.byref(r1), 1)
+            oracle_lib.vo_search(C.byref(j), C.byref(r2), 0)
+            assert r0.tuple() == r1.tuple(), ("literal", w, h, imv, ssm)
+            assert r0.tuple() == r2.tuple(), ("direct", w, h, imv, ssm)
+
+
+def planted_frac(oracle_lib, rng, w, h, sr):
+    """Like planted(), but the original block sits at a random quarter-pel phase of the reference."""
+    ref, org, off, stride, (dx, dy) = planted(rng, w, h, sr)
+    dq = (int(rng.integers(-3, 4)), int(rng.integers(-3, 4)))
+    j = B.make_job(org, ref, stride, off, w, h, (0, 0, 0, 0), (0, 0))
+    pred = np.zeros((h, w), np.int16)
+    oracle_lib.vo_pred_qpel(C.byref(j), dx, dy, dq[0], dq[1], 0, B.ptr(pred), w)
+    org = np.clip(pred.astype(np.int32) + np.rint(rng.normal(0, 3, pred.shape)).astype(np.int32), 0, 1023).astype(np.int16)
+    return ref, np.ascontiguousarray(org), off, stride, (dx, dy), dq
+
+
+@pytest.mark.ref
+def test_fractional_branches_match_reference(oracle_lib, ref_lib):
+    """Sub-pel planted motion so that every (half, quarter) branch of xExtDIFUpSamplingQ is exercised."""
+    rng = np.random.default_rng(4242)
+    seen = set()
+    for rep in range(240):
+        w, h = [(8, 8), (16, 16), (8, 16), (16, 8), (4, 8), (8, 4), (32, 16), (16, 32)][rep % 8]
+        sr = 12
+        ref, org, off, stride, _, _ = planted_frac(oracle_lib, rng, w, h, sr)
+        imv, alt = ((0, 0), (0, 0), (0, 0), (1, 1))[rep % 4]
+        pred = (int(rng.integers(-40, 40)), int(rng.integers(-40, 40)))
+        j = B.make_job(org, ref, stride, off, w, h, (-sr, sr, -sr, sr), pred, imv, 0, 10, 1, alt, 1, 12.5)
+        r0, r1, r2 = B.Result(), B.Result(), B.Result()
+        ref_lib.ref_search(C.byref(j), C.byref(r0))
+        oracle_lib.vo_search(C.byref(j), C.byref(r1), 1)
+        oracle_lib.vo_search(C.byref(j), C.byref(r2), 0)
+        assert r0.tuple() == r1.tuple()
+        assert r0.tuple() == r2.tuple()
+        seen.add((r0.halfX, r0.halfY, r0.qterX, r0.qterY))
+    assert len({s[:2] for s in seen}) >= 8      # (nearly) all nine half-pel outcomes
+    assert len(seen) >= 30                      # and a good share of the 81 (half, quarter) combinations
