@@ -1,0 +1,172 @@
+/* libvtmme — B200-native (sm_100a CUDA) motion search for VTM 9.3, C ABI.
+ *
+ * This is the drop-in boundary for ONE path of the reference encoder: the inter-prediction motion
+ * search (integer full search + half/quarter-pel refinement) and the distortion / interpolation
+ * kernels it bottoms out in.  Plain C, POD arguments, no exceptions; every entry point returns
+ * VTMME_OK (0) or a negative error code and never falls back to a CPU implementation — when the CUDA
+ * path cannot run, the call fails and the caller (VTM: THROW) must stop.
+ *
+ * Paths below are relative to the reference's source/Lib directory.
+ *
+ *   reference interface replaced                                   entry point here
+ *   ------------------------------------------------------------  ---------------------------------
+ *   RdCost::m_afpDistortFunc[DF_SAD*]  (RdCost.h:113,               vtmme_sad_batch / vtmme_dist_host
+ *     RdCost.cpp:125-208; x86/RdCostX86.h:2307-2321)
+ *   RdCost::m_afpDistortFunc[DF_HAD*]  (x86/RdCostX86.h:2323-2330)  vtmme_satd_batch / vtmme_dist_host
+ *   InterpolationFilter::m_filterHor/m_filterVer/m_filterCopy       vtmme_interp_batch / vtmme_interp_host
+ *     (InterpolationFilter.h:96-98, InterpolationFilter.cpp:749-895)
+ *   InterSearch::xPatternSearch + xPatternSearchFracDIF             vtmme_search          (per-call jobs)
+ *     (EncoderLib/InterSearch.cpp:3566-3608, 4284-4339)             vtmme_search_frames   (batched, per CTU tree)
+ *   Picture::getRecoBuf / getOrigBuf planes handed to ME            vtmme_upload_picture / vtmme_release_picture
+ *     (Picture.cpp:322-329, extendPicBorder :1050-1110)
+ *
+ * Threading: one context per encoder thread; calls on one context are serialised by the caller
+ * (VTM is single-threaded).  All host-pointer entry points are synchronous on return.
+ */
+#ifndef VTMME_H
+#define VTMME_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VTMME_OK 0
+#define VTMME_ERR_CUDA (-1)    /* a CUDA runtime call or kernel failed; see vtmme_last_error */
+#define VTMME_ERR_ARG (-2)     /* invalid argument */
+#define VTMME_ERR_NOMEM (-3)   /* device allocation failed */
+#define VTMME_ERR_NOPIC (-4)   /* unknown picture id */
+#define VTMME_ERR_RANGE (-5)   /* a window / predictor spread exceeds what the context was sized for */
+
+typedef struct vtmme_ctx vtmme_ctx;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int         vtmme_create(int device, vtmme_ctx** ctx);
+void        vtmme_destroy(vtmme_ctx* ctx);
+const char* vtmme_last_error(const vtmme_ctx* ctx);
+/* Run on the caller's CUDA stream (a cudaStream_t, e.g. torch's current stream); NULL = library stream. */
+int         vtmme_set_stream(vtmme_ctx* ctx, void* cudaStream);
+int         vtmme_synchronize(vtmme_ctx* ctx);
+/* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
+uint64_t    vtmme_launch_count(const vtmme_ctx* ctx);
+
+/* ---- pictures -------------------------------------------------------------------------------
+ * A picture is one int16 luma plane (Pel, TypeDef.h:259).  `origin` points at sample (0,0).
+ * withBorder != 0: the caller's plane already carries `margin` valid samples on every side (what
+ *   Picture::extendPicBorder produced, Picture.cpp:1050-1110) and they are copied as they are.
+ * withBorder == 0: only the width x height area is read and the library replicates the border on
+ *   the device (same rule as extendPicBorder: edge samples repeated).
+ * The device copy always has a margin of at least VTMME_MIN_MARGIN samples.                     */
+#define VTMME_MIN_MARGIN 192
+int vtmme_upload_picture(vtmme_ctx* ctx, int picId, const int16_t* origin, int stride, int width, int height,
+                         int margin, int withBorder);
+/* Same, source plane already in device memory (copied device-to-device on the context stream). */
+int vtmme_upload_picture_device(vtmme_ctx* ctx, int picId, const int16_t* dOrigin, int stride, int width, int height,
+                                int margin, int withBorder);
+int vtmme_release_picture(vtmme_ctx* ctx, int picId);
+
+/* ---- per-call motion search ------------------------------------------------------------------
+ * One job = one InterSearch::xMotionEstimation call's integer search + fractional refinement:
+ * xPatternSearch over searchRange (InterSearch.cpp:3566-3608), then the body of
+ * xPatternSearchFracDIF (:4296-4338).  Field meaning follows IntTZSearchStruct / DistParam.      */
+typedef struct
+{
+  int32_t        curPic;       /* picture holding the original block; ignored when org != NULL        */
+  int32_t        refPic;       /* reference picture (recon plane with border)                          */
+  int32_t        x, y, w, h;   /* PU luma rectangle; w,h in {4,8,16,32,64,128}                         */
+  const int16_t* org;          /* optional HOST pointer to the pattern (bi-pred: 2*org - otherPred,    */
+  int32_t        orgStride;    /*   InterSearch.cpp:3317-3328); NULL = read curPic at (x,y)            */
+  int32_t        srLeft, srRight, srTop, srBottom; /* cStruct.searchRange (integer pel, inclusive)     */
+  int32_t        predQx, predQy;                   /* RdCost::setPredictor value, quarter-pel          */
+  int32_t        imvShift;     /* 0 qpel, 1 hpel, 2 fpel, 4 4pel (InterSearch.cpp:3344)                */
+  int32_t        subShift;     /* DistParam::subShift of the integer search (RdCost.cpp:289-323)       */
+  int32_t        bitDepth;     /* <= 10 (larger falls outside the SIMD tables too: RdCostX86.h:213)    */
+  int32_t        useHad;       /* HadamardME && !DisableSATDForRD                                      */
+  int32_t        useAltHpel;   /* cStruct.useAltHpelIf                                                 */
+  int32_t        fracMode;     /* 0: integer only; 1: xPatternSearchFracDIF body                       */
+  double         lambdaMotion; /* RdCost::m_motionLambda                                               */
+} vtmme_job;
+
+typedef struct
+{
+  int32_t  mvX, mvY;      /* best integer MV (xPatternSearch rcMv)                                     */
+  uint64_t intSad;        /* ruiSAD: best cost minus its MV cost (InterSearch.cpp:3606)                */
+  int32_t  halfX, halfY;  /* rcMvHalf                                                                  */
+  int32_t  qterX, qterY;  /* rcMvQter                                                                  */
+  uint64_t fracCost;      /* ruiCost after xPatternSearchFracDIF                                       */
+} vtmme_result;
+
+int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_result* results);
+
+/* ---- batched per-CTU search (standalone ME, BASELINE config 4) ---------------------------------
+ * For every picture pair, every grid-aligned square CU of size 8,16,32,64,128 fully inside the
+ * picture is searched: window = xSetSearchRange(pred, searchRange) (InterSearch.cpp:3496-3535),
+ * integer full search, then half + quarter-pel refinement with SATD.  SADs of nested CUs are
+ * computed once per 8x8 block and displacement and summed up the quad-tree.
+ *
+ * CU order in pred / result arrays: level-major, level l = CUs of size 8<<l (l = 0..4), each level in
+ * raster order over floor(width/size) x floor(height/size) CUs.                                   */
+typedef struct
+{
+  int32_t searchRange;   /* SearchRange (integer pel)                                               */
+  int32_t bitDepth;      /* internal bit depth (10)                                                 */
+  int32_t ctuSize;       /* sps.getMaxCUWidth() used by the MV clip (128)                           */
+  int32_t imvShift;      /* 0                                                                       */
+  int32_t useHad;        /* 1: SATD in the fractional stage                                         */
+  int32_t fracMode;      /* 0 integer only, 1 half + quarter                                        */
+  int32_t predSpread;    /* max |pred_a - pred_b| (integer pel, per component) among CUs of one CTU  */
+  int32_t reserved;
+  double  lambdaMotion;
+} vtmme_frame_params;
+
+typedef struct
+{
+  int16_t  mvQx, mvQy;   /* final MV, quarter-pel: (int<<2) + (half<<1) + qter (InterSearch.cpp:3478-3480) */
+  int16_t  intX, intY;   /* best integer MV                                                         */
+  uint32_t intSad;       /* ruiSAD of xPatternSearch                                                */
+  uint32_t fracCost;     /* ruiCost after the fractional stage (= intSad + mv cost when fracMode 0)  */
+} vtmme_cu_result;
+
+/* Number of CUs per picture and the offset of each of the 5 levels in the CU order. */
+int vtmme_frame_cu_count(int width, int height, int32_t levelOffset[6]);
+
+/* Host buffers: predQ = nPairs * nCU * 2 int16 (quarter-pel x,y) or NULL for zero predictors;
+ * results = nPairs * nCU entries.  Synchronous. */
+int vtmme_search_frames(vtmme_ctx* ctx, int nPairs, const int32_t* curPics, const int32_t* refPics,
+                        const vtmme_frame_params* params, const int16_t* predQ, vtmme_cu_result* results);
+/* Device buffers, asynchronous on the context stream (vtmme_synchronize to wait). */
+int vtmme_search_frames_device(vtmme_ctx* ctx, int nPairs, const int32_t* curPics, const int32_t* refPics,
+                               const vtmme_frame_params* params, const int16_t* dPredQ, vtmme_cu_result* dResults);
+
+/* ---- table-level kernels (dispatch-table flavour; BASELINE config 5) ----------------------------
+ * n independent block pairs.  Block i: org at org + i*orgBlockStride (row stride orgStride), cur
+ * likewise; all blocks w x h.  kind 0: SAD with row sub-sampling subShift (RdCost.cpp:493-528);
+ * kind 1: SATD with the reference tiling (RdCost.cpp:2819-2934).  Pointers are DEVICE pointers;
+ * out = n uint64 (Distortion, TypeDef.h:270). */
+int vtmme_dist_batch(vtmme_ctx* ctx, int kind, const int16_t* dOrg, int orgStride, int64_t orgBlockStride,
+                     const int16_t* dCur, int curStride, int64_t curBlockStride, int w, int h, int subShift, int n,
+                     uint64_t* dOut);
+/* One block pair in HOST memory, synchronous: the signature a DistParam hook needs (RdCost.h:60-105). */
+int vtmme_dist_host(vtmme_ctx* ctx, int kind, const int16_t* org, int orgStride, const int16_t* cur, int curStride,
+                    int w, int h, int subShift, uint64_t* out);
+
+/* Separable interpolation of n blocks (DEVICE pointers), semantics of InterpolationFilter::filterHor /
+ * filterVer (InterpolationFilter.cpp:749-895): comp 0 luma 8-tap (frac in 1/16), comp 1 chroma 4-tap of
+ * 4:2:0 (frac in 1/32); vertical 0/1; isFirst/isLast as in the reference; src points at the first
+ * output sample position (the callee steps back (N/2-1) taps itself, InterpolationFilter.cpp:574-575). */
+int vtmme_interp_batch(vtmme_ctx* ctx, int comp, int vertical, const int16_t* dSrc, int srcStride,
+                       int64_t srcBlockStride, int16_t* dDst, int dstStride, int64_t dstBlockStride, int w, int h,
+                       int frac, int isFirst, int isLast, int bitDepth, int useAltHpel, int n);
+int vtmme_interp_host(vtmme_ctx* ctx, int comp, int vertical, const int16_t* src, int srcStride, int16_t* dst,
+                      int dstStride, int w, int h, int frac, int isFirst, int isLast, int bitDepth, int useAltHpel);
+
+/* ---- measurement helper -------------------------------------------------------------------------
+ * Issue-rate microbenchmark of one instruction class on the current device (roofline denominator of
+ * the integer search).  variant: see vtm_b200/peaks.py. */
+int vtmme_int_peak(int variant, int iters, double* laneInstrPerClkPerSm, double* ms, double* smClockMHz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,52 @@
+"""Shared test helpers: the CPU side of the parity checks (oracle-driven)."""
+import ctypes as C
+
+import numpy as np
+
+from oracle import bindings as B
+
+MARGIN = 192
+
+
+def pad_plane(plane, margin=MARGIN):
+    """Replicated border, what Picture::extendPicBorder produces."""
+    return np.ascontiguousarray(np.pad(plane, margin, mode="edge"))
+
+
+def oracle_window(L, pred_q, x, y, pic_w, pic_h, sr, ctu=128):
+    l, r, t, b = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    L.vo_set_search_range(int(pred_q[0]) * 4, int(pred_q[1]) * 4, x, y, pic_w, pic_h, ctu, ctu, sr,
+                          C.byref(l), C.byref(r), C.byref(t), C.byref(b))
+    return l.value, r.value, t.value, b.value
+
+
+def oracle_frame_search(L, cur, ref_padded, margin, sr, lam, pred_q=None, frac=1, use_had=1, levels=range(5),
+                        only=None, literal=0):
+    """Every grid-aligned square CU (level-major, raster) through vo_search.  Returns list of result tuples
+    (mvQx, mvQy, intX, intY, intSad, fracCost) indexed like the frame API; `only` = subset of CU indices."""
+    h, w = cur.shape
+    stride = ref_padded.shape[1]
+    out = {}
+    idx = 0
+    for l in range(5):
+        s = 8 << l
+        for cy in range(h // s):
+            for cx in range(w // s):
+                if l in levels and (only is None or idx in only):
+                    x, y = cx * s, cy * s
+                    pq = (0, 0) if pred_q is None else (int(pred_q[idx][0]), int(pred_q[idx][1]))
+                    win = oracle_window(L, pq, x, y, w, h, sr)
+                    j = B.make_job(cur, ref_padded, stride, (margin + y) * stride + margin + x, s, s, win, pq, 0, 0,
+                                   10, use_had, 0, frac, lam, org_off=y * w + x, org_stride=w)
+                    r = B.Result()
+                    L.vo_search(C.byref(j), C.byref(r), literal)
+                    out[idx] = (4 * r.mvX + 2 * r.halfX + r.qterX, 4 * r.mvY + 2 * r.halfY + r.qterY, r.mvX, r.mvY,
+                                int(r.intSad), int(r.fracCost) if frac else int(r.intSad) + int(
+                                    L.vo_mv_cost(lam, L.vo_mv_bits(r.mvX, r.mvY, pq[0], pq[1], 2, 0))))
+                idx += 1
+    return out
+
+
+def gpu_tuple(rec):
+    return (int(rec["mvQx"]), int(rec["mvQy"]), int(rec["intX"]), int(rec["intY"]), int(rec["intSad"]),
+            int(rec["fracCost"]))

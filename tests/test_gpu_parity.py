@@ -1,0 +1,208 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (vtm_b200 -> libvtmme.so), against the CPU oracle
+on the same seeded inputs.  Bit-exact: integer MVs, SADs, fractional MVs and costs must all be identical."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import bindings as B  # noqa: E402
+from tests.helpers import MARGIN, gpu_tuple, oracle_frame_search, oracle_window, pad_plane  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ms():
+    import vtm_b200
+    m = vtm_b200.MotionSearch(0)
+    yield m
+    m.close()
+
+
+def _frame_case(ms, oracle_lib, w, h, sr, seed, spread, lam=31.33, frac=1, use_had=1):
+    from vtm_b200 import FrameParams
+    from vtm_b200.synth import make_pair, random_predictors
+    cur, ref, _ = make_pair(seed, w, h, max_global=min(sr - 2, 12), max_local=min(sr - 2, 14), n_rects=3, sigma=4.0)
+    refp = pad_plane(ref)
+    ms.upload_picture(1, cur)
+    ms.upload_picture(2, refp, MARGIN)
+    ncu = ms.set_frame_size(w, h)
+    pred = random_predictors(seed, ncu, spread) if spread else None
+    prm = FrameParams(searchRange=sr, predSpread=2 * spread + 1 if spread else 0, lambdaMotion=lam, fracMode=frac,
+                      useHad=use_had)
+    got = ms.search_frames([1], [2], prm, None if pred is None else pred[None])
+    want = oracle_frame_search(oracle_lib, cur, refp, MARGIN, sr, lam, pred, frac, use_had)
+    bad = [(i, gpu_tuple(got[0][i]), want[i]) for i in range(ncu) if gpu_tuple(got[0][i]) != want[i]]
+    assert not bad, "%d of %d CUs differ, first: %s" % (len(bad), ncu, bad[:3])
+
+
+def test_frame_search_zero_pred_small(ms, oracle_lib):
+    _frame_case(ms, oracle_lib, 256, 128, 16, 1, 0)
+
+
+def test_frame_search_partial_regions(ms, oracle_lib):
+    # 200x152: neither a multiple of 32 nor of 128 -> partial regions / CTUs, border-clipped windows
+    _frame_case(ms, oracle_lib, 200, 152, 24, 2, 0, lam=12.0)
+
+
+def test_frame_search_random_predictors(ms, oracle_lib):
+    _frame_case(ms, oracle_lib, 256, 192, 16, 3, 8)
+
+
+def test_frame_search_integer_only_and_sad_frac(ms, oracle_lib):
+    _frame_case(ms, oracle_lib, 128, 128, 12, 4, 0, frac=0)
+    _frame_case(ms, oracle_lib, 128, 128, 12, 5, 4, use_had=0)
+
+
+def test_frame_search_sr64(ms, oracle_lib):
+    # the BASELINE search range on a picture the oracle finishes in seconds
+    _frame_case(ms, oracle_lib, 256, 256, 64, 6, 0)
+
+
+SIZES = [4, 8, 16, 32, 64, 128]
+
+
+def test_job_search_all_shapes(ms, oracle_lib):
+    """vtmme_search vs oracle: every (w,h) except 4x4, row sub-sampling, IMV shifts, signed (bi-pred) patterns."""
+    from vtm_b200 import Job
+    rng = np.random.default_rng(77)
+    W, H = 320, 256
+    ref = np.clip(np.rint(rng.normal(512, 180, (H, W))), 0, 1023).astype(np.int16)
+    # low-pass so that sub-pel positions matter
+    ref = ((ref[:-1, :-1].astype(np.int32) + ref[1:, :-1] + ref[:-1, 1:] + ref[1:, 1:]) // 4).astype(np.int16)
+    H, W = ref.shape
+    cur = np.clip(np.roll(ref, (3, -5), (0, 1)).astype(np.int32) + np.rint(rng.normal(0, 5, ref.shape)).astype(np.int32), 0, 1023).astype(np.int16)
+    cur = np.ascontiguousarray(cur)
+    refp = pad_plane(ref)
+    ms.upload_picture(10, cur)
+    ms.upload_picture(11, refp, MARGIN)
+    stride = refp.shape[1]
+    jobs, want = [], []
+    keep = []
+    for w in SIZES:
+        for h in SIZES:
+            if w == 4 and h == 4:
+                continue
+            for variant in range(3):
+                x = int(rng.integers(0, (W - w) // 4 + 1)) * 4
+                y = int(rng.integers(0, (H - h) // 4 + 1)) * 4
+                sr = int(rng.integers(4, 20))
+                pq = (int(rng.integers(-40, 41)), int(rng.integers(-40, 41)))
+                win = oracle_window(oracle_lib, pq, x, y, W, H, sr)
+                imv, alt = [(0, 0), (1, 1), (0, 0)][variant]
+                ssm = 2 if variant == 2 else 0
+                ss = oracle_lib.vo_subshift(ssm, w, h)
+                lam = float(rng.uniform(4, 60))
+                org = None
+                if variant == 1:   # bi-pred style pattern: 2*org - otherPred, outside [0,1023]
+                    org = (2 * cur[y:y + h, x:x + w].astype(np.int32) - rng.integers(0, 1024, (h, w))).astype(np.int16)
+                    org = np.ascontiguousarray(org)
+                    keep.append(org)
+                jobs.append(Job(10, 11, x, y, w, h, win, pq, imv, ss, 10, 1, alt, 1, lam, org))
+                o_arr, o_off, o_stride = (cur, y * W + x, W) if org is None else (org, 0, w)
+                oj = B.make_job(o_arr, refp, stride, (MARGIN + y) * stride + MARGIN + x, w, h, win, pq, imv, ssm, 10, 1,
+                                alt, 1, lam, org_off=o_off, org_stride=o_stride)
+                r = B.Result()
+                oracle_lib.vo_search(C.byref(oj), C.byref(r), 0)
+                want.append(r.tuple())
+    got = ms.search(jobs)
+    bad = [(i, jobs[i].w, jobs[i].h, got[i], want[i]) for i in range(len(jobs)) if got[i] != want[i]]
+    assert not bad, "%d of %d jobs differ, first: %s" % (len(bad), len(jobs), bad[:3])
+
+
+def test_job_search_integer_amvr(ms, oracle_lib):
+    """imvShift 2/4 (FPEL / 4PEL): xPatternSearchFracDIF's integer-only branch (one SATD + rate at scale 2)."""
+    from vtm_b200 import Job
+    rng = np.random.default_rng(78)
+    W, H = 192, 160
+    ref = rng.integers(0, 1024, (H, W), dtype=np.int16)
+    cur = np.ascontiguousarray(np.roll(ref, (-2, 4), (0, 1)))
+    refp = pad_plane(ref)
+    ms.upload_picture(12, cur)
+    ms.upload_picture(13, refp, MARGIN)
+    stride = refp.shape[1]
+    jobs, want = [], []
+    for (w, h) in [(8, 8), (16, 8), (8, 16), (32, 32), (64, 32), (4, 8)]:
+        for imv in (2, 4):
+            x, y = 48, 40
+            pq = (int(rng.integers(-20, 21)) * 4, int(rng.integers(-20, 21)) * 4)
+            win = oracle_window(oracle_lib, pq, x, y, W, H, 10)
+            jobs.append(Job(12, 13, x, y, w, h, win, pq, imv, 0, 10, 1, 0, 1, 20.0))
+            oj = B.make_job(cur, refp, stride, (MARGIN + y) * stride + MARGIN + x, w, h, win, pq, imv, 0, 10, 1, 0, 1,
+                            20.0, org_off=y * W + x, org_stride=W)
+            r = B.Result()
+            oracle_lib.vo_search(C.byref(oj), C.byref(r), 0)
+            want.append(r.tuple())
+    got = ms.search(jobs)
+    assert got == want
+
+
+def test_dist_host_all_shapes(ms, oracle_lib):
+    """The DistParam-hook flavour: one block pair in host memory, SAD (subShift 0/1) and SATD, incl. 4x4."""
+    rng = np.random.default_rng(79)
+    for w in SIZES:
+        for h in SIZES:
+            org = rng.integers(0, 1024, (h, w + 3), dtype=np.int16)
+            cur = np.clip(org.astype(np.int32) + np.rint(rng.normal(0, 16, org.shape)).astype(np.int32), 0, 1023).astype(np.int16)
+            o, c = org[:, 1:1 + w], cur[:, 2:2 + w]
+            for ss in (0, 1):
+                if (h >> ss) < 1:
+                    continue
+                assert ms.dist_host(0, o, c, ss) == oracle_lib.vo_sad(B.ptr(org, 1), w + 3, B.ptr(cur, 2), w + 3, w, h, ss)
+            assert ms.dist_host(1, o, c) == oracle_lib.vo_satd(B.ptr(org, 1), w + 3, B.ptr(cur, 2), w + 3, w, h)
+
+
+def test_dist_batch_device(ms, oracle_lib):
+    import torch
+    rng = np.random.default_rng(80)
+    n = 512
+    for (w, h) in [(8, 8), (16, 16), (32, 8), (8, 32), (64, 64), (4, 16), (16, 4), (128, 128), (4, 4)]:
+        org = rng.integers(0, 1024, (n, h, w), dtype=np.int16)
+        cur = rng.integers(0, 1024, (n, h, w), dtype=np.int16)
+        d_org, d_cur = torch.from_numpy(org).cuda(), torch.from_numpy(cur).cuda()
+        out = torch.zeros(n, dtype=torch.int64, device="cuda")
+        for kind, ss in ((0, 0), (0, 1), (1, 0)):
+            if (h >> ss) < 1:
+                continue
+            ms.dist_batch(kind, d_org.data_ptr(), w, w * h, d_cur.data_ptr(), w, w * h, w, h, ss, n, out.data_ptr())
+            ms.synchronize()
+            torch.cuda.synchronize()
+            got = out.cpu().numpy()
+            for i in range(0, n, 37):
+                if kind == 0:
+                    ref = oracle_lib.vo_sad(B.ptr(org[i]), w, B.ptr(cur[i]), w, w, h, ss)
+                else:
+                    ref = oracle_lib.vo_satd(B.ptr(org[i]), w, B.ptr(cur[i]), w, w, h)
+                assert int(got[i]) == ref, (w, h, kind, ss, i)
+
+
+def test_interp_host_matches_oracle(ms, oracle_lib):
+    rng = np.random.default_rng(81)
+    for bd in (8, 10):
+        for (w, h) in [(4, 4), (4, 11), (8, 8), (9, 16), (17, 24), (64, 64), (129, 136)]:
+            for frac in (0, 1, 4, 8, 12, 15):
+                for alt in ((0, 1) if frac == 8 else (0,)):
+                    src = rng.integers(0, 1 << bd, (h + 10, w + 10), dtype=np.int16)
+                    mid = rng.integers(-8192, 8192, (h + 10, w + 10), dtype=np.int16)
+                    off, ss = 4 * (w + 10) + 4, w + 10
+                    for (vert, first, last, s) in [(0, 1, 0, src), (0, 1, 1, src), (1, 1, 0, src), (1, 1, 1, src),
+                                                   (1, 0, 1, mid), (1, 0, 0, mid)]:
+                        want = np.zeros((h, w), np.int16)
+                        if vert:
+                            oracle_lib.vo_filter_ver(0, B.ptr(s, off), ss, B.ptr(want), w, w, h, frac, first, last, bd, alt)
+                        else:
+                            oracle_lib.vo_filter_hor(0, B.ptr(s, off), ss, B.ptr(want), w, w, h, frac, last, bd, alt)
+                        got = ms.interp_host(0, vert, s, off, ss, w, h, frac, first, last, bd, alt)
+                        assert np.array_equal(got, want), (bd, w, h, frac, alt, vert, first, last)
+    for (w, h) in [(2, 2), (4, 4), (8, 2), (16, 16), (64, 64)]:
+        for frac in (0, 1, 7, 16, 31):
+            src = rng.integers(0, 1024, (h + 6, w + 6), dtype=np.int16)
+            off, ss = 2 * (w + 6) + 2, w + 6
+            for (vert, first, last) in [(0, 1, 0), (0, 1, 1), (1, 1, 1), (1, 1, 0)]:
+                want = np.zeros((h, w), np.int16)
+                if vert:
+                    oracle_lib.vo_filter_ver(1, B.ptr(src, off), ss, B.ptr(want), w, w, h, frac, first, last, 10, 0)
+                else:
+                    oracle_lib.vo_filter_hor(1, B.ptr(src, off), ss, B.ptr(want), w, w, h, frac, last, 10, 0)
+                got = ms.interp_host(1, vert, src, off, ss, w, h, frac, first, last, 10, 0)
+                assert np.array_equal(got, want), ("chroma", w, h, frac, vert, first, last)

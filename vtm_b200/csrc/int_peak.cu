@@ -1,0 +1,187 @@
+// INT/ALU-pipe peak microbenchmark for sm_100a (the roofline denominator of the motion search
+// is the measured issue rate of the SAD instruction, not a datasheet number).
+//
+// Each kernel runs a long dependency-free stream of one instruction class (8-16 independent accumulators
+// per thread, 256 threads/CTA, 8 CTAs/SM resident) and reports lane-instructions / clk / SM from the
+// elapsed time and the SM clock it ran at (clock64 inside the kernel).
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#include "vtmme_internal.h"
+
+namespace {
+
+constexpr int kUnroll = 16;   // independent accumulators per thread
+
+// Variant ids (keep in sync with vtm_b200/peaks.py)
+enum { V_VABSDIFF = 0, V_IADD3, V_IMAD, V_LOP3, V_PRMT, V_VABSDIFF_IMAD, V_FADD_ABS, V_VABSDIFF_FADD, V_VIADD16X2,
+       V_VIADDMNMX16X2, V_VABSDIFF4, V_VABSDIFF_FADD2, V_COUNT };
+
+template <int V>
+__global__ void __launch_bounds__(256) peak_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int iters,
+                                                   unsigned long long* __restrict__ clk)
+{
+  uint32_t acc[kUnroll];
+  uint32_t b[kUnroll];
+#pragma unroll
+  for (int i = 0; i < kUnroll; i++)
+  {
+    b[i]   = in[(threadIdx.x * 3 + i * 11 + 5) & 1023];
+    acc[i] = in[(threadIdx.x + i * 37) & 1023];
+  }
+  float facc[kUnroll];
+#pragma unroll
+  for (int i = 0; i < kUnroll; i++) facc[i] = __uint_as_float(acc[i] >> 3);
+
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; it++)
+  {
+    // operand x is another accumulator (static index), so nothing is loop-invariant and every chain stays
+    // independent of its own previous result only through acc[i] (16 chains per thread).
+#pragma unroll
+    for (int i = 0; i < kUnroll; i++)
+    {
+      const uint32_t x = acc[(i + 5) & (kUnroll - 1)];
+      const float    fx = facc[(i + 5) & (kUnroll - 1)];
+      if (V == V_VABSDIFF) acc[i] = __usad(x, b[i], acc[i]);
+      if (V == V_IADD3) acc[i] = acc[i] + x + b[i];
+      if (V == V_IMAD) acc[i] = x * b[i] + acc[i];
+      if (V == V_LOP3) acc[i] = (acc[i] & x) ^ b[i];
+      if (V == V_PRMT) acc[i] = __byte_perm(acc[i], x, b[i]);
+      if (V == V_VABSDIFF_IMAD)
+      {
+        if (i & 1) acc[i] = __usad(x, b[i], acc[i]);
+        else       acc[i] = x * b[i] + acc[i];
+      }
+      if (V == V_FADD_ABS)
+      {
+        // |a-b| accumulated in FP32 on raw integer bit patterns (denormals: exact fixed point, no .ftz)
+        float d = __fsub_rn(fx, __uint_as_float(b[i]));
+        facc[i] = __fadd_rn(facc[i], fabsf(d));
+      }
+      if (V == V_VABSDIFF_FADD)
+      {   // 2 px on the ALU pipe per 1 px on the FP pipe (1 + 1 + 2 instructions per 4 slots)
+        if ((i & 3) < 2) acc[i] = __usad(x, b[i], acc[i]);
+        if ((i & 3) == 3)
+        {
+          float d = __fsub_rn(fx, __uint_as_float(b[i]));
+          facc[i] = __fadd_rn(facc[i], fabsf(d));
+        }
+      }
+      if (V == V_VABSDIFF_FADD2)
+      {   // 1 px ALU : 1 px FP  (1 + 2 instructions per 2 slots)
+        if (i & 1) acc[i] = __usad(x, b[i], acc[i]);
+        else
+        {
+          float d = __fsub_rn(fx, __uint_as_float(b[i]));
+          facc[i] = __fadd_rn(facc[i], fabsf(d));
+        }
+      }
+      if (V == V_VIADD16X2) acc[i] = __vadd2(x, b[i]) ^ acc[i];
+      if (V == V_VIADDMNMX16X2) acc[i] = __viaddmax_s16x2(x, b[i], acc[i]);
+      if (V == V_VABSDIFF4) acc[i] = __vsadu4(x, b[i]) + acc[i];
+    }
+  }
+  const long long t1 = clock64();
+  uint32_t        r  = 0;
+#pragma unroll
+  for (int i = 0; i < kUnroll; i++) r += acc[i] + __float_as_uint(facc[i]);
+  out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+  if (threadIdx.x == 0) clk[blockIdx.x] = (unsigned long long) (t1 - t0);
+}
+
+// instructions per accumulator-slot per iteration (for the rate computation)
+__host__ double instr_per_slot(int v)
+{
+  switch (v)
+  {
+    case V_FADD_ABS: return 2.0;
+    case V_VABSDIFF_FADD: return (2 * 1.0 + 1 * 2.0) / 4.0;   // slots 0,1 usad; slot 2 idle; slot 3 = 2 FADD
+    case V_VIADD16X2: return 2.0;   // VIADD.16x2 + LOP3
+    case V_VABSDIFF_FADD2: return 1.5;
+    case V_VABSDIFF4: return 1.0;   // ptxas folds the add into VABSDIFF4.U8.ACC
+    default: return 1.0;
+  }
+}
+
+template <int V>
+int run_variant(int iters, int sms, const uint32_t* din, uint32_t* dout, unsigned long long* dclk, double* laneRate,
+                double* ms, cudaStream_t st)
+{
+  const int   grid = sms * 8;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  peak_kernel<V><<<grid, 256, 0, st>>>(din, dout, iters / 8 + 1, dclk);   // warm-up
+  cudaEventRecord(e0, st);
+  peak_kernel<V><<<grid, 256, 0, st>>>(din, dout, iters, dclk);
+  cudaEventRecord(e1, st);
+  cudaError_t err = cudaStreamSynchronize(st);
+  if (err != cudaSuccess) return -1;
+  float t = 0;
+  cudaEventElapsedTime(&t, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  unsigned long long hclk[8];
+  cudaMemcpy(hclk, dclk, sizeof(hclk), cudaMemcpyDeviceToHost);
+  double cyc = 0;
+  for (int i = 0; i < 8; i++) cyc += (double) hclk[i];
+  cyc /= 8.0;
+  // one CTA's span in cycles covers 8 co-resident CTAs' work on that SM (grid = 8 CTAs/SM, one wave)
+  const double laneInstrPerSm = 8.0 * 256.0 * (double) iters * kUnroll * instr_per_slot(V);
+  *laneRate = laneInstrPerSm / cyc;
+  *ms       = t;
+  return 0;
+}
+
+}   // namespace
+
+extern "C" int vtmme_int_peak(int variant, int iters, double* laneInstrPerClkPerSm, double* ms, double* smClockMHz)
+{
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return VTMME_ERR_CUDA;
+  const int sms = prop.multiProcessorCount;
+  uint32_t *din = nullptr, *dout = nullptr;
+  unsigned long long* dclk = nullptr;
+  cudaMalloc(&din, 1024 * 4);
+  cudaMalloc(&dout, (size_t) sms * 8 * 256 * 4);
+  cudaMalloc(&dclk, (size_t) sms * 8 * 8);
+  uint32_t h[1024];
+  for (int i = 0; i < 1024; i++) h[i] = (uint32_t) ((i * 2654435761u) >> 22);   // 10-bit values
+  cudaMemcpy(din, h, sizeof(h), cudaMemcpyHostToDevice);
+  cudaStream_t st;
+  cudaStreamCreate(&st);
+  int rc = -1;
+  switch (variant)
+  {
+#define CASE(V) case V: rc = run_variant<V>(iters, sms, din, dout, dclk, laneInstrPerClkPerSm, ms, st); break;
+    CASE(V_VABSDIFF) CASE(V_IADD3) CASE(V_IMAD) CASE(V_LOP3) CASE(V_PRMT) CASE(V_VABSDIFF_IMAD) CASE(V_FADD_ABS)
+    CASE(V_VABSDIFF_FADD) CASE(V_VIADD16X2) CASE(V_VIADDMNMX16X2) CASE(V_VABSDIFF4) CASE(V_VABSDIFF_FADD2)
+#undef CASE
+    default: rc = -2;
+  }
+  if (rc == 0)
+  {
+    // clocks: lane-instr / (ms * sms * rate) -> MHz the SMs ran at
+    const double total = *laneInstrPerClkPerSm;   // per clk per SM
+    const double laneInstr = 8.0 * 256.0 * (double) iters * kUnroll;
+    (void) laneInstr;
+    (void) total;
+    *smClockMHz = 0.0;
+    if (*ms > 0)
+    {
+      // cycles of one CTA span / elapsed time
+      unsigned long long hclk0 = 0;
+      cudaMemcpy(&hclk0, dclk, 8, cudaMemcpyDeviceToHost);
+      *smClockMHz = (double) hclk0 / (*ms * 1e3);
+    }
+  }
+  cudaStreamDestroy(st);
+  cudaFree(din);
+  cudaFree(dout);
+  cudaFree(dclk);
+  return rc == 0 ? VTMME_OK : VTMME_ERR_CUDA;
+}

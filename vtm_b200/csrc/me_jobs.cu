@@ -1,0 +1,276 @@
+// Per-call motion search (vtmme_search): one job = the integer full search of one
+// InterSearch::xMotionEstimation call (xPatternSearch, EncoderLib/InterSearch.cpp:3566-3608) followed by
+// the xPatternSearchFracDIF body (:4296-4338).  Any w,h in {4..128}, any window, row sub-sampling
+// (DistParam::subShift) and signed patterns (bi-pred 2*org - otherPred, :3317-3328).
+//
+//   me_job_sad_kernel     CTA = (job, 32x32 sub-block of the pattern, slice of window rows): SADs with signed
+//                         VABSDIFF, 8 displacements x 1 row per thread step.  Single-sub-block jobs keep their
+//                         argmin directly; larger patterns write one SAD surface per sub-block.
+//   me_job_reduce_kernel  sums the sub-block surfaces of a large pattern, adds lambda*bits, argmin.
+//   me_job_frac_kernel    fractional refinement (me_frac.cuh) and result write-out.
+#include "me_frac.cuh"
+#include "me_kernels.h"
+
+namespace vtmme {
+
+namespace {
+
+constexpr int kJobThreads  = 256;
+constexpr int kJobBandRows = 32;
+
+struct JobSmemHdr
+{
+  unsigned long long best;
+  int                pad[2];
+};
+constexpr int kJobOffOrg = 16;                   // int32 [32][32]
+constexpr int kJobOffRef = kJobOffOrg + 4096;    // int16 [rows][refStride]
+
+__device__ __forceinline__ void job_consider(const DevJob& j, unsigned long long* best, int dx, int dy, uint32_t sad)
+{
+  if (dx < j.l || dx > j.r || dy < j.t || dy > j.b) return;
+  const uint32_t cost = sad + mv_cost(j.lambda, mv_bits_q(dx * 4, dy * 4, j.predQx, j.predQy, j.imvShift));
+  atomicMin(best, make_key(cost, dx, dy));
+}
+
+__device__ __forceinline__ int regions_of(const DevJob& j) { return ((j.w + 31) >> 5) * ((j.h + 31) >> 5); }
+
+__global__ void __launch_bounds__(kJobThreads, 2) me_job_sad_kernel(const DevJob* __restrict__ jobs,
+                                                                    unsigned long long* __restrict__ keys,
+                                                                    uint32_t* __restrict__ surf,
+                                                                    const long long* __restrict__ surfOff, int nSplit)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  JobSmemHdr* hdr   = reinterpret_cast<JobSmemHdr*>(smem);
+  int32_t*    s_org = reinterpret_cast<int32_t*>(smem + kJobOffOrg);
+  int16_t*    s_ref = reinterpret_cast<int16_t*>(smem + kJobOffRef);
+
+  const DevJob j      = jobs[blockIdx.y];
+  const int    nReg   = regions_of(j);
+  const int    region = blockIdx.x / nSplit, split = blockIdx.x % nSplit;
+  if (region >= nReg) return;
+  const int tid = threadIdx.x;
+  const int regX = (j.w + 31) >> 5;
+  const int rx0 = (region % regX) * 32, ry0 = (region / regX) * 32;
+  const int rw = min(32, j.w), rh = min(32, j.h);
+  const int wl8 = j.l & ~7;
+  const int ngx = (j.r - wl8 + 8) >> 3, nrows = j.b - j.t + 1;
+  const int refStride = ngx * 8 + 40;
+  const int step = 1 << j.subShift;
+  const bool direct = nReg == 1;
+
+  if (tid == 0) hdr->best = ~0ull;
+  for (int i = tid; i < rw * rh; i += kJobThreads)
+  {
+    const int y = i / rw, x = i - y * rw;
+    s_org[y * 32 + x] = (int32_t) j.org[(size_t) (ry0 + y) * j.orgStride + rx0 + x];
+  }
+  uint32_t* mySurf = direct ? nullptr : surf + surfOff[blockIdx.y] + (long long) region * nrows * (ngx * 8);
+
+  for (int band0 = split * kJobBandRows; band0 < nrows; band0 += nSplit * kJobBandRows)
+  {
+    const int bh = min(kJobBandRows, nrows - band0);
+    __syncthreads();
+    {
+      // rows [j.t+band0, +bh+rh-1), cols [wl8, wl8 + ngx*8 + rw + 7] relative to the sub-block position
+      const int cols = ngx * 8 + rw + 8;
+      const int16_t* src = j.refAtPU + (ptrdiff_t) (ry0 + j.t + band0) * j.refStride + (rx0 + wl8);
+      for (int i = tid; i < (bh + rh - 1) * cols; i += kJobThreads)
+      {
+        const int r = i / cols, c = i - r * cols;
+        s_ref[r * refStride + c] = src[(ptrdiff_t) r * j.refStride + c];
+      }
+    }
+    __syncthreads();
+    const int ntiles = ngx * bh;
+    for (int t = tid; t < ntiles; t += kJobThreads)
+    {
+      const int      dyi = t / ngx, gx = t - dyi * ngx;
+      const int      dy = j.t + band0 + dyi, dx0 = wl8 + gx * 8;
+      const int16_t* refTile = s_ref + dyi * refStride + gx * 8;
+      uint32_t       a[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) a[k] = 0;
+      for (int r = 0; r < rh; r += step)
+      {
+        if (rw >= 8)
+        {
+          for (int g = 0; g < rw; g += 8)
+          {
+            const int4  o0 = *reinterpret_cast<const int4*>(s_org + r * 32 + g);
+            const int4  o1 = *reinterpret_cast<const int4*>(s_org + r * 32 + g + 4);
+            const uint4 w0 = *reinterpret_cast<const uint4*>(refTile + r * refStride + g);
+            const uint4 w1 = *reinterpret_cast<const uint4*>(refTile + r * refStride + g + 8);
+            const int   o[8]   = { o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w };
+            const int   px[16] = { (int) (short) (w0.x & 0xffffu), (int) w0.x >> 16, (int) (short) (w0.y & 0xffffu), (int) w0.y >> 16,
+                                   (int) (short) (w0.z & 0xffffu), (int) w0.z >> 16, (int) (short) (w0.w & 0xffffu), (int) w0.w >> 16,
+                                   (int) (short) (w1.x & 0xffffu), (int) w1.x >> 16, (int) (short) (w1.y & 0xffffu), (int) w1.y >> 16,
+                                   (int) (short) (w1.z & 0xffffu), (int) w1.z >> 16, (int) (short) (w1.w & 0xffffu), (int) w1.w >> 16 };
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+#pragma unroll
+              for (int i = 0; i < 8; i++) a[k] = __sad(o[i], px[i + k], a[k]);
+          }
+        }
+        else
+        {
+          const int4  o0 = *reinterpret_cast<const int4*>(s_org + r * 32);
+          const uint4 w0 = *reinterpret_cast<const uint4*>(refTile + r * refStride);
+          const uint2 w1 = *reinterpret_cast<const uint2*>(refTile + r * refStride + 8);
+          const int   o[4]   = { o0.x, o0.y, o0.z, o0.w };
+          const int   px[12] = { (int) (short) (w0.x & 0xffffu), (int) w0.x >> 16, (int) (short) (w0.y & 0xffffu), (int) w0.y >> 16,
+                                 (int) (short) (w0.z & 0xffffu), (int) w0.z >> 16, (int) (short) (w0.w & 0xffffu), (int) w0.w >> 16,
+                                 (int) (short) (w1.x & 0xffffu), (int) w1.x >> 16, (int) (short) (w1.y & 0xffffu), (int) w1.y >> 16 };
+#pragma unroll
+          for (int k = 0; k < 8; k++)
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[k] = __sad(o[i], px[i + k], a[k]);
+        }
+      }
+      if (direct)
+      {
+        const uint32_t thr = (uint32_t) (*reinterpret_cast<volatile unsigned long long*>(&hdr->best) >> 32);
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+        {
+          const uint32_t sad = a[k] << j.subShift;
+          if (sad <= thr) job_consider(j, &hdr->best, dx0 + k, dy, sad);
+        }
+      }
+      else
+      {
+        uint4* dst = reinterpret_cast<uint4*>(mySurf + (size_t) (band0 + dyi) * (ngx * 8) + gx * 8);
+        dst[0]     = make_uint4(a[0], a[1], a[2], a[3]);
+        dst[1]     = make_uint4(a[4], a[5], a[6], a[7]);
+      }
+    }
+  }
+  __syncthreads();
+  if (direct && tid == 0 && hdr->best != ~0ull) atomicMin(keys + blockIdx.y, hdr->best);
+}
+
+__global__ void __launch_bounds__(256) me_job_reduce_kernel(const DevJob* __restrict__ jobs,
+                                                            unsigned long long* __restrict__ keys,
+                                                            const uint32_t* __restrict__ surf,
+                                                            const long long* __restrict__ surfOff)
+{
+  const DevJob j    = jobs[blockIdx.y];
+  const int    nReg = regions_of(j);
+  if (nReg == 1) return;
+  const int wl8 = j.l & ~7;
+  const int ngx = (j.r - wl8 + 8) >> 3, nrows = j.b - j.t + 1;
+  const int ww = j.r - j.l + 1;
+  const uint32_t* base = surf + surfOff[blockIdx.y];
+  const size_t    regStride = (size_t) nrows * ngx * 8;
+  unsigned long long best = ~0ull;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ww * nrows; i += gridDim.x * blockDim.x)
+  {
+    const int dyi = i / ww, dxi = i - dyi * ww;
+    const int dx = j.l + dxi, dy = j.t + dyi;
+    const size_t off = (size_t) dyi * (ngx * 8) + (dx - wl8);
+    uint32_t     s = 0;
+    for (int r = 0; r < nReg; r++) s += base[r * regStride + off];
+    s <<= j.subShift;
+    if (s <= key_cost(best))
+    {
+      const uint32_t cost = s + mv_cost(j.lambda, mv_bits_q(dx * 4, dy * 4, j.predQx, j.predQy, j.imvShift));
+      const unsigned long long k = make_key(cost, dx, dy);
+      if (k < best) best = k;
+    }
+  }
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1)
+  {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, m);
+    best                       = o < best ? o : best;
+  }
+  if ((threadIdx.x & 31) == 0 && best != ~0ull) atomicMin(keys + blockIdx.y, best);
+}
+
+__global__ void __launch_bounds__(kFracThreads) me_job_frac_kernel(const DevJob* __restrict__ jobs,
+                                                                   const unsigned long long* __restrict__ keys,
+                                                                   DevJobResult* __restrict__ results)
+{
+  __shared__ FracSmem sm;
+  const DevJob             j   = jobs[blockIdx.x];
+  const unsigned long long key = keys[blockIdx.x];
+  const int                dx = key_dx(key), dy = key_dy(key);
+  const uint32_t           intCost = key_cost(key);
+  DevJobResult             res;
+  res.mvX    = dx;
+  res.mvY    = dy;
+  res.intSad = intCost - mv_cost(j.lambda, mv_bits_q(dx * 4, dy * 4, j.predQx, j.predQy, j.imvShift));
+  res.halfX = res.halfY = res.qterX = res.qterY = 0;
+  res.fracCost = res.intSad;
+  if (j.fracMode)
+  {
+    FracJob f;
+    f.org        = j.org;
+    f.orgStride  = j.orgStride;
+    f.refAtMv    = j.refAtPU + (ptrdiff_t) dy * j.refStride + dx;
+    f.refStride  = j.refStride;
+    f.w          = j.w;
+    f.h          = j.h;
+    f.mvX        = dx;
+    f.mvY        = dy;
+    f.predQx     = j.predQx;
+    f.predQy     = j.predQy;
+    f.bitDepth   = j.bitDepth;
+    f.useHad     = j.useHad;
+    f.useAltHpel = j.useAltHpel;
+    f.imvShift   = j.imvShift;
+    f.lambda     = j.lambda;
+    if (j.imvShift > 1)
+    {
+      // xPatternSearchFracDIF :4311-4317 — integer AMVR: one SATD/SAD at the integer MV, rate at cost scale 2
+      frac_stage(sm, f, 0, 0, 2, false);
+      res.fracCost = sm.centre + mv_cost(j.lambda, mv_bits_q(dx * 4, dy * 4, j.predQx, j.predQy, j.imvShift));
+    }
+    else
+    {
+      const FracOut o = frac_refine_cta(sm, f);
+      res.halfX    = o.halfX;
+      res.halfY    = o.halfY;
+      res.qterX    = o.qterX;
+      res.qterY    = o.qterY;
+      res.fracCost = o.cost;
+    }
+  }
+  if (threadIdx.x == 0) results[blockIdx.x] = res;
+}
+
+}   // namespace
+
+// dJobs must be followed in the same buffer by nothing the kernels need; dKeys [n]; surfaces are sized and
+// offset by the caller (vtmme_api.cu) and passed through dSurf / dSurfOff.
+cudaError_t launch_job_search_impl(const DevJob* dJobs, unsigned long long* dKeys, DevJobResult* dResults, int n,
+                                   int maxRegions, int nSplit, int maxGx, bool anyMulti, uint32_t* dSurf,
+                                   const long long* dSurfOff, cudaStream_t st, int* launches)
+{
+  const size_t smem = (size_t) kJobOffRef + (size_t) (kJobBandRows + 31) * (maxGx * 8 + 40) * 2;
+  static size_t configured = 0;
+  if (smem > configured)
+  {
+    cudaError_t e = cudaFuncSetAttribute(me_job_sad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  dim3 grid(maxRegions * nSplit, n, 1);
+  me_job_sad_kernel<<<grid, kJobThreads, smem, st>>>(dJobs, dKeys, dSurf, dSurfOff, nSplit);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  *launches += 1;
+  if (anyMulti)
+  {
+    dim3 g2(16, n, 1);
+    me_job_reduce_kernel<<<g2, 256, 0, st>>>(dJobs, dKeys, dSurf, dSurfOff);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    *launches += 1;
+  }
+  me_job_frac_kernel<<<n, kFracThreads, 0, st>>>(dJobs, dKeys, dResults);
+  *launches += 1;
+  return cudaGetLastError();
+}
+
+}   // namespace vtmme

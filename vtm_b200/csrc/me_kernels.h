@@ -1,0 +1,111 @@
+// Host-side launch interface of the motion-search kernels (internal to libvtmme.so).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "me_common.cuh"
+
+namespace vtmme {
+
+// Geometry of the batched per-CTU search (vtmme_search_frames): 5 levels of grid-aligned square CUs.
+struct FrameGeom
+{
+  int picW, picH;
+  int nx[5], ny[5];   // CUs per level (size 8<<l), floor(pic/size)
+  int off[6];         // level offsets in the CU order, off[5] = total
+  int nRegX, nRegY;   // 32x32 regions, ceil
+  int nCtuX, nCtuY;   // 128x128 CTUs, ceil
+};
+
+inline FrameGeom make_geom(int w, int h)
+{
+  FrameGeom g;
+  g.picW = w;
+  g.picH = h;
+  int acc = 0;
+  for (int l = 0; l < 5; l++)
+  {
+    g.nx[l]  = w / (8 << l);
+    g.ny[l]  = h / (8 << l);
+    g.off[l] = acc;
+    acc += g.nx[l] * g.ny[l];
+  }
+  g.off[5] = acc;
+  g.nRegX  = (w + 31) / 32;
+  g.nRegY  = (h + 31) / 32;
+  g.nCtuX  = (w + 127) / 128;
+  g.nCtuY  = (h + 127) / 128;
+  return g;
+}
+
+struct TreeParams
+{
+  FrameGeom           g;
+  const DevPic*       cur;       // [nPairs]
+  const DevPic*       ref;       // [nPairs]
+  const short2*       predQ;     // [nPairs][nCU] quarter-pel, or nullptr (zero)
+  unsigned long long* keys;      // [nPairs][nCU] best (cost, position) per CU
+  uint32_t*           surf;      // [nPairs][nReg][surfCap] SAD32 surfaces for the 64/128 levels
+  int4*               regInfo;   // [nPairs][nReg] {wl8, wt, ngx, nrows} of each surface
+  int*                errFlag;
+  int                 surfCap;     // elements per region surface
+  int                 maxGx;       // capacity: 8-wide displacement groups per row
+  int                 maxRows;     // capacity: displacement rows per region
+  int                 bandRows;    // displacement rows staged per band
+  int                 sr, ctu, imvShift;
+  double              lambda;
+};
+
+size_t tree_sad_smem_bytes(int maxGx, int bandRows);
+cudaError_t launch_tree_sad(const TreeParams& p, int nPairs, cudaStream_t st);
+cudaError_t launch_tree_upper(const TreeParams& p, int nPairs, cudaStream_t st);
+
+// Fractional refinement + result write-out for the frame path.
+struct FracFrameParams
+{
+  FrameGeom                 g;
+  const DevPic*             cur;
+  const DevPic*             ref;
+  const short2*             predQ;
+  const unsigned long long* keys;
+  void*                     results;   // vtmme_cu_result[nPairs][nCU]
+  int                       bitDepth, imvShift, useHad, fracMode;
+  double                    lambda;
+};
+cudaError_t launch_frac_frame(const FracFrameParams& p, int nPairs, cudaStream_t st);
+
+// Generic per-call jobs (vtmme_search)
+struct DevJob
+{
+  const int16_t* org;        // device pointer to the pattern
+  int            orgStride;
+  const int16_t* refAtPU;    // device pointer: reference plane at the PU position
+  int            refStride;
+  int            w, h;
+  int            l, r, t, b;
+  int            predQx, predQy;
+  int            imvShift, subShift, bitDepth, useHad, useAltHpel, fracMode;
+  int            signedOrg;  // pattern may be outside [0, 2^bd): bi-pred 2*org - otherPred
+  double         lambda;
+};
+struct DevJobResult
+{
+  int                mvX, mvY;
+  unsigned long long intSad;
+  int                halfX, halfY, qterX, qterY;
+  unsigned long long fracCost;
+};
+cudaError_t launch_job_search_impl(const DevJob* dJobs, unsigned long long* dKeys, DevJobResult* dResults, int n,
+                                   int maxRegions, int nSplit, int maxGx, bool anyMulti, uint32_t* dSurf,
+                                   const long long* dSurfOff, cudaStream_t st, int* launches);
+
+// Table-level batches
+cudaError_t launch_dist_batch(int kind, const int16_t* org, int orgStride, long long orgBlockStride, const int16_t* cur,
+                              int curStride, long long curBlockStride, int w, int h, int subShift, int n,
+                              unsigned long long* out, cudaStream_t st);
+cudaError_t launch_interp_batch(int comp, int vertical, const int16_t* src, int srcStride, long long srcBlockStride,
+                                int16_t* dst, int dstStride, long long dstBlockStride, int w, int h, int frac, int isFirst,
+                                int isLast, int bitDepth, int useAltHpel, int n, cudaStream_t st);
+cudaError_t launch_extend_border(DevPic pic, cudaStream_t st);
+
+}   // namespace vtmme

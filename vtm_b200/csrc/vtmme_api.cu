@@ -1,0 +1,601 @@
+// C ABI of libvtmme.so (include/vtmme.h): context, device pictures, and the orchestration of the kernels.
+// There is no CPU implementation of anything behind these entry points: a failing CUDA call is an error.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "me_kernels.h"
+#include "vtmme_internal.h"
+
+using namespace vtmme;
+
+struct vtmme_ctx
+{
+  int          device    = 0;
+  cudaStream_t stream    = nullptr;
+  cudaStream_t ownStream = nullptr;
+  std::string  err;
+  uint64_t     launches = 0;
+  std::unordered_map<int, DevPic> pics;
+
+  // scratch of the frame path (grown on demand)
+  DevPic*             dCur = nullptr;
+  DevPic*             dRef = nullptr;
+  size_t              curArrCap = 0, refArrCap = 0;
+  unsigned long long* dKeys = nullptr;
+  size_t              keysCap = 0;
+  uint32_t*           dSurf = nullptr;
+  size_t              surfCapBytes = 0;
+  int4*               dRegInfo = nullptr;
+  size_t              regInfoCap = 0;
+  int*                dErr = nullptr;
+  int16_t*            dPred = nullptr;
+  size_t              predCap = 0;
+  vtmme_cu_result*    dRes = nullptr;
+  size_t              resCap = 0;
+
+  // scratch of the per-call job path
+  unsigned char* dJobBuf = nullptr;
+  size_t         jobBufCap = 0;
+  unsigned char* hPinned = nullptr;
+  size_t         hPinnedCap = 0;
+  uint32_t*      dJobSurf = nullptr;
+  size_t         jobSurfCap = 0;
+};
+
+int vtmme_set_error(vtmme_ctx* ctx, int code, const char* what, const char* detail)
+{
+  if (ctx)
+  {
+    ctx->err = std::string(what ? what : "") + ": " + (detail ? detail : "");
+  }
+  return code;
+}
+
+namespace {
+
+template <typename T>
+int ensure(vtmme_ctx* ctx, T*& ptr, size_t& capBytes, size_t needBytes)
+{
+  if (needBytes <= capBytes) return VTMME_OK;
+  if (ptr) cudaFree(ptr);
+  ptr      = nullptr;
+  capBytes = 0;
+  void* p  = nullptr;
+  if (cudaMalloc(&p, needBytes) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return vtmme_set_error(ctx, VTMME_ERR_NOMEM, "cudaMalloc", "out of device memory");
+  }
+  ptr      = reinterpret_cast<T*>(p);
+  capBytes = needBytes;
+  return VTMME_OK;
+}
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+int alloc_pic(vtmme_ctx* ctx, int picId, int width, int height, int margin, DevPic* out)
+{
+  auto it = ctx->pics.find(picId);
+  const int m = round_up(margin < VTMME_MIN_MARGIN ? VTMME_MIN_MARGIN : margin, 64);
+  if (it != ctx->pics.end())
+  {
+    if (it->second.width == width && it->second.height == height && it->second.margin == m)
+    {
+      *out = it->second;
+      return VTMME_OK;
+    }
+    cudaFree(it->second.base);
+    ctx->pics.erase(it);
+  }
+  DevPic p;
+  p.width  = width;
+  p.height = height;
+  p.margin = m;
+  p.stride = round_up(width + 2 * m, 64);
+  const size_t bytes = (size_t) p.stride * (height + 2 * m) * sizeof(int16_t);
+  void* base = nullptr;
+  if (cudaMalloc(&base, bytes) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return vtmme_set_error(ctx, VTMME_ERR_NOMEM, "cudaMalloc(picture)", "out of device memory");
+  }
+  p.base   = reinterpret_cast<int16_t*>(base);
+  p.origin = p.base + (size_t) m * p.stride + m;
+  ctx->pics[picId] = p;
+  *out = p;
+  return VTMME_OK;
+}
+
+int upload_common(vtmme_ctx* ctx, int picId, const int16_t* origin, int stride, int width, int height, int margin,
+                  int withBorder, cudaMemcpyKind kind)
+{
+  if (!ctx) return VTMME_ERR_ARG;
+  if (!origin || width <= 0 || height <= 0 || stride < width || margin < 0)
+    return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_upload_picture", "bad plane description");
+  VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  DevPic p;
+  int rc = alloc_pic(ctx, picId, width, height, margin, &p);
+  if (rc != VTMME_OK) return rc;
+  // copy what the caller owns: the picture area, plus its own border when asked to
+  const int cm = withBorder ? (margin < p.margin ? margin : p.margin) : 0;
+  VTMME_CUDA_CHECK(ctx, cudaMemcpy2DAsync(p.origin - (ptrdiff_t) cm * p.stride - cm, (size_t) p.stride * 2,
+                                          origin - (ptrdiff_t) cm * stride - cm, (size_t) stride * 2,
+                                          (size_t) (width + 2 * cm) * 2, height + 2 * cm, kind, ctx->stream));
+  // everything beyond is edge replication (Picture::extendPicBorder, Picture.cpp:1050-1096)
+  VTMME_CUDA_CHECK(ctx, launch_extend_border(p, ctx->stream));
+  ctx->launches += 1;
+  if (kind == cudaMemcpyHostToDevice) VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return VTMME_OK;
+}
+
+}   // namespace
+
+extern "C" {
+
+int vtmme_create(int device, vtmme_ctx** out)
+{
+  if (!out) return VTMME_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return VTMME_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return VTMME_ERR_CUDA;
+  vtmme_ctx* ctx = new vtmme_ctx();
+  ctx->device = device;
+  if (cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking) != cudaSuccess)
+  {
+    delete ctx;
+    return VTMME_ERR_CUDA;
+  }
+  ctx->stream = ctx->ownStream;
+  if (cudaMalloc(&ctx->dErr, sizeof(int)) != cudaSuccess)
+  {
+    cudaStreamDestroy(ctx->ownStream);
+    delete ctx;
+    return VTMME_ERR_NOMEM;
+  }
+  cudaMemset(ctx->dErr, 0, sizeof(int));
+  *out = ctx;
+  return VTMME_OK;
+}
+
+void vtmme_destroy(vtmme_ctx* ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& kv : ctx->pics) cudaFree(kv.second.base);
+  cudaFree(ctx->dCur);
+  cudaFree(ctx->dRef);
+  cudaFree(ctx->dKeys);
+  cudaFree(ctx->dSurf);
+  cudaFree(ctx->dRegInfo);
+  cudaFree(ctx->dErr);
+  cudaFree(ctx->dPred);
+  cudaFree(ctx->dRes);
+  cudaFree(ctx->dJobBuf);
+  cudaFree(ctx->dJobSurf);
+  if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
+  cudaStreamDestroy(ctx->ownStream);
+  delete ctx;
+}
+
+const char* vtmme_last_error(const vtmme_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int vtmme_set_stream(vtmme_ctx* ctx, void* cudaStream)
+{
+  if (!ctx) return VTMME_ERR_ARG;
+  ctx->stream = cudaStream ? reinterpret_cast<cudaStream_t>(cudaStream) : ctx->ownStream;
+  return VTMME_OK;
+}
+
+int vtmme_synchronize(vtmme_ctx* ctx)
+{
+  if (!ctx) return VTMME_ERR_ARG;
+  VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return VTMME_OK;
+}
+
+uint64_t vtmme_launch_count(const vtmme_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int vtmme_upload_picture(vtmme_ctx* ctx, int picId, const int16_t* origin, int stride, int width, int height,
+                         int margin, int withBorder)
+{
+  return upload_common(ctx, picId, origin, stride, width, height, margin, withBorder, cudaMemcpyHostToDevice);
+}
+
+int vtmme_upload_picture_device(vtmme_ctx* ctx, int picId, const int16_t* dOrigin, int stride, int width, int height,
+                                int margin, int withBorder)
+{
+  return upload_common(ctx, picId, dOrigin, stride, width, height, margin, withBorder, cudaMemcpyDeviceToDevice);
+}
+
+int vtmme_release_picture(vtmme_ctx* ctx, int picId)
+{
+  if (!ctx) return VTMME_ERR_ARG;
+  auto it = ctx->pics.find(picId);
+  if (it == ctx->pics.end()) return vtmme_set_error(ctx, VTMME_ERR_NOPIC, "vtmme_release_picture", "unknown picture id");
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(it->second.base);
+  ctx->pics.erase(it);
+  return VTMME_OK;
+}
+
+int vtmme_frame_cu_count(int width, int height, int32_t levelOffset[6])
+{
+  if (width <= 0 || height <= 0) return VTMME_ERR_ARG;
+  const FrameGeom g = make_geom(width, height);
+  if (levelOffset)
+    for (int i = 0; i < 6; i++) levelOffset[i] = g.off[i];
+  return g.off[5];
+}
+
+int vtmme_search_frames_device(vtmme_ctx* ctx, int nPairs, const int32_t* curPics, const int32_t* refPics,
+                               const vtmme_frame_params* prm, const int16_t* dPredQ, vtmme_cu_result* dResults)
+{
+  if (!ctx) return VTMME_ERR_ARG;
+  if (nPairs <= 0 || !curPics || !refPics || !prm || !dResults)
+    return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search_frames", "null argument");
+  if (prm->searchRange < 1 || prm->searchRange > 512 || prm->bitDepth < 8 || prm->bitDepth > 10 || prm->predSpread < 0)
+    return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search_frames", "unsupported parameters");
+  VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+
+  std::vector<DevPic> hc(nPairs), hr(nPairs);
+  for (int i = 0; i < nPairs; i++)
+  {
+    auto a = ctx->pics.find(curPics[i]), b = ctx->pics.find(refPics[i]);
+    if (a == ctx->pics.end() || b == ctx->pics.end())
+      return vtmme_set_error(ctx, VTMME_ERR_NOPIC, "vtmme_search_frames", "unknown picture id");
+    hc[i] = a->second;
+    hr[i] = b->second;
+    if (hc[i].width != hc[0].width || hc[i].height != hc[0].height || hr[i].width != hc[0].width ||
+        hr[i].height != hc[0].height)
+      return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search_frames", "all pictures must have the same size");
+  }
+  const FrameGeom g    = make_geom(hc[0].width, hc[0].height);
+  const int       nCU  = g.off[5];
+  const int       nReg = g.nRegX * g.nRegY;
+  if (nCU == 0) return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search_frames", "picture smaller than 8x8");
+
+  // capacity of a region's displacement superset: own window + predictor spread, 8-aligned on the left
+  const int spanMax = 2 * prm->searchRange + 1 + prm->predSpread;
+  const int maxGx   = (spanMax + 7 + 7) / 8;
+  const int maxRows = spanMax;
+  // The MV clip (xClipMv) keeps every block within ctu+7 samples of the picture, so with ctu <= 128 all window,
+  // staging-pad and filter-tap reads stay inside VTMME_MIN_MARGIN whatever the search range is.
+  if (prm->ctuSize < 8 || prm->ctuSize > 128)
+    return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search_frames", "ctuSize must be in [8,128]");
+  // rows per band: keep the staged window under ~72 KB so three CTAs fit one SM
+  int bandRows = maxRows;
+  while (bandRows > 16 && tree_sad_smem_bytes(maxGx, bandRows) > 72 * 1024) bandRows = (bandRows + 1) / 2;
+  const size_t surfCap = (size_t) maxGx * 8 * maxRows;
+
+  int rc;
+  if ((rc = ensure(ctx, ctx->dCur, ctx->curArrCap, (size_t) nPairs * sizeof(DevPic))) != VTMME_OK) return rc;
+  if ((rc = ensure(ctx, ctx->dRef, ctx->refArrCap, (size_t) nPairs * sizeof(DevPic))) != VTMME_OK) return rc;
+  if ((rc = ensure(ctx, ctx->dKeys, ctx->keysCap, (size_t) nPairs * nCU * 8)) != VTMME_OK) return rc;
+  if ((rc = ensure(ctx, ctx->dSurf, ctx->surfCapBytes, (size_t) nPairs * nReg * surfCap * 4)) != VTMME_OK) return rc;
+  if ((rc = ensure(ctx, ctx->dRegInfo, ctx->regInfoCap, (size_t) nPairs * nReg * sizeof(int4))) != VTMME_OK) return rc;
+
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dCur, hc.data(), nPairs * sizeof(DevPic), cudaMemcpyHostToDevice, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dRef, hr.data(), nPairs * sizeof(DevPic), cudaMemcpyHostToDevice, ctx->stream));
+  // the pageable staging vectors above must outlive the copies
+  VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  VTMME_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dKeys, 0xff, (size_t) nPairs * nCU * 8, ctx->stream));
+
+  TreeParams tp;
+  tp.g        = g;
+  tp.cur      = ctx->dCur;
+  tp.ref      = ctx->dRef;
+  tp.predQ    = reinterpret_cast<const short2*>(dPredQ);
+  tp.keys     = ctx->dKeys;
+  tp.surf     = ctx->dSurf;
+  tp.regInfo  = ctx->dRegInfo;
+  tp.errFlag  = ctx->dErr;
+  tp.surfCap  = (int) surfCap;
+  tp.maxGx    = maxGx;
+  tp.maxRows  = maxRows;
+  tp.bandRows = bandRows;
+  tp.sr       = prm->searchRange;
+  tp.ctu      = prm->ctuSize;
+  tp.imvShift = prm->imvShift;
+  tp.lambda   = prm->lambdaMotion;
+  VTMME_CUDA_CHECK(ctx, launch_tree_sad(tp, nPairs, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, launch_tree_upper(tp, nPairs, ctx->stream));
+
+  FracFrameParams fp;
+  fp.g        = g;
+  fp.cur      = ctx->dCur;
+  fp.ref      = ctx->dRef;
+  fp.predQ    = reinterpret_cast<const short2*>(dPredQ);
+  fp.keys     = ctx->dKeys;
+  fp.results  = dResults;
+  fp.bitDepth = prm->bitDepth;
+  fp.imvShift = prm->imvShift;
+  fp.useHad   = prm->useHad;
+  fp.fracMode = prm->fracMode;
+  fp.lambda   = prm->lambdaMotion;
+  VTMME_CUDA_CHECK(ctx, launch_frac_frame(fp, nPairs, ctx->stream));
+  ctx->launches += 3;
+  return VTMME_OK;
+}
+
+int vtmme_search_frames(vtmme_ctx* ctx, int nPairs, const int32_t* curPics, const int32_t* refPics,
+                        const vtmme_frame_params* prm, const int16_t* predQ, vtmme_cu_result* results)
+{
+  if (!ctx) return VTMME_ERR_ARG;
+  if (nPairs <= 0 || !curPics || !results) return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search_frames", "null argument");
+  auto a = ctx->pics.find(curPics[0]);
+  if (a == ctx->pics.end()) return vtmme_set_error(ctx, VTMME_ERR_NOPIC, "vtmme_search_frames", "unknown picture id");
+  const int nCU = make_geom(a->second.width, a->second.height).off[5];
+  int       rc;
+  VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  if ((rc = ensure(ctx, ctx->dRes, ctx->resCap, (size_t) nPairs * nCU * sizeof(vtmme_cu_result))) != VTMME_OK) return rc;
+  const int16_t* dPred = nullptr;
+  if (predQ)
+  {
+    if ((rc = ensure(ctx, ctx->dPred, ctx->predCap, (size_t) nPairs * nCU * 4)) != VTMME_OK) return rc;
+    VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dPred, predQ, (size_t) nPairs * nCU * 4, cudaMemcpyHostToDevice, ctx->stream));
+    dPred = ctx->dPred;
+  }
+  rc = vtmme_search_frames_device(ctx, nPairs, curPics, refPics, prm, dPred, ctx->dRes);
+  if (rc != VTMME_OK) return rc;
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(results, ctx->dRes, (size_t) nPairs * nCU * sizeof(vtmme_cu_result),
+                                        cudaMemcpyDeviceToHost, ctx->stream));
+  int flag = 0;
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(&flag, ctx->dErr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (flag)
+  {
+    cudaMemsetAsync(ctx->dErr, 0, sizeof(int), ctx->stream);
+    return vtmme_set_error(ctx, VTMME_ERR_RANGE, "vtmme_search_frames", "predictor spread exceeds params.predSpread");
+  }
+  return VTMME_OK;
+}
+
+}   // extern "C"
+
+// ---- per-call jobs ---------------------------------------------------------------------------------------
+static_assert(sizeof(vtmme_result) == sizeof(DevJobResult), "result layouts must match");
+
+static int ensure_pinned(vtmme_ctx* ctx, size_t bytes)
+{
+  if (bytes <= ctx->hPinnedCap) return VTMME_OK;
+  if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
+  ctx->hPinned    = nullptr;
+  ctx->hPinnedCap = 0;
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return vtmme_set_error(ctx, VTMME_ERR_NOMEM, "cudaMallocHost", "out of pinned host memory");
+  }
+  ctx->hPinned    = reinterpret_cast<unsigned char*>(p);
+  ctx->hPinnedCap = bytes;
+  return VTMME_OK;
+}
+
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t) 255; }
+
+extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_result* results)
+{
+  if (!ctx) return VTMME_ERR_ARG;
+  if (!jobs || !results || n <= 0) return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search", "null argument");
+  VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+
+  // ---- validate, size the buffers
+  size_t orgBytes = 0, surfElems = 0;
+  int    maxGx = 1, maxRegions = 1, maxBands = 1;
+  long long totalRegions = 0;
+  bool   anyMulti = false;
+  for (int i = 0; i < n; i++)
+  {
+    const vtmme_job& j = jobs[i];
+    const bool pow2w = j.w >= 4 && j.w <= 128 && (j.w & (j.w - 1)) == 0;
+    const bool pow2h = j.h >= 4 && j.h <= 128 && (j.h & (j.h - 1)) == 0;
+    if (!pow2w || !pow2h) return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search", "w,h must be powers of two in [4,128]");
+    if (j.srRight < j.srLeft || j.srBottom < j.srTop || j.srRight - j.srLeft > 1024 || j.srBottom - j.srTop > 1024)
+      return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search", "bad search range");
+    if (j.bitDepth < 8 || j.bitDepth > 10 || j.subShift < 0 || j.subShift > 4 || (j.h >> j.subShift) < 1)
+      return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search", "unsupported bitDepth / subShift");
+    if (ctx->pics.find(j.refPic) == ctx->pics.end() || (!j.org && ctx->pics.find(j.curPic) == ctx->pics.end()))
+      return vtmme_set_error(ctx, VTMME_ERR_NOPIC, "vtmme_search", "unknown picture id");
+    const DevPic& rp = ctx->pics[j.refPic];
+    // every read (window + pattern + 8-tap halo + staging pad) must stay inside the device margin
+    if (j.x + j.srLeft - 24 < -rp.margin || j.x + j.w + j.srRight + 24 > rp.width + rp.margin ||
+        j.y + j.srTop - 8 < -rp.margin || j.y + j.h + j.srBottom + 8 > rp.height + rp.margin)
+      return vtmme_set_error(ctx, VTMME_ERR_RANGE, "vtmme_search", "search window leaves the padded reference picture");
+    if (j.org) orgBytes += align256((size_t) j.w * j.h * 2);
+    const int wl8 = j.srLeft & ~7;
+    const int ngx = (j.srRight - wl8 + 8) >> 3, nrows = j.srBottom - j.srTop + 1;
+    const int nReg = ((j.w + 31) >> 5) * ((j.h + 31) >> 5);
+    maxGx      = ngx > maxGx ? ngx : maxGx;
+    maxRegions = nReg > maxRegions ? nReg : maxRegions;
+    maxBands   = (nrows + 31) / 32 > maxBands ? (nrows + 31) / 32 : maxBands;
+    totalRegions += nReg;
+    if (nReg > 1)
+    {
+      anyMulti = true;
+      surfElems += (size_t) nReg * nrows * ngx * 8;
+    }
+  }
+  int nSplit = (int) ((4 * 148 + totalRegions - 1) / totalRegions);
+  nSplit     = nSplit < 1 ? 1 : (nSplit > maxBands ? maxBands : nSplit);
+
+  // ---- one pinned staging block, one device block: [jobs][surfOff][patterns] + [keys][results]
+  const size_t offJobs = 0, offSurfOff = align256(offJobs + (size_t) n * sizeof(DevJob));
+  const size_t offOrg = align256(offSurfOff + (size_t) n * sizeof(long long));
+  const size_t upBytes = offOrg + orgBytes;
+  const size_t offKeys = align256(upBytes), offRes = align256(offKeys + (size_t) n * 8);
+  const size_t devBytes = offRes + (size_t) n * sizeof(DevJobResult);
+  int rc;
+  if ((rc = ensure_pinned(ctx, devBytes)) != VTMME_OK) return rc;
+  if ((rc = ensure(ctx, ctx->dJobBuf, ctx->jobBufCap, devBytes)) != VTMME_OK) return rc;
+  if (anyMulti && (rc = ensure(ctx, ctx->dJobSurf, ctx->jobSurfCap, surfElems * 4)) != VTMME_OK) return rc;
+
+  DevJob*    hj   = reinterpret_cast<DevJob*>(ctx->hPinned + offJobs);
+  long long* hoff = reinterpret_cast<long long*>(ctx->hPinned + offSurfOff);
+  size_t     orgCur = offOrg, surfCur = 0;
+  for (int i = 0; i < n; i++)
+  {
+    const vtmme_job& j  = jobs[i];
+    const DevPic&    rp = ctx->pics[j.refPic];
+    DevJob           d;
+    if (j.org)
+    {
+      int16_t* dst = reinterpret_cast<int16_t*>(ctx->hPinned + orgCur);
+      for (int y = 0; y < j.h; y++) memcpy(dst + (size_t) y * j.w, j.org + (size_t) y * j.orgStride, (size_t) j.w * 2);
+      d.org       = reinterpret_cast<const int16_t*>(ctx->dJobBuf + orgCur);
+      d.orgStride = j.w;
+      orgCur += align256((size_t) j.w * j.h * 2);
+    }
+    else
+    {
+      const DevPic& cp = ctx->pics[j.curPic];
+      d.org       = cp.origin + (ptrdiff_t) j.y * cp.stride + j.x;
+      d.orgStride = cp.stride;
+    }
+    d.refAtPU   = rp.origin + (ptrdiff_t) j.y * rp.stride + j.x;
+    d.refStride = rp.stride;
+    d.w = j.w;
+    d.h = j.h;
+    d.l = j.srLeft;
+    d.r = j.srRight;
+    d.t = j.srTop;
+    d.b = j.srBottom;
+    d.predQx = j.predQx;
+    d.predQy = j.predQy;
+    d.imvShift = j.imvShift;
+    d.subShift = j.subShift;
+    d.bitDepth = j.bitDepth;
+    d.useHad = j.useHad;
+    d.useAltHpel = j.useAltHpel;
+    d.fracMode = j.fracMode;
+    d.signedOrg = j.org != nullptr;
+    d.lambda = j.lambdaMotion;
+    hj[i]   = d;
+    hoff[i] = (long long) surfCur;
+    const int nReg = ((j.w + 31) >> 5) * ((j.h + 31) >> 5);
+    if (nReg > 1)
+    {
+      const int wl8 = j.srLeft & ~7;
+      surfCur += (size_t) nReg * (j.srBottom - j.srTop + 1) * (((j.srRight - wl8 + 8) >> 3) * 8);
+    }
+  }
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dJobBuf, ctx->hPinned, upBytes, cudaMemcpyHostToDevice, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dJobBuf + offKeys, 0xff, (size_t) n * 8, ctx->stream));
+  int launches = 0;
+  VTMME_CUDA_CHECK(ctx, launch_job_search_impl(reinterpret_cast<const DevJob*>(ctx->dJobBuf + offJobs),
+                                               reinterpret_cast<unsigned long long*>(ctx->dJobBuf + offKeys),
+                                               reinterpret_cast<DevJobResult*>(ctx->dJobBuf + offRes), n, maxRegions,
+                                               nSplit, maxGx, anyMulti, ctx->dJobSurf,
+                                               reinterpret_cast<const long long*>(ctx->dJobBuf + offSurfOff),
+                                               ctx->stream, &launches));
+  ctx->launches += launches;
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->hPinned + offRes, ctx->dJobBuf + offRes, (size_t) n * sizeof(DevJobResult),
+                                        cudaMemcpyDeviceToHost, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(results, ctx->hPinned + offRes, (size_t) n * sizeof(vtmme_result));
+  return VTMME_OK;
+}
+
+// ---- table-level entry points -------------------------------------------------------------------------------
+extern "C" int vtmme_dist_batch(vtmme_ctx* ctx, int kind, const int16_t* dOrg, int orgStride, int64_t orgBlockStride,
+                                const int16_t* dCur, int curStride, int64_t curBlockStride, int w, int h, int subShift,
+                                int n, uint64_t* dOut)
+{
+  if (!ctx) return VTMME_ERR_ARG;
+  if (!dOrg || !dCur || !dOut || n <= 0 || w < 2 || h < 2 || w > 128 || h > 128 || (w & 1) || (h & 1) || kind < 0 ||
+      kind > 1 || subShift < 0 || (h >> subShift) < 1)
+    return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_dist_batch", "bad argument");
+  VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  VTMME_CUDA_CHECK(ctx, launch_dist_batch(kind, dOrg, orgStride, orgBlockStride, dCur, curStride, curBlockStride, w, h,
+                                          kind == 0 ? subShift : 0, n, reinterpret_cast<unsigned long long*>(dOut),
+                                          ctx->stream));
+  ctx->launches += 1;
+  return VTMME_OK;
+}
+
+extern "C" int vtmme_dist_host(vtmme_ctx* ctx, int kind, const int16_t* org, int orgStride, const int16_t* cur,
+                               int curStride, int w, int h, int subShift, uint64_t* out)
+{
+  if (!ctx) return VTMME_ERR_ARG;
+  if (!org || !cur || !out || w < 2 || h < 2 || w > 128 || h > 128)
+    return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_dist_host", "bad argument");
+  VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  const size_t blk = align256((size_t) w * h * 2);
+  int          rc;
+  if ((rc = ensure_pinned(ctx, 2 * blk + 256)) != VTMME_OK) return rc;
+  if ((rc = ensure(ctx, ctx->dJobBuf, ctx->jobBufCap, 2 * blk + 256)) != VTMME_OK) return rc;
+  int16_t* ho = reinterpret_cast<int16_t*>(ctx->hPinned);
+  int16_t* hc = reinterpret_cast<int16_t*>(ctx->hPinned + blk);
+  for (int y = 0; y < h; y++)
+  {
+    memcpy(ho + (size_t) y * w, org + (size_t) y * orgStride, (size_t) w * 2);
+    memcpy(hc + (size_t) y * w, cur + (size_t) y * curStride, (size_t) w * 2);
+  }
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dJobBuf, ctx->hPinned, 2 * blk, cudaMemcpyHostToDevice, ctx->stream));
+  rc = vtmme_dist_batch(ctx, kind, reinterpret_cast<int16_t*>(ctx->dJobBuf), w, 0,
+                        reinterpret_cast<int16_t*>(ctx->dJobBuf + blk), w, 0, w, h, subShift, 1,
+                        reinterpret_cast<uint64_t*>(ctx->dJobBuf + 2 * blk));
+  if (rc != VTMME_OK) return rc;
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->hPinned + 2 * blk, ctx->dJobBuf + 2 * blk, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  *out = *reinterpret_cast<uint64_t*>(ctx->hPinned + 2 * blk);
+  return VTMME_OK;
+}
+
+static int interp_args_ok(int comp, int w, int h, int frac, int bitDepth)
+{
+  if (comp < 0 || comp > 1 || w < 1 || h < 1 || w > 256 || h > 256 || bitDepth < 8 || bitDepth > 10) return 0;
+  if (frac < 0 || frac >= (comp == 0 ? 16 : 32)) return 0;
+  return 1;
+}
+
+extern "C" int vtmme_interp_batch(vtmme_ctx* ctx, int comp, int vertical, const int16_t* dSrc, int srcStride,
+                                  int64_t srcBlockStride, int16_t* dDst, int dstStride, int64_t dstBlockStride, int w,
+                                  int h, int frac, int isFirst, int isLast, int bitDepth, int useAltHpel, int n)
+{
+  if (!ctx) return VTMME_ERR_ARG;
+  if (!dSrc || !dDst || n <= 0 || !interp_args_ok(comp, w, h, frac, bitDepth))
+    return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_interp_batch", "bad argument");
+  VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  VTMME_CUDA_CHECK(ctx, launch_interp_batch(comp, vertical, dSrc, srcStride, srcBlockStride, dDst, dstStride,
+                                            dstBlockStride, w, h, frac, isFirst, isLast, bitDepth, useAltHpel, n,
+                                            ctx->stream));
+  ctx->launches += 1;
+  return VTMME_OK;
+}
+
+extern "C" int vtmme_interp_host(vtmme_ctx* ctx, int comp, int vertical, const int16_t* src, int srcStride, int16_t* dst,
+                                 int dstStride, int w, int h, int frac, int isFirst, int isLast, int bitDepth,
+                                 int useAltHpel)
+{
+  if (!ctx) return VTMME_ERR_ARG;
+  if (!src || !dst || !interp_args_ok(comp, w, h, frac, bitDepth))
+    return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_interp_host", "bad argument");
+  VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  // source halo: (N/2-1) samples before and N/2 after along the filtered direction
+  const int taps = comp == 0 ? 8 : 4, before = taps / 2 - 1, after = taps / 2;
+  const int sw = w + (vertical ? 0 : before + after), sh = h + (vertical ? before + after : 0);
+  const size_t srcBytes = align256((size_t) sw * sh * 2), dstBytes = align256((size_t) w * h * 2);
+  int rc;
+  if ((rc = ensure_pinned(ctx, srcBytes + dstBytes)) != VTMME_OK) return rc;
+  if ((rc = ensure(ctx, ctx->dJobBuf, ctx->jobBufCap, srcBytes + dstBytes)) != VTMME_OK) return rc;
+  int16_t*       hs = reinterpret_cast<int16_t*>(ctx->hPinned);
+  const int16_t* s0 = src - (vertical ? (ptrdiff_t) before * srcStride : before);
+  for (int y = 0; y < sh; y++) memcpy(hs + (size_t) y * sw, s0 + (ptrdiff_t) y * srcStride, (size_t) sw * 2);
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dJobBuf, ctx->hPinned, srcBytes, cudaMemcpyHostToDevice, ctx->stream));
+  const int16_t* dsrc = reinterpret_cast<int16_t*>(ctx->dJobBuf) + (vertical ? (size_t) before * sw : before);
+  rc = vtmme_interp_batch(ctx, comp, vertical, dsrc, sw, 0, reinterpret_cast<int16_t*>(ctx->dJobBuf + srcBytes), w, 0, w, h,
+                          frac, isFirst, isLast, bitDepth, useAltHpel, 1);
+  if (rc != VTMME_OK) return rc;
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->hPinned + srcBytes, ctx->dJobBuf + srcBytes, (size_t) w * h * 2,
+                                        cudaMemcpyDeviceToHost, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  const int16_t* hd = reinterpret_cast<int16_t*>(ctx->hPinned + srcBytes);
+  for (int y = 0; y < h; y++) memcpy(dst + (size_t) y * dstStride, hd + (size_t) y * w, (size_t) w * 2);
+  return VTMME_OK;
+}

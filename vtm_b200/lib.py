@@ -1,0 +1,96 @@
+"""ctypes binding of libvtmme.so (include/vtmme.h).  Fails loudly when the library is missing."""
+import ctypes as C
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+class VtmmeError(RuntimeError):
+    pass
+
+
+ERR_NAMES = {0: "VTMME_OK", -1: "VTMME_ERR_CUDA", -2: "VTMME_ERR_ARG", -3: "VTMME_ERR_NOMEM",
+             -4: "VTMME_ERR_NOPIC", -5: "VTMME_ERR_RANGE"}
+
+# every symbol include/vtmme.h declares (tests check the built library exports all of them)
+SYMBOLS = ["vtmme_create", "vtmme_destroy", "vtmme_last_error", "vtmme_set_stream", "vtmme_synchronize",
+           "vtmme_launch_count", "vtmme_upload_picture", "vtmme_upload_picture_device", "vtmme_release_picture",
+           "vtmme_search", "vtmme_frame_cu_count", "vtmme_search_frames", "vtmme_search_frames_device",
+           "vtmme_dist_batch", "vtmme_dist_host", "vtmme_interp_batch", "vtmme_interp_host", "vtmme_int_peak"]
+
+
+class CJob(C.Structure):
+    """vtmme_job"""
+    _fields_ = [("curPic", C.c_int32), ("refPic", C.c_int32), ("x", C.c_int32), ("y", C.c_int32),
+                ("w", C.c_int32), ("h", C.c_int32), ("org", C.c_void_p), ("orgStride", C.c_int32),
+                ("srLeft", C.c_int32), ("srRight", C.c_int32), ("srTop", C.c_int32), ("srBottom", C.c_int32),
+                ("predQx", C.c_int32), ("predQy", C.c_int32), ("imvShift", C.c_int32), ("subShift", C.c_int32),
+                ("bitDepth", C.c_int32), ("useHad", C.c_int32), ("useAltHpel", C.c_int32), ("fracMode", C.c_int32),
+                ("lambdaMotion", C.c_double)]
+
+
+class CResult(C.Structure):
+    """vtmme_result"""
+    _fields_ = [("mvX", C.c_int32), ("mvY", C.c_int32), ("intSad", C.c_uint64),
+                ("halfX", C.c_int32), ("halfY", C.c_int32), ("qterX", C.c_int32), ("qterY", C.c_int32),
+                ("fracCost", C.c_uint64)]
+
+    def tuple(self):
+        return (self.mvX, self.mvY, self.intSad, self.halfX, self.halfY, self.qterX, self.qterY, self.fracCost)
+
+
+class CFrameParams(C.Structure):
+    """vtmme_frame_params"""
+    _fields_ = [("searchRange", C.c_int32), ("bitDepth", C.c_int32), ("ctuSize", C.c_int32), ("imvShift", C.c_int32),
+                ("useHad", C.c_int32), ("fracMode", C.c_int32), ("predSpread", C.c_int32), ("reserved", C.c_int32),
+                ("lambdaMotion", C.c_double)]
+
+
+def library_path():
+    return os.path.join(HERE, "libvtmme.so")
+
+
+def build_library(jobs=8):
+    """Compile every CUDA source for sm_100a into vtm_b200/libvtmme.so (nvcc cross-compiles without a GPU)."""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "csrc"), "-j%d" % jobs])
+    return library_path()
+
+
+_lib = None
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise VtmmeError("libvtmme.so is not built (%s): run `make -C vtm_b200/csrc` or __graft_entry__.build(); "
+                         "there is no CPU fallback for the motion-search path" % path)
+    L = C.CDLL(path)
+    P, I, I64 = C.c_void_p, C.c_int, C.c_int64
+    L.vtmme_create.argtypes = [I, C.POINTER(P)]
+    L.vtmme_destroy.argtypes = [P]
+    L.vtmme_destroy.restype = None
+    L.vtmme_last_error.argtypes = [P]
+    L.vtmme_last_error.restype = C.c_char_p
+    L.vtmme_set_stream.argtypes = [P, P]
+    L.vtmme_synchronize.argtypes = [P]
+    L.vtmme_launch_count.argtypes = [P]
+    L.vtmme_launch_count.restype = C.c_uint64
+    L.vtmme_upload_picture.argtypes = [P, I, P, I, I, I, I, I]
+    L.vtmme_upload_picture_device.argtypes = [P, I, P, I, I, I, I, I]
+    L.vtmme_release_picture.argtypes = [P, I]
+    L.vtmme_search.argtypes = [P, C.POINTER(CJob), I, C.POINTER(CResult)]
+    L.vtmme_frame_cu_count.argtypes = [I, I, C.POINTER(C.c_int32)]
+    L.vtmme_search_frames.argtypes = [P, I, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(CFrameParams), P, P]
+    L.vtmme_search_frames_device.argtypes = [P, I, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(CFrameParams), P, P]
+    L.vtmme_dist_batch.argtypes = [P, I, P, I, I64, P, I, I64, I, I, I, I, P]
+    L.vtmme_dist_host.argtypes = [P, I, P, I, P, I, I, I, I, C.POINTER(C.c_uint64)]
+    L.vtmme_interp_batch.argtypes = [P, I, I, P, I, I64, P, I, I64, I, I, I, I, I, I, I, I]
+    L.vtmme_interp_host.argtypes = [P, I, I, P, I, P, I, I, I, I, I, I, I, I]
+    L.vtmme_int_peak.argtypes = [I, I, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    _lib = L
+    return L

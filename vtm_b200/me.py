@@ -1,0 +1,205 @@
+"""Host-side mirror of the reference's motion-search interface over the C ABI (include/vtmme.h).
+
+Names follow the reference: a *picture* is a luma plane with border (Picture::getRecoBuf), a *job* is one
+xMotionEstimation call's integer search + fractional refinement (IntTZSearchStruct / DistParam fields),
+the frame search covers the quad-tree of square CUs of every CTU.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from .lib import CFrameParams, CJob, CResult, ERR_NAMES, VtmmeError, load_library
+
+# vtmme_cu_result
+CU_RESULT_DTYPE = np.dtype([("mvQx", "<i2"), ("mvQy", "<i2"), ("intX", "<i2"), ("intY", "<i2"),
+                            ("intSad", "<u4"), ("fracCost", "<u4")])
+
+
+@dataclass
+class FrameParams:
+    searchRange: int = 64
+    bitDepth: int = 10
+    ctuSize: int = 128
+    imvShift: int = 0
+    useHad: int = 1
+    fracMode: int = 1
+    predSpread: int = 0
+    lambdaMotion: float = 31.33
+
+    def c(self):
+        return CFrameParams(self.searchRange, self.bitDepth, self.ctuSize, self.imvShift, self.useHad, self.fracMode,
+                            self.predSpread, 0, self.lambdaMotion)
+
+
+@dataclass
+class Job:
+    """One xMotionEstimation search: fields of IntTZSearchStruct / DistParam (EncoderLib/InterSearch.h:337-352)."""
+    curPic: int
+    refPic: int
+    x: int
+    y: int
+    w: int
+    h: int
+    sr: tuple                 # (left, right, top, bottom), integer pel, inclusive
+    predQ: tuple              # quarter-pel predictor
+    imvShift: int = 0
+    subShift: int = 0
+    bitDepth: int = 10
+    useHad: int = 1
+    useAltHpel: int = 0
+    fracMode: int = 1
+    lambdaMotion: float = 31.33
+    org: np.ndarray = None    # optional int16 pattern override (bi-pred)
+
+
+def frame_cu_layout(width, height):
+    """CU order of the frame search: (total, level offsets[6]); level l = CUs of size 8<<l in raster order."""
+    off, acc = [], 0
+    for l in range(5):
+        s = 8 << l
+        off.append(acc)
+        acc += (width // s) * (height // s)
+    off.append(acc)
+    return acc, off
+
+
+class MotionSearch:
+    """One libvtmme context on one GPU."""
+
+    def __init__(self, device=0):
+        self.L = load_library()
+        self.ctx = C.c_void_p()
+        rc = self.L.vtmme_create(int(device), C.byref(self.ctx))
+        if rc != 0:
+            raise VtmmeError("vtmme_create(device=%d) failed: %s (no CUDA device? there is no CPU fallback)"
+                             % (device, ERR_NAMES.get(rc, rc)))
+        self.device = device
+
+    def close(self):
+        if self.ctx:
+            self.L.vtmme_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise VtmmeError("%s failed: %s: %s" % (what, ERR_NAMES.get(rc, rc),
+                                                     self.L.vtmme_last_error(self.ctx).decode()))
+
+    # ---- stream / sync -------------------------------------------------------------------------------------
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.L.vtmme_set_stream(self.ctx, C.c_void_p(cuda_stream_ptr)), "vtmme_set_stream")
+
+    def synchronize(self):
+        self._check(self.L.vtmme_synchronize(self.ctx), "vtmme_synchronize")
+
+    @property
+    def launches(self):
+        return int(self.L.vtmme_launch_count(self.ctx))
+
+    # ---- pictures ------------------------------------------------------------------------------------------
+    def upload_picture(self, pic_id, plane, margin=0):
+        """plane: int16 array [height + 2*margin, width + 2*margin] (margin = valid border it already carries)."""
+        assert plane.dtype == np.int16 and plane.ndim == 2 and plane.flags["C_CONTIGUOUS"]
+        h, w = plane.shape[0] - 2 * margin, plane.shape[1] - 2 * margin
+        origin = plane.ctypes.data + 2 * (margin * plane.shape[1] + margin)
+        self._check(self.L.vtmme_upload_picture(self.ctx, pic_id, C.c_void_p(origin), plane.shape[1], w, h, margin,
+                                                1 if margin else 0), "vtmme_upload_picture")
+
+    def upload_picture_device(self, pic_id, dptr, stride, width, height, margin=0):
+        """dptr: device address of sample (0,0) of an int16 plane (e.g. a torch tensor's data_ptr())."""
+        self._check(self.L.vtmme_upload_picture_device(self.ctx, pic_id, C.c_void_p(dptr), stride, width, height,
+                                                       margin, 1 if margin else 0), "vtmme_upload_picture_device")
+
+    def release_picture(self, pic_id):
+        self._check(self.L.vtmme_release_picture(self.ctx, pic_id), "vtmme_release_picture")
+
+    # ---- per-call jobs ---------------------------------------------------------------------------------------
+    def search(self, jobs):
+        n = len(jobs)
+        cj = (CJob * n)()
+        keep = []
+        for i, j in enumerate(jobs):
+            org_ptr, org_stride = None, 0
+            if j.org is not None:
+                o = np.ascontiguousarray(j.org, dtype=np.int16)
+                keep.append(o)
+                org_ptr, org_stride = o.ctypes.data, o.shape[1]
+            cj[i] = CJob(j.curPic, j.refPic, j.x, j.y, j.w, j.h, org_ptr, org_stride, j.sr[0], j.sr[1], j.sr[2],
+                         j.sr[3], j.predQ[0], j.predQ[1], j.imvShift, j.subShift, j.bitDepth, j.useHad, j.useAltHpel,
+                         j.fracMode, j.lambdaMotion)
+        res = (CResult * n)()
+        self._check(self.L.vtmme_search(self.ctx, cj, n, res), "vtmme_search")
+        return [r.tuple() for r in res]
+
+    # ---- batched frame search --------------------------------------------------------------------------------
+    def search_frames(self, cur_ids, ref_ids, params, pred_q=None):
+        """Host buffers.  pred_q: int16 [nPairs, nCU, 2] or None.  Returns a structured array [nPairs, nCU]."""
+        n = len(cur_ids)
+        cur = (C.c_int32 * n)(*cur_ids)
+        ref = (C.c_int32 * n)(*ref_ids)
+        prm = params.c()
+        ncu = self._ncu
+        out = np.zeros((n, ncu), dtype=CU_RESULT_DTYPE)
+        pp = None
+        if pred_q is not None:
+            pred_q = np.ascontiguousarray(pred_q, dtype=np.int16)
+            assert pred_q.shape == (n, ncu, 2)
+            pp = C.c_void_p(pred_q.ctypes.data)
+        self._check(self.L.vtmme_search_frames(self.ctx, n, cur, ref, C.byref(prm), pp, C.c_void_p(out.ctypes.data)),
+                    "vtmme_search_frames")
+        return out
+
+    def search_frames_device(self, cur_ids, ref_ids, params, d_pred_q, d_results):
+        """Device buffers (addresses), asynchronous on the context stream."""
+        n = len(cur_ids)
+        cur = (C.c_int32 * n)(*cur_ids)
+        ref = (C.c_int32 * n)(*ref_ids)
+        prm = params.c()
+        self._check(self.L.vtmme_search_frames_device(self.ctx, n, cur, ref, C.byref(prm),
+                                                      C.c_void_p(d_pred_q) if d_pred_q else None,
+                                                      C.c_void_p(d_results)), "vtmme_search_frames_device")
+
+    def set_frame_size(self, width, height):
+        self._ncu, self._off = frame_cu_layout(width, height)
+        lo = (C.c_int32 * 6)()
+        n = self.L.vtmme_frame_cu_count(width, height, lo)
+        assert n == self._ncu and list(lo) == self._off
+        return self._ncu
+
+    # ---- table-level ---------------------------------------------------------------------------------------
+    def dist_host(self, kind, org, cur, sub_shift=0):
+        """One block pair in host memory (the DistParam-hook flavour).  org, cur: int16 2-D arrays (views ok)."""
+        assert org.dtype == np.int16 and cur.dtype == np.int16
+        h, w = org.shape
+        out = C.c_uint64()
+        self._check(self.L.vtmme_dist_host(self.ctx, kind, C.c_void_p(org.ctypes.data), org.strides[0] // 2,
+                                           C.c_void_p(cur.ctypes.data), cur.strides[0] // 2, w, h, sub_shift,
+                                           C.byref(out)), "vtmme_dist_host")
+        return out.value
+
+    def dist_batch(self, kind, d_org, org_stride, org_blk, d_cur, cur_stride, cur_blk, w, h, sub_shift, n, d_out):
+        self._check(self.L.vtmme_dist_batch(self.ctx, kind, C.c_void_p(d_org), org_stride, org_blk, C.c_void_p(d_cur),
+                                            cur_stride, cur_blk, w, h, sub_shift, n, C.c_void_p(d_out)),
+                    "vtmme_dist_batch")
+
+    def interp_host(self, comp, vertical, src, src_off, src_stride, w, h, frac, is_first, is_last, bit_depth=10,
+                    use_alt_hpel=0):
+        """src: int16 array, src_off: element offset of the first output position.  Returns int16 [h, w]."""
+        dst = np.zeros((h, w), np.int16)
+        self._check(self.L.vtmme_interp_host(self.ctx, comp, vertical, C.c_void_p(src.ctypes.data + 2 * src_off),
+                                             src_stride, C.c_void_p(dst.ctypes.data), w, w, h, frac, is_first, is_last,
+                                             bit_depth, use_alt_hpel), "vtmme_interp_host")
+        return dst
+
+    def interp_batch(self, comp, vertical, d_src, src_stride, src_blk, d_dst, dst_stride, dst_blk, w, h, frac, is_first,
+                     is_last, bit_depth, use_alt_hpel, n):
+        self._check(self.L.vtmme_interp_batch(self.ctx, comp, vertical, C.c_void_p(d_src), src_stride, src_blk,
+                                              C.c_void_p(d_dst), dst_stride, dst_blk, w, h, frac, is_first, is_last,
+                                              bit_depth, use_alt_hpel, n), "vtmme_interp_batch")
