@@ -161,7 +161,15 @@ int vtmme_interp_batch(vtmme_ctx* ctx, int comp, int vertical, const int16_t* dS
 int vtmme_interp_host(vtmme_ctx* ctx, int comp, int vertical, const int16_t* src, int srcStride, int16_t* dst,
                       int dstStride, int w, int h, int frac, int isFirst, int isLast, int bitDepth, int useAltHpel);
 
-/* ---- measurement helper -------------------------------------------------------------------------
+/* ---- measurement helpers ------------------------------------------------------------------------
+ * Per-kernel timing of the frame path: when enabled, vtmme_search_frames[_device] brackets each of its
+ * kernels with CUDA events on the context stream; vtmme_frame_kernel_ms returns the durations of the most
+ * recent call, in launch order: [0] me_tree_sad (8/16/32 levels), [1] me_tree_upper (64/128), [2] me_frac_frame.
+ * It synchronises the stream. */
+int vtmme_set_profiling(vtmme_ctx* ctx, int enable);
+int vtmme_frame_kernel_ms(vtmme_ctx* ctx, float ms[3]);
+
+/* ------------------------------------------------------------------------------------------------
  * Issue-rate microbenchmark of one instruction class on the current device (roofline denominator of
  * the integer search).  variant: see vtm_b200/peaks.py. */
 int vtmme_int_peak(int variant, int iters, double* laneInstrPerClkPerSm, double* ms, double* smClockMHz);

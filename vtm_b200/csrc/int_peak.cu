@@ -34,6 +34,8 @@ __global__ void __launch_bounds__(256) peak_kernel(const uint32_t* __restrict__ 
 #pragma unroll
   for (int i = 0; i < kUnroll; i++) facc[i] = __uint_as_float(acc[i] >> 3);
 
+  unsigned long long g0 = 0;
+  if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
   const long long t0 = clock64();
   for (int it = 0; it < iters; it++)
   {
@@ -88,7 +90,13 @@ __global__ void __launch_bounds__(256) peak_kernel(const uint32_t* __restrict__ 
 #pragma unroll
   for (int i = 0; i < kUnroll; i++) r += acc[i] + __float_as_uint(facc[i]);
   out[blockIdx.x * blockDim.x + threadIdx.x] = r;
-  if (threadIdx.x == 0) clk[blockIdx.x] = (unsigned long long) (t1 - t0);
+  if (threadIdx.x == 0)
+  {
+    unsigned long long g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    clk[2 * blockIdx.x]     = (unsigned long long) (t1 - t0);   // SM cycles of this CTA's span
+    clk[2 * blockIdx.x + 1] = g1 - g0;                          // nanoseconds of the same span
+  }
 }
 
 // instructions per accumulator-slot per iteration (for the rate computation)
@@ -107,7 +115,7 @@ __host__ double instr_per_slot(int v)
 
 template <int V>
 int run_variant(int iters, int sms, const uint32_t* din, uint32_t* dout, unsigned long long* dclk, double* laneRate,
-                double* ms, cudaStream_t st)
+                double* ms, double* mhzOut, cudaStream_t st)
 {
   const int   grid = sms * 8;
   cudaEvent_t e0, e1;
@@ -123,15 +131,23 @@ int run_variant(int iters, int sms, const uint32_t* din, uint32_t* dout, unsigne
   cudaEventElapsedTime(&t, e0, e1);
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  unsigned long long hclk[8];
+  // SM clock = cycles / nanoseconds of CTA spans (averaged over the first 64 CTAs); the kernel's cycle count is
+  // its event-timed duration at that clock.  (CTA spans themselves are useless for the rate: the scheduler runs
+  // co-resident CTAs greedily, one after the other.)
+  unsigned long long hclk[128];
   cudaMemcpy(hclk, dclk, sizeof(hclk), cudaMemcpyDeviceToHost);
-  double cyc = 0;
-  for (int i = 0; i < 8; i++) cyc += (double) hclk[i];
-  cyc /= 8.0;
-  // one CTA's span in cycles covers 8 co-resident CTAs' work on that SM (grid = 8 CTAs/SM, one wave)
+  double cyc = 0, ns = 0;
+  for (int i = 0; i < 64; i++)
+  {
+    cyc += (double) hclk[2 * i];
+    ns += (double) hclk[2 * i + 1];
+  }
+  const double mhz           = ns > 0 ? cyc / ns * 1e3 : 0.0;
+  const double kernelCycles  = (double) t * 1e-3 * mhz * 1e6;
   const double laneInstrPerSm = 8.0 * 256.0 * (double) iters * kUnroll * instr_per_slot(V);
-  *laneRate = laneInstrPerSm / cyc;
+  *laneRate = kernelCycles > 0 ? laneInstrPerSm / kernelCycles : 0.0;
   *ms       = t;
+  *mhzOut   = mhz;
   return 0;
 }
 
@@ -148,7 +164,7 @@ extern "C" int vtmme_int_peak(int variant, int iters, double* laneInstrPerClkPer
   unsigned long long* dclk = nullptr;
   cudaMalloc(&din, 1024 * 4);
   cudaMalloc(&dout, (size_t) sms * 8 * 256 * 4);
-  cudaMalloc(&dclk, (size_t) sms * 8 * 8);
+  cudaMalloc(&dclk, (size_t) sms * 8 * 16);
   uint32_t h[1024];
   for (int i = 0; i < 1024; i++) h[i] = (uint32_t) ((i * 2654435761u) >> 22);   // 10-bit values
   cudaMemcpy(din, h, sizeof(h), cudaMemcpyHostToDevice);
@@ -157,27 +173,11 @@ extern "C" int vtmme_int_peak(int variant, int iters, double* laneInstrPerClkPer
   int rc = -1;
   switch (variant)
   {
-#define CASE(V) case V: rc = run_variant<V>(iters, sms, din, dout, dclk, laneInstrPerClkPerSm, ms, st); break;
+#define CASE(V) case V: rc = run_variant<V>(iters, sms, din, dout, dclk, laneInstrPerClkPerSm, ms, smClockMHz, st); break;
     CASE(V_VABSDIFF) CASE(V_IADD3) CASE(V_IMAD) CASE(V_LOP3) CASE(V_PRMT) CASE(V_VABSDIFF_IMAD) CASE(V_FADD_ABS)
     CASE(V_VABSDIFF_FADD) CASE(V_VIADD16X2) CASE(V_VIADDMNMX16X2) CASE(V_VABSDIFF4) CASE(V_VABSDIFF_FADD2)
 #undef CASE
     default: rc = -2;
-  }
-  if (rc == 0)
-  {
-    // clocks: lane-instr / (ms * sms * rate) -> MHz the SMs ran at
-    const double total = *laneInstrPerClkPerSm;   // per clk per SM
-    const double laneInstr = 8.0 * 256.0 * (double) iters * kUnroll;
-    (void) laneInstr;
-    (void) total;
-    *smClockMHz = 0.0;
-    if (*ms > 0)
-    {
-      // cycles of one CTA span / elapsed time
-      unsigned long long hclk0 = 0;
-      cudaMemcpy(&hclk0, dclk, 8, cudaMemcpyDeviceToHost);
-      *smClockMHz = (double) hclk0 / (*ms * 1e3);
-    }
   }
   cudaStreamDestroy(st);
   cudaFree(din);

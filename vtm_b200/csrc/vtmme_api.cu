@@ -43,6 +43,10 @@ struct vtmme_ctx
   size_t         hPinnedCap = 0;
   uint32_t*      dJobSurf = nullptr;
   size_t         jobSurfCap = 0;
+
+  bool        profiling = false;
+  cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+  bool        evValid = false;
 };
 
 int vtmme_set_error(vtmme_ctx* ctx, int code, const char* what, const char* detail)
@@ -178,6 +182,8 @@ void vtmme_destroy(vtmme_ctx* ctx)
   cudaFree(ctx->dJobBuf);
   cudaFree(ctx->dJobSurf);
   if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
+  for (int i = 0; i < 4; i++)
+    if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   cudaStreamDestroy(ctx->ownStream);
   delete ctx;
 }
@@ -199,6 +205,26 @@ int vtmme_synchronize(vtmme_ctx* ctx)
 }
 
 uint64_t vtmme_launch_count(const vtmme_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int vtmme_set_profiling(vtmme_ctx* ctx, int enable)
+{
+  if (!ctx) return VTMME_ERR_ARG;
+  VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  if (enable && !ctx->ev[0])
+    for (int i = 0; i < 4; i++) VTMME_CUDA_CHECK(ctx, cudaEventCreate(&ctx->ev[i]));
+  ctx->profiling = enable != 0;
+  ctx->evValid   = false;
+  return VTMME_OK;
+}
+
+int vtmme_frame_kernel_ms(vtmme_ctx* ctx, float ms[3])
+{
+  if (!ctx || !ms) return VTMME_ERR_ARG;
+  if (!ctx->evValid) return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_frame_kernel_ms", "no profiled frame search yet");
+  VTMME_CUDA_CHECK(ctx, cudaEventSynchronize(ctx->ev[3]));
+  for (int i = 0; i < 3; i++) VTMME_CUDA_CHECK(ctx, cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]));
+  return VTMME_OK;
+}
 
 int vtmme_upload_picture(vtmme_ctx* ctx, int picId, const int16_t* origin, int stride, int width, int height,
                          int margin, int withBorder)
@@ -302,8 +328,12 @@ int vtmme_search_frames_device(vtmme_ctx* ctx, int nPairs, const int32_t* curPic
   tp.ctu      = prm->ctuSize;
   tp.imvShift = prm->imvShift;
   tp.lambda   = prm->lambdaMotion;
+  const bool prof = ctx->profiling;
+  if (prof) VTMME_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
   VTMME_CUDA_CHECK(ctx, launch_tree_sad(tp, nPairs, ctx->stream));
+  if (prof) VTMME_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
   VTMME_CUDA_CHECK(ctx, launch_tree_upper(tp, nPairs, ctx->stream));
+  if (prof) VTMME_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
 
   FracFrameParams fp;
   fp.g        = g;
@@ -318,6 +348,11 @@ int vtmme_search_frames_device(vtmme_ctx* ctx, int nPairs, const int32_t* curPic
   fp.fracMode = prm->fracMode;
   fp.lambda   = prm->lambdaMotion;
   VTMME_CUDA_CHECK(ctx, launch_frac_frame(fp, nPairs, ctx->stream));
+  if (prof)
+  {
+    VTMME_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    ctx->evValid = true;
+  }
   ctx->launches += 3;
   return VTMME_OK;
 }

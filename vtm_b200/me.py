@@ -99,6 +99,15 @@ class MotionSearch:
     def synchronize(self):
         self._check(self.L.vtmme_synchronize(self.ctx), "vtmme_synchronize")
 
+    def set_profiling(self, on=True):
+        self._check(self.L.vtmme_set_profiling(self.ctx, 1 if on else 0), "vtmme_set_profiling")
+
+    def frame_kernel_ms(self):
+        """(me_tree_sad, me_tree_upper, me_frac_frame) milliseconds of the most recent profiled frame search."""
+        ms = (C.c_float * 3)()
+        self._check(self.L.vtmme_frame_kernel_ms(self.ctx, ms), "vtmme_frame_kernel_ms")
+        return tuple(float(v) for v in ms)
+
     @property
     def launches(self):
         return int(self.L.vtmme_launch_count(self.ctx))
