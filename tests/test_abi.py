@@ -1,0 +1,56 @@
+"""CPU: the C-ABI library builds/loads, exports every symbol include/vtmme.h declares, and refuses to run
+without a GPU (no CPU fallback on the product path)."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "vtmme.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vtmme_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    from vtm_b200.lib import SYMBOLS
+    assert header_functions() == sorted(SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    import vtm_b200
+    if not os.path.exists(vtm_b200.library_path()):
+        vtm_b200.build_library()
+    lib = vtm_b200.load_library()
+    for name in header_functions():
+        assert hasattr(lib, name), name
+
+
+def test_no_cpu_fallback():
+    import torch
+    import vtm_b200
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(vtm_b200.VtmmeError):
+        vtm_b200.MotionSearch(0)
+
+
+def test_product_never_touches_the_oracle():
+    """Nothing under vtm_b200/ (python or CUDA/C++) may import, include or link oracle/."""
+    pkg = os.path.join(ROOT, "vtm_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "build" in dirpath.split(os.sep):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle|#include\s+\"[^\"]*oracle|vtm_oracle|libvtmref|libvtmoracle",
+                                     text, flags=re.M), os.path.join(dirpath, f)
+
+
+def test_frame_cu_layout():
+    from vtm_b200.me import frame_cu_layout
+    n, off = frame_cu_layout(1920, 1080)
+    assert n == 43020 and off == [0, 32400, 40440, 42420, 42900, 43020]

@@ -1,0 +1,84 @@
+"""CPU: the oracle against the committed golden vectors (tests/golden/vtm_golden.npz, generated from the
+compiled reference by tests/golden/make_golden.py).  Runs where /root/reference does not exist."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import bindings as B
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vtm_golden.npz"))
+
+
+def iter_dist():
+    off = 0
+    for (w, h, kind), vals in zip(G["dist_meta"], G["dist_val"]):
+        n = int(w) * int(h)
+        org = np.ascontiguousarray(G["dist_org"][off:off + n].reshape(h, w))
+        cur = np.ascontiguousarray(G["dist_cur"][off:off + n].reshape(h, w))
+        off += n
+        yield int(w), int(h), int(kind), org, cur, [int(v) for v in vals]
+
+
+def iter_interp():
+    off = 0
+    for m in G["if_meta"]:
+        comp, w, h, frac, vert, first, last, alt = (int(v) for v in m)
+        want = G["if_out"][off:off + w * h].reshape(h, w)
+        off += w * h
+        yield comp, w, h, frac, vert, first, last, alt, want
+
+
+def iter_search():
+    off = 0
+    for m, lam, res in zip(G["search_meta"], G["search_lambda"], G["search_res"]):
+        w, h, x, y, l, r, t, b, pqx, pqy, imv, alt, ssm = (int(v) for v in m)
+        org = np.ascontiguousarray(G["search_org"][off:off + w * h].reshape(h, w))
+        off += w * h
+        yield w, h, x, y, (l, r, t, b), (pqx, pqy), imv, alt, ssm, float(lam), org, tuple(int(v) for v in res)
+
+
+def test_golden_was_made_with_simd_reference():
+    assert int(G["simd_level"][0]) >= 1
+
+
+def test_dist_golden(oracle_lib):
+    n = 0
+    for w, h, kind, org, cur, vals in iter_dist():
+        assert oracle_lib.vo_sad(B.ptr(org), w, B.ptr(cur), w, w, h, 0) == vals[0]
+        assert oracle_lib.vo_sad(B.ptr(org), w, B.ptr(cur), w, w, h, oracle_lib.vo_subshift(2, w, h)) == vals[1]
+        assert oracle_lib.vo_satd(B.ptr(org), w, B.ptr(cur), w, w, h) == vals[2]
+        n += 1
+    assert n == 72
+
+
+def test_mv_rate_golden(oracle_lib):
+    for x, y, px, py, scale, imv, bits in G["mv_bits"]:
+        assert oracle_lib.vo_mv_bits(int(x), int(y), int(px), int(py), int(scale), int(imv)) == int(bits)
+    for lam, row in zip(G["mv_cost_lambda"], G["mv_cost"]):
+        for b, c in enumerate(row):
+            assert oracle_lib.vo_mv_cost(float(lam), b) == int(c)
+
+
+def test_interp_golden(oracle_lib):
+    src, mid = np.ascontiguousarray(G["if_src"]), np.ascontiguousarray(G["if_mid"])
+    for comp, w, h, frac, vert, first, last, alt, want in iter_interp():
+        s = src if first else mid
+        got = np.zeros((h, w), np.int16)
+        if vert:
+            oracle_lib.vo_filter_ver(comp, B.ptr(s, 8 * 40 + 8), 40, B.ptr(got), w, w, h, frac, first, last, 10, alt)
+        else:
+            oracle_lib.vo_filter_hor(comp, B.ptr(s, 8 * 40 + 8), 40, B.ptr(got), w, w, h, frac, last, 10, alt)
+        assert np.array_equal(got, want), (comp, w, h, frac, vert, first, last, alt)
+
+
+@pytest.mark.parametrize("literal", [1, 0])
+def test_search_golden(oracle_lib, literal):
+    plane = np.ascontiguousarray(G["search_ref"])
+    W = plane.shape[1]
+    for w, h, x, y, win, pq, imv, alt, ssm, lam, org, want in iter_search():
+        j = B.make_job(org, plane, W, y * W + x, w, h, win, pq, imv, ssm, 10, 1, alt, 1, lam)
+        r = B.Result()
+        oracle_lib.vo_search(C.byref(j), C.byref(r), literal)
+        assert r.tuple() == want, (w, h, imv, ssm, literal)

@@ -1,0 +1,45 @@
+"""GPU: the CUDA path (through the C ABI) against the committed golden vectors generated from the compiled
+reference (tests/golden/vtm_golden.npz)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from tests.test_golden import G, iter_dist, iter_interp, iter_search  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ms():
+    import vtm_b200
+    m = vtm_b200.MotionSearch(0)
+    yield m
+    m.close()
+
+
+def test_gpu_dist_golden(ms):
+    for w, h, kind, org, cur, vals in iter_dist():
+        assert ms.dist_host(0, org, cur, 0) == vals[0], (w, h, kind)
+        ss = 1 if (h > 8 and w <= 64) else 0          # subShiftMode 2 (RdCost.cpp:310-316)
+        assert ms.dist_host(0, org, cur, ss) == vals[1], (w, h, kind, "subshift")
+        assert ms.dist_host(1, org, cur) == vals[2], (w, h, kind, "satd")
+
+
+def test_gpu_interp_golden(ms):
+    src, mid = np.ascontiguousarray(G["if_src"]), np.ascontiguousarray(G["if_mid"])
+    for comp, w, h, frac, vert, first, last, alt, want in iter_interp():
+        s = src if first else mid
+        got = ms.interp_host(comp, vert, s, 8 * 40 + 8, 40, w, h, frac, first, last, 10, alt)
+        assert np.array_equal(got, want), (comp, w, h, frac, vert, first, last, alt)
+
+
+def test_gpu_search_golden(ms):
+    from vtm_b200 import Job
+    plane = np.ascontiguousarray(G["search_ref"])
+    ms.upload_picture(50, plane)
+    jobs, want = [], []
+    for w, h, x, y, win, pq, imv, alt, ssm, lam, org, res in iter_search():
+        ss = 1 if (ssm == 2 and h > 8 and w <= 64) else 0
+        jobs.append(Job(50, 50, x, y, w, h, win, pq, imv, ss, 10, 1, alt, 1, lam, org))
+        want.append(res)
+    got = ms.search(jobs)
+    assert got == want

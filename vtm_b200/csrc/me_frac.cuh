@@ -3,7 +3,7 @@
 // interpolation (InterpolationFilter.cpp:550-656, 14-bit intermediates) feeds the Hadamard SATD
 // (RdCost.cpp:2140-2934) directly, nothing goes back to global memory.
 //
-// Direct form (oracle/vtm_oracle.c: vo_frac_direct; tests check it equals the reference's m_filteredBlock
+// Direct form (the tests check against the CPU restatement that it equals the reference's m_filteredBlock
 // planes): the candidate at quarter-pel offset (dqx,dqy) from the integer MV is interpolated at integer
 // base (dq >> 2) with phase (dq & 3).  One CTA refines one CU, in chunks of at most 32x32 samples:
 //   1. stage the chunk's original samples and the (cw+8)x(ch+8) reference patch in shared memory,
