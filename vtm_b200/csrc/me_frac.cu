@@ -1,4 +1,15 @@
-// Fractional refinement + result write-out of the batched frame path (one CTA per CU).
+// Fractional refinement + result write-out of the batched frame path.
+//
+// Same arithmetic as me_frac.cuh (xPatternSearchFracDIF, EncoderLib/InterSearch.cpp:4296-4338, with the separable
+// 8-tap interpolation of InterpolationFilter.cpp:550-656 fused into the Hadamard SATD of RdCost.cpp:2267-2366),
+// organised for throughput: the work item is one warp x one chunk of at most 16x16 samples, nothing but
+// __syncwarp inside an item, four items per CTA.
+//
+//   8x8 and 16x16 CUs (94 % of the CUs) are one item each: half-pel stage, decision, quarter-pel stage, result.
+//   Larger CUs are split into 16x16 chunks whose nine candidate SATDs are summed with atomics:
+//     me_frac_items_kernel<0>  half-pel stage of every chunk            -> acc[cu][0..8]
+//     me_frac_items_kernel<1>  decision from acc, quarter-pel stage      -> acc[cu][9..17]
+//     me_frac_finish_kernel    decisions from acc, result
 #include "me_frac.cuh"
 #include "me_kernels.h"
 
@@ -8,67 +19,396 @@ namespace vtmme {
 
 namespace {
 
-__global__ void __launch_bounds__(kFracThreads) me_frac_frame_kernel(FracFrameParams p)
-{
-  __shared__ FracSmem sm;
-  const int cu = blockIdx.x, pair = blockIdx.y;
-  const int nCU = p.g.off[5];
-  int       level = 0;
-#pragma unroll
-  for (int l = 1; l < 5; l++)
-    if (cu >= p.g.off[l]) level = l;
-  const int size = 8 << level;
-  const int li = cu - p.g.off[level];
-  const int cx = li % p.g.nx[level], cy = li / p.g.nx[level];
-  const int x = cx * size, y = cy * size;
+constexpr int kItemWarps  = 4;
+constexpr int kChunk      = 16;
+constexpr int kPatchW     = kChunk + 8;          // 24
+constexpr int kPlaneElems = kPatchW * kChunk;    // rows [-4, ch+4) x cols [0, cw)
 
+struct __align__(16) ItemSmem
+{
+  int32_t  plane[3][kPlaneElems];   // 14-bit horizontal intermediates, widened
+  int16_t  org[kChunk * kChunk];
+  uint16_t patch[kPatchW * kPatchW];
+  uint32_t acc[12];
+};
+
+struct ItemGeom
+{
+  int level, cu, x, y, size, chunkX, chunkY, nChunks;
+};
+
+// item index -> CU and chunk.  Items are ordered by level; level l >= 1 has (size/16)^2 chunks per CU.
+__device__ __forceinline__ ItemGeom item_geom(const FrameGeom& g, int item)
+{
+  ItemGeom r;
+  int base = 0;
+#pragma unroll
+  for (int l = 0; l < 5; l++)
+  {
+    const int per = l <= 1 ? 1 : (1 << (2 * (l - 1)));
+    const int n   = g.nx[l] * g.ny[l] * per;
+    if (item < base + n || l == 4)
+    {
+      const int li = (item - base) / per, ch = (item - base) - li * per;
+      const int side = l <= 1 ? 1 : (1 << (l - 1));
+      r.level   = l;
+      r.cu      = g.off[l] + li;
+      r.size    = 8 << l;
+      r.x       = (li % g.nx[l]) * r.size;
+      r.y       = (li / g.nx[l]) * r.size;
+      r.chunkX  = (ch % side) * kChunk;
+      r.chunkY  = (ch / side) * kChunk;
+      r.nChunks = per;
+      return r;
+    }
+    base += n;
+  }
+  return r;
+}
+
+__host__ __device__ inline int frame_items(const FrameGeom& g)
+{
+  int n = 0;
+  for (int l = 0; l < 5; l++) n += g.nx[l] * g.ny[l] * (l <= 1 ? 1 : (1 << (2 * (l - 1))));
+  return n;
+}
+__host__ __device__ inline int frame_items_small(const FrameGeom& g) { return g.nx[0] * g.ny[0] + g.nx[1] * g.ny[1]; }
+
+// Nine candidate distortions of one CW x CW chunk (8x8 tiles) around quarter-pel offset (cqx,cqy) with step
+// `step`, accumulated into sm.acc[0..8].  One warp.
+template <bool HAD, int CW>
+__device__ __forceinline__ void item_stage(ItemSmem& sm, const int16_t* __restrict__ org, int orgStride,
+                                           const int16_t* __restrict__ refAtMv, int refStride, int cqx, int cqy, int step,
+                                           int bitDepth, const int8_t (*tab)[2])
+{
+  constexpr int cw = CW, ch = CW, pw = CW + 8;
+  const int lane = threadIdx.x & 31;
+  const int hr   = max(2, 14 - bitDepth);
+  const int maxv = (1 << bitDepth) - 1;
+  if (lane < 12) sm.acc[lane] = 0;
+  // 1. original chunk and reference patch rows/cols [-4, +4)
+#pragma unroll
+  for (int i = lane; i < cw * ch; i += 32)
+  {
+    const int y = i / cw, x = i % cw;
+    sm.org[y * kChunk + x] = org[(size_t) y * orgStride + x];
+  }
+#pragma unroll 4
+  for (int i = lane; i < (ch + 8) * pw; i += 32)
+  {
+    const int y = i / pw, x = i % pw;
+    sm.patch[y * kPatchW + x] = (uint16_t) refAtMv[(ptrdiff_t) (y - 4) * refStride + (x - 4)];
+  }
+  __syncwarp();
+  // 2. horizontal pass: lane r filters patch row r (picture row r-4) once for the three planes
+  //    dqx = cqx + (p-1)*step: plane[p][r][c], 14-bit intermediates (filter<8,false,true,false> / filterCopy<true,false>)
+  if (lane < ch + 8)
+  {
+    int s[pw];
+    const uint16_t* prow = sm.patch + lane * kPatchW;
+#pragma unroll
+    for (int i = 0; i < pw; i += 2)
+    {
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(prow + i);
+      s[i]     = (int) (w & 0xffffu);
+      s[i + 1] = (int) (w >> 16);
+    }
+#pragma unroll
+    for (int p = 0; p < 3; p++)
+    {
+      const int dq = cqx + (p - 1) * step;
+      const int ix = dq >> 2, px = dq & 3;   // ix in {-1, 0}
+      int32_t*  dst = sm.plane[p] + lane * kChunk;
+      if (px == 0)
+      {
+#pragma unroll
+        for (int c = 0; c < cw; c++)
+        {
+          const int v0 = ix ? s[c + 3] : s[c + 4];
+          dst[c]       = (int16_t) ((int16_t) (v0 << hr) - (int16_t) 8192);
+        }
+      }
+      else
+      {
+        int cf[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) cf[k] = c_lumaFilter[px * 4][k];
+        const int shift = 6 - hr, off = 8192 << shift;
+#pragma unroll
+        for (int c = 0; c < cw; c++)
+        {
+          int sum = 0;
+#pragma unroll
+          for (int k = 0; k < 8; k++) sum += (ix ? s[c + k] : s[c + k + 1]) * cf[k];
+          dst[c] = (int16_t) ((sum - off) >> shift);
+        }
+      }
+    }
+  }
+  __syncwarp();
+  // 3. (candidate, 8x8 tile) units, 8 lanes each
+  const int tilesX = cw >> 3, nTiles = tilesX * (ch >> 3), units = 9 * nTiles;
+  const int group = lane >> 3, lit = lane & 7;
+  for (int u0 = 0; u0 < units; u0 += 4)
+  {
+    const int  u      = u0 + group;
+    const bool active = u < units;
+    const int  uu     = active ? u : 0;
+    const int  c = uu / nTiles, t = uu - c * nTiles;
+    const int  tx = (t % tilesX) * 8, ty = (t / tilesX) * 8;
+    const int  dqy = cqy + tab[c][1] * step;
+    const int  iy = dqy >> 2, py = dqy & 3;
+    const int  y = ty + lit;
+    const int32_t* pp = sm.plane[tab[c][0] + 1] + (y + iy + 4) * kChunk + tx;
+    int d[8];
+    if (py == 0)
+    {
+      const int4 a = *reinterpret_cast<const int4*>(pp), b = *reinterpret_cast<const int4*>(pp + 4);
+      const int  s[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+      {
+        const int v = (int16_t) ((s[i] + 8192 + (1 << (hr - 1))) >> hr);
+        d[i]        = min(max(v, 0), maxv);
+      }
+    }
+    else
+    {
+      const int16_t* cfp = c_lumaFilter[py * 4];
+      int            sum[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) sum[i] = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+      {
+        const int32_t* row = pp + (k - 3) * kChunk;
+        const int4     a = *reinterpret_cast<const int4*>(row), b = *reinterpret_cast<const int4*>(row + 4);
+        const int      cf = cfp[k];
+        sum[0] += a.x * cf; sum[1] += a.y * cf; sum[2] += a.z * cf; sum[3] += a.w * cf;
+        sum[4] += b.x * cf; sum[5] += b.y * cf; sum[6] += b.z * cf; sum[7] += b.w * cf;
+      }
+      const int shift = 6 + hr, offset = (1 << (shift - 1)) + (8192 << 6);
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+      {
+        const int v = (int16_t) ((sum[i] + offset) >> shift);
+        d[i]        = min(max(v, 0), maxv);
+      }
+    }
+    const int16_t* op = sm.org + y * kChunk + tx;
+#pragma unroll
+    for (int i = 0; i < 8; i++) d[i] = op[i] - d[i];
+    uint32_t v;
+    if (HAD)
+      v = satd_tile_rows<8, 8>(d, lit);
+    else
+    {
+      v = 0;
+#pragma unroll
+      for (int i = 0; i < 8; i++) v += (uint32_t) abs(d[i]);
+#pragma unroll
+      for (int m = 1; m < 8; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    }
+    if (active && lit == 0) atomicAdd(&sm.acc[c], v);
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void run_stage(ItemSmem& sm, int useHad, int cw, const int16_t* org, int orgStride,
+                                          const int16_t* rf, int refStride, int cqx, int cqy, int step, int bitDepth,
+                                          const int8_t (*tab)[2])
+{
+  if (cw == 8)
+  {
+    if (useHad) item_stage<true, 8>(sm, org, orgStride, rf, refStride, cqx, cqy, step, bitDepth, tab);
+    else item_stage<false, 8>(sm, org, orgStride, rf, refStride, cqx, cqy, step, bitDepth, tab);
+  }
+  else
+  {
+    if (useHad) item_stage<true, 16>(sm, org, orgStride, rf, refStride, cqx, cqy, step, bitDepth, tab);
+    else item_stage<false, 16>(sm, org, orgStride, rf, refStride, cqx, cqy, step, bitDepth, tab);
+  }
+}
+
+// xPatternRefinement's choice (InterSearch.cpp:727-756): first strict minimum over the nine candidates in list order.
+// dist[] read by lanes 0..8 from `dist`; returns (direction, cost) to all lanes.
+__device__ __forceinline__ void pick_best(const uint32_t* dist, const int8_t (*tab)[2], int baseQx, int baseQy, int step,
+                                          int predQx, int predQy, double lambda, int& dir, uint32_t& cost)
+{
+  const int lane = threadIdx.x & 31;
+  uint32_t  key  = 0xffffffffu;
+  if (lane < 9)
+  {
+    const uint32_t c = dist[lane] + mv_cost(lambda, mv_bits_q(baseQx + tab[lane][0] * step, baseQy + tab[lane][1] * step,
+                                                               predQx, predQy, 0));
+    key = (c << 4) | (uint32_t) lane;   // costs stay below 2^28
+  }
+  key  = __reduce_min_sync(0xffffffffu, key);
+  dir  = (int) (key & 15u);
+  cost = key >> 4;
+}
+
+struct ItemParams
+{
+  FracFrameParams f;
+  uint32_t*       acc;      // [nPairs][nCU][18] (only CUs of level >= 2 are used)
+  int             nItems;   // per pair, for this launch
+  int             itemBase; // first item index of this launch (0, or the first level-2 item)
+};
+
+template <int PASS>   // 0: every item, half stage (+ everything for single-item CUs); 1: quarter stage of multi-item CUs
+__global__ void __launch_bounds__(kItemWarps * 32) me_frac_items_kernel(ItemParams ip)
+{
+  __shared__ ItemSmem s_items[kItemWarps];
+  const FracFrameParams& p = ip.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * kItemWarps + warp;
+  if (item >= ip.nItems) return;
+  const int      pair = blockIdx.y;
+  const int      nCU  = p.g.off[5];
+  ItemSmem&      sm   = s_items[warp];
+  const ItemGeom ig   = item_geom(p.g, ip.itemBase + item);
+
+  const unsigned long long key = p.keys[(size_t) pair * nCU + ig.cu];
+  short2 pr = make_short2(0, 0);
+  if (p.predQ) pr = p.predQ[(size_t) pair * nCU + ig.cu];
+  const int    dx = key_dx(key), dy = key_dy(key);
+  const DevPic cur = p.cur[pair], ref = p.ref[pair];
+  const int    cw = min(ig.size, kChunk);
+  const int16_t* org = cur.origin + (size_t) (ig.y + ig.chunkY) * cur.stride + ig.x + ig.chunkX;
+  const int16_t* rf  = ref.origin + (ptrdiff_t) (ig.y + ig.chunkY + dy) * ref.stride + (ig.x + ig.chunkX + dx);
+  uint32_t*      acc = ip.acc + ((size_t) pair * nCU + ig.cu) * 18;
+
+  int      hdir = 0, qdir = 0;
+  uint32_t cost = 0;
+  if (PASS == 0)
+  {
+    run_stage(sm, p.useHad, cw, org, cur.stride, rf, ref.stride, 0, 0, 2, p.bitDepth, c_refineH);
+    if (ig.nChunks > 1)
+    {
+      if (lane < 9) atomicAdd(&acc[lane], sm.acc[lane]);
+      return;
+    }
+    pick_best(sm.acc, c_refineH, dx * 4, dy * 4, 2, pr.x, pr.y, p.lambda, hdir, cost);
+  }
+  else
+  {
+    pick_best(acc, c_refineH, dx * 4, dy * 4, 2, pr.x, pr.y, p.lambda, hdir, cost);
+  }
+  const int hx = c_refineH[hdir][0], hy = c_refineH[hdir][1];
+  if (p.imvShift == 0)
+  {
+    __syncwarp();
+    run_stage(sm, p.useHad, cw, org, cur.stride, rf, ref.stride, hx * 2, hy * 2, 1, p.bitDepth, c_refineQ);
+    if (ig.nChunks > 1)
+    {
+      if (lane < 9) atomicAdd(&acc[9 + lane], sm.acc[lane]);
+      return;
+    }
+    pick_best(sm.acc, c_refineQ, dx * 4 + hx * 2, dy * 4 + hy * 2, 1, pr.x, pr.y, p.lambda, qdir, cost);
+  }
+  else if (ig.nChunks > 1)
+    return;
+  if (lane == 0)
+  {
+    const int qx = p.imvShift == 0 ? c_refineQ[qdir][0] : 0, qy = p.imvShift == 0 ? c_refineQ[qdir][1] : 0;
+    vtmme_cu_result res;
+    res.intX     = (int16_t) dx;
+    res.intY     = (int16_t) dy;
+    res.intSad   = key_cost(key) - mv_cost(p.lambda, mv_bits_q(dx * 4, dy * 4, pr.x, pr.y, p.imvShift));
+    res.mvQx     = (int16_t) (dx * 4 + hx * 2 + qx);
+    res.mvQy     = (int16_t) (dy * 4 + hy * 2 + qy);
+    res.fracCost = cost;
+    reinterpret_cast<vtmme_cu_result*>(p.results)[(size_t) pair * nCU + ig.cu] = res;
+  }
+}
+
+// Results of the CUs whose stages were accumulated across chunks (levels >= 2), and of every CU when fracMode == 0.
+__global__ void __launch_bounds__(128) me_frac_finish_kernel(ItemParams ip, int firstCu)
+{
+  const FracFrameParams& p = ip.f;
+  const int nCU = p.g.off[5];
+  const int cu  = firstCu + blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (cu >= nCU) return;
+  const int pair = blockIdx.y, lane = threadIdx.x & 31;
   const unsigned long long key = p.keys[(size_t) pair * nCU + cu];
   short2 pr = make_short2(0, 0);
   if (p.predQ) pr = p.predQ[(size_t) pair * nCU + cu];
   const int      dx = key_dx(key), dy = key_dy(key);
   const uint32_t intCost = key_cost(key);
-  const uint32_t intSad  = intCost - mv_cost(p.lambda, mv_bits_q(dx * 4, dy * 4, pr.x, pr.y, p.imvShift));
-
-  vtmme_cu_result res;
-  res.intX     = (int16_t) dx;
-  res.intY     = (int16_t) dy;
-  res.intSad   = intSad;
-  res.mvQx     = (int16_t) (dx * 4);
-  res.mvQy     = (int16_t) (dy * 4);
-  res.fracCost = intCost;
+  int      hdir = 0, qdir = 0;
+  uint32_t cost = intCost;
+  int      hx = 0, hy = 0, qx = 0, qy = 0;
   if (p.fracMode)
   {
-    const DevPic cur = p.cur[pair], ref = p.ref[pair];
-    FracJob      j;
-    j.org        = cur.origin + (size_t) y * cur.stride + x;
-    j.orgStride  = cur.stride;
-    j.refAtMv    = ref.origin + (ptrdiff_t) (y + dy) * ref.stride + (x + dx);
-    j.refStride  = ref.stride;
-    j.w = j.h    = size;
-    j.mvX        = dx;
-    j.mvY        = dy;
-    j.predQx     = pr.x;
-    j.predQy     = pr.y;
-    j.bitDepth   = p.bitDepth;
-    j.useHad     = p.useHad;
-    j.useAltHpel = 0;
-    j.imvShift   = p.imvShift;
-    j.lambda     = p.lambda;
-    const FracOut o = frac_refine_cta(sm, j);
-    res.mvQx     = (int16_t) (dx * 4 + o.halfX * 2 + o.qterX);
-    res.mvQy     = (int16_t) (dy * 4 + o.halfY * 2 + o.qterY);
-    res.fracCost = o.cost;
+    const uint32_t* acc = ip.acc + ((size_t) pair * nCU + cu) * 18;
+    pick_best(acc, c_refineH, dx * 4, dy * 4, 2, pr.x, pr.y, p.lambda, hdir, cost);
+    hx = c_refineH[hdir][0];
+    hy = c_refineH[hdir][1];
+    if (p.imvShift == 0)
+    {
+      pick_best(acc + 9, c_refineQ, dx * 4 + hx * 2, dy * 4 + hy * 2, 1, pr.x, pr.y, p.lambda, qdir, cost);
+      qx = c_refineQ[qdir][0];
+      qy = c_refineQ[qdir][1];
+    }
   }
-  if (threadIdx.x == 0) reinterpret_cast<vtmme_cu_result*>(p.results)[(size_t) pair * nCU + cu] = res;
+  if (lane == 0)
+  {
+    vtmme_cu_result res;
+    res.intX     = (int16_t) dx;
+    res.intY     = (int16_t) dy;
+    res.intSad   = intCost - mv_cost(p.lambda, mv_bits_q(dx * 4, dy * 4, pr.x, pr.y, p.imvShift));
+    res.mvQx     = (int16_t) (dx * 4 + hx * 2 + qx);
+    res.mvQy     = (int16_t) (dy * 4 + hy * 2 + qy);
+    res.fracCost = cost;
+    reinterpret_cast<vtmme_cu_result*>(p.results)[(size_t) pair * nCU + cu] = res;
+  }
 }
 
 }   // namespace
 
-cudaError_t launch_frac_frame(const FracFrameParams& p, int nPairs, cudaStream_t st)
+size_t frac_frame_acc_bytes(const FrameGeom& g, int nPairs) { return (size_t) nPairs * g.off[5] * 18 * sizeof(uint32_t); }
+
+cudaError_t launch_frac_frame(const FracFrameParams& p, uint32_t* acc, int nPairs, cudaStream_t st, int* launches)
 {
-  dim3 grid(p.g.off[5], nPairs, 1);
-  me_frac_frame_kernel<<<grid, kFracThreads, 0, st>>>(p);
-  return cudaGetLastError();
+  ItemParams ip;
+  ip.f   = p;
+  ip.acc = acc;
+  cudaError_t e;
+  if (!p.fracMode)
+  {
+    ip.nItems = ip.itemBase = 0;
+    dim3 g((p.g.off[5] + 3) / 4, nPairs, 1);
+    me_frac_finish_kernel<<<g, 128, 0, st>>>(ip, 0);
+    *launches += 1;
+    return cudaGetLastError();
+  }
+  if ((e = cudaMemsetAsync(acc, 0, frac_frame_acc_bytes(p.g, nPairs), st)) != cudaSuccess) return e;
+  const int nAll = frame_items(p.g), nSmall = frame_items_small(p.g);
+  ip.nItems   = nAll;
+  ip.itemBase = 0;
+  dim3 g0((nAll + kItemWarps - 1) / kItemWarps, nPairs, 1);
+  me_frac_items_kernel<0><<<g0, kItemWarps * 32, 0, st>>>(ip);
+  *launches += 1;
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (nAll > nSmall)
+  {
+    if (p.imvShift == 0)
+    {
+      ip.nItems   = nAll - nSmall;
+      ip.itemBase = nSmall;
+      dim3 g1((ip.nItems + kItemWarps - 1) / kItemWarps, nPairs, 1);
+      me_frac_items_kernel<1><<<g1, kItemWarps * 32, 0, st>>>(ip);
+      *launches += 1;
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    const int firstCu = p.g.off[2];
+    dim3 g2((p.g.off[5] - firstCu + 3) / 4, nPairs, 1);
+    me_frac_finish_kernel<<<g2, 128, 0, st>>>(ip, firstCu);
+    *launches += 1;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
 }   // namespace vtmme

@@ -56,7 +56,7 @@ struct TreeParams
   double              lambda;
 };
 
-size_t tree_sad_smem_bytes(int maxGx, int bandRows);
+size_t tree_sad_smem_bytes(int maxGx, int maxRows, int bandRows);
 cudaError_t launch_tree_sad(const TreeParams& p, int nPairs, cudaStream_t st);
 cudaError_t launch_tree_upper(const TreeParams& p, int nPairs, cudaStream_t st);
 
@@ -72,7 +72,8 @@ struct FracFrameParams
   int                       bitDepth, imvShift, useHad, fracMode;
   double                    lambda;
 };
-cudaError_t launch_frac_frame(const FracFrameParams& p, int nPairs, cudaStream_t st);
+size_t      frac_frame_acc_bytes(const FrameGeom& g, int nPairs);
+cudaError_t launch_frac_frame(const FracFrameParams& p, uint32_t* acc, int nPairs, cudaStream_t st, int* launches);
 
 // Generic per-call jobs (vtmme_search)
 struct DevJob

@@ -14,14 +14,18 @@
 // Each CU has its own window (xSetSearchRange around its own predictor); a region computes the bounding
 // box of the windows of the 23 CUs that contain it or lie in it, and every candidate is tested against the
 // window of the CU it is evaluated for.
+#include <cstdio>
+#include <cstdlib>
+
 #include "me_kernels.h"
 
 namespace vtmme {
 
 namespace {
 
-constexpr int kTreeThreads = 256;
-constexpr int kSlots       = 23;   // 16 8x8 + 4 16x16 + 1 32x32 (+ the 64x64 and 128x128 ancestors, window only)
+constexpr int kTreeMaxThreads = 256;
+constexpr int kSlots          = 23;   // 16 8x8 + 4 16x16 + 1 32x32 (+ the 64x64 and 128x128 ancestors, window only)
+constexpr int kCheckSlots     = 21;   // CUs this kernel keeps an argmin for
 
 struct CuInfo
 {
@@ -30,16 +34,25 @@ struct CuInfo
   int   idx;           // index in the CU order, -1 if the CU does not exist
 };
 
-// shared-memory layout (bytes)
-constexpr int kOffOrg  = 0;                       // uint32 [32][32]
-constexpr int kOffBest = 4096;                    // u64 [24]
+// shared-memory layout (bytes); the tables after kOffLut are sized from TreeParams::maxGx / maxRows
+constexpr int kOffOrg  = 0;                       // uint32 [32][32]   original samples widened to 32 bit
+constexpr int kOffBest = 4096;                    // u64 [24]          per-CU best (cost, position)
 constexpr int kOffCu   = kOffBest + 24 * 8;       // CuInfo [24]
 constexpr int kOffMisc = kOffCu + 24 * 16;        // int [8]
-constexpr int kOffRef  = kOffMisc + 32;           // uint16 [rows][refStride]
+constexpr int kOffLut  = kOffMisc + 32;           // uint32 [512]      lambda * bits, entries >= 256 = "outside the window"
+constexpr int kOffTab  = kOffLut + 2048;          // u8 minBitsX[21][gxPad], u8 bitsY[21][rowsPad], then the window
+constexpr uint32_t kLutInvalid = 0x3fffffffu;
 static_assert(sizeof(CuInfo) == 16, "CuInfo layout");
-static_assert(kOffRef % 16 == 0, "alignment");
+static_assert(kOffTab % 16 == 0, "alignment");
 
-// Candidate that passed the cheap SAD <= current-best test: exact window test, exact cost, atomic argmin.
+__host__ __device__ inline int tree_gx_pad(int maxGx) { return (maxGx + 3) & ~3; }
+__host__ __device__ inline int tree_rows_pad(int maxRows) { return (maxRows + 3) & ~3; }
+__host__ __device__ inline int tree_off_ref(int maxGx, int maxRows)
+{
+  return (kOffTab + kCheckSlots * (tree_gx_pad(maxGx) + tree_rows_pad(maxRows)) + 15) & ~15;
+}
+
+// Candidate that passed the cheap lower-bound test: exact window test, exact cost, atomic argmin.
 __device__ __noinline__ void consider(const CuInfo* cu, unsigned long long* best, int dx, int dy, uint32_t sad,
                                       double lambda, int imvShift)
 {
@@ -48,34 +61,105 @@ __device__ __noinline__ void consider(const CuInfo* cu, unsigned long long* best
   atomicMin(best, make_key(cost, dx, dy));
 }
 
-__device__ __forceinline__ void check8(const uint32_t (&a)[8], const CuInfo* cu, unsigned long long* best, int dx0,
-                                       int dy, double lambda, int imvShift)
+// Fast reject of 8 candidates of one CU: cost >= SAD + lambda*(min bitsX of the group + bitsY of the row).
+__device__ __forceinline__ void check8(const uint32_t (&a)[8], uint32_t lb, const CuInfo* cu, unsigned long long* best,
+                                       int dx0, int dy, double lambda, int imvShift)
 {
-  const uint32_t thr = (uint32_t) (*reinterpret_cast<volatile unsigned long long*>(best) >> 32);
+  const uint32_t thr = reinterpret_cast<volatile uint2*>(best)->y;
   const uint32_t m   = min(min(min(a[0], a[1]), min(a[2], a[3])), min(min(a[4], a[5]), min(a[6], a[7])));
-  if (m <= thr)
+  if (m + lb <= thr)
   {
 #pragma unroll
     for (int k = 0; k < 8; k++)
-      if (a[k] <= thr) consider(cu, best, dx0 + k, dy, a[k], lambda, imvShift);
+      if (a[k] + lb <= thr) consider(cu, best, dx0 + k, dy, a[k], lambda, imvShift);
   }
 }
 
-__global__ void __launch_bounds__(kTreeThreads, 3) me_tree_sad_kernel(TreeParams p)
+// 64 pixel-candidates: 8 original samples of one row against 8 displacements.  The first 8-NFP displacements
+// use VABSDIFF.U32 on the ALU pipe; the last NFP use two FADDs on the FP32 pipe: the 10-bit samples and the
+// partial sums are treated as denormal floats (bit pattern == integer below 2^24), for which FADD is exact
+// fixed-point arithmetic, so both halves produce the same integers.
+template <int NFP>
+__device__ __forceinline__ void sad_row(uint32_t (&a)[8], const uint32_t (&o)[8], const uint32_t (&px)[16])
+{
+#pragma unroll
+  for (int k = 0; k < 8 - NFP; k++)
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[k] = __usad(o[i], px[i + k], a[k]);
+#pragma unroll
+  for (int k = 8 - NFP; k < 8; k++)
+  {
+    float acc = __uint_as_float(a[k]);
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      acc = __fadd_rn(acc, fabsf(__fsub_rn(__uint_as_float(o[i]), __uint_as_float(px[i + k]))));
+    a[k] = __float_as_uint(acc);
+  }
+}
+
+// The staged reference window holds two samples per 32-bit word in 12-bit fields (lo | hi << 12), so that a word
+// stays below 2^24: seen as a float it is then a denormal (value = bits * 2^-149) and the FP32 pipe can split it
+// exactly — w * 2^-12 rounds to hi (lo < 2048), and w - hi * 4096 = lo.
+__device__ __forceinline__ uint32_t pack12(uint32_t x)   // x = lo | hi << 16, both < 1024
+{
+  return (x & 0xfffu) | ((x >> 4) & 0x3ff000u);
+}
+
+// 16 reference samples (two 128-bit shared loads) widened to 32 bit; FPU: on the FP32 pipe, else LOP3/SHF.
+template <bool FPU>
+__device__ __forceinline__ void load_ref16(const uint16_t* p, uint32_t (&px)[16])
+{
+  const uint4    w0 = *reinterpret_cast<const uint4*>(p);
+  const uint4    w1 = *reinterpret_cast<const uint4*>(p + 8);
+  const uint32_t w[8] = { w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w };
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+  {
+    if (FPU)
+    {
+      const float wf = __uint_as_float(w[i]);
+      const float hi = __fmul_rn(wf, 0.000244140625f);   // 2^-12
+      px[2 * i + 1]  = __float_as_uint(hi);
+      px[2 * i]      = __float_as_uint(__fmaf_rn(hi, -4096.0f, wf));
+    }
+    else
+    {
+      px[2 * i]     = w[i] & 0xfffu;
+      px[2 * i + 1] = w[i] >> 12;
+    }
+  }
+}
+
+__device__ __forceinline__ void load_org8(const uint32_t* p, uint32_t (&o)[8])
+{
+  const uint4 o0 = *reinterpret_cast<const uint4*>(p);
+  const uint4 o1 = *reinterpret_cast<const uint4*>(p + 4);
+  o[0] = o0.x; o[1] = o0.y; o[2] = o0.z; o[3] = o0.w;
+  o[4] = o1.x; o[5] = o1.y; o[6] = o1.z; o[7] = o1.w;
+}
+
+template <int NFP, bool FPU, int DY>
+__global__ void __launch_bounds__(kTreeMaxThreads, DY == 2 ? 2 : 3) me_tree_sad_kernel(TreeParams p)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   uint32_t*           s_org  = reinterpret_cast<uint32_t*>(smem + kOffOrg);
   unsigned long long* s_best = reinterpret_cast<unsigned long long*>(smem + kOffBest);
   CuInfo*             s_cu   = reinterpret_cast<CuInfo*>(smem + kOffCu);
   int*                s_misc = reinterpret_cast<int*>(smem + kOffMisc);
-  uint16_t*           s_ref  = reinterpret_cast<uint16_t*>(smem + kOffRef);
+  uint32_t*           s_lut  = reinterpret_cast<uint32_t*>(smem + kOffLut);
+  const int           gxPad = tree_gx_pad(p.maxGx), rowsPad = tree_rows_pad(p.maxRows);
+  uint8_t*            s_minbx = smem + kOffTab;
+  uint8_t*            s_by    = s_minbx + kCheckSlots * gxPad;
+  uint16_t*           s_ref   = reinterpret_cast<uint16_t*>(smem + tree_off_ref(p.maxGx, p.maxRows));
 
-  const int tid    = threadIdx.x;
+  const int tid = threadIdx.x, nthr = blockDim.x;
   const int region = blockIdx.x;
   const int pair   = blockIdx.y;
   const int rx = region % p.g.nRegX, ry = region / p.g.nRegX;
   const int x0 = rx * 32, y0 = ry * 32;
   const int nCU = p.g.off[5];
+  const double lambda   = p.lambda;
+  const int    imvShift = p.imvShift;
 
   // ---- 1. windows of the 23 CUs touching this region ------------------------------------------------
   if (tid < kSlots)
@@ -123,6 +207,7 @@ __global__ void __launch_bounds__(kTreeThreads, 3) me_tree_sad_kernel(TreeParams
     s_cu[tid]   = ci;
     s_best[tid] = ~0ull;
   }
+  for (int i = tid; i < 512; i += nthr) s_lut[i] = i < 256 ? mv_cost(lambda, (uint32_t) i) : kLutInvalid;
   __syncthreads();
   if (tid == 0)
   {
@@ -154,10 +239,35 @@ __global__ void __launch_bounds__(kTreeThreads, 3) me_tree_sad_kernel(TreeParams
   const bool writeSurf = s_cu[20].idx >= 0 && (s_cu[21].idx >= 0 || s_cu[22].idx >= 0);
   if (tid == 0) p.regInfo[(size_t) pair * p.g.nRegX * p.g.nRegY + region] = make_int4(wl8, wt, ngx, nrows);
 
-  // ---- 2. original samples of the region, widened to 32 bit -------------------------------------------
+  // ---- 2. rate tables of the 21 CUs: min bitsX per 8-wide displacement group, bitsY per row (255 = outside) ----
+  for (int i = tid; i < kCheckSlots * ngx; i += nthr)
+  {
+    const int    slot = i / ngx, g = i - slot * ngx;
+    const CuInfo ci   = s_cu[slot];
+    uint32_t     mb   = 255;
+    if (ci.idx >= 0)
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+      {
+        const int dx = wl8 + g * 8 + k;
+        if (dx >= ci.l && dx <= ci.r) mb = min(mb, eg_bits((dx * 4 - ci.pqx) >> imvShift));
+      }
+    s_minbx[slot * gxPad + g] = (uint8_t) mb;
+  }
+  for (int i = tid; i < kCheckSlots * nrows; i += nthr)
+  {
+    const int    slot = i / nrows, r = i - slot * nrows;
+    const CuInfo ci   = s_cu[slot];
+    const int    dy   = wt + r;
+    uint32_t     b    = 255;
+    if (ci.idx >= 0 && dy >= ci.t && dy <= ci.b) b = eg_bits((dy * 4 - ci.pqy) >> imvShift);
+    s_by[slot * rowsPad + r] = (uint8_t) b;
+  }
+
+  // ---- 3. original samples of the region, widened to 32 bit -------------------------------------------
   const DevPic cur = p.cur[pair];
   const DevPic ref = p.ref[pair];
-  for (int i = tid; i < 1024; i += kTreeThreads)
+  for (int i = tid; i < 1024; i += nthr)
   {
     const int y = i >> 5, x = i & 31;
     s_org[i]    = (uint32_t) (uint16_t) cur.origin[(size_t) (y0 + y) * cur.stride + x0 + x];
@@ -165,42 +275,60 @@ __global__ void __launch_bounds__(kTreeThreads, 3) me_tree_sad_kernel(TreeParams
 
   const int refStride = ngx * 8 + 32;   // samples per staged row
   uint32_t* surf = p.surf + ((size_t) pair * p.g.nRegX * p.g.nRegY + region) * p.surfCap;
-  const double lambda   = p.lambda;
-  const int    imvShift = p.imvShift;
 
-  // ---- 3. bands of displacement rows ----------------------------------------------------------------
+  // ---- 4. bands of displacement rows ----------------------------------------------------------------
   for (int band0 = blockIdx.z * p.bandRows; band0 < nrows; band0 += gridDim.z * p.bandRows)
   {
     const int bh = min(p.bandRows, nrows - band0);
-    __syncthreads();   // previous band fully consumed (and s_org written)
+    const int tileRows = (bh + DY - 1) / DY;
+    __syncthreads();   // previous band fully consumed (and s_org / tables written)
+    if (tid == 0) s_misc[5] = 0;   // tile counter of this band
     {
       const int      vecPerRow = refStride >> 3;
-      const int      nvec      = (bh + 31) * vecPerRow;
+      const int      nvec      = (tileRows * DY + 31) * vecPerRow;
       const int16_t* src       = ref.origin + (ptrdiff_t) (y0 + wt + band0) * ref.stride + (x0 + wl8);
-      for (int i = tid; i < nvec; i += kTreeThreads)
+      for (int i = tid; i < nvec; i += nthr)
       {
         const int r = i / vecPerRow, c = i - r * vecPerRow;
-        const uint4 v = *reinterpret_cast<const uint4*>(src + (ptrdiff_t) r * ref.stride + c * 8);
+        uint4 v = *reinterpret_cast<const uint4*>(src + (ptrdiff_t) r * ref.stride + c * 8);
+        v.x = pack12(v.x);
+        v.y = pack12(v.y);
+        v.z = pack12(v.z);
+        v.w = pack12(v.w);
         *reinterpret_cast<uint4*>(s_ref + r * refStride + c * 8) = v;
       }
     }
     __syncthreads();
 
-    const int ntiles = ngx * bh;
-    for (int t = tid; t < ntiles; t += kTreeThreads)
+    // Tiles (8 displacements x DY rows) are handed out to warps 32 at a time from a shared counter, so that all
+    // warps of the CTA finish within one tile of each other whatever the window size is.
+    const int ntiles = ngx * tileRows;
+    for (;;)
     {
-      const int       dyi = t / ngx, gx = t - dyi * ngx;
-      const int       dy = wt + band0 + dyi, dx0 = wl8 + gx * 8;
-      const uint16_t* refTile = s_ref + dyi * refStride + gx * 8;
-      uint32_t        a32[8];
+      int tbase = 0;
+      if ((tid & 31) == 0) tbase = atomicAdd(&s_misc[5], 32);
+      tbase = __shfl_sync(0xffffffffu, tbase, 0);
+      if (tbase >= ntiles) break;
+      const int t = tbase + (tid & 31);
+      if (t >= ntiles) continue;
+      const int       tr = t / ngx, gx = t - tr * ngx;
+      const int       row0 = band0 + tr * DY;          // displacement row index of this tile's first row
+      const int       dx0 = wl8 + gx * 8;
+      const bool      row1ok = DY == 2 && (tr * DY + 1 < bh);
+      const uint16_t* refTile = s_ref + tr * DY * refStride + gx * 8;
+      uint32_t        a32[DY][8];
 #pragma unroll
-      for (int k = 0; k < 8; k++) a32[k] = 0;
+      for (int d = 0; d < DY; d++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) a32[d][k] = 0;
 
       for (int q = 0; q < 4; q++)
       {
-        uint32_t a16[8];
+        uint32_t a16[DY][8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) a16[k] = 0;
+        for (int d = 0; d < DY; d++)
+#pragma unroll
+          for (int k = 0; k < 8; k++) a16[d][k] = 0;
         if ((mask8 >> (q * 4)) & 15)
         {
           for (int s = 0; s < 4; s++)
@@ -208,46 +336,91 @@ __global__ void __launch_bounds__(kTreeThreads, 3) me_tree_sad_kernel(TreeParams
             const int slot = q * 4 + s;
             if (!((mask8 >> slot) & 1)) continue;
             const int bx = (q & 1) * 16 + (s & 1) * 8, by = (q >> 1) * 16 + (s >> 1) * 8;
-            uint32_t  a8[8];
+            const uint32_t* orgRow = s_org + by * 32 + bx;
+            const uint16_t* refRow = refTile + by * refStride + bx;
+            uint32_t        a8[DY][8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) a8[k] = 0;
+            for (int d = 0; d < DY; d++)
 #pragma unroll
-            for (int r = 0; r < 8; r++)
+              for (int k = 0; k < 8; k++) a8[d][k] = 0;
+            if (DY == 1)
             {
-              const uint4 o0 = *reinterpret_cast<const uint4*>(s_org + (by + r) * 32 + bx);
-              const uint4 o1 = *reinterpret_cast<const uint4*>(s_org + (by + r) * 32 + bx + 4);
-              const uint4 w0 = *reinterpret_cast<const uint4*>(refTile + (by + r) * refStride + bx);
-              const uint4 w1 = *reinterpret_cast<const uint4*>(refTile + (by + r) * refStride + bx + 8);
-              const uint32_t o[8]   = { o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w };
-              const uint32_t px[16] = { w0.x & 0xffffu, w0.x >> 16, w0.y & 0xffffu, w0.y >> 16,
-                                        w0.z & 0xffffu, w0.z >> 16, w0.w & 0xffffu, w0.w >> 16,
-                                        w1.x & 0xffffu, w1.x >> 16, w1.y & 0xffffu, w1.y >> 16,
-                                        w1.z & 0xffffu, w1.z >> 16, w1.w & 0xffffu, w1.w >> 16 };
-#pragma unroll
-              for (int k = 0; k < 8; k++)
-#pragma unroll
-                for (int i = 0; i < 8; i++) a8[k] = __usad(o[i], px[i + k], a8[k]);
+#pragma unroll 2
+              for (int r = 0; r < 8; r++)
+              {
+                uint32_t o[8], px[16];
+                load_org8(orgRow + r * 32, o);
+                load_ref16<FPU>(refRow + r * refStride, px);
+                sad_row<NFP>(a8[0], o, px);
+              }
             }
-            check8(a8, &s_cu[slot], &s_best[slot], dx0, dy, lambda, imvShift);
+            else
+            {
+              // reference row jr serves original row jr at displacement row 0 and original row jr-1 at row 1;
+              // kept as a rolled loop (uniform branches) so that the body stays inside the instruction cache
+#pragma unroll 1
+              for (int jr = 0; jr < 9; jr++)
+              {
+                uint32_t o[8], px[16];
+                load_ref16<FPU>(refRow + jr * refStride, px);
+                if (jr < 8)
+                {
+                  load_org8(orgRow + jr * 32, o);
+                  sad_row<NFP>(a8[0], o, px);
+                }
+                if (jr > 0)
+                {
+                  load_org8(orgRow + (jr - 1) * 32, o);
+                  sad_row<NFP>(a8[DY - 1], o, px);
+                }
+              }
+            }
 #pragma unroll
-            for (int k = 0; k < 8; k++) a16[k] += a8[k];
+            for (int d = 0; d < DY; d++)
+            {
+              if (d == 0 || row1ok)
+              {
+                const uint32_t lb = s_lut[s_minbx[slot * gxPad + gx] + s_by[slot * rowsPad + row0 + d]];
+                check8(a8[d], lb, &s_cu[slot], &s_best[slot], dx0, wt + row0 + d, lambda, imvShift);
+              }
+#pragma unroll
+              for (int k = 0; k < 8; k++) a16[d][k] += a8[d][k];
+            }
           }
-          if (s_cu[16 + q].idx >= 0) check8(a16, &s_cu[16 + q], &s_best[16 + q], dx0, dy, lambda, imvShift);
+          if (s_cu[16 + q].idx >= 0)
+#pragma unroll
+            for (int d = 0; d < DY; d++)
+              if (d == 0 || row1ok)
+              {
+                const uint32_t lb = s_lut[s_minbx[(16 + q) * gxPad + gx] + s_by[(16 + q) * rowsPad + row0 + d]];
+                check8(a16[d], lb, &s_cu[16 + q], &s_best[16 + q], dx0, wt + row0 + d, lambda, imvShift);
+              }
         }
 #pragma unroll
-        for (int k = 0; k < 8; k++) a32[k] += a16[k];
+        for (int d = 0; d < DY; d++)
+#pragma unroll
+          for (int k = 0; k < 8; k++) a32[d][k] += a16[d][k];
       }
-      if (s_cu[20].idx >= 0) check8(a32, &s_cu[20], &s_best[20], dx0, dy, lambda, imvShift);
-      if (writeSurf)
+#pragma unroll
+      for (int d = 0; d < DY; d++)
       {
-        uint4* dst = reinterpret_cast<uint4*>(surf + (size_t) (band0 + dyi) * (ngx * 8) + gx * 8);
-        dst[0]     = make_uint4(a32[0], a32[1], a32[2], a32[3]);
-        dst[1]     = make_uint4(a32[4], a32[5], a32[6], a32[7]);
+        if (d == 1 && !row1ok) continue;
+        if (s_cu[20].idx >= 0)
+        {
+          const uint32_t lb = s_lut[s_minbx[20 * gxPad + gx] + s_by[20 * rowsPad + row0 + d]];
+          check8(a32[d], lb, &s_cu[20], &s_best[20], dx0, wt + row0 + d, lambda, imvShift);
+        }
+        if (writeSurf)
+        {
+          uint4* dst = reinterpret_cast<uint4*>(surf + (size_t) (row0 + d) * (ngx * 8) + gx * 8);
+          dst[0]     = make_uint4(a32[d][0], a32[d][1], a32[d][2], a32[d][3]);
+          dst[1]     = make_uint4(a32[d][4], a32[d][5], a32[d][6], a32[d][7]);
+        }
       }
     }
   }
   __syncthreads();
-  if (tid < 21 && s_cu[tid].idx >= 0 && s_best[tid] != ~0ull)
+  if (tid < kCheckSlots && s_cu[tid].idx >= 0 && s_best[tid] != ~0ull)
     atomicMin(p.keys + (size_t) pair * nCU + s_cu[tid].idx, s_best[tid]);
 }
 
@@ -387,24 +560,59 @@ __global__ void __launch_bounds__(kUpperThreads) me_tree_upper_kernel(TreeParams
 
 }   // namespace
 
-size_t tree_sad_smem_bytes(int maxGx, int bandRows)
+size_t tree_sad_smem_bytes(int maxGx, int maxRows, int bandRows)
 {
-  return (size_t) kOffRef + (size_t) (bandRows + 31) * (size_t) (maxGx * 8 + 32) * 2;
+  return (size_t) tree_off_ref(maxGx, maxRows) + (size_t) (bandRows + 1 + 31) * (size_t) (maxGx * 8 + 32) * 2;
 }
 
-cudaError_t launch_tree_sad(const TreeParams& p, int nPairs, cudaStream_t st)
+// Tuning knobs (development): VTMME_TREE_VARIANT="nfp,fpu,dy,threads"
+static void tree_variant(int& nfp, int& fpu, int& dy, int& threads)
 {
-  const size_t smem = tree_sad_smem_bytes(p.maxGx, p.bandRows);
+  static int v[4] = { -1, 0, 0, 0 };
+  if (v[0] < 0)
+  {
+    v[0] = 2; v[1] = 1; v[2] = 1; v[3] = 256;
+    if (const char* e = getenv("VTMME_TREE_VARIANT")) sscanf(e, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]);
+  }
+  nfp = v[0]; fpu = v[1]; dy = v[2]; threads = v[3];
+}
+
+template <int NFP, bool FPU, int DY>
+static cudaError_t launch_tree_sad_t(const TreeParams& p, int nPairs, int threads, size_t smem, cudaStream_t st)
+{
   static size_t configured = 0;
   if (smem > configured)
   {
-    cudaError_t e = cudaFuncSetAttribute(me_tree_sad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    cudaError_t e = cudaFuncSetAttribute(me_tree_sad_kernel<NFP, FPU, DY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
   dim3 grid(p.g.nRegX * p.g.nRegY, nPairs, 1);
-  me_tree_sad_kernel<<<grid, kTreeThreads, smem, st>>>(p);
+  me_tree_sad_kernel<NFP, FPU, DY><<<grid, threads, smem, st>>>(p);
   return cudaGetLastError();
+}
+
+cudaError_t launch_tree_sad(const TreeParams& p, int nPairs, cudaStream_t st)
+{
+  int nfp, fpu, dy, threads;
+  tree_variant(nfp, fpu, dy, threads);
+  const size_t smem = tree_sad_smem_bytes(p.maxGx, p.maxRows, p.bandRows);
+  if (threads <= 0)
+  {
+    // even out the tile loop: interior regions have (2*sr+1 -> groups) x rows tiles
+    const int ngx = (2 * p.sr + 1 + 7) / 8, rows = (2 * p.sr + 1 + dy - 1) / dy;
+    const int tiles = ngx * rows, iters = (tiles + kTreeMaxThreads - 1) / kTreeMaxThreads;
+    threads = ((tiles + iters - 1) / iters + 127) & ~127;   // whole multiples of 4 warps: one per SM sub-partition
+    if (threads > kTreeMaxThreads) threads = kTreeMaxThreads;
+    if (threads < 128) threads = 128;
+  }
+#define VTMME_TREE_CASE(N, F, D) \
+  if (nfp == N && fpu == F && dy == D) return launch_tree_sad_t<N, F != 0, D>(p, nPairs, threads, smem, st);
+  VTMME_TREE_CASE(0, 0, 1) VTMME_TREE_CASE(0, 1, 1) VTMME_TREE_CASE(1, 1, 1) VTMME_TREE_CASE(2, 1, 1) VTMME_TREE_CASE(3, 1, 1)
+  VTMME_TREE_CASE(0, 0, 2) VTMME_TREE_CASE(0, 1, 2) VTMME_TREE_CASE(1, 1, 2) VTMME_TREE_CASE(2, 1, 2) VTMME_TREE_CASE(3, 1, 2)
+  VTMME_TREE_CASE(2, 0, 2) VTMME_TREE_CASE(2, 0, 1)
+#undef VTMME_TREE_CASE
+  return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_tree_upper(const TreeParams& p, int nPairs, cudaStream_t st)
@@ -415,3 +623,129 @@ cudaError_t launch_tree_upper(const TreeParams& p, int nPairs, cudaStream_t st)
 }
 
 }   // namespace vtmme
+
+// ---- development microbenchmark: the 8x8-block SAD inner loop alone (no staging, no argmin, no tails) ----------
+namespace vtmme {
+namespace {
+template <int NFP, bool FPU, int DY>
+__global__ void __launch_bounds__(kTreeMaxThreads, DY == 2 ? 2 : 3) sad_block_bench_kernel(uint32_t* out, int iters)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint32_t* s_org = reinterpret_cast<uint32_t*>(smem);
+  uint16_t* s_ref = reinterpret_cast<uint16_t*>(smem + 4096);
+  constexpr int refStride = 17 * 8 + 32;
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_org[i] = (i * 2654435761u) >> 22;
+  for (int i = threadIdx.x; i < 48 * refStride / 2; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(s_ref)[i] = pack12((((i * 40503u) >> 6) & 0x3ffu) | ((((i * 9973u) >> 5) & 0x3ffu) << 16));
+  __syncthreads();
+  uint32_t acc[DY][8];
+#pragma unroll
+  for (int d = 0; d < DY; d++)
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[d][k] = 0;
+  const int gx = threadIdx.x % 17, tr = (threadIdx.x / 17) % 6;
+  const uint16_t* refTile = s_ref + tr * DY * refStride + gx * 8;
+  for (int it = 0; it < iters; it++)
+  {
+    for (int blk = 0; blk < 16; blk++)
+    {
+      const int bx = (blk & 3) * 8, by = (blk >> 2) * 8;
+      const uint32_t* orgRow = s_org + by * 32 + bx;
+      const uint16_t* refRow = refTile + by * refStride + bx;
+      uint32_t a8[DY][8];
+#pragma unroll
+      for (int d = 0; d < DY; d++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) a8[d][k] = 0;
+      if (DY == 1)
+      {
+#pragma unroll 2
+        for (int r = 0; r < 8; r++)
+        {
+          uint32_t o[8], px[16];
+          load_org8(orgRow + r * 32, o);
+          load_ref16<FPU>(refRow + r * refStride, px);
+          sad_row<NFP>(a8[0], o, px);
+        }
+      }
+      else
+      {
+#pragma unroll 1
+        for (int jr = 0; jr < 9; jr++)
+        {
+          uint32_t o[8], px[16];
+          load_ref16<FPU>(refRow + jr * refStride, px);
+          if (jr < 8)
+          {
+            load_org8(orgRow + jr * 32, o);
+            sad_row<NFP>(a8[0], o, px);
+          }
+          if (jr > 0)
+          {
+            load_org8(orgRow + (jr - 1) * 32, o);
+            sad_row<NFP>(a8[DY - 1], o, px);
+          }
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < DY; d++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[d][k] += a8[d][k];
+    }
+  }
+  uint32_t r = 0;
+#pragma unroll
+  for (int d = 0; d < DY; d++)
+#pragma unroll
+    for (int k = 0; k < 8; k++) r += acc[d][k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+template <int NFP, bool FPU, int DY>
+double run_sad_block_bench(int threads, int ctasPerSm, int iters, int sms, uint32_t* dout, cudaStream_t st)
+{
+  const size_t smem = 4096 + 48 * (17 * 8 + 32) * 2;
+  cudaFuncSetAttribute(sad_block_bench_kernel<NFP, FPU, DY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  sad_block_bench_kernel<NFP, FPU, DY><<<sms * ctasPerSm, threads, smem, st>>>(dout, 2);
+  cudaEventRecord(e0, st);
+  sad_block_bench_kernel<NFP, FPU, DY><<<sms * ctasPerSm, threads, smem, st>>>(dout, iters);
+  cudaEventRecord(e1, st);
+  cudaStreamSynchronize(st);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  // pixel-candidates per second
+  return (double) sms * ctasPerSm * threads * (double) iters * 16.0 * 64.0 * 8.0 * DY / (ms * 1e-3);
+}
+}   // namespace
+
+// returns pixel-candidates/s of the bare inner loop for (nfp, fpu, dy) at the given launch shape
+double sad_block_bench(int nfp, int fpu, int dy, int threads, int ctasPerSm, int iters)
+{
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  uint32_t* dout = nullptr;
+  cudaMalloc(&dout, (size_t) sms * ctasPerSm * threads * 4);
+  cudaStream_t st;
+  cudaStreamCreate(&st);
+  double r = -1;
+#define VTMME_BB_CASE(N, F, D) if (nfp == N && fpu == F && dy == D) r = run_sad_block_bench<N, F != 0, D>(threads, ctasPerSm, iters, sms, dout, st);
+  VTMME_BB_CASE(0, 0, 1) VTMME_BB_CASE(0, 1, 1) VTMME_BB_CASE(1, 1, 1) VTMME_BB_CASE(2, 1, 1) VTMME_BB_CASE(3, 1, 1)
+  VTMME_BB_CASE(0, 0, 2) VTMME_BB_CASE(0, 1, 2) VTMME_BB_CASE(1, 1, 2) VTMME_BB_CASE(2, 1, 2) VTMME_BB_CASE(3, 1, 2)
+  VTMME_BB_CASE(2, 0, 2) VTMME_BB_CASE(2, 0, 1)
+#undef VTMME_BB_CASE
+  cudaStreamDestroy(st);
+  cudaFree(dout);
+  return r;
+}
+}   // namespace vtmme
+
+extern "C" double vtmme_dev_sad_block_bench(int nfp, int fpu, int dy, int threads, int ctasPerSm, int iters)
+{
+  return vtmme::sad_block_bench(nfp, fpu, dy, threads, ctasPerSm, iters);
+}

@@ -35,6 +35,8 @@ struct vtmme_ctx
   size_t              predCap = 0;
   vtmme_cu_result*    dRes = nullptr;
   size_t              resCap = 0;
+  uint32_t*           dFracAcc = nullptr;
+  size_t              fracAccCap = 0;
 
   // scratch of the per-call job path
   unsigned char* dJobBuf = nullptr;
@@ -179,6 +181,7 @@ void vtmme_destroy(vtmme_ctx* ctx)
   cudaFree(ctx->dErr);
   cudaFree(ctx->dPred);
   cudaFree(ctx->dRes);
+  cudaFree(ctx->dFracAcc);
   cudaFree(ctx->dJobBuf);
   cudaFree(ctx->dJobSurf);
   if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
@@ -293,9 +296,10 @@ int vtmme_search_frames_device(vtmme_ctx* ctx, int nPairs, const int32_t* curPic
   // staging-pad and filter-tap reads stay inside VTMME_MIN_MARGIN whatever the search range is.
   if (prm->ctuSize < 8 || prm->ctuSize > 128)
     return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search_frames", "ctuSize must be in [8,128]");
-  // rows per band: keep the staged window under ~72 KB so three CTAs fit one SM
+  // rows per band: keep the staged window under ~100 KB so two CTAs fit one SM
   int bandRows = maxRows;
-  while (bandRows > 16 && tree_sad_smem_bytes(maxGx, bandRows) > 72 * 1024) bandRows = (bandRows + 1) / 2;
+  while (bandRows > 16 && tree_sad_smem_bytes(maxGx, maxRows, bandRows) > 100 * 1024) bandRows = (bandRows + 1) / 2;
+  bandRows = (bandRows + 1) & ~1;
   const size_t surfCap = (size_t) maxGx * 8 * maxRows;
 
   int rc;
@@ -304,6 +308,7 @@ int vtmme_search_frames_device(vtmme_ctx* ctx, int nPairs, const int32_t* curPic
   if ((rc = ensure(ctx, ctx->dKeys, ctx->keysCap, (size_t) nPairs * nCU * 8)) != VTMME_OK) return rc;
   if ((rc = ensure(ctx, ctx->dSurf, ctx->surfCapBytes, (size_t) nPairs * nReg * surfCap * 4)) != VTMME_OK) return rc;
   if ((rc = ensure(ctx, ctx->dRegInfo, ctx->regInfoCap, (size_t) nPairs * nReg * sizeof(int4))) != VTMME_OK) return rc;
+  if ((rc = ensure(ctx, ctx->dFracAcc, ctx->fracAccCap, frac_frame_acc_bytes(g, nPairs))) != VTMME_OK) return rc;
 
   VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dCur, hc.data(), nPairs * sizeof(DevPic), cudaMemcpyHostToDevice, ctx->stream));
   VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dRef, hr.data(), nPairs * sizeof(DevPic), cudaMemcpyHostToDevice, ctx->stream));
@@ -347,13 +352,14 @@ int vtmme_search_frames_device(vtmme_ctx* ctx, int nPairs, const int32_t* curPic
   fp.useHad   = prm->useHad;
   fp.fracMode = prm->fracMode;
   fp.lambda   = prm->lambdaMotion;
-  VTMME_CUDA_CHECK(ctx, launch_frac_frame(fp, nPairs, ctx->stream));
+  int fracLaunches = 0;
+  VTMME_CUDA_CHECK(ctx, launch_frac_frame(fp, ctx->dFracAcc, nPairs, ctx->stream, &fracLaunches));
   if (prof)
   {
     VTMME_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
     ctx->evValid = true;
   }
-  ctx->launches += 3;
+  ctx->launches += 2 + fracLaunches;
   return VTMME_OK;
 }
 
