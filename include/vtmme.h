@@ -161,6 +161,12 @@ int vtmme_interp_batch(vtmme_ctx* ctx, int comp, int vertical, const int16_t* dS
 int vtmme_interp_host(vtmme_ctx* ctx, int comp, int vertical, const int16_t* src, int srcStride, int16_t* dst,
                       int dstStride, int w, int h, int frac, int isFirst, int isLast, int bitDepth, int useAltHpel);
 
+/* The function-pointer flavour of the same filters: explicit taps, exactly the arguments the reference's table
+ * entries m_filterHor[taps][isFirst][isLast] / m_filterVer / m_filterCopy receive (InterpolationFilter.h:96-98).
+ * nTaps 8, 4 or 2; copy != 0 selects filterCopy<isFirst,isLast> (coeff ignored).  HOST pointers, synchronous. */
+int vtmme_filter_host(vtmme_ctx* ctx, int nTaps, int vertical, int isFirst, int isLast, int copy, const int16_t* src,
+                      int srcStride, int16_t* dst, int dstStride, int w, int h, const int16_t* coeff, int bitDepth);
+
 /* ---- measurement helpers ------------------------------------------------------------------------
  * Per-kernel timing of the frame path: when enabled, vtmme_search_frames[_device] brackets each of its
  * kernels with CUDA events on the context stream; vtmme_frame_kernel_ms returns the durations of the most

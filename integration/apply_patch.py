@@ -1,0 +1,122 @@
+#!/usr/bin/env python
+"""Creates a patched scratch copy of VTM 9.3 with the libvtmme hooks.
+
+  python integration/apply_patch.py [/root/reference] [oracle/_ref/patched]
+
+Nothing of the reference is stored in this repository: the script copies <ref>/source into the scratch directory
+(git-ignored) and inserts a handful of lines at anchors; the new files it adds (cuda/VtmCudaME.*, cuda/InitCUDA.cpp)
+are this repository's own (integration/vtm_cuda/).  INTEGRATION.md lists every insertion.
+"""
+import os
+import re
+import shutil
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def edit(path, fn):
+    src = open(path).read()
+    out = fn(src)
+    assert out != src, "anchor not found in " + path
+    open(path, "w").write(out)
+
+
+def once(src, anchor, repl, count=1):
+    assert src.count(anchor) >= 1, anchor
+    return src.replace(anchor, repl, count)
+
+
+def main():
+    ref = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+    dst = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "oracle", "_ref", "patched")
+    if os.path.isdir(dst):
+        shutil.rmtree(dst)
+    shutil.copytree(os.path.join(ref, "source"), os.path.join(dst, "source"))
+    lib = os.path.join(dst, "source", "Lib")
+    cuda = os.path.join(lib, "CommonLib", "cuda")
+    os.makedirs(cuda)
+    for f in ("VtmCudaME.h", "VtmCudaME.cpp", "InitCUDA.cpp"):
+        shutil.copy(os.path.join(HERE, "vtm_cuda", f), cuda)
+
+    # 1. RdCost.h: declare the hook next to initRdCostX86(), expose the selected motion lambda
+    edit(os.path.join(lib, "CommonLib", "RdCost.h"), lambda s: once(
+        s, "  void           setDistParam( DistParam &rcDP, const CPelBuf &org, const Pel* piRefY , int iRefStride, int bitDepth,",
+        "  void          initRdCostCUDA();                                              // libvtmme\n"
+        "  double        getSelectedMotionLambda() const { return m_motionLambda; }     // libvtmme\n"
+        "  void           setDistParam( DistParam &rcDP, const CPelBuf &org, const Pel* piRefY , int iRefStride, int bitDepth,"))
+    # 2. RdCost.cpp: call it right after initRdCostX86() in RdCost::init()
+    edit(os.path.join(lib, "CommonLib", "RdCost.cpp"), lambda s: once(
+        s, "  m_costMode                   = COST_STANDARD_LOSSY;",
+        "  initRdCostCUDA();   // libvtmme: after the X86 table, same entries\n\n  m_costMode                   = COST_STANDARD_LOSSY;"))
+    # 3. InterpolationFilter.h / .cpp
+    edit(os.path.join(lib, "CommonLib", "InterpolationFilter.h"), lambda s: once(
+        s, "  void filterHor(const ComponentID compID, Pel const* src,",
+        "  void initInterpolationFilterCUDA();   // libvtmme\n  void filterHor(const ComponentID compID, Pel const* src,"))
+    edit(os.path.join(lib, "CommonLib", "InterpolationFilter.cpp"), lambda s: re.sub(
+        r"(void InterpolationFilter::initInterpolationFilter\( bool enable \)\n\{\n(?:.*\n)*?#endif\n#endif\n)\}",
+        r"\1  if ( enable )\n  {\n    initInterpolationFilterCUDA();   // libvtmme\n  }\n}", s, count=1))
+
+    # 4. InterSearch.cpp: xMotionEstimation calls the batched entry instead of xPatternSearch + xPatternSearchFracDIF
+    def inter(s):
+        s = once(s, '#include "InterSearch.h"\n', '#include "InterSearch.h"\n#include "CommonLib/cuda/VtmCudaME.h"   // libvtmme\n')
+        # locals, placed at the second "Do integer search" marker (the one inside xMotionEstimation)
+        first = s.index("  //  Do integer search\n")
+        second = s.index("  //  Do integer search\n", first + 1)
+        s = s[:second] + ("  vtmcuda::SearchOut cudaOut;   // libvtmme\n  bool cudaFracDone = false;\n") + s[second:]
+        s = once(s, "    xPatternSearch( cStruct, rcMv, ruiCost);\n", """\
+    if( vtmcuda::enabled() && !m_cDistParam.applyWeight && m_lumaClpRng.bd <= 10 && !wrap
+        && !pu.cu->slice->getRefPic( eRefPicList, iRefIdxPred )->isRefScaled( pu.cs->pps ) )
+    {
+      // libvtmme: integer full search (+ fractional refinement when this call does one) on the GPU
+      vtmcuda::SearchIn in;
+      in.refPic       = pu.cu->slice->getRefPic( eRefPicList, iRefIdxPred );
+      in.x            = pu.Y().x;
+      in.y            = pu.Y().y;
+      in.w            = pu.Y().width;
+      in.h            = pu.Y().height;
+      in.org          = cStruct.pcPatternKey->buf;
+      in.orgStride    = cStruct.pcPatternKey->stride;
+      in.srLeft       = cStruct.searchRange.left;
+      in.srRight      = cStruct.searchRange.right;
+      in.srTop        = cStruct.searchRange.top;
+      in.srBottom     = cStruct.searchRange.bottom;
+      in.predQx       = predQuarter.getHor();
+      in.predQy       = predQuarter.getVer();
+      in.imvShift     = cStruct.imvShift;
+      in.subShiftMode = cStruct.subShiftMode;
+      in.bitDepth     = m_lumaClpRng.bd;
+      in.useHad       = m_pcEncCfg->getUseHADME() && !pu.cs->slice->getDisableSATDForRD();
+      in.useAltHpel   = cStruct.useAltHpelIf;
+      in.doFrac       = ( pu.cu->imv == 0 || pu.cu->imv == IMV_HPEL ) && !m_pcEncCfg->getMCTSEncConstraint();
+      in.lambdaMotion = m_pcRdCost->getSelectedMotionLambda();
+      vtmcuda::search( in, cudaOut );
+      rcMv.set( cudaOut.mvX, cudaOut.mvY );
+      ruiCost      = cudaOut.intSad;
+      cudaFracDone = in.doFrac;
+    }
+    else
+    {
+      xPatternSearch( cStruct, rcMv, ruiCost);
+    }
+""")
+        s = once(s, "    xPatternSearchFracDIF( pu, eRefPicList, iRefIdxPred, cStruct, rcMv, cMvHalf, cMvQter, ruiCost );\n", """\
+    if( cudaFracDone )   // libvtmme: the GPU call above already refined this MV
+    {
+      cMvHalf.set( cudaOut.halfX, cudaOut.halfY );
+      cMvQter.set( cudaOut.qterX, cudaOut.qterY );
+      ruiCost = cudaOut.fracCost;
+    }
+    else
+    {
+      xPatternSearchFracDIF( pu, eRefPicList, iRefIdxPred, cStruct, rcMv, cMvHalf, cMvQter, ruiCost );
+    }
+""")
+        return s
+    edit(os.path.join(lib, "EncoderLib", "InterSearch.cpp"), inter)
+    print("patched tree:", dst)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,38 @@
+#!/bin/bash
+# Encoder-level parity run (BASELINE configs 1-3): patched VTM (oracle/_ref/EncoderAppCUDA) with the GPU motion
+# search against the golden md5 of the unmodified CPU encoder (tests/golden/encoder_md5.json).
+#   bash integration/run_config.sh <1|2|3> [gpu|cpu] [frames]
+set -e
+CFGN=${1:-1}; MODE=${2:-gpu}; ROOT=$(cd "$(dirname "$0")/.." && pwd); W=$ROOT/gpurun_out/enc_c$CFGN; mkdir -p $W; cd $W
+case $CFGN in
+  1) WD=416; HT=240; FR=${3:-8}; BITS=8; CFG=encoder_lowdelay_P_vtm.cfg; SR=64; EXTRA="-q 32";;
+  2) WD=1920; HT=1080; FR=${3:-32}; BITS=10; CFG=encoder_randomaccess_vtm.cfg; SR=64; EXTRA="-q 32 --IntraPeriod=32";;
+  3) WD=3840; HT=2160; FR=${3:-16}; BITS=10; CFG=encoder_lowdelay_vtm.cfg; SR=128; EXTRA="-q 32";;
+esac
+python $ROOT/integration/make_yuv.py in.yuv --width $WD --height $HT --frames $FR --bits $BITS
+echo "input md5: $(md5sum in.yuv | cut -d' ' -f1)"
+ARGS="-c $ROOT/oracle/_ref/cfg/$CFG -i in.yuv -wdt $WD -hgt $HT -fr 30 -f $FR $EXTRA --InputBitDepth=$BITS --FastSearch=0 --SearchRange=$SR --SEIDecodedPictureHash=1"
+if [ "$MODE" = gpu ]; then
+  export VTMME_ENABLE=1; BIN=$ROOT/oracle/_ref/EncoderAppCUDA
+else
+  BIN=$ROOT/oracle/_ref/EncoderApp
+fi
+T0=$SECONDS
+$BIN $ARGS -b out_$MODE.bin -o rec_$MODE.yuv > enc_$MODE.log 2> enc_$MODE.err || { tail -20 enc_$MODE.err; tail -5 enc_$MODE.log; exit 1; }
+echo "wall $((SECONDS-T0)) s ($MODE)"
+grep -E "Total Time" enc_$MODE.log; tail -3 enc_$MODE.err
+$ROOT/oracle/_ref/DecoderApp -b out_$MODE.bin -o dec_$MODE.yuv > dec_$MODE.log 2>&1 || true
+echo "bitstream md5: $(md5sum out_$MODE.bin | cut -d' ' -f1)"
+echo "recon md5:     $(md5sum rec_$MODE.yuv | cut -d' ' -f1)"
+echo "decoded md5:   $(md5sum dec_$MODE.yuv | cut -d' ' -f1)  (decoder hash check: $(grep -c '(OK)' dec_$MODE.log) OK, $(grep -c 'ERROR' dec_$MODE.log) ERROR)"
+python - <<PY
+import json
+g = json.load(open("$ROOT/tests/golden/encoder_md5.json")).get("config$CFGN")
+import hashlib
+bs = hashlib.md5(open("out_$MODE.bin","rb").read()).hexdigest()
+if g and "$FR" == str(g["args"].split("-f ")[1].split()[0]):
+    print("PARITY", "OK" if bs == g["bitstream_md5"] else "MISMATCH", "bitstream md5 vs golden", g["bitstream_md5"])
+else:
+    print("no golden for this configuration/frame count")
+PY
+rm -f in.yuv rec_$MODE.yuv dec_$MODE.yuv

@@ -1,0 +1,153 @@
+// See VtmCudaME.h.  Host side of the drop-in, written in the reference's language (C++11) over the C ABI
+// (include/vtmme.h).
+#include "VtmCudaME.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+
+#include "CommonLib/CommonDef.h"
+#include "CommonLib/Picture.h"
+#include "vtmme.h"
+
+namespace vtmcuda
+{
+namespace
+{
+vtmme_ctx* g_ctx        = nullptr;
+uint64_t   g_calls      = 0;
+uint64_t   g_uploads    = 0;
+int        g_nextPicId  = 1;
+
+struct Uploaded
+{
+  int id;
+  int poc;
+};
+std::map<const Picture*, Uploaded> g_pics;   // Picture objects are recycled for new POCs: keyed by (object, POC)
+
+int envFlag( const char* name )
+{
+  const char* e = getenv( name );
+  return e && e[0] && e[0] != '0';
+}
+
+vtmme_ctx* ctx()
+{
+  if( !g_ctx )
+  {
+    const char* d  = getenv( "VTMME_DEVICE" );
+    const int   rc = vtmme_create( d ? atoi( d ) : 0, &g_ctx );
+    CHECK( rc != VTMME_OK, "vtmme_create failed (no CUDA device?) — the GPU motion search has no CPU fallback" );
+    atexit( printStats );
+  }
+  return g_ctx;
+}
+
+// device copy of a reference picture's luma recon plane; uploaded once per (picture, POC)
+int pictureId( const Picture* pic )
+{
+  auto it = g_pics.find( pic );
+  if( it != g_pics.end() && it->second.poc == pic->getPOC() )
+  {
+    return it->second.id;
+  }
+  const int     id  = it != g_pics.end() ? it->second.id : g_nextPicId++;
+  const CPelBuf buf = pic->getRecoBuf( COMPONENT_Y );   // (0,0) of the picture; border extended by extendPicBorder
+  const int     rc  = vtmme_upload_picture( ctx(), id, buf.buf, buf.stride, buf.width, buf.height, (int) pic->margin, 1 );
+  CHECK( rc != VTMME_OK, vtmme_last_error( g_ctx ) );
+  g_pics[pic] = Uploaded{ id, pic->getPOC() };
+  g_uploads++;
+  return id;
+}
+}   // namespace
+
+bool enabled()
+{
+  static int e = -1;
+  if( e < 0 ) e = envFlag( "VTMME_ENABLE" );
+  return e != 0;
+}
+
+bool tableHooksEnabled()
+{
+  static int e = -1;
+  if( e < 0 ) e = envFlag( "VTMME_TABLE_HOOKS" );
+  return e != 0;
+}
+
+void search( const SearchIn& in, SearchOut& out )
+{
+  vtmme_job j;
+  j.curPic   = 0;
+  j.refPic   = pictureId( in.refPic );
+  j.x        = in.x;
+  j.y        = in.y;
+  j.w        = in.w;
+  j.h        = in.h;
+  j.org      = in.org;
+  j.orgStride = in.orgStride;
+  j.srLeft   = in.srLeft;
+  j.srRight  = in.srRight;
+  j.srTop    = in.srTop;
+  j.srBottom = in.srBottom;
+  j.predQx   = in.predQx;
+  j.predQy   = in.predQy;
+  j.imvShift = in.imvShift;
+  // DistParam::subShift as RdCost::setDistParam derives it (RdCost.cpp:289-323); full search uses mode 0 or 2
+  j.subShift = 0;
+  if( in.subShiftMode == 2 && in.h > 8 && in.w <= 64 ) j.subShift = 1;
+  CHECK( in.subShiftMode != 0 && in.subShiftMode != 2, "unexpected subShiftMode on the full-search path" );
+  j.bitDepth     = in.bitDepth;
+  j.useHad       = in.useHad;
+  j.useAltHpel   = in.useAltHpel;
+  j.fracMode     = in.doFrac;
+  j.lambdaMotion = in.lambdaMotion;
+  vtmme_result r;
+  const int rc = vtmme_search( ctx(), &j, 1, &r );
+  CHECK( rc != VTMME_OK, vtmme_last_error( g_ctx ) );
+  out.mvX      = r.mvX;
+  out.mvY      = r.mvY;
+  out.intSad   = r.intSad;
+  out.halfX    = r.halfX;
+  out.halfY    = r.halfY;
+  out.qterX    = r.qterX;
+  out.qterY    = r.qterY;
+  out.fracCost = r.fracCost;
+  g_calls++;
+}
+
+uint64_t distHost( int kind, const int16_t* org, int orgStride, const int16_t* cur, int curStride, int w, int h, int subShift )
+{
+  uint64_t  v  = 0;
+  const int rc = vtmme_dist_host( ctx(), kind, org, orgStride, cur, curStride, w, h, subShift, &v );
+  CHECK( rc != VTMME_OK, vtmme_last_error( g_ctx ) );
+  return v;
+}
+
+void interpHost( int comp, int vertical, const int16_t* src, int srcStride, int16_t* dst, int dstStride, int w, int h,
+                 int frac, int isFirst, int isLast, int bitDepth, int useAltHpel )
+{
+  const int rc = vtmme_interp_host( ctx(), comp, vertical, src, srcStride, dst, dstStride, w, h, frac, isFirst, isLast,
+                                    bitDepth, useAltHpel );
+  CHECK( rc != VTMME_OK, vtmme_last_error( g_ctx ) );
+}
+
+void filterHost( int taps, int vertical, int isFirst, int isLast, int copy, const int16_t* src, int srcStride, int16_t* dst,
+                 int dstStride, int w, int h, const int16_t* coeff, int bitDepth )
+{
+  const int rc = vtmme_filter_host( ctx(), taps, vertical, isFirst, isLast, copy, src, srcStride, dst, dstStride, w, h, coeff,
+                                    bitDepth );
+  CHECK( rc != VTMME_OK, vtmme_last_error( g_ctx ) );
+}
+
+void printStats()
+{
+  if( g_ctx )
+  {
+    fprintf( stderr, "[vtmcuda] GPU motion searches: %llu, reference pictures uploaded: %llu, kernel launches: %llu\n",
+             (unsigned long long) g_calls, (unsigned long long) g_uploads, (unsigned long long) vtmme_launch_count( g_ctx ) );
+  }
+}
+}   // namespace vtmcuda
+

@@ -1,0 +1,53 @@
+// VTM-side glue of libvtmme (this repository's own code; added to a scratch copy of VTM 9.3 by
+// integration/apply_patch.py under source/Lib/CommonLib/cuda/).  Mirrors how x86/InitX86.cpp hooks the SIMD kernels:
+//   RdCost::initRdCostCUDA(), InterpolationFilter::initInterpolationFilterCUDA()  (cuda/InitCUDA.cpp)
+//   vtmcuda::search()  — the batched entry used by InterSearch::xMotionEstimation in place of
+//                        xPatternSearch (InterSearch.cpp:3432) + xPatternSearchFracDIF (:3476)
+#pragma once
+#include <cstdint>
+
+class Picture;
+
+namespace vtmcuda
+{
+// VTMME_ENABLE=1 in the environment switches the motion search to the GPU (read once; cf. --SIMD= in encmain.cpp:92-100)
+bool enabled();
+// VTMME_TABLE_HOOKS=1 additionally routes the distortion / interpolation dispatch tables through the GPU
+bool tableHooksEnabled();
+
+struct SearchIn
+{
+  const Picture* refPic;        // reference picture (recon plane, border extended)
+  int            x, y, w, h;    // PU luma rectangle
+  const int16_t* org;           // pattern (cStruct.pcPatternKey), host memory
+  int            orgStride;
+  int            srLeft, srRight, srTop, srBottom;   // cStruct.searchRange
+  int            predQx, predQy;                     // predictor, quarter-pel
+  int            imvShift;
+  int            subShiftMode;  // cStruct.subShiftMode (0 or 2)
+  int            bitDepth;
+  bool           useHad, useAltHpel, doFrac;
+  double         lambdaMotion;
+};
+
+struct SearchOut
+{
+  int      mvX, mvY;
+  uint64_t intSad;
+  int      halfX, halfY, qterX, qterY;
+  uint64_t fracCost;
+};
+
+// Runs one xMotionEstimation search on the GPU.  Any failure of the CUDA path is fatal (THROW): there is no
+// CPU fallback once the GPU path is enabled.
+void search( const SearchIn& in, SearchOut& out );
+
+// per-block table entries (used by InitCUDA.cpp)
+uint64_t distHost( int kind, const int16_t* org, int orgStride, const int16_t* cur, int curStride, int w, int h, int subShift );
+void     interpHost( int comp, int vertical, const int16_t* src, int srcStride, int16_t* dst, int dstStride, int w, int h,
+                     int frac, int isFirst, int isLast, int bitDepth, int useAltHpel );
+// table-entry flavour of the filters: explicit taps (what m_filterHor/m_filterVer/m_filterCopy entries receive)
+void     filterHost( int taps, int vertical, int isFirst, int isLast, int copy, const int16_t* src, int srcStride, int16_t* dst,
+                     int dstStride, int w, int h, const int16_t* coeff, int bitDepth );
+void     printStats();
+}   // namespace vtmcuda

@@ -22,7 +22,8 @@ namespace {
 constexpr int kItemWarps  = 4;
 constexpr int kChunk      = 16;
 constexpr int kPatchW     = kChunk + 8;          // 24
-constexpr int kPlaneElems = kPatchW * kChunk;    // rows [-4, ch+4) x cols [0, cw)
+constexpr int kPlaneStride = kChunk + 4;         // 20 words: rows of one 8-lane group fall into distinct 16-byte bank groups
+constexpr int kPlaneElems = kPatchW * kPlaneStride;   // rows [-4, ch+4) x cols [0, cw)
 
 struct __align__(16) ItemSmem
 {
@@ -30,6 +31,7 @@ struct __align__(16) ItemSmem
   int16_t  org[kChunk * kChunk];
   uint16_t patch[kPatchW * kPatchW];
   uint32_t acc[12];
+  int32_t  cf[4][8];                // luma filter taps of the four quarter-pel phases
 };
 
 struct ItemGeom
@@ -86,6 +88,7 @@ __device__ __forceinline__ void item_stage(ItemSmem& sm, const int16_t* __restri
   const int hr   = max(2, 14 - bitDepth);
   const int maxv = (1 << bitDepth) - 1;
   if (lane < 12) sm.acc[lane] = 0;
+  sm.cf[lane >> 3][lane & 7] = c_lumaFilter[(lane >> 3) * 4][lane & 7];
   // 1. original chunk and reference patch rows/cols [-4, +4)
 #pragma unroll
   for (int i = lane; i < cw * ch; i += 32)
@@ -118,7 +121,7 @@ __device__ __forceinline__ void item_stage(ItemSmem& sm, const int16_t* __restri
     {
       const int dq = cqx + (p - 1) * step;
       const int ix = dq >> 2, px = dq & 3;   // ix in {-1, 0}
-      int32_t*  dst = sm.plane[p] + lane * kChunk;
+      int32_t*  dst = sm.plane[p] + lane * kPlaneStride;
       if (px == 0)
       {
 #pragma unroll
@@ -132,7 +135,7 @@ __device__ __forceinline__ void item_stage(ItemSmem& sm, const int16_t* __restri
       {
         int cf[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) cf[k] = c_lumaFilter[px * 4][k];
+        for (int k = 0; k < 8; k++) cf[k] = sm.cf[px][k];
         const int shift = 6 - hr, off = 8192 << shift;
 #pragma unroll
         for (int c = 0; c < cw; c++)
@@ -159,7 +162,7 @@ __device__ __forceinline__ void item_stage(ItemSmem& sm, const int16_t* __restri
     const int  dqy = cqy + tab[c][1] * step;
     const int  iy = dqy >> 2, py = dqy & 3;
     const int  y = ty + lit;
-    const int32_t* pp = sm.plane[tab[c][0] + 1] + (y + iy + 4) * kChunk + tx;
+    const int32_t* pp = sm.plane[tab[c][0] + 1] + (y + iy + 4) * kPlaneStride + tx;
     int d[8];
     if (py == 0)
     {
@@ -174,14 +177,14 @@ __device__ __forceinline__ void item_stage(ItemSmem& sm, const int16_t* __restri
     }
     else
     {
-      const int16_t* cfp = c_lumaFilter[py * 4];
+      const int32_t* cfp = sm.cf[py];
       int            sum[8];
 #pragma unroll
       for (int i = 0; i < 8; i++) sum[i] = 0;
 #pragma unroll
       for (int k = 0; k < 8; k++)
       {
-        const int32_t* row = pp + (k - 3) * kChunk;
+        const int32_t* row = pp + (k - 3) * kPlaneStride;
         const int4     a = *reinterpret_cast<const int4*>(row), b = *reinterpret_cast<const int4*>(row + 4);
         const int      cf = cfp[k];
         sum[0] += a.x * cf; sum[1] += a.y * cf; sum[2] += a.z * cf; sum[3] += a.w * cf;
@@ -195,9 +198,15 @@ __device__ __forceinline__ void item_stage(ItemSmem& sm, const int16_t* __restri
         d[i]        = min(max(v, 0), maxv);
       }
     }
-    const int16_t* op = sm.org + y * kChunk + tx;
-#pragma unroll
-    for (int i = 0; i < 8; i++) d[i] = op[i] - d[i];
+    const uint4 ow = *reinterpret_cast<const uint4*>(sm.org + y * kChunk + tx);
+    d[0] = (int) (short) (ow.x & 0xffffu) - d[0];
+    d[1] = ((int) ow.x >> 16) - d[1];
+    d[2] = (int) (short) (ow.y & 0xffffu) - d[2];
+    d[3] = ((int) ow.y >> 16) - d[3];
+    d[4] = (int) (short) (ow.z & 0xffffu) - d[4];
+    d[5] = ((int) ow.z >> 16) - d[5];
+    d[6] = (int) (short) (ow.w & 0xffffu) - d[6];
+    d[7] = ((int) ow.w >> 16) - d[7];
     uint32_t v;
     if (HAD)
       v = satd_tile_rows<8, 8>(d, lit);

@@ -107,6 +107,9 @@ cudaError_t launch_dist_batch(int kind, const int16_t* org, int orgStride, long 
 cudaError_t launch_interp_batch(int comp, int vertical, const int16_t* src, int srcStride, long long srcBlockStride,
                                 int16_t* dst, int dstStride, long long dstBlockStride, int w, int h, int frac, int isFirst,
                                 int isLast, int bitDepth, int useAltHpel, int n, cudaStream_t st);
+cudaError_t launch_filter_batch(int taps, int vertical, int isFirst, int isLast, int copy, const int16_t* src, int srcStride,
+                                long long srcBlockStride, int16_t* dst, int dstStride, long long dstBlockStride, int w, int h,
+                                const int16_t* coeff, int bitDepth, int n, cudaStream_t st);
 cudaError_t launch_extend_border(DevPic pic, cudaStream_t st);
 
 }   // namespace vtmme

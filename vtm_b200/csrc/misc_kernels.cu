@@ -204,6 +204,30 @@ cudaError_t launch_dist_batch(int kind, const int16_t* org, int orgStride, long 
   return cudaGetLastError();
 }
 
+cudaError_t launch_filter_batch(int taps, int vertical, int isFirst, int isLast, int copy, const int16_t* src, int srcStride,
+                                long long srcBlockStride, int16_t* dst, int dstStride, long long dstBlockStride, int w, int h,
+                                const int16_t* coeff, int bitDepth, int n, cudaStream_t st)
+{
+  InterpArgs a;
+  a.src = src;
+  a.dst = dst;
+  a.srcBlk = srcBlockStride;
+  a.dstBlk = dstBlockStride;
+  a.srcStride = srcStride;
+  a.dstStride = dstStride;
+  a.w = w;
+  a.h = h;
+  a.vertical = vertical;
+  a.isFirst  = isFirst;
+  a.isLast   = isLast;
+  a.bitDepth = bitDepth;
+  a.copy     = copy;
+  a.taps     = taps;
+  for (int k = 0; k < 8; k++) a.coeff[k] = (!copy && k < taps) ? coeff[k] : 0;
+  interp_batch_kernel<<<n, 128, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_interp_batch(int comp, int vertical, const int16_t* src, int srcStride, long long srcBlockStride,
                                 int16_t* dst, int dstStride, long long dstBlockStride, int w, int h, int frac, int isFirst,
                                 int isLast, int bitDepth, int useAltHpel, int n, cudaStream_t st)

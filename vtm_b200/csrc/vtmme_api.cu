@@ -640,3 +640,34 @@ extern "C" int vtmme_interp_host(vtmme_ctx* ctx, int comp, int vertical, const i
   for (int y = 0; y < h; y++) memcpy(dst + (size_t) y * dstStride, hd + (size_t) y * w, (size_t) w * 2);
   return VTMME_OK;
 }
+
+extern "C" int vtmme_filter_host(vtmme_ctx* ctx, int nTaps, int vertical, int isFirst, int isLast, int copy, const int16_t* src,
+                                 int srcStride, int16_t* dst, int dstStride, int w, int h, const int16_t* coeff, int bitDepth)
+{
+  if (!ctx) return VTMME_ERR_ARG;
+  if (!src || !dst || (!copy && !coeff) || (nTaps != 8 && nTaps != 4 && nTaps != 2) || w < 1 || h < 1 || w > 256 || h > 256 ||
+      bitDepth < 8 || bitDepth > 10)
+    return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_filter_host", "bad argument");
+  VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  const int before = copy ? 0 : nTaps / 2 - 1, after = copy ? 0 : nTaps / 2;
+  const int sw = w + (vertical ? 0 : before + after), sh = h + (vertical ? before + after : 0);
+  const size_t srcBytes = align256((size_t) sw * sh * 2), dstBytes = align256((size_t) w * h * 2);
+  int rc;
+  if ((rc = ensure_pinned(ctx, srcBytes + dstBytes)) != VTMME_OK) return rc;
+  if ((rc = ensure(ctx, ctx->dJobBuf, ctx->jobBufCap, srcBytes + dstBytes)) != VTMME_OK) return rc;
+  int16_t*       hs = reinterpret_cast<int16_t*>(ctx->hPinned);
+  const int16_t* s0 = src - (vertical ? (ptrdiff_t) before * srcStride : before);
+  for (int y = 0; y < sh; y++) memcpy(hs + (size_t) y * sw, s0 + (ptrdiff_t) y * srcStride, (size_t) sw * 2);
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dJobBuf, ctx->hPinned, srcBytes, cudaMemcpyHostToDevice, ctx->stream));
+  const int16_t* dsrc = reinterpret_cast<int16_t*>(ctx->dJobBuf) + (vertical ? (size_t) before * sw : before);
+  VTMME_CUDA_CHECK(ctx, launch_filter_batch(nTaps, vertical, isFirst, isLast, copy, dsrc, sw, 0,
+                                            reinterpret_cast<int16_t*>(ctx->dJobBuf + srcBytes), w, 0, w, h, coeff, bitDepth,
+                                            1, ctx->stream));
+  ctx->launches += 1;
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->hPinned + srcBytes, ctx->dJobBuf + srcBytes, (size_t) w * h * 2,
+                                        cudaMemcpyDeviceToHost, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  const int16_t* hd = reinterpret_cast<int16_t*>(ctx->hPinned + srcBytes);
+  for (int y = 0; y < h; y++) memcpy(dst + (size_t) y * dstStride, hd + (size_t) y * w, (size_t) w * 2);
+  return VTMME_OK;
+}

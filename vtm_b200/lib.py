@@ -18,7 +18,7 @@ ERR_NAMES = {0: "VTMME_OK", -1: "VTMME_ERR_CUDA", -2: "VTMME_ERR_ARG", -3: "VTMM
 SYMBOLS = ["vtmme_create", "vtmme_destroy", "vtmme_last_error", "vtmme_set_stream", "vtmme_synchronize",
            "vtmme_launch_count", "vtmme_set_profiling", "vtmme_frame_kernel_ms", "vtmme_upload_picture", "vtmme_upload_picture_device", "vtmme_release_picture",
            "vtmme_search", "vtmme_frame_cu_count", "vtmme_search_frames", "vtmme_search_frames_device",
-           "vtmme_dist_batch", "vtmme_dist_host", "vtmme_interp_batch", "vtmme_interp_host", "vtmme_int_peak"]
+           "vtmme_dist_batch", "vtmme_dist_host", "vtmme_interp_batch", "vtmme_interp_host", "vtmme_filter_host", "vtmme_int_peak"]
 
 
 class CJob(C.Structure):
@@ -93,6 +93,7 @@ def load_library():
     L.vtmme_dist_host.argtypes = [P, I, P, I, P, I, I, I, I, C.POINTER(C.c_uint64)]
     L.vtmme_interp_batch.argtypes = [P, I, I, P, I, I64, P, I, I64, I, I, I, I, I, I, I, I]
     L.vtmme_interp_host.argtypes = [P, I, I, P, I, P, I, I, I, I, I, I, I, I]
+    L.vtmme_filter_host.argtypes = [P, I, I, I, I, I, P, I, P, I, I, I, P, I]
     L.vtmme_int_peak.argtypes = [I, I, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _lib = L
     return L
