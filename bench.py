@@ -184,6 +184,7 @@ def run_ours(args, rank, world, local_rank):
     from vtm_b200 import FrameParams
     from vtm_b200.me import CU_RESULT_DTYPE
     from vtm_b200.peaks import int_peak
+    from vtm_b200.shard import max_over_ranks, pairs_for_rank
     from vtm_b200.synth import make_pairs_torch
 
     torch.cuda.set_device(local_rank)
@@ -200,7 +201,7 @@ def run_ours(args, rank, world, local_rank):
     ms.set_frame_size(WIDTH, HEIGHT)
 
     # synthetic pairs of this rank: distinct seeds per rank, generated on the GPU, uploaded as library pictures
-    ids = [rank * pool + i for i in range(pool)]
+    ids = pairs_for_rank(world * pool, world, rank)   # pair p of the job belongs to rank p % world
     host_cur, host_ref = [], []
     for c0 in range(0, pool, 8):
         cur, ref = make_pairs_torch(ids[c0:c0 + 8], dev, WIDTH, HEIGHT)
@@ -253,10 +254,7 @@ def run_ours(args, rank, world, local_rank):
     launches = ms.launches - launches0
     ms.set_profiling(False)
     elapsed_ms = ev0.elapsed_time(ev1)
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
+    elapsed_ms = max_over_ranks(elapsed_ms, dev)
     value = world * B * K * cands_pair / (elapsed_ms * 1e-3)
 
     # ---- e2e: host buffers through the C ABI (upload both planes of every pair, search, results back to the host)
@@ -282,10 +280,8 @@ def run_ours(args, rank, world, local_rank):
         h_res = e2e_step(s + 1)
     e1.record(stream)
     barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * e2e_steps * cands_pair / (float(t.item()) * 1e-3)
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1), dev)
+    e2e_value = world * B * e2e_steps * cands_pair / (e2e_ms * 1e-3)
     h2d = B * 2 * WIDTH * HEIGHT * 2
     d2h = B * ncu * CU_RESULT_DTYPE.itemsize
 
