@@ -40,7 +40,7 @@ constexpr int kOffBest = 4096;                    // u64 [24]          per-CU be
 constexpr int kOffCu   = kOffBest + 24 * 8;       // CuInfo [24]
 constexpr int kOffMisc = kOffCu + 24 * 16;        // int [8]
 constexpr int kOffLut  = kOffMisc + 32;           // uint32 [512]      lambda * bits, entries >= 256 = "outside the window"
-constexpr int kOffTab  = kOffLut + 2048;          // u8 minBitsX[21][gxPad], u8 bitsY[21][rowsPad], then the window
+constexpr int kOffTab  = kOffLut + 2048;          // u8 bitsX[21][maxGx*8], u8 minBitsX[21][gxPad], u8 bitsY[21][rowsPad], then the window
 constexpr uint32_t kLutInvalid = 0x3fffffffu;
 static_assert(sizeof(CuInfo) == 16, "CuInfo layout");
 static_assert(kOffTab % 16 == 0, "alignment");
@@ -49,29 +49,42 @@ __host__ __device__ inline int tree_gx_pad(int maxGx) { return (maxGx + 3) & ~3;
 __host__ __device__ inline int tree_rows_pad(int maxRows) { return (maxRows + 3) & ~3; }
 __host__ __device__ inline int tree_off_ref(int maxGx, int maxRows)
 {
-  return (kOffTab + kCheckSlots * (tree_gx_pad(maxGx) + tree_rows_pad(maxRows)) + 15) & ~15;
+  return (kOffTab + kCheckSlots * (maxGx * 8 + tree_gx_pad(maxGx) + tree_rows_pad(maxRows)) + 15) & ~15;
 }
 
-// Candidate that passed the cheap lower-bound test: exact window test, exact cost, atomic argmin.
-__device__ __noinline__ void consider(const CuInfo* cu, unsigned long long* best, int dx, int dy, uint32_t sad,
-                                      double lambda, int imvShift)
+// Argmin update for 8 candidates (one 8-wide displacement group, one row) of one CU.
+//   fast reject: cost >= SAD + lambda*(min bitsX of the group + bitsY of the row) =: SAD + lb
+//   survivors:   exact cost SAD + lut[bitsX(dx) + bitsY(dy)] (tables hold 255 outside the CU's window, lut[>=256] is
+//                "never"), atomicMin on the shared (cost, position) key = first minimum in raster order.
+// The candidate with the smallest SAD goes first: on a cold threshold it tightens it for the other seven.
+__device__ __forceinline__ void check8(const uint32_t (&a)[8], uint32_t lb, const uint8_t* bx8, uint32_t by,
+                                       const uint32_t* lut, unsigned long long* best, int dx0, int dy)
 {
-  if (dx < cu->l || dx > cu->r || dy < cu->t || dy > cu->b) return;
-  const uint32_t cost = sad + mv_cost(lambda, mv_bits_q(dx * 4, dy * 4, cu->pqx, cu->pqy, imvShift));
-  atomicMin(best, make_key(cost, dx, dy));
-}
-
-// Fast reject of 8 candidates of one CU: cost >= SAD + lambda*(min bitsX of the group + bitsY of the row).
-__device__ __forceinline__ void check8(const uint32_t (&a)[8], uint32_t lb, const CuInfo* cu, unsigned long long* best,
-                                       int dx0, int dy, double lambda, int imvShift)
-{
-  const uint32_t thr = reinterpret_cast<volatile uint2*>(best)->y;
+  uint32_t       thr = reinterpret_cast<volatile uint2*>(best)->y;
   const uint32_t m   = min(min(min(a[0], a[1]), min(a[2], a[3])), min(min(a[4], a[5]), min(a[6], a[7])));
   if (m + lb <= thr)
   {
+    const uint2 bw = *reinterpret_cast<const uint2*>(bx8);
+    uint32_t    c[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) c[k] = a[k] + lut[(((k < 4 ? bw.x : bw.y) >> (8 * (k & 3))) & 0xffu) + by];
+    int      kmin = 0;
+    uint32_t cmin = c[0];
+#pragma unroll
+    for (int k = 7; k >= 0; k--)
+      if (a[k] == m)
+      {
+        kmin = k;
+        cmin = c[k];
+      }
+    if (cmin <= thr)
+    {
+      atomicMin(best, make_key(cmin, dx0 + kmin, dy));
+      thr = reinterpret_cast<volatile uint2*>(best)->y;
+    }
 #pragma unroll
     for (int k = 0; k < 8; k++)
-      if (a[k] + lb <= thr) consider(cu, best, dx0 + k, dy, a[k], lambda, imvShift);
+      if (k != kmin && c[k] <= thr) atomicMin(best, make_key(c[k], dx0 + k, dy));
   }
 }
 
@@ -148,7 +161,9 @@ __global__ void __launch_bounds__(kTreeMaxThreads, DY == 2 ? 2 : 3) me_tree_sad_
   int*                s_misc = reinterpret_cast<int*>(smem + kOffMisc);
   uint32_t*           s_lut  = reinterpret_cast<uint32_t*>(smem + kOffLut);
   const int           gxPad = tree_gx_pad(p.maxGx), rowsPad = tree_rows_pad(p.maxRows);
-  uint8_t*            s_minbx = smem + kOffTab;
+  const int           bxStride = p.maxGx * 8;
+  uint8_t*            s_bx    = smem + kOffTab;
+  uint8_t*            s_minbx = s_bx + kCheckSlots * bxStride;
   uint8_t*            s_by    = s_minbx + kCheckSlots * gxPad;
   uint16_t*           s_ref   = reinterpret_cast<uint16_t*>(smem + tree_off_ref(p.maxGx, p.maxRows));
 
@@ -244,14 +259,18 @@ __global__ void __launch_bounds__(kTreeMaxThreads, DY == 2 ? 2 : 3) me_tree_sad_
   {
     const int    slot = i / ngx, g = i - slot * ngx;
     const CuInfo ci   = s_cu[slot];
-    uint32_t     mb   = 255;
-    if (ci.idx >= 0)
+    uint32_t     mb   = 255, lo = 0, hi = 0;
 #pragma unroll
-      for (int k = 0; k < 8; k++)
-      {
-        const int dx = wl8 + g * 8 + k;
-        if (dx >= ci.l && dx <= ci.r) mb = min(mb, eg_bits((dx * 4 - ci.pqx) >> imvShift));
-      }
+    for (int k = 0; k < 8; k++)
+    {
+      const int dx = wl8 + g * 8 + k;
+      uint32_t  b  = 255;
+      if (ci.idx >= 0 && dx >= ci.l && dx <= ci.r) b = eg_bits((dx * 4 - ci.pqx) >> imvShift);
+      mb = min(mb, b);
+      if (k < 4) lo |= b << (8 * k);
+      else hi |= b << (8 * (k - 4));
+    }
+    *reinterpret_cast<uint2*>(s_bx + slot * bxStride + g * 8) = make_uint2(lo, hi);
     s_minbx[slot * gxPad + g] = (uint8_t) mb;
   }
   for (int i = tid; i < kCheckSlots * nrows; i += nthr)
@@ -380,8 +399,9 @@ __global__ void __launch_bounds__(kTreeMaxThreads, DY == 2 ? 2 : 3) me_tree_sad_
             {
               if (d == 0 || row1ok)
               {
-                const uint32_t lb = s_lut[s_minbx[slot * gxPad + gx] + s_by[slot * rowsPad + row0 + d]];
-                check8(a8[d], lb, &s_cu[slot], &s_best[slot], dx0, wt + row0 + d, lambda, imvShift);
+                const uint32_t by = s_by[slot * rowsPad + row0 + d];
+                check8(a8[d], s_lut[s_minbx[slot * gxPad + gx] + by], s_bx + slot * bxStride + gx * 8, by, s_lut,
+                       &s_best[slot], dx0, wt + row0 + d);
               }
 #pragma unroll
               for (int k = 0; k < 8; k++) a16[d][k] += a8[d][k];
@@ -392,8 +412,9 @@ __global__ void __launch_bounds__(kTreeMaxThreads, DY == 2 ? 2 : 3) me_tree_sad_
             for (int d = 0; d < DY; d++)
               if (d == 0 || row1ok)
               {
-                const uint32_t lb = s_lut[s_minbx[(16 + q) * gxPad + gx] + s_by[(16 + q) * rowsPad + row0 + d]];
-                check8(a16[d], lb, &s_cu[16 + q], &s_best[16 + q], dx0, wt + row0 + d, lambda, imvShift);
+                const uint32_t by = s_by[(16 + q) * rowsPad + row0 + d];
+                check8(a16[d], s_lut[s_minbx[(16 + q) * gxPad + gx] + by], s_bx + (16 + q) * bxStride + gx * 8, by, s_lut,
+                       &s_best[16 + q], dx0, wt + row0 + d);
               }
         }
 #pragma unroll
@@ -407,8 +428,9 @@ __global__ void __launch_bounds__(kTreeMaxThreads, DY == 2 ? 2 : 3) me_tree_sad_
         if (d == 1 && !row1ok) continue;
         if (s_cu[20].idx >= 0)
         {
-          const uint32_t lb = s_lut[s_minbx[20 * gxPad + gx] + s_by[20 * rowsPad + row0 + d]];
-          check8(a32[d], lb, &s_cu[20], &s_best[20], dx0, wt + row0 + d, lambda, imvShift);
+          const uint32_t by = s_by[20 * rowsPad + row0 + d];
+          check8(a32[d], s_lut[s_minbx[20 * gxPad + gx] + by], s_bx + 20 * bxStride + gx * 8, by, s_lut, &s_best[20], dx0,
+                 wt + row0 + d);
         }
         if (writeSurf)
         {
