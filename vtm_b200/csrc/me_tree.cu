@@ -364,13 +364,17 @@ __global__ void __launch_bounds__(kTreeMaxThreads, DY == 2 ? 2 : 3) me_tree_sad_
               for (int k = 0; k < 8; k++) a8[d][k] = 0;
             if (DY == 1)
             {
+              const uint32_t* op = orgRow;
+              const uint16_t* rp = refRow;
 #pragma unroll 2
               for (int r = 0; r < 8; r++)
               {
                 uint32_t o[8], px[16];
-                load_org8(orgRow + r * 32, o);
-                load_ref16<FPU>(refRow + r * refStride, px);
+                load_org8(op, o);
+                load_ref16<FPU>(rp, px);
                 sad_row<NFP>(a8[0], o, px);
+                op += 32;
+                rp += refStride;
               }
             }
             else
@@ -451,10 +455,12 @@ constexpr int kUpperThreads = 256;
 
 __global__ void __launch_bounds__(kUpperThreads) me_tree_upper_kernel(TreeParams p)
 {
+  extern __shared__ __align__(16) unsigned char usmem[];
   __shared__ CuInfo          s_cu[5];
   __shared__ int4            s_reg[16];
   __shared__ const uint32_t* s_surf[16];
   __shared__ int             s_box[4];
+  __shared__ uint32_t        s_lut[512];
 
   const int tid  = threadIdx.x;
   const int ctu  = blockIdx.x;
@@ -503,6 +509,7 @@ __global__ void __launch_bounds__(kUpperThreads) me_tree_upper_kernel(TreeParams
     s_reg[i]  = info;
     s_surf[i] = sp;
   }
+  for (int i = tid; i < 512; i += kUpperThreads) s_lut[i] = i < 256 ? mv_cost(p.lambda, (uint32_t) i) : kLutInvalid;
   __syncthreads();
   if (tid == 0)
   {
@@ -524,25 +531,48 @@ __global__ void __launch_bounds__(kUpperThreads) me_tree_upper_kernel(TreeParams
   const int bl = s_box[0], br = s_box[1], bt = s_box[2], bb = s_box[3];
   if (br < bl) return;   // no 64x64 / 128x128 CU in this CTU
   const int bw = br - bl + 1, bhgt = bb - bt + 1;
+  // rate tables of the five CUs over the bounding box (255 = outside the CU's window)
+  uint8_t* s_bx = usmem;                  // [5][bw]
+  uint8_t* s_by = usmem + 5 * bw;         // [5][bhgt]
+  for (int i = tid; i < 5 * bw; i += kUpperThreads)
+  {
+    const int    s = i / bw, dx = bl + (i - s * bw);
+    const CuInfo ci = s_cu[s];
+    s_bx[i] = (ci.idx >= 0 && dx >= ci.l && dx <= ci.r) ? (uint8_t) eg_bits((dx * 4 - ci.pqx) >> p.imvShift) : 255;
+  }
+  for (int i = tid; i < 5 * bhgt; i += kUpperThreads)
+  {
+    const int    s = i / bhgt, dy = bt + (i - s * bhgt);
+    const CuInfo ci = s_cu[s];
+    s_by[i] = (ci.idx >= 0 && dy >= ci.t && dy <= ci.b) ? (uint8_t) eg_bits((dy * 4 - ci.pqy) >> p.imvShift) : 255;
+  }
+  __syncthreads();
 
   unsigned long long best[5];
 #pragma unroll
   for (int s = 0; s < 5; s++) best[s] = ~0ull;
 
+  // displacements of the box, flattened; consecutive threads read consecutive dx of the surfaces
   const int total = bw * bhgt;
   for (int i = blockIdx.z * kUpperThreads + tid; i < total; i += gridDim.z * kUpperThreads)
   {
-    const int dy = bt + i / bw, dx = bl + i % bw;
-    bool      in[5];
+    const int yi = i / bw, xi = i - yi * bw;
+    const int dx = bl + xi, dy = bt + yi;
+    uint32_t  bits[5];
+    bool      any = false;
 #pragma unroll
     for (int s = 0; s < 5; s++)
-      in[s] = s_cu[s].idx >= 0 && dx >= s_cu[s].l && dx <= s_cu[s].r && dy >= s_cu[s].t && dy <= s_cu[s].b;
+    {
+      bits[s] = (uint32_t) s_bx[s * bw + xi] + (uint32_t) s_by[s * bhgt + yi];
+      any |= bits[s] < 256;
+    }
+    if (!any) continue;
     uint32_t s64[4];
 #pragma unroll
     for (int j = 0; j < 4; j++)
     {
       s64[j] = 0;
-      if (in[j] || in[4])
+      if (bits[j] < 256 || bits[4] < 256)
       {
 #pragma unroll
         for (int k = 0; k < 4; k++)
@@ -556,14 +586,10 @@ __global__ void __launch_bounds__(kUpperThreads) me_tree_upper_kernel(TreeParams
 #pragma unroll
     for (int s = 0; s < 5; s++)
     {
-      if (!in[s]) continue;
-      const uint32_t sad = s < 4 ? s64[s] : s64[0] + s64[1] + s64[2] + s64[3];
-      if (sad <= key_cost(best[s]))
-      {
-        const uint32_t cost = sad + mv_cost(p.lambda, mv_bits_q(dx * 4, dy * 4, s_cu[s].pqx, s_cu[s].pqy, p.imvShift));
-        const unsigned long long k = make_key(cost, dx, dy);
-        if (k < best[s]) best[s] = k;
-      }
+      const uint32_t sad  = s < 4 ? s64[s] : s64[0] + s64[1] + s64[2] + s64[3];
+      const uint32_t cost = sad + s_lut[bits[s]];   // >= 0x3fffffff outside the window
+      const unsigned long long k = make_key(cost, dx, dy);
+      if (cost < kLutInvalid && k < best[s]) best[s] = k;
     }
   }
 #pragma unroll
@@ -640,7 +666,9 @@ cudaError_t launch_tree_sad(const TreeParams& p, int nPairs, cudaStream_t st)
 cudaError_t launch_tree_upper(const TreeParams& p, int nPairs, cudaStream_t st)
 {
   dim3 grid(p.g.nCtuX * p.g.nCtuY, nPairs, 4);
-  me_tree_upper_kernel<<<grid, kUpperThreads, 0, st>>>(p);
+  // dynamic shared memory: rate tables over the bounding box of the CTU's five windows
+  const size_t smem = (size_t) 5 * 2 * (p.maxGx * 8 + 8 + p.maxRows + 8);
+  me_tree_upper_kernel<<<grid, kUpperThreads, smem, st>>>(p);
   return cudaGetLastError();
 }
 
