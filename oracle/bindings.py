@@ -102,6 +102,10 @@ def ref():
         L.ref_search.argtypes = [C.POINTER(Job), C.POINTER(Result)]
         L.ref_search_batch.argtypes = [C.POINTER(Job), C.POINTER(Result), _I, _I]
         L.ref_search_batch.restype = C.c_double
+        L.ref_dist_batch.restype = C.c_double
+        L.ref_dist_batch.argtypes = [_P, _P, _I, _I, _I, _I, _I, _I, _P]
+        L.ref_filter_batch.restype = C.c_double
+        L.ref_filter_batch.argtypes = [_I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I]
         _ref = L
     return _ref
 

@@ -223,6 +223,46 @@ void ref_search(const RefSearchJob* j, RefSearchResult* r)
   r->fracCost = cost;
 }
 
+// n block pairs stored back to back (block stride w*h), one distFunc call each; returns seconds (table-level baseline)
+double ref_dist_batch(const int16_t* org, const int16_t* cur, int w, int h, int n, int bitDepth, int subShiftMode,
+                      int useHad, uint64_t* out)
+{
+  Probe& p = probe();
+  DistParam dp;
+  CPelBuf o0(org, w, w, h);
+  p.rd.setDistParam(dp, o0, cur, w, bitDepth, COMPONENT_Y, subShiftMode, 1, useHad != 0);
+  auto t0 = std::chrono::steady_clock::now();
+  for (int i = 0; i < n; i++)
+  {
+    dp.org.buf = org + (size_t) i * w * h;
+    dp.cur.buf = cur + (size_t) i * w * h;
+    out[i]     = dp.distFunc(dp);
+  }
+  auto t1 = std::chrono::steady_clock::now();
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// n blocks: source blocks (w+8)x(h+8) back to back (output position at +4,+4), destination blocks w x h back to back
+double ref_filter_batch(int comp, int vertical, const int16_t* src, int16_t* dst, int w, int h, int n, int frac,
+                        int isFirst, int isLast, int bd)
+{
+  Probe&       p  = probe();
+  const ClpRng c  = makeClp(bd);
+  const int    sw = w + 8, sh = h + 8;
+  auto t0 = std::chrono::steady_clock::now();
+  for (int i = 0; i < n; i++)
+  {
+    const int16_t* s = src + (size_t) i * sw * sh + 4 * sw + 4;
+    int16_t*       d = dst + (size_t) i * w * h;
+    if (vertical)
+      p.m_if.filterVer(ComponentID(comp), s, sw, d, w, w, h, frac, isFirst != 0, isLast != 0, CHROMA_420, c);
+    else
+      p.m_if.filterHor(ComponentID(comp), s, sw, d, w, w, h, frac, isLast != 0, CHROMA_420, c);
+  }
+  auto t1 = std::chrono::steady_clock::now();
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
 // Batch driver used as the CPU baseline: nThreads workers over disjoint job ranges.
 // Returns wall seconds spent in the searches (steady_clock around the work only).
 double ref_search_batch(const RefSearchJob* jobs, RefSearchResult* res, int n, int nThreads)

@@ -206,3 +206,31 @@ def test_interp_host_matches_oracle(ms, oracle_lib):
                     oracle_lib.vo_filter_hor(1, B.ptr(src, off), ss, B.ptr(want), w, w, h, frac, last, 10, 0)
                 got = ms.interp_host(1, vert, src, off, ss, w, h, frac, first, last, 10, 0)
                 assert np.array_equal(got, want), ("chroma", w, h, frac, vert, first, last)
+
+
+LUMA = {4: (-1, 4, -10, 58, 17, -5, 1, 0), 8: (-1, 4, -11, 40, 40, -11, 4, -1), 13: (0, 1, -4, 13, 60, -8, 3, -1)}
+CHROMA = {5: (-3, 57, 12, -2), 16: (-4, 36, 36, -4)}
+
+
+def test_filter_host_explicit_taps(ms, oracle_lib):
+    """vtmme_filter_host (the table-entry flavour with explicit coefficients) against the oracle's dispatch."""
+    rng = np.random.default_rng(82)
+    w, h = 24, 16
+    src = rng.integers(0, 1024, (h + 10, w + 10), dtype=np.int16)
+    mid = rng.integers(-8192, 8192, (h + 10, w + 10), dtype=np.int16)
+    off, ss = 4 * (w + 10) + 4, w + 10
+    for comp, table, taps in ((0, LUMA, 8), (1, CHROMA, 4)):
+        for frac, coeff in table.items():
+            for (vert, first, last, s) in [(0, 1, 0, src), (0, 1, 1, src), (1, 0, 1, mid), (1, 1, 1, src), (1, 0, 0, mid)]:
+                want = np.zeros((h, w), np.int16)
+                if vert:
+                    oracle_lib.vo_filter_ver(comp, B.ptr(s, off), ss, B.ptr(want), w, w, h, frac, first, last, 10, 0)
+                else:
+                    oracle_lib.vo_filter_hor(comp, B.ptr(s, off), ss, B.ptr(want), w, w, h, frac, last, 10, 0)
+                got = ms.filter_host(taps, vert, first, last, 0, s, off, ss, w, h, coeff, 10)
+                assert np.array_equal(got, want), (comp, frac, vert, first, last)
+    for (first, last, s) in [(1, 0, src), (0, 1, mid)]:      # filterCopy<true,false> / <false,true>
+        want = np.zeros((h, w), np.int16)
+        oracle_lib.vo_filter_ver(0, B.ptr(s, off), ss, B.ptr(want), w, w, h, 0, first, last, 10, 0)
+        got = ms.filter_host(8, 1, first, last, 1, s, off, ss, w, h, None, 10)
+        assert np.array_equal(got, want), ("copy", first, last)

@@ -207,6 +207,17 @@ class MotionSearch:
                                              bit_depth, use_alt_hpel), "vtmme_interp_host")
         return dst
 
+    def filter_host(self, taps, vertical, is_first, is_last, copy, src, src_off, src_stride, w, h, coeff, bit_depth=10):
+        """Function-pointer flavour (explicit taps): what m_filterHor/m_filterVer/m_filterCopy entries receive."""
+        dst = np.zeros((h, w), np.int16)
+        c = np.ascontiguousarray(coeff, dtype=np.int16) if coeff is not None else None
+        self._check(self.L.vtmme_filter_host(self.ctx, taps, vertical, is_first, is_last, copy,
+                                             C.c_void_p(src.ctypes.data + 2 * src_off), src_stride,
+                                             C.c_void_p(dst.ctypes.data), w, w, h,
+                                             C.c_void_p(c.ctypes.data) if c is not None else None, bit_depth),
+                    "vtmme_filter_host")
+        return dst
+
     def interp_batch(self, comp, vertical, d_src, src_stride, src_blk, d_dst, dst_stride, dst_blk, w, h, frac, is_first,
                      is_last, bit_depth, use_alt_hpel, n):
         self._check(self.L.vtmme_interp_batch(self.ctx, comp, vertical, C.c_void_p(d_src), src_stride, src_blk,
