@@ -196,7 +196,10 @@ def run_ours(args, rank, world, local_rank):
     cands_pair, ops_pair, ncu = workload_counts()
 
     ms = vtm_b200.MotionSearch(local_rank)
-    stream = torch.cuda.current_stream()
+    # a dedicated stream shared by torch (events, synthetic-data kernels) and the library (NULL would mean the
+    # library's own stream, and torch's default stream handle IS NULL)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     ms.set_stream(stream.cuda_stream)
     ms.set_frame_size(WIDTH, HEIGHT)
 

@@ -45,7 +45,8 @@ typedef struct vtmme_ctx vtmme_ctx;
 int         vtmme_create(int device, vtmme_ctx** ctx);
 void        vtmme_destroy(vtmme_ctx* ctx);
 const char* vtmme_last_error(const vtmme_ctx* ctx);
-/* Run on the caller's CUDA stream (a cudaStream_t, e.g. torch's current stream); NULL = library stream. */
+/* Run on the caller's CUDA stream (a cudaStream_t, e.g. a torch.cuda.Stream's .cuda_stream); NULL = the library's
+ * own non-blocking stream.  (The legacy default stream's handle is NULL too: pass cudaStreamLegacy for it.) */
 int         vtmme_set_stream(vtmme_ctx* ctx, void* cudaStream);
 int         vtmme_synchronize(vtmme_ctx* ctx);
 /* Number of kernels launched by this context since creation (bench.py's gpu_launches). */

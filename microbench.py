@@ -31,7 +31,8 @@ def main():
     R = B.ref()
     O = B.oracle()
     ms = vtm_b200.MotionSearch(0)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # not the default stream: its handle is NULL = "library stream" in the C ABI
+    torch.cuda.set_stream(stream)
     ms.set_stream(stream.cuda_stream)
     rows = []
     shapes = [(w, h) for w in SIZES for h in SIZES]
