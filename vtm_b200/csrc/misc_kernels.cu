@@ -18,7 +18,8 @@ __global__ void extend_border_kernel(DevPic p)
   }
 }
 
-// ---- SAD: RdCost::xGetSAD (RdCost.cpp:493-528) / xGetSAD_NxN_SIMD (x86/RdCostX86.h:341-456); one warp per block ----
+// ---- SAD: RdCost::xGetSAD (RdCost.cpp:493-528) / xGetSAD_NxN_SIMD (x86/RdCostX86.h:341-456) ----
+// Generic layout: one warp per block, scalar loads.
 __global__ void __launch_bounds__(256) sad_batch_kernel(const int16_t* __restrict__ org, int orgStride, long long orgBlk,
                                                         const int16_t* __restrict__ cur, int curStride, long long curBlk,
                                                         int w, int h, int subShift, int n, unsigned long long* out)
@@ -39,8 +40,55 @@ __global__ void __launch_bounds__(256) sad_batch_kernel(const int16_t* __restric
   if (lane == 0) out[warp] = (unsigned long long) s << subShift;
 }
 
+// Aligned layout (strides, block strides and bases multiples of VEC samples): VEC-sample vector loads (128-bit for
+// VEC = 8, 64-bit for VEC = 4), several small blocks per warp so that every lane has a vector to load.
+__device__ __forceinline__ uint32_t sad_packed(uint32_t a, uint32_t b, uint32_t acc)
+{
+  acc = __sad((int) (short) (a & 0xffffu), (int) (short) (b & 0xffffu), acc);
+  return __sad((int) a >> 16, (int) b >> 16, acc);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) sad_batch_vec_kernel(const int16_t* __restrict__ org, int orgStride, long long orgBlk,
+                                                            const int16_t* __restrict__ cur, int curStride, long long curBlk,
+                                                            int w, int h, int subShift, int n, unsigned long long* out)
+{
+  const int vecPerRow = w / VEC, rows = h >> subShift, vecPerBlock = vecPerRow * rows;
+  const int lanesPerBlock = vecPerBlock >= 32 ? 32 : vecPerBlock;   // power of two
+  const int blocksPerWarp = 32 / lanesPerBlock;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int blk = warp * blocksPerWarp + lane / lanesPerBlock, lib = lane % lanesPerBlock;
+  uint32_t  s = 0;
+  if (blk < n)
+  {
+    const int16_t* o = org + (long long) blk * orgBlk;
+    const int16_t* c = cur + (long long) blk * curBlk;
+    for (int v = lib; v < vecPerBlock; v += lanesPerBlock)
+    {
+      const int    r = (v / vecPerRow) << subShift, x = (v % vecPerRow) * VEC;
+      const size_t oo = (size_t) r * orgStride + x, co = (size_t) r * curStride + x;
+      if (VEC == 8)
+      {
+        const uint4 a = *reinterpret_cast<const uint4*>(o + oo), b = *reinterpret_cast<const uint4*>(c + co);
+        s = sad_packed(a.x, b.x, s);
+        s = sad_packed(a.y, b.y, s);
+        s = sad_packed(a.z, b.z, s);
+        s = sad_packed(a.w, b.w, s);
+      }
+      else
+      {
+        const uint2 a = *reinterpret_cast<const uint2*>(o + oo), b = *reinterpret_cast<const uint2*>(c + co);
+        s = sad_packed(a.x, b.x, s);
+        s = sad_packed(a.y, b.y, s);
+      }
+    }
+  }
+  for (int m = lanesPerBlock >> 1; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+  if (blk < n && lib == 0) out[blk] = (unsigned long long) s << subShift;
+}
+
 // ---- SATD: RdCost::xGetHADs tiling (RdCost.cpp:2819-2934); one warp per block, TH lanes per tile ----
-template <int TW, int TH>
+template <int TW, int TH, bool ALIGNED>
 __device__ __forceinline__ uint32_t satd_block(const int16_t* o, int os, const int16_t* c, int cs, int w, int h, int lane)
 {
   const int tilesX = w / TW, nTiles = tilesX * (h / TH);
@@ -53,8 +101,28 @@ __device__ __forceinline__ uint32_t satd_block(const int16_t* o, int os, const i
     const int  tt     = active ? t : 0;
     const int  tx = (tt % tilesX) * TW, ty = (tt / tilesX) * TH + lit;
     int        d[TW];
+    const int16_t* op = o + (size_t) ty * os + tx;
+    const int16_t* cp = c + (size_t) ty * cs + tx;
+    if (ALIGNED && TW >= 8)
+    {
 #pragma unroll
-    for (int i = 0; i < TW; i++) d[i] = (int) o[(size_t) ty * os + tx + i] - (int) c[(size_t) ty * cs + tx + i];
+      for (int i = 0; i < TW; i += 8)
+      {
+        const uint4 a = *reinterpret_cast<const uint4*>(op + i), b = *reinterpret_cast<const uint4*>(cp + i);
+        const uint32_t aw[4] = { a.x, a.y, a.z, a.w }, bw[4] = { b.x, b.y, b.z, b.w };
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+          d[i + 2 * k]     = (int) (short) (aw[k] & 0xffffu) - (int) (short) (bw[k] & 0xffffu);
+          d[i + 2 * k + 1] = ((int) aw[k] >> 16) - ((int) bw[k] >> 16);
+        }
+      }
+    }
+    else
+    {
+#pragma unroll
+      for (int i = 0; i < TW; i++) d[i] = (int) op[i] - (int) cp[i];
+    }
     const uint32_t v = satd_tile_rows<TW, TH>(d, lit);
     if (active && lit == 0) sum += v;
   }
@@ -77,6 +145,7 @@ __device__ __forceinline__ uint32_t satd_block_2x2(const int16_t* o, int os, con
   return sum;
 }
 
+template <bool ALIGNED>
 __global__ void __launch_bounds__(256) satd_batch_kernel(const int16_t* __restrict__ org, int orgStride, long long orgBlk,
                                                          const int16_t* __restrict__ cur, int curStride, long long curBlk,
                                                          int w, int h, int n, unsigned long long* out)
@@ -88,12 +157,12 @@ __global__ void __launch_bounds__(256) satd_batch_kernel(const int16_t* __restri
   int tw, th;
   satd_tiling(w, h, tw, th);
   uint32_t s;
-  if (tw == 16) s = satd_block<16, 8>(o, orgStride, c, curStride, w, h, lane);
-  else if (th == 16) s = satd_block<8, 16>(o, orgStride, c, curStride, w, h, lane);
-  else if (tw == 8 && th == 8) s = satd_block<8, 8>(o, orgStride, c, curStride, w, h, lane);
-  else if (tw == 8 && th == 4) s = satd_block<8, 4>(o, orgStride, c, curStride, w, h, lane);
-  else if (tw == 4 && th == 8) s = satd_block<4, 8>(o, orgStride, c, curStride, w, h, lane);
-  else if (tw == 4) s = satd_block<4, 4>(o, orgStride, c, curStride, w, h, lane);
+  if (tw == 16) s = satd_block<16, 8, ALIGNED>(o, orgStride, c, curStride, w, h, lane);
+  else if (th == 16) s = satd_block<8, 16, ALIGNED>(o, orgStride, c, curStride, w, h, lane);
+  else if (tw == 8 && th == 8) s = satd_block<8, 8, ALIGNED>(o, orgStride, c, curStride, w, h, lane);
+  else if (tw == 8 && th == 4) s = satd_block<8, 4, ALIGNED>(o, orgStride, c, curStride, w, h, lane);
+  else if (tw == 4 && th == 8) s = satd_block<4, 8, false>(o, orgStride, c, curStride, w, h, lane);
+  else if (tw == 4) s = satd_block<4, 4, false>(o, orgStride, c, curStride, w, h, lane);
   else s = satd_block_2x2(o, orgStride, c, curStride, w, h, lane);
 #pragma unroll
   for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
@@ -111,13 +180,15 @@ struct InterpArgs
   int16_t        coeff[8];
 };
 
-__global__ void __launch_bounds__(128) interp_batch_kernel(InterpArgs a)
+// The source block with its tap halo is staged in shared memory with row-contiguous loads, every output then reads its
+// taps from there; a CTA handles `bpc` consecutive blocks so that small blocks still fill it.
+constexpr int kInterpThreads = 256;
+
+__global__ void __launch_bounds__(kInterpThreads) interp_batch_kernel(InterpArgs a, int n, int bpc)
 {
-  const int16_t* src = a.src + (long long) blockIdx.x * a.srcBlk;
-  int16_t*       dst = a.dst + (long long) blockIdx.x * a.dstBlk;
+  extern __shared__ __align__(16) int16_t s_src[];
   const int hr   = max(2, 14 - a.bitDepth);
   const int maxv = (1 << a.bitDepth) - 1;
-  const int cStride = a.vertical ? a.srcStride : 1;
   int       shift = 6, offset;
   if (a.isLast)
   {
@@ -130,31 +201,107 @@ __global__ void __launch_bounds__(128) interp_batch_kernel(InterpArgs a)
     shift -= a.isFirst ? hr : 0;
     offset = a.isFirst ? -(8192 << shift) : 0;
   }
-  for (int i = threadIdx.x; i < a.w * a.h; i += blockDim.x)
+  const int before = a.copy ? 0 : a.taps / 2 - 1, halo = a.copy ? 0 : a.taps - 1;
+  const int sw = a.w + (a.vertical ? 0 : halo), sh = a.h + (a.vertical ? halo : 0);
+  const int tile = sw * sh;
+  const int first = blockIdx.x * bpc, count = min(bpc, n - first);
+  // stage: block b of this CTA at s_src + b * tile; one warp per source row (no per-element index arithmetic)
+  const int  warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nWarps = kInterpThreads / 32;
+  const bool wide = a.w >= 32;   // narrow blocks: flat indexing keeps all lanes busy
+  if (!wide)
   {
-    const int y = i / a.w, x = i % a.w;
-    const int16_t* s = src + (size_t) y * a.srcStride + x;
-    int            v;
-    if (a.copy)
+    for (int i = threadIdx.x; i < count * tile; i += kInterpThreads)
     {
-      if (a.isFirst == a.isLast) v = s[0];
-      else if (a.isFirst) v = (int16_t) ((int16_t) (s[0] << hr) - (int16_t) 8192);
-      else
-      {
-        v = (int16_t) ((s[0] + 8192 + (1 << (hr - 1))) >> hr);
-        v = min(max(v, 0), maxv);
-      }
+      const int b = i / tile, r = (i - b * tile) / sw, c = (i - b * tile) - r * sw;
+      const int16_t* src = a.src + (long long) (first + b) * a.srcBlk;
+      s_src[i] = a.vertical ? src[(ptrdiff_t) (r - before) * a.srcStride + c] : src[(ptrdiff_t) r * a.srcStride + (c - before)];
+    }
+  }
+  else
+  for (int row = warp; row < count * sh; row += nWarps)
+  {
+    const int      b = row / sh, r = row - b * sh;
+    const int16_t* src = a.src + (long long) (first + b) * a.srcBlk +
+                         (a.vertical ? (ptrdiff_t) (r - before) * a.srcStride : (ptrdiff_t) r * a.srcStride - before);
+    int16_t* d = s_src + b * tile + r * sw;
+    for (int c = lane; c < sw; c += 32) d[c] = src[c];
+  }
+  __syncthreads();
+  const int tStride = a.vertical ? sw : 1;
+  int       cf[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) cf[k] = a.coeff[k];
+  const int outs = a.w * a.h;
+  const int units = wide ? count * a.h : count * outs;   // wide: one warp per output row; narrow: one thread per output
+  for (int u = wide ? warp : threadIdx.x; u < units; u += wide ? nWarps : kInterpThreads)
+  {
+    int b, y, x0, xStep;
+    if (wide)
+    {
+      b = u / a.h;
+      y = u - b * a.h;
+      x0 = lane;
+      xStep = 32;
     }
     else
     {
-      int sum = 0;
-      s -= (a.taps / 2 - 1) * cStride;
-      for (int k = 0; k < a.taps; k++) sum += (int) s[k * cStride] * a.coeff[k];
-      v = (int16_t) ((sum + offset) >> shift);
-      if (a.isLast) v = min(max(v, 0), maxv);
+      b = u / outs;
+      y = (u - b * outs) / a.w;
+      x0 = (u - b * outs) - y * a.w;
+      xStep = a.w;   // exactly one output
     }
-    dst[(size_t) y * a.dstStride + x] = (int16_t) v;
+    const int16_t* srow = s_src + b * tile + y * sw;
+    int16_t*       drow = a.dst + (long long) (first + b) * a.dstBlk + (size_t) y * a.dstStride;
+    for (int x = x0; x < a.w; x += xStep)
+    {
+      const int16_t* sp = srow + x;   // first tap of this output
+      int            v;
+      if (a.copy)
+      {
+        if (a.isFirst == a.isLast) v = sp[0];
+        else if (a.isFirst) v = (int16_t) ((int16_t) (sp[0] << hr) - (int16_t) 8192);
+        else
+        {
+          v = (int16_t) ((sp[0] + 8192 + (1 << (hr - 1))) >> hr);
+          v = min(max(v, 0), maxv);
+        }
+      }
+      else
+      {
+        int sum = 0;
+        if (a.taps == 8)
+        {
+#pragma unroll
+          for (int k = 0; k < 8; k++) sum += (int) sp[k * tStride] * cf[k];
+        }
+        else
+        {
+          for (int k = 0; k < a.taps; k++) sum += (int) sp[k * tStride] * cf[k];
+        }
+        v = (int16_t) ((sum + offset) >> shift);
+        if (a.isLast) v = min(max(v, 0), maxv);
+      }
+      drow[x] = (int16_t) v;
+    }
   }
+}
+
+static cudaError_t launch_interp(const InterpArgs& a, int n, cudaStream_t st)
+{
+  const int halo = a.copy ? 0 : a.taps - 1;
+  const int sw = a.w + (a.vertical ? 0 : halo), sh = a.h + (a.vertical ? halo : 0);
+  int bpc = 2048 / (a.w * a.h);
+  bpc     = bpc < 1 ? 1 : (bpc > 32 ? 32 : bpc);
+  const size_t smem = (size_t) bpc * sw * sh * sizeof(int16_t);
+  static size_t configured = 48 * 1024;
+  if (smem > configured)
+  {
+    cudaError_t e = cudaFuncSetAttribute(interp_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  interp_batch_kernel<<<(n + bpc - 1) / bpc, kInterpThreads, smem, st>>>(a, n, bpc);
+  return cudaGetLastError();
 }
 
 const int16_t h_luma[16][8] = {
@@ -191,16 +338,39 @@ cudaError_t launch_extend_border(DevPic pic, cudaStream_t st)
   return cudaGetLastError();
 }
 
+static bool aligned_layout(const void* p, int stride, long long blk, int vec)
+{
+  return (reinterpret_cast<uintptr_t>(p) % (2 * vec)) == 0 && stride % vec == 0 && blk % vec == 0;
+}
+
 cudaError_t launch_dist_batch(int kind, const int16_t* org, int orgStride, long long orgBlockStride, const int16_t* cur,
                               int curStride, long long curBlockStride, int w, int h, int subShift, int n,
                               unsigned long long* out, cudaStream_t st)
 {
-  const int blocks = (n + 7) / 8;   // 8 warps per CTA
+  const bool pow2 = (w & (w - 1)) == 0 && (h & (h - 1)) == 0;
   if (kind == 0)
-    sad_batch_kernel<<<blocks, 256, 0, st>>>(org, orgStride, orgBlockStride, cur, curStride, curBlockStride, w, h,
-                                             subShift, n, out);
+  {
+    const int vec = (w % 8 == 0) ? 8 : (w % 4 == 0 ? 4 : 0);
+    if (vec && pow2 && aligned_layout(org, orgStride, orgBlockStride, vec) && aligned_layout(cur, curStride, curBlockStride, vec))
+    {
+      const int vecPerBlock = (w / vec) * (h >> subShift);
+      const int blocksPerWarp = vecPerBlock >= 32 ? 1 : 32 / vecPerBlock;
+      const int warps = (n + blocksPerWarp - 1) / blocksPerWarp, ctas = (warps + 7) / 8;
+      if (vec == 8)
+        sad_batch_vec_kernel<8><<<ctas, 256, 0, st>>>(org, orgStride, orgBlockStride, cur, curStride, curBlockStride, w, h, subShift, n, out);
+      else
+        sad_batch_vec_kernel<4><<<ctas, 256, 0, st>>>(org, orgStride, orgBlockStride, cur, curStride, curBlockStride, w, h, subShift, n, out);
+      return cudaGetLastError();
+    }
+    sad_batch_kernel<<<(n + 7) / 8, 256, 0, st>>>(org, orgStride, orgBlockStride, cur, curStride, curBlockStride, w, h,
+                                                  subShift, n, out);
+    return cudaGetLastError();
+  }
+  const int blocks = (n + 7) / 8;   // 8 warps per CTA
+  if (aligned_layout(org, orgStride, orgBlockStride, 8) && aligned_layout(cur, curStride, curBlockStride, 8))
+    satd_batch_kernel<true><<<blocks, 256, 0, st>>>(org, orgStride, orgBlockStride, cur, curStride, curBlockStride, w, h, n, out);
   else
-    satd_batch_kernel<<<blocks, 256, 0, st>>>(org, orgStride, orgBlockStride, cur, curStride, curBlockStride, w, h, n, out);
+    satd_batch_kernel<false><<<blocks, 256, 0, st>>>(org, orgStride, orgBlockStride, cur, curStride, curBlockStride, w, h, n, out);
   return cudaGetLastError();
 }
 
@@ -224,8 +394,7 @@ cudaError_t launch_filter_batch(int taps, int vertical, int isFirst, int isLast,
   a.copy     = copy;
   a.taps     = taps;
   for (int k = 0; k < 8; k++) a.coeff[k] = (!copy && k < taps) ? coeff[k] : 0;
-  interp_batch_kernel<<<n, 128, 0, st>>>(a);
-  return cudaGetLastError();
+  return launch_interp(a, n, st);
 }
 
 cudaError_t launch_interp_batch(int comp, int vertical, const int16_t* src, int srcStride, long long srcBlockStride,
@@ -259,8 +428,7 @@ cudaError_t launch_interp_batch(int comp, int vertical, const int16_t* src, int 
   else
     c = h_chroma[frac];
   for (int k = 0; k < 8; k++) a.coeff[k] = k < a.taps ? c[k] : 0;
-  interp_batch_kernel<<<n, 128, 0, st>>>(a);
-  return cudaGetLastError();
+  return launch_interp(a, n, st);
 }
 
 }   // namespace vtmme
