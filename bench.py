@@ -268,22 +268,30 @@ def run_ours(args, rank, world, local_rank):
     npool = len(host_cur)
     h_res = np.zeros((B, ncu), dtype=CU_RESULT_DTYPE)
 
-    def e2e_step(s):
-        cids, rids = [], []
+    def e2e_upload(s):
+        """queue the H2D copies of step s (pipelined on the library's copy stream); picture ids double-buffered"""
+        base = 100000 + (s & 1) * 2 * B
         for i in range(B):
             p = (s * B + i) % npool
-            ms.upload_picture(100000 + 2 * i, host_cur[p].numpy())
-            ms.upload_picture(100000 + 2 * i + 1, host_ref[p].numpy())
-            cids.append(100000 + 2 * i)
-            rids.append(100000 + 2 * i + 1)
-        return ms.search_frames(cids, rids, prm)
+            ms.upload_picture_async(base + 2 * i, host_cur[p].data_ptr(), WIDTH, WIDTH, HEIGHT)
+            ms.upload_picture_async(base + 2 * i + 1, host_ref[p].data_ptr(), WIDTH, WIDTH, HEIGHT)
 
-    e2e_step(0)
+    def e2e_search(s):
+        base = 100000 + (s & 1) * 2 * B
+        return ms.search_frames([base + 2 * i for i in range(B)], [base + 2 * i + 1 for i in range(B)], prm)
+
+    # every timed step uploads the NEXT step's pictures while it searches its own (uploaded during the previous step)
+    # and reads its results back to the host: per step, one full set of H2D copies and one D2H of all results
+    e2e_upload(0)
+    e2e_search(0)
+    e2e_upload(1)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for s in range(e2e_steps):
-        h_res = e2e_step(s + 1)
+    for s in range(1, e2e_steps + 1):
+        e2e_upload(s + 1)
+        h_res = e2e_search(s)
+    ms.synchronize()
     e1.record(stream)
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1), dev)
@@ -351,8 +359,8 @@ def main():
     ap.add_argument("--pairs-per-step", type=int, default=32)
     ap.add_argument("--pool", type=int, default=64, help="distinct resident pairs per GPU")
     ap.add_argument("--e2e-pool", type=int, default=16, help="pairs kept in pinned host memory for the e2e pass")
-    ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-every", type=int, default=4, help="CPU baseline sample: every n-th CU of pair 0")
+    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--cpu-every", type=int, default=1, help="CPU baseline sample: every n-th CU of pair 0")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

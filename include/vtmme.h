@@ -62,6 +62,11 @@ uint64_t    vtmme_launch_count(const vtmme_ctx* ctx);
 #define VTMME_MIN_MARGIN 192
 int vtmme_upload_picture(vtmme_ctx* ctx, int picId, const int16_t* origin, int stride, int width, int height,
                          int margin, int withBorder);
+/* Asynchronous flavour for pipelining: the copy and the border extension run on an internal copy stream and overlap
+ * with searches on other pictures; any later search / job that names picId waits for it on the device.  `origin` must
+ * be page-locked and stay valid until vtmme_synchronize() (or a synchronous call that used the picture) returned. */
+int vtmme_upload_picture_async(vtmme_ctx* ctx, int picId, const int16_t* origin, int stride, int width, int height,
+                               int margin, int withBorder);
 /* Same, source plane already in device memory (copied device-to-device on the context stream). */
 int vtmme_upload_picture_device(vtmme_ctx* ctx, int picId, const int16_t* dOrigin, int stride, int width, int height,
                                 int margin, int withBorder);

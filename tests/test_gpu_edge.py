@@ -182,3 +182,36 @@ def test_full_size_properties(ms, oracle_lib):
     # (c) idempotent
     r2 = ms.search_frames([62], [63], prm2)[0]
     assert np.array_equal(r1, r2)
+
+
+def test_async_upload_pipeline(ms, oracle_lib):
+    """vtmme_upload_picture_async: searches wait on the device for the pictures they name; results equal the
+    synchronous path, also when an upload is queued while a search on other pictures is in flight."""
+    import torch
+    from vtm_b200 import FrameParams
+    from vtm_b200.synth import make_pair
+    w, h = 192, 128
+    prm = FrameParams(searchRange=12, lambdaMotion=31.33)
+    ms.set_frame_size(w, h)
+    pairs = [make_pair(70 + i, w, h, max_global=8, max_local=8, n_rects=2, sigma=4.0)[:2] for i in range(2)]
+    want = []
+    for i, (cur, ref) in enumerate(pairs):
+        ms.upload_picture(80, cur)
+        ms.upload_picture(81, ref)
+        want.append(ms.search_frames([80], [81], prm).copy())
+    pinned = [[torch.from_numpy(a).pin_memory() for a in pr] for pr in pairs]
+    # pipeline: upload pair 0, then queue pair 1's upload before searching pair 0
+    ms.upload_picture_async(90, pinned[0][0].data_ptr(), w, w, h)
+    ms.upload_picture_async(91, pinned[0][1].data_ptr(), w, w, h)
+    ms.upload_picture_async(92, pinned[1][0].data_ptr(), w, w, h)
+    ms.upload_picture_async(93, pinned[1][1].data_ptr(), w, w, h)
+    got0 = ms.search_frames([90], [91], prm)
+    # re-use the ids of pair 0 for pair 1 while nothing is pending on them
+    ms.upload_picture_async(90, pinned[1][0].data_ptr(), w, w, h)
+    ms.upload_picture_async(91, pinned[1][1].data_ptr(), w, w, h)
+    got1 = ms.search_frames([92], [93], prm)
+    got1b = ms.search_frames([90], [91], prm)
+    ms.synchronize()
+    assert np.array_equal(got0, want[0])
+    assert np.array_equal(got1, want[1])
+    assert np.array_equal(got1b, want[1])

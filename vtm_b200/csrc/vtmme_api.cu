@@ -19,6 +19,8 @@ struct vtmme_ctx
   std::string  err;
   uint64_t     launches = 0;
   std::unordered_map<int, DevPic> pics;
+  std::unordered_map<int, cudaEvent_t> picReady;   // pictures uploaded asynchronously on copyStream
+  cudaStream_t copyStream = nullptr;
 
   // scratch of the frame path (grown on demand)
   DevPic*             dCur = nullptr;
@@ -115,8 +117,17 @@ int alloc_pic(vtmme_ctx* ctx, int picId, int width, int height, int margin, DevP
   return VTMME_OK;
 }
 
+// compute-stream work that reads picture `picId` must wait for its asynchronous upload
+int wait_picture(vtmme_ctx* ctx, int picId)
+{
+  auto it = ctx->picReady.find(picId);
+  if (it == ctx->picReady.end()) return VTMME_OK;
+  VTMME_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, it->second, 0));
+  return VTMME_OK;
+}
+
 int upload_common(vtmme_ctx* ctx, int picId, const int16_t* origin, int stride, int width, int height, int margin,
-                  int withBorder, cudaMemcpyKind kind)
+                  int withBorder, cudaMemcpyKind kind, bool async = false)
 {
   if (!ctx) return VTMME_ERR_ARG;
   if (!origin || width <= 0 || height <= 0 || stride < width || margin < 0)
@@ -127,13 +138,35 @@ int upload_common(vtmme_ctx* ctx, int picId, const int16_t* origin, int stride, 
   if (rc != VTMME_OK) return rc;
   // copy what the caller owns: the picture area, plus its own border when asked to
   const int cm = withBorder ? (margin < p.margin ? margin : p.margin) : 0;
+  cudaStream_t st = ctx->stream;
+  if (async)
+  {
+    if (!ctx->copyStream) VTMME_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+    st = ctx->copyStream;
+    // the copy must not overtake searches already queued on the compute stream that still read this picture
+    cudaEvent_t& ev = ctx->picReady[picId];
+    if (!ev) VTMME_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    VTMME_CUDA_CHECK(ctx, cudaEventRecord(ev, ctx->stream));
+    VTMME_CUDA_CHECK(ctx, cudaStreamWaitEvent(st, ev, 0));
+  }
+  else
+  {
+    auto it = ctx->picReady.find(picId);   // a synchronous re-upload supersedes a pending asynchronous one
+    if (it != ctx->picReady.end())
+    {
+      VTMME_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, it->second, 0));
+      cudaEventDestroy(it->second);
+      ctx->picReady.erase(it);
+    }
+  }
   VTMME_CUDA_CHECK(ctx, cudaMemcpy2DAsync(p.origin - (ptrdiff_t) cm * p.stride - cm, (size_t) p.stride * 2,
                                           origin - (ptrdiff_t) cm * stride - cm, (size_t) stride * 2,
-                                          (size_t) (width + 2 * cm) * 2, height + 2 * cm, kind, ctx->stream));
+                                          (size_t) (width + 2 * cm) * 2, height + 2 * cm, kind, st));
   // everything beyond is edge replication (Picture::extendPicBorder, Picture.cpp:1050-1096)
-  VTMME_CUDA_CHECK(ctx, launch_extend_border(p, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, launch_extend_border(p, st));
   ctx->launches += 1;
-  if (kind == cudaMemcpyHostToDevice) VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (async) VTMME_CUDA_CHECK(ctx, cudaEventRecord(ctx->picReady[picId], st));
+  else if (kind == cudaMemcpyHostToDevice) VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   return VTMME_OK;
 }
 
@@ -172,7 +205,10 @@ void vtmme_destroy(vtmme_ctx* ctx)
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->copyStream) cudaStreamSynchronize(ctx->copyStream);
   for (auto& kv : ctx->pics) cudaFree(kv.second.base);
+  for (auto& kv : ctx->picReady) cudaEventDestroy(kv.second);
+  if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
   cudaFree(ctx->dCur);
   cudaFree(ctx->dRef);
   cudaFree(ctx->dKeys);
@@ -204,6 +240,7 @@ int vtmme_synchronize(vtmme_ctx* ctx)
 {
   if (!ctx) return VTMME_ERR_ARG;
   VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->copyStream) VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->copyStream));
   return VTMME_OK;
 }
 
@@ -241,12 +278,25 @@ int vtmme_upload_picture_device(vtmme_ctx* ctx, int picId, const int16_t* dOrigi
   return upload_common(ctx, picId, dOrigin, stride, width, height, margin, withBorder, cudaMemcpyDeviceToDevice);
 }
 
+int vtmme_upload_picture_async(vtmme_ctx* ctx, int picId, const int16_t* origin, int stride, int width, int height,
+                               int margin, int withBorder)
+{
+  return upload_common(ctx, picId, origin, stride, width, height, margin, withBorder, cudaMemcpyHostToDevice, true);
+}
+
 int vtmme_release_picture(vtmme_ctx* ctx, int picId)
 {
   if (!ctx) return VTMME_ERR_ARG;
   auto it = ctx->pics.find(picId);
   if (it == ctx->pics.end()) return vtmme_set_error(ctx, VTMME_ERR_NOPIC, "vtmme_release_picture", "unknown picture id");
   cudaStreamSynchronize(ctx->stream);
+  auto ev = ctx->picReady.find(picId);
+  if (ev != ctx->picReady.end())
+  {
+    cudaEventSynchronize(ev->second);
+    cudaEventDestroy(ev->second);
+    ctx->picReady.erase(ev);
+  }
   cudaFree(it->second.base);
   ctx->pics.erase(it);
   return VTMME_OK;
@@ -279,6 +329,8 @@ int vtmme_search_frames_device(vtmme_ctx* ctx, int nPairs, const int32_t* curPic
       return vtmme_set_error(ctx, VTMME_ERR_NOPIC, "vtmme_search_frames", "unknown picture id");
     hc[i] = a->second;
     hr[i] = b->second;
+    int wrc;
+    if ((wrc = wait_picture(ctx, curPics[i])) != VTMME_OK || (wrc = wait_picture(ctx, refPics[i])) != VTMME_OK) return wrc;
     if (hc[i].width != hc[0].width || hc[i].height != hc[0].height || hr[i].width != hc[0].width ||
         hr[i].height != hc[0].height)
       return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search_frames", "all pictures must have the same size");
@@ -444,6 +496,8 @@ extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_
     if (ctx->pics.find(j.refPic) == ctx->pics.end() || (!j.org && ctx->pics.find(j.curPic) == ctx->pics.end()))
       return vtmme_set_error(ctx, VTMME_ERR_NOPIC, "vtmme_search", "unknown picture id");
     const DevPic& rp = ctx->pics[j.refPic];
+    int wrc;
+    if ((wrc = wait_picture(ctx, j.refPic)) != VTMME_OK || (!j.org && (wrc = wait_picture(ctx, j.curPic)) != VTMME_OK)) return wrc;
     // every read (window + pattern + 8-tap halo + staging pad) must stay inside the device margin
     if (j.x + j.srLeft - 24 < -rp.margin || j.x + j.w + j.srRight + 24 > rp.width + rp.margin ||
         j.y + j.srTop - 8 < -rp.margin || j.y + j.h + j.srBottom + 8 > rp.height + rp.margin)

@@ -16,7 +16,7 @@ ERR_NAMES = {0: "VTMME_OK", -1: "VTMME_ERR_CUDA", -2: "VTMME_ERR_ARG", -3: "VTMM
 
 # every symbol include/vtmme.h declares (tests check the built library exports all of them)
 SYMBOLS = ["vtmme_create", "vtmme_destroy", "vtmme_last_error", "vtmme_set_stream", "vtmme_synchronize",
-           "vtmme_launch_count", "vtmme_set_profiling", "vtmme_frame_kernel_ms", "vtmme_upload_picture", "vtmme_upload_picture_device", "vtmme_release_picture",
+           "vtmme_launch_count", "vtmme_set_profiling", "vtmme_frame_kernel_ms", "vtmme_upload_picture", "vtmme_upload_picture_async", "vtmme_upload_picture_device", "vtmme_release_picture",
            "vtmme_search", "vtmme_frame_cu_count", "vtmme_search_frames", "vtmme_search_frames_device",
            "vtmme_dist_batch", "vtmme_dist_host", "vtmme_interp_batch", "vtmme_interp_host", "vtmme_filter_host", "vtmme_int_peak"]
 
@@ -83,6 +83,7 @@ def load_library():
     L.vtmme_set_profiling.argtypes = [P, I]
     L.vtmme_frame_kernel_ms.argtypes = [P, C.POINTER(C.c_float)]
     L.vtmme_upload_picture.argtypes = [P, I, P, I, I, I, I, I]
+    L.vtmme_upload_picture_async.argtypes = [P, I, P, I, I, I, I, I]
     L.vtmme_upload_picture_device.argtypes = [P, I, P, I, I, I, I, I]
     L.vtmme_release_picture.argtypes = [P, I]
     L.vtmme_search.argtypes = [P, C.POINTER(CJob), I, C.POINTER(CResult)]

@@ -121,6 +121,12 @@ class MotionSearch:
         self._check(self.L.vtmme_upload_picture(self.ctx, pic_id, C.c_void_p(origin), plane.shape[1], w, h, margin,
                                                 1 if margin else 0), "vtmme_upload_picture")
 
+    def upload_picture_async(self, pic_id, host_ptr, stride, width, height, margin=0):
+        """Pipelined upload from PAGE-LOCKED host memory (address of sample (0,0)); overlaps with searches on other
+        pictures.  Keep the buffer alive until synchronize()."""
+        self._check(self.L.vtmme_upload_picture_async(self.ctx, pic_id, C.c_void_p(host_ptr), stride, width, height, margin,
+                                                      1 if margin else 0), "vtmme_upload_picture_async")
+
     def upload_picture_device(self, pic_id, dptr, stride, width, height, margin=0):
         """dptr: device address of sample (0,0) of an int16 plane (e.g. a torch tensor's data_ptr())."""
         self._check(self.L.vtmme_upload_picture_device(self.ctx, pic_id, C.c_void_p(dptr), stride, width, height,
