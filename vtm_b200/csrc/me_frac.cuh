@@ -135,18 +135,43 @@ __device__ __forceinline__ void frac_chunk_tiles(FracSmem& sm, int cw, int ch, c
   }
 }
 
-// One refinement stage around (cqx,cqy) (quarter-pel offset from the integer MV) with step `step`
-// (2 = half-pel, 1 = quarter-pel).  Returns the winning direction index in sm.best and its cost.
-__device__ inline uint32_t frac_stage(FracSmem& sm, const FracJob& j, int cqx, int cqy, int step, bool alt)
+// xPatternRefinement's choice (InterSearch.cpp:727-756) from the nine candidate distortions of a stage around
+// (cqx,cqy): first strict minimum in list order.  Serial, one thread.
+__device__ inline void frac_pick(const uint32_t* dist, const FracJob& j, int cqx, int cqy, int step, int& bestDir,
+                                 uint32_t& bestCost)
+{
+  const int8_t (*tab)[2] = (step == 2) ? c_refineH : c_refineQ;
+  bestCost = 0xffffffffu;
+  bestDir  = 0;
+  for (int i = 0; i < 9; i++)
+  {
+    const uint32_t cost = dist[i] + mv_cost(j.lambda, mv_bits_q(j.mvX * 4 + cqx + tab[i][0] * step, j.mvY * 4 + cqy + tab[i][1] * step,
+                                                                j.predQx, j.predQy, 0));
+    if (cost < bestCost)
+    {
+      bestCost = cost;
+      bestDir  = i;
+    }
+  }
+}
+
+__device__ __forceinline__ int frac_num_chunks(int w, int h)
+{
+  const int cw = min(w, kFracChunk), ch = min(h, kFracChunk);
+  return (w / cw) * (h / ch);
+}
+
+// Candidate distortions of one refinement stage around (cqx,cqy) (quarter-pel offset from the integer MV) with step
+// `step` (2 = half-pel, 1 = quarter-pel), accumulated into sm.acc[0..8] over chunk `chunkSel` (or all chunks if < 0).
+__device__ inline void frac_stage_sums(FracSmem& sm, const FracJob& j, int cqx, int cqy, int step, bool alt, int chunkSel)
 {
   const int8_t (*tab)[2] = (step == 2) ? c_refineH : c_refineQ;
   const int tid = threadIdx.x;
   if (tid < 9) sm.acc[tid] = 0;
-  int dqx[9], dqy[9], plane[9];
+  int dqy[9], plane[9];
 #pragma unroll
   for (int i = 0; i < 9; i++)
   {
-    dqx[i]   = cqx + tab[i][0] * step;
     dqy[i]   = cqy + tab[i][1] * step;
     plane[i] = tab[i][0] + 1;   // plane 0,1,2 = dqx of cqx-step, cqx, cqx+step
   }
@@ -162,9 +187,12 @@ __device__ inline uint32_t frac_stage(FracSmem& sm, const FracJob& j, int cqx, i
   }
   const int cw = min(j.w, kFracChunk), ch = min(j.h, kFracChunk);
 
+  const int chunksX = j.w / cw;
+  int       chunk   = 0;
   for (int cy0 = 0; cy0 < j.h; cy0 += ch)
-    for (int cx0 = 0; cx0 < j.w; cx0 += cw)
+    for (int cx0 = 0; cx0 < j.w; cx0 += cw, chunk++)
     {
+      if (chunkSel >= 0 && chunk != chunkSel) continue;
       __syncthreads();
       // 1. stage original chunk and reference patch rows [-4, ch+4), cols [-4, cw+4)
       for (int i = tid; i < cw * ch; i += kFracThreads)
@@ -221,21 +249,19 @@ __device__ inline uint32_t frac_stage(FracSmem& sm, const FracJob& j, int cqx, i
         else frac_chunk_tiles<4, 4, false>(sm, cw, ch, dqy, plane, j.bitDepth, altV);
       }
     }
+  (void) chunksX;
   __syncthreads();
-  // xPatternRefinement's loop (InterSearch.cpp:727-756): first strict minimum in list order
-  if (tid == 0)
+}
+
+// One whole stage (all chunks) and its decision.  Returns the winning direction index in sm.best and its cost.
+__device__ inline uint32_t frac_stage(FracSmem& sm, const FracJob& j, int cqx, int cqy, int step, bool alt)
+{
+  frac_stage_sums(sm, j, cqx, cqy, step, alt, -1);
+  if (threadIdx.x == 0)
   {
-    uint32_t bestCost = 0xffffffffu;
-    int      bestDir  = 0;
-    for (int i = 0; i < 9; i++)
-    {
-      const uint32_t cost = sm.acc[i] + mv_cost(j.lambda, mv_bits_q(j.mvX * 4 + dqx[i], j.mvY * 4 + dqy[i], j.predQx, j.predQy, 0));
-      if (cost < bestCost)
-      {
-        bestCost = cost;
-        bestDir  = i;
-      }
-    }
+    int      bestDir;
+    uint32_t bestCost;
+    frac_pick(sm.acc, j, cqx, cqy, step, bestDir, bestCost);
     sm.best   = bestDir;
     sm.centre = sm.acc[0];
     sm.acc[0] = bestCost;

@@ -187,56 +187,148 @@ __global__ void __launch_bounds__(256) me_job_reduce_kernel(const DevJob* __rest
   if ((threadIdx.x & 31) == 0 && best != ~0ull) atomicMin(keys + blockIdx.y, best);
 }
 
+__device__ __forceinline__ FracJob make_frac_job(const DevJob& j, int dx, int dy)
+{
+  FracJob f;
+  f.org        = j.org;
+  f.orgStride  = j.orgStride;
+  f.refAtMv    = j.refAtPU + (ptrdiff_t) dy * j.refStride + dx;
+  f.refStride  = j.refStride;
+  f.w          = j.w;
+  f.h          = j.h;
+  f.mvX        = dx;
+  f.mvY        = dy;
+  f.predQx     = j.predQx;
+  f.predQy     = j.predQy;
+  f.bitDepth   = j.bitDepth;
+  f.useHad     = j.useHad;
+  f.useAltHpel = j.useAltHpel;
+  f.imvShift   = j.imvShift;
+  f.lambda     = j.lambda;
+  return f;
+}
+
+// Fractional refinement of the per-call jobs.  Patterns of one 32x32 chunk (the common case) run the whole
+// xPatternSearchFracDIF body in one CTA (PASS 0).  Larger patterns are spread over one CTA per chunk: PASS 0 sums the
+// half-pel candidates of each chunk into acc[job][0..8], PASS 1 takes the half-pel decision from those sums and adds the
+// quarter-pel candidates to acc[job][9..17], me_job_frac_finish_kernel decides and writes the result.
+template <int PASS>
 __global__ void __launch_bounds__(kFracThreads) me_job_frac_kernel(const DevJob* __restrict__ jobs,
-                                                                   const unsigned long long* __restrict__ keys,
-                                                                   DevJobResult* __restrict__ results)
+                                                                   unsigned long long* __restrict__ keys,
+                                                                   DevJobResult* __restrict__ results,
+                                                                   uint32_t* __restrict__ acc)
 {
   __shared__ FracSmem sm;
-  const DevJob             j   = jobs[blockIdx.x];
-  const unsigned long long key = keys[blockIdx.x];
+  const int    job = blockIdx.y, chunk = blockIdx.x;
+  const DevJob j   = jobs[job];
+  const int    nChunks = frac_num_chunks(j.w, j.h);
+  if (chunk >= nChunks) return;
+  const unsigned long long key = keys[job];
   const int                dx = key_dx(key), dy = key_dy(key);
-  const uint32_t           intCost = key_cost(key);
-  DevJobResult             res;
+  const bool               single = nChunks == 1 || !j.fracMode;
+  if (single)
+  {
+    if (PASS != 0 || chunk != 0) return;
+    __syncthreads();
+    if (threadIdx.x == 0) keys[job] = ~0ull;   // leave the slot ready for the next call (no memset per call)
+    const uint32_t intCost = key_cost(key);
+    DevJobResult   res;
+    res.mvX    = dx;
+    res.mvY    = dy;
+    res.intSad = intCost - mv_cost(j.lambda, mv_bits_q(dx * 4, dy * 4, j.predQx, j.predQy, j.imvShift));
+    res.halfX = res.halfY = res.qterX = res.qterY = 0;
+    res.fracCost = res.intSad;
+    if (j.fracMode)
+    {
+      const FracJob f = make_frac_job(j, dx, dy);
+      if (j.imvShift > 1)
+      {
+        // xPatternSearchFracDIF :4311-4317 — integer AMVR: one SATD/SAD at the integer MV, rate at cost scale 2
+        frac_stage(sm, f, 0, 0, 2, false);
+        res.fracCost = sm.centre + mv_cost(j.lambda, mv_bits_q(dx * 4, dy * 4, j.predQx, j.predQy, j.imvShift));
+      }
+      else
+      {
+        const FracOut o = frac_refine_cta(sm, f);
+        res.halfX    = o.halfX;
+        res.halfY    = o.halfY;
+        res.qterX    = o.qterX;
+        res.qterY    = o.qterY;
+        res.fracCost = o.cost;
+      }
+    }
+    if (threadIdx.x == 0)
+    {
+      results[job] = res;   // mapped pinned host memory
+      __threadfence_system();
+    }
+    return;
+  }
+  // ---- one chunk of a large pattern
+  const FracJob f = make_frac_job(j, dx, dy);
+  uint32_t*     a = acc + (size_t) job * 18;
+  if (PASS == 0)
+  {
+    frac_stage_sums(sm, f, 0, 0, 2, j.useAltHpel != 0, chunk);
+    if (threadIdx.x < 9) atomicAdd(&a[threadIdx.x], sm.acc[threadIdx.x]);
+  }
+  else if (j.imvShift == 0)
+  {
+    if (threadIdx.x == 0)
+    {
+      int      dir;
+      uint32_t cost;
+      frac_pick(a, f, 0, 0, 2, dir, cost);
+      sm.best = dir;
+    }
+    __syncthreads();
+    const int hx = c_refineH[sm.best][0], hy = c_refineH[sm.best][1];
+    __syncthreads();
+    frac_stage_sums(sm, f, hx * 2, hy * 2, 1, false, chunk);
+    if (threadIdx.x < 9) atomicAdd(&a[9 + threadIdx.x], sm.acc[threadIdx.x]);
+  }
+}
+
+// Decisions and result of the large patterns; resets their key and sums for the next call.
+__global__ void __launch_bounds__(128) me_job_frac_finish_kernel(const DevJob* __restrict__ jobs,
+                                                                 unsigned long long* __restrict__ keys,
+                                                                 DevJobResult* __restrict__ results, uint32_t* __restrict__ acc,
+                                                                 int n)
+{
+  const int job = blockIdx.x * blockDim.x + threadIdx.x;
+  if (job >= n) return;
+  const DevJob j = jobs[job];
+  if (frac_num_chunks(j.w, j.h) == 1 || !j.fracMode) return;
+  const unsigned long long key = keys[job];
+  keys[job] = ~0ull;
+  const int      dx = key_dx(key), dy = key_dy(key);
+  const FracJob  f  = make_frac_job(j, dx, dy);
+  uint32_t*      a  = acc + (size_t) job * 18;
+  DevJobResult   res;
   res.mvX    = dx;
   res.mvY    = dy;
-  res.intSad = intCost - mv_cost(j.lambda, mv_bits_q(dx * 4, dy * 4, j.predQx, j.predQy, j.imvShift));
+  res.intSad = key_cost(key) - mv_cost(j.lambda, mv_bits_q(dx * 4, dy * 4, j.predQx, j.predQy, j.imvShift));
   res.halfX = res.halfY = res.qterX = res.qterY = 0;
-  res.fracCost = res.intSad;
-  if (j.fracMode)
+  if (j.imvShift > 1)
+    res.fracCost = a[0] + mv_cost(j.lambda, mv_bits_q(dx * 4, dy * 4, j.predQx, j.predQy, j.imvShift));
+  else
   {
-    FracJob f;
-    f.org        = j.org;
-    f.orgStride  = j.orgStride;
-    f.refAtMv    = j.refAtPU + (ptrdiff_t) dy * j.refStride + dx;
-    f.refStride  = j.refStride;
-    f.w          = j.w;
-    f.h          = j.h;
-    f.mvX        = dx;
-    f.mvY        = dy;
-    f.predQx     = j.predQx;
-    f.predQy     = j.predQy;
-    f.bitDepth   = j.bitDepth;
-    f.useHad     = j.useHad;
-    f.useAltHpel = j.useAltHpel;
-    f.imvShift   = j.imvShift;
-    f.lambda     = j.lambda;
-    if (j.imvShift > 1)
+    int      dir;
+    uint32_t cost;
+    frac_pick(a, f, 0, 0, 2, dir, cost);
+    res.halfX = c_refineH[dir][0];
+    res.halfY = c_refineH[dir][1];
+    if (j.imvShift == 0)
     {
-      // xPatternSearchFracDIF :4311-4317 — integer AMVR: one SATD/SAD at the integer MV, rate at cost scale 2
-      frac_stage(sm, f, 0, 0, 2, false);
-      res.fracCost = sm.centre + mv_cost(j.lambda, mv_bits_q(dx * 4, dy * 4, j.predQx, j.predQy, j.imvShift));
+      frac_pick(a + 9, f, res.halfX * 2, res.halfY * 2, 1, dir, cost);
+      res.qterX = c_refineQ[dir][0];
+      res.qterY = c_refineQ[dir][1];
     }
-    else
-    {
-      const FracOut o = frac_refine_cta(sm, f);
-      res.halfX    = o.halfX;
-      res.halfY    = o.halfY;
-      res.qterX    = o.qterX;
-      res.qterY    = o.qterY;
-      res.fracCost = o.cost;
-    }
+    res.fracCost = cost;
   }
-  if (threadIdx.x == 0) results[blockIdx.x] = res;
+  for (int i = 0; i < 18; i++) a[i] = 0;
+  results[job] = res;   // mapped pinned host memory
+  __threadfence_system();
 }
 
 }   // namespace
@@ -245,7 +337,8 @@ __global__ void __launch_bounds__(kFracThreads) me_job_frac_kernel(const DevJob*
 // offset by the caller (vtmme_api.cu) and passed through dSurf / dSurfOff.
 cudaError_t launch_job_search_impl(const DevJob* dJobs, unsigned long long* dKeys, DevJobResult* dResults, int n,
                                    int maxRegions, int nSplit, int maxGx, bool anyMulti, uint32_t* dSurf,
-                                   const long long* dSurfOff, cudaStream_t st, int* launches)
+                                   const long long* dSurfOff, uint32_t* dFracAcc, int maxFracChunks, cudaStream_t st,
+                                   int* launches)
 {
   const size_t smem = (size_t) kJobOffRef + (size_t) (kJobBandRows + 31) * (maxGx * 8 + 40) * 2;
   static size_t configured = 0;
@@ -268,8 +361,15 @@ cudaError_t launch_job_search_impl(const DevJob* dJobs, unsigned long long* dKey
     if (e != cudaSuccess) return e;
     *launches += 1;
   }
-  me_job_frac_kernel<<<n, kFracThreads, 0, st>>>(dJobs, dKeys, dResults);
+  dim3 gf(maxFracChunks, n, 1);
+  me_job_frac_kernel<0><<<gf, kFracThreads, 0, st>>>(dJobs, dKeys, dResults, dFracAcc);
   *launches += 1;
+  if (maxFracChunks > 1)
+  {
+    me_job_frac_kernel<1><<<gf, kFracThreads, 0, st>>>(dJobs, dKeys, dResults, dFracAcc);
+    me_job_frac_finish_kernel<<<(n + 127) / 128, 128, 0, st>>>(dJobs, dKeys, dResults, dFracAcc, n);
+    *launches += 2;
+  }
   return cudaGetLastError();
 }
 

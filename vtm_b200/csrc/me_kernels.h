@@ -98,7 +98,8 @@ struct DevJobResult
 };
 cudaError_t launch_job_search_impl(const DevJob* dJobs, unsigned long long* dKeys, DevJobResult* dResults, int n,
                                    int maxRegions, int nSplit, int maxGx, bool anyMulti, uint32_t* dSurf,
-                                   const long long* dSurfOff, cudaStream_t st, int* launches);
+                                   const long long* dSurfOff, uint32_t* dFracAcc, int maxFracChunks, cudaStream_t st,
+                                   int* launches);
 
 // Table-level batches
 cudaError_t launch_dist_batch(int kind, const int16_t* org, int orgStride, long long orgBlockStride, const int16_t* cur,

@@ -47,6 +47,11 @@ struct vtmme_ctx
   size_t         hPinnedCap = 0;
   uint32_t*      dJobSurf = nullptr;
   size_t         jobSurfCap = 0;
+  unsigned long long* dJobKeys = nullptr;   // persistent, all-ones between calls (the frac kernel resets what it read)
+  size_t         jobKeysCap = 0;
+  uint32_t*      dJobFracAcc = nullptr;     // persistent, all-zero between calls (18 sums per job slot)
+  size_t         jobFracAccCap = 0;
+  unsigned char* dPinnedAlias = nullptr;    // device address of hPinned (mapped, zero-copy result write-back)
 
   bool        profiling = false;
   cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
@@ -220,6 +225,8 @@ void vtmme_destroy(vtmme_ctx* ctx)
   cudaFree(ctx->dFracAcc);
   cudaFree(ctx->dJobBuf);
   cudaFree(ctx->dJobSurf);
+  cudaFree(ctx->dJobKeys);
+  cudaFree(ctx->dJobFracAcc);
   if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
   for (int i = 0; i < 4; i++)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -460,13 +467,22 @@ static int ensure_pinned(vtmme_ctx* ctx, size_t bytes)
   ctx->hPinned    = nullptr;
   ctx->hPinnedCap = 0;
   void* p = nullptr;
-  if (cudaMallocHost(&p, bytes) != cudaSuccess)
+  bytes   = (bytes + 65535) & ~(size_t) 65535;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocMapped) != cudaSuccess)
   {
     cudaGetLastError();
-    return vtmme_set_error(ctx, VTMME_ERR_NOMEM, "cudaMallocHost", "out of pinned host memory");
+    return vtmme_set_error(ctx, VTMME_ERR_NOMEM, "cudaHostAlloc", "out of pinned host memory");
   }
-  ctx->hPinned    = reinterpret_cast<unsigned char*>(p);
-  ctx->hPinnedCap = bytes;
+  void* dp = nullptr;
+  if (cudaHostGetDevicePointer(&dp, p, 0) != cudaSuccess)
+  {
+    cudaGetLastError();
+    cudaFreeHost(p);
+    return vtmme_set_error(ctx, VTMME_ERR_CUDA, "cudaHostGetDevicePointer", "mapped pinned memory unavailable");
+  }
+  ctx->hPinned      = reinterpret_cast<unsigned char*>(p);
+  ctx->dPinnedAlias = reinterpret_cast<unsigned char*>(dp);
+  ctx->hPinnedCap   = bytes;
   return VTMME_OK;
 }
 
@@ -480,7 +496,7 @@ extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_
 
   // ---- validate, size the buffers
   size_t orgBytes = 0, surfElems = 0;
-  int    maxGx = 1, maxRegions = 1, maxBands = 1;
+  int    maxGx = 1, maxRegions = 1, maxBands = 1, maxFracChunks = 1;
   long long totalRegions = 0;
   bool   anyMulti = false;
   for (int i = 0; i < n; i++)
@@ -508,6 +524,7 @@ extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_
     const int nReg = ((j.w + 31) >> 5) * ((j.h + 31) >> 5);
     maxGx      = ngx > maxGx ? ngx : maxGx;
     maxRegions = nReg > maxRegions ? nReg : maxRegions;
+    if (j.fracMode && nReg > maxFracChunks) maxFracChunks = nReg;   // fractional chunks are 32x32 too
     maxBands   = (nrows + 31) / 32 > maxBands ? (nrows + 31) / 32 : maxBands;
     totalRegions += nReg;
     if (nReg > 1)
@@ -580,17 +597,23 @@ extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_
     }
   }
   VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dJobBuf, ctx->hPinned, upBytes, cudaMemcpyHostToDevice, ctx->stream));
-  VTMME_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dJobBuf + offKeys, 0xff, (size_t) n * 8, ctx->stream));
+  if ((size_t) n * 8 > ctx->jobKeysCap)
+  {
+    const size_t want = (size_t) (n < 256 ? 256 : n) * 8;
+    if ((rc = ensure(ctx, ctx->dJobKeys, ctx->jobKeysCap, want)) != VTMME_OK) return rc;
+    VTMME_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dJobKeys, 0xff, want, ctx->stream));
+    if ((rc = ensure(ctx, ctx->dJobFracAcc, ctx->jobFracAccCap, want / 8 * 18 * 4)) != VTMME_OK) return rc;
+    VTMME_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dJobFracAcc, 0, want / 8 * 18 * 4, ctx->stream));
+  }
   int launches = 0;
   VTMME_CUDA_CHECK(ctx, launch_job_search_impl(reinterpret_cast<const DevJob*>(ctx->dJobBuf + offJobs),
-                                               reinterpret_cast<unsigned long long*>(ctx->dJobBuf + offKeys),
-                                               reinterpret_cast<DevJobResult*>(ctx->dJobBuf + offRes), n, maxRegions,
+                                               ctx->dJobKeys,
+                                               reinterpret_cast<DevJobResult*>(ctx->dPinnedAlias + offRes), n, maxRegions,
                                                nSplit, maxGx, anyMulti, ctx->dJobSurf,
                                                reinterpret_cast<const long long*>(ctx->dJobBuf + offSurfOff),
-                                               ctx->stream, &launches));
+                                               ctx->dJobFracAcc, maxFracChunks, ctx->stream, &launches));
   ctx->launches += launches;
-  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->hPinned + offRes, ctx->dJobBuf + offRes, (size_t) n * sizeof(DevJobResult),
-                                        cudaMemcpyDeviceToHost, ctx->stream));
+  // the frac kernel wrote the results straight into the mapped pinned block: no device-to-host copy
   VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   memcpy(results, ctx->hPinned + offRes, (size_t) n * sizeof(vtmme_result));
   return VTMME_OK;
