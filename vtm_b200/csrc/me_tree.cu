@@ -242,6 +242,7 @@ __global__ void __launch_bounds__(kTreeMaxThreads, DY == 2 ? 2 : 3) me_tree_sad_
     s_misc[2] = (wr - wl8 + 8) >> 3;   // ngx
     s_misc[3] = wb - wt + 1;           // nrows
     s_misc[4] = mask8;
+    s_misc[6] = wr - wl8 - (s_misc[2] - 1) * 8 + 1;   // valid displacements in the last 8-wide group (1..8)
   }
   __syncthreads();
   const int wl8 = s_misc[0], wt = s_misc[1], ngx = s_misc[2], nrows = s_misc[3], mask8 = s_misc[4];
@@ -321,7 +322,10 @@ __global__ void __launch_bounds__(kTreeMaxThreads, DY == 2 ? 2 : 3) me_tree_sad_
 
     // Tiles (8 displacements x DY rows) are handed out to warps 32 at a time from a shared counter, so that all
     // warps of the CTA finish within one tile of each other whatever the window size is.
-    const int ntiles = ngx * tileRows;
+    const int ntiles    = ngx * tileRows;
+    const int lastValid = s_misc[6];
+    const int ngxFull   = (DY == 1 && lastValid <= 4 && ngx > 1) ? ngx - 1 : ngx;
+    const int nFull     = ngxFull * tileRows;
     for (;;)
     {
       int tbase = 0;
@@ -330,7 +334,21 @@ __global__ void __launch_bounds__(kTreeMaxThreads, DY == 2 ? 2 : 3) me_tree_sad_
       if (tbase >= ntiles) break;
       const int t = tbase + (tid & 31);
       if (t >= ntiles) continue;
-      const int       tr = t / ngx, gx = t - tr * ngx;
+      // a last group with few valid displacements (129 = 16 * 8 + 1 for SR = 64) is handled by a narrow path; its
+      // tiles are numbered after all full tiles so that whole warps take one path
+      int  tr, gx;
+      bool narrow = false;
+      if (t < nFull)
+      {
+        tr = t / ngxFull;
+        gx = t - tr * ngxFull;
+      }
+      else
+      {
+        tr     = t - nFull;
+        gx     = ngx - 1;
+        narrow = true;
+      }
       const int       row0 = band0 + tr * DY;          // displacement row index of this tile's first row
       const int       dx0 = wl8 + gx * 8;
       const bool      row1ok = DY == 2 && (tr * DY + 1 < bh);
@@ -362,7 +380,32 @@ __global__ void __launch_bounds__(kTreeMaxThreads, DY == 2 ? 2 : 3) me_tree_sad_
             for (int d = 0; d < DY; d++)
 #pragma unroll
               for (int k = 0; k < 8; k++) a8[d][k] = 0;
-            if (DY == 1)
+            if (DY == 1 && narrow)
+            {
+              // only the first lastValid (<= 4) displacements exist: the others start from a value no minimum picks
+#pragma unroll
+              for (int k = 1; k < 8; k++)
+                if (k >= lastValid) a8[0][k] = 1u << 24;
+              const uint32_t* op = orgRow;
+              const uint16_t* rp = refRow;
+#pragma unroll 1
+              for (int r = 0; r < 8; r++)
+              {
+                uint32_t o[8], px[16];
+                load_org8(op, o);
+                load_ref16<false>(rp, px);
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                  if (k < lastValid)
+                  {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) a8[0][k] = __usad(o[i], px[i + k], a8[0][k]);
+                  }
+                op += 32;
+                rp += refStride;
+              }
+            }
+            else if (DY == 1)
             {
               const uint32_t* op = orgRow;
               const uint16_t* rp = refRow;
