@@ -57,11 +57,22 @@ def windows(level, pred_q=None):
     return l, r, t, b
 
 
-def workload_counts():
-    """Per pair: naive block-candidates (what the CPU evaluates) and reuse-minimal integer ops."""
-    cands, ops, ncu = 0, 0, 0
+def level_slices():
+    off, acc = [], 0
     for level in range(5):
-        l, r, t, b = windows(level)
+        s = 8 << level
+        off.append(acc)
+        acc += (WIDTH // s) * (HEIGHT // s)
+    return off + [acc]
+
+
+def workload_counts(pred_q=None):
+    """Per pair: naive block-candidates (what the CPU evaluates) and reuse-minimal integer ops.
+    pred_q: optional int16 [nCU, 2] quarter-pel predictors (run B)."""
+    cands, ops, ncu = 0, 0, 0
+    off = level_slices()
+    for level in range(5):
+        l, r, t, b = windows(level, None if pred_q is None else pred_q[off[level]:off[level + 1]])
         area = (r - l + 1) * (b - t + 1)
         n = len(area)
         ncu += n
@@ -222,6 +233,16 @@ def run_ours(args, rank, world, local_rank):
         del cur, ref
     prm = FrameParams(searchRange=SR, bitDepth=10, ctuSize=CTU, lambdaMotion=LAMBDA, predSpread=0)
     d_res = torch.zeros(B * ncu * CU_RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    d_pred_ptr, h_pred = 0, None
+    if args.run == "B":
+        # run B of config 4: seeded random quarter-pel predictors within +-16 px, one set per pair slot of a step
+        from vtm_b200.synth import random_predictors
+        h_pred = np.stack([random_predictors(7000 + i, ncu, 16) for i in range(B)])
+        d_pred = torch.from_numpy(h_pred).to(dev)
+        d_pred_ptr = d_pred.data_ptr()
+        prm.predSpread = 33
+        cands_pair = int(np.mean([workload_counts(h_pred[i])[0] for i in range(min(B, 4))]))
+        ops_pair = int(np.mean([workload_counts(h_pred[i])[1] for i in range(min(B, 4))]))
 
     def step_ids(s):
         sel = [(s * B + i) % pool for i in range(B)]
@@ -240,7 +261,7 @@ def run_ours(args, rank, world, local_rank):
 
     for s in range(W):
         c, r = step_ids(s)
-        ms.search_frames_device(c, r, prm, 0, d_res.data_ptr())
+        ms.search_frames_device(c, r, prm, d_pred_ptr, d_res.data_ptr())
     ms.set_profiling(True)
     sampler = ClockSampler(local_rank)
     launches0 = ms.launches
@@ -251,7 +272,7 @@ def run_ours(args, rank, world, local_rank):
     kms = []
     for s in range(W, W + K):
         c, r = step_ids(s)
-        ms.search_frames_device(c, r, prm, 0, d_res.data_ptr())
+        ms.search_frames_device(c, r, prm, d_pred_ptr, d_res.data_ptr())
         kms.append(ms.frame_kernel_ms())
     ev1.record(stream)
     barrier()
@@ -278,7 +299,7 @@ def run_ours(args, rank, world, local_rank):
 
     def e2e_search(s):
         base = 100000 + (s & 1) * 2 * B
-        return ms.search_frames([base + 2 * i for i in range(B)], [base + 2 * i + 1 for i in range(B)], prm)
+        return ms.search_frames([base + 2 * i for i in range(B)], [base + 2 * i + 1 for i in range(B)], prm, h_pred)
 
     # every timed step uploads the NEXT step's pictures while it searches its own (uploaded during the previous step)
     # and reads its results back to the host: per step, one full set of H2D copies and one D2H of all results
@@ -317,7 +338,7 @@ def run_ours(args, rank, world, local_rank):
             "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int16 samples, int32 SAD/SATD arithmetic", "data": "synthetic",
             "config": {"workload": "config4: synthetic 1080p 10-bit pairs, CUs 8..128 (43,020/pair), full search SR=64 "
-                                   "+ half/quarter-pel SATD refinement, zero predictors",
+                                   "+ half/quarter-pel SATD refinement, " + ("zero predictors (run A)" if args.run == "A" else "random quarter-pel predictors within +-16 px (run B)"),
                        "pairs_per_step_per_gpu": B, "pool_pairs_per_gpu": pool, "search_range": SR,
                        "block_candidates_per_pair": cands_pair, "frame_pairs_per_s": world * B * K / (elapsed_ms * 1e-3),
                        "l2": "inputs of a step (%d MB of planes + %d MB of SAD surfaces) exceed the 126 MB L2; steps cycle "
@@ -362,6 +383,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--cpu-every", type=int, default=1, help="CPU baseline sample: every n-th CU of pair 0")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--run", default="A", choices=["A", "B"], help="config 4 run A (zero predictors) or B (random predictors)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
