@@ -122,7 +122,7 @@ typedef struct
   int32_t useHad;        /* 1: SATD in the fractional stage                                         */
   int32_t fracMode;      /* 0 integer only, 1 half + quarter                                        */
   int32_t predSpread;    /* max |pred_a - pred_b| (integer pel, per component) among CUs of one CTU  */
-  int32_t reserved;
+  int32_t subShiftMode;  /* 0: every row; 2 (FEN=1/3): CUs with H > 8 and W <= 64 use even rows only, x2 (RdCost.cpp:310-316) */
   double  lambdaMotion;
 } vtmme_frame_params;
 

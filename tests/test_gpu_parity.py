@@ -54,6 +54,25 @@ def test_frame_search_integer_only_and_sad_frac(ms, oracle_lib):
     _frame_case(ms, oracle_lib, 128, 128, 12, 5, 4, use_had=0)
 
 
+def test_frame_search_row_subsampling(ms, oracle_lib):
+    """subShiftMode 2 (FEN=1, what the CTC encoder configs use): 16x16..64x64 CUs use 2 * SAD(even rows), 8x8 and
+    128x128 every row (RdCost.cpp:310-316) — zero and random predictors, partial regions."""
+    from vtm_b200 import FrameParams
+    from vtm_b200.synth import make_pair, random_predictors
+    for (w, h, sr, seed, spread) in [(256, 128, 16, 11, 0), (200, 152, 20, 12, 0), (256, 256, 12, 13, 6)]:
+        cur, ref, _ = make_pair(seed, w, h, max_global=10, max_local=12, n_rects=3, sigma=4.0)
+        refp = pad_plane(ref)
+        ms.upload_picture(1, cur)
+        ms.upload_picture(2, refp, MARGIN)
+        ncu = ms.set_frame_size(w, h)
+        pred = random_predictors(seed, ncu, spread) if spread else None
+        prm = FrameParams(searchRange=sr, predSpread=2 * spread + 1 if spread else 0, lambdaMotion=27.0, subShiftMode=2)
+        got = ms.search_frames([1], [2], prm, None if pred is None else pred[None])
+        want = oracle_frame_search(oracle_lib, cur, refp, MARGIN, sr, 27.0, pred, sub_shift_mode=2)
+        bad = [(i, gpu_tuple(got[0][i]), want[i]) for i in range(ncu) if gpu_tuple(got[0][i]) != want[i]]
+        assert not bad, "%dx%d: %d of %d CUs differ, first: %s" % (w, h, len(bad), ncu, bad[:3])
+
+
 def test_frame_search_sr64(ms, oracle_lib):
     # the BASELINE search range on a picture the oracle finishes in seconds
     _frame_case(ms, oracle_lib, 256, 256, 64, 6, 0)

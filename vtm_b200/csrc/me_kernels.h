@@ -46,6 +46,7 @@ struct TreeParams
   const short2*       predQ;     // [nPairs][nCU] quarter-pel, or nullptr (zero)
   unsigned long long* keys;      // [nPairs][nCU] best (cost, position) per CU
   uint32_t*           surf;      // [nPairs][nReg][surfCap] SAD32 surfaces for the 64/128 levels
+  uint32_t*           surfEven;  // same, even rows only x2 (subShiftMode 2: feeds the 64x64 level); nullptr in mode 0
   int4*               regInfo;   // [nPairs][nReg] {wl8, wt, ngx, nrows} of each surface
   int*                errFlag;
   int                 surfCap;     // elements per region surface
@@ -53,6 +54,7 @@ struct TreeParams
   int                 maxRows;     // capacity: displacement rows per region
   int                 bandRows;    // displacement rows staged per band
   int                 sr, ctu, imvShift;
+  int                 subShiftMode;   // 0 or 2
   double              lambda;
 };
 

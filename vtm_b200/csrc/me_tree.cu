@@ -151,9 +151,12 @@ __device__ __forceinline__ void load_org8(const uint32_t* p, uint32_t (&o)[8])
   o[4] = o1.x; o[5] = o1.y; o[6] = o1.z; o[7] = o1.w;
 }
 
-template <int NFP, bool FPU, int DY>
-__global__ void __launch_bounds__(kTreeMaxThreads, DY == 2 ? 2 : 3) me_tree_sad_kernel(TreeParams p)
+// SS (subShiftMode 2, DY == 1 only): CUs with H > 8 and W <= 64 (16x16 .. 64x64) use 2 * SAD(even rows)
+// (RdCost.cpp:310-316, 489); accumulator set 0 then holds the even rows and set 1 the odd rows (8x8) / all rows.
+template <int NFP, bool FPU, int DY, bool SS>
+__global__ void __launch_bounds__(kTreeMaxThreads, (DY == 2 || SS) ? 2 : 3) me_tree_sad_kernel(TreeParams p)
 {
+  constexpr int NACC = SS ? 2 : DY;
   extern __shared__ __align__(16) unsigned char smem[];
   uint32_t*           s_org  = reinterpret_cast<uint32_t*>(smem + kOffOrg);
   unsigned long long* s_best = reinterpret_cast<unsigned long long*>(smem + kOffBest);
@@ -295,6 +298,7 @@ __global__ void __launch_bounds__(kTreeMaxThreads, DY == 2 ? 2 : 3) me_tree_sad_
 
   const int refStride = ngx * 8 + 32;   // samples per staged row
   uint32_t* surf = p.surf + ((size_t) pair * p.g.nRegX * p.g.nRegY + region) * p.surfCap;
+  uint32_t* surfEven = SS ? p.surfEven + ((size_t) pair * p.g.nRegX * p.g.nRegY + region) * p.surfCap : nullptr;
 
   // ---- 4. bands of displacement rows ----------------------------------------------------------------
   for (int band0 = blockIdx.z * p.bandRows; band0 < nrows; band0 += gridDim.z * p.bandRows)
@@ -353,17 +357,17 @@ __global__ void __launch_bounds__(kTreeMaxThreads, DY == 2 ? 2 : 3) me_tree_sad_
       const int       dx0 = wl8 + gx * 8;
       const bool      row1ok = DY == 2 && (tr * DY + 1 < bh);
       const uint16_t* refTile = s_ref + tr * DY * refStride + gx * 8;
-      uint32_t        a32[DY][8];
+      uint32_t        a32[NACC][8];
 #pragma unroll
-      for (int d = 0; d < DY; d++)
+      for (int d = 0; d < NACC; d++)
 #pragma unroll
         for (int k = 0; k < 8; k++) a32[d][k] = 0;
 
       for (int q = 0; q < 4; q++)
       {
-        uint32_t a16[DY][8];
+        uint32_t a16[NACC][8];
 #pragma unroll
-        for (int d = 0; d < DY; d++)
+        for (int d = 0; d < NACC; d++)
 #pragma unroll
           for (int k = 0; k < 8; k++) a16[d][k] = 0;
         if ((mask8 >> (q * 4)) & 15)
@@ -375,9 +379,9 @@ __global__ void __launch_bounds__(kTreeMaxThreads, DY == 2 ? 2 : 3) me_tree_sad_
             const int bx = (q & 1) * 16 + (s & 1) * 8, by = (q >> 1) * 16 + (s >> 1) * 8;
             const uint32_t* orgRow = s_org + by * 32 + bx;
             const uint16_t* refRow = refTile + by * refStride + bx;
-            uint32_t        a8[DY][8];
+            uint32_t        a8[NACC][8];
 #pragma unroll
-            for (int d = 0; d < DY; d++)
+            for (int d = 0; d < NACC; d++)
 #pragma unroll
               for (int k = 0; k < 8; k++) a8[d][k] = 0;
             if (DY == 1 && narrow)
@@ -386,9 +390,15 @@ __global__ void __launch_bounds__(kTreeMaxThreads, DY == 2 ? 2 : 3) me_tree_sad_
 #pragma unroll
               for (int k = 1; k < 8; k++)
                 if (k >= lastValid) a8[0][k] = 1u << 24;
+              if (SS)
+              {
+#pragma unroll
+                for (int k = 1; k < 8; k++)
+                  if (k >= lastValid) a8[NACC - 1][k] = 1u << 24;
+              }
               const uint32_t* op = orgRow;
               const uint16_t* rp = refRow;
-#pragma unroll 1
+#pragma unroll 2
               for (int r = 0; r < 8; r++)
               {
                 uint32_t o[8], px[16];
@@ -399,7 +409,7 @@ __global__ void __launch_bounds__(kTreeMaxThreads, DY == 2 ? 2 : 3) me_tree_sad_
                   if (k < lastValid)
                   {
 #pragma unroll
-                    for (int i = 0; i < 8; i++) a8[0][k] = __usad(o[i], px[i + k], a8[0][k]);
+                    for (int i = 0; i < 8; i++) a8[SS ? (r & 1) : 0][k] = __usad(o[i], px[i + k], a8[SS ? (r & 1) : 0][k]);
                   }
                 op += 32;
                 rp += refStride;
@@ -415,7 +425,7 @@ __global__ void __launch_bounds__(kTreeMaxThreads, DY == 2 ? 2 : 3) me_tree_sad_
                 uint32_t o[8], px[16];
                 load_org8(op, o);
                 load_ref16<FPU>(rp, px);
-                sad_row<NFP>(a8[0], o, px);
+                sad_row<NFP>(a8[SS ? (r & 1) : 0], o, px);
                 op += 32;
                 rp += refStride;
               }
@@ -441,33 +451,87 @@ __global__ void __launch_bounds__(kTreeMaxThreads, DY == 2 ? 2 : 3) me_tree_sad_
                 }
               }
             }
-#pragma unroll
-            for (int d = 0; d < DY; d++)
+            if (SS)
             {
-              if (d == 0 || row1ok)
-              {
-                const uint32_t by = s_by[slot * rowsPad + row0 + d];
-                check8(a8[d], s_lut[s_minbx[slot * gxPad + gx] + by], s_bx + slot * bxStride + gx * 8, by, s_lut,
-                       &s_best[slot], dx0, wt + row0 + d);
-              }
+              // 8x8 CUs use every row; the parents need the even rows (x2 later) and, for 128x128, all rows
 #pragma unroll
-              for (int k = 0; k < 8; k++) a16[d][k] += a8[d][k];
+              for (int k = 0; k < 8; k++) a8[1][k] += a8[0][k];
+              const uint32_t by = s_by[slot * rowsPad + row0];
+              check8(a8[1], s_lut[s_minbx[slot * gxPad + gx] + by], s_bx + slot * bxStride + gx * 8, by, s_lut, &s_best[slot],
+                     dx0, wt + row0);
+#pragma unroll
+              for (int k = 0; k < 8; k++)
+              {
+                a16[0][k] += a8[0][k];
+                a16[1][k] += a8[1][k];
+              }
+            }
+            else
+            {
+#pragma unroll
+              for (int d = 0; d < DY; d++)
+              {
+                if (d == 0 || row1ok)
+                {
+                  const uint32_t by = s_by[slot * rowsPad + row0 + d];
+                  check8(a8[d], s_lut[s_minbx[slot * gxPad + gx] + by], s_bx + slot * bxStride + gx * 8, by, s_lut,
+                         &s_best[slot], dx0, wt + row0 + d);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) a16[d][k] += a8[d][k];
+              }
             }
           }
           if (s_cu[16 + q].idx >= 0)
+          {
+            if (SS)
+            {
+              uint32_t v[8];
 #pragma unroll
-            for (int d = 0; d < DY; d++)
-              if (d == 0 || row1ok)
-              {
-                const uint32_t by = s_by[(16 + q) * rowsPad + row0 + d];
-                check8(a16[d], s_lut[s_minbx[(16 + q) * gxPad + gx] + by], s_bx + (16 + q) * bxStride + gx * 8, by, s_lut,
-                       &s_best[16 + q], dx0, wt + row0 + d);
-              }
+              for (int k = 0; k < 8; k++) v[k] = a16[0][k] << 1;
+              const uint32_t by = s_by[(16 + q) * rowsPad + row0];
+              check8(v, s_lut[s_minbx[(16 + q) * gxPad + gx] + by], s_bx + (16 + q) * bxStride + gx * 8, by, s_lut,
+                     &s_best[16 + q], dx0, wt + row0);
+            }
+            else
+            {
+#pragma unroll
+              for (int d = 0; d < DY; d++)
+                if (d == 0 || row1ok)
+                {
+                  const uint32_t by = s_by[(16 + q) * rowsPad + row0 + d];
+                  check8(a16[d], s_lut[s_minbx[(16 + q) * gxPad + gx] + by], s_bx + (16 + q) * bxStride + gx * 8, by, s_lut,
+                         &s_best[16 + q], dx0, wt + row0 + d);
+                }
+            }
+          }
         }
 #pragma unroll
-        for (int d = 0; d < DY; d++)
+        for (int d = 0; d < NACC; d++)
 #pragma unroll
           for (int k = 0; k < 8; k++) a32[d][k] += a16[d][k];
+      }
+      if (SS)
+      {
+        uint32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = a32[0][k] << 1;
+        if (s_cu[20].idx >= 0)
+        {
+          const uint32_t by = s_by[20 * rowsPad + row0];
+          check8(v, s_lut[s_minbx[20 * gxPad + gx] + by], s_bx + 20 * bxStride + gx * 8, by, s_lut, &s_best[20], dx0, wt + row0);
+        }
+        if (writeSurf)
+        {
+          const size_t so = (size_t) row0 * (ngx * 8) + gx * 8;
+          uint4* de = reinterpret_cast<uint4*>(surfEven + so);
+          de[0]     = make_uint4(v[0], v[1], v[2], v[3]);
+          de[1]     = make_uint4(v[4], v[5], v[6], v[7]);
+          uint4* df = reinterpret_cast<uint4*>(surf + so);
+          df[0]     = make_uint4(a32[1][0], a32[1][1], a32[1][2], a32[1][3]);
+          df[1]     = make_uint4(a32[1][4], a32[1][5], a32[1][6], a32[1][7]);
+        }
+        continue;
       }
 #pragma unroll
       for (int d = 0; d < DY; d++)
@@ -502,6 +566,7 @@ __global__ void __launch_bounds__(kUpperThreads) me_tree_upper_kernel(TreeParams
   __shared__ CuInfo          s_cu[5];
   __shared__ int4            s_reg[16];
   __shared__ const uint32_t* s_surf[16];
+  __shared__ const uint32_t* s_surfE[16];   // even-row surfaces (subShiftMode 2), else the same as s_surf
   __shared__ int             s_box[4];
   __shared__ uint32_t        s_lut[512];
 
@@ -542,15 +607,17 @@ __global__ void __launch_bounds__(kUpperThreads) me_tree_upper_kernel(TreeParams
     const int i = tid - 32;
     const int rx = cx * 4 + (i & 3), ry = cy * 4 + (i >> 2);
     int4      info = make_int4(0, 0, 0, 0);
-    const uint32_t* sp = nullptr;
+    const uint32_t *sp = nullptr, *se = nullptr;
     if (rx < p.g.nx[2] && ry < p.g.ny[2])
     {
       const size_t r = (size_t) pair * nReg + ry * p.g.nRegX + rx;
       info = p.regInfo[r];
       sp   = p.surf + r * p.surfCap;
+      se   = p.subShiftMode == 2 ? p.surfEven + r * p.surfCap : sp;
     }
-    s_reg[i]  = info;
-    s_surf[i] = sp;
+    s_reg[i]   = info;
+    s_surf[i]  = sp;
+    s_surfE[i] = se;
   }
   for (int i = tid; i < 512; i += kUpperThreads) s_lut[i] = i < 256 ? mv_cost(p.lambda, (uint32_t) i) : kLutInvalid;
   __syncthreads();
@@ -610,11 +677,13 @@ __global__ void __launch_bounds__(kUpperThreads) me_tree_upper_kernel(TreeParams
       any |= bits[s] < 256;
     }
     if (!any) continue;
-    uint32_t s64[4];
+    // s64: what the 64x64 CUs compare (even rows x2 in subShiftMode 2); s64f: all rows, summed into the 128x128 CU
+    const bool twoSurf = p.subShiftMode == 2;
+    uint32_t   s64[4], s64f[4];
 #pragma unroll
     for (int j = 0; j < 4; j++)
     {
-      s64[j] = 0;
+      s64[j] = s64f[j] = 0;
       if (bits[j] < 256 || bits[4] < 256)
       {
 #pragma unroll
@@ -622,14 +691,20 @@ __global__ void __launch_bounds__(kUpperThreads) me_tree_upper_kernel(TreeParams
         {
           const int  ri   = ((j >> 1) * 2 + (k >> 1)) * 4 + (j & 1) * 2 + (k & 1);
           const int4 info = s_reg[ri];
-          if (s_surf[ri]) s64[j] += s_surf[ri][(size_t) (dy - info.y) * (info.z * 8) + (dx - info.x)];
+          if (s_surf[ri])
+          {
+            const size_t o = (size_t) (dy - info.y) * (info.z * 8) + (dx - info.x);
+            const uint32_t f = s_surf[ri][o];
+            s64f[j] += f;
+            s64[j] += twoSurf ? s_surfE[ri][o] : f;
+          }
         }
       }
     }
 #pragma unroll
     for (int s = 0; s < 5; s++)
     {
-      const uint32_t sad  = s < 4 ? s64[s] : s64[0] + s64[1] + s64[2] + s64[3];
+      const uint32_t sad  = s < 4 ? s64[s] : s64f[0] + s64f[1] + s64f[2] + s64f[3];
       const uint32_t cost = sad + s_lut[bits[s]];   // >= 0x3fffffff outside the window
       const unsigned long long k = make_key(cost, dx, dy);
       if (cost < kLutInvalid && k < best[s]) best[s] = k;
@@ -668,18 +743,18 @@ static void tree_variant(int& nfp, int& fpu, int& dy, int& threads)
   nfp = v[0]; fpu = v[1]; dy = v[2]; threads = v[3];
 }
 
-template <int NFP, bool FPU, int DY>
+template <int NFP, bool FPU, int DY, bool SS>
 static cudaError_t launch_tree_sad_t(const TreeParams& p, int nPairs, int threads, size_t smem, cudaStream_t st)
 {
   static size_t configured = 0;
   if (smem > configured)
   {
-    cudaError_t e = cudaFuncSetAttribute(me_tree_sad_kernel<NFP, FPU, DY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    cudaError_t e = cudaFuncSetAttribute(me_tree_sad_kernel<NFP, FPU, DY, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
   dim3 grid(p.g.nRegX * p.g.nRegY, nPairs, 1);
-  me_tree_sad_kernel<NFP, FPU, DY><<<grid, threads, smem, st>>>(p);
+  me_tree_sad_kernel<NFP, FPU, DY, SS><<<grid, threads, smem, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -697,8 +772,15 @@ cudaError_t launch_tree_sad(const TreeParams& p, int nPairs, cudaStream_t st)
     if (threads > kTreeMaxThreads) threads = kTreeMaxThreads;
     if (threads < 128) threads = 128;
   }
+  if (p.subShiftMode == 2)   // row sub-sampling: one instantiation (1 displacement row per tile)
+  {
+    const int ngx = (2 * p.sr + 1 + 7) / 8, tiles = ngx * (2 * p.sr + 1);
+    int       thr = ((tiles + (tiles + 255) / 256 - 1) / ((tiles + 255) / 256) + 127) & ~127;
+    thr           = thr > kTreeMaxThreads ? kTreeMaxThreads : (thr < 128 ? 128 : thr);
+    return launch_tree_sad_t<2, true, 1, true>(p, nPairs, thr, smem, st);
+  }
 #define VTMME_TREE_CASE(N, F, D) \
-  if (nfp == N && fpu == F && dy == D) return launch_tree_sad_t<N, F != 0, D>(p, nPairs, threads, smem, st);
+  if (nfp == N && fpu == F && dy == D) return launch_tree_sad_t<N, F != 0, D, false>(p, nPairs, threads, smem, st);
   VTMME_TREE_CASE(0, 0, 1) VTMME_TREE_CASE(0, 1, 1) VTMME_TREE_CASE(1, 1, 1) VTMME_TREE_CASE(2, 1, 1) VTMME_TREE_CASE(3, 1, 1)
   VTMME_TREE_CASE(0, 0, 2) VTMME_TREE_CASE(0, 1, 2) VTMME_TREE_CASE(1, 1, 2) VTMME_TREE_CASE(2, 1, 2) VTMME_TREE_CASE(3, 1, 2)
   VTMME_TREE_CASE(2, 0, 2) VTMME_TREE_CASE(2, 0, 1)

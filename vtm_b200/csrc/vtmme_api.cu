@@ -30,6 +30,8 @@ struct vtmme_ctx
   size_t              keysCap = 0;
   uint32_t*           dSurf = nullptr;
   size_t              surfCapBytes = 0;
+  uint32_t*           dSurfEven = nullptr;
+  size_t              surfEvenCapBytes = 0;
   int4*               dRegInfo = nullptr;
   size_t              regInfoCap = 0;
   int*                dErr = nullptr;
@@ -218,6 +220,7 @@ void vtmme_destroy(vtmme_ctx* ctx)
   cudaFree(ctx->dRef);
   cudaFree(ctx->dKeys);
   cudaFree(ctx->dSurf);
+  cudaFree(ctx->dSurfEven);
   cudaFree(ctx->dRegInfo);
   cudaFree(ctx->dErr);
   cudaFree(ctx->dPred);
@@ -324,7 +327,8 @@ int vtmme_search_frames_device(vtmme_ctx* ctx, int nPairs, const int32_t* curPic
   if (!ctx) return VTMME_ERR_ARG;
   if (nPairs <= 0 || !curPics || !refPics || !prm || !dResults)
     return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search_frames", "null argument");
-  if (prm->searchRange < 1 || prm->searchRange > 512 || prm->bitDepth < 8 || prm->bitDepth > 10 || prm->predSpread < 0)
+  if (prm->searchRange < 1 || prm->searchRange > 512 || prm->bitDepth < 8 || prm->bitDepth > 10 || prm->predSpread < 0 ||
+      (prm->subShiftMode != 0 && prm->subShiftMode != 2))
     return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search_frames", "unsupported parameters");
   VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
 
@@ -366,6 +370,9 @@ int vtmme_search_frames_device(vtmme_ctx* ctx, int nPairs, const int32_t* curPic
   if ((rc = ensure(ctx, ctx->dRef, ctx->refArrCap, (size_t) nPairs * sizeof(DevPic))) != VTMME_OK) return rc;
   if ((rc = ensure(ctx, ctx->dKeys, ctx->keysCap, (size_t) nPairs * nCU * 8)) != VTMME_OK) return rc;
   if ((rc = ensure(ctx, ctx->dSurf, ctx->surfCapBytes, (size_t) nPairs * nReg * surfCap * 4)) != VTMME_OK) return rc;
+  if (prm->subShiftMode == 2 &&
+      (rc = ensure(ctx, ctx->dSurfEven, ctx->surfEvenCapBytes, (size_t) nPairs * nReg * surfCap * 4)) != VTMME_OK)
+    return rc;
   if ((rc = ensure(ctx, ctx->dRegInfo, ctx->regInfoCap, (size_t) nPairs * nReg * sizeof(int4))) != VTMME_OK) return rc;
   if ((rc = ensure(ctx, ctx->dFracAcc, ctx->fracAccCap, frac_frame_acc_bytes(g, nPairs))) != VTMME_OK) return rc;
 
@@ -382,6 +389,8 @@ int vtmme_search_frames_device(vtmme_ctx* ctx, int nPairs, const int32_t* curPic
   tp.predQ    = reinterpret_cast<const short2*>(dPredQ);
   tp.keys     = ctx->dKeys;
   tp.surf     = ctx->dSurf;
+  tp.surfEven = prm->subShiftMode == 2 ? ctx->dSurfEven : nullptr;
+  tp.subShiftMode = prm->subShiftMode;
   tp.regInfo  = ctx->dRegInfo;
   tp.errFlag  = ctx->dErr;
   tp.surfCap  = (int) surfCap;

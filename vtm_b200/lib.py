@@ -44,7 +44,7 @@ class CResult(C.Structure):
 class CFrameParams(C.Structure):
     """vtmme_frame_params"""
     _fields_ = [("searchRange", C.c_int32), ("bitDepth", C.c_int32), ("ctuSize", C.c_int32), ("imvShift", C.c_int32),
-                ("useHad", C.c_int32), ("fracMode", C.c_int32), ("predSpread", C.c_int32), ("reserved", C.c_int32),
+                ("useHad", C.c_int32), ("fracMode", C.c_int32), ("predSpread", C.c_int32), ("subShiftMode", C.c_int32),
                 ("lambdaMotion", C.c_double)]
 
 

@@ -26,10 +26,11 @@ class FrameParams:
     fracMode: int = 1
     predSpread: int = 0
     lambdaMotion: float = 31.33
+    subShiftMode: int = 0
 
     def c(self):
         return CFrameParams(self.searchRange, self.bitDepth, self.ctuSize, self.imvShift, self.useHad, self.fracMode,
-                            self.predSpread, 0, self.lambdaMotion)
+                            self.predSpread, self.subShiftMode, self.lambdaMotion)
 
 
 @dataclass
