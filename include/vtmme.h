@@ -173,6 +173,38 @@ int vtmme_interp_host(vtmme_ctx* ctx, int comp, int vertical, const int16_t* src
 int vtmme_filter_host(vtmme_ctx* ctx, int nTaps, int vertical, int isFirst, int isLast, int copy, const int16_t* src,
                       int srcStride, int16_t* dst, int dstStride, int w, int h, const int16_t* coeff, int bitDepth);
 
+/* ---- motion compensation (the consumer of the motion vectors the search returns) ------------------
+ * Uni-directional block prediction with the semantics of InterPrediction::xPredInterBlk
+ * (CommonLib/InterPrediction.cpp:660-830), plain path: no RPR, wrap-around, BDOF padding, DMVR or
+ * bilinear filter.  comp 0: luma plane, 8-tap, 4 fractional MV bits; comp 1: a 4:2:0 chroma plane
+ * (uploaded as a picture of its own), 4-tap, 5 fractional bits of the SAME luma MV (:675-676).
+ * bi != 0 keeps the 14-bit intermediates (rndRes = !bi, :673) for vtmme_add_avg.  The MV must already
+ * be clipped (clipMv, as xPredInterUni does): a block whose taps leave the padded plane is
+ * VTMME_ERR_RANGE.  Block i's w*h samples are written packed (row stride w) at the sum of the
+ * previous blocks' sizes. */
+typedef struct vtmme_mc_block
+{
+  int32_t refPic;    /* uploaded plane of the component */
+  int32_t x, y;      /* block position in samples of that plane */
+  int32_t w, h;      /* 1..128 */
+  int32_t mvX, mvY;  /* 1/16 luma sample (MV_PRECISION_INTERNAL) */
+  int32_t reserved;  /* 0 */
+} vtmme_mc_block;
+
+/* blocks: HOST array; dDst: DEVICE buffer; asynchronous on the context stream. */
+int vtmme_mc_batch(vtmme_ctx* ctx, int comp, int bi, int bitDepth, int useAltHpel, int n, const vtmme_mc_block* blocks,
+                   int16_t* dDst);
+/* dst: HOST buffer; synchronous. */
+int vtmme_mc_host(vtmme_ctx* ctx, int comp, int bi, int bitDepth, int useAltHpel, int n, const vtmme_mc_block* blocks,
+                  int16_t* dst);
+/* AreaBuf<Pel>::addAvg (CommonLib/Buffer.cpp:467-507): dDst = clip((dSrc0 + dSrc1 + offset) >> shift) over count
+ * samples of two bi != 0 predictions.  DEVICE pointers, asynchronous. */
+int vtmme_add_avg(vtmme_ctx* ctx, const int16_t* dSrc0, const int16_t* dSrc1, int16_t* dDst, int64_t count, int bitDepth);
+/* AreaBuf<T>::removeHighFreq (CommonLib/Buffer.h:474-517): dOrg = 2*dOrg - dPred (clipped to the sample range when
+ * clip != 0) — how the pattern of a bi-predictive search is formed from the original block and the other
+ * direction's prediction (InterSearch.cpp:3317-3325).  DEVICE pointers, asynchronous. */
+int vtmme_remove_high_freq(vtmme_ctx* ctx, int16_t* dOrg, const int16_t* dPred, int64_t count, int clip, int bitDepth);
+
 /* ---- measurement helpers ------------------------------------------------------------------------
  * Per-kernel timing of the frame path: when enabled, vtmme_search_frames[_device] brackets each of its
  * kernels with CUDA events on the context stream; vtmme_frame_kernel_ms returns the durations of the most

@@ -78,6 +78,9 @@ def oracle():
         L.vo_pred_qpel.argtypes = [C.POINTER(Job), _I, _I, _I, _I, _I, _P, _I]
         L.vo_me_finish.argtypes = [C.POINTER(Job), C.POINTER(Result), C.c_double, C.c_uint32,
                                    C.POINTER(_I), C.POINTER(_I), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+        L.vo_mc_block.argtypes = [_I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I]
+        L.vo_add_avg.argtypes = [_P, _P, _P, _I, _I]
+        L.vo_remove_high_freq.argtypes = [_P, _P, _I, _I, _I]
         _oracle = L
     return _oracle
 
@@ -106,6 +109,9 @@ def ref():
         L.ref_dist_batch.argtypes = [_P, _P, _I, _I, _I, _I, _I, _I, _P]
         L.ref_filter_batch.restype = C.c_double
         L.ref_filter_batch.argtypes = [_I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I]
+        L.ref_mc_blocks.argtypes = [_I, _P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P]
+        L.ref_add_avg.argtypes = [_P, _P, _P, _I, _I, _I]
+        L.ref_remove_high_freq.argtypes = [_P, _I, _P, _I, _I, _I, _I, _I]
         _ref = L
     return _ref
 

@@ -8,6 +8,7 @@
 //   InterpolationFilter::filterHor / filterVer          (CommonLib/InterpolationFilter.cpp:749-895)
 //   InterSearch::xPatternSearch                         (EncoderLib/InterSearch.cpp:3566-3608)
 //   InterSearch::xExtDIFUpSamplingH/Q, xPatternRefinement (InterSearch.cpp:5840-6050, 707-761)
+//   InterPrediction::xPredInterBlk                      (CommonLib/InterPrediction.cpp:660-830), AreaBuf::removeHighFreq
 //
 // xPatternSearchFracDIF itself needs a PredictionUnit with a slice; its PU-independent body
 // (InterSearch.cpp:4296-4338) is driven here by calling the three reference functions it calls.
@@ -25,6 +26,9 @@
 #include "CommonLib/InterpolationFilter.h"
 #include "CommonLib/InterPrediction.h"
 #include "CommonLib/Buffer.h"
+#include "CommonLib/Picture.h"
+#include "CommonLib/Slice.h"
+#include "CommonLib/CodingStructure.h"
 #include "EncoderLib/EncCfg.h"
 #include "EncoderLib/InterSearch.h"
 
@@ -261,6 +265,72 @@ double ref_filter_batch(int comp, int vertical, const int16_t* src, int16_t* dst
   }
   auto t1 = std::chrono::steady_clock::now();
   return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// ---- motion compensation: the reference's own InterPrediction::xPredInterBlk (InterPrediction.cpp:660-830) -------------
+// A Picture is created with the given luma size, the reconstruction plane of component `comp` (0 Y, 1 Cb) is loaded from
+// `plane` (component-sized, `margin` border samples on each side already extended), and xPredInterBlk runs for every block.
+// blk: n x 6 int32 {x, y, w, h, mvX, mvY}; x,y,w,h in samples of the component, mv in 1/16 luma sample.
+// dst: blocks packed back to back (row stride = w).  Returns 0, or -1 when the margin does not fit the Picture's own.
+int ref_mc_blocks(int comp, const int16_t* plane, int planeStride, int lumaW, int lumaH, int margin, int n,
+                  const int32_t* blk, int bi, int bitDepth, int imvHpel, int16_t* dst)
+{
+  Probe& p = probe();
+  Picture pic;
+  pic.create(CHROMA_420, Size(lumaW, lumaH), 128, 128 + 16, false, 0);
+  pic.unscaledPic = &pic;
+  PelBuf reco = pic.getRecoBuf(ComponentID(comp));
+  const int cw = comp ? lumaW / 2 : lumaW, ch = comp ? lumaH / 2 : lumaH;
+  if (margin > (int) (pic.margin >> (comp ? 1 : 0))) return -1;
+  for (int y = -margin; y < ch + margin; y++)
+    memcpy(reco.buf + (ptrdiff_t) y * reco.stride - margin, plane + (ptrdiff_t) (y + margin) * planeStride,
+           sizeof(int16_t) * (cw + 2 * margin));
+
+  PPS pps;
+  pps.setPicWidthInLumaSamples(lumaW);
+  pps.setPicHeightInLumaSamples(lumaH);
+  SPS sps;
+  // xPredInterBlk reads cs->sps / cs->pps only (wrap-around, RPR): a zeroed CodingStructure shell carries the two pointers
+  std::vector<uint64_t> shell((sizeof(CodingStructure) + 7) / 8, 0);
+  CodingStructure* cs = reinterpret_cast<CodingStructure*>(shell.data());
+  cs->sps = &sps;
+  cs->pps = &pps;
+  const ClpRng clp = makeClp(bitDepth);
+  const int    sc  = comp ? 1 : 0;
+  for (int i = 0; i < n; i++)
+  {
+    const int32_t* b = blk + 6 * i;
+    const int w = b[2], h = b[3];
+    CodingUnit     cu;
+    cu.imv    = imvHpel ? IMV_HPEL : IMV_OFF;
+    cu.affine = false;
+    PredictionUnit pu(CHROMA_420, Area(b[0] << sc, b[1] << sc, w << sc, h << sc));
+    pu.cu = &cu;
+    pu.cs = cs;
+    PelBuf     d(dst, w, w, h);
+    PelBuf     none;
+    PelUnitBuf out = comp ? PelUnitBuf(CHROMA_420, none, d, none) : PelUnitBuf(CHROMA_420, d);
+    p.xPredInterBlk(ComponentID(comp), pu, &pic, Mv(b[4], b[5]), out, bi != 0, clp, false, false);
+    dst += w * h;
+  }
+  pic.destroy();
+  return 0;
+}
+
+// AreaBuf<Pel>::removeHighFreq (Buffer.h:474-517): dst = 2*dst - src, optionally clipped (bi-pred ME target)
+void ref_remove_high_freq(int16_t* dst, int dstStride, const int16_t* src, int srcStride, int w, int h, int clip, int bd)
+{
+  PelBuf  d(dst, dstStride, w, h);
+  PelBuf  s(const_cast<int16_t*>(src), srcStride, w, h);
+  d.removeHighFreq(s, clip != 0, makeClp(bd));
+}
+
+// AreaBuf<Pel>::addAvg (Buffer.cpp:467-507) through the SIMD table where the width allows
+void ref_add_avg(const int16_t* s0, const int16_t* s1, int16_t* dst, int w, int h, int bd)
+{
+  PelBuf  d(dst, w, w, h);
+  CPelBuf a(s0, w, w, h), b(s1, w, w, h);
+  d.addAvg(a, b, makeClp(bd));
 }
 
 // Batch driver used as the CPU baseline: nThreads workers over disjoint job ranges.

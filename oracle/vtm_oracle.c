@@ -7,6 +7,7 @@
 
 #include <limits.h>
 #include <math.h>
+#include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
@@ -626,6 +627,57 @@ double vo_search_batch(const vo_job* jobs, vo_result* res, int n, int literal)
   for (int i = 0; i < n; i++) vo_search(&jobs[i], &res[i], literal);
   clock_gettime(CLOCK_MONOTONIC, &t1);
   return (double) (t1.tv_sec - t0.tv_sec) + 1e-9 * (double) (t1.tv_nsec - t0.tv_nsec);
+}
+
+/* ---- motion compensation (SURVEY.md §8f "next": the caller-side consumer of the found MVs) ------------------------- */
+
+/* InterPrediction::xPredInterBlk — CommonLib/InterPrediction.cpp:660-830, the plain path (no RPR, wrap-around, BDOF
+ * padding, DMVR or bilinear).  refAtBlk: component plane at the block position; mv in 1/16 luma sample, so the
+ * fractional part has 4 bits for luma and 5 for 4:2:0 chroma (:675-676, :697-698).  bi != 0 leaves the 14-bit
+ * intermediates for the weighted average (rndRes = !bi, :673). */
+void vo_mc_block(int comp, const vo_pel* refAtBlk, int refStride, int w, int h, int mvX, int mvY, int bi, int bd,
+                 int useAltHpel, vo_pel* dst, int dstStride)
+{
+  const int     shift = 4 + (comp ? 1 : 0);
+  const int     xFrac = mvX & ((1 << shift) - 1), yFrac = mvY & ((1 << shift) - 1);
+  const vo_pel* src   = refAtBlk + (ptrdiff_t) (mvY >> shift) * refStride + (mvX >> shift);
+  const int     rnd   = !bi;
+  if (yFrac == 0)
+    vo_filter_hor(comp, src, refStride, dst, dstStride, w, h, xFrac, rnd, bd, useAltHpel);
+  else if (xFrac == 0)
+    vo_filter_ver(comp, src, refStride, dst, dstStride, w, h, yFrac, 1, rnd, bd, useAltHpel);
+  else
+  {
+    const int taps = comp ? 4 : VO_NTAPS_LUMA, above = (taps >> 1) - 1;
+    vo_pel    tmp[(VO_MAX_CU + 8) * VO_MAX_CU];
+    vo_filter_hor(comp, src - above * refStride, refStride, tmp, w, w, h + taps - 1, xFrac, 0, bd, useAltHpel);
+    vo_filter_ver(comp, tmp + above * w, w, dst, dstStride, w, h, yFrac, 0, rnd, bd, useAltHpel);
+  }
+}
+
+/* AreaBuf<Pel>::addAvg — CommonLib/Buffer.cpp:467-507 (the default bi-prediction average of two bi=1 predictions) */
+void vo_add_avg(const vo_pel* s0, const vo_pel* s1, vo_pel* dst, int n, int bd)
+{
+  const int shift  = ((VO_IF_INTERNAL_PREC - bd) > 2 ? (VO_IF_INTERNAL_PREC - bd) : 2) + 1;
+  const int offset = (1 << (shift - 1)) + 2 * VO_IF_INTERNAL_OFFS;
+  const int maxv   = (1 << bd) - 1;
+  for (int i = 0; i < n; i++)
+  {
+    int v  = (s0[i] + s1[i] + offset) >> shift;
+    dst[i] = (vo_pel) (v < 0 ? 0 : (v > maxv ? maxv : v));
+  }
+}
+
+/* AreaBuf<T>::removeHighFreq — CommonLib/Buffer.h:474-517: the bi-prediction search target 2*org - otherPred */
+void vo_remove_high_freq(vo_pel* dst, const vo_pel* src, int n, int clip, int bd)
+{
+  const int maxv = (1 << bd) - 1;
+  for (int i = 0; i < n; i++)
+  {
+    int v = 2 * dst[i] - src[i];
+    if (clip) v = v < 0 ? 0 : (v > maxv ? maxv : v);
+    dst[i] = (vo_pel) v;
+  }
 }
 
 /* Tail of xMotionEstimation — EncoderLib/InterSearch.cpp:3477-3484 */

@@ -81,6 +81,12 @@ void vo_pred_qpel(const vo_job* j, int mvx, int mvy, int dqx, int dqy, int useAl
 void vo_search(const vo_job* j, vo_result* r, int literal);
 double vo_search_batch(const vo_job* jobs, vo_result* res, int n, int literal);
 
+/* motion compensation of one block (xPredInterBlk plain path), bi-pred average, bi-pred search target */
+void vo_mc_block(int comp, const vo_pel* refAtBlk, int refStride, int w, int h, int mvX, int mvY, int bi, int bd,
+                 int useAltHpel, vo_pel* dst, int dstStride);
+void vo_add_avg(const vo_pel* s0, const vo_pel* s1, vo_pel* dst, int n, int bd);
+void vo_remove_high_freq(vo_pel* dst, const vo_pel* src, int n, int clip, int bd);
+
 /* tail of xMotionEstimation (InterSearch.cpp:3477-3484): final MV (quarter-pel), bits and cost */
 void vo_me_finish(const vo_job* j, const vo_result* r, double fWeight, uint32_t bitsIn, int* mvQx, int* mvQy,
                   uint32_t* bitsOut, uint64_t* costOut);

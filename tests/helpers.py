@@ -50,3 +50,43 @@ def oracle_frame_search(L, cur, ref_padded, margin, sr, lam, pred_q=None, frac=1
 def gpu_tuple(rec):
     return (int(rec["mvQx"]), int(rec["mvQy"]), int(rec["intX"]), int(rec["intY"]), int(rec["intSad"]),
             int(rec["fracCost"]))
+
+
+# ---- motion compensation -------------------------------------------------------------------------------------------
+def mc_cases(seed, comp, cw, ch, n, sizes=None, max_mv_pel=40):
+    """n blocks (x, y, w, h, mvX, mvY) inside a cw x ch component plane; MVs in 1/16 luma sample covering every
+    branch of xPredInterBlk (integer, horizontal-only, vertical-only, two-stage, half-pel)."""
+    rng = np.random.default_rng(seed)
+    if sizes is None:
+        sizes = [4, 8, 16, 32, 64, 128] if comp == 0 else [2, 4, 8, 16, 32, 64]
+    unit = 16 if comp == 0 else 32
+    out = []
+    for i in range(n):
+        w = min(int(rng.choice(sizes)), cw)
+        h = min(int(rng.choice(sizes)), ch)
+        x = int(rng.integers(0, (cw - w) // w + 1)) * w
+        y = int(rng.integers(0, (ch - h) // h + 1)) * h
+        mvx = int(rng.integers(-max_mv_pel * unit, max_mv_pel * unit))
+        mvy = int(rng.integers(-max_mv_pel * unit, max_mv_pel * unit))
+        if i % 5 == 0:
+            mvx &= ~(unit - 1)
+        if i % 7 == 0:
+            mvy &= ~(unit - 1)
+        if i % 11 == 0:
+            mvx = (mvx & ~(unit - 1)) | (unit // 2)
+        if i % 13 == 0:
+            mvy = (mvy & ~(unit - 1)) | (unit // 2)
+        out.append((x, y, w, h, mvx, mvy))
+    return out
+
+
+def oracle_mc(L, comp, padded, margin, blocks, bi=0, bit_depth=10, alt=0):
+    """vo_mc_block over the blocks; packed int16 like vtmme_mc_host."""
+    stride = padded.shape[1]
+    parts = []
+    for (x, y, w, h, mvx, mvy) in blocks:
+        d = np.zeros((h, w), np.int16)
+        L.vo_mc_block(comp, B.ptr(padded, (margin + y) * stride + margin + x), stride, w, h, mvx, mvy, bi, bit_depth,
+                      alt, B.ptr(d), w)
+        parts.append(d.ravel())
+    return np.concatenate(parts)

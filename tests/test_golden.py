@@ -82,3 +82,43 @@ def test_search_golden(oracle_lib, literal):
         r = B.Result()
         oracle_lib.vo_search(C.byref(j), C.byref(r), literal)
         assert r.tuple() == want, (w, h, imv, ssm, literal)
+
+
+# ---- motion compensation fixtures (tests/golden/mc_golden.npz, from the reference's xPredInterBlk) -------------------
+GM = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mc_golden.npz"))
+
+
+def iter_mc():
+    """(comp, padded plane, margin, blocks, bi, alt, golden packed prediction)"""
+    m = int(GM["dims"][2])
+    for comp, name in ((0, "y"), (1, "c")):
+        padded = np.ascontiguousarray(np.pad(GM["plane_" + name], m, mode="edge"))
+        blks = [tuple(int(v) for v in b) for b in GM["blocks_" + name]]
+        for bi in (0, 1):
+            for alt in (0, 1):
+                key = "pred_%s_bi%d_alt%d" % (name, bi, alt)
+                if key in GM:
+                    yield comp, padded, m, blks, bi, alt, GM[key]
+
+
+def test_oracle_mc_golden():
+    from tests.helpers import oracle_mc
+    L = B.oracle()
+    n = 0
+    for comp, padded, m, blks, bi, alt, want in iter_mc():
+        assert np.array_equal(oracle_mc(L, comp, padded, m, blks, bi, 10, alt), want), (comp, bi, alt)
+        n += 1
+    assert n == 6
+
+
+def test_oracle_bipred_helpers_golden():
+    L = B.oracle()
+    s0, s1 = np.ascontiguousarray(GM["avg_s0"]), np.ascontiguousarray(GM["avg_s1"])
+    d = np.zeros_like(s0)
+    L.vo_add_avg(B.ptr(s0), B.ptr(s1), B.ptr(d), s0.size, 10)
+    assert np.array_equal(d, GM["avg_out"])
+    pred = np.ascontiguousarray(GM["hf_pred"])
+    for clip in (0, 1):
+        t = np.ascontiguousarray(GM["hf_org"]).copy()
+        L.vo_remove_high_freq(B.ptr(t), B.ptr(pred), t.size, clip, 10)
+        assert np.array_equal(t, GM["hf_out%d" % clip])

@@ -194,3 +194,63 @@ def test_fractional_branches_match_reference(oracle_lib, ref_lib):
         seen.add((r0.halfX, r0.halfY, r0.qterX, r0.qterY))
     assert len({s[:2] for s in seen}) >= 8      # (nearly) all nine half-pel outcomes
     assert len(seen) >= 30                      # and a good share of the 81 (half, quarter) combinations
+
+
+# ---- motion compensation: the oracle against the reference's own InterPrediction::xPredInterBlk ---------------------
+@pytest.mark.ref
+@pytest.mark.parametrize("comp", [0, 1])
+@pytest.mark.parametrize("bi", [0, 1])
+@pytest.mark.parametrize("alt", [0, 1])
+def test_mc_block_matches_xPredInterBlk(oracle_lib, ref_lib, comp, bi, alt):
+    from tests.helpers import mc_cases, oracle_mc
+    W, H, M = 256, 128, 96
+    cw, ch = (W, H) if comp == 0 else (W // 2, H // 2)
+    rng = np.random.default_rng(20 + comp)
+    padded = np.ascontiguousarray(np.pad(rng.integers(0, 1024, (ch, cw), dtype=np.int16), M, mode="edge"))
+    blks = mc_cases(31 + comp * 2 + bi, comp, cw, ch, 250)
+    ba = np.array(blks, dtype=np.int32)
+    got = np.zeros(int((ba[:, 2] * ba[:, 3]).sum()), np.int16)
+    rc = ref_lib.ref_mc_blocks(comp, B.ptr(padded), padded.shape[1], W, H, M, len(blks), C.c_void_p(ba.ctypes.data), bi, 10,
+                               alt, B.ptr(got))
+    assert rc == 0
+    want = oracle_mc(oracle_lib, comp, padded, M, blks, bi, 10, alt)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.ref
+def test_mc_block_8bit(oracle_lib, ref_lib):
+    from tests.helpers import mc_cases, oracle_mc
+    W, H, M = 128, 64, 96
+    rng = np.random.default_rng(5)
+    padded = np.ascontiguousarray(np.pad(rng.integers(0, 256, (H, W), dtype=np.int16), M, mode="edge"))
+    blks = mc_cases(6, 0, W, H, 120, sizes=[4, 8, 16, 32])
+    ba = np.array(blks, dtype=np.int32)
+    for bi in (0, 1):
+        got = np.zeros(int((ba[:, 2] * ba[:, 3]).sum()), np.int16)
+        assert ref_lib.ref_mc_blocks(0, B.ptr(padded), padded.shape[1], W, H, M, len(blks), C.c_void_p(ba.ctypes.data), bi, 8, 0,
+                                     B.ptr(got)) == 0
+        assert np.array_equal(got, oracle_mc(oracle_lib, 0, padded, M, blks, bi, 8, 0))
+
+
+@pytest.mark.ref
+def test_add_avg_and_remove_high_freq(oracle_lib, ref_lib):
+    rng = np.random.default_rng(9)
+    for bd in (8, 10):
+        for w, h in [(4, 4), (8, 16), (12, 8), (64, 64), (2, 8)]:
+            # 14-bit intermediates of two bi predictions
+            s0 = rng.integers(-8192, 8192, (h, w), dtype=np.int16)
+            s1 = rng.integers(-8192, 8192, (h, w), dtype=np.int16)
+            a = np.zeros((h, w), np.int16)
+            b = np.zeros((h, w), np.int16)
+            ref_lib.ref_add_avg(B.ptr(s0), B.ptr(s1), B.ptr(a), w, h, bd)
+            oracle_lib.vo_add_avg(B.ptr(s0), B.ptr(s1), B.ptr(b), w * h, bd)
+            assert np.array_equal(a, b), (bd, w, h)
+            if w % 4:
+                continue   # removeHighFreq's unclipped branch exists for widths that are multiples of 4 only (Buffer.h:486-491)
+            for clip in (0, 1):
+                org = rng.integers(0, 1 << bd, (h, w), dtype=np.int16)
+                pred = rng.integers(0, 1 << bd, (h, w), dtype=np.int16)
+                a, b = org.copy(), org.copy()
+                ref_lib.ref_remove_high_freq(B.ptr(a), w, B.ptr(pred), w, w, h, clip, bd)
+                oracle_lib.vo_remove_high_freq(B.ptr(b), B.ptr(pred), w * h, clip, bd)
+                assert np.array_equal(a, b), (bd, w, h, clip)

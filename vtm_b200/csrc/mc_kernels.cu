@@ -1,0 +1,230 @@
+// Motion compensation of a batch of blocks and the two element-wise helpers of bi-prediction.
+//
+//   InterPrediction::xPredInterBlk   CommonLib/InterPrediction.cpp:660-830 (plain path: no RPR, wrap-around, BDOF padding,
+//                                    DMVR or bilinear filters)
+//   AreaBuf<Pel>::addAvg             CommonLib/Buffer.cpp:467-507
+//   AreaBuf<T>::removeHighFreq       CommonLib/Buffer.h:474-517
+//
+// HBM/L2-bound work: a block is cut into tiles of at most 16x16 outputs, one warp per tile.  The warp stages the tile's
+// reference patch (with the tap halo the fractional phases need) in shared memory with row-major loads, runs the
+// horizontal pass into a 14-bit intermediate plane and the vertical pass out of it, and writes the prediction rows.
+// Warps are independent (__syncwarp only), so ragged batches of mixed block sizes keep every warp busy.
+#include "me_kernels.h"
+
+namespace vtmme {
+namespace {
+
+constexpr int kMcWarps    = 8;
+constexpr int kTile       = 16;
+constexpr int kPatchRows  = kTile + 7;
+constexpr int kPatchPitch = kTile + 8;   // 24 int16 = 12 words: rows of a column walk hit distinct banks pairwise
+
+// rounding of one filter stage, InterpolationFilter::filter<> (InterpolationFilter.cpp:578-603)
+__device__ __forceinline__ void stage_rounding(bool isFirst, bool isLast, int hr, int& shift, int& offset)
+{
+  shift = 6;
+  if (isLast)
+  {
+    shift += isFirst ? 0 : hr;
+    offset = 1 << (shift - 1);
+    offset += isFirst ? 0 : (8192 << 6);
+  }
+  else
+  {
+    shift -= isFirst ? hr : 0;
+    offset = isFirst ? -(8192 << shift) : 0;
+  }
+}
+
+template <int TAPS>
+__device__ __forceinline__ void load_coeff(int (&c)[TAPS], int frac, bool q4, bool alt)
+{
+  if (TAPS == 8)
+  {
+    // coefficient choice of filterHor / filterVer (InterpolationFilter.cpp:782-794, 865-877)
+    const int16_t* t = (frac == 8 && alt) ? c_lumaAltHpel : (q4 ? c_lumaFilter4x4[frac] : c_lumaFilter[frac]);
+#pragma unroll
+    for (int k = 0; k < TAPS; k++) c[k] = t[k];
+  }
+  else
+  {
+#pragma unroll
+    for (int k = 0; k < TAPS; k++) c[k] = c_chromaFilter[frac][k];
+  }
+}
+
+template <int TAPS>
+__global__ void __launch_bounds__(kMcWarps * 32) mc_batch_kernel(const McTile* __restrict__ tiles, int nTiles, int bi,
+                                                                  int bitDepth, int alt)
+{
+  __shared__ int16_t s_patch[kMcWarps][kPatchRows * kPatchPitch];
+  __shared__ int16_t s_mid[kMcWarps][kPatchRows * kTile];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int idx  = blockIdx.x * kMcWarps + warp;
+  if (idx >= nTiles) return;
+  const McTile t = tiles[idx];
+  constexpr int above = TAPS / 2 - 1, halo = TAPS - 1;
+  const bool px = t.xFrac != 0, py = t.yFrac != 0;
+  const int  tw = t.tw, th = t.th;
+  const int  c0 = px ? -above : 0, pw = tw + (px ? halo : 0);
+  const int  r0 = py ? -above : 0, ph = th + (py ? halo : 0);
+  int16_t*   patch = s_patch[warp];
+  int16_t*   mid   = s_mid[warp];
+
+  for (int i = lane; i < pw * ph; i += 32)
+  {
+    const int r = i / pw, c = i - r * pw;
+    patch[r * kPatchPitch + c] = t.src[(ptrdiff_t) (r0 + r) * t.srcStride + c0 + c];
+  }
+  __syncwarp();
+
+  const int  hr   = max(2, 14 - bitDepth);
+  const int  maxv = (1 << bitDepth) - 1;
+  const bool rnd  = !bi;   // rndRes (InterPrediction.cpp:673)
+  const int  outs = tw * th;
+  int16_t*   dst  = t.dst;
+
+  if (!px && !py)
+  {
+    // filterCopy<true, rnd> (InterpolationFilter.cpp:397-470)
+    for (int o = lane; o < outs; o += 32)
+    {
+      const int y = o / tw, x = o - y * tw;
+      const int v = patch[y * kPatchPitch + x];
+      dst[(size_t) y * t.dstStride + x] = rnd ? (int16_t) v : (int16_t) ((int16_t) (v << hr) - (int16_t) 8192);
+    }
+    return;
+  }
+  int shift, offset;
+  if (px)
+  {
+    int cf[TAPS];
+    load_coeff<TAPS>(cf, t.xFrac, t.q4Hor != 0, alt != 0);
+    const bool last = rnd && !py;
+    stage_rounding(true, last, hr, shift, offset);
+    const int n = tw * ph;   // with a vertical pass to follow: every staged row
+    for (int o = lane; o < n; o += 32)
+    {
+      const int      y = o / tw, x = o - y * tw;
+      const int16_t* sp = patch + y * kPatchPitch + x;
+      int            sum = 0;
+#pragma unroll
+      for (int k = 0; k < TAPS; k++) sum += (int) sp[k] * cf[k];
+      int v = (int16_t) ((sum + offset) >> shift);
+      if (!py)
+      {
+        if (last) v = min(max(v, 0), maxv);
+        dst[(size_t) y * t.dstStride + x] = (int16_t) v;
+      }
+      else
+        mid[y * kTile + x] = (int16_t) v;
+    }
+    if (!py) return;
+    __syncwarp();
+  }
+  {
+    int cf[TAPS];
+    load_coeff<TAPS>(cf, t.yFrac, t.q4Ver != 0, alt != 0);
+    stage_rounding(!px, rnd, hr, shift, offset);
+    const int16_t* plane = px ? mid : patch;
+    const int      pitch = px ? kTile : kPatchPitch;
+    for (int o = lane; o < outs; o += 32)
+    {
+      const int      y = o / tw, x = o - y * tw;
+      const int16_t* sp = plane + y * pitch + x;
+      int            sum = 0;
+#pragma unroll
+      for (int k = 0; k < TAPS; k++) sum += (int) sp[k * pitch] * cf[k];
+      int v = (int16_t) ((sum + offset) >> shift);
+      if (rnd) v = min(max(v, 0), maxv);
+      dst[(size_t) y * t.dstStride + x] = (int16_t) v;
+    }
+  }
+}
+
+// addAvg: (a + b + offset) >> shift, clipped — the default bi-prediction average of two 14-bit predictions
+__global__ void __launch_bounds__(256) add_avg_kernel(const int16_t* __restrict__ a, const int16_t* __restrict__ b,
+                                                      int16_t* __restrict__ d, long long n, int shift, int offset, int maxv)
+{
+  const long long stride = (long long) gridDim.x * blockDim.x;
+  for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    const int v = ((int) a[i] + (int) b[i] + offset) >> shift;
+    d[i]        = (int16_t) min(max(v, 0), maxv);
+  }
+}
+
+// the same on 8 samples per thread (16-byte accesses) for aligned buffers
+__global__ void __launch_bounds__(256) add_avg_vec_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
+                                                          uint4* __restrict__ d, long long nVec, int shift, int offset, int maxv)
+{
+  const long long stride = (long long) gridDim.x * blockDim.x;
+  for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < nVec; i += stride)
+  {
+    const uint4 va = a[i], vb = b[i];
+    const uint32_t wa[4] = { va.x, va.y, va.z, va.w }, wb[4] = { vb.x, vb.y, vb.z, vb.w };
+    uint32_t       wd[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+    {
+      const int lo = ((int) (int16_t) (wa[k] & 0xffffu) + (int) (int16_t) (wb[k] & 0xffffu) + offset) >> shift;
+      const int hi = ((int) (int16_t) (wa[k] >> 16) + (int) (int16_t) (wb[k] >> 16) + offset) >> shift;
+      wd[k] = (uint32_t) min(max(lo, 0), maxv) | ((uint32_t) min(max(hi, 0), maxv) << 16);
+    }
+    d[i] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+  }
+}
+
+// removeHighFreq: dst = 2*dst - src (optionally clipped): the search target of the second bi-prediction direction
+__global__ void __launch_bounds__(256) remove_high_freq_kernel(int16_t* __restrict__ d, const int16_t* __restrict__ s,
+                                                               long long n, int clip, int maxv)
+{
+  const long long stride = (long long) gridDim.x * blockDim.x;
+  for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    int v = 2 * (int) d[i] - (int) s[i];
+    if (clip) v = min(max(v, 0), maxv);
+    d[i] = (int16_t) v;
+  }
+}
+
+int elementwise_grid(long long n)
+{
+  long long g = (n + 255) / 256;
+  return (int) (g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g));
+}
+
+}   // namespace
+
+cudaError_t launch_mc_batch(int comp, const McTile* dTiles, int nTiles, int bi, int bitDepth, int useAltHpel, cudaStream_t st)
+{
+  const int grid = (nTiles + kMcWarps - 1) / kMcWarps;
+  if (comp == 0)
+    mc_batch_kernel<8><<<grid, kMcWarps * 32, 0, st>>>(dTiles, nTiles, bi, bitDepth, useAltHpel);
+  else
+    mc_batch_kernel<4><<<grid, kMcWarps * 32, 0, st>>>(dTiles, nTiles, bi, bitDepth, 0);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_add_avg(const int16_t* a, const int16_t* b, int16_t* d, long long n, int bitDepth, cudaStream_t st)
+{
+  const int hr = 14 - bitDepth > 2 ? 14 - bitDepth : 2, shift = hr + 1, offset = (1 << (shift - 1)) + 2 * 8192;
+  const int maxv = (1 << bitDepth) - 1;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(d)) & 15) == 0;
+  const long long nVec = aligned ? n / 8 : 0;
+  if (nVec)
+    add_avg_vec_kernel<<<elementwise_grid(nVec), 256, 0, st>>>(reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b),
+                                                               reinterpret_cast<uint4*>(d), nVec, shift, offset, maxv);
+  if (n - nVec * 8)
+    add_avg_kernel<<<elementwise_grid(n - nVec * 8), 256, 0, st>>>(a + nVec * 8, b + nVec * 8, d + nVec * 8, n - nVec * 8, shift,
+                                                                    offset, maxv);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_remove_high_freq(int16_t* d, const int16_t* s, long long n, int clip, int bitDepth, cudaStream_t st)
+{
+  remove_high_freq_kernel<<<elementwise_grid(n), 256, 0, st>>>(d, s, n, clip, (1 << bitDepth) - 1);
+  return cudaGetLastError();
+}
+
+}   // namespace vtmme

@@ -115,4 +115,19 @@ cudaError_t launch_filter_batch(int taps, int vertical, int isFirst, int isLast,
                                 const int16_t* coeff, int bitDepth, int n, cudaStream_t st);
 cudaError_t launch_extend_border(DevPic pic, cudaStream_t st);
 
+// Motion compensation (mc_kernels.cu): a block is cut into tiles of at most 16x16 outputs, one warp each
+struct McTile
+{
+  const int16_t* src;          // reference plane at the tile's integer position (block position + (mv >> shift))
+  int16_t*       dst;
+  int            srcStride, dstStride;
+  uint8_t        tw, th;       // 1..16
+  uint8_t        xFrac, yFrac; // 1/16 (luma) or 1/32 (chroma) phase
+  uint8_t        q4Hor, q4Ver; // the 4x4 coefficient table applies to the horizontal / vertical pass
+  uint8_t        pad[2];
+};
+cudaError_t launch_mc_batch(int comp, const McTile* dTiles, int nTiles, int bi, int bitDepth, int useAltHpel, cudaStream_t st);
+cudaError_t launch_add_avg(const int16_t* a, const int16_t* b, int16_t* d, long long n, int bitDepth, cudaStream_t st);
+cudaError_t launch_remove_high_freq(int16_t* d, const int16_t* s, long long n, int clip, int bitDepth, cudaStream_t st);
+
 }   // namespace vtmme

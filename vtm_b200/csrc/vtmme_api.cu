@@ -54,6 +54,11 @@ struct vtmme_ctx
   uint32_t*      dJobFracAcc = nullptr;     // persistent, all-zero between calls (18 sums per job slot)
   size_t         jobFracAccCap = 0;
   unsigned char* dPinnedAlias = nullptr;    // device address of hPinned (mapped, zero-copy result write-back)
+  unsigned char* dMcTiles = nullptr;        // tile descriptors of vtmme_mc_batch / vtmme_mc_host
+  size_t         mcTilesCap = 0;
+  unsigned char* hMcTiles = nullptr;        // their own pinned staging block (vtmme_mc_batch returns before the upload ends)
+  size_t         hMcTilesCap = 0;
+  cudaEvent_t    mcUploaded = nullptr;      // recorded after the tile upload: the next call waits before re-filling
 
   bool        profiling = false;
   cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
@@ -227,6 +232,9 @@ void vtmme_destroy(vtmme_ctx* ctx)
   cudaFree(ctx->dRes);
   cudaFree(ctx->dFracAcc);
   cudaFree(ctx->dJobBuf);
+  cudaFree(ctx->dMcTiles);
+  if (ctx->hMcTiles) cudaFreeHost(ctx->hMcTiles);
+  if (ctx->mcUploaded) cudaEventDestroy(ctx->mcUploaded);
   cudaFree(ctx->dJobSurf);
   cudaFree(ctx->dJobKeys);
   cudaFree(ctx->dJobFracAcc);
@@ -755,5 +763,159 @@ extern "C" int vtmme_filter_host(vtmme_ctx* ctx, int nTaps, int vertical, int is
   VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   const int16_t* hd = reinterpret_cast<int16_t*>(ctx->hPinned + srcBytes);
   for (int y = 0; y < h; y++) memcpy(dst + (size_t) y * dstStride, hd + (size_t) y * w, (size_t) w * 2);
+  return VTMME_OK;
+}
+
+// ---- motion compensation -------------------------------------------------------------------------------------------
+// Validates the blocks, cuts them into <=16x16 tiles in the pinned staging block, uploads the tiles to *dTiles (device
+// scratch) and launches the kernel writing to dDst (block i packed at the running sum of w*h).
+static int mc_launch(vtmme_ctx* ctx, const char* who, int comp, int bi, int bitDepth, int useAltHpel, int n,
+                     const vtmme_mc_block* blocks, int nTiles, int16_t* dDst)
+{
+  const size_t tileBytes = align256((size_t) nTiles * sizeof(McTile));
+  int rc;
+  if (!ctx->mcUploaded) VTMME_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&ctx->mcUploaded, cudaEventDisableTiming));
+  else VTMME_CUDA_CHECK(ctx, cudaEventSynchronize(ctx->mcUploaded));
+  if (tileBytes > ctx->hMcTilesCap)
+  {
+    if (ctx->hMcTiles) cudaFreeHost(ctx->hMcTiles);
+    ctx->hMcTiles    = nullptr;
+    ctx->hMcTilesCap = 0;
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, tileBytes, cudaHostAllocDefault) != cudaSuccess)
+    {
+      cudaGetLastError();
+      return vtmme_set_error(ctx, VTMME_ERR_NOMEM, "cudaHostAlloc", "out of pinned host memory");
+    }
+    ctx->hMcTiles    = reinterpret_cast<unsigned char*>(p);
+    ctx->hMcTilesCap = tileBytes;
+  }
+  if (tileBytes > ctx->mcTilesCap)
+  {
+    // the previous launch may still read the old descriptor buffer
+    VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((rc = ensure(ctx, ctx->dMcTiles, ctx->mcTilesCap, tileBytes)) != VTMME_OK) return rc;
+  }
+  const int shift = 4 + (comp ? 1 : 0), taps = comp ? 4 : 8, before = taps / 2 - 1, after = taps / 2;
+  McTile* ht = reinterpret_cast<McTile*>(ctx->hMcTiles);
+  int     k = 0;
+  size_t  off = 0;
+  for (int i = 0; i < n; i++)
+  {
+    const vtmme_mc_block& b = blocks[i];
+    const DevPic& rp = ctx->pics[b.refPic];
+    int wrc;
+    if ((wrc = wait_picture(ctx, b.refPic)) != VTMME_OK) return wrc;
+    const int ix = b.mvX >> shift, iy = b.mvY >> shift, xFrac = b.mvX & ((1 << shift) - 1), yFrac = b.mvY & ((1 << shift) - 1);
+    if (b.x + ix - before < -rp.margin || b.x + b.w + ix + after > rp.width + rp.margin ||
+        b.y + iy - before < -rp.margin || b.y + b.h + iy + after > rp.height + rp.margin)
+      return vtmme_set_error(ctx, VTMME_ERR_RANGE, who, "block + MV leaves the padded reference plane (clip the MV first)");
+    // 4x4 coefficient table: keyed on the (w,h) the reference hands each pass; the horizontal pass of the two-stage
+    // case runs over h + taps - 1 rows (InterpolationFilter.cpp:786, 869; InterPrediction.cpp:763)
+    const int  hHor  = yFrac ? b.h + taps - 1 : b.h;
+    const bool q4Hor = comp == 0 && b.w == 4 && (hHor == 4 || hHor == 11), q4Ver = comp == 0 && b.w == 4 && b.h == 4;
+    const int16_t* src = rp.origin + (ptrdiff_t) (b.y + iy) * rp.stride + b.x + ix;
+    for (int ty = 0; ty < b.h; ty += 16)
+      for (int tx = 0; tx < b.w; tx += 16)
+      {
+        McTile& t = ht[k++];
+        t.src = src + (ptrdiff_t) ty * rp.stride + tx;
+        t.dst = dDst + off + (size_t) ty * b.w + tx;
+        t.srcStride = rp.stride;
+        t.dstStride = b.w;
+        t.tw = (uint8_t) (b.w - tx < 16 ? b.w - tx : 16);
+        t.th = (uint8_t) (b.h - ty < 16 ? b.h - ty : 16);
+        t.xFrac = (uint8_t) xFrac;
+        t.yFrac = (uint8_t) yFrac;
+        t.q4Hor = q4Hor;
+        t.q4Ver = q4Ver;
+        t.pad[0] = t.pad[1] = 0;
+      }
+    off += (size_t) b.w * b.h;
+  }
+  if (k != nTiles) return vtmme_set_error(ctx, VTMME_ERR_ARG, who, "internal: tile count");
+  McTile* dTiles = reinterpret_cast<McTile*>(ctx->dMcTiles);
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(dTiles, ht, (size_t) nTiles * sizeof(McTile), cudaMemcpyHostToDevice, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, cudaEventRecord(ctx->mcUploaded, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, launch_mc_batch(comp, dTiles, nTiles, bi, bitDepth, useAltHpel, ctx->stream));
+  ctx->launches += 1;
+  return VTMME_OK;
+}
+
+// shared argument check; returns the tile count and the packed output size
+static int mc_check(vtmme_ctx* ctx, const char* who, int comp, int bitDepth, int n, const vtmme_mc_block* blocks, const void* dst,
+                    int* nTiles, size_t* outElems)
+{
+  if (!blocks || !dst || n <= 0 || (comp != 0 && comp != 1) || bitDepth < 8 || bitDepth > 10)
+    return vtmme_set_error(ctx, VTMME_ERR_ARG, who, "bad argument");
+  long long tiles = 0;
+  size_t    elems = 0;
+  for (int i = 0; i < n; i++)
+  {
+    const vtmme_mc_block& b = blocks[i];
+    if (b.w < 1 || b.h < 1 || b.w > 128 || b.h > 128) return vtmme_set_error(ctx, VTMME_ERR_ARG, who, "w,h must be in [1,128]");
+    if (ctx->pics.find(b.refPic) == ctx->pics.end()) return vtmme_set_error(ctx, VTMME_ERR_NOPIC, who, "unknown picture id");
+    tiles += (long long) ((b.w + 15) / 16) * ((b.h + 15) / 16);
+    elems += (size_t) b.w * b.h;
+  }
+  if (tiles > (1 << 24)) return vtmme_set_error(ctx, VTMME_ERR_ARG, who, "too many blocks in one call");
+  *nTiles   = (int) tiles;
+  *outElems = elems;
+  return VTMME_OK;
+}
+
+extern "C" int vtmme_mc_batch(vtmme_ctx* ctx, int comp, int bi, int bitDepth, int useAltHpel, int n,
+                              const vtmme_mc_block* blocks, int16_t* dDst)
+{
+  if (!ctx) return VTMME_ERR_ARG;
+  int    nTiles = 0, rc;
+  size_t elems = 0;
+  if ((rc = mc_check(ctx, "vtmme_mc_batch", comp, bitDepth, n, blocks, dDst, &nTiles, &elems)) != VTMME_OK) return rc;
+  VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  return mc_launch(ctx, "vtmme_mc_batch", comp, bi, bitDepth, useAltHpel, n, blocks, nTiles, dDst);
+}
+
+extern "C" int vtmme_mc_host(vtmme_ctx* ctx, int comp, int bi, int bitDepth, int useAltHpel, int n,
+                             const vtmme_mc_block* blocks, int16_t* dst)
+{
+  if (!ctx) return VTMME_ERR_ARG;
+  int    nTiles = 0, rc;
+  size_t elems = 0;
+  if ((rc = mc_check(ctx, "vtmme_mc_host", comp, bitDepth, n, blocks, dst, &nTiles, &elems)) != VTMME_OK) return rc;
+  VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));   // scratch below is shared with the other synchronous calls
+  const size_t outBytes = align256(elems * 2);
+  if ((rc = ensure_pinned(ctx, outBytes)) != VTMME_OK) return rc;
+  if ((rc = ensure(ctx, ctx->dJobBuf, ctx->jobBufCap, outBytes)) != VTMME_OK) return rc;
+  if ((rc = mc_launch(ctx, "vtmme_mc_host", comp, bi, bitDepth, useAltHpel, n, blocks, nTiles,
+                      reinterpret_cast<int16_t*>(ctx->dJobBuf))) != VTMME_OK)
+    return rc;
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->hPinned, ctx->dJobBuf, elems * 2, cudaMemcpyDeviceToHost, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(dst, ctx->hPinned, elems * 2);
+  return VTMME_OK;
+}
+
+extern "C" int vtmme_add_avg(vtmme_ctx* ctx, const int16_t* dSrc0, const int16_t* dSrc1, int16_t* dDst, int64_t count,
+                             int bitDepth)
+{
+  if (!ctx) return VTMME_ERR_ARG;
+  if (!dSrc0 || !dSrc1 || !dDst || count <= 0 || bitDepth < 8 || bitDepth > 10)
+    return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_add_avg", "bad argument");
+  VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  VTMME_CUDA_CHECK(ctx, launch_add_avg(dSrc0, dSrc1, dDst, count, bitDepth, ctx->stream));
+  ctx->launches += 1;
+  return VTMME_OK;
+}
+
+extern "C" int vtmme_remove_high_freq(vtmme_ctx* ctx, int16_t* dOrg, const int16_t* dPred, int64_t count, int clip,
+                                      int bitDepth)
+{
+  if (!ctx) return VTMME_ERR_ARG;
+  if (!dOrg || !dPred || count <= 0 || bitDepth < 8 || bitDepth > 10)
+    return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_remove_high_freq", "bad argument");
+  VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  VTMME_CUDA_CHECK(ctx, launch_remove_high_freq(dOrg, dPred, count, clip, bitDepth, ctx->stream));
+  ctx->launches += 1;
   return VTMME_OK;
 }

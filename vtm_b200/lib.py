@@ -18,7 +18,8 @@ ERR_NAMES = {0: "VTMME_OK", -1: "VTMME_ERR_CUDA", -2: "VTMME_ERR_ARG", -3: "VTMM
 SYMBOLS = ["vtmme_create", "vtmme_destroy", "vtmme_last_error", "vtmme_set_stream", "vtmme_synchronize",
            "vtmme_launch_count", "vtmme_set_profiling", "vtmme_frame_kernel_ms", "vtmme_upload_picture", "vtmme_upload_picture_async", "vtmme_upload_picture_device", "vtmme_release_picture",
            "vtmme_search", "vtmme_frame_cu_count", "vtmme_search_frames", "vtmme_search_frames_device",
-           "vtmme_dist_batch", "vtmme_dist_host", "vtmme_interp_batch", "vtmme_interp_host", "vtmme_filter_host", "vtmme_int_peak"]
+           "vtmme_dist_batch", "vtmme_dist_host", "vtmme_interp_batch", "vtmme_interp_host", "vtmme_filter_host",
+           "vtmme_mc_batch", "vtmme_mc_host", "vtmme_add_avg", "vtmme_remove_high_freq", "vtmme_int_peak"]
 
 
 class CJob(C.Structure):
@@ -46,6 +47,12 @@ class CFrameParams(C.Structure):
     _fields_ = [("searchRange", C.c_int32), ("bitDepth", C.c_int32), ("ctuSize", C.c_int32), ("imvShift", C.c_int32),
                 ("useHad", C.c_int32), ("fracMode", C.c_int32), ("predSpread", C.c_int32), ("subShiftMode", C.c_int32),
                 ("lambdaMotion", C.c_double)]
+
+
+class CMcBlock(C.Structure):
+    """vtmme_mc_block"""
+    _fields_ = [("refPic", C.c_int32), ("x", C.c_int32), ("y", C.c_int32), ("w", C.c_int32), ("h", C.c_int32),
+                ("mvX", C.c_int32), ("mvY", C.c_int32), ("reserved", C.c_int32)]
 
 
 def library_path():
@@ -95,6 +102,10 @@ def load_library():
     L.vtmme_interp_batch.argtypes = [P, I, I, P, I, I64, P, I, I64, I, I, I, I, I, I, I, I]
     L.vtmme_interp_host.argtypes = [P, I, I, P, I, P, I, I, I, I, I, I, I, I]
     L.vtmme_filter_host.argtypes = [P, I, I, I, I, I, P, I, P, I, I, I, P, I]
+    L.vtmme_mc_batch.argtypes = [P, I, I, I, I, I, C.POINTER(CMcBlock), P]
+    L.vtmme_mc_host.argtypes = [P, I, I, I, I, I, C.POINTER(CMcBlock), P]
+    L.vtmme_add_avg.argtypes = [P, P, P, P, I64, I]
+    L.vtmme_remove_high_freq.argtypes = [P, P, P, I64, I, I]
     L.vtmme_int_peak.argtypes = [I, I, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _lib = L
     return L

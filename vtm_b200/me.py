@@ -9,7 +9,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .lib import CFrameParams, CJob, CResult, ERR_NAMES, VtmmeError, load_library
+from .lib import CFrameParams, CJob, CMcBlock, CResult, ERR_NAMES, VtmmeError, load_library
 
 # vtmme_cu_result
 CU_RESULT_DTYPE = np.dtype([("mvQx", "<i2"), ("mvQy", "<i2"), ("intX", "<i2"), ("intY", "<i2"),
@@ -230,3 +230,36 @@ class MotionSearch:
         self._check(self.L.vtmme_interp_batch(self.ctx, comp, vertical, C.c_void_p(d_src), src_stride, src_blk,
                                               C.c_void_p(d_dst), dst_stride, dst_blk, w, h, frac, is_first, is_last,
                                               bit_depth, use_alt_hpel, n), "vtmme_interp_batch")
+
+    # ---- motion compensation -------------------------------------------------------------------------------
+    @staticmethod
+    def _mc_blocks(blocks):
+        """blocks: iterable of (refPic, x, y, w, h, mvX, mvY); mv in 1/16 luma sample."""
+        arr = (CMcBlock * len(blocks))()
+        total = 0
+        for i, b in enumerate(blocks):
+            arr[i] = CMcBlock(int(b[0]), int(b[1]), int(b[2]), int(b[3]), int(b[4]), int(b[5]), int(b[6]), 0)
+            total += int(b[3]) * int(b[4])
+        return arr, total
+
+    def mc_host(self, comp, blocks, bi=0, bit_depth=10, use_alt_hpel=0):
+        """xPredInterBlk for every block; returns the packed int16 predictions (block i at the sum of earlier w*h)."""
+        arr, total = self._mc_blocks(blocks)
+        dst = np.zeros(total, np.int16)
+        self._check(self.L.vtmme_mc_host(self.ctx, comp, bi, bit_depth, use_alt_hpel, len(blocks), arr,
+                                         C.c_void_p(dst.ctypes.data)), "vtmme_mc_host")
+        return dst
+
+    def mc_batch(self, comp, blocks, d_dst, bi=0, bit_depth=10, use_alt_hpel=0):
+        """Same, into device memory at d_dst, asynchronous on the context stream."""
+        arr, _ = self._mc_blocks(blocks) if not isinstance(blocks, C.Array) else (blocks, 0)
+        self._check(self.L.vtmme_mc_batch(self.ctx, comp, bi, bit_depth, use_alt_hpel, len(arr), arr, C.c_void_p(d_dst)),
+                    "vtmme_mc_batch")
+
+    def add_avg(self, d_src0, d_src1, d_dst, count, bit_depth=10):
+        self._check(self.L.vtmme_add_avg(self.ctx, C.c_void_p(d_src0), C.c_void_p(d_src1), C.c_void_p(d_dst), count,
+                                         bit_depth), "vtmme_add_avg")
+
+    def remove_high_freq(self, d_org, d_pred, count, clip=0, bit_depth=10):
+        self._check(self.L.vtmme_remove_high_freq(self.ctx, C.c_void_p(d_org), C.c_void_p(d_pred), count, clip, bit_depth),
+                    "vtmme_remove_high_freq")
