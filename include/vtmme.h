@@ -205,6 +205,28 @@ int vtmme_add_avg(vtmme_ctx* ctx, const int16_t* dSrc0, const int16_t* dSrc1, in
  * direction's prediction (InterSearch.cpp:3317-3325).  DEVICE pointers, asynchronous. */
 int vtmme_remove_high_freq(vtmme_ctx* ctx, int16_t* dOrg, const int16_t* dPred, int64_t count, int clip, int bitDepth);
 
+/* ---- candidate distortion (the step BEFORE the search: AMVP template cost and ME seeds) ----------
+ * For one PU and a list of candidate MVs: SAD(org, xPredInterBlk(ref, mv)) per candidate, without
+ * materialising the predictions.  With fractional MVs and subShift 0 this is the distortion term of
+ * InterSearch::xGetTemplateCost (InterSearch.cpp:3235-3270, getDistPart DF_SAD); with integer MVs
+ * (multiples of 16) and the search's subShift it is the SAD of the predictor / history-MV seeds that
+ * choose the search-window centre (InterSearch.cpp:3388-3426).  The caller adds its own rate term
+ * (m_auiMVPIdxCost resp. getCostOfVectorWithPredictor) and keeps the first strict minimum.  MVs must be
+ * clipped already (clipMv).  out: HOST array, one uint64 per candidate in job order.  Synchronous. */
+typedef struct vtmme_cand_job
+{
+  int32_t        curPic;     /* picture holding the original block; ignored when org != NULL           */
+  int32_t        refPic;
+  int32_t        x, y, w, h; /* PU luma rectangle, w,h in [1,128]                                      */
+  const int16_t* org;        /* optional HOST pointer to the pattern (row stride orgStride)            */
+  int32_t        orgStride;
+  int32_t        nCand;      /* 1..64                                                                  */
+  const int32_t* mv;         /* HOST: nCand x {mvX, mvY}, 1/16 luma sample                             */
+  int32_t        subShift;   /* DistParam::subShift                                                    */
+  int32_t        reserved;   /* 0 */
+} vtmme_cand_job;
+int vtmme_cand_sad(vtmme_ctx* ctx, int bitDepth, int useAltHpel, int nJobs, const vtmme_cand_job* jobs, uint64_t* out);
+
 /* ---- measurement helpers ------------------------------------------------------------------------
  * Per-kernel timing of the frame path: when enabled, vtmme_search_frames[_device] brackets each of its
  * kernels with CUDA events on the context stream; vtmme_frame_kernel_ms returns the durations of the most

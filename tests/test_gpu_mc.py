@@ -123,3 +123,43 @@ def test_mc_errors(ms):
         ms.mc_host(0, [(66, 0, 0, 200, 16, 0, 0)])
     with pytest.raises(VtmmeError, match="VTMME_ERR_ARG"):
         ms.mc_host(2, [(66, 0, 0, 16, 16, 0, 0)])
+
+
+def test_cand_sad_matches_oracle(ms, oracle_lib):
+    """Template-cost / seed distortion: SAD(org, MC(ref, mv)) per candidate == vo_sad on vo_mc_block's output."""
+    from oracle import bindings as B
+    from vtm_b200.synth import make_pair
+    W, H, M = 256, 128, 192
+    cur, ref, _ = make_pair(21, W, H, max_global=6, max_local=8, n_rects=2, sigma=3.0)
+    refp = np.ascontiguousarray(np.pad(ref, M, mode="edge"))
+    ms.upload_picture(70, cur)
+    ms.upload_picture(71, refp, M)
+    rng = np.random.default_rng(22)
+    jobs, want = [], []
+    stride = refp.shape[1]
+    for i in range(120):
+        w, h = int(rng.choice([4, 8, 16, 32, 64, 128])), int(rng.choice([4, 8, 16, 32, 64, 128]))
+        x = int(rng.integers(0, (W - w) // w + 1)) * w
+        y = int(rng.integers(0, (H - h) // h + 1)) * h
+        ncand = int(rng.integers(1, 17))
+        mv = rng.integers(-30 * 16, 30 * 16, (ncand, 2)).astype(np.int32)
+        ss = 0
+        if i % 3 == 0:   # seeds: integer MVs with the search's row sub-sampling
+            mv &= ~15
+            ss = oracle_lib.vo_subshift(2, w, h)
+        host_org = None
+        if i % 4 == 1:   # bi-pred style pattern handed over from host memory
+            host_org = np.ascontiguousarray((2 * cur[y:y + h, x:x + w].astype(np.int32) - rng.integers(0, 1024, (h, w))).astype(np.int16))
+        jobs.append(dict(curPic=70, refPic=71, x=x, y=y, w=w, h=h, mv=mv, subShift=ss, org=host_org))
+        org = host_org if host_org is not None else np.ascontiguousarray(cur[y:y + h, x:x + w])
+        sads = []
+        for c in range(ncand):
+            pred = np.zeros((h, w), np.int16)
+            oracle_lib.vo_mc_block(0, B.ptr(refp, (M + y) * stride + M + x), stride, w, h, int(mv[c, 0]), int(mv[c, 1]), 0, 10, 0,
+                                   B.ptr(pred), w)
+            sads.append(int(oracle_lib.vo_sad(B.ptr(org), w, B.ptr(pred), w, w, h, ss)))
+        want.append(sads)
+    got = ms.cand_sad(jobs)
+    assert got == want
+    # one by one (different batch composition, same answers)
+    assert ms.cand_sad(jobs[:1]) == want[:1]

@@ -254,3 +254,23 @@ def test_add_avg_and_remove_high_freq(oracle_lib, ref_lib):
                 ref_lib.ref_remove_high_freq(B.ptr(a), w, B.ptr(pred), w, w, h, clip, bd)
                 oracle_lib.vo_remove_high_freq(B.ptr(b), B.ptr(pred), w * h, clip, bd)
                 assert np.array_equal(a, b), (bd, w, h, clip)
+
+
+@pytest.mark.ref
+def test_template_distortion_composition(oracle_lib, ref_lib):
+    """xGetTemplateCost's distortion (InterSearch.cpp:3252-3266): getDistPart(DF_SAD) on xPredInterBlk's output — the
+    reference's two functions chained against the oracle's two."""
+    W, H, M = 128, 64, 96
+    rng = np.random.default_rng(41)
+    padded = np.ascontiguousarray(np.pad(rng.integers(0, 1024, (H, W), dtype=np.int16), M, mode="edge"))
+    stride = padded.shape[1]
+    for w, h in [(8, 8), (16, 8), (4, 16), (32, 32), (64, 16), (128, 64)]:
+        org = rng.integers(0, 1024, (h, w), dtype=np.int16)
+        for rep in range(6):
+            mvx, mvy = (int(v) for v in rng.integers(-300, 300, 2))
+            blk = np.array([[0, 0, w, h, mvx, mvy]], dtype=np.int32)
+            rp = np.zeros((h, w), np.int16)
+            assert ref_lib.ref_mc_blocks(0, B.ptr(padded), stride, W, H, M, 1, C.c_void_p(blk.ctypes.data), 0, 10, 0, B.ptr(rp)) == 0
+            op = np.zeros((h, w), np.int16)
+            oracle_lib.vo_mc_block(0, B.ptr(padded, M * stride + M), stride, w, h, mvx, mvy, 0, 10, 0, B.ptr(op), w)
+            assert ref_lib.ref_dist(B.ptr(org), w, B.ptr(rp), w, w, h, 10, 0, 0) == oracle_lib.vo_sad(B.ptr(org), w, B.ptr(op), w, w, h, 0)

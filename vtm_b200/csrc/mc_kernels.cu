@@ -53,23 +53,16 @@ __device__ __forceinline__ void load_coeff(int (&c)[TAPS], int frac, bool q4, bo
   }
 }
 
-template <int TAPS>
-__global__ void __launch_bounds__(kMcWarps * 32) mc_batch_kernel(const McTile* __restrict__ tiles, int nTiles, int bi,
-                                                                  int bitDepth, int alt)
+// One tile by one warp.  sink(y, x, v) receives every prediction sample of the tile.
+template <int TAPS, class Sink>
+__device__ __forceinline__ void mc_tile(const McTile& t, int bi, int bitDepth, int alt, int16_t* patch, int16_t* mid, int lane,
+                                        Sink& sink)
 {
-  __shared__ int16_t s_patch[kMcWarps][kPatchRows * kPatchPitch];
-  __shared__ int16_t s_mid[kMcWarps][kPatchRows * kTile];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int idx  = blockIdx.x * kMcWarps + warp;
-  if (idx >= nTiles) return;
-  const McTile t = tiles[idx];
   constexpr int above = TAPS / 2 - 1, halo = TAPS - 1;
   const bool px = t.xFrac != 0, py = t.yFrac != 0;
   const int  tw = t.tw, th = t.th;
   const int  c0 = px ? -above : 0, pw = tw + (px ? halo : 0);
   const int  r0 = py ? -above : 0, ph = th + (py ? halo : 0);
-  int16_t*   patch = s_patch[warp];
-  int16_t*   mid   = s_mid[warp];
 
   for (int i = lane; i < pw * ph; i += 32)
   {
@@ -82,7 +75,6 @@ __global__ void __launch_bounds__(kMcWarps * 32) mc_batch_kernel(const McTile* _
   const int  maxv = (1 << bitDepth) - 1;
   const bool rnd  = !bi;   // rndRes (InterPrediction.cpp:673)
   const int  outs = tw * th;
-  int16_t*   dst  = t.dst;
 
   if (!px && !py)
   {
@@ -91,7 +83,7 @@ __global__ void __launch_bounds__(kMcWarps * 32) mc_batch_kernel(const McTile* _
     {
       const int y = o / tw, x = o - y * tw;
       const int v = patch[y * kPatchPitch + x];
-      dst[(size_t) y * t.dstStride + x] = rnd ? (int16_t) v : (int16_t) ((int16_t) (v << hr) - (int16_t) 8192);
+      sink(y, x, rnd ? v : (int) (int16_t) ((int16_t) (v << hr) - (int16_t) 8192));
     }
     return;
   }
@@ -114,7 +106,7 @@ __global__ void __launch_bounds__(kMcWarps * 32) mc_batch_kernel(const McTile* _
       if (!py)
       {
         if (last) v = min(max(v, 0), maxv);
-        dst[(size_t) y * t.dstStride + x] = (int16_t) v;
+        sink(y, x, v);
       }
       else
         mid[y * kTile + x] = (int16_t) v;
@@ -137,9 +129,61 @@ __global__ void __launch_bounds__(kMcWarps * 32) mc_batch_kernel(const McTile* _
       for (int k = 0; k < TAPS; k++) sum += (int) sp[k * pitch] * cf[k];
       int v = (int16_t) ((sum + offset) >> shift);
       if (rnd) v = min(max(v, 0), maxv);
-      dst[(size_t) y * t.dstStride + x] = (int16_t) v;
+      sink(y, x, v);
     }
   }
+}
+
+struct StoreSink
+{
+  int16_t* dst;
+  int      stride;
+  __device__ __forceinline__ void operator()(int y, int x, int v) const { dst[(size_t) y * stride + x] = (int16_t) v; }
+};
+
+template <int TAPS>
+__global__ void __launch_bounds__(kMcWarps * 32) mc_batch_kernel(const McTile* __restrict__ tiles, int nTiles, int bi,
+                                                                  int bitDepth, int alt)
+{
+  __shared__ int16_t s_patch[kMcWarps][kPatchRows * kPatchPitch];
+  __shared__ int16_t s_mid[kMcWarps][kPatchRows * kTile];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int idx  = blockIdx.x * kMcWarps + warp;
+  if (idx >= nTiles) return;   // warps are independent: no CTA-wide barrier below
+  const McTile t = tiles[idx];
+  StoreSink    sink{ t.dst, t.dstStride };
+  mc_tile<TAPS>(t, bi, bitDepth, alt, s_patch[warp], s_mid[warp], lane, sink);
+}
+
+// SAD of the original block against the motion-compensated prediction at a (fractional) candidate MV, without
+// materialising the prediction: RdCost::xGetSAD (RdCost.cpp:493-528) on xPredInterBlk's output — the distortion term of
+// InterSearch::xGetTemplateCost (InterSearch.cpp:3235-3270) and, for integer MVs, of the ME seeds (:3388-3426).
+struct SadSink
+{
+  const int16_t* org;
+  int            stride, rowMask;
+  uint32_t       acc;
+  __device__ __forceinline__ void operator()(int y, int x, int v)
+  {
+    if ((y & rowMask) == 0) acc += (uint32_t) abs((int) org[(size_t) y * stride + x] - v);
+  }
+};
+
+__global__ void __launch_bounds__(kMcWarps * 32) mc_sad_kernel(const McSadTile* __restrict__ tiles, int nTiles, int bitDepth,
+                                                                int alt, unsigned long long* __restrict__ out)
+{
+  __shared__ int16_t s_patch[kMcWarps][kPatchRows * kPatchPitch];
+  __shared__ int16_t s_mid[kMcWarps][kPatchRows * kTile];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int idx  = blockIdx.x * kMcWarps + warp;
+  if (idx >= nTiles) return;
+  const McSadTile t = tiles[idx];
+  SadSink         sink{ t.org, t.orgStride, (1 << t.subShift) - 1, 0u };
+  mc_tile<8>(t.mc, 0, bitDepth, alt, s_patch[warp], s_mid[warp], lane, sink);
+  uint32_t s = sink.acc;
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+  if (lane == 0) atomicAdd(out + t.outIdx, (unsigned long long) s << t.subShift);
 }
 
 // addAvg: (a + b + offset) >> shift, clipped — the default bi-prediction average of two 14-bit predictions
@@ -203,6 +247,13 @@ cudaError_t launch_mc_batch(int comp, const McTile* dTiles, int nTiles, int bi, 
     mc_batch_kernel<8><<<grid, kMcWarps * 32, 0, st>>>(dTiles, nTiles, bi, bitDepth, useAltHpel);
   else
     mc_batch_kernel<4><<<grid, kMcWarps * 32, 0, st>>>(dTiles, nTiles, bi, bitDepth, 0);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mc_sad(const McSadTile* dTiles, int nTiles, int bitDepth, int useAltHpel, unsigned long long* dOut,
+                          cudaStream_t st)
+{
+  mc_sad_kernel<<<(nTiles + kMcWarps - 1) / kMcWarps, kMcWarps * 32, 0, st>>>(dTiles, nTiles, bitDepth, useAltHpel, dOut);
   return cudaGetLastError();
 }
 

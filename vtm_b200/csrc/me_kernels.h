@@ -126,6 +126,18 @@ struct McTile
   uint8_t        q4Hor, q4Ver; // the 4x4 coefficient table applies to the horizontal / vertical pass
   uint8_t        pad[2];
 };
+// the same tile with the original block it is compared against (candidate SAD, mc_sad_kernel)
+struct McSadTile
+{
+  McTile         mc;          // mc.dst unused
+  const int16_t* org;         // original block at the tile position
+  int            orgStride;
+  int            outIdx;      // candidate slot the tile's partial SAD is added to
+  int            subShift;    // rows with (row & ((1 << subShift) - 1)) == 0 are summed, the sum is shifted back up
+  int            pad;
+};
+cudaError_t launch_mc_sad(const McSadTile* dTiles, int nTiles, int bitDepth, int useAltHpel, unsigned long long* dOut,
+                          cudaStream_t st);
 cudaError_t launch_mc_batch(int comp, const McTile* dTiles, int nTiles, int bi, int bitDepth, int useAltHpel, cudaStream_t st);
 cudaError_t launch_add_avg(const int16_t* a, const int16_t* b, int16_t* d, long long n, int bitDepth, cudaStream_t st);
 cudaError_t launch_remove_high_freq(int16_t* d, const int16_t* s, long long n, int clip, int bitDepth, cudaStream_t st);

@@ -919,3 +919,104 @@ extern "C" int vtmme_remove_high_freq(vtmme_ctx* ctx, int16_t* dOrg, const int16
   ctx->launches += 1;
   return VTMME_OK;
 }
+
+// ---- candidate distortion (template cost / seeds) -------------------------------------------------------------------
+extern "C" int vtmme_cand_sad(vtmme_ctx* ctx, int bitDepth, int useAltHpel, int nJobs, const vtmme_cand_job* jobs, uint64_t* out)
+{
+  if (!ctx) return VTMME_ERR_ARG;
+  const char* who = "vtmme_cand_sad";
+  if (!jobs || !out || nJobs <= 0 || bitDepth < 8 || bitDepth > 10) return vtmme_set_error(ctx, VTMME_ERR_ARG, who, "bad argument");
+  VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  size_t    orgBytes = 0;
+  long long nTiles = 0, nCand = 0;
+  for (int i = 0; i < nJobs; i++)
+  {
+    const vtmme_cand_job& j = jobs[i];
+    if (j.w < 1 || j.h < 1 || j.w > 128 || j.h > 128 || j.nCand < 1 || j.nCand > 64 || !j.mv || j.subShift < 0 || j.subShift > 4)
+      return vtmme_set_error(ctx, VTMME_ERR_ARG, who, "bad job (w,h in [1,128], nCand in [1,64], subShift in [0,4])");
+    if (ctx->pics.find(j.refPic) == ctx->pics.end() || (!j.org && ctx->pics.find(j.curPic) == ctx->pics.end()))
+      return vtmme_set_error(ctx, VTMME_ERR_NOPIC, who, "unknown picture id");
+    if (j.org) orgBytes += align256((size_t) j.w * j.h * 2);
+    nTiles += (long long) j.nCand * ((j.w + 15) / 16) * ((j.h + 15) / 16);
+    nCand += j.nCand;
+  }
+  if (nTiles > (1 << 24)) return vtmme_set_error(ctx, VTMME_ERR_ARG, who, "too many candidates in one call");
+  // one pinned block / one device block: [tiles][patterns][sums]
+  const size_t offOrg = align256((size_t) nTiles * sizeof(McSadTile)), offOut = align256(offOrg + orgBytes);
+  const size_t total = offOut + align256((size_t) nCand * 8);
+  int rc;
+  VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));   // the staging blocks are shared with the other synchronous calls
+  if ((rc = ensure_pinned(ctx, total)) != VTMME_OK) return rc;
+  if ((rc = ensure(ctx, ctx->dJobBuf, ctx->jobBufCap, total)) != VTMME_OK) return rc;
+  McSadTile* ht = reinterpret_cast<McSadTile*>(ctx->hPinned);
+  size_t     orgCur = offOrg;
+  int        k = 0, slot = 0;
+  for (int i = 0; i < nJobs; i++)
+  {
+    const vtmme_cand_job& j = jobs[i];
+    const DevPic& rp = ctx->pics[j.refPic];
+    int wrc;
+    if ((wrc = wait_picture(ctx, j.refPic)) != VTMME_OK) return wrc;
+    const int16_t* dOrg;
+    int            orgStride;
+    if (j.org)
+    {
+      int16_t* ho = reinterpret_cast<int16_t*>(ctx->hPinned + orgCur);
+      for (int y = 0; y < j.h; y++) memcpy(ho + (size_t) y * j.w, j.org + (ptrdiff_t) y * j.orgStride, (size_t) j.w * 2);
+      dOrg      = reinterpret_cast<const int16_t*>(ctx->dJobBuf + orgCur);
+      orgStride = j.w;
+      orgCur += align256((size_t) j.w * j.h * 2);
+    }
+    else
+    {
+      const DevPic& cp = ctx->pics[j.curPic];
+      if ((wrc = wait_picture(ctx, j.curPic)) != VTMME_OK) return wrc;
+      if (j.x < 0 || j.y < 0 || j.x + j.w > cp.width || j.y + j.h > cp.height)
+        return vtmme_set_error(ctx, VTMME_ERR_RANGE, who, "PU outside the original picture");
+      dOrg      = cp.origin + (ptrdiff_t) j.y * cp.stride + j.x;
+      orgStride = cp.stride;
+    }
+    for (int c = 0; c < j.nCand; c++, slot++)
+    {
+      const int mvX = j.mv[2 * c], mvY = j.mv[2 * c + 1];
+      const int ix = mvX >> 4, iy = mvY >> 4, xFrac = mvX & 15, yFrac = mvY & 15;
+      if (j.x + ix - 3 < -rp.margin || j.x + j.w + ix + 4 > rp.width + rp.margin || j.y + iy - 3 < -rp.margin ||
+          j.y + j.h + iy + 4 > rp.height + rp.margin)
+        return vtmme_set_error(ctx, VTMME_ERR_RANGE, who, "candidate leaves the padded reference plane (clip the MV first)");
+      const int  hHor  = yFrac ? j.h + 7 : j.h;
+      const bool q4Hor = j.w == 4 && (hHor == 4 || hHor == 11), q4Ver = j.w == 4 && j.h == 4;
+      const int16_t* src = rp.origin + (ptrdiff_t) (j.y + iy) * rp.stride + j.x + ix;
+      for (int ty = 0; ty < j.h; ty += 16)
+        for (int tx = 0; tx < j.w; tx += 16)
+        {
+          McSadTile& t = ht[k++];
+          t.mc.src = src + (ptrdiff_t) ty * rp.stride + tx;
+          t.mc.dst = nullptr;
+          t.mc.srcStride = rp.stride;
+          t.mc.dstStride = 0;
+          t.mc.tw = (uint8_t) (j.w - tx < 16 ? j.w - tx : 16);
+          t.mc.th = (uint8_t) (j.h - ty < 16 ? j.h - ty : 16);
+          t.mc.xFrac = (uint8_t) xFrac;
+          t.mc.yFrac = (uint8_t) yFrac;
+          t.mc.q4Hor = q4Hor;
+          t.mc.q4Ver = q4Ver;
+          t.mc.pad[0] = t.mc.pad[1] = 0;
+          t.org = dOrg + (ptrdiff_t) ty * orgStride + tx;
+          t.orgStride = orgStride;
+          t.outIdx = slot;
+          t.subShift = j.subShift;
+          t.pad = 0;
+        }
+    }
+  }
+  unsigned long long* dOut = reinterpret_cast<unsigned long long*>(ctx->dJobBuf + offOut);
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dJobBuf, ctx->hPinned, offOrg + orgBytes, cudaMemcpyHostToDevice, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, cudaMemsetAsync(dOut, 0, (size_t) nCand * 8, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, launch_mc_sad(reinterpret_cast<const McSadTile*>(ctx->dJobBuf), (int) nTiles, bitDepth, useAltHpel, dOut,
+                                      ctx->stream));
+  ctx->launches += 1;
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->hPinned + offOut, dOut, (size_t) nCand * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(out, ctx->hPinned + offOut, (size_t) nCand * 8);
+  return VTMME_OK;
+}

@@ -9,7 +9,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .lib import CFrameParams, CJob, CMcBlock, CResult, ERR_NAMES, VtmmeError, load_library
+from .lib import CCandJob, CFrameParams, CJob, CMcBlock, CResult, ERR_NAMES, VtmmeError, load_library
 
 # vtmme_cu_result
 CU_RESULT_DTYPE = np.dtype([("mvQx", "<i2"), ("mvQy", "<i2"), ("intX", "<i2"), ("intY", "<i2"),
@@ -263,3 +263,27 @@ class MotionSearch:
     def remove_high_freq(self, d_org, d_pred, count, clip=0, bit_depth=10):
         self._check(self.L.vtmme_remove_high_freq(self.ctx, C.c_void_p(d_org), C.c_void_p(d_pred), count, clip, bit_depth),
                     "vtmme_remove_high_freq")
+
+    # ---- candidate distortion (AMVP template cost / ME seeds) ----------------------------------------------
+    def cand_sad(self, jobs, bit_depth=10, use_alt_hpel=0):
+        """jobs: list of dicts {curPic, refPic, x, y, w, h, mv: [(mvX, mvY), ...] in 1/16 sample, subShift=0, org=None}
+        (org: optional int16 2-D array replacing the block read from curPic).  Returns a list of per-job SAD lists."""
+        arr = (CCandJob * len(jobs))()
+        keep = []
+        total = 0
+        for i, j in enumerate(jobs):
+            mv = np.ascontiguousarray(np.asarray(j["mv"], dtype=np.int32).reshape(-1, 2))
+            org = j.get("org")
+            keep.append((mv, org))
+            arr[i] = CCandJob(int(j.get("curPic", 0)), int(j["refPic"]), int(j["x"]), int(j["y"]), int(j["w"]), int(j["h"]),
+                              C.c_void_p(org.ctypes.data) if org is not None else None,
+                              org.strides[0] // 2 if org is not None else 0, len(mv), C.c_void_p(mv.ctypes.data),
+                              int(j.get("subShift", 0)), 0)
+            total += len(mv)
+        out = (C.c_uint64 * total)()
+        self._check(self.L.vtmme_cand_sad(self.ctx, bit_depth, use_alt_hpel, len(jobs), arr, out), "vtmme_cand_sad")
+        res, k = [], 0
+        for mv, _ in keep:
+            res.append([int(out[k + c]) for c in range(len(mv))])
+            k += len(mv)
+        return res
