@@ -113,6 +113,7 @@ def main():
                          "cpu": "reference AVX2, 1 core" if R is not None else "n/a"})
             print(json.dumps(rows[-1]))
             assert equal, (label, w, h)
+    mc_rows = bench_mc(ms, torch, stream, B, R, O, a.quick)
     if a.out:
         with open(a.out, "w") as f:
             f.write("# Distortion / interpolation micro-benchmark (BASELINE config 5)\n\n")
@@ -122,7 +123,73 @@ def main():
             for r in rows:
                 f.write("| %s | %dx%d | %s | %d | %.3g | %.3g | %.1f | %s |\n" % (r["op"], r["w"], r["h"], r["data"], r["n"], r["gpu_blocks_per_s"],
                                                                                 r["cpu_blocks_per_s"], r["gpu_blocks_per_s"] / r["cpu_blocks_per_s"], r["equal"]))
+            if mc_rows:
+                f.write("\n## Motion compensation of a whole 1080p picture (xPredInterBlk, uni-directional, random fractional MVs)\n\n"
+                        "GPU: `vtmme_mc_batch` (host block list -> device prediction, wall time per call incl. the host-side tile "
+                        "build); CPU: the reference's own `InterPrediction::xPredInterBlk` on one core.\n\n"
+                        "| component | block | blocks | GPU Msamples/s | CPU Msamples/s (1 core) | ratio | equal |\n|---|---|---|---|---|---|---|\n")
+                for r in mc_rows:
+                    f.write("| %s | %dx%d | %d | %.0f | %.0f | %.1f | %s |\n" % (r["comp"], r["s"], r["s"], r["n"], r["gpu_msps"],
+                                                                                   r["cpu_msps"], r["gpu_msps"] / r["cpu_msps"] if r["cpu_msps"] else float("nan"), r["equal"]))
     ms.close()
+
+
+def bench_mc(ms, torch, stream, B, R, O, quick):
+    """Whole-picture motion compensation: every SxS block of a 1080p luma plane (960x540 chroma plane) with its own
+    random fractional MV."""
+    import time
+    from vtm_b200.lib import CMcBlock
+    rows = []
+    W, H = 1920, 1080
+    for comp, name in ((0, "luma 8-tap"), (1, "chroma 4-tap")):
+        cw, ch = (W, H) if comp == 0 else (W // 2, H // 2)
+        M = 192 if comp == 0 else 128      # the reference Picture's own chroma margin is 144
+        rng = np.random.default_rng(90 + comp)
+        padded = np.ascontiguousarray(np.pad(rng.integers(0, 1024, (ch, cw), dtype=np.int16), M, mode="edge"))
+        ms.upload_picture(900 + comp, padded, M)
+        for s in ((8, 16, 64) if not quick else (16,)):
+            if comp == 1:
+                s //= 2
+            blks = [(x, y, min(s, cw - x), min(s, ch - y), int(rng.integers(-32 * 16, 32 * 16)), int(rng.integers(-32 * 16, 32 * 16)))
+                    for y in range(0, ch, s) for x in range(0, cw, s)]
+            arr = (CMcBlock * len(blks))()
+            for i, b in enumerate(blks):
+                arr[i] = CMcBlock(900 + comp, b[0], b[1], b[2], b[3], b[4], b[5], 0)
+            total = sum(b[2] * b[3] for b in blks)
+            d_dst = torch.zeros(total, dtype=torch.int16, device="cuda")
+            for _ in range(2):
+                ms.mc_batch(comp, arr, d_dst.data_ptr(), 0)
+            ms.synchronize()
+            reps = 5
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                ms.mc_batch(comp, arr, d_dst.data_ptr(), 0)
+            ms.synchronize()
+            t_gpu = (time.perf_counter() - t0) / reps
+            got = d_dst.cpu().numpy()
+            if R is not None:
+                ba = np.array(blks, dtype=np.int32)
+                want = np.zeros(total, np.int16)
+                sec = C.c_double()
+                assert R.ref_mc_blocks(comp, B.ptr(padded), padded.shape[1], W, H, M, len(blks), C.c_void_p(ba.ctypes.data), 0, 10, 0,
+                                       B.ptr(want), C.byref(sec)) == 0
+                t_cpu = sec.value
+                equal = bool(np.array_equal(got, want))
+            else:
+                t_cpu, equal = float("nan"), True
+                stride = padded.shape[1]
+                off = 0
+                for i, (x, y, w, h, mvx, mvy) in enumerate(blks):
+                    if i % 97 == 0:
+                        d = np.zeros((h, w), np.int16)
+                        O.vo_mc_block(comp, B.ptr(padded, (M + y) * stride + M + x), stride, w, h, mvx, mvy, 0, 10, 0, B.ptr(d), w)
+                        equal &= bool(np.array_equal(d.ravel(), got[off:off + w * h]))
+                    off += w * h
+            rows.append({"op": "mc", "comp": name, "s": s, "n": len(blks), "gpu_msps": total / t_gpu / 1e6,
+                         "cpu_msps": total / t_cpu / 1e6 if t_cpu == t_cpu else float("nan"), "equal": equal})
+            print(json.dumps(rows[-1]))
+            assert equal, ("mc", name, s)
+    return rows
 
 
 if __name__ == "__main__":

@@ -109,7 +109,7 @@ def ref():
         L.ref_dist_batch.argtypes = [_P, _P, _I, _I, _I, _I, _I, _I, _P]
         L.ref_filter_batch.restype = C.c_double
         L.ref_filter_batch.argtypes = [_I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I]
-        L.ref_mc_blocks.argtypes = [_I, _P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P]
+        L.ref_mc_blocks.argtypes = [_I, _P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, C.POINTER(C.c_double)]
         L.ref_add_avg.argtypes = [_P, _P, _P, _I, _I, _I]
         L.ref_remove_high_freq.argtypes = [_P, _I, _P, _I, _I, _I, _I, _I]
         _ref = L

@@ -271,9 +271,9 @@ double ref_filter_batch(int comp, int vertical, const int16_t* src, int16_t* dst
 // A Picture is created with the given luma size, the reconstruction plane of component `comp` (0 Y, 1 Cb) is loaded from
 // `plane` (component-sized, `margin` border samples on each side already extended), and xPredInterBlk runs for every block.
 // blk: n x 6 int32 {x, y, w, h, mvX, mvY}; x,y,w,h in samples of the component, mv in 1/16 luma sample.
-// dst: blocks packed back to back (row stride = w).  Returns 0, or -1 when the margin does not fit the Picture's own.
+// dst: blocks packed back to back (row stride = w); *seconds (optional) = time spent in the xPredInterBlk calls.  Returns 0, or -1 when the margin does not fit the Picture's own.
 int ref_mc_blocks(int comp, const int16_t* plane, int planeStride, int lumaW, int lumaH, int margin, int n,
-                  const int32_t* blk, int bi, int bitDepth, int imvHpel, int16_t* dst)
+                  const int32_t* blk, int bi, int bitDepth, int imvHpel, int16_t* dst, double* seconds)
 {
   Probe& p = probe();
   Picture pic;
@@ -297,6 +297,7 @@ int ref_mc_blocks(int comp, const int16_t* plane, int planeStride, int lumaW, in
   cs->pps = &pps;
   const ClpRng clp = makeClp(bitDepth);
   const int    sc  = comp ? 1 : 0;
+  auto t0 = std::chrono::steady_clock::now();
   for (int i = 0; i < n; i++)
   {
     const int32_t* b = blk + 6 * i;
@@ -313,6 +314,7 @@ int ref_mc_blocks(int comp, const int16_t* plane, int planeStride, int lumaW, in
     p.xPredInterBlk(ComponentID(comp), pu, &pic, Mv(b[4], b[5]), out, bi != 0, clp, false, false);
     dst += w * h;
   }
+  if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   pic.destroy();
   return 0;
 }

@@ -38,7 +38,7 @@ def main():
                     continue
                 dst = np.zeros(n, np.int16)
                 rc = R.ref_mc_blocks(comp, B.ptr(padded), padded.shape[1], W, H, M, len(blks), C.c_void_p(ba.ctypes.data), bi, 10,
-                                     alt, B.ptr(dst))
+                                     alt, B.ptr(dst), None)
                 assert rc == 0
                 out["pred_%s_bi%d_alt%d" % (name, bi, alt)] = dst
     # bi-prediction helpers on 64x32 samples

@@ -211,7 +211,7 @@ def test_mc_block_matches_xPredInterBlk(oracle_lib, ref_lib, comp, bi, alt):
     ba = np.array(blks, dtype=np.int32)
     got = np.zeros(int((ba[:, 2] * ba[:, 3]).sum()), np.int16)
     rc = ref_lib.ref_mc_blocks(comp, B.ptr(padded), padded.shape[1], W, H, M, len(blks), C.c_void_p(ba.ctypes.data), bi, 10,
-                               alt, B.ptr(got))
+                               alt, B.ptr(got), None)
     assert rc == 0
     want = oracle_mc(oracle_lib, comp, padded, M, blks, bi, 10, alt)
     assert np.array_equal(got, want)
@@ -228,7 +228,7 @@ def test_mc_block_8bit(oracle_lib, ref_lib):
     for bi in (0, 1):
         got = np.zeros(int((ba[:, 2] * ba[:, 3]).sum()), np.int16)
         assert ref_lib.ref_mc_blocks(0, B.ptr(padded), padded.shape[1], W, H, M, len(blks), C.c_void_p(ba.ctypes.data), bi, 8, 0,
-                                     B.ptr(got)) == 0
+                                     B.ptr(got), None) == 0
         assert np.array_equal(got, oracle_mc(oracle_lib, 0, padded, M, blks, bi, 8, 0))
 
 
@@ -270,7 +270,7 @@ def test_template_distortion_composition(oracle_lib, ref_lib):
             mvx, mvy = (int(v) for v in rng.integers(-300, 300, 2))
             blk = np.array([[0, 0, w, h, mvx, mvy]], dtype=np.int32)
             rp = np.zeros((h, w), np.int16)
-            assert ref_lib.ref_mc_blocks(0, B.ptr(padded), stride, W, H, M, 1, C.c_void_p(blk.ctypes.data), 0, 10, 0, B.ptr(rp)) == 0
+            assert ref_lib.ref_mc_blocks(0, B.ptr(padded), stride, W, H, M, 1, C.c_void_p(blk.ctypes.data), 0, 10, 0, B.ptr(rp), None) == 0
             op = np.zeros((h, w), np.int16)
             oracle_lib.vo_mc_block(0, B.ptr(padded, M * stride + M), stride, w, h, mvx, mvy, 0, 10, 0, B.ptr(op), w)
             assert ref_lib.ref_dist(B.ptr(org), w, B.ptr(rp), w, w, h, 10, 0, 0) == oracle_lib.vo_sad(B.ptr(org), w, B.ptr(op), w, w, h, 0)
