@@ -10,13 +10,18 @@
  *
  *   reference interface replaced                                   entry point here
  *   ------------------------------------------------------------  ---------------------------------
- *   RdCost::m_afpDistortFunc[DF_SAD*]  (RdCost.h:113,               vtmme_sad_batch / vtmme_dist_host
+ *   RdCost::m_afpDistortFunc[DF_SAD*]  (RdCost.h:113,               vtmme_dist_batch (kind 0) / vtmme_dist_host
  *     RdCost.cpp:125-208; x86/RdCostX86.h:2307-2321)
- *   RdCost::m_afpDistortFunc[DF_HAD*]  (x86/RdCostX86.h:2323-2330)  vtmme_satd_batch / vtmme_dist_host
+ *   RdCost::m_afpDistortFunc[DF_HAD*]  (x86/RdCostX86.h:2323-2330)  vtmme_dist_batch (kind 1) / vtmme_dist_host
  *   InterpolationFilter::m_filterHor/m_filterVer/m_filterCopy       vtmme_interp_batch / vtmme_interp_host
  *     (InterpolationFilter.h:96-98, InterpolationFilter.cpp:749-895)
  *   InterSearch::xPatternSearch + xPatternSearchFracDIF             vtmme_search          (per-call jobs)
  *     (EncoderLib/InterSearch.cpp:3566-3608, 4284-4339)             vtmme_search_frames   (batched, per CTU tree)
+ *   InterPrediction::xPredInterBlk (CommonLib/InterPrediction.cpp   vtmme_mc_batch / vtmme_mc_host
+ *     :660-830), AreaBuf::addAvg (Buffer.cpp:467-507),              vtmme_add_avg
+ *     AreaBuf::removeHighFreq (Buffer.h:474-517)                    vtmme_remove_high_freq
+ *   distortion of InterSearch::xGetTemplateCost and of the ME      vtmme_cand_sad
+ *     seeds (EncoderLib/InterSearch.cpp:3235-3270, 3388-3426)
  *   Picture::getRecoBuf / getOrigBuf planes handed to ME            vtmme_upload_picture / vtmme_release_picture
  *     (Picture.cpp:322-329, extendPicBorder :1050-1110)
  *
