@@ -187,7 +187,7 @@ def run_reference(args, rank):
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": kind, "sample": desc},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---- this repo's arm ------------------------------------------------------------------------------------------------
@@ -365,10 +365,24 @@ def run_ours(args, rank, world, local_rank):
             rate, sec, desc, kind, threads = cpu_reference_rate(cur0, ref0, args.cpu_every, os.cpu_count() or 1)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind, "sample": desc,
                                     "seconds": sec}
-        print(json.dumps(line))
+        emit(line)
     ms.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+_STDOUT = {"fd": None}
+
+
+def emit(line):
+    """The one JSON line of the bench contract, on the process's original stdout."""
+    text = json.dumps(line) + "\n"
+    sys.stdout.flush()
+    if _STDOUT["fd"] is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        os.write(_STDOUT["fd"], text.encode())
 
 
 def main():
@@ -388,6 +402,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: anything a library prints on fd 1 while we run (e.g. NCCL's version banner)
+    # is sent to stderr, and emit() writes the line to the real stdout.
+    sys.stdout.flush()
+    _STDOUT["fd"] = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank)
     else:

@@ -2,6 +2,7 @@
 // (include/vtmme.h).
 #include "VtmCudaME.h"
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <map>
@@ -17,6 +18,7 @@ namespace
 vtmme_ctx* g_ctx        = nullptr;
 uint64_t   g_calls      = 0;
 uint64_t   g_uploads    = 0;
+double     g_searchSec  = 0;   // wall time spent inside vtmme_search (upload of the pattern, kernels, sync)
 int        g_nextPicId  = 1;
 
 struct Uploaded
@@ -104,7 +106,10 @@ void search( const SearchIn& in, SearchOut& out )
   j.fracMode     = in.doFrac;
   j.lambdaMotion = in.lambdaMotion;
   vtmme_result r;
-  const int rc = vtmme_search( ctx(), &j, 1, &r );
+  vtmme_ctx*   c  = ctx();
+  const auto   t0 = std::chrono::steady_clock::now();
+  const int    rc = vtmme_search( c, &j, 1, &r );
+  g_searchSec += std::chrono::duration<double>( std::chrono::steady_clock::now() - t0 ).count();
   CHECK( rc != VTMME_OK, vtmme_last_error( g_ctx ) );
   out.mvX      = r.mvX;
   out.mvY      = r.mvY;
@@ -145,8 +150,10 @@ void printStats()
 {
   if( g_ctx )
   {
-    fprintf( stderr, "[vtmcuda] GPU motion searches: %llu, reference pictures uploaded: %llu, kernel launches: %llu\n",
-             (unsigned long long) g_calls, (unsigned long long) g_uploads, (unsigned long long) vtmme_launch_count( g_ctx ) );
+    fprintf( stderr, "[vtmcuda] GPU motion searches: %llu (%.1f s inside vtmme_search, %.1f us per call), reference pictures "
+                     "uploaded: %llu, kernel launches: %llu\n",
+             (unsigned long long) g_calls, g_searchSec, g_calls ? 1e6 * g_searchSec / g_calls : 0.0,
+             (unsigned long long) g_uploads, (unsigned long long) vtmme_launch_count( g_ctx ) );
   }
 }
 }   // namespace vtmcuda

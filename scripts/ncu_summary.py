@@ -1,4 +1,4 @@
-"""Summarise an .ncu-rep (raw + source pages) into a few lines / a markdown file.  usage: ncu_summary.py rep [out.md] [title]"""
+"""Summarise an .ncu-rep (raw + source pages) into a few lines / a markdown file.  usage: ncu_summary.py rep [out.md] [title] [launch index]"""
 import collections
 import csv
 import io
@@ -7,7 +7,8 @@ import subprocess
 import sys
 
 rep = sys.argv[1]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+sel = ["--launch-skip", sys.argv[4], "--launch-count", "1"] if len(sys.argv) > 4 else []   # which launch of the report
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"] + sel, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, vals = rows[0], rows[1], rows[2]
 d = {h: (u, v) for h, u, v in zip(hdr, units, vals)}
@@ -36,12 +37,14 @@ out += ['# %s\n' % title, '| metric | value | unit |', '|---|---|---|']
 for k in keys:
     if k in d:
         out.append('| %s | %s | %s |' % (k, d[k][1], d[k][0]))
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + sel, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
 ops, thr, tot = collections.Counter(), collections.Counter(), 0
 for r in rows[2:]:
+    if r and r[0] == "Kernel Name":   # a second view of the same kernel follows: the first one is complete
+        break
     if len(r) < 10:
         continue
     m = re.match(r'(@!?U?P\d+\s+)?([A-Z0-9_.]+)', r[ix['Source']].strip())

@@ -127,6 +127,10 @@ def test_job_search_all_shapes(ms, oracle_lib):
     got = ms.search(jobs)
     bad = [(i, jobs[i].w, jobs[i].h, got[i], want[i]) for i in range(len(jobs)) if got[i] != want[i]]
     assert not bad, "%d of %d jobs differ, first: %s" % (len(bad), len(jobs), bad[:3])
+    # one job per call: what the in-loop encoder does (patterns up to 32x32 take the single-launch path)
+    got1 = [ms.search([j])[0] for j in jobs]
+    bad = [(i, jobs[i].w, jobs[i].h, got1[i], want[i]) for i in range(len(jobs)) if got1[i] != want[i]]
+    assert not bad, "single calls: %d of %d jobs differ, first: %s" % (len(bad), len(jobs), bad[:3])
 
 
 def test_job_search_integer_amvr(ms, oracle_lib):
@@ -154,6 +158,7 @@ def test_job_search_integer_amvr(ms, oracle_lib):
             want.append(r.tuple())
     got = ms.search(jobs)
     assert got == want
+    assert [ms.search([j])[0] for j in jobs] == want   # single-launch path of the small patterns
 
 
 def test_dist_host_all_shapes(ms, oracle_lib):

@@ -16,7 +16,7 @@ constexpr int kUnroll = 16;   // independent accumulators per thread
 
 // Variant ids (keep in sync with vtm_b200/peaks.py)
 enum { V_VABSDIFF = 0, V_IADD3, V_IMAD, V_LOP3, V_PRMT, V_VABSDIFF_IMAD, V_FADD_ABS, V_VABSDIFF_FADD, V_VIADD16X2,
-       V_VIADDMNMX16X2, V_VABSDIFF4, V_VABSDIFF_FADD2, V_COUNT };
+       V_VIADDMNMX16X2, V_VABSDIFF4, V_VABSDIFF_FADD2, V_DP2A, V_DP4A, V_COUNT };
 
 template <int V>
 __global__ void __launch_bounds__(256) peak_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int iters,
@@ -83,6 +83,8 @@ __global__ void __launch_bounds__(256) peak_kernel(const uint32_t* __restrict__ 
       if (V == V_VIADD16X2) acc[i] = __vadd2(x, b[i]) ^ acc[i];
       if (V == V_VIADDMNMX16X2) acc[i] = __viaddmax_s16x2(x, b[i], acc[i]);
       if (V == V_VABSDIFF4) acc[i] = __vsadu4(x, b[i]) + acc[i];
+      if (V == V_DP2A) acc[i] = (uint32_t) __dp2a_lo((int) x, (int) b[i], (int) acc[i]);
+      if (V == V_DP4A) acc[i] = (uint32_t) __dp4a((int) x, (int) b[i], (int) acc[i]);
     }
   }
   const long long t1 = clock64();
@@ -175,7 +177,7 @@ extern "C" int vtmme_int_peak(int variant, int iters, double* laneInstrPerClkPer
   {
 #define CASE(V) case V: rc = run_variant<V>(iters, sms, din, dout, dclk, laneInstrPerClkPerSm, ms, smClockMHz, st); break;
     CASE(V_VABSDIFF) CASE(V_IADD3) CASE(V_IMAD) CASE(V_LOP3) CASE(V_PRMT) CASE(V_VABSDIFF_IMAD) CASE(V_FADD_ABS)
-    CASE(V_VABSDIFF_FADD) CASE(V_VIADD16X2) CASE(V_VIADDMNMX16X2) CASE(V_VABSDIFF4) CASE(V_VABSDIFF_FADD2)
+    CASE(V_VABSDIFF_FADD) CASE(V_VIADD16X2) CASE(V_VIADDMNMX16X2) CASE(V_VABSDIFF4) CASE(V_VABSDIFF_FADD2) CASE(V_DP2A) CASE(V_DP4A)
 #undef CASE
     default: rc = -2;
   }

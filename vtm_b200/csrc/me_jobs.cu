@@ -16,7 +16,7 @@ namespace vtmme {
 namespace {
 
 constexpr int kJobThreads  = 256;
-constexpr int kJobBandRows = 32;
+constexpr int kJobBandRows = 32;   // maximum; small calls use 16 or 8 so that one job still spreads over many SMs
 
 struct JobSmemHdr
 {
@@ -38,7 +38,7 @@ __device__ __forceinline__ int regions_of(const DevJob& j) { return ((j.w + 31) 
 __global__ void __launch_bounds__(kJobThreads, 2) me_job_sad_kernel(const DevJob* __restrict__ jobs,
                                                                     unsigned long long* __restrict__ keys,
                                                                     uint32_t* __restrict__ surf,
-                                                                    const long long* __restrict__ surfOff, int nSplit)
+                                                                    const long long* __restrict__ surfOff, int nSplit, int bandRows)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   JobSmemHdr* hdr   = reinterpret_cast<JobSmemHdr*>(smem);
@@ -67,9 +67,9 @@ __global__ void __launch_bounds__(kJobThreads, 2) me_job_sad_kernel(const DevJob
   }
   uint32_t* mySurf = direct ? nullptr : surf + surfOff[blockIdx.y] + (long long) region * nrows * (ngx * 8);
 
-  for (int band0 = split * kJobBandRows; band0 < nrows; band0 += nSplit * kJobBandRows)
+  for (int band0 = split * bandRows; band0 < nrows; band0 += nSplit * bandRows)
   {
-    const int bh = min(kJobBandRows, nrows - band0);
+    const int bh = min(bandRows, nrows - band0);
     __syncthreads();
     {
       // rows [j.t+band0, +bh+rh-1), cols [wl8, wl8 + ngx*8 + rw + 7] relative to the sub-block position
@@ -331,12 +331,165 @@ __global__ void __launch_bounds__(128) me_job_frac_finish_kernel(const DevJob* _
   __threadfence_system();
 }
 
+
+// ---- single small job, one launch (the in-loop encoder's call: one PU, pattern <= 32x32) ----------------------------
+// Job descriptor and pattern travel as kernel parameters (no upload, no dependent global reads at kernel start); every
+// CTA searches one band of window rows, the last CTA to finish (ticket) runs the fractional refinement and writes the
+// result to mapped pinned memory.
+constexpr int kFusedThreads = kFracThreads;   // 128: the refinement code is written for CTAs of kFracThreads threads
+
+__global__ void __launch_bounds__(kFusedThreads) me_job_fused_kernel(const __grid_constant__ FusedJobArgs a)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ FracSmem fsm;
+  __shared__ int16_t  s_pat[32 * 32];
+  __shared__ int      s_last;
+  JobSmemHdr* hdr   = reinterpret_cast<JobSmemHdr*>(smem);
+  int32_t*    s_org = reinterpret_cast<int32_t*>(smem + kJobOffOrg);
+  int16_t*    s_ref = reinterpret_cast<int16_t*>(smem + kJobOffRef);
+
+  const DevJob& j   = a.job;
+  const int     tid = threadIdx.x;
+  const int rw = j.w, rh = j.h;
+  const int wl8 = j.l & ~7;
+  const int ngx = (j.r - wl8 + 8) >> 3, nrows = j.b - j.t + 1;
+  const int refStride = ngx * 8 + 40;
+  const int step = 1 << j.subShift;
+
+  if (tid == 0) hdr->best = ~0ull;
+  for (int i = tid; i < rw * rh; i += kFusedThreads)
+  {
+    const int     y = i / rw, x = i - y * rw;
+    const int16_t v = a.inlinePattern ? a.pattern[i] : j.org[(size_t) y * j.orgStride + x];
+    s_org[y * 32 + x] = (int32_t) v;
+    s_pat[i]          = v;
+  }
+  for (int band0 = blockIdx.x * a.bandRows; band0 < nrows; band0 += gridDim.x * a.bandRows)
+  {
+    const int bh = min(a.bandRows, nrows - band0);
+    __syncthreads();
+    {
+      const int cols = ngx * 8 + rw + 8;
+      const int16_t* src = j.refAtPU + (ptrdiff_t) (j.t + band0) * j.refStride + wl8;
+      for (int i = tid; i < (bh + rh - 1) * cols; i += kFusedThreads)
+      {
+        const int r = i / cols, c = i - r * cols;
+        s_ref[r * refStride + c] = src[(ptrdiff_t) r * j.refStride + c];
+      }
+    }
+    __syncthreads();
+    const int ntiles = ngx * bh;
+    for (int t = tid; t < ntiles; t += kFusedThreads)
+    {
+      const int      dyi = t / ngx, gx = t - dyi * ngx;
+      const int      dy = j.t + band0 + dyi, dx0 = wl8 + gx * 8;
+      const int16_t* refTile = s_ref + dyi * refStride + gx * 8;
+      uint32_t       acc[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) acc[k] = 0;
+      for (int r = 0; r < rh; r += step)
+      {
+        if (rw >= 8)
+        {
+          for (int g = 0; g < rw; g += 8)
+          {
+            const int4  o0 = *reinterpret_cast<const int4*>(s_org + r * 32 + g);
+            const int4  o1 = *reinterpret_cast<const int4*>(s_org + r * 32 + g + 4);
+            const uint4 w0 = *reinterpret_cast<const uint4*>(refTile + r * refStride + g);
+            const uint4 w1 = *reinterpret_cast<const uint4*>(refTile + r * refStride + g + 8);
+            const int   o[8]   = { o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w };
+            const int   px[16] = { (int) (short) (w0.x & 0xffffu), (int) w0.x >> 16, (int) (short) (w0.y & 0xffffu), (int) w0.y >> 16,
+                                   (int) (short) (w0.z & 0xffffu), (int) w0.z >> 16, (int) (short) (w0.w & 0xffffu), (int) w0.w >> 16,
+                                   (int) (short) (w1.x & 0xffffu), (int) w1.x >> 16, (int) (short) (w1.y & 0xffffu), (int) w1.y >> 16,
+                                   (int) (short) (w1.z & 0xffffu), (int) w1.z >> 16, (int) (short) (w1.w & 0xffffu), (int) w1.w >> 16 };
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+#pragma unroll
+              for (int i = 0; i < 8; i++) acc[k] = __sad(o[i], px[i + k], acc[k]);
+          }
+        }
+        else
+        {
+          const int4  o0 = *reinterpret_cast<const int4*>(s_org + r * 32);
+          const uint4 w0 = *reinterpret_cast<const uint4*>(refTile + r * refStride);
+          const uint2 w1 = *reinterpret_cast<const uint2*>(refTile + r * refStride + 8);
+          const int   o[4]   = { o0.x, o0.y, o0.z, o0.w };
+          const int   px[12] = { (int) (short) (w0.x & 0xffffu), (int) w0.x >> 16, (int) (short) (w0.y & 0xffffu), (int) w0.y >> 16,
+                                 (int) (short) (w0.z & 0xffffu), (int) w0.z >> 16, (int) (short) (w0.w & 0xffffu), (int) w0.w >> 16,
+                                 (int) (short) (w1.x & 0xffffu), (int) w1.x >> 16, (int) (short) (w1.y & 0xffffu), (int) w1.y >> 16 };
+#pragma unroll
+          for (int k = 0; k < 8; k++)
+#pragma unroll
+            for (int i = 0; i < 4; i++) acc[k] = __sad(o[i], px[i + k], acc[k]);
+        }
+      }
+      const uint32_t thr = (uint32_t) (*reinterpret_cast<volatile unsigned long long*>(&hdr->best) >> 32);
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+      {
+        const uint32_t sad = acc[k] << j.subShift;
+        if (sad <= thr) job_consider(j, &hdr->best, dx0 + k, dy, sad);
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0)
+  {
+    if (hdr->best != ~0ull) atomicMin(a.key, hdr->best);
+    __threadfence();
+    s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+
+  // ---- last CTA: the window is complete.  xPatternSearchFracDIF body and result.
+  if (tid == 0)
+  {
+    *a.ticket = 0;                                                   // ready for the next call
+    hdr->best = atomicExch(a.key, ~0ull);                            // coherent read + reset of the slot
+  }
+  __syncthreads();
+  const unsigned long long key = hdr->best;
+  const int                dx = key_dx(key), dy = key_dy(key);
+  DevJobResult             res;
+  res.mvX    = dx;
+  res.mvY    = dy;
+  res.intSad = key_cost(key) - mv_cost(j.lambda, mv_bits_q(dx * 4, dy * 4, j.predQx, j.predQy, j.imvShift));
+  res.halfX = res.halfY = res.qterX = res.qterY = 0;
+  res.fracCost = res.intSad;
+  if (j.fracMode)
+  {
+    FracJob f   = make_frac_job(j, dx, dy);
+    f.org       = s_pat;
+    f.orgStride = rw;
+    if (j.imvShift > 1)
+    {
+      frac_stage(fsm, f, 0, 0, 2, false);
+      res.fracCost = fsm.centre + mv_cost(j.lambda, mv_bits_q(dx * 4, dy * 4, j.predQx, j.predQy, j.imvShift));
+    }
+    else
+    {
+      const FracOut o = frac_refine_cta(fsm, f);
+      res.halfX    = o.halfX;
+      res.halfY    = o.halfY;
+      res.qterX    = o.qterX;
+      res.qterY    = o.qterY;
+      res.fracCost = o.cost;
+    }
+  }
+  if (tid == 0)
+  {
+    *a.result = res;   // mapped pinned host memory
+    __threadfence_system();
+  }
+}
+
 }   // namespace
 
 // dJobs must be followed in the same buffer by nothing the kernels need; dKeys [n]; surfaces are sized and
 // offset by the caller (vtmme_api.cu) and passed through dSurf / dSurfOff.
 cudaError_t launch_job_search_impl(const DevJob* dJobs, unsigned long long* dKeys, DevJobResult* dResults, int n,
-                                   int maxRegions, int nSplit, int maxGx, bool anyMulti, uint32_t* dSurf,
+                                   int maxRegions, int nSplit, int bandRows, int maxGx, bool anyMulti, uint32_t* dSurf,
                                    const long long* dSurfOff, uint32_t* dFracAcc, int maxFracChunks, cudaStream_t st,
                                    int* launches)
 {
@@ -349,7 +502,7 @@ cudaError_t launch_job_search_impl(const DevJob* dJobs, unsigned long long* dKey
     configured = smem;
   }
   dim3 grid(maxRegions * nSplit, n, 1);
-  me_job_sad_kernel<<<grid, kJobThreads, smem, st>>>(dJobs, dKeys, dSurf, dSurfOff, nSplit);
+  me_job_sad_kernel<<<grid, kJobThreads, smem, st>>>(dJobs, dKeys, dSurf, dSurfOff, nSplit, bandRows);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   *launches += 1;
@@ -370,6 +523,18 @@ cudaError_t launch_job_search_impl(const DevJob* dJobs, unsigned long long* dKey
     me_job_frac_finish_kernel<<<(n + 127) / 128, 128, 0, st>>>(dJobs, dKeys, dResults, dFracAcc, n);
     *launches += 2;
   }
+  return cudaGetLastError();
+}
+
+size_t fused_job_smem_bytes(const FusedJobArgs& a)
+{
+  const int wl8 = a.job.l & ~7, ngx = (a.job.r - wl8 + 8) >> 3;
+  return (size_t) kJobOffRef + (size_t) (a.bandRows + a.job.h - 1) * (ngx * 8 + 40) * 2;
+}
+
+cudaError_t launch_job_fused(const FusedJobArgs& a, int grid, cudaStream_t st)
+{
+  me_job_fused_kernel<<<grid, kFusedThreads, fused_job_smem_bytes(a), st>>>(a);
   return cudaGetLastError();
 }
 

@@ -99,9 +99,23 @@ struct DevJobResult
   unsigned long long fracCost;
 };
 cudaError_t launch_job_search_impl(const DevJob* dJobs, unsigned long long* dKeys, DevJobResult* dResults, int n,
-                                   int maxRegions, int nSplit, int maxGx, bool anyMulti, uint32_t* dSurf,
+                                   int maxRegions, int nSplit, int bandRows, int maxGx, bool anyMulti, uint32_t* dSurf,
                                    const long long* dSurfOff, uint32_t* dFracAcc, int maxFracChunks, cudaStream_t st,
                                    int* launches);
+
+// One small job per launch (me_job_fused_kernel): descriptor and pattern as kernel parameters
+struct FusedJobArgs
+{
+  DevJob              job;             // job.org is used only when !inlinePattern (pattern read from an uploaded picture)
+  unsigned long long* key;             // persistent slot, all-ones between calls
+  DevJobResult*       result;          // mapped pinned host memory
+  unsigned int*       ticket;          // zero between calls
+  int                 bandRows;        // window rows per CTA pass
+  int                 inlinePattern;
+  int16_t             pattern[32 * 32];   // row stride job.w
+};
+size_t      fused_job_smem_bytes(const FusedJobArgs& a);
+cudaError_t launch_job_fused(const FusedJobArgs& a, int grid, cudaStream_t st);
 
 // Table-level batches
 cudaError_t launch_dist_batch(int kind, const int16_t* org, int orgStride, long long orgBlockStride, const int16_t* cur,

@@ -1,6 +1,8 @@
 // C ABI of libvtmme.so (include/vtmme.h): context, device pictures, and the orchestration of the kernels.
 // There is no CPU implementation of anything behind these entry points: a failing CUDA call is an error.
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -54,6 +56,8 @@ struct vtmme_ctx
   uint32_t*      dJobFracAcc = nullptr;     // persistent, all-zero between calls (18 sums per job slot)
   size_t         jobFracAccCap = 0;
   unsigned char* dPinnedAlias = nullptr;    // device address of hPinned (mapped, zero-copy result write-back)
+  unsigned int*  dJobTicket = nullptr;      // CTA ticket of the single-launch small-job path, zero between calls
+  size_t         jobTicketCap = 0;
   unsigned char* dMcTiles = nullptr;        // tile descriptors of vtmme_mc_batch / vtmme_mc_host
   size_t         mcTilesCap = 0;
   unsigned char* hMcTiles = nullptr;        // their own pinned staging block (vtmme_mc_batch returns before the upload ends)
@@ -233,6 +237,7 @@ void vtmme_destroy(vtmme_ctx* ctx)
   cudaFree(ctx->dFracAcc);
   cudaFree(ctx->dJobBuf);
   cudaFree(ctx->dMcTiles);
+  cudaFree(ctx->dJobTicket);
   if (ctx->hMcTiles) cudaFreeHost(ctx->hMcTiles);
   if (ctx->mcUploaded) cudaEventDestroy(ctx->mcUploaded);
   cudaFree(ctx->dJobSurf);
@@ -505,15 +510,32 @@ static int ensure_pinned(vtmme_ctx* ctx, size_t bytes)
 
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t) 255; }
 
+namespace {
+struct SearchTiming
+{
+  bool   on = getenv("VTMME_TIMING") != nullptr;
+  double prep = 0, enqueue = 0, wait = 0;
+  long   calls = 0;
+  ~SearchTiming()
+  {
+    if (on && calls)
+      fprintf(stderr, "[vtmme] vtmme_search x%ld: prep %.2f us, enqueue %.2f us, wait %.2f us per call\n", calls,
+              1e6 * prep / calls, 1e6 * enqueue / calls, 1e6 * wait / calls);
+  }
+} g_timing;
+inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+}   // namespace
+
 extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_result* results)
 {
   if (!ctx) return VTMME_ERR_ARG;
+  const double tStart = g_timing.on ? now_s() : 0;
   if (!jobs || !results || n <= 0) return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search", "null argument");
   VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
 
   // ---- validate, size the buffers
   size_t orgBytes = 0, surfElems = 0;
-  int    maxGx = 1, maxRegions = 1, maxBands = 1, maxFracChunks = 1;
+  int    maxGx = 1, maxRegions = 1, maxRows = 1, maxFracChunks = 1;
   long long totalRegions = 0;
   bool   anyMulti = false;
   for (int i = 0; i < n; i++)
@@ -542,7 +564,7 @@ extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_
     maxGx      = ngx > maxGx ? ngx : maxGx;
     maxRegions = nReg > maxRegions ? nReg : maxRegions;
     if (j.fracMode && nReg > maxFracChunks) maxFracChunks = nReg;   // fractional chunks are 32x32 too
-    maxBands   = (nrows + 31) / 32 > maxBands ? (nrows + 31) / 32 : maxBands;
+    maxRows    = nrows > maxRows ? nrows : maxRows;
     totalRegions += nReg;
     if (nReg > 1)
     {
@@ -550,6 +572,88 @@ extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_
       surfElems += (size_t) nReg * nrows * ngx * 8;
     }
   }
+  // ---- one small job: single launch, descriptor + pattern as kernel parameters (me_job_fused_kernel)
+  if (n == 1 && jobs[0].w <= 32 && jobs[0].h <= 32)
+  {
+    const vtmme_job& j  = jobs[0];
+    const DevPic&    rp = ctx->pics[j.refPic];
+    FusedJobArgs     a;
+    const int wl8 = j.srLeft & ~7, ngx = (j.srRight - wl8 + 8) >> 3, nrows = j.srBottom - j.srTop + 1;
+    a.bandRows = 128 / ngx < 1 ? 1 : (128 / ngx > 32 ? 32 : 128 / ngx);   // <= one 8-wide tile per thread and pass
+    a.job.w = j.w;
+    a.job.h = j.h;
+    a.job.l = j.srLeft;
+    a.job.r = j.srRight;
+    if (fused_job_smem_bytes(a) <= 30 * 1024)
+    {
+      int rc;
+      if ((rc = ensure_pinned(ctx, 4096)) != VTMME_OK) return rc;
+      if (!ctx->dJobTicket)
+      {
+        if ((rc = ensure(ctx, ctx->dJobTicket, ctx->jobTicketCap, 256)) != VTMME_OK) return rc;
+        VTMME_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dJobTicket, 0, 256, ctx->stream));
+      }
+      if (!ctx->dJobKeys)
+      {
+        if ((rc = ensure(ctx, ctx->dJobKeys, ctx->jobKeysCap, 256 * 8)) != VTMME_OK) return rc;
+        VTMME_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dJobKeys, 0xff, 256 * 8, ctx->stream));
+        if ((rc = ensure(ctx, ctx->dJobFracAcc, ctx->jobFracAccCap, 256 * 18 * 4)) != VTMME_OK) return rc;
+        VTMME_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dJobFracAcc, 0, 256 * 18 * 4, ctx->stream));
+      }
+      a.inlinePattern = j.org != nullptr;
+      if (j.org)
+      {
+        for (int y = 0; y < j.h; y++) memcpy(a.pattern + (size_t) y * j.w, j.org + (ptrdiff_t) y * j.orgStride, (size_t) j.w * 2);
+        a.job.org       = nullptr;
+        a.job.orgStride = j.w;
+      }
+      else
+      {
+        const DevPic& cp = ctx->pics[j.curPic];
+        a.job.org       = cp.origin + (ptrdiff_t) j.y * cp.stride + j.x;
+        a.job.orgStride = cp.stride;
+      }
+      a.job.refAtPU   = rp.origin + (ptrdiff_t) j.y * rp.stride + j.x;
+      a.job.refStride = rp.stride;
+      a.job.t = j.srTop;
+      a.job.b = j.srBottom;
+      a.job.predQx = j.predQx;
+      a.job.predQy = j.predQy;
+      a.job.imvShift = j.imvShift;
+      a.job.subShift = j.subShift;
+      a.job.bitDepth = j.bitDepth;
+      a.job.useHad = j.useHad;
+      a.job.useAltHpel = j.useAltHpel;
+      a.job.fracMode = j.fracMode;
+      a.job.signedOrg = j.org != nullptr;
+      a.job.lambda = j.lambdaMotion;
+      a.key    = ctx->dJobKeys;
+      a.ticket = ctx->dJobTicket;
+      a.result = reinterpret_cast<DevJobResult*>(ctx->dPinnedAlias);
+      int grid = (nrows + a.bandRows - 1) / a.bandRows;
+      if (grid > 4 * 148) grid = 4 * 148;
+      const double tPrep = g_timing.on ? now_s() : 0;
+      VTMME_CUDA_CHECK(ctx, launch_job_fused(a, grid, ctx->stream));
+      ctx->launches += 1;
+      const double tEnq = g_timing.on ? now_s() : 0;
+      VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+      memcpy(results, ctx->hPinned, sizeof(vtmme_result));
+      if (g_timing.on)
+      {
+        const double tEnd = now_s();
+        g_timing.prep += tPrep - tStart;
+        g_timing.enqueue += tEnq - tPrep;
+        g_timing.wait += tEnd - tEnq;
+        g_timing.calls++;
+      }
+      return VTMME_OK;
+    }
+  }
+
+  // window rows per CTA pass: 32, or fewer when the call is small, so that even one 8x8 search spreads over >= 16 SMs
+  int bandRows = 32;
+  while (bandRows > 8 && totalRegions * ((maxRows + bandRows - 1) / bandRows) < 148) bandRows >>= 1;
+  const int maxBands = (maxRows + bandRows - 1) / bandRows;
   int nSplit = (int) ((4 * 148 + totalRegions - 1) / totalRegions);
   nSplit     = nSplit < 1 ? 1 : (nSplit > maxBands ? maxBands : nSplit);
 
@@ -564,6 +668,10 @@ extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_
   if ((rc = ensure(ctx, ctx->dJobBuf, ctx->jobBufCap, devBytes)) != VTMME_OK) return rc;
   if (anyMulti && (rc = ensure(ctx, ctx->dJobSurf, ctx->jobSurfCap, surfElems * 4)) != VTMME_OK) return rc;
 
+  // tiny uploads (descriptors, patterns up to 16x16): the kernels read them straight from the
+  // mapped pinned block, which saves the enqueue + DMA latency of a copy; anything larger is copied to HBM first (reads over PCIe are slow)
+  const bool           zeroCopy = upBytes <= 2048;
+  const unsigned char* dIn      = zeroCopy ? ctx->dPinnedAlias : ctx->dJobBuf;
   DevJob*    hj   = reinterpret_cast<DevJob*>(ctx->hPinned + offJobs);
   long long* hoff = reinterpret_cast<long long*>(ctx->hPinned + offSurfOff);
   size_t     orgCur = offOrg, surfCur = 0;
@@ -576,7 +684,7 @@ extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_
     {
       int16_t* dst = reinterpret_cast<int16_t*>(ctx->hPinned + orgCur);
       for (int y = 0; y < j.h; y++) memcpy(dst + (size_t) y * j.w, j.org + (size_t) y * j.orgStride, (size_t) j.w * 2);
-      d.org       = reinterpret_cast<const int16_t*>(ctx->dJobBuf + orgCur);
+      d.org       = reinterpret_cast<const int16_t*>(dIn + orgCur);
       d.orgStride = j.w;
       orgCur += align256((size_t) j.w * j.h * 2);
     }
@@ -613,7 +721,8 @@ extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_
       surfCur += (size_t) nReg * (j.srBottom - j.srTop + 1) * (((j.srRight - wl8 + 8) >> 3) * 8);
     }
   }
-  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dJobBuf, ctx->hPinned, upBytes, cudaMemcpyHostToDevice, ctx->stream));
+  const double tPrep = g_timing.on ? now_s() : 0;
+  if (!zeroCopy) VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dJobBuf, ctx->hPinned, upBytes, cudaMemcpyHostToDevice, ctx->stream));
   if ((size_t) n * 8 > ctx->jobKeysCap)
   {
     const size_t want = (size_t) (n < 256 ? 256 : n) * 8;
@@ -623,16 +732,25 @@ extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_
     VTMME_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dJobFracAcc, 0, want / 8 * 18 * 4, ctx->stream));
   }
   int launches = 0;
-  VTMME_CUDA_CHECK(ctx, launch_job_search_impl(reinterpret_cast<const DevJob*>(ctx->dJobBuf + offJobs),
+  VTMME_CUDA_CHECK(ctx, launch_job_search_impl(reinterpret_cast<const DevJob*>(dIn + offJobs),
                                                ctx->dJobKeys,
                                                reinterpret_cast<DevJobResult*>(ctx->dPinnedAlias + offRes), n, maxRegions,
-                                               nSplit, maxGx, anyMulti, ctx->dJobSurf,
-                                               reinterpret_cast<const long long*>(ctx->dJobBuf + offSurfOff),
+                                               nSplit, bandRows, maxGx, anyMulti, ctx->dJobSurf,
+                                               reinterpret_cast<const long long*>(dIn + offSurfOff),
                                                ctx->dJobFracAcc, maxFracChunks, ctx->stream, &launches));
   ctx->launches += launches;
   // the frac kernel wrote the results straight into the mapped pinned block: no device-to-host copy
+  const double tEnq = g_timing.on ? now_s() : 0;
   VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   memcpy(results, ctx->hPinned + offRes, (size_t) n * sizeof(vtmme_result));
+  if (g_timing.on)
+  {
+    const double tEnd = now_s();
+    g_timing.prep += tPrep - tStart;
+    g_timing.enqueue += tEnq - tPrep;
+    g_timing.wait += tEnd - tEnq;
+    g_timing.calls++;
+  }
   return VTMME_OK;
 }
 

@@ -4,7 +4,7 @@ import ctypes as C
 from .lib import VtmmeError, load_library
 
 VARIANTS = ["vabsdiff", "iadd3", "imad", "lop3", "prmt", "vabsdiff+imad", "fadd_abs(denormal)", "vabsdiff:fadd 2:1",
-            "viadd.16x2", "viaddmnmx.s16x2", "vabsdiff4.u8", "vabsdiff:fadd 1:1"]
+            "viadd.16x2", "viaddmnmx.s16x2", "vabsdiff4.u8", "vabsdiff:fadd 1:1", "idp.2a (dp2a)", "idp.4a (dp4a)"]
 
 
 def int_peak(variant, iters=4096):
