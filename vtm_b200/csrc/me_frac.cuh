@@ -163,7 +163,9 @@ __device__ __forceinline__ int frac_num_chunks(int w, int h)
 
 // Candidate distortions of one refinement stage around (cqx,cqy) (quarter-pel offset from the integer MV) with step
 // `step` (2 = half-pel, 1 = quarter-pel), accumulated into sm.acc[0..8] over chunk `chunkSel` (or all chunks if < 0).
-__device__ inline void frac_stage_sums(FracSmem& sm, const FracJob& j, int cqx, int cqy, int step, bool alt, int chunkSel)
+// `staged`: the (single) chunk's original samples and reference patch are already in sm from the previous stage.
+__device__ inline void frac_stage_sums(FracSmem& sm, const FracJob& j, int cqx, int cqy, int step, bool alt, int chunkSel,
+                                       bool staged = false)
 {
   const int8_t (*tab)[2] = (step == 2) ? c_refineH : c_refineQ;
   const int tid = threadIdx.x;
@@ -195,18 +197,21 @@ __device__ inline void frac_stage_sums(FracSmem& sm, const FracJob& j, int cqx, 
       if (chunkSel >= 0 && chunk != chunkSel) continue;
       __syncthreads();
       // 1. stage original chunk and reference patch rows [-4, ch+4), cols [-4, cw+4)
-      for (int i = tid; i < cw * ch; i += kFracThreads)
+      if (!staged)
       {
-        const int y = i / cw, x = i - y * cw;
-        sm.org[y * kFracChunk + x] = j.org[(size_t) (cy0 + y) * j.orgStride + cx0 + x];
+        for (int i = tid; i < cw * ch; i += kFracThreads)
+        {
+          const int y = i / cw, x = i - y * cw;
+          sm.org[y * kFracChunk + x] = j.org[(size_t) (cy0 + y) * j.orgStride + cx0 + x];
+        }
+        for (int i = tid; i < (ch + 8) * (cw + 8); i += kFracThreads)
+        {
+          const int y = i / (cw + 8), x = i - y * (cw + 8);
+          sm.patch[y * kPatchStride + x] =
+            (uint16_t) j.refAtMv[(ptrdiff_t) (cy0 + y - 4) * j.refStride + (cx0 + x - 4)];
+        }
+        __syncthreads();
       }
-      for (int i = tid; i < (ch + 8) * (cw + 8); i += kFracThreads)
-      {
-        const int y = i / (cw + 8), x = i - y * (cw + 8);
-        sm.patch[y * kPatchStride + x] =
-          (uint16_t) j.refAtMv[(ptrdiff_t) (cy0 + y - 4) * j.refStride + (cx0 + x - 4)];
-      }
-      __syncthreads();
       // 2. horizontal pass: plane[p][r][c], r in [0,ch+8) <-> picture row r-4, for dqx = cqx + (p-1)*step
       for (int i = tid; i < 3 * (ch + 8) * cw; i += kFracThreads)
       {
@@ -254,17 +259,37 @@ __device__ inline void frac_stage_sums(FracSmem& sm, const FracJob& j, int cqx, 
 }
 
 // One whole stage (all chunks) and its decision.  Returns the winning direction index in sm.best and its cost.
-__device__ inline uint32_t frac_stage(FracSmem& sm, const FracJob& j, int cqx, int cqy, int step, bool alt)
+__device__ inline uint32_t frac_stage(FracSmem& sm, const FracJob& j, int cqx, int cqy, int step, bool alt, bool staged = false)
 {
-  frac_stage_sums(sm, j, cqx, cqy, step, alt, -1);
-  if (threadIdx.x == 0)
+  frac_stage_sums(sm, j, cqx, cqy, step, alt, -1, staged);
+  if (threadIdx.x < 32)
   {
-    int      bestDir;
-    uint32_t bestCost;
-    frac_pick(sm.acc, j, cqx, cqy, step, bestDir, bestCost);
-    sm.best   = bestDir;
-    sm.centre = sm.acc[0];
-    sm.acc[0] = bestCost;
+    // frac_pick's choice with one candidate per lane: min over (cost, list index) = first strict minimum in list order
+    const int8_t (*tab)[2] = (step == 2) ? c_refineH : c_refineQ;
+    const int          i   = threadIdx.x;
+    unsigned long long key = ~0ull;
+    uint32_t           d0  = 0;
+    if (i < 9)
+    {
+      const uint32_t dist = sm.acc[i];
+      d0                  = dist;
+      const uint32_t cost = dist + mv_cost(j.lambda, mv_bits_q(j.mvX * 4 + cqx + tab[i][0] * step, j.mvY * 4 + cqy + tab[i][1] * step,
+                                                               j.predQx, j.predQy, 0));
+      key = ((unsigned long long) cost << 8) | (unsigned) i;
+    }
+#pragma unroll
+    for (int m = 8; m >= 1; m >>= 1)
+    {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, m);
+      key                        = o < key ? o : key;
+    }
+    __syncwarp();
+    if (i == 0)
+    {
+      sm.best   = (int) (key & 0xffu);
+      sm.centre = d0;
+      sm.acc[0] = (uint32_t) (key >> 8);
+    }
   }
   __syncthreads();
   const uint32_t cost = sm.acc[0];
@@ -283,7 +308,7 @@ __device__ inline FracOut frac_refine_cta(FracSmem& sm, const FracJob& j)
   o.halfY = c_refineH[hd][1];
   if (j.imvShift == 0)
   {
-    o.cost = frac_stage(sm, j, o.halfX * 2, o.halfY * 2, 1, false);
+    o.cost = frac_stage(sm, j, o.halfX * 2, o.halfY * 2, 1, false, frac_num_chunks(j.w, j.h) == 1);
     const int qd = sm.best;
     o.qterX = c_refineQ[qd][0];
     o.qterY = c_refineQ[qd][1];
