@@ -28,12 +28,13 @@ echo "bitstream md5: $(md5sum out_$MODE.bin | cut -d' ' -f1)"
 echo "recon md5:     $(md5sum rec_$MODE.yuv | cut -d' ' -f1)"
 echo "decoded md5:   $(md5sum dec_$MODE.yuv | cut -d' ' -f1)  (decoder hash check: $(grep -c '(OK)' dec_$MODE.log) OK, $(grep -c 'ERROR' dec_$MODE.log) ERROR)"
 python - <<PY
-import json
-g = json.load(open("$ROOT/tests/golden/encoder_md5.json")).get("config$CFGN")
-import hashlib
+import hashlib, json
+gold = json.load(open("$ROOT/tests/golden/encoder_md5.json"))
 bs = hashlib.md5(open("out_$MODE.bin","rb").read()).hexdigest()
-if g and "$FR" == str(g["args"].split("-f ")[1].split()[0]):
-    print("PARITY", "OK" if bs == g["bitstream_md5"] else "MISMATCH", "bitstream md5 vs golden", g["bitstream_md5"])
+# several goldens may exist per configuration (e.g. config2 = first 3 pictures, config2_full = all 32): match on -f
+hit = [g for k, g in gold.items() if k.split("_")[0] == "config$CFGN" and g["args"].split("-f ")[1].split()[0] == "$FR"]
+if hit:
+    print("PARITY", "OK" if bs == hit[0]["bitstream_md5"] else "MISMATCH", "bitstream md5 vs golden", hit[0]["bitstream_md5"])
 else:
     print("no golden for this configuration/frame count")
 PY

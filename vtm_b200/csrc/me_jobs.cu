@@ -494,13 +494,8 @@ cudaError_t launch_job_search_impl(const DevJob* dJobs, unsigned long long* dKey
                                    int* launches)
 {
   const size_t smem = (size_t) kJobOffRef + (size_t) (kJobBandRows + 31) * (maxGx * 8 + 40) * 2;
-  static size_t configured = 0;
-  if (smem > configured)
-  {
-    cudaError_t e = cudaFuncSetAttribute(me_job_sad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
+  static SmemOptIn optIn;
+  if (cudaError_t e = optIn.ensure(me_job_sad_kernel, smem)) return e;
   dim3 grid(maxRegions * nSplit, n, 1);
   me_job_sad_kernel<<<grid, kJobThreads, smem, st>>>(dJobs, dKeys, dSurf, dSurfOff, nSplit, bandRows);
   cudaError_t e = cudaGetLastError();

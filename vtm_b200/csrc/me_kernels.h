@@ -7,6 +7,26 @@
 
 namespace vtmme {
 
+// Dynamic shared memory above 48 KB is an opt-in per kernel AND per device: launchers remember what they configured for
+// the current device (a process may hold contexts on several GPUs).
+struct SmemOptIn
+{
+  size_t configured[64] = {};
+  template <class Kernel>
+  cudaError_t ensure(Kernel k, size_t bytes, size_t floorBytes = 0)
+  {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    size_t& c = configured[dev & 63];
+    if (c < floorBytes) c = floorBytes;
+    if (bytes <= c) return cudaSuccess;
+    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    if (e == cudaSuccess) c = bytes;
+    return e;
+  }
+};
+
 // Geometry of the batched per-CTU search (vtmme_search_frames): 5 levels of grid-aligned square CUs.
 struct FrameGeom
 {

@@ -746,13 +746,8 @@ static void tree_variant(int& nfp, int& fpu, int& dy, int& threads)
 template <int NFP, bool FPU, int DY, bool SS>
 static cudaError_t launch_tree_sad_t(const TreeParams& p, int nPairs, int threads, size_t smem, cudaStream_t st)
 {
-  static size_t configured = 0;
-  if (smem > configured)
-  {
-    cudaError_t e = cudaFuncSetAttribute(me_tree_sad_kernel<NFP, FPU, DY, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
+  static SmemOptIn optIn;
+  if (cudaError_t e = optIn.ensure(me_tree_sad_kernel<NFP, FPU, DY, SS>, smem)) return e;
   dim3 grid(p.g.nRegX * p.g.nRegY, nPairs, 1);
   me_tree_sad_kernel<NFP, FPU, DY, SS><<<grid, threads, smem, st>>>(p);
   return cudaGetLastError();

@@ -293,13 +293,8 @@ static cudaError_t launch_interp(const InterpArgs& a, int n, cudaStream_t st)
   int bpc = 2048 / (a.w * a.h);
   bpc     = bpc < 1 ? 1 : (bpc > 32 ? 32 : bpc);
   const size_t smem = (size_t) bpc * sw * sh * sizeof(int16_t);
-  static size_t configured = 48 * 1024;
-  if (smem > configured)
-  {
-    cudaError_t e = cudaFuncSetAttribute(interp_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
+  static SmemOptIn optIn;
+  if (cudaError_t e = optIn.ensure(interp_batch_kernel, smem, 48 * 1024)) return e;
   interp_batch_kernel<<<(n + bpc - 1) / bpc, kInterpThreads, smem, st>>>(a, n, bpc);
   return cudaGetLastError();
 }
