@@ -79,6 +79,8 @@ struct TreeParams
 };
 
 size_t tree_sad_smem_bytes(int maxGx, int maxRows, int bandRows);
+int    tree_band_override();   // development knob (VTMME_TREE_VARIANT), 0 = none
+int    tree_pick_band_rows(int maxGx, int maxRows, bool subSampling);
 cudaError_t launch_tree_sad(const TreeParams& p, int nPairs, cudaStream_t st);
 cudaError_t launch_tree_upper(const TreeParams& p, int nPairs, cudaStream_t st);
 

@@ -119,9 +119,25 @@ __device__ __forceinline__ uint32_t pack12(uint32_t x)   // x = lo | hi << 16, b
 }
 
 // 16 reference samples (two 128-bit shared loads) widened to 32 bit; FPU: on the FP32 pipe, else LOP3/SHF.
-template <bool FPU>
-__device__ __forceinline__ void load_ref16(const uint16_t* p, uint32_t (&px)[16])
+// W32: the window is staged one sample per 32-bit word (no unpack instructions at all, four 128-bit loads): a staged
+// row of `refStride` samples holds its even 4-sample chunks in words [0, refStride/2) and the odd chunks in
+// [refStride/2, refStride), so that the 16-byte pieces the lanes of a warp read are contiguous (no bank conflicts);
+// p points at the even chunk of the first sample (a multiple of 8).
+template <bool FPU, bool W32 = false>
+__device__ __forceinline__ void load_ref16(const uint16_t* p, uint32_t (&px)[16], int refStride = 0)
 {
+  if (W32)
+  {
+    const uint32_t* q    = reinterpret_cast<const uint32_t*>(p);
+    const int       half = refStride >> 1;
+    const uint4     e0 = *reinterpret_cast<const uint4*>(q), o0 = *reinterpret_cast<const uint4*>(q + half);
+    const uint4     e1 = *reinterpret_cast<const uint4*>(q + 4), o1 = *reinterpret_cast<const uint4*>(q + half + 4);
+    px[0] = e0.x; px[1] = e0.y; px[2] = e0.z; px[3] = e0.w;
+    px[4] = o0.x; px[5] = o0.y; px[6] = o0.z; px[7] = o0.w;
+    px[8] = e1.x; px[9] = e1.y; px[10] = e1.z; px[11] = e1.w;
+    px[12] = o1.x; px[13] = o1.y; px[14] = o1.z; px[15] = o1.w;
+    return;
+  }
   const uint4    w0 = *reinterpret_cast<const uint4*>(p);
   const uint4    w1 = *reinterpret_cast<const uint4*>(p + 8);
   const uint32_t w[8] = { w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w };
@@ -153,7 +169,7 @@ __device__ __forceinline__ void load_org8(const uint32_t* p, uint32_t (&o)[8])
 
 // SS (subShiftMode 2, DY == 1 only): CUs with H > 8 and W <= 64 (16x16 .. 64x64) use 2 * SAD(even rows)
 // (RdCost.cpp:310-316, 489); accumulator set 0 then holds the even rows and set 1 the odd rows (8x8) / all rows.
-template <int NFP, bool FPU, int DY, bool SS>
+template <int NFP, bool FPU, int DY, bool SS, bool W32>
 __global__ void __launch_bounds__(kTreeMaxThreads, (DY == 2 || SS) ? 2 : 3) me_tree_sad_kernel(TreeParams p)
 {
   constexpr int NACC = SS ? 2 : DY;
@@ -297,6 +313,7 @@ __global__ void __launch_bounds__(kTreeMaxThreads, (DY == 2 || SS) ? 2 : 3) me_t
   }
 
   const int refStride = ngx * 8 + 32;   // samples per staged row
+  const int rs        = W32 ? 2 * refStride : refStride;   // the same in uint16 units of s_ref (W32: one word per sample)
   uint32_t* surf = p.surf + ((size_t) pair * p.g.nRegX * p.g.nRegY + region) * p.surfCap;
   uint32_t* surfEven = SS ? p.surfEven + ((size_t) pair * p.g.nRegX * p.g.nRegY + region) * p.surfCap : nullptr;
 
@@ -315,6 +332,13 @@ __global__ void __launch_bounds__(kTreeMaxThreads, (DY == 2 || SS) ? 2 : 3) me_t
       {
         const int r = i / vecPerRow, c = i - r * vecPerRow;
         uint4 v = *reinterpret_cast<const uint4*>(src + (ptrdiff_t) r * ref.stride + c * 8);
+        if (W32)
+        {
+          uint32_t* row = reinterpret_cast<uint32_t*>(s_ref) + r * refStride;
+          *reinterpret_cast<uint4*>(row + c * 4) = make_uint4(v.x & 0xffffu, v.x >> 16, v.y & 0xffffu, v.y >> 16);
+          *reinterpret_cast<uint4*>(row + (refStride >> 1) + c * 4) = make_uint4(v.z & 0xffffu, v.z >> 16, v.w & 0xffffu, v.w >> 16);
+          continue;
+        }
         v.x = pack12(v.x);
         v.y = pack12(v.y);
         v.z = pack12(v.z);
@@ -356,7 +380,7 @@ __global__ void __launch_bounds__(kTreeMaxThreads, (DY == 2 || SS) ? 2 : 3) me_t
       const int       row0 = band0 + tr * DY;          // displacement row index of this tile's first row
       const int       dx0 = wl8 + gx * 8;
       const bool      row1ok = DY == 2 && (tr * DY + 1 < bh);
-      const uint16_t* refTile = s_ref + tr * DY * refStride + gx * 8;
+      const uint16_t* refTile = s_ref + tr * DY * rs + gx * 8;
       uint32_t        a32[NACC][8];
 #pragma unroll
       for (int d = 0; d < NACC; d++)
@@ -378,7 +402,7 @@ __global__ void __launch_bounds__(kTreeMaxThreads, (DY == 2 || SS) ? 2 : 3) me_t
             if (!((mask8 >> slot) & 1)) continue;
             const int bx = (q & 1) * 16 + (s & 1) * 8, by = (q >> 1) * 16 + (s >> 1) * 8;
             const uint32_t* orgRow = s_org + by * 32 + bx;
-            const uint16_t* refRow = refTile + by * refStride + bx;
+            const uint16_t* refRow = refTile + by * rs + bx;
             uint32_t        a8[NACC][8];
 #pragma unroll
             for (int d = 0; d < NACC; d++)
@@ -403,7 +427,7 @@ __global__ void __launch_bounds__(kTreeMaxThreads, (DY == 2 || SS) ? 2 : 3) me_t
               {
                 uint32_t o[8], px[16];
                 load_org8(op, o);
-                load_ref16<false>(rp, px);
+                load_ref16<false, W32>(rp, px, refStride);
 #pragma unroll
                 for (int k = 0; k < 4; k++)
                   if (k < lastValid)
@@ -412,7 +436,7 @@ __global__ void __launch_bounds__(kTreeMaxThreads, (DY == 2 || SS) ? 2 : 3) me_t
                     for (int i = 0; i < 8; i++) a8[SS ? (r & 1) : 0][k] = __usad(o[i], px[i + k], a8[SS ? (r & 1) : 0][k]);
                   }
                 op += 32;
-                rp += refStride;
+                rp += rs;
               }
             }
             else if (DY == 1)
@@ -424,10 +448,10 @@ __global__ void __launch_bounds__(kTreeMaxThreads, (DY == 2 || SS) ? 2 : 3) me_t
               {
                 uint32_t o[8], px[16];
                 load_org8(op, o);
-                load_ref16<FPU>(rp, px);
+                load_ref16<FPU, W32>(rp, px, refStride);
                 sad_row<NFP>(a8[SS ? (r & 1) : 0], o, px);
                 op += 32;
-                rp += refStride;
+                rp += rs;
               }
             }
             else
@@ -438,7 +462,7 @@ __global__ void __launch_bounds__(kTreeMaxThreads, (DY == 2 || SS) ? 2 : 3) me_t
               for (int jr = 0; jr < 9; jr++)
               {
                 uint32_t o[8], px[16];
-                load_ref16<FPU>(refRow + jr * refStride, px);
+                load_ref16<FPU, W32>(refRow + jr * rs, px, refStride);
                 if (jr < 8)
                 {
                   load_org8(orgRow + jr * 32, o);
@@ -726,37 +750,66 @@ __global__ void __launch_bounds__(kUpperThreads) me_tree_upper_kernel(TreeParams
 
 }   // namespace
 
-size_t tree_sad_smem_bytes(int maxGx, int maxRows, int bandRows)
+// Tuning knobs (development): VTMME_TREE_VARIANT="nfp,fpu,dy,threads,w32,bandRows"
+static void tree_variant(int& nfp, int& fpu, int& dy, int& threads, int& w32, int& band)
 {
-  return (size_t) tree_off_ref(maxGx, maxRows) + (size_t) (bandRows + 1 + 31) * (size_t) (maxGx * 8 + 32) * 2;
-}
-
-// Tuning knobs (development): VTMME_TREE_VARIANT="nfp,fpu,dy,threads"
-static void tree_variant(int& nfp, int& fpu, int& dy, int& threads)
-{
-  static int v[4] = { -1, 0, 0, 0 };
+  static int v[6] = { -1, 0, 0, 0, 0, 0 };
   if (v[0] < 0)
   {
-    v[0] = 2; v[1] = 1; v[2] = 1; v[3] = 256;
-    if (const char* e = getenv("VTMME_TREE_VARIANT")) sscanf(e, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]);
+    v[0] = 2; v[1] = 1; v[2] = 1; v[3] = 256; v[4] = 1; v[5] = 0;
+    if (const char* e = getenv("VTMME_TREE_VARIANT")) sscanf(e, "%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]);
   }
-  nfp = v[0]; fpu = v[1]; dy = v[2]; threads = v[3];
+  nfp = v[0]; fpu = v[1]; dy = v[2]; threads = v[3]; w32 = v[4]; band = v[5];
 }
 
-template <int NFP, bool FPU, int DY, bool SS>
+bool tree_window_w32()
+{
+  int nfp, fpu, dy, threads, w32, band;
+  tree_variant(nfp, fpu, dy, threads, w32, band);
+  return w32 != 0 && dy == 1;
+}
+
+int tree_band_override()
+{
+  int nfp, fpu, dy, threads, w32, band;
+  tree_variant(nfp, fpu, dy, threads, w32, band);
+  return band;
+}
+
+// Displacement rows staged per band: the largest even split of the window whose staged rows, next to the tables, leave
+// room for 3 CTAs per SM (2 for the row-sub-sampling instantiation, which is register-limited to 2 anyway).
+int tree_pick_band_rows(int maxGx, int maxRows, bool subSampling)
+{
+  if (tree_band_override() > 0) return (tree_band_override() + 1) & ~1;
+  const long budget   = (subSampling ? 112L : 75L) * 1024 - tree_off_ref(maxGx, maxRows);
+  const long rowBytes = (long) (maxGx * 8 + 32) * (tree_window_w32() ? 4 : 2);
+  long       fit      = budget / rowBytes - 33;
+  if (fit < 16) fit = 16;
+  const int bands = (int) ((maxRows + fit - 1) / fit);
+  return ((maxRows + bands - 1) / bands + 1) & ~1;
+}
+
+size_t tree_sad_smem_bytes(int maxGx, int maxRows, int bandRows)
+{
+  return (size_t) tree_off_ref(maxGx, maxRows) +
+         (size_t) (bandRows + 1 + 31) * (size_t) (maxGx * 8 + 32) * (tree_window_w32() ? 4 : 2);
+}
+
+template <int NFP, bool FPU, int DY, bool SS, bool W32 = false>
 static cudaError_t launch_tree_sad_t(const TreeParams& p, int nPairs, int threads, size_t smem, cudaStream_t st)
 {
   static SmemOptIn optIn;
-  if (cudaError_t e = optIn.ensure(me_tree_sad_kernel<NFP, FPU, DY, SS>, smem)) return e;
+  if (cudaError_t e = optIn.ensure(me_tree_sad_kernel<NFP, FPU, DY, SS, W32>, smem)) return e;
   dim3 grid(p.g.nRegX * p.g.nRegY, nPairs, 1);
-  me_tree_sad_kernel<NFP, FPU, DY, SS><<<grid, threads, smem, st>>>(p);
+  me_tree_sad_kernel<NFP, FPU, DY, SS, W32><<<grid, threads, smem, st>>>(p);
   return cudaGetLastError();
 }
 
 cudaError_t launch_tree_sad(const TreeParams& p, int nPairs, cudaStream_t st)
 {
-  int nfp, fpu, dy, threads;
-  tree_variant(nfp, fpu, dy, threads);
+  int nfp, fpu, dy, threads, w32, band;
+  tree_variant(nfp, fpu, dy, threads, w32, band);
+  w32 = tree_window_w32();
   const size_t smem = tree_sad_smem_bytes(p.maxGx, p.maxRows, p.bandRows);
   if (threads <= 0)
   {
@@ -772,7 +825,16 @@ cudaError_t launch_tree_sad(const TreeParams& p, int nPairs, cudaStream_t st)
     const int ngx = (2 * p.sr + 1 + 7) / 8, tiles = ngx * (2 * p.sr + 1);
     int       thr = ((tiles + (tiles + 255) / 256 - 1) / ((tiles + 255) / 256) + 127) & ~127;
     thr           = thr > kTreeMaxThreads ? kTreeMaxThreads : (thr < 128 ? 128 : thr);
+    if (w32) return launch_tree_sad_t<2, true, 1, true, true>(p, nPairs, thr, smem, st);
     return launch_tree_sad_t<2, true, 1, true>(p, nPairs, thr, smem, st);
+  }
+  if (w32)
+  {
+    if (nfp == 0) return launch_tree_sad_t<0, true, 1, false, true>(p, nPairs, threads, smem, st);
+    if (nfp == 1) return launch_tree_sad_t<1, true, 1, false, true>(p, nPairs, threads, smem, st);
+    if (nfp == 2) return launch_tree_sad_t<2, true, 1, false, true>(p, nPairs, threads, smem, st);
+    if (nfp == 3) return launch_tree_sad_t<3, true, 1, false, true>(p, nPairs, threads, smem, st);
+    return cudaErrorInvalidValue;
   }
 #define VTMME_TREE_CASE(N, F, D) \
   if (nfp == N && fpu == F && dy == D) return launch_tree_sad_t<N, F != 0, D, false>(p, nPairs, threads, smem, st);

@@ -372,10 +372,7 @@ int vtmme_search_frames_device(vtmme_ctx* ctx, int nPairs, const int32_t* curPic
   // staging-pad and filter-tap reads stay inside VTMME_MIN_MARGIN whatever the search range is.
   if (prm->ctuSize < 8 || prm->ctuSize > 128)
     return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search_frames", "ctuSize must be in [8,128]");
-  // rows per band: keep the staged window under ~100 KB so two CTAs fit one SM
-  int bandRows = maxRows;
-  while (bandRows > 16 && tree_sad_smem_bytes(maxGx, maxRows, bandRows) > 100 * 1024) bandRows = (bandRows + 1) / 2;
-  bandRows = (bandRows + 1) & ~1;
+  const int bandRows = tree_pick_band_rows(maxGx, maxRows, prm->subShiftMode == 2);
   const size_t surfCap = (size_t) maxGx * 8 * maxRows;
 
   int rc;
