@@ -24,6 +24,10 @@ namespace vtmme {
 namespace {
 
 constexpr int kTreeMaxThreads = 256;
+#ifndef VTMME_ROW_UNROLL
+#define VTMME_ROW_UNROLL 4
+#endif
+constexpr int kRowUnroll = VTMME_ROW_UNROLL;   // rows of an 8x8 block per loop trip in the hot loop
 constexpr int kSlots          = 23;   // 16 8x8 + 4 16x16 + 1 32x32 (+ the 64x64 and 128x128 ancestors, window only)
 constexpr int kCheckSlots     = 21;   // CUs this kernel keeps an argmin for
 
@@ -443,7 +447,7 @@ __global__ void __launch_bounds__(kTreeMaxThreads, (DY == 2 || SS) ? 2 : 3) me_t
             {
               const uint32_t* op = orgRow;
               const uint16_t* rp = refRow;
-#pragma unroll 2
+#pragma unroll kRowUnroll
               for (int r = 0; r < 8; r++)
               {
                 uint32_t o[8], px[16];
