@@ -78,6 +78,10 @@ __host__ __device__ inline int frame_items_small(const FrameGeom& g) { return g.
 
 // Nine candidate distortions of one CW x CW chunk (8x8 tiles) around quarter-pel offset (cqx,cqy) with step
 // `step`, accumulated into sm.acc[0..8].  One warp.
+// The reference narrows every filter output to Pel (int16).  With reference samples in [0, 2^bd) the narrowing never
+// changes a value here, so it is not spelled out (one PRMT per sample saved): the first stage gives
+// (sum - (8192 << shift)) >> shift with sum in [-24, 88] * (2^bd - 1), i.e. within +-14330 for bd = 8..10, and the second
+// ((sum + offset) >> shift) stays within [-1055, 2079] before the clip.
 template <bool HAD, int CW>
 __device__ __forceinline__ void item_stage(ItemSmem& sm, const int16_t* __restrict__ org, int orgStride,
                                            const int16_t* __restrict__ refAtMv, int refStride, int cqx, int cqy, int step,
@@ -128,7 +132,7 @@ __device__ __forceinline__ void item_stage(ItemSmem& sm, const int16_t* __restri
         for (int c = 0; c < cw; c++)
         {
           const int v0 = ix ? s[c + 3] : s[c + 4];
-          dst[c]       = (int16_t) ((int16_t) (v0 << hr) - (int16_t) 8192);
+          dst[c]       = (v0 << hr) - 8192;
         }
       }
       else
@@ -143,7 +147,7 @@ __device__ __forceinline__ void item_stage(ItemSmem& sm, const int16_t* __restri
           int sum = 0;
 #pragma unroll
           for (int k = 0; k < 8; k++) sum += (ix ? s[c + k] : s[c + k + 1]) * cf[k];
-          dst[c] = (int16_t) ((sum - off) >> shift);
+          dst[c] = (sum - off) >> shift;
         }
       }
     }
@@ -171,7 +175,7 @@ __device__ __forceinline__ void item_stage(ItemSmem& sm, const int16_t* __restri
 #pragma unroll
       for (int i = 0; i < 8; i++)
       {
-        const int v = (int16_t) ((s[i] + 8192 + (1 << (hr - 1))) >> hr);
+        const int v = (s[i] + 8192 + (1 << (hr - 1))) >> hr;
         d[i]        = min(max(v, 0), maxv);
       }
     }
@@ -194,7 +198,7 @@ __device__ __forceinline__ void item_stage(ItemSmem& sm, const int16_t* __restri
 #pragma unroll
       for (int i = 0; i < 8; i++)
       {
-        const int v = (int16_t) ((sum[i] + offset) >> shift);
+        const int v = (sum[i] + offset) >> shift;
         d[i]        = min(max(v, 0), maxv);
       }
     }
