@@ -588,6 +588,8 @@ __global__ void __launch_bounds__(kTreeMaxThreads, (DY == 2 || SS) ? 2 : 3) me_t
 // ---- 64x64 and 128x128 levels from the 32x32 surfaces ----------------------------------------------------
 constexpr int kUpperThreads = 256;
 
+// TWO: subShiftMode 2 (a second, even-row surface feeds the 64x64 level).
+template <bool TWO>
 __global__ void __launch_bounds__(kUpperThreads) me_tree_upper_kernel(TreeParams p)
 {
   extern __shared__ __align__(16) unsigned char usmem[];
@@ -641,7 +643,7 @@ __global__ void __launch_bounds__(kUpperThreads) me_tree_upper_kernel(TreeParams
       const size_t r = (size_t) pair * nReg + ry * p.g.nRegX + rx;
       info = p.regInfo[r];
       sp   = p.surf + r * p.surfCap;
-      se   = p.subShiftMode == 2 ? p.surfEven + r * p.surfCap : sp;
+      se   = TWO ? p.surfEven + r * p.surfCap : sp;
     }
     s_reg[i]   = info;
     s_surf[i]  = sp;
@@ -706,7 +708,6 @@ __global__ void __launch_bounds__(kUpperThreads) me_tree_upper_kernel(TreeParams
     }
     if (!any) continue;
     // s64: what the 64x64 CUs compare (even rows x2 in subShiftMode 2); s64f: all rows, summed into the 128x128 CU
-    const bool twoSurf = p.subShiftMode == 2;
     uint32_t   s64[4], s64f[4];
 #pragma unroll
     for (int j = 0; j < 4; j++)
@@ -724,7 +725,7 @@ __global__ void __launch_bounds__(kUpperThreads) me_tree_upper_kernel(TreeParams
             const size_t o = (size_t) (dy - info.y) * (info.z * 8) + (dx - info.x);
             const uint32_t f = s_surf[ri][o];
             s64f[j] += f;
-            s64[j] += twoSurf ? s_surfE[ri][o] : f;
+            if (TWO) s64[j] += s_surfE[ri][o];
           }
         }
       }
@@ -732,7 +733,7 @@ __global__ void __launch_bounds__(kUpperThreads) me_tree_upper_kernel(TreeParams
 #pragma unroll
     for (int s = 0; s < 5; s++)
     {
-      const uint32_t sad  = s < 4 ? s64[s] : s64f[0] + s64f[1] + s64f[2] + s64f[3];
+      const uint32_t sad  = s < 4 ? (TWO ? s64[s] : s64f[s]) : s64f[0] + s64f[1] + s64f[2] + s64f[3];
       const uint32_t cost = sad + s_lut[bits[s]];   // >= 0x3fffffff outside the window
       const unsigned long long k = make_key(cost, dx, dy);
       if (cost < kLutInvalid && k < best[s]) best[s] = k;
@@ -854,7 +855,10 @@ cudaError_t launch_tree_upper(const TreeParams& p, int nPairs, cudaStream_t st)
   dim3 grid(p.g.nCtuX * p.g.nCtuY, nPairs, 4);
   // dynamic shared memory: rate tables over the bounding box of the CTU's five windows
   const size_t smem = (size_t) 5 * 2 * (p.maxGx * 8 + 8 + p.maxRows + 8);
-  me_tree_upper_kernel<<<grid, kUpperThreads, smem, st>>>(p);
+  if (p.subShiftMode == 2)
+    me_tree_upper_kernel<true><<<grid, kUpperThreads, smem, st>>>(p);
+  else
+    me_tree_upper_kernel<false><<<grid, kUpperThreads, smem, st>>>(p);
   return cudaGetLastError();
 }
 
