@@ -23,7 +23,12 @@ namespace vtmme {
 
 namespace {
 
-constexpr int kTreeMaxThreads = 256;
+#ifndef VTMME_TREE_THREADS
+#define VTMME_TREE_THREADS 256
+#define VTMME_TREE_MINBLOCKS 3
+#endif
+constexpr int kTreeMaxThreads = VTMME_TREE_THREADS;
+constexpr int kTreeMinBlocks  = VTMME_TREE_MINBLOCKS;   // CTAs per SM the register allocation must allow
 #ifndef VTMME_ROW_UNROLL
 #define VTMME_ROW_UNROLL 4
 #endif
@@ -174,7 +179,7 @@ __device__ __forceinline__ void load_org8(const uint32_t* p, uint32_t (&o)[8])
 // SS (subShiftMode 2, DY == 1 only): CUs with H > 8 and W <= 64 (16x16 .. 64x64) use 2 * SAD(even rows)
 // (RdCost.cpp:310-316, 489); accumulator set 0 then holds the even rows and set 1 the odd rows (8x8) / all rows.
 template <int NFP, bool FPU, int DY, bool SS, bool W32>
-__global__ void __launch_bounds__(kTreeMaxThreads, (DY == 2 || SS) ? 2 : 3) me_tree_sad_kernel(TreeParams p)
+__global__ void __launch_bounds__(kTreeMaxThreads, (DY == 2 || SS) ? 2 : kTreeMinBlocks) me_tree_sad_kernel(TreeParams p)
 {
   constexpr int NACC = SS ? 2 : DY;
   extern __shared__ __align__(16) unsigned char smem[];
