@@ -17,6 +17,7 @@
  *     (InterpolationFilter.h:96-98, InterpolationFilter.cpp:749-895)
  *   InterSearch::xPatternSearch + xPatternSearchFracDIF             vtmme_search          (per-call jobs)
  *     (EncoderLib/InterSearch.cpp:3566-3608, 4284-4339)             vtmme_search_frames   (batched, per CTU tree)
+ *   InterSearch::xPatternSearchIntRefine (:4172-4282)               vtmme_search with fracMode 2 + vtmme_amvr
  *   InterPrediction::xPredInterBlk (CommonLib/InterPrediction.cpp   vtmme_mc_batch / vtmme_mc_host
  *     :660-830), AreaBuf::addAvg (Buffer.cpp:467-507),              vtmme_add_avg
  *     AreaBuf::removeHighFreq (Buffer.h:474-517)                    vtmme_remove_high_freq
@@ -78,9 +79,26 @@ int vtmme_upload_picture_device(vtmme_ctx* ctx, int picId, const int16_t* dOrigi
 int vtmme_release_picture(vtmme_ctx* ctx, int picId);
 
 /* ---- per-call motion search ------------------------------------------------------------------
- * One job = one InterSearch::xMotionEstimation call's integer search + fractional refinement:
+ * One job = one InterSearch::xMotionEstimation call's integer search + refinement:
  * xPatternSearch over searchRange (InterSearch.cpp:3566-3608), then the body of
- * xPatternSearchFracDIF (:4296-4338).  Field meaning follows IntTZSearchStruct / DistParam.      */
+ * xPatternSearchFracDIF (:4296-4338) for quarter / half-pel CUs, or xPatternSearchIntRefine
+ * (:4172-4282) for integer / 4-pel AMVR CUs.  Field meaning follows IntTZSearchStruct / DistParam. */
+/* State of an integer-pel / 4-pel AMVR call (cu.imv = IMV_FPEL / IMV_4PEL): what
+ * InterSearch::xPatternSearchIntRefine (InterSearch.cpp:4172-4282) receives besides the search result.
+ * MVs in 1/16 sample (MV_PRECISION_INTERNAL). */
+typedef struct
+{
+  int32_t  imv;            /* cu.imv: 1 IMV_FPEL, 2 IMV_4PEL                                           */
+  int32_t  numCand;        /* amvpInfo.numCand, 1 or 2                                                 */
+  int32_t  candX[2], candY[2]; /* amvpInfo.mvCand[]                                                    */
+  int32_t  mvpIdx;         /* riMVPIdx on entry (mvCand[mvpIdx] == rcMvPred)                           */
+  uint32_t mvpIdxBits[2];  /* m_auiMVPIdxCost[i][AMVP_MAX_NUM_CANDS]                                   */
+  uint32_t bits;           /* ruiBits on entry                                                         */
+  int32_t  picW, picH;     /* pps.getPicWidth/HeightInLumaSamples (clipMvInPic, Mv.cpp:53-71)          */
+  int32_t  maxCuW, maxCuH; /* sps.getMaxCUWidth/Height, <= 128                                         */
+  double   fWeight;        /* xGetMEDistortionWeight (InterSearch.cpp:7666-7676)                       */
+} vtmme_amvr;
+
 typedef struct
 {
   int32_t        curPic;       /* picture holding the original block; ignored when org != NULL        */
@@ -95,8 +113,10 @@ typedef struct
   int32_t        bitDepth;     /* <= 10 (larger falls outside the SIMD tables too: RdCostX86.h:213)    */
   int32_t        useHad;       /* HadamardME && !DisableSATDForRD                                      */
   int32_t        useAltHpel;   /* cStruct.useAltHpelIf                                                 */
-  int32_t        fracMode;     /* 0: integer only; 1: xPatternSearchFracDIF body                       */
+  int32_t        fracMode;     /* 0: integer only; 1: xPatternSearchFracDIF body; 2: the search is     */
+                               /*   followed by xPatternSearchIntRefine on `amvr` (:3486-3489)         */
   double         lambdaMotion; /* RdCost::m_motionLambda                                               */
+  const vtmme_amvr* amvr;      /* HOST pointer, fracMode 2 only (else ignored, may be NULL)            */
 } vtmme_job;
 
 typedef struct
@@ -106,6 +126,11 @@ typedef struct
   int32_t  halfX, halfY;  /* rcMvHalf                                                                  */
   int32_t  qterX, qterY;  /* rcMvQter                                                                  */
   uint64_t fracCost;      /* ruiCost after xPatternSearchFracDIF                                       */
+  /* fracMode 2 only — outputs of xPatternSearchIntRefine: */
+  int32_t  amvrMvX, amvrMvY; /* rcMv, 1/16 sample                                                      */
+  int32_t  mvpIdx;        /* riMVPIdx (rcMvPred = mvCand[mvpIdx])                                      */
+  uint32_t bits;          /* ruiBits                                                                   */
+  uint64_t cost;          /* ruiCost                                                                   */
 } vtmme_result;
 
 int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_result* results);

@@ -64,7 +64,7 @@ def main():
         # locals, placed at the second "Do integer search" marker (the one inside xMotionEstimation)
         first = s.index("  //  Do integer search\n")
         second = s.index("  //  Do integer search\n", first + 1)
-        s = s[:second] + ("  vtmcuda::SearchOut cudaOut;   // libvtmme\n  bool cudaFracDone = false;\n") + s[second:]
+        s = s[:second] + ("  vtmcuda::SearchOut cudaOut;   // libvtmme\n  bool cudaFracDone = false;\n  bool cudaIntRefineDone = false;\n") + s[second:]
         s = once(s, "    xPatternSearch( cStruct, rcMv, ruiCost);\n", """\
     if( vtmcuda::enabled() && !m_cDistParam.applyWeight && m_lumaClpRng.bd <= 10 && !wrap
         && !pu.cu->slice->getRefPic( eRefPicList, iRefIdxPred )->isRefScaled( pu.cs->pps ) )
@@ -89,12 +89,39 @@ def main():
       in.bitDepth     = m_lumaClpRng.bd;
       in.useHad       = m_pcEncCfg->getUseHADME() && !pu.cs->slice->getDisableSATDForRD();
       in.useAltHpel   = cStruct.useAltHpelIf;
-      in.doFrac       = ( pu.cu->imv == 0 || pu.cu->imv == IMV_HPEL ) && !m_pcEncCfg->getMCTSEncConstraint();
+      in.doFrac       = 0;
+      if( !m_pcEncCfg->getMCTSEncConstraint() )
+      {
+        in.doFrac = ( pu.cu->imv == 0 || pu.cu->imv == IMV_HPEL ) ? 1 : 2;
+      }
       in.lambdaMotion = m_pcRdCost->getSelectedMotionLambda();
+      if( in.doFrac == 2 )   // integer / 4-pel AMVR: xPatternSearchIntRefine follows the search on the GPU too
+      {
+        in.imv     = pu.cu->imv;
+        in.numCand = amvpInfo.numCand;
+        for( int i = 0; i < 2; i++ )
+        {
+          in.candX[i]      = amvpInfo.mvCand[i].getHor();
+          in.candY[i]      = amvpInfo.mvCand[i].getVer();
+          in.mvpIdxBits[i] = m_auiMVPIdxCost[i][AMVP_MAX_NUM_CANDS];
+        }
+        in.mvpIdx  = riMVPIdx;
+        in.bits    = ruiBits;
+        in.picW    = pu.cs->pps->getPicWidthInLumaSamples();
+        in.picH    = pu.cs->pps->getPicHeightInLumaSamples();
+        in.maxCuW  = pu.cs->sps->getMaxCUWidth();
+        in.maxCuH  = pu.cs->sps->getMaxCUHeight();
+        in.fWeight = fWeight;
+        if( clipMv != clipMvInPic || pu.cs->sps->getWrapAroundEnabledFlag() )
+        {
+          in.doFrac = 0;   // sub-picture / wrap-around clipping: the refinement stays on the CPU
+        }
+      }
       vtmcuda::search( in, cudaOut );
       rcMv.set( cudaOut.mvX, cudaOut.mvY );
-      ruiCost      = cudaOut.intSad;
-      cudaFracDone = in.doFrac;
+      ruiCost          = cudaOut.intSad;
+      cudaFracDone     = in.doFrac == 1;
+      cudaIntRefineDone = in.doFrac == 2;
     }
     else
     {
@@ -111,6 +138,22 @@ def main():
     else
     {
       xPatternSearchFracDIF( pu, eRefPicList, iRefIdxPred, cStruct, rcMv, cMvHalf, cMvQter, ruiCost );
+    }
+""")
+        s = once(s, "    xPatternSearchIntRefine( pu, cStruct, rcMv, rcMvPred, riMVPIdx, ruiBits, ruiCost, amvpInfo, fWeight);\n", """\
+    if( cudaIntRefineDone )   // libvtmme: the GPU call above already ran xPatternSearchIntRefine
+    {
+      rcMv.set( cudaOut.amvrMvX, cudaOut.amvrMvY );
+      riMVPIdx = cudaOut.mvpIdx;
+      rcMvPred = amvpInfo.mvCand[riMVPIdx];
+      m_pcRdCost->setCostScale( 0 );
+      m_pcRdCost->setPredictor( rcMvPred );
+      ruiBits  = cudaOut.bits;
+      ruiCost  = cudaOut.cost;
+    }
+    else
+    {
+      xPatternSearchIntRefine( pu, cStruct, rcMv, rcMvPred, riMVPIdx, ruiBits, ruiCost, amvpInfo, fWeight);
     }
 """)
         return s

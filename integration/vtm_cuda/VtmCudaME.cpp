@@ -18,6 +18,7 @@ namespace
 vtmme_ctx* g_ctx        = nullptr;
 uint64_t   g_calls      = 0;
 uint64_t   g_uploads    = 0;
+uint64_t   g_intRefines = 0;   // searches whose xPatternSearchIntRefine ran on the GPU too
 double     g_searchSec  = 0;   // wall time spent inside vtmme_search (upload of the pattern, kernels, sync)
 int        g_nextPicId  = 1;
 
@@ -105,6 +106,27 @@ void search( const SearchIn& in, SearchOut& out )
   j.useAltHpel   = in.useAltHpel;
   j.fracMode     = in.doFrac;
   j.lambdaMotion = in.lambdaMotion;
+  vtmme_amvr a;
+  j.amvr = nullptr;
+  if( in.doFrac == 2 )
+  {
+    a.imv     = in.imv;
+    a.numCand = in.numCand;
+    for( int i = 0; i < 2; i++ )
+    {
+      a.candX[i]      = in.candX[i];
+      a.candY[i]      = in.candY[i];
+      a.mvpIdxBits[i] = in.mvpIdxBits[i];
+    }
+    a.mvpIdx  = in.mvpIdx;
+    a.bits    = in.bits;
+    a.picW    = in.picW;
+    a.picH    = in.picH;
+    a.maxCuW  = in.maxCuW;
+    a.maxCuH  = in.maxCuH;
+    a.fWeight = in.fWeight;
+    j.amvr    = &a;
+  }
   vtmme_result r;
   vtmme_ctx*   c  = ctx();
   const auto   t0 = std::chrono::steady_clock::now();
@@ -119,7 +141,13 @@ void search( const SearchIn& in, SearchOut& out )
   out.qterX    = r.qterX;
   out.qterY    = r.qterY;
   out.fracCost = r.fracCost;
+  out.amvrMvX  = r.amvrMvX;
+  out.amvrMvY  = r.amvrMvY;
+  out.mvpIdx   = r.mvpIdx;
+  out.bits     = r.bits;
+  out.cost     = r.cost;
   g_calls++;
+  if( in.doFrac == 2 ) g_intRefines++;
 }
 
 uint64_t distHost( int kind, const int16_t* org, int orgStride, const int16_t* cur, int curStride, int w, int h, int subShift )
@@ -150,9 +178,9 @@ void printStats()
 {
   if( g_ctx )
   {
-    fprintf( stderr, "[vtmcuda] GPU motion searches: %llu (%.1f s inside vtmme_search, %.1f us per call), reference pictures "
-                     "uploaded: %llu, kernel launches: %llu\n",
-             (unsigned long long) g_calls, g_searchSec, g_calls ? 1e6 * g_searchSec / g_calls : 0.0,
+    fprintf( stderr, "[vtmcuda] GPU motion searches: %llu (%llu with AMVR integer refinement; %.1f s inside vtmme_search, %.1f us per "
+                     "call), reference pictures uploaded: %llu, kernel launches: %llu\n",
+             (unsigned long long) g_calls, (unsigned long long) g_intRefines, g_searchSec, g_calls ? 1e6 * g_searchSec / g_calls : 0.0,
              (unsigned long long) g_uploads, (unsigned long long) vtmme_launch_count( g_ctx ) );
   }
 }

@@ -26,8 +26,14 @@ struct SearchIn
   int            imvShift;
   int            subShiftMode;  // cStruct.subShiftMode (0 or 2)
   int            bitDepth;
-  bool           useHad, useAltHpel, doFrac;
+  bool           useHad, useAltHpel;
+  int            doFrac;        // 0 integer search only, 1 + xPatternSearchFracDIF, 2 + xPatternSearchIntRefine (AMVR)
   double         lambdaMotion;
+  // doFrac == 2: what xPatternSearchIntRefine receives (InterSearch.cpp:4172), MVs in MV_PRECISION_INTERNAL
+  int            imv, numCand, candX[2], candY[2], mvpIdx;
+  uint32_t       mvpIdxBits[2], bits;
+  int            picW, picH, maxCuW, maxCuH;
+  double         fWeight;
 };
 
 struct SearchOut
@@ -36,6 +42,9 @@ struct SearchOut
   uint64_t intSad;
   int      halfX, halfY, qterX, qterY;
   uint64_t fracCost;
+  int      amvrMvX, amvrMvY, mvpIdx;   // doFrac == 2: rcMv (internal precision), riMVPIdx,
+  uint32_t bits;                       //   ruiBits,
+  uint64_t cost;                       //   ruiCost
 };
 
 // Runs one xMotionEstimation search on the GPU.  Any failure of the CUDA path is fatal (THROW): there is no

@@ -37,6 +37,18 @@ class Result(C.Structure):
         return (self.mvX, self.mvY, self.intSad, self.halfX, self.halfY, self.qterX, self.qterY, self.fracCost)
 
 
+class IntRefine(C.Structure):
+    """vo_int_refine_io / RefIntRefine (identical layout): xPatternSearchIntRefine's in/out state."""
+    _fields_ = [("imv", C.c_int), ("mvX", C.c_int), ("mvY", C.c_int), ("numCand", C.c_int),
+                ("candX", C.c_int * 2), ("candY", C.c_int * 2), ("mvpIdx", C.c_int),
+                ("mvpIdxBits", C.c_uint32 * 2), ("bits", C.c_uint32), ("fWeight", C.c_double),
+                ("posX", C.c_int), ("posY", C.c_int), ("picW", C.c_int), ("picH", C.c_int),
+                ("maxCuW", C.c_int), ("maxCuH", C.c_int), ("cost", C.c_uint64)]
+
+    def tuple(self):
+        return (self.mvX, self.mvY, self.mvpIdx, self.bits, self.cost)
+
+
 def build_oracle():
     subprocess.check_call(["make", "-s", "-f", "oracle/Makefile"], cwd=ROOT)
 
@@ -78,6 +90,7 @@ def oracle():
         L.vo_pred_qpel.argtypes = [C.POINTER(Job), _I, _I, _I, _I, _I, _P, _I]
         L.vo_me_finish.argtypes = [C.POINTER(Job), C.POINTER(Result), C.c_double, C.c_uint32,
                                    C.POINTER(_I), C.POINTER(_I), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+        L.vo_int_refine.argtypes = [C.POINTER(Job), C.POINTER(IntRefine)]
         L.vo_mc_block.argtypes = [_I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I]
         L.vo_add_avg.argtypes = [_P, _P, _P, _I, _I]
         L.vo_remove_high_freq.argtypes = [_P, _P, _I, _I, _I]
@@ -109,6 +122,7 @@ def ref():
         L.ref_dist_batch.argtypes = [_P, _P, _I, _I, _I, _I, _I, _I, _P]
         L.ref_filter_batch.restype = C.c_double
         L.ref_filter_batch.argtypes = [_I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I]
+        L.ref_int_refine.argtypes = [C.POINTER(Job), C.POINTER(IntRefine)]
         L.ref_mc_blocks.argtypes = [_I, _P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, C.POINTER(C.c_double)]
         L.ref_add_avg.argtypes = [_P, _P, _P, _I, _I, _I]
         L.ref_remove_high_freq.argtypes = [_P, _I, _P, _I, _I, _I, _I, _I]

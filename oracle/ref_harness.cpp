@@ -335,6 +335,77 @@ void ref_add_avg(const int16_t* s0, const int16_t* s1, int16_t* dst, int w, int 
   d.addAvg(a, b, makeClp(bd));
 }
 
+// ---- InterSearch::xPatternSearchIntRefine (InterSearch.cpp:4172-4282), the reference's own member -----------------
+// Same layout as vo_int_refine_io (oracle/vtm_oracle.h).
+struct RefIntRefine
+{
+  int      imv;
+  int      mvX, mvY;
+  int      numCand;
+  int      candX[2], candY[2];
+  int      mvpIdx;
+  uint32_t mvpIdxBits[2];
+  uint32_t bits;
+  double   fWeight;
+  int      posX, posY, picW, picH, maxCuW, maxCuH;
+  uint64_t cost;
+};
+
+void ref_int_refine(const RefSearchJob* j, RefIntRefine* io)
+{
+  Probe& p = probe();
+  p.rd.m_motionLambda = j->lambdaMotion;
+  p.cfg.setUseHADME(j->useHad != 0);
+  p.cfg.setMCTSEncConstraint(false);
+  p.m_lumaClpRng = makeClp(j->bitDepth);
+  clipMv = clipMvInPic;   // EncGOP.cpp:2766
+
+  PPS pps;
+  pps.setPicWidthInLumaSamples(io->picW);
+  pps.setPicHeightInLumaSamples(io->picH);
+  SPS sps;
+  sps.setMaxCUWidth(io->maxCuW);
+  sps.setMaxCUHeight(io->maxCuH);
+  sps.setWrapAroundEnabledFlag(false);
+  Slice slice;
+  slice.setDisableSATDForRD(false);
+  std::vector<uint64_t> shell((sizeof(CodingStructure) + 7) / 8, 0);
+  CodingStructure* cs = reinterpret_cast<CodingStructure*>(shell.data());
+  cs->sps   = &sps;
+  cs->pps   = &pps;
+  cs->slice = &slice;
+  CodingUnit cu(CHROMA_420, Area(io->posX, io->posY, j->w, j->h));
+  cu.imv    = io->imv;
+  cu.affine = false;
+  PredictionUnit pu(CHROMA_420, Area(io->posX, io->posY, j->w, j->h));
+  pu.cu = &cu;
+  pu.cs = cs;
+
+  CPelBuf pattern(j->org, j->orgStride, j->w, j->h);
+  InterSearch::IntTZSearchStruct st;
+  memset(&st, 0, sizeof(st));
+  st.pcPatternKey = &pattern;
+  st.piRefY       = j->refAtPU;
+  st.iRefStride   = j->refStride;
+
+  AMVPInfo amvp;
+  amvp.numCand = io->numCand;
+  for (int i = 0; i < 2; i++) amvp.mvCand[i] = Mv(io->candX[i], io->candY[i]);
+  for (int i = 0; i < 2; i++) p.m_auiMVPIdxCost[i][AMVP_MAX_NUM_CANDS] = io->mvpIdxBits[i];
+
+  Mv         mv(io->mvX, io->mvY);
+  Mv         pred = amvp.mvCand[io->mvpIdx];
+  int        idx  = io->mvpIdx;
+  uint32_t   bits = io->bits;
+  Distortion cost = 0;
+  p.xPatternSearchIntRefine(pu, st, mv, pred, idx, bits, cost, amvp, io->fWeight);
+  io->mvX    = mv.hor;
+  io->mvY    = mv.ver;
+  io->mvpIdx = idx;
+  io->bits   = bits;
+  io->cost   = cost;
+}
+
 // Batch driver used as the CPU baseline: nThreads workers over disjoint job ranges.
 // Returns wall seconds spent in the searches (steady_clock around the work only).
 double ref_search_batch(const RefSearchJob* jobs, RefSearchResult* res, int n, int nThreads)

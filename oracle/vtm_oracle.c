@@ -694,3 +694,83 @@ void vo_me_finish(const vo_job* j, const vo_result* r, double fWeight, uint32_t 
   *costOut = (uint64_t) (floor(fWeight * ((double) r->fracCost - (double) vo_mv_cost(j->lambdaMotion, mvBits))) +
                          (double) vo_mv_cost(j->lambdaMotion, bits));
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Integer / 4-pel AMVR refinement
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Mv::changePrecision — CommonLib/Mv.h:183-197: left shift, or right shift rounding to nearest, ties toward zero */
+static int vo_change_prec(int v, int shift)
+{
+  if (shift >= 0) return v * (1 << shift);
+  {
+    const int rs = -shift, off = 1 << (rs - 1);
+    return v >= 0 ? (v + off - 1) >> rs : (v + off) >> rs;
+  }
+}
+
+/* InterSearch::xPatternSearchIntRefine — EncoderLib/InterSearch.cpp:4172-4282 (no MCTS constraint).
+ * j supplies the pattern, the reference plane at the PU position, bit depth, useHad and lambda; subShift is 0
+ * (setDistParam(..., 0, 1, useHad), :4179). */
+void vo_int_refine(const vo_job* j, vo_int_refine_io* io)
+{
+  static const int testPos[9][2] = { { 0, 0 }, { -1, -1 }, { -1, 0 }, { -1, 1 }, { 0, -1 }, { 0, 1 }, { 1, -1 }, { 1, 0 }, { 1, 1 } };
+  /* Mv::m_amvrPrecision (Mv.cpp:41): imv 1 -> MV_PRECISION_INT (2), imv 2 -> MV_PRECISION_4PEL (0); internal = 6 */
+  const int prec  = io->imv == 1 ? 2 : 0;
+  const int down  = prec - 6, up = 6 - prec;
+  uint64_t  dist, satd = 0, bestDist = UINT64_MAX;
+  uint32_t  bits = io->bits - io->mvpIdxBits[io->mvpIdx]; /* :4188 */
+  int       bestX = io->mvX, bestY = io->mvY, bestBits = 0, bestIdx = io->mvpIdx;
+  int       baseX[2], baseY[2], testX[2] = { 0, 0 }, testY[2] = { 0, 0 };
+  int       pos, i;
+  for (i = 0; i < 2; i++) /* cBaseMvd[i] = roundTransPrecInternal2Amvr(rcMv - mvCand[i]), :4198-4204 */
+  {
+    baseX[i] = vo_change_prec(vo_change_prec(io->mvX - io->candX[i], down), up);
+    baseY[i] = vo_change_prec(vo_change_prec(io->mvY - io->candY[i], down), up);
+  }
+  for (pos = 0; pos < 9; pos++)
+    for (i = 0; i < io->numCand; i++)
+    {
+      int      mvBits, px, py, mx, my;
+      testX[i] = vo_change_prec(testPos[pos][0], up) + baseX[i] + io->candX[i]; /* :4214-4217 */
+      testY[i] = vo_change_prec(testPos[pos][1], up) + baseY[i] + io->candY[i];
+      if (i == 0 || testX[0] != testX[1] || testY[0] != testY[1])
+      {
+        int cx = testX[i], cy = testY[i];
+        vo_clip_mv(&cx, &cy, io->posX, io->posY, io->picW, io->picH, io->maxCuW, io->maxCuH); /* :4237 */
+        {
+          const vo_pel* cur = j->refAtPU + (ptrdiff_t) j->refStride * (cy >> 4) + (cx >> 4);
+          dist = satd = (uint64_t) ((double) vo_dist(j, cur, j->refStride) * io->fWeight); /* :4240 */
+        }
+      }
+      else
+        dist = satd;
+      mvBits = (int) io->mvpIdxBits[i];
+      px     = vo_change_prec(io->candX[i], down);
+      py     = vo_change_prec(io->candY[i], down);
+      mx     = vo_change_prec(testX[i], down);
+      my     = vo_change_prec(testY[i], down);
+      mvBits += (int) vo_mv_bits(mx, my, px, py, 0, 0);
+      dist += vo_mv_cost(j->lambdaMotion, (uint32_t) mvBits);
+      if (dist < bestDist)
+      {
+        bestDist = dist;
+        bestX    = testX[i];
+        bestY    = testY[i];
+        bestIdx  = i;
+        bestBits = mvBits;
+      }
+    }
+  if (bestDist == UINT64_MAX)
+  {
+    io->bits = bits;
+    io->cost = UINT64_MAX;
+    return;
+  }
+  io->mvX    = bestX;
+  io->mvY    = bestY;
+  io->mvpIdx = bestIdx;
+  bits += (uint32_t) bestBits;
+  io->bits = bits;
+  io->cost = bestDist - vo_mv_cost(j->lambdaMotion, (uint32_t) bestBits) + vo_mv_cost(j->lambdaMotion, bits); /* :4276 */
+}

@@ -91,6 +91,23 @@ void vo_remove_high_freq(vo_pel* dst, const vo_pel* src, int n, int clip, int bd
 void vo_me_finish(const vo_job* j, const vo_result* r, double fWeight, uint32_t bitsIn, int* mvQx, int* mvQy,
                   uint32_t* bitsOut, uint64_t* costOut);
 
+/* Integer-pel / 4-pel AMVR refinement, InterSearch::xPatternSearchIntRefine (InterSearch.cpp:4172-4282).
+ * Same field layout as RefIntRefine in oracle/ref_harness.cpp.  MVs in 1/16 sample (MV_PRECISION_INTERNAL). */
+typedef struct
+{
+  int      imv;            /* cu.imv: 1 IMV_FPEL, 2 IMV_4PEL                                            */
+  int      mvX, mvY;       /* in: rcMv (integer-pel precise); out: refined MV                            */
+  int      numCand;        /* amvpInfo.numCand (1 or 2)                                                  */
+  int      candX[2], candY[2]; /* amvpInfo.mvCand[] (already rounded to the AMVR precision)              */
+  int      mvpIdx;         /* in/out riMVPIdx                                                            */
+  uint32_t mvpIdxBits[2];  /* m_auiMVPIdxCost[i][AMVP_MAX_NUM_CANDS]                                     */
+  uint32_t bits;           /* in/out ruiBits                                                             */
+  double   fWeight;        /* xGetMEDistortionWeight                                                     */
+  int      posX, posY, picW, picH, maxCuW, maxCuH; /* clipMv (clipMvInPic) arguments                    */
+  uint64_t cost;           /* out ruiCost                                                                */
+} vo_int_refine_io;
+void vo_int_refine(const vo_job* j, vo_int_refine_io* io);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,3 +90,39 @@ def oracle_mc(L, comp, padded, margin, blocks, bi=0, bit_depth=10, alt=0):
                       alt, B.ptr(d), w)
         parts.append(d.ravel())
     return np.concatenate(parts)
+
+
+# ---- integer / 4-pel AMVR refinement ---------------------------------------------------------------------------------
+def round_amvr(v, imv):
+    """Mv::roundTransPrecInternal2Amvr (Mv.h:216-219) on one component."""
+    rs = 4 if imv == 1 else 6
+    off = 1 << (rs - 1)
+    q = (v + off - 1) >> rs if v >= 0 else (v + off) >> rs
+    return q << rs
+
+
+def int_refine_case(rng, imv, x, y, w, h, pic_w, pic_h, max_pel=24):
+    """Random state of one xPatternSearchIntRefine call: integer-pel MV, two AMVP candidates rounded to the AMVR
+    precision, MVP index bits and incoming ruiBits."""
+    mv = [int(rng.integers(-max_pel, max_pel + 1)) * 16 for _ in range(2)]
+    cands = [[round_amvr(int(m + rng.integers(-80, 81)), imv) for m in mv] for _ in range(2)]
+    if rng.integers(0, 4) == 0:
+        cands[1] = list(cands[0])
+    num = 2 if rng.integers(0, 5) else 1
+    idx = int(rng.integers(0, num))
+    idx_bits = [1, 1] if num == 2 else [0, 0]
+    io = B.IntRefine()
+    io.imv, io.mvX, io.mvY, io.numCand, io.mvpIdx = imv, mv[0], mv[1], num, idx
+    for i in range(2):
+        io.candX[i], io.candY[i] = cands[i]
+        io.mvpIdxBits[i] = idx_bits[i]
+    io.bits = int(rng.integers(3, 12)) + idx_bits[idx]
+    io.fWeight = float(rng.choice([1.0, 0.5, 0.375, 0.625]))
+    io.posX, io.posY, io.picW, io.picH, io.maxCuW, io.maxCuH = x, y, pic_w, pic_h, 128, 128
+    return io
+
+
+def clone_int_refine(io):
+    c = B.IntRefine()
+    C.memmove(C.byref(c), C.byref(io), C.sizeof(io))
+    return c

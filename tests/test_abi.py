@@ -54,3 +54,27 @@ def test_frame_cu_layout():
     from vtm_b200.me import frame_cu_layout
     n, off = frame_cu_layout(1920, 1080)
     assert n == 43020 and off == [0, 32400, 40440, 42420, 42900, 43020]
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors (vtm_b200/lib.py) have the size and field offsets the C compiler gives include/vtmme.h."""
+    import ctypes as C
+    import subprocess
+    from vtm_b200 import lib
+    pairs = {"vtmme_job": lib.CJob, "vtmme_result": lib.CResult, "vtmme_amvr": lib.CAmvr,
+             "vtmme_frame_params": lib.CFrameParams, "vtmme_mc_block": lib.CMcBlock, "vtmme_cand_job": lib.CCandJob}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "vtmme.h"', 'int main(void){']
+    for cname, cls in pairs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for f in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, f[0], cname, f[0]))
+    lines.append('return 0;}')
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)]).decode().splitlines())
+    for cname, cls in pairs.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for f in cls._fields_:
+            assert int(got["%s.%s" % (cname, f[0])]) == getattr(cls, f[0]).offset, (cname, f[0])

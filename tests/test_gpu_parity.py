@@ -161,6 +161,65 @@ def test_job_search_integer_amvr(ms, oracle_lib):
     assert [ms.search([j])[0] for j in jobs] == want   # single-launch path of the small patterns
 
 
+def test_job_search_int_refine(ms, oracle_lib):
+    """fracMode 2: the integer search followed by xPatternSearchIntRefine (InterSearch.cpp:4172-4282) — FPEL and
+    4PEL AMVR, SATD and SAD, one or two AMVP candidates, bi-pred weights and patterns, border clipping; batched call,
+    single-launch path (patterns <= 32x32) and the multi-CTA path of larger patterns."""
+    from tests.helpers import int_refine_case
+    from vtm_b200 import Amvr, Job
+    rng = np.random.default_rng(79)
+    W, H = 256, 192
+    ref = np.clip(np.rint(rng.normal(512, 200, (H, W))), 0, 1023).astype(np.int16)
+    cur = np.clip(np.roll(ref, (2, -3), (0, 1)).astype(np.int32) + np.rint(rng.normal(0, 6, ref.shape)).astype(np.int32), 0, 1023)
+    cur = np.ascontiguousarray(cur.astype(np.int16))
+    refp = pad_plane(ref)
+    ms.upload_picture(14, cur)
+    ms.upload_picture(15, refp, MARGIN)
+    stride = refp.shape[1]
+    jobs, want, keep = [], [], []
+    for w in SIZES:
+        for h in SIZES:
+            if w == 4 and h == 4:
+                continue
+            for variant in range(4):
+                imv = 1 + (variant & 1)
+                use_had = 0 if variant == 3 else 1
+                # positions at the picture border too, so that clipMv matters for the probes
+                x = [0, W - w][variant & 1] if variant >= 2 else int(rng.integers(0, (W - w) // 4 + 1)) * 4
+                y = [0, H - h][(variant >> 1) & 1] if variant >= 2 else int(rng.integers(0, (H - h) // 4 + 1)) * 4
+                sr = int(rng.integers(3, 12))
+                lam = float(rng.uniform(4, 60))
+                io = int_refine_case(rng, imv, x, y, w, h, W, H, max_pel=6)
+                pred16 = (io.candX[io.mvpIdx], io.candY[io.mvpIdx])
+                # xMotionEstimation: predictor INTERNAL -> QUARTER (InterSearch.cpp:3370-3372), window around it
+                pq = tuple((v + 1) >> 2 if v >= 0 else (v + 2) >> 2 for v in pred16)
+                win = oracle_window(oracle_lib, pq, x, y, W, H, sr)
+                imv_shift = imv << 1
+                org = None
+                if variant == 1:
+                    org = (2 * cur[y:y + h, x:x + w].astype(np.int32) - rng.integers(0, 1024, (h, w))).astype(np.int16)
+                    org = np.ascontiguousarray(org)
+                    keep.append(org)
+                am = Amvr(imv, ((io.candX[0], io.candY[0]), (io.candX[1], io.candY[1])), io.numCand, io.mvpIdx,
+                          (io.mvpIdxBits[0], io.mvpIdxBits[1]), io.bits, W, H, io.fWeight)
+                jobs.append(Job(14, 15, x, y, w, h, win, pq, imv_shift, 0, 10, use_had, 0, 2, lam, org, am))
+                o_arr, o_off, o_stride = (cur, y * W + x, W) if org is None else (org, 0, w)
+                oj = B.make_job(o_arr, refp, stride, (MARGIN + y) * stride + MARGIN + x, w, h, win, pq, imv_shift, 0, 10,
+                                use_had, 0, 0, lam, org_off=o_off, org_stride=o_stride)
+                r = B.Result()
+                oracle_lib.vo_search(C.byref(oj), C.byref(r), 0)
+                io.mvX, io.mvY = r.mvX * 16, r.mvY * 16   # rcMv.changePrecision(INT -> INTERNAL), :3488
+                oracle_lib.vo_int_refine(C.byref(oj), C.byref(io))
+                want.append((r.mvX, r.mvY, r.intSad) + io.tuple())
+    pick = lambda t: t[:3] + t[8:]
+    got = [pick(t) for t in ms.search(jobs)]
+    bad = [(i, jobs[i].w, jobs[i].h, got[i], want[i]) for i in range(len(jobs)) if got[i] != want[i]]
+    assert not bad, "%d of %d jobs differ, first: %s" % (len(bad), len(jobs), bad[:3])
+    got1 = [pick(ms.search([j])[0]) for j in jobs]
+    bad = [(i, jobs[i].w, jobs[i].h, got1[i], want[i]) for i in range(len(jobs)) if got1[i] != want[i]]
+    assert not bad, "single calls: %d of %d jobs differ, first: %s" % (len(bad), len(jobs), bad[:3])
+
+
 def test_dist_host_all_shapes(ms, oracle_lib):
     """The DistParam-hook flavour: one block pair in host memory, SAD (subShift 0/1) and SATD, incl. 4x4."""
     rng = np.random.default_rng(79)

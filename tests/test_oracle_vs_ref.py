@@ -274,3 +274,35 @@ def test_template_distortion_composition(oracle_lib, ref_lib):
             op = np.zeros((h, w), np.int16)
             oracle_lib.vo_mc_block(0, B.ptr(padded, M * stride + M), stride, w, h, mvx, mvy, 0, 10, 0, B.ptr(op), w)
             assert ref_lib.ref_dist(B.ptr(org), w, B.ptr(rp), w, w, h, 10, 0, 0) == oracle_lib.vo_sad(B.ptr(org), w, B.ptr(op), w, w, h, 0)
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("imv", [1, 2])
+@pytest.mark.parametrize("use_had", [0, 1])
+def test_int_refine(oracle_lib, ref_lib, imv, use_had):
+    """xPatternSearchIntRefine (InterSearch.cpp:4172-4282): the reference's own member against the restatement, over
+    random AMVP states, all CU shapes, positions at the picture border (clipMv) and bi-pred weights."""
+    from tests.helpers import MARGIN, clone_int_refine, int_refine_case, pad_plane
+    rng = np.random.default_rng(100 + 10 * imv + use_had)
+    pic_w, pic_h = 192, 128
+    ref = rng.integers(0, 1024, (pic_h, pic_w), dtype=np.int16)
+    refp = pad_plane(ref)
+    stride = refp.shape[1]
+    n = 0
+    for w, h in [(a, b) for a in (4, 8, 16, 32, 64, 128) for b in (4, 8, 16, 32, 64, 128) if a * b > 16]:
+        for rep in range(6):
+            x = int(rng.integers(0, (pic_w - w) // 4 + 1)) * 4
+            y = int(rng.integers(0, (pic_h - h) // 4 + 1)) * 4
+            org = np.ascontiguousarray(rng.integers(0, 1024, (h, w), dtype=np.int16))
+            if rep == 5:   # bi-pred pattern range
+                org = (2 * org.astype(np.int32) - rng.integers(0, 1024, org.shape)).astype(np.int16)
+            io = int_refine_case(rng, imv, x, y, w, h, pic_w, pic_h, max_pel=24 if rep else 150)
+            j = B.make_job(org, refp, stride, (MARGIN + y) * stride + MARGIN + x, w, h, (0, 0, 0, 0), (0, 0), 0, 0, 10,
+                           use_had, 0, 0, 31.33 if rep % 2 else 57.91)
+            a, b = clone_int_refine(io), clone_int_refine(io)
+            # the clip keeps the block within CTU+8 samples of the picture: inside the padded plane for this size
+            oracle_lib.vo_int_refine(C.byref(j), C.byref(a))
+            ref_lib.ref_int_refine(C.byref(j), C.byref(b))
+            assert a.tuple() == b.tuple(), (w, h, rep, a.tuple(), b.tuple())
+            n += 1
+    assert n > 100

@@ -7,8 +7,10 @@
 //                         VABSDIFF, 8 displacements x 1 row per thread step.  Single-sub-block jobs keep their
 //                         argmin directly; larger patterns write one SAD surface per sub-block.
 //   me_job_reduce_kernel  sums the sub-block surfaces of a large pattern, adds lambda*bits, argmin.
-//   me_job_frac_kernel    fractional refinement (me_frac.cuh) and result write-out.
+//   me_job_frac_kernel    fractional refinement (me_frac.cuh) or integer / 4-pel AMVR refinement (me_intrefine.cuh,
+//                         fracMode 2 = xPatternSearchIntRefine) and result write-out.
 #include "me_frac.cuh"
+#include "me_intrefine.cuh"
 #include "me_kernels.h"
 
 namespace vtmme {
@@ -218,7 +220,8 @@ __global__ void __launch_bounds__(kFracThreads) me_job_frac_kernel(const DevJob*
                                                                    DevJobResult* __restrict__ results,
                                                                    uint32_t* __restrict__ acc)
 {
-  __shared__ FracSmem sm;
+  __shared__ FracSmem   sm;
+  __shared__ IntRefSmem irs;
   const int    job = blockIdx.y, chunk = blockIdx.x;
   const DevJob j   = jobs[job];
   const int    nChunks = frac_num_chunks(j.w, j.h);
@@ -238,7 +241,15 @@ __global__ void __launch_bounds__(kFracThreads) me_job_frac_kernel(const DevJob*
     res.intSad = intCost - mv_cost(j.lambda, mv_bits_q(dx * 4, dy * 4, j.predQx, j.predQy, j.imvShift));
     res.halfX = res.halfY = res.qterX = res.qterY = 0;
     res.fracCost = res.intSad;
-    if (j.fracMode)
+    res.amvrMvX = res.amvrMvY = res.mvpIdx = 0;
+    res.bits = 0;
+    res.cost = 0;
+    if (j.fracMode == 2)
+    {
+      intrefine_accumulate<kFracThreads>(irs, j, j.org, j.orgStride, dx, dy, 0, 1);
+      if (threadIdx.x == 0) intrefine_decide(j, dx, dy, irs.acc, res);
+    }
+    else if (j.fracMode)
     {
       const FracJob f = make_frac_job(j, dx, dy);
       if (j.imvShift > 1)
@@ -267,6 +278,16 @@ __global__ void __launch_bounds__(kFracThreads) me_job_frac_kernel(const DevJob*
   // ---- one chunk of a large pattern
   const FracJob f = make_frac_job(j, dx, dy);
   uint32_t*     a = acc + (size_t) job * 18;
+  if (j.fracMode == 2)
+  {
+    if (PASS == 0)
+    {
+      intrefine_accumulate<kFracThreads>(irs, j, j.org, j.orgStride, dx, dy, chunk, nChunks);
+      if (threadIdx.x < kIntRefProbes && irs.acc[threadIdx.x] != 0xffffffffu && irs.acc[threadIdx.x])
+        atomicAdd(&a[threadIdx.x], irs.acc[threadIdx.x]);
+    }
+    return;
+  }
   if (PASS == 0)
   {
     frac_stage_sums(sm, f, 0, 0, 2, j.useAltHpel != 0, chunk);
@@ -309,7 +330,15 @@ __global__ void __launch_bounds__(128) me_job_frac_finish_kernel(const DevJob* _
   res.mvY    = dy;
   res.intSad = key_cost(key) - mv_cost(j.lambda, mv_bits_q(dx * 4, dy * 4, j.predQx, j.predQy, j.imvShift));
   res.halfX = res.halfY = res.qterX = res.qterY = 0;
-  if (j.imvShift > 1)
+  res.amvrMvX = res.amvrMvY = res.mvpIdx = 0;
+  res.bits = 0;
+  res.cost = 0;
+  if (j.fracMode == 2)
+  {
+    res.fracCost = res.intSad;
+    intrefine_decide(j, dx, dy, a, res);
+  }
+  else if (j.imvShift > 1)
     res.fracCost = a[0] + mv_cost(j.lambda, mv_bits_q(dx * 4, dy * 4, j.predQx, j.predQy, j.imvShift));
   else
   {
@@ -341,8 +370,9 @@ constexpr int kFusedThreads = kFracThreads;   // 128: the refinement code is wri
 __global__ void __launch_bounds__(kFusedThreads) me_job_fused_kernel(const __grid_constant__ FusedJobArgs a)
 {
   extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ FracSmem fsm;
-  __shared__ int16_t  s_pat[32 * 32];
+  __shared__ FracSmem   fsm;
+  __shared__ IntRefSmem irs;
+  __shared__ int16_t    s_pat[32 * 32];
   __shared__ int      s_last;
   JobSmemHdr* hdr   = reinterpret_cast<JobSmemHdr*>(smem);
   int32_t*    s_org = reinterpret_cast<int32_t*>(smem + kJobOffOrg);
@@ -457,7 +487,15 @@ __global__ void __launch_bounds__(kFusedThreads) me_job_fused_kernel(const __gri
   res.intSad = key_cost(key) - mv_cost(j.lambda, mv_bits_q(dx * 4, dy * 4, j.predQx, j.predQy, j.imvShift));
   res.halfX = res.halfY = res.qterX = res.qterY = 0;
   res.fracCost = res.intSad;
-  if (j.fracMode)
+  res.amvrMvX = res.amvrMvY = res.mvpIdx = 0;
+  res.bits = 0;
+  res.cost = 0;
+  if (j.fracMode == 2)
+  {
+    intrefine_accumulate<kFusedThreads>(irs, j, s_pat, rw, dx, dy, 0, 1);
+    if (tid == 0) intrefine_decide(j, dx, dy, irs.acc, res);
+  }
+  else if (j.fracMode)
   {
     FracJob f   = make_frac_job(j, dx, dy);
     f.org       = s_pat;

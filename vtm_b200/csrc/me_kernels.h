@@ -99,6 +99,18 @@ struct FracFrameParams
 size_t      frac_frame_acc_bytes(const FrameGeom& g, int nPairs);
 cudaError_t launch_frac_frame(const FracFrameParams& p, uint32_t* acc, int nPairs, cudaStream_t st, int* launches);
 
+// State of an xPatternSearchIntRefine call (InterSearch.cpp:4172-4282), MVs in 1/16 sample
+struct DevAmvr
+{
+  int      imv, numCand;
+  int      candX[2], candY[2];
+  int      mvpIdx;
+  uint32_t mvpIdxBits[2];
+  uint32_t bits;
+  int      posX, posY, picW, picH, maxCuW, maxCuH;   // clipMv
+  double   fWeight;
+};
+
 // Generic per-call jobs (vtmme_search)
 struct DevJob
 {
@@ -112,6 +124,7 @@ struct DevJob
   int            imvShift, subShift, bitDepth, useHad, useAltHpel, fracMode;
   int            signedOrg;  // pattern may be outside [0, 2^bd): bi-pred 2*org - otherPred
   double         lambda;
+  DevAmvr        amvr;       // fracMode 2 only
 };
 struct DevJobResult
 {
@@ -119,6 +132,9 @@ struct DevJobResult
   unsigned long long intSad;
   int                halfX, halfY, qterX, qterY;
   unsigned long long fracCost;
+  int                amvrMvX, amvrMvY, mvpIdx;   // fracMode 2: xPatternSearchIntRefine's rcMv (1/16), riMVPIdx,
+  uint32_t           bits;                       //   ruiBits and
+  unsigned long long cost;                       //   ruiCost
 };
 cudaError_t launch_job_search_impl(const DevJob* dJobs, unsigned long long* dKeys, DevJobResult* dResults, int n,
                                    int maxRegions, int nSplit, int bandRows, int maxGx, bool anyMulti, uint32_t* dSurf,

@@ -508,6 +508,32 @@ static int ensure_pinned(vtmme_ctx* ctx, size_t bytes)
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t) 255; }
 
 namespace {
+DevAmvr make_dev_amvr(const vtmme_job& j)
+{
+  DevAmvr d;
+  memset(&d, 0, sizeof(d));
+  if (j.fracMode != 2) return d;
+  const vtmme_amvr& a = *j.amvr;
+  d.imv     = a.imv;
+  d.numCand = a.numCand;
+  for (int i = 0; i < 2; i++)
+  {
+    d.candX[i]      = a.candX[i];
+    d.candY[i]      = a.candY[i];
+    d.mvpIdxBits[i] = a.mvpIdxBits[i];
+  }
+  d.mvpIdx  = a.mvpIdx;
+  d.bits    = a.bits;
+  d.posX    = j.x;
+  d.posY    = j.y;
+  d.picW    = a.picW;
+  d.picH    = a.picH;
+  d.maxCuW  = a.maxCuW;
+  d.maxCuH  = a.maxCuH;
+  d.fWeight = a.fWeight;
+  return d;
+}
+
 struct SearchTiming
 {
   bool   on = getenv("VTMME_TIMING") != nullptr;
@@ -554,6 +580,16 @@ extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_
     if (j.x + j.srLeft - 24 < -rp.margin || j.x + j.w + j.srRight + 24 > rp.width + rp.margin ||
         j.y + j.srTop - 8 < -rp.margin || j.y + j.h + j.srBottom + 8 > rp.height + rp.margin)
       return vtmme_set_error(ctx, VTMME_ERR_RANGE, "vtmme_search", "search window leaves the padded reference picture");
+    if (j.fracMode < 0 || j.fracMode > 2) return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search", "fracMode must be 0, 1 or 2");
+    if (j.fracMode == 2)
+    {
+      // clipMvInPic keeps every probe within maxCu + 8 samples of the picture, i.e. inside the device margin, provided
+      // the clip rectangle is the reference picture's own
+      const vtmme_amvr* a = j.amvr;
+      if (!a || (a->imv != 1 && a->imv != 2) || a->numCand < 1 || a->numCand > 2 || a->mvpIdx < 0 || a->mvpIdx >= a->numCand ||
+          a->picW != rp.width || a->picH != rp.height || a->maxCuW < 1 || a->maxCuW > 128 || a->maxCuH < 1 || a->maxCuH > 128)
+        return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search", "fracMode 2 needs a valid vtmme_amvr (imv 1|2, 1-2 candidates, picture size of refPic)");
+    }
     if (j.org) orgBytes += align256((size_t) j.w * j.h * 2);
     const int wl8 = j.srLeft & ~7;
     const int ngx = (j.srRight - wl8 + 8) >> 3, nrows = j.srBottom - j.srTop + 1;
@@ -624,6 +660,7 @@ extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_
       a.job.fracMode = j.fracMode;
       a.job.signedOrg = j.org != nullptr;
       a.job.lambda = j.lambdaMotion;
+      a.job.amvr   = make_dev_amvr(j);
       a.key    = ctx->dJobKeys;
       a.ticket = ctx->dJobTicket;
       a.result = reinterpret_cast<DevJobResult*>(ctx->dPinnedAlias);
@@ -709,6 +746,7 @@ extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_
     d.fracMode = j.fracMode;
     d.signedOrg = j.org != nullptr;
     d.lambda = j.lambdaMotion;
+    d.amvr   = make_dev_amvr(j);
     hj[i]   = d;
     hoff[i] = (long long) surfCur;
     const int nReg = ((j.w + 31) >> 5) * ((j.h + 31) >> 5);

@@ -22,6 +22,14 @@ SYMBOLS = ["vtmme_create", "vtmme_destroy", "vtmme_last_error", "vtmme_set_strea
            "vtmme_mc_batch", "vtmme_mc_host", "vtmme_add_avg", "vtmme_remove_high_freq", "vtmme_cand_sad", "vtmme_int_peak"]
 
 
+class CAmvr(C.Structure):
+    """vtmme_amvr"""
+    _fields_ = [("imv", C.c_int32), ("numCand", C.c_int32), ("candX", C.c_int32 * 2), ("candY", C.c_int32 * 2),
+                ("mvpIdx", C.c_int32), ("mvpIdxBits", C.c_uint32 * 2), ("bits", C.c_uint32),
+                ("picW", C.c_int32), ("picH", C.c_int32), ("maxCuW", C.c_int32), ("maxCuH", C.c_int32),
+                ("fWeight", C.c_double)]
+
+
 class CJob(C.Structure):
     """vtmme_job"""
     _fields_ = [("curPic", C.c_int32), ("refPic", C.c_int32), ("x", C.c_int32), ("y", C.c_int32),
@@ -29,17 +37,23 @@ class CJob(C.Structure):
                 ("srLeft", C.c_int32), ("srRight", C.c_int32), ("srTop", C.c_int32), ("srBottom", C.c_int32),
                 ("predQx", C.c_int32), ("predQy", C.c_int32), ("imvShift", C.c_int32), ("subShift", C.c_int32),
                 ("bitDepth", C.c_int32), ("useHad", C.c_int32), ("useAltHpel", C.c_int32), ("fracMode", C.c_int32),
-                ("lambdaMotion", C.c_double)]
+                ("lambdaMotion", C.c_double), ("amvr", C.POINTER(CAmvr))]
 
 
 class CResult(C.Structure):
     """vtmme_result"""
     _fields_ = [("mvX", C.c_int32), ("mvY", C.c_int32), ("intSad", C.c_uint64),
                 ("halfX", C.c_int32), ("halfY", C.c_int32), ("qterX", C.c_int32), ("qterY", C.c_int32),
-                ("fracCost", C.c_uint64)]
+                ("fracCost", C.c_uint64),
+                ("amvrMvX", C.c_int32), ("amvrMvY", C.c_int32), ("mvpIdx", C.c_int32), ("bits", C.c_uint32),
+                ("cost", C.c_uint64)]
 
     def tuple(self):
         return (self.mvX, self.mvY, self.intSad, self.halfX, self.halfY, self.qterX, self.qterY, self.fracCost)
+
+    def amvr_tuple(self):
+        """xPatternSearchIntRefine's outputs (fracMode 2): (rcMv x, y in 1/16 sample, riMVPIdx, ruiBits, ruiCost)"""
+        return (self.amvrMvX, self.amvrMvY, self.mvpIdx, self.bits, self.cost)
 
 
 class CFrameParams(C.Structure):

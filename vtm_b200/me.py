@@ -9,7 +9,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .lib import CCandJob, CFrameParams, CJob, CMcBlock, CResult, ERR_NAMES, VtmmeError, load_library
+from .lib import CAmvr, CCandJob, CFrameParams, CJob, CMcBlock, CResult, ERR_NAMES, VtmmeError, load_library
 
 # vtmme_cu_result
 CU_RESULT_DTYPE = np.dtype([("mvQx", "<i2"), ("mvQy", "<i2"), ("intX", "<i2"), ("intY", "<i2"),
@@ -52,6 +52,29 @@ class Job:
     fracMode: int = 1
     lambdaMotion: float = 31.33
     org: np.ndarray = None    # optional int16 pattern override (bi-pred)
+    amvr: "Amvr" = None       # fracMode 2: state of the xPatternSearchIntRefine call that follows the search
+
+
+@dataclass
+class Amvr:
+    """vtmme_amvr: what xPatternSearchIntRefine (EncoderLib/InterSearch.cpp:4172-4282) receives; MVs in 1/16 sample."""
+    imv: int                  # 1 IMV_FPEL, 2 IMV_4PEL
+    cands: tuple              # ((x0, y0), (x1, y1)) amvpInfo.mvCand
+    numCand: int
+    mvpIdx: int
+    mvpIdxBits: tuple
+    bits: int
+    picW: int
+    picH: int
+    fWeight: float = 1.0
+    maxCuW: int = 128
+    maxCuH: int = 128
+
+    def c(self):
+        return CAmvr(self.imv, self.numCand, (C.c_int32 * 2)(self.cands[0][0], self.cands[1][0]),
+                     (C.c_int32 * 2)(self.cands[0][1], self.cands[1][1]), self.mvpIdx,
+                     (C.c_uint32 * 2)(*self.mvpIdxBits), self.bits, self.picW, self.picH, self.maxCuW, self.maxCuH,
+                     self.fWeight)
 
 
 def frame_cu_layout(width, height):
@@ -147,12 +170,17 @@ class MotionSearch:
                 o = np.ascontiguousarray(j.org, dtype=np.int16)
                 keep.append(o)
                 org_ptr, org_stride = o.ctypes.data, o.shape[1]
+            amvr = None
+            if j.amvr is not None:
+                amvr = j.amvr.c()
+                keep.append(amvr)
+                amvr = C.pointer(amvr)
             cj[i] = CJob(j.curPic, j.refPic, j.x, j.y, j.w, j.h, org_ptr, org_stride, j.sr[0], j.sr[1], j.sr[2],
                          j.sr[3], j.predQ[0], j.predQ[1], j.imvShift, j.subShift, j.bitDepth, j.useHad, j.useAltHpel,
-                         j.fracMode, j.lambdaMotion)
+                         j.fracMode, j.lambdaMotion, amvr)
         res = (CResult * n)()
         self._check(self.L.vtmme_search(self.ctx, cj, n, res), "vtmme_search")
-        return [r.tuple() for r in res]
+        return [r.tuple() + (r.amvr_tuple() if j.fracMode == 2 else ()) for r, j in zip(res, jobs)]
 
     # ---- batched frame search --------------------------------------------------------------------------------
     def search_frames(self, cur_ids, ref_ids, params, pred_q=None):
