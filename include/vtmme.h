@@ -18,6 +18,7 @@
  *   InterSearch::xPatternSearch + xPatternSearchFracDIF             vtmme_search          (per-call jobs)
  *     (EncoderLib/InterSearch.cpp:3566-3608, 4284-4339)             vtmme_search_frames   (batched, per CTU tree)
  *   InterSearch::xPatternSearchIntRefine (:4172-4282)               vtmme_search with fracMode 2 + vtmme_amvr
+ *   InterSearch::xTZSearch (:3640-3974, FastSearch=1/3)             vtmme_search with vtmme_tz
  *   InterPrediction::xPredInterBlk (CommonLib/InterPrediction.cpp   vtmme_mc_batch / vtmme_mc_host
  *     :660-830), AreaBuf::addAvg (Buffer.cpp:467-507),              vtmme_add_avg
  *     AreaBuf::removeHighFreq (Buffer.h:474-517)                    vtmme_remove_high_freq
@@ -99,6 +100,26 @@ typedef struct
   double   fWeight;        /* xGetMEDistortionWeight (InterSearch.cpp:7666-7676)                       */
 } vtmme_amvr;
 
+/* State of a TZ search call, InterSearch::xTZSearch (InterSearch.cpp:3640-3974): when a job carries one, its
+ * integer search is the TZ search of FastSearch=1 (MESEARCH_DIAMOND: extended 0, fast 0), FastSearch=3
+ * (MESEARCH_DIAMOND_ENHANCED: extended 1) or of the cached-MV re-search (:3445, fast 1) instead of the full
+ * search; the job's srLeft..srBottom are ignored (xTZSearch sets its own window around the best start point).
+ * No hash ME, MCTS or composite reference; subShift as RdCost::setDistParam gives it for subShiftMode 0 or 2. */
+typedef struct
+{
+  int32_t startX, startY;       /* rcMv on entry (the AMVP predictor, or the cached integer MV), 1/16 sample      */
+  int32_t hasInt2Nx2N;          /* pIntegerMv2Nx2NPred != NULL                                                    */
+  int32_t int2Nx2NX, int2Nx2NY; /*   its value, integer pel                                                       */
+  int32_t nSeeds;               /* m_uniMvListSize, 0..15                                                         */
+  int32_t seedX[16], seedY[16]; /* uniMvs[list][ref] of the history entries, newest first (duplicates allowed,   */
+                                /*   the search skips them like :3738-3748), 1/16 sample                          */
+  int32_t searchRange;          /* m_iSearchRange                                                                 */
+  int32_t extended, fast;       /* bExtendedSettings, bFastSettings                                               */
+  int32_t firstSearchStop;      /* EncCfg::getFastMEAssumingSmootherMVEnabled                                     */
+  int32_t picW, picH;           /* clipMvInPic / xClipMv rectangle = size of refPic                               */
+  int32_t maxCu;                /* sps.getMaxCUWidth() == getMaxCUHeight(), <= 128                                */
+} vtmme_tz;
+
 typedef struct
 {
   int32_t        curPic;       /* picture holding the original block; ignored when org != NULL        */
@@ -117,6 +138,8 @@ typedef struct
                                /*   followed by xPatternSearchIntRefine on `amvr` (:3486-3489)         */
   double         lambdaMotion; /* RdCost::m_motionLambda                                               */
   const vtmme_amvr* amvr;      /* HOST pointer, fracMode 2 only (else ignored, may be NULL)            */
+  const vtmme_tz*   tz;        /* HOST pointer or NULL; non-NULL: xTZSearch instead of xPatternSearch  */
+                               /*   (all jobs of one call must agree)                                  */
 } vtmme_job;
 
 typedef struct
@@ -154,6 +177,9 @@ typedef struct
   int32_t predSpread;    /* max |pred_a - pred_b| (integer pel, per component) among CUs of one CTU  */
   int32_t subShiftMode;  /* 0: every row; 2 (FEN=1/3): CUs with H > 8 and W <= 64 use even rows only, x2 (RdCost.cpp:310-316) */
   double  lambdaMotion;
+  int32_t fastSearch;    /* integer search, like --FastSearch: 0 full search (xPatternSearch); 1 TZ search (xTZSearch,  */
+                         /*   MESEARCH_DIAMOND) started at the predictor; 3 enhanced TZ search (MESEARCH_DIAMOND_ENHANCED) */
+  int32_t tzFirstSearchStop; /* EncCfg::getFastMEAssumingSmootherMVEnabled (VTM default 1); fastSearch 1 / 3 only */
 } vtmme_frame_params;
 
 typedef struct

@@ -58,74 +58,122 @@ def main():
         r"(void InterpolationFilter::initInterpolationFilter\( bool enable \)\n\{\n(?:.*\n)*?#endif\n#endif\n)\}",
         r"\1  if ( enable )\n  {\n    initInterpolationFilterCUDA();   // libvtmme\n  }\n}", s, count=1))
 
-    # 4. InterSearch.cpp: xMotionEstimation calls the batched entry instead of xPatternSearch + xPatternSearchFracDIF
+    # 4. InterSearch.cpp: xMotionEstimation calls the GPU entry instead of xPatternSearch / xTZSearch (+ the refinement)
     def inter(s):
         s = once(s, '#include "InterSearch.h"\n', '#include "InterSearch.h"\n#include "CommonLib/cuda/VtmCudaME.h"   // libvtmme\n')
-        # locals, placed at the second "Do integer search" marker (the one inside xMotionEstimation)
+        # locals + one lambda, placed at the second "Do integer search" marker (the one inside xMotionEstimation)
         first = s.index("  //  Do integer search\n")
         second = s.index("  //  Do integer search\n", first + 1)
-        s = s[:second] + ("  vtmcuda::SearchOut cudaOut;   // libvtmme\n  bool cudaFracDone = false;\n  bool cudaIntRefineDone = false;\n") + s[second:]
-        s = once(s, "    xPatternSearch( cStruct, rcMv, ruiCost);\n", """\
-    if( vtmcuda::enabled() && !m_cDistParam.applyWeight && m_lumaClpRng.bd <= 10 && !wrap
-        && !pu.cu->slice->getRefPic( eRefPicList, iRefIdxPred )->isRefScaled( pu.cs->pps ) )
+        s = s[:second] + """\
+  // ---- libvtmme: the integer search (full search or TZ search) and the refinement that follows it run on the GPU
+  vtmcuda::SearchOut cudaOut;
+  bool cudaFracDone      = false;
+  bool cudaIntRefineDone = false;
+  const bool cudaUsable  = vtmcuda::enabled() && !m_cDistParam.applyWeight && m_lumaClpRng.bd <= 10 && !wrap
+                           && !pu.cu->slice->getRefPic( eRefPicList, iRefIdxPred )->isRefScaled( pu.cs->pps )
+                           && !pu.cs->sps->getWrapAroundEnabledFlag();
+  auto cudaSearch = [&]( const bool tz, const bool tzFast, const Mv& tzStart )
+  {
+    vtmcuda::SearchIn in;
+    in.refPic       = pu.cu->slice->getRefPic( eRefPicList, iRefIdxPred );
+    in.x            = pu.Y().x;
+    in.y            = pu.Y().y;
+    in.w            = pu.Y().width;
+    in.h            = pu.Y().height;
+    in.org          = cStruct.pcPatternKey->buf;
+    in.orgStride    = cStruct.pcPatternKey->stride;
+    in.srLeft       = cStruct.searchRange.left;
+    in.srRight      = cStruct.searchRange.right;
+    in.srTop        = cStruct.searchRange.top;
+    in.srBottom     = cStruct.searchRange.bottom;
+    in.predQx       = predQuarter.getHor();
+    in.predQy       = predQuarter.getVer();
+    in.imvShift     = cStruct.imvShift;
+    in.subShiftMode = cStruct.subShiftMode;
+    in.bitDepth     = m_lumaClpRng.bd;
+    in.useHad       = m_pcEncCfg->getUseHADME() && !pu.cs->slice->getDisableSATDForRD();
+    in.useAltHpel   = cStruct.useAltHpelIf;
+    in.lambdaMotion = m_pcRdCost->getSelectedMotionLambda();
+    in.picW         = pu.cs->pps->getPicWidthInLumaSamples();
+    in.picH         = pu.cs->pps->getPicHeightInLumaSamples();
+    in.maxCuW       = pu.cs->sps->getMaxCUWidth();
+    in.maxCuH       = pu.cs->sps->getMaxCUHeight();
+    in.doFrac       = 0;
+    if( !m_pcEncCfg->getMCTSEncConstraint() )
     {
-      // libvtmme: integer full search (+ fractional refinement when this call does one) on the GPU
-      vtmcuda::SearchIn in;
-      in.refPic       = pu.cu->slice->getRefPic( eRefPicList, iRefIdxPred );
-      in.x            = pu.Y().x;
-      in.y            = pu.Y().y;
-      in.w            = pu.Y().width;
-      in.h            = pu.Y().height;
-      in.org          = cStruct.pcPatternKey->buf;
-      in.orgStride    = cStruct.pcPatternKey->stride;
-      in.srLeft       = cStruct.searchRange.left;
-      in.srRight      = cStruct.searchRange.right;
-      in.srTop        = cStruct.searchRange.top;
-      in.srBottom     = cStruct.searchRange.bottom;
-      in.predQx       = predQuarter.getHor();
-      in.predQy       = predQuarter.getVer();
-      in.imvShift     = cStruct.imvShift;
-      in.subShiftMode = cStruct.subShiftMode;
-      in.bitDepth     = m_lumaClpRng.bd;
-      in.useHad       = m_pcEncCfg->getUseHADME() && !pu.cs->slice->getDisableSATDForRD();
-      in.useAltHpel   = cStruct.useAltHpelIf;
-      in.doFrac       = 0;
-      if( !m_pcEncCfg->getMCTSEncConstraint() )
+      in.doFrac = ( pu.cu->imv == 0 || pu.cu->imv == IMV_HPEL ) ? 1 : 2;
+    }
+    if( in.doFrac == 2 )   // integer / 4-pel AMVR: xPatternSearchIntRefine follows the search on the GPU too
+    {
+      in.imv     = pu.cu->imv;
+      in.numCand = amvpInfo.numCand;
+      for( int i = 0; i < 2; i++ )
       {
-        in.doFrac = ( pu.cu->imv == 0 || pu.cu->imv == IMV_HPEL ) ? 1 : 2;
+        in.candX[i]      = amvpInfo.mvCand[i].getHor();
+        in.candY[i]      = amvpInfo.mvCand[i].getVer();
+        in.mvpIdxBits[i] = m_auiMVPIdxCost[i][AMVP_MAX_NUM_CANDS];
       }
-      in.lambdaMotion = m_pcRdCost->getSelectedMotionLambda();
-      if( in.doFrac == 2 )   // integer / 4-pel AMVR: xPatternSearchIntRefine follows the search on the GPU too
+      in.mvpIdx  = riMVPIdx;
+      in.bits    = ruiBits;
+      in.fWeight = fWeight;
+    }
+    in.tzSearch = tz;
+    if( tz )   // xTZSearch's inputs (FastSearch=1/3; the re-search of a cached integer MV uses the fast settings)
+    {
+      in.tzExtended        = !tzFast && m_motionEstimationSearchMethod == MESEARCH_DIAMOND_ENHANCED;
+      in.tzFast            = tzFast;
+      in.tzFirstSearchStop = m_pcEncCfg->getFastMEAssumingSmootherMVEnabled();
+      in.tzStartX          = tzStart.getHor();
+      in.tzStartY          = tzStart.getVer();
+      in.tzSearchRange     = m_iSearchRange;
+      in.tzNumSeeds        = m_uniMvListSize;
+      for( int i = 0; i < m_uniMvListSize; i++ )
       {
-        in.imv     = pu.cu->imv;
-        in.numCand = amvpInfo.numCand;
-        for( int i = 0; i < 2; i++ )
-        {
-          in.candX[i]      = amvpInfo.mvCand[i].getHor();
-          in.candY[i]      = amvpInfo.mvCand[i].getVer();
-          in.mvpIdxBits[i] = m_auiMVPIdxCost[i][AMVP_MAX_NUM_CANDS];
-        }
-        in.mvpIdx  = riMVPIdx;
-        in.bits    = ruiBits;
-        in.picW    = pu.cs->pps->getPicWidthInLumaSamples();
-        in.picH    = pu.cs->pps->getPicHeightInLumaSamples();
-        in.maxCuW  = pu.cs->sps->getMaxCUWidth();
-        in.maxCuH  = pu.cs->sps->getMaxCUHeight();
-        in.fWeight = fWeight;
-        if( clipMv != clipMvInPic || pu.cs->sps->getWrapAroundEnabledFlag() )
-        {
-          in.doFrac = 0;   // sub-picture / wrap-around clipping: the refinement stays on the CPU
-        }
+        const BlkUniMvInfo* e = m_uniMvList + ( ( m_uniMvListIdx - 1 - i + m_uniMvListMaxSize ) % ( m_uniMvListMaxSize ) );
+        in.tzSeedX[i] = e->uniMvs[eRefPicList][iRefIdxPred].getHor();
+        in.tzSeedY[i] = e->uniMvs[eRefPicList][iRefIdxPred].getVer();
       }
-      vtmcuda::search( in, cudaOut );
-      rcMv.set( cudaOut.mvX, cudaOut.mvY );
-      ruiCost          = cudaOut.intSad;
-      cudaFracDone     = in.doFrac == 1;
-      cudaIntRefineDone = in.doFrac == 2;
+    }
+    vtmcuda::search( in, cudaOut );
+    rcMv.set( cudaOut.mvX, cudaOut.mvY );
+    ruiCost           = cudaOut.intSad;
+    cudaFracDone      = in.doFrac == 1;
+    cudaIntRefineDone = in.doFrac == 2;
+  };
+  // the TZ search runs on the GPU for the diamond methods without hash ME / MCTS / composite reference
+  const bool cudaTzUsable = cudaUsable && clipMv == clipMvInPic && !m_pcEncCfg->getMCTSEncConstraint() && !m_pcEncCfg->getUseHashME()
+                            && !cStruct.inCtuSearch
+                            && ( m_motionEstimationSearchMethod == MESEARCH_DIAMOND || m_motionEstimationSearchMethod == MESEARCH_DIAMOND_ENHANCED )
+                            && ( m_pcEncCfg->getRestrictMESampling() || m_pcEncCfg->getMotionEstimationSearchMethod() != MESEARCH_SELECTIVE );
+""" + s[second:]
+        s = once(s, "    xPatternSearch( cStruct, rcMv, ruiCost);\n", """\
+    if( cudaUsable && ( clipMv == clipMvInPic || ( pu.cu->imv == 0 || pu.cu->imv == IMV_HPEL ) ) )
+    {
+      cudaSearch( false, false, Mv() );   // libvtmme: integer full search + refinement
     }
     else
     {
       xPatternSearch( cStruct, rcMv, ruiCost);
+    }
+""")
+        s = once(s, "    xTZSearch(pu, eRefPicList, iRefIdxPred, cStruct, rcMv, ruiCost, NULL, false, true);\n", """\
+    if( cudaTzUsable )
+    {
+      cudaSearch( true, true, rcMv );   // libvtmme: xTZSearch with the fast settings + refinement
+    }
+    else
+    {
+      xTZSearch(pu, eRefPicList, iRefIdxPred, cStruct, rcMv, ruiCost, NULL, false, true);
+    }
+""")
+        s = once(s, "    xPatternSearchFast(pu, eRefPicList, iRefIdxPred, cStruct, rcMv, ruiCost, pIntegerMv2Nx2NPred);\n", """\
+    if( cudaTzUsable )
+    {
+      cudaSearch( true, false, rcMv );   // libvtmme: xTZSearch (FastSearch=1/3) + refinement
+    }
+    else
+    {
+      xPatternSearchFast(pu, eRefPicList, iRefIdxPred, cStruct, rcMv, ruiCost, pIntegerMv2Nx2NPred);
     }
 """)
         s = once(s, "    xPatternSearchFracDIF( pu, eRefPicList, iRefIdxPred, cStruct, rcMv, cMvHalf, cMvQter, ruiCost );\n", """\

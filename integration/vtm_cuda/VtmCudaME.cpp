@@ -18,6 +18,7 @@ namespace
 vtmme_ctx* g_ctx        = nullptr;
 uint64_t   g_calls      = 0;
 uint64_t   g_uploads    = 0;
+uint64_t   g_tzSearches = 0;   // searches whose integer stage was xTZSearch (FastSearch=1/3)
 uint64_t   g_intRefines = 0;   // searches whose xPatternSearchIntRefine ran on the GPU too
 double     g_searchSec  = 0;   // wall time spent inside vtmme_search (upload of the pattern, kernels, sync)
 int        g_nextPicId  = 1;
@@ -127,6 +128,30 @@ void search( const SearchIn& in, SearchOut& out )
     a.fWeight = in.fWeight;
     j.amvr    = &a;
   }
+  vtmme_tz t;
+  j.tz = nullptr;
+  if( in.tzSearch )
+  {
+    t.startX      = in.tzStartX;
+    t.startY      = in.tzStartY;
+    t.hasInt2Nx2N = 0;   // xMotionEstimation always passes pIntegerMv2Nx2NPred = 0 (InterSearch.cpp:3453,3455)
+    t.int2Nx2NX = t.int2Nx2NY = 0;
+    t.nSeeds      = in.tzNumSeeds;
+    for( int i = 0; i < 16; i++ )
+    {
+      t.seedX[i] = i < in.tzNumSeeds ? in.tzSeedX[i] : 0;
+      t.seedY[i] = i < in.tzNumSeeds ? in.tzSeedY[i] : 0;
+    }
+    t.searchRange     = in.tzSearchRange;
+    t.extended        = in.tzExtended;
+    t.fast            = in.tzFast;
+    t.firstSearchStop = in.tzFirstSearchStop;
+    t.picW            = in.picW;
+    t.picH            = in.picH;
+    t.maxCu           = in.maxCuW;
+    j.tz              = &t;
+    g_tzSearches++;
+  }
   vtmme_result r;
   vtmme_ctx*   c  = ctx();
   const auto   t0 = std::chrono::steady_clock::now();
@@ -178,9 +203,9 @@ void printStats()
 {
   if( g_ctx )
   {
-    fprintf( stderr, "[vtmcuda] GPU motion searches: %llu (%llu with AMVR integer refinement; %.1f s inside vtmme_search, %.1f us per "
+    fprintf( stderr, "[vtmcuda] GPU motion searches: %llu (%llu TZ searches, %llu with AMVR integer refinement; %.1f s inside vtmme_search, %.1f us per "
                      "call), reference pictures uploaded: %llu, kernel launches: %llu\n",
-             (unsigned long long) g_calls, (unsigned long long) g_intRefines, g_searchSec, g_calls ? 1e6 * g_searchSec / g_calls : 0.0,
+             (unsigned long long) g_calls, (unsigned long long) g_tzSearches, (unsigned long long) g_intRefines, g_searchSec, g_calls ? 1e6 * g_searchSec / g_calls : 0.0,
              (unsigned long long) g_uploads, (unsigned long long) vtmme_launch_count( g_ctx ) );
   }
 }

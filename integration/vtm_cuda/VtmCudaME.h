@@ -34,6 +34,11 @@ struct SearchIn
   uint32_t       mvpIdxBits[2], bits;
   int            picW, picH, maxCuW, maxCuH;
   double         fWeight;
+  // tzSearch: the integer search is xTZSearch (FastSearch=1/3) instead of the full search; sr* are ignored
+  bool           tzSearch, tzExtended, tzFast, tzFirstSearchStop;
+  int            tzStartX, tzStartY;       // rcMv on entry, MV_PRECISION_INTERNAL
+  int            tzSearchRange;            // m_iSearchRange
+  int            tzNumSeeds, tzSeedX[16], tzSeedY[16];   // m_uniMvList entries of (list, ref), newest first
 };
 
 struct SearchOut

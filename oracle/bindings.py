@@ -49,6 +49,15 @@ class IntRefine(C.Structure):
         return (self.mvX, self.mvY, self.mvpIdx, self.bits, self.cost)
 
 
+class TzParams(C.Structure):
+    """vo_tz_params / RefTzParams (identical layout): what xTZSearch receives besides the job."""
+    _fields_ = [("startX", C.c_int), ("startY", C.c_int), ("hasInt2Nx2N", C.c_int), ("int2Nx2NX", C.c_int),
+                ("int2Nx2NY", C.c_int), ("nSeeds", C.c_int), ("seedX", C.c_int * 16), ("seedY", C.c_int * 16),
+                ("searchRange", C.c_int), ("extended", C.c_int), ("fast", C.c_int), ("firstSearchStop", C.c_int),
+                ("posX", C.c_int), ("posY", C.c_int), ("picW", C.c_int), ("picH", C.c_int),
+                ("maxCuW", C.c_int), ("maxCuH", C.c_int)]
+
+
 def build_oracle():
     subprocess.check_call(["make", "-s", "-f", "oracle/Makefile"], cwd=ROOT)
 
@@ -87,10 +96,13 @@ def oracle():
         L.vo_search.argtypes = [C.POINTER(Job), C.POINTER(Result), _I]
         L.vo_search_batch.argtypes = [C.POINTER(Job), C.POINTER(Result), _I, _I]
         L.vo_search_batch.restype = C.c_double
+        L.vo_frac_direct.argtypes = [C.POINTER(Job), _I, _I] + [C.POINTER(_I)] * 4 + [C.POINTER(C.c_uint64)]
         L.vo_pred_qpel.argtypes = [C.POINTER(Job), _I, _I, _I, _I, _I, _P, _I]
         L.vo_me_finish.argtypes = [C.POINTER(Job), C.POINTER(Result), C.c_double, C.c_uint32,
                                    C.POINTER(_I), C.POINTER(_I), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
         L.vo_int_refine.argtypes = [C.POINTER(Job), C.POINTER(IntRefine)]
+        L.vo_tz_search.argtypes = [C.POINTER(Job), C.POINTER(TzParams), C.POINTER(_I), C.POINTER(_I),
+                                   C.POINTER(C.c_uint64), C.POINTER(_I)]
         L.vo_mc_block.argtypes = [_I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I]
         L.vo_add_avg.argtypes = [_P, _P, _P, _I, _I]
         L.vo_remove_high_freq.argtypes = [_P, _P, _I, _I, _I]
@@ -123,6 +135,8 @@ def ref():
         L.ref_filter_batch.restype = C.c_double
         L.ref_filter_batch.argtypes = [_I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I]
         L.ref_int_refine.argtypes = [C.POINTER(Job), C.POINTER(IntRefine)]
+        L.ref_tz_search.argtypes = [C.POINTER(Job), C.POINTER(TzParams), C.POINTER(_I), C.POINTER(_I),
+                                    C.POINTER(C.c_uint64)]
         L.ref_mc_blocks.argtypes = [_I, _P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, C.POINTER(C.c_double)]
         L.ref_add_avg.argtypes = [_P, _P, _P, _I, _I, _I]
         L.ref_remove_high_freq.argtypes = [_P, _I, _P, _I, _I, _I, _I, _I]

@@ -406,6 +406,84 @@ void ref_int_refine(const RefSearchJob* j, RefIntRefine* io)
   io->cost   = cost;
 }
 
+// ---- InterSearch::xTZSearch (InterSearch.cpp:3640-3974), the reference's own member ---------------------------------
+// Same layout as vo_tz_params (oracle/vtm_oracle.h).
+struct RefTzParams
+{
+  int startX, startY;
+  int hasInt2Nx2N, int2Nx2NX, int2Nx2NY;
+  int nSeeds;
+  int seedX[16], seedY[16];
+  int searchRange;
+  int extended, fast, firstSearchStop;
+  int posX, posY, picW, picH, maxCuW, maxCuH;
+};
+
+void ref_tz_search(const RefSearchJob* j, const RefTzParams* t, int* mvx, int* mvy, uint64_t* sad)
+{
+  Probe& p = probe();
+  p.rd.m_motionLambda = j->lambdaMotion;
+  p.rd.setPredictor(Mv(j->predQx, j->predQy));
+  p.rd.setCostScale(2);
+  p.cfg.setMCTSEncConstraint(false);
+  p.cfg.setFastMEAssumingSmootherMVEnabled(t->firstSearchStop != 0);
+  p.cfg.setUseHashME(false);
+  p.m_lumaClpRng   = makeClp(j->bitDepth);
+  p.m_iSearchRange = t->searchRange;
+  clipMv = clipMvInPic;
+
+  PPS pps;
+  pps.setPicWidthInLumaSamples(t->picW);
+  pps.setPicHeightInLumaSamples(t->picH);
+  SPS sps;
+  sps.setMaxCUWidth(t->maxCuW);
+  sps.setMaxCUHeight(t->maxCuH);
+  sps.setWrapAroundEnabledFlag(false);
+  // xClipMv (InterSearch.cpp:7735-7764) looks the sub-picture up: one sub-picture, not treated as a picture
+  pps.m_numSubPics = 1;
+  pps.m_subPics.resize(1);
+  pps.m_subPics[0].setTreatedAsPicFlag(false);
+  pps.setWrapAroundEnabledFlag(false);
+  std::vector<uint64_t> shell((sizeof(CodingStructure) + 7) / 8, 0);
+  CodingStructure* cs = reinterpret_cast<CodingStructure*>(shell.data());
+  cs->sps = &sps;
+  cs->pps = &pps;
+  CodingUnit cu(CHROMA_420, Area(t->posX, t->posY, j->w, j->h));
+  cu.imv    = 0;
+  cu.affine = false;
+  PredictionUnit pu(CHROMA_420, Area(t->posX, t->posY, j->w, j->h));
+  pu.cu = &cu;
+  pu.cs = cs;
+
+  // history of uni-directional MVs (m_uniMvList): entry i of the caller's list is the i-th newest
+  const int maxSize = 15;
+  std::vector<BlkUniMvInfo> list(maxSize);
+  p.m_uniMvList        = list.data();
+  p.m_uniMvListMaxSize = maxSize;
+  p.m_uniMvListSize    = t->nSeeds;
+  p.m_uniMvListIdx     = t->nSeeds % maxSize;
+  for (int i = 0; i < t->nSeeds; i++)
+    list[(p.m_uniMvListIdx - 1 - i + maxSize) % maxSize].uniMvs[0][0] = Mv(t->seedX[i], t->seedY[i]);
+
+  CPelBuf pattern(j->org, j->orgStride, j->w, j->h);
+  InterSearch::IntTZSearchStruct st;
+  memset(&st, 0, sizeof(st));
+  st.pcPatternKey = &pattern;
+  st.piRefY       = j->refAtPU;
+  st.iRefStride   = j->refStride;
+  st.imvShift     = j->imvShift;
+  st.subShiftMode = j->subShiftMode;
+
+  Mv         mv(t->startX, t->startY);
+  Mv         int2Nx2N(t->int2Nx2NX, t->int2Nx2NY);
+  Distortion cost = 0;
+  p.xTZSearch(pu, REF_PIC_LIST_0, 0, st, mv, cost, t->hasInt2Nx2N ? &int2Nx2N : nullptr, t->extended != 0, t->fast != 0);
+  p.m_uniMvList = nullptr;
+  *mvx = mv.hor;
+  *mvy = mv.ver;
+  *sad = cost;
+}
+
 // Batch driver used as the CPU baseline: nThreads workers over disjoint job ranges.
 // Returns wall seconds spent in the searches (steady_clock around the work only).
 double ref_search_batch(const RefSearchJob* jobs, RefSearchResult* res, int n, int nThreads)

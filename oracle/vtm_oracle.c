@@ -774,3 +774,245 @@ void vo_int_refine(const vo_job* j, vo_int_refine_io* io)
   io->bits = bits;
   io->cost = bestDist - vo_mv_cost(j->lambdaMotion, (uint32_t) bestBits) + vo_mv_cost(j->lambdaMotion, bits); /* :4276 */
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * TZ search
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef struct
+{
+  const vo_job* j;
+  int           subShift;
+  int           l, r, t, b; /* cStruct.searchRange */
+  uint64_t      bestSad;
+  int           bestX, bestY;
+  unsigned      bestDistance, bestRound;
+  int           pointNr;
+  int           probes;
+} vo_tz;
+
+/* xTZSearchHelp, subShiftMode != 1 branch — InterSearch.cpp:394-416 */
+static void vo_tz_probe(vo_tz* s, int x, int y, int pointNr, unsigned dist)
+{
+  const vo_job* j   = s->j;
+  uint64_t      sad = vo_sad(j->org, j->orgStride, j->refAtPU + (ptrdiff_t) y * j->refStride + x, j->refStride, j->w, j->h, s->subShift);
+  s->probes++;
+  if (sad < s->bestSad)
+  {
+    sad += vo_mv_cost(j->lambdaMotion, vo_mv_bits(x, y, j->predQx, j->predQy, 2, j->imvShift));
+    if (sad < s->bestSad)
+    {
+      s->bestSad      = sad;
+      s->bestX        = x;
+      s->bestY        = y;
+      s->bestDistance = dist;
+      s->bestRound    = 0;
+      s->pointNr      = pointNr;
+    }
+  }
+}
+
+/* One point of a diamond: a coordinate that moved away from the start is checked against the window on its side,
+ * a coordinate equal to the start's is not checked — the rule every branch of xTZ8PointDiamondSearch follows. */
+static void vo_tz_point(vo_tz* s, int sx, int sy, int dx, int dy, int pointNr, unsigned dist)
+{
+  const int x = sx + dx, y = sy + dy;
+  if ((dx < 0 && x < s->l) || (dx > 0 && x > s->r) || (dy < 0 && y < s->t) || (dy > 0 && y > s->b)) return;
+  vo_tz_probe(s, x, y, pointNr, dist);
+}
+
+/* xTZ8PointDiamondSearch — InterSearch.cpp:503-705 (probe order and point numbers as there) */
+static void vo_tz_diamond(vo_tz* s, int sx, int sy, int d, int cornersAtDist1)
+{
+  s->bestRound += 1;
+  if (d == 1)
+  {
+    if (cornersAtDist1)
+    {
+      if (sy - 1 >= s->t)
+      {
+        vo_tz_point(s, sx, sy, -1, -1, 1, 1);
+        vo_tz_point(s, sx, sy, 0, -1, 2, 1);
+        vo_tz_point(s, sx, sy, 1, -1, 3, 1);
+      }
+    }
+    else
+      vo_tz_point(s, sx, sy, 0, -1, 2, 1);
+    vo_tz_point(s, sx, sy, -1, 0, 4, 1);
+    vo_tz_point(s, sx, sy, 1, 0, 5, 1);
+    if (cornersAtDist1)
+    {
+      if (sy + 1 <= s->b)
+      {
+        vo_tz_point(s, sx, sy, -1, 1, 6, 1);
+        vo_tz_point(s, sx, sy, 0, 1, 7, 1);
+        vo_tz_point(s, sx, sy, 1, 1, 8, 1);
+      }
+    }
+    else
+      vo_tz_point(s, sx, sy, 0, 1, 7, 1);
+  }
+  else if (d <= 8)
+  {
+    const int h = d >> 1;
+    vo_tz_point(s, sx, sy, 0, -d, 2, d);
+    vo_tz_point(s, sx, sy, -h, -h, 1, h);
+    vo_tz_point(s, sx, sy, h, -h, 3, h);
+    vo_tz_point(s, sx, sy, -d, 0, 4, d);
+    vo_tz_point(s, sx, sy, d, 0, 5, d);
+    vo_tz_point(s, sx, sy, -h, h, 6, h);
+    vo_tz_point(s, sx, sy, h, h, 8, h);
+    vo_tz_point(s, sx, sy, 0, d, 7, d);
+  }
+  else
+  {
+    int i;
+    vo_tz_point(s, sx, sy, 0, -d, 0, d);
+    vo_tz_point(s, sx, sy, -d, 0, 0, d);
+    vo_tz_point(s, sx, sy, d, 0, 0, d);
+    vo_tz_point(s, sx, sy, 0, d, 0, d);
+    for (i = 1; i < 4; i++)
+    {
+      const int q = (d >> 2) * i;
+      vo_tz_point(s, sx, sy, -q, -d + q, 0, d);
+      vo_tz_point(s, sx, sy, q, -d + q, 0, d);
+      vo_tz_point(s, sx, sy, -q, d - q, 0, d);
+      vo_tz_point(s, sx, sy, q, d - q, 0, d);
+    }
+  }
+}
+
+/* xTZ2PointSearch — InterSearch.cpp:420-446 */
+static void vo_tz_two_points(vo_tz* s)
+{
+  static const int xo[2][9] = { { 0, -1, -1, 0, -1, +1, -1, -1, +1 }, { 0, 0, +1, +1, -1, +1, 0, +1, 0 } };
+  static const int yo[2][9] = { { 0, 0, -1, -1, +1, -1, 0, +1, 0 }, { 0, -1, -1, 0, -1, +1, +1, +1, +1 } };
+  int              k;
+  const int        bx = s->bestX, by = s->bestY, pn = s->pointNr; /* both points are derived before the first probe */
+  for (k = 0; k < 2; k++)
+  {
+    const int x = bx + xo[k][pn], y = by + yo[k][pn];
+    if (x >= s->l && x <= s->r && y >= s->t && y <= s->b) vo_tz_probe(s, x, y, 0, 2);
+  }
+}
+
+/* clipMv + changePrecision(INTERNAL -> QUARTER) + divideByPowerOf2(2) — InterSearch.cpp:3682-3683 */
+static void vo_tz_to_int(const vo_tz_params* p, int* x, int* y)
+{
+  vo_clip_mv(x, y, p->posX, p->posY, p->picW, p->picH, p->maxCuW, p->maxCuH);
+  *x = vo_div_pow2(vo_change_prec(*x, -2), 2);
+  *y = vo_div_pow2(vo_change_prec(*y, -2), 2);
+}
+
+/* InterSearch::xTZSearch — EncoderLib/InterSearch.cpp:3640-3974 */
+void vo_tz_search(const vo_job* j, const vo_tz_params* p, int* mvx, int* mvy, uint64_t* sadOut, int* nProbes)
+{
+  const int raster      = p->fast ? 8 : 5;               /* iRaster */
+  const int firstRounds = 3;                             /* uiFirstSearchRounds (both settings) */
+  const int range       = p->searchRange;
+  vo_tz     s;
+  int       sx, sy, d, i, k, bestIsZero;
+  memset(&s, 0, sizeof(s));
+  s.j        = j;
+  s.subShift = vo_subshift(j->subShiftMode, j->w, j->h);
+  s.bestSad  = UINT64_MAX;
+
+  sx = p->startX;
+  sy = p->startY;
+  vo_tz_to_int(p, &sx, &sy);
+  vo_tz_probe(&s, sx, sy, 0, 0); /* :3695 */
+  if (!p->fast && (sx != 0 || sy != 0) && (s.bestX != 0 || s.bestY != 0)) vo_tz_probe(&s, 0, 0, 0, 0); /* :3698-3707 */
+
+  if (p->hasInt2Nx2N) /* :3711-3732 */
+  {
+    int ix = p->int2Nx2NX * 16, iy = p->int2Nx2NY * 16;
+    vo_tz_to_int(p, &ix, &iy);
+    if ((sx != ix || sy != iy) && (ix != s.bestX || iy != s.bestY)) vo_tz_probe(&s, ix, iy, 0, 0);
+  }
+
+  for (i = 0; i < p->nSeeds; i++) /* :3734-3765: history MVs; only the position and cost are updated */
+  {
+    int      x = p->seedX[i], y = p->seedY[i];
+    uint64_t sad;
+    for (k = 0; k < i; k++)
+      if (p->seedX[k] == x && p->seedY[k] == y) break;
+    if (k < i) continue;
+    vo_clip_mv(&x, &y, p->posX, p->posY, p->picW, p->picH, p->maxCuW, p->maxCuH);
+    x   = vo_change_prec(x, -4);
+    y   = vo_change_prec(y, -4);
+    sad = vo_sad(j->org, j->orgStride, j->refAtPU + (ptrdiff_t) y * j->refStride + x, j->refStride, j->w, j->h, s.subShift);
+    s.probes++;
+    sad += vo_mv_cost(j->lambdaMotion, vo_mv_bits(x, y, j->predQx, j->predQy, 2, j->imvShift));
+    if (sad < s.bestSad)
+    {
+      s.bestSad = sad;
+      s.bestX   = x;
+      s.bestY   = y;
+    }
+  }
+
+  vo_set_search_range(s.bestX * 16, s.bestY * 16, p->posX, p->posY, p->picW, p->picH, p->maxCuW, p->maxCuH,
+                      range >> (p->fast ? 1 : 0), &s.l, &s.r, &s.t, &s.b); /* :3767-3772 */
+
+  sx         = s.bestX;
+  sy         = s.bestY;
+  bestIsZero = s.bestX == 0 && s.bestY == 0;
+  for (d = 1; d <= range; d *= 2) /* first search, :3803-3818 */
+  {
+    vo_tz_diamond(&s, sx, sy, d, p->extended);
+    if (p->firstSearchStop && s.bestRound >= (unsigned) firstRounds) break;
+  }
+  if (p->extended && !bestIsZero) /* zero neighbourhood with half the range, :3841-3855 (bNewZeroNeighbourhoodTest) */
+    for (d = 1; d <= (range >> 1); d *= 2) vo_tz_diamond(&s, 0, 0, d, 0);
+
+  if (s.bestDistance == 1) /* :3858-3863 */
+  {
+    s.bestDistance = 0;
+    vo_tz_two_points(&s);
+  }
+
+  if (p->extended) /* adaptive raster, :3865-3885 */
+  {
+    int win = raster, l = s.l, r = s.r, t = s.t, b = s.b, x, y;
+    if (!((int) s.bestDistance >= raster))
+    {
+      win++;
+      l /= 2;
+      r /= 2;
+      t /= 2;
+      b /= 2;
+    }
+    s.bestDistance = (unsigned) win;
+    for (y = t; y <= b; y += win)
+      for (x = l; x <= r; x += win) vo_tz_probe(&s, x, y, 0, (unsigned) win);
+  }
+  else if ((int) s.bestDistance >= raster) /* :3886-3899 */
+  {
+    int x, y;
+    s.bestDistance = (unsigned) raster;
+    for (y = s.t; y <= s.b; y += raster)
+      for (x = s.l; x <= s.r; x += raster) vo_tz_probe(&s, x, y, 0, (unsigned) raster);
+  }
+
+  while (s.bestDistance > 0) /* star refinement, :3932-3967 */
+  {
+    sx             = s.bestX;
+    sy             = s.bestY;
+    s.bestDistance = 0;
+    s.pointNr      = 0;
+    for (d = 1; d < range + 1; d *= 2)
+    {
+      vo_tz_diamond(&s, sx, sy, d, p->extended);
+      if (p->fast && s.bestRound >= 2) break;
+    }
+    if (s.bestDistance == 1)
+    {
+      s.bestDistance = 0;
+      if (s.pointNr != 0) vo_tz_two_points(&s);
+    }
+  }
+  *mvx    = s.bestX;
+  *mvy    = s.bestY;
+  *sadOut = s.bestSad - vo_mv_cost(j->lambdaMotion, vo_mv_bits(s.bestX, s.bestY, j->predQx, j->predQy, 2, j->imvShift));
+  if (nProbes) *nProbes = s.probes;
+}

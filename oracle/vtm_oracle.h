@@ -108,6 +108,26 @@ typedef struct
 } vo_int_refine_io;
 void vo_int_refine(const vo_job* j, vo_int_refine_io* io);
 
+/* TZ search, InterSearch::xTZSearch (InterSearch.cpp:3640-3974) with its helpers xTZSearchHelp (:330-417),
+ * xTZ2PointSearch (:420-446) and xTZ8PointDiamondSearch (:503-705): the integer search of FastSearch=1
+ * (MESEARCH_DIAMOND: extended 0, fast 0), FastSearch=3 (MESEARCH_DIAMOND_ENHANCED: extended 1) and of the cached-MV
+ * re-search (fast 1, :3445).  Same field layout as RefTzParams in oracle/ref_harness.cpp.  No hash ME, no MCTS, no
+ * composite reference; subShiftMode 0 or 2 (mode 1 belongs to the selective search). */
+typedef struct
+{
+  int startX, startY;       /* rcMv on entry, 1/16 sample                                                  */
+  int hasInt2Nx2N;          /* pIntegerMv2Nx2NPred != NULL                                                 */
+  int int2Nx2NX, int2Nx2NY; /*   its value, integer pel                                                    */
+  int nSeeds;               /* m_uniMvListSize (<= 15)                                                     */
+  int seedX[16], seedY[16]; /* uniMvs[list][ref] of the history entries, newest first, 1/16 sample         */
+  int searchRange;          /* m_iSearchRange                                                              */
+  int extended, fast;       /* bExtendedSettings, bFastSettings                                            */
+  int firstSearchStop;      /* EncCfg::getFastMEAssumingSmootherMVEnabled                                  */
+  int posX, posY, picW, picH, maxCuW, maxCuH;
+} vo_tz_params;
+/* mvx,mvy: rcMv (integer pel); sad: ruiSAD; nProbes (optional): number of xTZSearchHelp + seed distortions */
+void vo_tz_search(const vo_job* j, const vo_tz_params* p, int* mvx, int* mvy, uint64_t* sad, int* nProbes);
+
 #ifdef __cplusplus
 }
 #endif

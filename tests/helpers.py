@@ -126,3 +126,23 @@ def clone_int_refine(io):
     c = B.IntRefine()
     C.memmove(C.byref(c), C.byref(io), C.sizeof(io))
     return c
+
+
+# ---- TZ search -------------------------------------------------------------------------------------------------------
+def tz_case(rng, x, y, pic_w, pic_h, search_range, extended=0, fast=0, first_stop=1, max_pel=20, n_seeds=None):
+    """Random state of one xTZSearch call: start MV (the AMVP predictor, 1/16 sample), optional 2Nx2N integer MV,
+    history MVs with duplicates."""
+    t = B.TzParams()
+    t.startX, t.startY = (int(rng.integers(-max_pel * 16, max_pel * 16 + 1)) for _ in range(2))
+    t.hasInt2Nx2N = int(rng.integers(0, 2))
+    t.int2Nx2NX, t.int2Nx2NY = (int(rng.integers(-max_pel, max_pel + 1)) for _ in range(2))
+    t.nSeeds = int(rng.integers(0, 16)) if n_seeds is None else n_seeds
+    for i in range(t.nSeeds):
+        if i and rng.integers(0, 3) == 0:
+            k = int(rng.integers(0, i))
+            t.seedX[i], t.seedY[i] = t.seedX[k], t.seedY[k]
+        else:
+            t.seedX[i], t.seedY[i] = (int(rng.integers(-max_pel * 16, max_pel * 16 + 1)) for _ in range(2))
+    t.searchRange, t.extended, t.fast, t.firstSearchStop = search_range, extended, fast, first_stop
+    t.posX, t.posY, t.picW, t.picH, t.maxCuW, t.maxCuH = x, y, pic_w, pic_h, 128, 128
+    return t

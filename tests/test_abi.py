@@ -61,7 +61,7 @@ def test_struct_layouts_match_the_header(tmp_path):
     import ctypes as C
     import subprocess
     from vtm_b200 import lib
-    pairs = {"vtmme_job": lib.CJob, "vtmme_result": lib.CResult, "vtmme_amvr": lib.CAmvr,
+    pairs = {"vtmme_job": lib.CJob, "vtmme_result": lib.CResult, "vtmme_amvr": lib.CAmvr, "vtmme_tz": lib.CTz,
              "vtmme_frame_params": lib.CFrameParams, "vtmme_mc_block": lib.CMcBlock, "vtmme_cand_job": lib.CCandJob}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "vtmme.h"', 'int main(void){']
     for cname, cls in pairs.items():

@@ -220,6 +220,56 @@ def test_job_search_int_refine(ms, oracle_lib):
     assert not bad, "single calls: %d of %d jobs differ, first: %s" % (len(bad), len(jobs), bad[:3])
 
 
+@pytest.mark.parametrize("extended,fast", [(0, 0), (1, 0), (0, 1)])
+def test_job_tz_search(ms, oracle_lib, extended, fast):
+    """vtmme_search with vtmme_tz: xTZSearch (InterSearch.cpp:3640-3974) as the integer search — FastSearch=1,
+    FastSearch=3 (extended) and the fast re-search — followed by the fractional refinement, against the oracle
+    (which is pinned on the reference's own xTZSearch): all shapes, FEN row sub-sampling, history seeds with
+    duplicates, 2Nx2N integer MV, border positions, real motion so that raster scan and star refinement run."""
+    from tests.helpers import tz_case
+    from vtm_b200 import Job, TzSearch
+    from vtm_b200.synth import make_pair
+    rng = np.random.default_rng(300 + 2 * extended + fast)
+    W, H = 256, 192
+    cur, ref, _ = make_pair(60 + extended, W, H, max_global=20, max_local=30, n_rects=4, sigma=6.0)
+    refp = pad_plane(ref)
+    ms.upload_picture(16, cur)
+    ms.upload_picture(17, refp, MARGIN)
+    stride = refp.shape[1]
+    jobs, want = [], []
+    for w in SIZES:
+        for h in SIZES:
+            if w == 4 and h == 4:
+                continue
+            for rep in range(3):
+                x = int(rng.integers(0, (W - w) // 4 + 1)) * 4
+                y = int(rng.integers(0, (H - h) // 4 + 1)) * 4
+                if rep == 2:
+                    x, y = [0, W - w][int(rng.integers(0, 2))], [0, H - h][int(rng.integers(0, 2))]
+                sr = [64, 32, 96][rep]
+                t = tz_case(rng, x, y, W, H, sr, extended, fast, first_stop=int(rep != 1), max_pel=20 if rep < 2 else 160)
+                pq = (int(rng.integers(-80, 81)), int(rng.integers(-80, 81)))
+                ssm = [0, 2, 2][rep]
+                ss = oracle_lib.vo_subshift(ssm, w, h)
+                lam = 31.33 if rep else 8.5
+                tz = TzSearch((t.startX, t.startY), sr, W, H, tuple((t.seedX[i], t.seedY[i]) for i in range(t.nSeeds)),
+                              (t.int2Nx2NX, t.int2Nx2NY) if t.hasInt2Nx2N else None, extended, fast, t.firstSearchStop)
+                jobs.append(Job(16, 17, x, y, w, h, (0, 0, 0, 0), pq, 0, ss, 10, 1, 0, 1, lam, None, None, tz))
+                oj = B.make_job(cur, refp, stride, (MARGIN + y) * stride + MARGIN + x, w, h, (0, 0, 0, 0), pq, 0, ssm, 10, 1,
+                                0, 1, lam, org_off=y * W + x, org_stride=W)
+                mx, my, sad = C.c_int(), C.c_int(), C.c_uint64()
+                oracle_lib.vo_tz_search(C.byref(oj), C.byref(t), C.byref(mx), C.byref(my), C.byref(sad), None)
+                hx, hy, qx, qy, cost = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_uint64()
+                oracle_lib.vo_frac_direct(C.byref(oj), mx.value, my.value, C.byref(hx), C.byref(hy), C.byref(qx),
+                                          C.byref(qy), C.byref(cost))
+                want.append((mx.value, my.value, sad.value, hx.value, hy.value, qx.value, qy.value, cost.value))
+    got = ms.search(jobs)
+    bad = [(i, jobs[i].w, jobs[i].h, got[i], want[i]) for i in range(len(jobs)) if got[i] != want[i]]
+    assert not bad, "%d of %d jobs differ, first: %s" % (len(bad), len(jobs), bad[:3])
+    got1 = [ms.search([j])[0] for j in jobs[::7]]
+    assert got1 == want[::7]
+
+
 def test_dist_host_all_shapes(ms, oracle_lib):
     """The DistParam-hook flavour: one block pair in host memory, SAD (subShift 0/1) and SATD, incl. 4x4."""
     rng = np.random.default_rng(79)

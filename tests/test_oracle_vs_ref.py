@@ -306,3 +306,41 @@ def test_int_refine(oracle_lib, ref_lib, imv, use_had):
             assert a.tuple() == b.tuple(), (w, h, rep, a.tuple(), b.tuple())
             n += 1
     assert n > 100
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("extended,fast", [(0, 0), (1, 0), (0, 1)])
+def test_tz_search(oracle_lib, ref_lib, extended, fast):
+    """xTZSearch (InterSearch.cpp:3640-3974): the reference's own member against the restatement — FastSearch=1
+    (diamond), FastSearch=3 (enhanced) and the fast re-search; real motion so that raster and star refinement run;
+    all CU shapes, FEN row sub-sampling, history seeds with duplicates, picture-border positions."""
+    from tests.helpers import MARGIN, pad_plane, tz_case
+    from vtm_b200.synth import make_pair
+    rng = np.random.default_rng(200 + 2 * extended + fast)
+    pic_w, pic_h = 256, 192
+    n = probes = 0
+    for seed in range(3):
+        cur, ref, _ = make_pair(50 + seed, pic_w, pic_h, max_global=20, max_local=30, n_rects=4, sigma=6.0)
+        refp = pad_plane(ref)
+        stride = refp.shape[1]
+        for w, h in [(a, b) for a in (4, 8, 16, 32, 64, 128) for b in (4, 8, 16, 32, 64, 128) if a * b > 16]:
+            for rep in range(3):
+                x = int(rng.integers(0, (pic_w - w) // 4 + 1)) * 4
+                y = int(rng.integers(0, (pic_h - h) // 4 + 1)) * 4
+                if rep == 2:
+                    x, y = [0, pic_w - w][int(rng.integers(0, 2))], [0, pic_h - h][int(rng.integers(0, 2))]
+                sr = [64, 32, 96][rep]
+                t = tz_case(rng, x, y, pic_w, pic_h, sr, extended, fast, first_stop=int(rep != 1),
+                            max_pel=20 if rep < 2 else 160)
+                pq = (int(rng.integers(-80, 81)), int(rng.integers(-80, 81)))
+                j = B.make_job(cur, refp, stride, (MARGIN + y) * stride + MARGIN + x, w, h, (0, 0, 0, 0), pq,
+                               [0, 2, 0][rep], [0, 2, 2][rep], 10, 1, 0, 0, 31.33 if rep else 8.5, org_off=y * pic_w + x,
+                               org_stride=pic_w)
+                a = (C.c_int(), C.c_int(), C.c_uint64(), C.c_int())
+                b = (C.c_int(), C.c_int(), C.c_uint64())
+                oracle_lib.vo_tz_search(C.byref(j), C.byref(t), *[C.byref(v) for v in a])
+                ref_lib.ref_tz_search(C.byref(j), C.byref(t), *[C.byref(v) for v in b])
+                assert [v.value for v in a[:3]] == [v.value for v in b], (w, h, rep, seed)
+                n += 1
+                probes += a[3].value
+    assert n > 300 and probes / n > 20

@@ -5,4 +5,4 @@ used by the tests and the standalone batched-ME benchmark.  There is no CPU fall
 anywhere, but every compute entry point needs the built library and a CUDA device.
 """
 from .lib import VtmmeError, load_library, library_path, build_library  # noqa: F401
-from .me import Amvr, MotionSearch, FrameParams, Job  # noqa: F401
+from .me import Amvr, MotionSearch, FrameParams, Job, TzSearch  # noqa: F401

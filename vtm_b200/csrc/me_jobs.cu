@@ -7,10 +7,13 @@
 //                         VABSDIFF, 8 displacements x 1 row per thread step.  Single-sub-block jobs keep their
 //                         argmin directly; larger patterns write one SAD surface per sub-block.
 //   me_job_reduce_kernel  sums the sub-block surfaces of a large pattern, adds lambda*bits, argmin.
+//   me_job_tz_kernel      the integer search as xTZSearch (FastSearch=1/3, me_tz.cuh) instead of the full search: one CTA
+//                         per job, leaves the same (cost, position) key for the refinement stage.
 //   me_job_frac_kernel    fractional refinement (me_frac.cuh) or integer / 4-pel AMVR refinement (me_intrefine.cuh,
 //                         fracMode 2 = xPatternSearchIntRefine) and result write-out.
 #include "me_frac.cuh"
 #include "me_intrefine.cuh"
+#include "me_tz.cuh"
 #include "me_kernels.h"
 
 namespace vtmme {
@@ -187,6 +190,38 @@ __global__ void __launch_bounds__(256) me_job_reduce_kernel(const DevJob* __rest
     best                       = o < best ? o : best;
   }
   if ((threadIdx.x & 31) == 0 && best != ~0ull) atomicMin(keys + blockIdx.y, best);
+}
+
+// TZ search jobs: one CTA per job, pattern staged in shared memory (row stride w), reference read through L1/L2
+__global__ void __launch_bounds__(kTzThreads) me_job_tz_kernel(const DevJob* __restrict__ jobs, const DevTz* __restrict__ tz,
+                                                               unsigned long long* __restrict__ keys)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ TzSmem sm;
+  int16_t*     s_pat = reinterpret_cast<int16_t*>(smem);
+  const DevJob j     = jobs[blockIdx.x];
+  const DevTz  t     = tz[blockIdx.x];
+  for (int i = threadIdx.x; i < j.w * j.h; i += kTzThreads)
+  {
+    const int y = i / j.w, x = i - y * j.w;
+    s_pat[i]    = j.org[(size_t) y * j.orgStride + x];
+  }
+  __syncthreads();
+  TzCtx c;
+  c.pat       = s_pat;
+  c.patStride = j.w;
+  c.refAtPU   = j.refAtPU;
+  c.refStride = j.refStride;
+  c.w         = j.w;
+  c.h         = j.h;
+  c.subShift  = j.subShift;
+  c.predQx    = j.predQx;
+  c.predQy    = j.predQy;
+  c.imvShift  = j.imvShift;
+  c.lambda    = j.lambda;
+  c.sm        = &sm;
+  const unsigned long long key = tz_search<kTzThreads / 32>(c, t);
+  if (threadIdx.x == 0) keys[blockIdx.x] = key;
 }
 
 __device__ __forceinline__ FracJob make_frac_job(const DevJob& j, int dx, int dy)
@@ -529,17 +564,26 @@ __global__ void __launch_bounds__(kFusedThreads) me_job_fused_kernel(const __gri
 cudaError_t launch_job_search_impl(const DevJob* dJobs, unsigned long long* dKeys, DevJobResult* dResults, int n,
                                    int maxRegions, int nSplit, int bandRows, int maxGx, bool anyMulti, uint32_t* dSurf,
                                    const long long* dSurfOff, uint32_t* dFracAcc, int maxFracChunks, cudaStream_t st,
-                                   int* launches)
+                                   int* launches, const DevTz* dTz, int maxPatternSamples)
 {
-  const size_t smem = (size_t) kJobOffRef + (size_t) (kJobBandRows + 31) * (maxGx * 8 + 40) * 2;
-  static SmemOptIn optIn;
-  if (cudaError_t e = optIn.ensure(me_job_sad_kernel, smem)) return e;
-  dim3 grid(maxRegions * nSplit, n, 1);
-  me_job_sad_kernel<<<grid, kJobThreads, smem, st>>>(dJobs, dKeys, dSurf, dSurfOff, nSplit, bandRows);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  *launches += 1;
-  if (anyMulti)
+  cudaError_t e;
+  if (dTz)
+  {
+    me_job_tz_kernel<<<n, kTzThreads, (size_t) maxPatternSamples * 2, st>>>(dJobs, dTz, dKeys);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    *launches += 1;
+  }
+  else
+  {
+    const size_t smem = (size_t) kJobOffRef + (size_t) (kJobBandRows + 31) * (maxGx * 8 + 40) * 2;
+    static SmemOptIn optIn;
+    if ((e = optIn.ensure(me_job_sad_kernel, smem)) != cudaSuccess) return e;
+    dim3 grid(maxRegions * nSplit, n, 1);
+    me_job_sad_kernel<<<grid, kJobThreads, smem, st>>>(dJobs, dKeys, dSurf, dSurfOff, nSplit, bandRows);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    *launches += 1;
+  }
+  if (anyMulti && !dTz)
   {
     dim3 g2(16, n, 1);
     me_job_reduce_kernel<<<g2, 256, 0, st>>>(dJobs, dKeys, dSurf, dSurfOff);

@@ -84,6 +84,20 @@ int    tree_pick_band_rows(int maxGx, int maxRows, bool subSampling);
 cudaError_t launch_tree_sad(const TreeParams& p, int nPairs, cudaStream_t st);
 cudaError_t launch_tree_upper(const TreeParams& p, int nPairs, cudaStream_t st);
 
+// TZ search of the frame path (me_tz.cu): fills keys like the tree kernels do
+struct TzFrameParams
+{
+  FrameGeom           g;
+  const DevPic*       cur;
+  const DevPic*       ref;
+  const short2*       predQ;
+  unsigned long long* keys;
+  int                 sr, ctu, imvShift, subShiftMode;
+  int                 extended, firstSearchStop;
+  double              lambda;
+};
+cudaError_t launch_tz_frame(const TzFrameParams& p, int nPairs, cudaStream_t st);
+
 // Fractional refinement + result write-out for the frame path.
 struct FracFrameParams
 {
@@ -109,6 +123,18 @@ struct DevAmvr
   uint32_t bits;
   int      posX, posY, picW, picH, maxCuW, maxCuH;   // clipMv
   double   fWeight;
+};
+
+// State of an xTZSearch call (InterSearch.cpp:3640-3974), see vtmme_tz in include/vtmme.h
+struct DevTz
+{
+  int startX, startY;
+  int hasInt2Nx2N, int2Nx2NX, int2Nx2NY;
+  int nSeeds;
+  int seedX[16], seedY[16];
+  int searchRange;
+  int extended, fast, firstSearchStop;
+  int posX, posY, picW, picH, maxCuW, maxCuH;
 };
 
 // Generic per-call jobs (vtmme_search)
@@ -139,7 +165,7 @@ struct DevJobResult
 cudaError_t launch_job_search_impl(const DevJob* dJobs, unsigned long long* dKeys, DevJobResult* dResults, int n,
                                    int maxRegions, int nSplit, int bandRows, int maxGx, bool anyMulti, uint32_t* dSurf,
                                    const long long* dSurfOff, uint32_t* dFracAcc, int maxFracChunks, cudaStream_t st,
-                                   int* launches);
+                                   int* launches, const DevTz* dTz = nullptr, int maxPatternSamples = 0);
 
 // One small job per launch (me_job_fused_kernel): descriptor and pattern as kernel parameters
 struct FusedJobArgs

@@ -1,0 +1,427 @@
+// TZ search, InterSearch::xTZSearch (EncoderLib/InterSearch.cpp:3640-3974) with xTZSearchHelp (:330-417),
+// xTZ2PointSearch (:420-446) and xTZ8PointDiamondSearch (:503-705): the integer search of FastSearch=1
+// (MESEARCH_DIAMOND), FastSearch=3 (MESEARCH_DIAMOND_ENHANCED, `extended`) and of the cached-MV re-search (`fast`).
+//
+// The reference probes one position after the other and updates its best state after each.  Between two decisions
+// that depend on that state, however, the probe positions are fixed: the points of one diamond, of the two-point
+// step, of the raster scan, the history seeds.  Such a *batch* is evaluated here in parallel — one warp per point, the
+// lanes over the samples — and reduced with the key (cost, order in the batch): the first strict minimum in
+// probe order, which is exactly the state the reference's sequential updates end in.  WARPS warps run one search
+// (4 for a per-call job, where latency counts; 1 in the batched frame search, where a CTA carries four independent
+// searches and nothing but warp-level synchronisation is needed); all their threads execute the (uniform) control
+// flow, the state lives in registers.
+#pragma once
+#include "me_common.cuh"
+#include "me_kernels.h"
+
+namespace vtmme {
+
+constexpr int kTzThreads   = 128;   // per-call jobs: 4 warps per search
+constexpr int kTzMaxPoints = 16;    // a diamond
+constexpr int kTzChunk     = 256;   // raster points per reduction
+
+struct TzState
+{
+  uint32_t best;          // cStruct.uiBestSad (cost incl. rate); 0xffffffff = none yet
+  int      bx, by;        // iBestX, iBestY
+  uint32_t dist, round;   // uiBestDistance, uiBestRound
+  int      pnr;           // ucPointNr
+  int      l, r, t, b;    // cStruct.searchRange
+};
+
+struct TzSmem
+{
+  unsigned long long key;
+};
+
+// SAD of the pattern (row stride patStride, 8-byte aligned rows) against the reference block at `cur`, rows r with
+// (r & (step-1)) == 0, shifted back up: DistParam::subShift semantics (RdCost.cpp:493-528).  One warp; the sum is
+// returned in every lane.
+__device__ __forceinline__ uint32_t tz_warp_sad(const int16_t* pat, int patStride, int w, int h, const int16_t* cur,
+                                                int refStride, int subShift)
+{
+  const int lane = threadIdx.x & 31;
+  const int q = w >> 2, rows = h >> subShift, units = q * rows;
+  const bool even = (reinterpret_cast<uintptr_t>(cur) & 2) == 0;   // reference rows start on a 4-byte boundary (stride is even)
+  uint32_t  s = 0;
+  for (int u = lane; u < units; u += 32)
+  {
+    const int      r = (u / q) << subShift, c = (u % q) << 2;
+    const uint2    o = *reinterpret_cast<const uint2*>(pat + r * patStride + c);
+    const int16_t* p = cur + (ptrdiff_t) r * refStride + c;
+    int            p0, p1, p2, p3;
+    if (even)
+    {
+      const uint32_t a = *reinterpret_cast<const uint32_t*>(p), b = *reinterpret_cast<const uint32_t*>(p + 2);
+      p0 = (int) (short) (a & 0xffffu);
+      p1 = (int) a >> 16;
+      p2 = (int) (short) (b & 0xffffu);
+      p3 = (int) b >> 16;
+    }
+    else
+    {
+      const uint32_t m = *reinterpret_cast<const uint32_t*>(p + 1);
+      p0 = (int) p[0];
+      p1 = (int) (short) (m & 0xffffu);
+      p2 = (int) m >> 16;
+      p3 = (int) p[3];
+    }
+    s = __sad((int) (short) (o.x & 0xffffu), p0, s);
+    s = __sad((int) o.x >> 16, p1, s);
+    s = __sad((int) (short) (o.y & 0xffffu), p2, s);
+    s = __sad((int) o.y >> 16, p3, s);
+  }
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+  return s << subShift;
+}
+
+struct TzCtx
+{
+  const int16_t* pat;       // pattern: shared memory (per-call jobs) or the current picture (frame search)
+  int            patStride;
+  const int16_t* refAtPU;   // global
+  int            refStride, w, h, subShift;
+  int            predQx, predQy, imvShift;
+  double         lambda;
+  TzSmem*        sm;
+};
+
+__device__ __forceinline__ uint32_t tz_cost(const TzCtx& c, int x, int y, uint32_t sad)
+{
+  return sad + mv_cost(c.lambda, mv_bits_q(x * 4, y * 4, c.predQx, c.predQy, c.imvShift));
+}
+
+// Ordered argmin of a batch of n points (uniform across the cooperating warps).  Returns the winner's index in the
+// batch and its cost, or -1 when no point beats `best` (strictly).
+template <int WARPS, class PointFn>
+__device__ __forceinline__ int tz_eval(const TzCtx& c, int n, uint32_t best, uint32_t& costOut, PointFn point)
+{
+  unsigned long long k = ~0ull;
+  if (WARPS > 1)
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (threadIdx.x == 0) c.sm->key = ~0ull;
+    __syncthreads();
+    for (int i = warp; i < n; i += WARPS)
+    {
+      int x, y;
+      point(i, x, y);
+      const uint32_t sad = tz_warp_sad(c.pat, c.patStride, c.w, c.h, c.refAtPU + (ptrdiff_t) y * c.refStride + x, c.refStride, c.subShift);
+      const unsigned long long ki = ((unsigned long long) tz_cost(c, x, y, sad) << 32) | (uint32_t) i;
+      k = ki < k ? ki : k;
+    }
+    if (lane == 0 && k != ~0ull) atomicMin(&c.sm->key, k);
+    __syncthreads();
+    k = c.sm->key;
+  }
+  else
+  {
+    for (int i = 0; i < n; i++)
+    {
+      int x, y;
+      point(i, x, y);
+      const uint32_t sad = tz_warp_sad(c.pat, c.patStride, c.w, c.h, c.refAtPU + (ptrdiff_t) y * c.refStride + x, c.refStride, c.subShift);
+      const unsigned long long ki = ((unsigned long long) tz_cost(c, x, y, sad) << 32) | (uint32_t) i;
+      k = ki < k ? ki : k;
+    }
+  }
+  costOut = (uint32_t) (k >> 32);
+  return (k != ~0ull && costOut < best) ? (int) (uint32_t) k : -1;
+}
+
+struct TzPoints
+{
+  short         x[kTzMaxPoints], y[kTzMaxPoints];
+  unsigned char  pnr[kTzMaxPoints];
+  unsigned short dist[kTzMaxPoints];
+  int           n;
+};
+
+// a coordinate that moved away from the start is checked against the window on its side, one equal to the start's is
+// not: the rule every branch of xTZ8PointDiamondSearch follows
+__device__ __forceinline__ void tz_add(TzPoints& p, const TzState& s, int sx, int sy, int dx, int dy, int pnr, int dist)
+{
+  const int x = sx + dx, y = sy + dy;
+  if ((dx < 0 && x < s.l) || (dx > 0 && x > s.r) || (dy < 0 && y < s.t) || (dy > 0 && y > s.b)) return;
+  p.x[p.n]    = (short) x;
+  p.y[p.n]    = (short) y;
+  p.pnr[p.n]  = (unsigned char) pnr;
+  p.dist[p.n] = (unsigned short) dist;
+  p.n++;
+}
+
+// xTZSearchHelp's state update for the winner of a batch
+__device__ __forceinline__ void tz_update(TzState& s, uint32_t cost, int x, int y, int pnr, uint32_t dist)
+{
+  s.best  = cost;
+  s.bx    = x;
+  s.by    = y;
+  s.dist  = dist;
+  s.round = 0;
+  s.pnr   = pnr;
+}
+
+template <int WARPS>
+__device__ __forceinline__ void tz_run_points(const TzCtx& c, TzState& s, const TzPoints& p)
+{
+  uint32_t  cost;
+  const int win = tz_eval<WARPS>(c, p.n, s.best, cost, [&](int i, int& x, int& y) { x = p.x[i]; y = p.y[i]; });
+  if (win >= 0) tz_update(s, cost, p.x[win], p.y[win], p.pnr[win], p.dist[win]);
+}
+
+// xTZ8PointDiamondSearch (:503-705)
+template <int WARPS>
+__device__ inline void tz_diamond(const TzCtx& c, TzState& s, int sx, int sy, int d, bool corners)
+{
+  TzPoints p;
+  p.n = 0;
+  s.round += 1;
+  if (d == 1)
+  {
+    if (corners)
+    {
+      if (sy - 1 >= s.t)
+      {
+        tz_add(p, s, sx, sy, -1, -1, 1, 1);
+        tz_add(p, s, sx, sy, 0, -1, 2, 1);
+        tz_add(p, s, sx, sy, 1, -1, 3, 1);
+      }
+    }
+    else
+      tz_add(p, s, sx, sy, 0, -1, 2, 1);
+    tz_add(p, s, sx, sy, -1, 0, 4, 1);
+    tz_add(p, s, sx, sy, 1, 0, 5, 1);
+    if (corners)
+    {
+      if (sy + 1 <= s.b)
+      {
+        tz_add(p, s, sx, sy, -1, 1, 6, 1);
+        tz_add(p, s, sx, sy, 0, 1, 7, 1);
+        tz_add(p, s, sx, sy, 1, 1, 8, 1);
+      }
+    }
+    else
+      tz_add(p, s, sx, sy, 0, 1, 7, 1);
+  }
+  else if (d <= 8)
+  {
+    const int h = d >> 1;
+    tz_add(p, s, sx, sy, 0, -d, 2, d);
+    tz_add(p, s, sx, sy, -h, -h, 1, h);
+    tz_add(p, s, sx, sy, h, -h, 3, h);
+    tz_add(p, s, sx, sy, -d, 0, 4, d);
+    tz_add(p, s, sx, sy, d, 0, 5, d);
+    tz_add(p, s, sx, sy, -h, h, 6, h);
+    tz_add(p, s, sx, sy, h, h, 8, h);
+    tz_add(p, s, sx, sy, 0, d, 7, d);
+  }
+  else
+  {
+    tz_add(p, s, sx, sy, 0, -d, 0, d);
+    tz_add(p, s, sx, sy, -d, 0, 0, d);
+    tz_add(p, s, sx, sy, d, 0, 0, d);
+    tz_add(p, s, sx, sy, 0, d, 0, d);
+    for (int i = 1; i < 4; i++)
+    {
+      const int q = (d >> 2) * i;
+      tz_add(p, s, sx, sy, -q, -d + q, 0, d);
+      tz_add(p, s, sx, sy, q, -d + q, 0, d);
+      tz_add(p, s, sx, sy, -q, d - q, 0, d);
+      tz_add(p, s, sx, sy, q, d - q, 0, d);
+    }
+  }
+  tz_run_points<WARPS>(c, s, p);
+}
+
+// xTZ2PointSearch (:420-446)
+template <int WARPS>
+__device__ inline void tz_two_points(const TzCtx& c, TzState& s)
+{
+  const int xo[2][9] = { { 0, -1, -1, 0, -1, +1, -1, -1, +1 }, { 0, 0, +1, +1, -1, +1, 0, +1, 0 } };
+  const int yo[2][9] = { { 0, 0, -1, -1, +1, -1, 0, +1, 0 }, { 0, -1, -1, 0, -1, +1, +1, +1, +1 } };
+  TzPoints  p;
+  p.n = 0;
+  for (int k = 0; k < 2; k++)
+  {
+    const int x = s.bx + xo[k][s.pnr], y = s.by + yo[k][s.pnr];
+    if (x >= s.l && x <= s.r && y >= s.t && y <= s.b)
+    {
+      p.x[p.n]    = (short) x;
+      p.y[p.n]    = (short) y;
+      p.pnr[p.n]  = 0;
+      p.dist[p.n] = 2;
+      p.n++;
+    }
+  }
+  tz_run_points<WARPS>(c, s, p);
+}
+
+// raster scan over [l,r] x [t,b] with step `win` (:3876-3898), in chunks of kTzChunk points
+template <int WARPS>
+__device__ inline void tz_raster(const TzCtx& c, TzState& s, int l, int r, int t, int b, int win)
+{
+  if (r < l || b < t) return;
+  const int nx = (r - l) / win + 1, ny = (b - t) / win + 1, n = nx * ny;
+  for (int base = 0; base < n; base += kTzChunk)
+  {
+    uint32_t  cost;
+    const int m   = min(kTzChunk, n - base);
+    const int idx = tz_eval<WARPS>(c, m, s.best, cost, [&](int i, int& x, int& y) {
+      const int g = base + i;
+      x           = l + (g % nx) * win;
+      y           = t + (g / nx) * win;
+    });
+    if (idx >= 0)
+    {
+      const int g = base + idx;
+      tz_update(s, cost, l + (g % nx) * win, t + (g / nx) * win, 0, (uint32_t) win);
+    }
+  }
+}
+
+// clipMv + changePrecision(INTERNAL -> QUARTER) + divideByPowerOf2(2)  (:3682-3683)
+__device__ __forceinline__ void tz_to_int(const DevTz& t, int& x, int& y)
+{
+  const int horMax = (t.picW + 8 - t.posX - 1) * 16, horMin = (-t.maxCuW - 8 - t.posX + 1) * 16;
+  const int verMax = (t.picH + 8 - t.posY - 1) * 16, verMin = (-t.maxCuH - 8 - t.posY + 1) * 16;
+  x = clampi(x, horMin, horMax);
+  y = clampi(y, verMin, verMax);
+  x = x >= 0 ? (x + 1) >> 2 : (x + 2) >> 2;
+  y = y >= 0 ? (y + 1) >> 2 : (y + 2) >> 2;
+  x = div_pow2_round(x, 2);
+  y = div_pow2_round(y, 2);
+}
+
+// The whole xTZSearch.  Returns the best key (cost, position) to every thread of the cooperating warps.
+template <int WARPS>
+__device__ inline unsigned long long tz_search(const TzCtx& c, const DevTz& t)
+{
+  const int raster = t.fast ? 8 : 5;
+  const int range  = t.searchRange;
+  TzState   s;
+  s.best = 0xffffffffu;
+  s.bx = s.by = 0;
+  s.dist = s.round = 0;
+  s.pnr = 0;
+  s.l = s.r = s.t = s.b = 0;
+
+  int sx = t.startX, sy = t.startY;
+  tz_to_int(t, sx, sy);
+  {
+    // start point, zero vector, 2Nx2N integer MV: each decision depends on the previous probe (:3695-3732)
+    TzPoints p;
+    p.n       = 1;
+    p.x[0]    = (short) sx;
+    p.y[0]    = (short) sy;
+    p.pnr[0]  = 0;
+    p.dist[0] = 0;
+    tz_run_points<WARPS>(c, s, p);
+    if (!t.fast && (sx != 0 || sy != 0) && (s.bx != 0 || s.by != 0))
+    {
+      p.x[0] = p.y[0] = 0;
+      tz_run_points<WARPS>(c, s, p);
+    }
+    if (t.hasInt2Nx2N)
+    {
+      int ix = t.int2Nx2NX * 16, iy = t.int2Nx2NY * 16;
+      tz_to_int(t, ix, iy);
+      if ((sx != ix || sy != iy) && (ix != s.bx || iy != s.by))
+      {
+        p.x[0] = (short) ix;
+        p.y[0] = (short) iy;
+        tz_run_points<WARPS>(c, s, p);
+      }
+    }
+  }
+  if (t.nSeeds > 0)
+  {
+    // history MVs (:3734-3765): duplicates of an earlier entry are skipped; only position and cost are updated
+    TzPoints  p;
+    const int horMax = (t.picW + 8 - t.posX - 1) * 16, horMin = (-t.maxCuW - 8 - t.posX + 1) * 16;
+    const int verMax = (t.picH + 8 - t.posY - 1) * 16, verMin = (-t.maxCuH - 8 - t.posY + 1) * 16;
+    p.n = 0;
+    for (int i = 0; i < t.nSeeds; i++)
+    {
+      int k = 0;
+      for (; k < i; k++)
+        if (t.seedX[k] == t.seedX[i] && t.seedY[k] == t.seedY[i]) break;
+      if (k < i) continue;
+      const int x = clampi(t.seedX[i], horMin, horMax), y = clampi(t.seedY[i], verMin, verMax);
+      p.x[p.n] = (short) (x >= 0 ? (x + 7) >> 4 : (x + 8) >> 4);   // changePrecision(INTERNAL -> INT)
+      p.y[p.n] = (short) (y >= 0 ? (y + 7) >> 4 : (y + 8) >> 4);
+      p.n++;
+    }
+    uint32_t  cost;
+    const int win = tz_eval<WARPS>(c, p.n, s.best, cost, [&](int i, int& x, int& y) { x = p.x[i]; y = p.y[i]; });
+    if (win >= 0)
+    {
+      s.best = cost;
+      s.bx   = p.x[win];
+      s.by   = p.y[win];
+    }
+  }
+  {
+    // xSetSearchRange around the best start point (:3767-3772)
+    const Window w = search_window(s.bx * 4, s.by * 4, t.posX, t.posY, t.picW, t.picH, t.maxCuW, range >> (t.fast ? 1 : 0));
+    s.l = w.l;
+    s.r = w.r;
+    s.t = w.t;
+    s.b = w.b;
+  }
+  sx = s.bx;
+  sy = s.by;
+  const bool bestIsZero = s.bx == 0 && s.by == 0;
+  for (int d = 1; d <= range; d *= 2)   // first search (:3803-3818)
+  {
+    tz_diamond<WARPS>(c, s, sx, sy, d, t.extended != 0);
+    if (t.firstSearchStop && s.round >= 3u) break;
+  }
+  if (t.extended && !bestIsZero)   // zero neighbourhood with half the range (:3841-3855)
+    for (int d = 1; d <= (range >> 1); d *= 2) tz_diamond<WARPS>(c, s, 0, 0, d, false);
+  if (s.dist == 1)   // :3858-3863
+  {
+    s.dist = 0;
+    tz_two_points<WARPS>(c, s);
+  }
+  if (t.extended)   // adaptive raster (:3865-3885)
+  {
+    int win = raster, l = s.l, r = s.r, tt = s.t, b = s.b;
+    if (!((int) s.dist >= raster))
+    {
+      win++;
+      l /= 2;
+      r /= 2;
+      tt /= 2;
+      b /= 2;
+    }
+    s.dist = (uint32_t) win;
+    tz_raster<WARPS>(c, s, l, r, tt, b, win);
+  }
+  else if ((int) s.dist >= raster)   // :3886-3899
+  {
+    s.dist = (uint32_t) raster;
+    tz_raster<WARPS>(c, s, s.l, s.r, s.t, s.b, raster);
+  }
+  while (s.dist > 0)   // star refinement (:3932-3967)
+  {
+    sx     = s.bx;
+    sy     = s.by;
+    s.dist = 0;
+    s.pnr  = 0;
+    for (int d = 1; d < range + 1; d *= 2)
+    {
+      tz_diamond<WARPS>(c, s, sx, sy, d, t.extended != 0);
+      if (t.fast && s.round >= 2u) break;
+    }
+    if (s.dist == 1)
+    {
+      s.dist = 0;
+      if (s.pnr != 0) tz_two_points<WARPS>(c, s);
+    }
+  }
+  return make_key(s.best, s.bx, s.by);
+}
+
+}   // namespace vtmme

@@ -341,8 +341,9 @@ int vtmme_search_frames_device(vtmme_ctx* ctx, int nPairs, const int32_t* curPic
   if (nPairs <= 0 || !curPics || !refPics || !prm || !dResults)
     return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search_frames", "null argument");
   if (prm->searchRange < 1 || prm->searchRange > 512 || prm->bitDepth < 8 || prm->bitDepth > 10 || prm->predSpread < 0 ||
-      (prm->subShiftMode != 0 && prm->subShiftMode != 2))
+      (prm->subShiftMode != 0 && prm->subShiftMode != 2) || (prm->fastSearch != 0 && prm->fastSearch != 1 && prm->fastSearch != 3))
     return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search_frames", "unsupported parameters");
+  const bool tzFrame = prm->fastSearch != 0;
   VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
 
   std::vector<DevPic> hc(nPairs), hr(nPairs);
@@ -379,8 +380,8 @@ int vtmme_search_frames_device(vtmme_ctx* ctx, int nPairs, const int32_t* curPic
   if ((rc = ensure(ctx, ctx->dCur, ctx->curArrCap, (size_t) nPairs * sizeof(DevPic))) != VTMME_OK) return rc;
   if ((rc = ensure(ctx, ctx->dRef, ctx->refArrCap, (size_t) nPairs * sizeof(DevPic))) != VTMME_OK) return rc;
   if ((rc = ensure(ctx, ctx->dKeys, ctx->keysCap, (size_t) nPairs * nCU * 8)) != VTMME_OK) return rc;
-  if ((rc = ensure(ctx, ctx->dSurf, ctx->surfCapBytes, (size_t) nPairs * nReg * surfCap * 4)) != VTMME_OK) return rc;
-  if (prm->subShiftMode == 2 &&
+  if (!tzFrame && (rc = ensure(ctx, ctx->dSurf, ctx->surfCapBytes, (size_t) nPairs * nReg * surfCap * 4)) != VTMME_OK) return rc;
+  if (!tzFrame && prm->subShiftMode == 2 &&
       (rc = ensure(ctx, ctx->dSurfEven, ctx->surfEvenCapBytes, (size_t) nPairs * nReg * surfCap * 4)) != VTMME_OK)
     return rc;
   if ((rc = ensure(ctx, ctx->dRegInfo, ctx->regInfoCap, (size_t) nPairs * nReg * sizeof(int4))) != VTMME_OK) return rc;
@@ -413,10 +414,33 @@ int vtmme_search_frames_device(vtmme_ctx* ctx, int nPairs, const int32_t* curPic
   tp.lambda   = prm->lambdaMotion;
   const bool prof = ctx->profiling;
   if (prof) VTMME_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-  VTMME_CUDA_CHECK(ctx, launch_tree_sad(tp, nPairs, ctx->stream));
-  if (prof) VTMME_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
-  VTMME_CUDA_CHECK(ctx, launch_tree_upper(tp, nPairs, ctx->stream));
-  if (prof) VTMME_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+  if (tzFrame)
+  {
+    // integer search = xTZSearch per CU (me_tz.cu); with profiling on its time is reported in the first slot
+    TzFrameParams zp;
+    zp.g               = g;
+    zp.cur             = ctx->dCur;
+    zp.ref             = ctx->dRef;
+    zp.predQ           = reinterpret_cast<const short2*>(dPredQ);
+    zp.keys            = ctx->dKeys;
+    zp.sr              = prm->searchRange;
+    zp.ctu             = prm->ctuSize;
+    zp.imvShift        = prm->imvShift;
+    zp.subShiftMode    = prm->subShiftMode;
+    zp.extended        = prm->fastSearch == 3;
+    zp.firstSearchStop = prm->tzFirstSearchStop;
+    zp.lambda          = prm->lambdaMotion;
+    VTMME_CUDA_CHECK(ctx, launch_tz_frame(zp, nPairs, ctx->stream));
+    if (prof) VTMME_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (prof) VTMME_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+  }
+  else
+  {
+    VTMME_CUDA_CHECK(ctx, launch_tree_sad(tp, nPairs, ctx->stream));
+    if (prof) VTMME_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    VTMME_CUDA_CHECK(ctx, launch_tree_upper(tp, nPairs, ctx->stream));
+    if (prof) VTMME_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+  }
 
   FracFrameParams fp;
   fp.g        = g;
@@ -437,7 +461,7 @@ int vtmme_search_frames_device(vtmme_ctx* ctx, int nPairs, const int32_t* curPic
     VTMME_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
     ctx->evValid = true;
   }
-  ctx->launches += 2 + fracLaunches;
+  ctx->launches += (tzFrame ? 1 : 2) + fracLaunches;
   return VTMME_OK;
 }
 
@@ -561,13 +585,17 @@ extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_
   int    maxGx = 1, maxRegions = 1, maxRows = 1, maxFracChunks = 1;
   long long totalRegions = 0;
   bool   anyMulti = false;
+  const bool tzCall = jobs[0].tz != nullptr;
+  int        maxPatternSamples = 0;
   for (int i = 0; i < n; i++)
   {
     const vtmme_job& j = jobs[i];
+    if ((j.tz != nullptr) != tzCall) return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search", "TZ and full-search jobs cannot share a call");
+    if (j.w * j.h > maxPatternSamples) maxPatternSamples = j.w * j.h;
     const bool pow2w = j.w >= 4 && j.w <= 128 && (j.w & (j.w - 1)) == 0;
     const bool pow2h = j.h >= 4 && j.h <= 128 && (j.h & (j.h - 1)) == 0;
     if (!pow2w || !pow2h) return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search", "w,h must be powers of two in [4,128]");
-    if (j.srRight < j.srLeft || j.srBottom < j.srTop || j.srRight - j.srLeft > 1024 || j.srBottom - j.srTop > 1024)
+    if (!tzCall && (j.srRight < j.srLeft || j.srBottom < j.srTop || j.srRight - j.srLeft > 1024 || j.srBottom - j.srTop > 1024))
       return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search", "bad search range");
     if (j.bitDepth < 8 || j.bitDepth > 10 || j.subShift < 0 || j.subShift > 4 || (j.h >> j.subShift) < 1)
       return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search", "unsupported bitDepth / subShift");
@@ -576,6 +604,28 @@ extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_
     const DevPic& rp = ctx->pics[j.refPic];
     int wrc;
     if ((wrc = wait_picture(ctx, j.refPic)) != VTMME_OK || (!j.org && (wrc = wait_picture(ctx, j.curPic)) != VTMME_OK)) return wrc;
+    if (tzCall)
+    {
+      // every probe lies in the clip rectangle of clipMvInPic (at most maxCu + 8 samples outside the picture), which is
+      // inside the device margin when the rectangle is the reference picture's own
+      const vtmme_tz& t = *j.tz;
+      if (t.picW != rp.width || t.picH != rp.height || t.maxCu < 1 || t.maxCu > 128 || t.nSeeds < 0 || t.nSeeds > 15 ||
+          t.searchRange < 1 || t.searchRange > 512)
+        return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search", "invalid vtmme_tz (picture size of refPic, maxCu <= 128, <= 15 seeds, range 1..512)");
+      if (j.org) orgBytes += align256((size_t) j.w * j.h * 2);
+      const int nReg = ((j.w + 31) >> 5) * ((j.h + 31) >> 5);
+      if (j.fracMode && nReg > maxFracChunks) maxFracChunks = nReg;
+      totalRegions += nReg;
+      if (j.fracMode < 0 || j.fracMode > 2) return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search", "fracMode must be 0, 1 or 2");
+      if (j.fracMode == 2)
+      {
+        const vtmme_amvr* a = j.amvr;
+        if (!a || (a->imv != 1 && a->imv != 2) || a->numCand < 1 || a->numCand > 2 || a->mvpIdx < 0 || a->mvpIdx >= a->numCand ||
+            a->picW != rp.width || a->picH != rp.height || a->maxCuW < 1 || a->maxCuW > 128 || a->maxCuH < 1 || a->maxCuH > 128)
+          return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search", "fracMode 2 needs a valid vtmme_amvr (imv 1|2, 1-2 candidates, picture size of refPic)");
+      }
+      continue;
+    }
     // every read (window + pattern + 8-tap halo + staging pad) must stay inside the device margin
     if (j.x + j.srLeft - 24 < -rp.margin || j.x + j.w + j.srRight + 24 > rp.width + rp.margin ||
         j.y + j.srTop - 8 < -rp.margin || j.y + j.h + j.srBottom + 8 > rp.height + rp.margin)
@@ -606,7 +656,7 @@ extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_
     }
   }
   // ---- one small job: single launch, descriptor + pattern as kernel parameters (me_job_fused_kernel)
-  if (n == 1 && jobs[0].w <= 32 && jobs[0].h <= 32)
+  if (n == 1 && jobs[0].w <= 32 && jobs[0].h <= 32 && !tzCall)
   {
     const vtmme_job& j  = jobs[0];
     const DevPic&    rp = ctx->pics[j.refPic];
@@ -693,7 +743,8 @@ extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_
 
   // ---- one pinned staging block, one device block: [jobs][surfOff][patterns] + [keys][results]
   const size_t offJobs = 0, offSurfOff = align256(offJobs + (size_t) n * sizeof(DevJob));
-  const size_t offOrg = align256(offSurfOff + (size_t) n * sizeof(long long));
+  const size_t offTz = align256(offSurfOff + (size_t) n * sizeof(long long));
+  const size_t offOrg = align256(offTz + (tzCall ? (size_t) n * sizeof(DevTz) : 0));
   const size_t upBytes = offOrg + orgBytes;
   const size_t offKeys = align256(upBytes), offRes = align256(offKeys + (size_t) n * 8);
   const size_t devBytes = offRes + (size_t) n * sizeof(DevJobResult);
@@ -747,10 +798,36 @@ extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_
     d.signedOrg = j.org != nullptr;
     d.lambda = j.lambdaMotion;
     d.amvr   = make_dev_amvr(j);
+    if (tzCall)
+    {
+      const vtmme_tz& t = *j.tz;
+      DevTz&          z = reinterpret_cast<DevTz*>(ctx->hPinned + offTz)[i];
+      z.startX      = t.startX;
+      z.startY      = t.startY;
+      z.hasInt2Nx2N = t.hasInt2Nx2N;
+      z.int2Nx2NX   = t.int2Nx2NX;
+      z.int2Nx2NY   = t.int2Nx2NY;
+      z.nSeeds      = t.nSeeds;
+      for (int k = 0; k < 16; k++)
+      {
+        z.seedX[k] = t.seedX[k];
+        z.seedY[k] = t.seedY[k];
+      }
+      z.searchRange     = t.searchRange;
+      z.extended        = t.extended;
+      z.fast            = t.fast;
+      z.firstSearchStop = t.firstSearchStop;
+      z.posX            = j.x;
+      z.posY            = j.y;
+      z.picW            = t.picW;
+      z.picH            = t.picH;
+      z.maxCuW = z.maxCuH = t.maxCu;
+      d.l = d.r = d.t = d.b = 0;
+    }
     hj[i]   = d;
     hoff[i] = (long long) surfCur;
     const int nReg = ((j.w + 31) >> 5) * ((j.h + 31) >> 5);
-    if (nReg > 1)
+    if (nReg > 1 && !tzCall)
     {
       const int wl8 = j.srLeft & ~7;
       surfCur += (size_t) nReg * (j.srBottom - j.srTop + 1) * (((j.srRight - wl8 + 8) >> 3) * 8);
@@ -772,7 +849,9 @@ extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_
                                                reinterpret_cast<DevJobResult*>(ctx->dPinnedAlias + offRes), n, maxRegions,
                                                nSplit, bandRows, maxGx, anyMulti, ctx->dJobSurf,
                                                reinterpret_cast<const long long*>(dIn + offSurfOff),
-                                               ctx->dJobFracAcc, maxFracChunks, ctx->stream, &launches));
+                                               ctx->dJobFracAcc, maxFracChunks, ctx->stream, &launches,
+                                               tzCall ? reinterpret_cast<const DevTz*>(dIn + offTz) : nullptr,
+                                               maxPatternSamples));
   ctx->launches += launches;
   // the frac kernel wrote the results straight into the mapped pinned block: no device-to-host copy
   const double tEnq = g_timing.on ? now_s() : 0;

@@ -30,6 +30,14 @@ class CAmvr(C.Structure):
                 ("fWeight", C.c_double)]
 
 
+class CTz(C.Structure):
+    """vtmme_tz"""
+    _fields_ = [("startX", C.c_int32), ("startY", C.c_int32), ("hasInt2Nx2N", C.c_int32), ("int2Nx2NX", C.c_int32),
+                ("int2Nx2NY", C.c_int32), ("nSeeds", C.c_int32), ("seedX", C.c_int32 * 16), ("seedY", C.c_int32 * 16),
+                ("searchRange", C.c_int32), ("extended", C.c_int32), ("fast", C.c_int32), ("firstSearchStop", C.c_int32),
+                ("picW", C.c_int32), ("picH", C.c_int32), ("maxCu", C.c_int32)]
+
+
 class CJob(C.Structure):
     """vtmme_job"""
     _fields_ = [("curPic", C.c_int32), ("refPic", C.c_int32), ("x", C.c_int32), ("y", C.c_int32),
@@ -37,7 +45,7 @@ class CJob(C.Structure):
                 ("srLeft", C.c_int32), ("srRight", C.c_int32), ("srTop", C.c_int32), ("srBottom", C.c_int32),
                 ("predQx", C.c_int32), ("predQy", C.c_int32), ("imvShift", C.c_int32), ("subShift", C.c_int32),
                 ("bitDepth", C.c_int32), ("useHad", C.c_int32), ("useAltHpel", C.c_int32), ("fracMode", C.c_int32),
-                ("lambdaMotion", C.c_double), ("amvr", C.POINTER(CAmvr))]
+                ("lambdaMotion", C.c_double), ("amvr", C.POINTER(CAmvr)), ("tz", C.POINTER(CTz))]
 
 
 class CResult(C.Structure):
@@ -60,7 +68,7 @@ class CFrameParams(C.Structure):
     """vtmme_frame_params"""
     _fields_ = [("searchRange", C.c_int32), ("bitDepth", C.c_int32), ("ctuSize", C.c_int32), ("imvShift", C.c_int32),
                 ("useHad", C.c_int32), ("fracMode", C.c_int32), ("predSpread", C.c_int32), ("subShiftMode", C.c_int32),
-                ("lambdaMotion", C.c_double)]
+                ("lambdaMotion", C.c_double), ("fastSearch", C.c_int32), ("tzFirstSearchStop", C.c_int32)]
 
 
 class CMcBlock(C.Structure):

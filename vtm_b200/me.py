@@ -9,7 +9,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .lib import CAmvr, CCandJob, CFrameParams, CJob, CMcBlock, CResult, ERR_NAMES, VtmmeError, load_library
+from .lib import CAmvr, CCandJob, CTz, CFrameParams, CJob, CMcBlock, CResult, ERR_NAMES, VtmmeError, load_library
 
 # vtmme_cu_result
 CU_RESULT_DTYPE = np.dtype([("mvQx", "<i2"), ("mvQy", "<i2"), ("intX", "<i2"), ("intY", "<i2"),
@@ -27,10 +27,13 @@ class FrameParams:
     predSpread: int = 0
     lambdaMotion: float = 31.33
     subShiftMode: int = 0
+    fastSearch: int = 0       # 0 full search, 1 TZ search, 3 enhanced TZ search (VTM's --FastSearch)
+    tzFirstSearchStop: int = 1
 
     def c(self):
         return CFrameParams(self.searchRange, self.bitDepth, self.ctuSize, self.imvShift, self.useHad, self.fracMode,
-                            self.predSpread, self.subShiftMode, self.lambdaMotion)
+                            self.predSpread, self.subShiftMode, self.lambdaMotion, self.fastSearch,
+                            self.tzFirstSearchStop)
 
 
 @dataclass
@@ -53,6 +56,35 @@ class Job:
     lambdaMotion: float = 31.33
     org: np.ndarray = None    # optional int16 pattern override (bi-pred)
     amvr: "Amvr" = None       # fracMode 2: state of the xPatternSearchIntRefine call that follows the search
+    tz: "TzSearch" = None     # integer search = xTZSearch (FastSearch=1/3) instead of the full search; `sr` is ignored
+
+
+@dataclass
+class TzSearch:
+    """vtmme_tz: what xTZSearch (EncoderLib/InterSearch.cpp:3640-3974) receives; MVs in 1/16 sample."""
+    start: tuple              # rcMv on entry
+    searchRange: int
+    picW: int
+    picH: int
+    seeds: tuple = ()         # history MVs, newest first
+    int2Nx2N: tuple = None    # integer-pel MV or None
+    extended: int = 0
+    fast: int = 0
+    firstSearchStop: int = 1
+    maxCu: int = 128
+
+    def c(self):
+        t = CTz()
+        t.startX, t.startY = self.start
+        t.hasInt2Nx2N = 0 if self.int2Nx2N is None else 1
+        if self.int2Nx2N is not None:
+            t.int2Nx2NX, t.int2Nx2NY = self.int2Nx2N
+        t.nSeeds = len(self.seeds)
+        for i, (x, y) in enumerate(self.seeds):
+            t.seedX[i], t.seedY[i] = x, y
+        t.searchRange, t.extended, t.fast, t.firstSearchStop = self.searchRange, self.extended, self.fast, self.firstSearchStop
+        t.picW, t.picH, t.maxCu = self.picW, self.picH, self.maxCu
+        return t
 
 
 @dataclass
@@ -175,9 +207,14 @@ class MotionSearch:
                 amvr = j.amvr.c()
                 keep.append(amvr)
                 amvr = C.pointer(amvr)
+            tz = None
+            if j.tz is not None:
+                tz = j.tz.c()
+                keep.append(tz)
+                tz = C.pointer(tz)
             cj[i] = CJob(j.curPic, j.refPic, j.x, j.y, j.w, j.h, org_ptr, org_stride, j.sr[0], j.sr[1], j.sr[2],
                          j.sr[3], j.predQ[0], j.predQ[1], j.imvShift, j.subShift, j.bitDepth, j.useHad, j.useAltHpel,
-                         j.fracMode, j.lambdaMotion, amvr)
+                         j.fracMode, j.lambdaMotion, amvr, tz)
         res = (CResult * n)()
         self._check(self.L.vtmme_search(self.ctx, cj, n, res), "vtmme_search")
         return [r.tuple() + (r.amvr_tuple() if j.fracMode == 2 else ()) for r, j in zip(res, jobs)]
