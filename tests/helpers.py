@@ -146,3 +146,33 @@ def tz_case(rng, x, y, pic_w, pic_h, search_range, extended=0, fast=0, first_sto
     t.searchRange, t.extended, t.fast, t.firstSearchStop = search_range, extended, fast, first_stop
     t.posX, t.posY, t.picW, t.picH, t.maxCuW, t.maxCuH = x, y, pic_w, pic_h, 128, 128
     return t
+
+
+def oracle_frame_tz(L, cur, ref_padded, margin, sr, lam, pred_q=None, fast_search=1, first_stop=1, sub_shift_mode=0):
+    """Every grid-aligned square CU through vo_tz_search (started at its predictor, no history seeds) + the fractional
+    refinement; result tuples like oracle_frame_search."""
+    h, w = cur.shape
+    stride = ref_padded.shape[1]
+    out = {}
+    idx = 0
+    for l in range(5):
+        s = 8 << l
+        for cy in range(h // s):
+            for cx in range(w // s):
+                x, y = cx * s, cy * s
+                pq = (0, 0) if pred_q is None else (int(pred_q[idx][0]), int(pred_q[idx][1]))
+                t = B.TzParams()
+                t.startX, t.startY = pq[0] * 4, pq[1] * 4
+                t.searchRange, t.extended, t.fast, t.firstSearchStop = sr, int(fast_search == 3), 0, first_stop
+                t.posX, t.posY, t.picW, t.picH, t.maxCuW, t.maxCuH = x, y, w, h, 128, 128
+                j = B.make_job(cur, ref_padded, stride, (margin + y) * stride + margin + x, s, s, (0, 0, 0, 0), pq, 0,
+                               sub_shift_mode, 10, 1, 0, 1, lam, org_off=y * w + x, org_stride=w)
+                mx, my, sad = C.c_int(), C.c_int(), C.c_uint64()
+                L.vo_tz_search(C.byref(j), C.byref(t), C.byref(mx), C.byref(my), C.byref(sad), None)
+                hx, hy, qx, qy, cost = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_uint64()
+                L.vo_frac_direct(C.byref(j), mx.value, my.value, C.byref(hx), C.byref(hy), C.byref(qx), C.byref(qy),
+                                 C.byref(cost))
+                out[idx] = (4 * mx.value + 2 * hx.value + qx.value, 4 * my.value + 2 * hy.value + qy.value, mx.value,
+                            my.value, int(sad.value), int(cost.value))
+                idx += 1
+    return out

@@ -270,6 +270,27 @@ def test_job_tz_search(ms, oracle_lib, extended, fast):
     assert got1 == want[::7]
 
 
+@pytest.mark.parametrize("fast_search,ssm,spread", [(1, 0, 0), (1, 2, 9), (3, 0, 9), (3, 2, 0)])
+def test_frame_tz_search(ms, oracle_lib, fast_search, ssm, spread):
+    """vtmme_search_frames with fastSearch 1 / 3: every CU's integer search is xTZSearch started at its predictor."""
+    from tests.helpers import oracle_frame_tz
+    from vtm_b200 import FrameParams
+    from vtm_b200.synth import make_pair, random_predictors
+    w, h, sr, lam = 320, 200, 64, 31.33
+    cur, ref, _ = make_pair(70 + fast_search + ssm, w, h, max_global=20, max_local=28, n_rects=4, sigma=5.0)
+    refp = pad_plane(ref)
+    ms.upload_picture(18, cur)
+    ms.upload_picture(19, refp, MARGIN)
+    ncu = ms.set_frame_size(w, h)
+    pred = random_predictors(5, ncu, spread) if spread else None
+    prm = FrameParams(searchRange=sr, lambdaMotion=lam, subShiftMode=ssm, fastSearch=fast_search,
+                      predSpread=2 * spread + 1 if spread else 0)
+    got = ms.search_frames([18], [19], prm, None if pred is None else pred[None])
+    want = oracle_frame_tz(oracle_lib, cur, refp, MARGIN, sr, lam, pred, fast_search, 1, ssm)
+    bad = [(i, gpu_tuple(got[0][i]), want[i]) for i in range(ncu) if gpu_tuple(got[0][i]) != want[i]]
+    assert not bad, "%d of %d CUs differ, first: %s" % (len(bad), ncu, bad[:3])
+
+
 def test_dist_host_all_shapes(ms, oracle_lib):
     """The DistParam-hook flavour: one block pair in host memory, SAD (subShift 0/1) and SATD, incl. 4x4."""
     rng = np.random.default_rng(79)
