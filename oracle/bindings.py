@@ -137,6 +137,8 @@ def ref():
         L.ref_int_refine.argtypes = [C.POINTER(Job), C.POINTER(IntRefine)]
         L.ref_tz_search.argtypes = [C.POINTER(Job), C.POINTER(TzParams), C.POINTER(_I), C.POINTER(_I),
                                     C.POINTER(C.c_uint64)]
+        L.ref_tz_batch.restype = C.c_double
+        L.ref_tz_batch.argtypes = [C.POINTER(Job), C.POINTER(TzParams), _I, _I, _P, _P]
         L.ref_mc_blocks.argtypes = [_I, _P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, C.POINTER(C.c_double)]
         L.ref_add_avg.argtypes = [_P, _P, _P, _I, _I, _I]
         L.ref_remove_high_freq.argtypes = [_P, _I, _P, _I, _I, _I, _I, _I]

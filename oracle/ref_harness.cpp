@@ -419,9 +419,34 @@ struct RefTzParams
   int posX, posY, picW, picH, maxCuW, maxCuH;
 };
 
+// per-thread environment of the xTZSearch calls: parameter sets and the CodingStructure shell are built once
+struct TzEnv
+{
+  PPS                       pps;
+  SPS                       sps;
+  std::vector<uint64_t>     shell;
+  std::vector<BlkUniMvInfo> list;
+  CodingStructure*          cs;
+  TzEnv() : shell((sizeof(CodingStructure) + 7) / 8, 0), list(15)
+  {
+    sps.setWrapAroundEnabledFlag(false);
+    // xClipMv (InterSearch.cpp:7735-7764) looks the sub-picture up: one sub-picture, not treated as a picture
+    pps.m_numSubPics = 1;
+    pps.m_subPics.resize(1);
+    pps.m_subPics[0].setTreatedAsPicFlag(false);
+    pps.setWrapAroundEnabledFlag(false);
+    cs      = reinterpret_cast<CodingStructure*>(shell.data());
+    cs->sps = &sps;
+    cs->pps = &pps;
+  }
+};
+thread_local TzEnv* t_tzEnv = nullptr;
+
 void ref_tz_search(const RefSearchJob* j, const RefTzParams* t, int* mvx, int* mvy, uint64_t* sad)
 {
   Probe& p = probe();
+  if (!t_tzEnv) t_tzEnv = new TzEnv();
+  TzEnv& e = *t_tzEnv;
   p.rd.m_motionLambda = j->lambdaMotion;
   p.rd.setPredictor(Mv(j->predQx, j->predQy));
   p.rd.setCostScale(2);
@@ -432,38 +457,25 @@ void ref_tz_search(const RefSearchJob* j, const RefTzParams* t, int* mvx, int* m
   p.m_iSearchRange = t->searchRange;
   clipMv = clipMvInPic;
 
-  PPS pps;
-  pps.setPicWidthInLumaSamples(t->picW);
-  pps.setPicHeightInLumaSamples(t->picH);
-  SPS sps;
-  sps.setMaxCUWidth(t->maxCuW);
-  sps.setMaxCUHeight(t->maxCuH);
-  sps.setWrapAroundEnabledFlag(false);
-  // xClipMv (InterSearch.cpp:7735-7764) looks the sub-picture up: one sub-picture, not treated as a picture
-  pps.m_numSubPics = 1;
-  pps.m_subPics.resize(1);
-  pps.m_subPics[0].setTreatedAsPicFlag(false);
-  pps.setWrapAroundEnabledFlag(false);
-  std::vector<uint64_t> shell((sizeof(CodingStructure) + 7) / 8, 0);
-  CodingStructure* cs = reinterpret_cast<CodingStructure*>(shell.data());
-  cs->sps = &sps;
-  cs->pps = &pps;
+  e.pps.setPicWidthInLumaSamples(t->picW);
+  e.pps.setPicHeightInLumaSamples(t->picH);
+  e.sps.setMaxCUWidth(t->maxCuW);
+  e.sps.setMaxCUHeight(t->maxCuH);
   CodingUnit cu(CHROMA_420, Area(t->posX, t->posY, j->w, j->h));
   cu.imv    = 0;
   cu.affine = false;
   PredictionUnit pu(CHROMA_420, Area(t->posX, t->posY, j->w, j->h));
   pu.cu = &cu;
-  pu.cs = cs;
+  pu.cs = e.cs;
 
   // history of uni-directional MVs (m_uniMvList): entry i of the caller's list is the i-th newest
   const int maxSize = 15;
-  std::vector<BlkUniMvInfo> list(maxSize);
-  p.m_uniMvList        = list.data();
+  p.m_uniMvList        = e.list.data();
   p.m_uniMvListMaxSize = maxSize;
   p.m_uniMvListSize    = t->nSeeds;
   p.m_uniMvListIdx     = t->nSeeds % maxSize;
   for (int i = 0; i < t->nSeeds; i++)
-    list[(p.m_uniMvListIdx - 1 - i + maxSize) % maxSize].uniMvs[0][0] = Mv(t->seedX[i], t->seedY[i]);
+    e.list[(p.m_uniMvListIdx - 1 - i + maxSize) % maxSize].uniMvs[0][0] = Mv(t->seedX[i], t->seedY[i]);
 
   CPelBuf pattern(j->org, j->orgStride, j->w, j->h);
   InterSearch::IntTZSearchStruct st;
@@ -482,6 +494,32 @@ void ref_tz_search(const RefSearchJob* j, const RefTzParams* t, int* mvx, int* m
   *mvx = mv.hor;
   *mvy = mv.ver;
   *sad = cost;
+}
+
+// n TZ searches over nThreads workers; mv = n x {x, y}; returns wall seconds (CPU baseline of the batched TZ search)
+double ref_tz_batch(const RefSearchJob* jobs, const RefTzParams* tz, int n, int nThreads, int* mv, uint64_t* sad)
+{
+  if (nThreads < 1) nThreads = 1;
+  std::atomic<int> next(0);
+  auto t0 = std::chrono::steady_clock::now();
+  auto worker = [&]() {
+    for (;;)
+    {
+      int i = next.fetch_add(16);
+      if (i >= n) break;
+      const int e = i + 16 < n ? i + 16 : n;
+      for (; i < e; i++) ref_tz_search(&jobs[i], &tz[i], &mv[2 * i], &mv[2 * i + 1], &sad[i]);
+    }
+  };
+  if (nThreads == 1)
+    worker();
+  else
+  {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nThreads; t++) th.emplace_back(worker);
+    for (auto& t : th) t.join();
+  }
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
 // Batch driver used as the CPU baseline: nThreads workers over disjoint job ranges.
