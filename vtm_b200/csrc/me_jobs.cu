@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kTzThreads) me_job_tz_kernel(const DevJob* __r
   c.imvShift  = j.imvShift;
   c.lambda    = j.lambda;
   c.sm        = &sm;
-  const unsigned long long key = tz_search<kTzThreads / 32>(c, t);
+  const unsigned long long key = tz_search<TzEvalWarps<kTzThreads / 32>>(c, t);
   if (threadIdx.x == 0) keys[blockIdx.x] = key;
 }
 

@@ -87,7 +87,8 @@ struct TzCtx
   TzSmem*        sm;
 };
 
-__device__ __forceinline__ uint32_t tz_cost(const TzCtx& c, int x, int y, uint32_t sad)
+template <class CTX>
+__device__ __forceinline__ uint32_t tz_cost(const CTX& c, int x, int y, uint32_t sad)
 {
   return sad + mv_cost(c.lambda, mv_bits_q(x * 4, y * 4, c.predQx, c.predQy, c.imvShift));
 }
@@ -131,6 +132,138 @@ __device__ __forceinline__ int tz_eval(const TzCtx& c, int n, uint32_t best, uin
   return (k != ~0ull && costOut < best) ? (int) (uint32_t) k : -1;
 }
 
+// evaluator of the generic path: WARPS warps per search, any block size, pattern and reference read from memory
+template <int WARPS>
+struct TzEvalWarps
+{
+  using Ctx = TzCtx;
+  template <class PointFn>
+  static __device__ __forceinline__ int eval(const Ctx& c, int n, uint32_t best, uint32_t& costOut, PointFn point)
+  {
+    return tz_eval<WARPS>(c, n, best, costOut, point);
+  }
+};
+
+// Evaluator of the batched frame search: one warp per search, square CU of SIZE samples with row sub-sampling SS known
+// at compile time.  A probe is spread over LP lanes (one sampled row each, or several for the largest CUs), so a warp
+// evaluates PPW = 32 / LP probes of a batch at a time; the pattern rows of a lane stay in registers (CUs up to 32x32).
+// Reference rows are fetched as aligned 32-bit words and shifted into place when the probe's x is odd.
+template <int SIZE, int SS>
+struct TzEvalTile
+{
+  static constexpr int  ROWS   = SIZE >> SS;               // sampled rows
+  static constexpr int  LP     = ROWS < 32 ? ROWS : 32;    // lanes per probe
+  static constexpr int  PPW    = 32 / LP;                  // probes per warp and round
+  static constexpr int  RPL    = ROWS / LP;                // rows per lane
+  static constexpr bool PATREG = SIZE * RPL <= 32;
+  struct Ctx
+  {
+    int            pat[PATREG ? SIZE * RPL : 1];   // this lane's pattern rows, one sample per register
+    const int16_t* patPtr;                         // pattern in the current picture (16-byte aligned rows)
+    int            patStride;
+    const int16_t* refAtPU;
+    int            refStride;
+    int            predQx, predQy, imvShift;
+    double         lambda;
+  };
+
+  static __device__ __forceinline__ void load_pattern(Ctx& c)
+  {
+    if (!PATREG) return;
+    const int rl = (threadIdx.x & 31) % LP;
+#pragma unroll
+    for (int k = 0; k < RPL; k++)
+    {
+      const int16_t* row = c.patPtr + (ptrdiff_t) ((rl + k * LP) << SS) * c.patStride;
+#pragma unroll
+      for (int x = 0; x < SIZE; x += 8)
+      {
+        const uint4    v    = *reinterpret_cast<const uint4*>(row + x);
+        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+          c.pat[k * SIZE + x + 2 * i]     = (int) (w[i] & 0xffffu);
+          c.pat[k * SIZE + x + 2 * i + 1] = (int) (w[i] >> 16);
+        }
+      }
+    }
+  }
+
+  // this lane's share of SAD(pattern, block at blk): its RPL sampled rows
+  static __device__ __forceinline__ uint32_t lane_sad(const Ctx& c, const int16_t* blk, int rl)
+  {
+    const unsigned sh = (reinterpret_cast<uintptr_t>(blk) & 2) ? 16u : 0u;   // rows start odd (stride is even: same for all)
+    uint32_t       acc = 0;
+#pragma unroll
+    for (int k = 0; k < RPL; k++)
+    {
+      const int       r = (rl + k * LP) << SS;
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(blk + (ptrdiff_t) r * c.refStride) & ~(uintptr_t) 3);
+      uint32_t        carry = w[0];
+#pragma unroll
+      for (int x = 0; x < SIZE; x += 8)
+      {
+        const uint32_t w1 = w[x / 2 + 1], w2 = w[x / 2 + 2], w3 = w[x / 2 + 3], w4 = w[x / 2 + 4];
+        const uint32_t a[4] = { __funnelshift_r(carry, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                                __funnelshift_r(w3, w4, sh) };
+        carry = w4;
+        if (PATREG)
+        {
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+          {
+            acc = __sad(c.pat[k * SIZE + x + 2 * i], (int) (a[i] & 0xffffu), acc);
+            acc = __sad(c.pat[k * SIZE + x + 2 * i + 1], (int) (a[i] >> 16), acc);
+          }
+        }
+        else
+        {
+          const uint4    v    = *reinterpret_cast<const uint4*>(c.patPtr + (ptrdiff_t) r * c.patStride + x);
+          const uint32_t o[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+          {
+            acc = __sad((int) (o[i] & 0xffffu), (int) (a[i] & 0xffffu), acc);
+            acc = __sad((int) (o[i] >> 16), (int) (a[i] >> 16), acc);
+          }
+        }
+      }
+    }
+    return acc;
+  }
+
+  template <class PointFn>
+  static __device__ __forceinline__ int eval(const Ctx& c, int n, uint32_t best, uint32_t& costOut, PointFn point)
+  {
+    const int lane = threadIdx.x & 31, g = lane / LP, rl = lane % LP;
+    unsigned long long k = ~0ull;
+    for (int i0 = 0; i0 < n; i0 += PPW)
+    {
+      const int  i   = i0 + g;
+      const bool act = i < n;
+      int        x = 0, y = 0;
+      if (act) point(i, x, y);
+      uint32_t s = lane_sad(c, c.refAtPU + (ptrdiff_t) y * c.refStride + x, rl);
+#pragma unroll
+      for (int m = LP >> 1; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+      if (act)
+      {
+        const unsigned long long ki = ((unsigned long long) tz_cost(c, x, y, s << SS) << 32) | (uint32_t) i;
+        k = ki < k ? ki : k;
+      }
+    }
+#pragma unroll
+    for (int m = LP; m < 32; m <<= 1)
+    {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, k, m);
+      k                          = o < k ? o : k;
+    }
+    costOut = (uint32_t) (k >> 32);
+    return (k != ~0ull && costOut < best) ? (int) (uint32_t) k : -1;
+  }
+};
+
 struct TzPoints
 {
   short         x[kTzMaxPoints], y[kTzMaxPoints];
@@ -163,17 +296,17 @@ __device__ __forceinline__ void tz_update(TzState& s, uint32_t cost, int x, int 
   s.pnr   = pnr;
 }
 
-template <int WARPS>
-__device__ __forceinline__ void tz_run_points(const TzCtx& c, TzState& s, const TzPoints& p)
+template <class EV>
+__device__ __forceinline__ void tz_run_points(const typename EV::Ctx& c, TzState& s, const TzPoints& p)
 {
   uint32_t  cost;
-  const int win = tz_eval<WARPS>(c, p.n, s.best, cost, [&](int i, int& x, int& y) { x = p.x[i]; y = p.y[i]; });
+  const int win = EV::eval(c, p.n, s.best, cost, [&](int i, int& x, int& y) { x = p.x[i]; y = p.y[i]; });
   if (win >= 0) tz_update(s, cost, p.x[win], p.y[win], p.pnr[win], p.dist[win]);
 }
 
 // xTZ8PointDiamondSearch (:503-705)
-template <int WARPS>
-__device__ inline void tz_diamond(const TzCtx& c, TzState& s, int sx, int sy, int d, bool corners)
+template <class EV>
+__device__ inline void tz_diamond(const typename EV::Ctx& c, TzState& s, int sx, int sy, int d, bool corners)
 {
   TzPoints p;
   p.n = 0;
@@ -232,12 +365,12 @@ __device__ inline void tz_diamond(const TzCtx& c, TzState& s, int sx, int sy, in
       tz_add(p, s, sx, sy, q, d - q, 0, d);
     }
   }
-  tz_run_points<WARPS>(c, s, p);
+  tz_run_points<EV>(c, s, p);
 }
 
 // xTZ2PointSearch (:420-446)
-template <int WARPS>
-__device__ inline void tz_two_points(const TzCtx& c, TzState& s)
+template <class EV>
+__device__ inline void tz_two_points(const typename EV::Ctx& c, TzState& s)
 {
   const int xo[2][9] = { { 0, -1, -1, 0, -1, +1, -1, -1, +1 }, { 0, 0, +1, +1, -1, +1, 0, +1, 0 } };
   const int yo[2][9] = { { 0, 0, -1, -1, +1, -1, 0, +1, 0 }, { 0, -1, -1, 0, -1, +1, +1, +1, +1 } };
@@ -255,12 +388,12 @@ __device__ inline void tz_two_points(const TzCtx& c, TzState& s)
       p.n++;
     }
   }
-  tz_run_points<WARPS>(c, s, p);
+  tz_run_points<EV>(c, s, p);
 }
 
 // raster scan over [l,r] x [t,b] with step `win` (:3876-3898), in chunks of kTzChunk points
-template <int WARPS>
-__device__ inline void tz_raster(const TzCtx& c, TzState& s, int l, int r, int t, int b, int win)
+template <class EV>
+__device__ inline void tz_raster(const typename EV::Ctx& c, TzState& s, int l, int r, int t, int b, int win)
 {
   if (r < l || b < t) return;
   const int nx = (r - l) / win + 1, ny = (b - t) / win + 1, n = nx * ny;
@@ -268,7 +401,7 @@ __device__ inline void tz_raster(const TzCtx& c, TzState& s, int l, int r, int t
   {
     uint32_t  cost;
     const int m   = min(kTzChunk, n - base);
-    const int idx = tz_eval<WARPS>(c, m, s.best, cost, [&](int i, int& x, int& y) {
+    const int idx = EV::eval(c, m, s.best, cost, [&](int i, int& x, int& y) {
       const int g = base + i;
       x           = l + (g % nx) * win;
       y           = t + (g / nx) * win;
@@ -295,8 +428,8 @@ __device__ __forceinline__ void tz_to_int(const DevTz& t, int& x, int& y)
 }
 
 // The whole xTZSearch.  Returns the best key (cost, position) to every thread of the cooperating warps.
-template <int WARPS>
-__device__ inline unsigned long long tz_search(const TzCtx& c, const DevTz& t)
+template <class EV>
+__device__ inline unsigned long long tz_search(const typename EV::Ctx& c, const DevTz& t)
 {
   const int raster = t.fast ? 8 : 5;
   const int range  = t.searchRange;
@@ -317,11 +450,11 @@ __device__ inline unsigned long long tz_search(const TzCtx& c, const DevTz& t)
     p.y[0]    = (short) sy;
     p.pnr[0]  = 0;
     p.dist[0] = 0;
-    tz_run_points<WARPS>(c, s, p);
+    tz_run_points<EV>(c, s, p);
     if (!t.fast && (sx != 0 || sy != 0) && (s.bx != 0 || s.by != 0))
     {
       p.x[0] = p.y[0] = 0;
-      tz_run_points<WARPS>(c, s, p);
+      tz_run_points<EV>(c, s, p);
     }
     if (t.hasInt2Nx2N)
     {
@@ -331,7 +464,7 @@ __device__ inline unsigned long long tz_search(const TzCtx& c, const DevTz& t)
       {
         p.x[0] = (short) ix;
         p.y[0] = (short) iy;
-        tz_run_points<WARPS>(c, s, p);
+        tz_run_points<EV>(c, s, p);
       }
     }
   }
@@ -354,7 +487,7 @@ __device__ inline unsigned long long tz_search(const TzCtx& c, const DevTz& t)
       p.n++;
     }
     uint32_t  cost;
-    const int win = tz_eval<WARPS>(c, p.n, s.best, cost, [&](int i, int& x, int& y) { x = p.x[i]; y = p.y[i]; });
+    const int win = EV::eval(c, p.n, s.best, cost, [&](int i, int& x, int& y) { x = p.x[i]; y = p.y[i]; });
     if (win >= 0)
     {
       s.best = cost;
@@ -375,15 +508,15 @@ __device__ inline unsigned long long tz_search(const TzCtx& c, const DevTz& t)
   const bool bestIsZero = s.bx == 0 && s.by == 0;
   for (int d = 1; d <= range; d *= 2)   // first search (:3803-3818)
   {
-    tz_diamond<WARPS>(c, s, sx, sy, d, t.extended != 0);
+    tz_diamond<EV>(c, s, sx, sy, d, t.extended != 0);
     if (t.firstSearchStop && s.round >= 3u) break;
   }
   if (t.extended && !bestIsZero)   // zero neighbourhood with half the range (:3841-3855)
-    for (int d = 1; d <= (range >> 1); d *= 2) tz_diamond<WARPS>(c, s, 0, 0, d, false);
+    for (int d = 1; d <= (range >> 1); d *= 2) tz_diamond<EV>(c, s, 0, 0, d, false);
   if (s.dist == 1)   // :3858-3863
   {
     s.dist = 0;
-    tz_two_points<WARPS>(c, s);
+    tz_two_points<EV>(c, s);
   }
   if (t.extended)   // adaptive raster (:3865-3885)
   {
@@ -397,12 +530,12 @@ __device__ inline unsigned long long tz_search(const TzCtx& c, const DevTz& t)
       b /= 2;
     }
     s.dist = (uint32_t) win;
-    tz_raster<WARPS>(c, s, l, r, tt, b, win);
+    tz_raster<EV>(c, s, l, r, tt, b, win);
   }
   else if ((int) s.dist >= raster)   // :3886-3899
   {
     s.dist = (uint32_t) raster;
-    tz_raster<WARPS>(c, s, s.l, s.r, s.t, s.b, raster);
+    tz_raster<EV>(c, s, s.l, s.r, s.t, s.b, raster);
   }
   while (s.dist > 0)   // star refinement (:3932-3967)
   {
@@ -412,13 +545,13 @@ __device__ inline unsigned long long tz_search(const TzCtx& c, const DevTz& t)
     s.pnr  = 0;
     for (int d = 1; d < range + 1; d *= 2)
     {
-      tz_diamond<WARPS>(c, s, sx, sy, d, t.extended != 0);
+      tz_diamond<EV>(c, s, sx, sy, d, t.extended != 0);
       if (t.fast && s.round >= 2u) break;
     }
     if (s.dist == 1)
     {
       s.dist = 0;
-      if (s.pnr != 0) tz_two_points<WARPS>(c, s);
+      if (s.pnr != 0) tz_two_points<EV>(c, s);
     }
   }
   return make_key(s.best, s.bx, s.by);
