@@ -96,7 +96,7 @@ struct TzFrameParams
   int                 extended, firstSearchStop;
   double              lambda;
 };
-cudaError_t launch_tz_frame(const TzFrameParams& p, int nPairs, cudaStream_t st);
+cudaError_t launch_tz_frame(const TzFrameParams& p, int nPairs, cudaStream_t st, int* launches);
 
 // Fractional refinement + result write-out for the frame path.
 struct FracFrameParams

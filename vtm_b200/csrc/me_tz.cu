@@ -32,19 +32,16 @@ __device__ __forceinline__ unsigned long long tz_frame_cu(const TzFrameParams& p
   return tz_search<EV>(c, t);
 }
 
-__global__ void __launch_bounds__(128) me_tz_frame_kernel(TzFrameParams p)
+// one launch per CU level (its own register budget and occupancy), four searches per CTA
+template <int SIZE, int SS>
+__global__ void __launch_bounds__(128) me_tz_frame_kernel(TzFrameParams p, int level)
 {
   const int warp = threadIdx.x >> 5;
-  const int nCU  = p.g.off[5];
-  const int item = blockIdx.x * 4 + warp, pair = blockIdx.y;
-  if (item >= nCU) return;
-  const int cu = nCU - 1 - item;   // level-major order, reversed: 128x128 CUs first
-  int       level = 0;
-#pragma unroll
-  for (int l = 1; l < 5; l++)
-    if (cu >= p.g.off[l]) level = l;
-  const int size = 8 << level, li = cu - p.g.off[level];
-  const int x = (li % p.g.nx[level]) * size, y = (li / p.g.nx[level]) * size;
+  const int nCU  = p.g.off[5], nLevel = p.g.nx[level] * p.g.ny[level];
+  const int li = blockIdx.x * 4 + warp, pair = blockIdx.y;
+  if (li >= nLevel) return;
+  const int cu = p.g.off[level] + li;
+  const int x = (li % p.g.nx[level]) * SIZE, y = (li / p.g.nx[level]) * SIZE;
   const DevPic cur = p.cur[pair], ref = p.ref[pair];
   short2       pr  = make_short2(0, 0);
   if (p.predQ) pr = p.predQ[(size_t) pair * nCU + cu];
@@ -64,27 +61,35 @@ __global__ void __launch_bounds__(128) me_tz_frame_kernel(TzFrameParams p)
   t.picW            = p.g.picW;
   t.picH            = p.g.picH;
   t.maxCuW = t.maxCuH = p.ctu;
-  // DistParam::subShift of the integer search: 1 for CUs of 16..64 rows when subShiftMode is 2 (RdCost.cpp:310-316)
-  const bool ss = p.subShiftMode == 2;
-  unsigned long long key;
-  switch (level)
-  {
-  case 0: key = tz_frame_cu<8, 0>(p, cur, ref, x, y, pr, t); break;
-  case 1: key = ss ? tz_frame_cu<16, 1>(p, cur, ref, x, y, pr, t) : tz_frame_cu<16, 0>(p, cur, ref, x, y, pr, t); break;
-  case 2: key = ss ? tz_frame_cu<32, 1>(p, cur, ref, x, y, pr, t) : tz_frame_cu<32, 0>(p, cur, ref, x, y, pr, t); break;
-  case 3: key = ss ? tz_frame_cu<64, 1>(p, cur, ref, x, y, pr, t) : tz_frame_cu<64, 0>(p, cur, ref, x, y, pr, t); break;
-  default: key = tz_frame_cu<128, 0>(p, cur, ref, x, y, pr, t); break;
-  }
+  const unsigned long long key = tz_frame_cu<SIZE, SS>(p, cur, ref, x, y, pr, t);
   if ((threadIdx.x & 31) == 0) p.keys[(size_t) pair * nCU + cu] = key;
+}
+
+template <int SIZE, int SS>
+cudaError_t launch_level(const TzFrameParams& p, int level, int nPairs, cudaStream_t st)
+{
+  const int n = p.g.nx[level] * p.g.ny[level];
+  if (n == 0) return cudaSuccess;
+  dim3 grid((n + 3) / 4, nPairs, 1);
+  me_tz_frame_kernel<SIZE, SS><<<grid, 128, 0, st>>>(p, level);
+  return cudaGetLastError();
 }
 
 }   // namespace
 
-cudaError_t launch_tz_frame(const TzFrameParams& p, int nPairs, cudaStream_t st)
+// DistParam::subShift of the integer search is 1 for CUs of 16..64 rows when subShiftMode is 2 (RdCost.cpp:310-316).
+// Largest CUs first.  Returns the number of kernels launched in *launches.
+cudaError_t launch_tz_frame(const TzFrameParams& p, int nPairs, cudaStream_t st, int* launches)
 {
-  dim3 grid((p.g.off[5] + 3) / 4, nPairs, 1);
-  me_tz_frame_kernel<<<grid, 128, 0, st>>>(p);
-  return cudaGetLastError();
+  const bool  ss = p.subShiftMode == 2;
+  cudaError_t e;
+  if ((e = launch_level<128, 0>(p, 4, nPairs, st)) != cudaSuccess) return e;
+  if ((e = ss ? launch_level<64, 1>(p, 3, nPairs, st) : launch_level<64, 0>(p, 3, nPairs, st)) != cudaSuccess) return e;
+  if ((e = ss ? launch_level<32, 1>(p, 2, nPairs, st) : launch_level<32, 0>(p, 2, nPairs, st)) != cudaSuccess) return e;
+  if ((e = ss ? launch_level<16, 1>(p, 1, nPairs, st) : launch_level<16, 0>(p, 1, nPairs, st)) != cudaSuccess) return e;
+  if ((e = launch_level<8, 0>(p, 0, nPairs, st)) != cudaSuccess) return e;
+  for (int l = 0; l < 5; l++) *launches += p.g.nx[l] * p.g.ny[l] > 0;
+  return cudaSuccess;
 }
 
 }   // namespace vtmme

@@ -145,21 +145,27 @@ struct TzEvalWarps
 };
 
 // Evaluator of the batched frame search: one warp per search, square CU of SIZE samples with row sub-sampling SS known
-// at compile time.  A probe is spread over LP lanes (one sampled row each, or several for the largest CUs), so a warp
-// evaluates PPW = 32 / LP probes of a batch at a time; the pattern rows of a lane stay in registers (CUs up to 32x32).
-// Reference rows are fetched as aligned 32-bit words and shifted into place when the probe's x is odd.
+// at compile time.  The 32 lanes lie ALONG the rows of a probe — two samples (one 32-bit word) per lane, LX lanes per
+// row, RPI = 32 / LX rows per load instruction — so that a load touches as few 128-byte lines as the block has rows
+// (the probes come straight from L1/L2, whose cost is one wavefront per distinct line and instruction).  A probe at
+// an odd x takes the second half of its word pair from the neighbouring lane.  K probes are in flight at a time; their
+// per-lane partial sums are reduced with a butterfly that halves the number of live values at every stage (about one
+// shuffle per probe) and leaves probe (i0 + id(lane)) in its lane, so the K rate terms are computed in parallel too.
 template <int SIZE, int SS>
 struct TzEvalTile
 {
-  static constexpr int  ROWS   = SIZE >> SS;               // sampled rows
-  static constexpr int  LP     = ROWS < 32 ? ROWS : 32;    // lanes per probe
-  static constexpr int  PPW    = 32 / LP;                  // probes per warp and round
-  static constexpr int  RPL    = ROWS / LP;                // rows per lane
-  static constexpr bool PATREG = SIZE * RPL <= 32;
+  static constexpr int  WPR    = SIZE / 2;                  // 32-bit words per row
+  static constexpr int  LX     = WPR < 32 ? WPR : 32;       // lanes along x
+  static constexpr int  CB     = WPR / LX;                  // column blocks per row (128 wide: 2)
+  static constexpr int  RPI    = 32 / LX;                   // rows per load instruction
+  static constexpr int  ROWS   = SIZE >> SS;                // sampled rows
+  static constexpr int  ITERS  = ROWS / RPI * CB;           // load instructions per probe
+  static constexpr bool PATREG = ITERS <= 16;               // the lane's pattern samples stay in registers
+  static constexpr int  K      = SIZE == 8 ? 16 : (SIZE == 16 ? 8 : 1);
   struct Ctx
   {
-    int            pat[PATREG ? SIZE * RPL : 1];   // this lane's pattern rows, one sample per register
-    const int16_t* patPtr;                         // pattern in the current picture (16-byte aligned rows)
+    int            pat[PATREG ? ITERS * 2 : 2];
+    const int16_t* patPtr;      // pattern in the current picture (rows 16-byte aligned)
     int            patStride;
     const int16_t* refAtPU;
     int            refStride;
@@ -170,91 +176,103 @@ struct TzEvalTile
   static __device__ __forceinline__ void load_pattern(Ctx& c)
   {
     if (!PATREG) return;
-    const int rl = (threadIdx.x & 31) % LP;
+    const int lane = threadIdx.x & 31, ri = lane / LX, lx = lane % LX;
 #pragma unroll
-    for (int k = 0; k < RPL; k++)
+    for (int it = 0; it < ITERS; it++)
     {
-      const int16_t* row = c.patPtr + (ptrdiff_t) ((rl + k * LP) << SS) * c.patStride;
-#pragma unroll
-      for (int x = 0; x < SIZE; x += 8)
-      {
-        const uint4    v    = *reinterpret_cast<const uint4*>(row + x);
-        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-        {
-          c.pat[k * SIZE + x + 2 * i]     = (int) (w[i] & 0xffffu);
-          c.pat[k * SIZE + x + 2 * i + 1] = (int) (w[i] >> 16);
-        }
-      }
+      const int      r = ((it / CB) * RPI + ri) << SS;
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(c.patPtr + (ptrdiff_t) r * c.patStride + (it % CB) * 64 + lx * 2);
+      c.pat[2 * it]     = (int) (w & 0xffffu);
+      c.pat[2 * it + 1] = (int) (w >> 16);
     }
   }
 
-  // this lane's share of SAD(pattern, block at blk): its RPL sampled rows
-  static __device__ __forceinline__ uint32_t lane_sad(const Ctx& c, const int16_t* blk, int rl)
+  // this lane's share of SAD(pattern, block at blk)
+  static __device__ __forceinline__ uint32_t lane_sad(const Ctx& c, const int16_t* blk)
   {
-    const unsigned sh = (reinterpret_cast<uintptr_t>(blk) & 2) ? 16u : 0u;   // rows start odd (stride is even: same for all)
-    uint32_t       acc = 0;
-#pragma unroll
-    for (int k = 0; k < RPL; k++)
+    const int      lane = threadIdx.x & 31, ri = lane / LX, lx = lane % LX;
+    const unsigned sh   = (reinterpret_cast<uintptr_t>(blk) & 2) ? 16u : 0u;   // odd x (the stride is even: same for all rows)
+    uint32_t       acc  = 0;
+#pragma unroll(PATREG ? ITERS : 4)
+    for (int it = 0; it < ITERS; it++)
     {
-      const int       r = (rl + k * LP) << SS;
-      const uint32_t* w = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(blk + (ptrdiff_t) r * c.refStride) & ~(uintptr_t) 3);
-      uint32_t        carry = w[0];
-#pragma unroll
-      for (int x = 0; x < SIZE; x += 8)
+      const int       r  = ((it / CB) * RPI + ri) << SS;
+      const int16_t*  q  = blk + (ptrdiff_t) r * c.refStride + (it % CB) * 64 + lx * 2;
+      const uint32_t* wa = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(q) & ~(uintptr_t) 3);
+      const uint32_t  w0 = __ldg(wa);
+      uint32_t        w1 = __shfl_down_sync(0xffffffffu, w0, 1);
+      if (lx == LX - 1 && sh) w1 = __ldg(wa + 1);
+      const uint32_t a = __funnelshift_r(w0, w1, sh);
+      int            p0, p1;
+      if (PATREG)
       {
-        const uint32_t w1 = w[x / 2 + 1], w2 = w[x / 2 + 2], w3 = w[x / 2 + 3], w4 = w[x / 2 + 4];
-        const uint32_t a[4] = { __funnelshift_r(carry, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
-                                __funnelshift_r(w3, w4, sh) };
-        carry = w4;
-        if (PATREG)
-        {
-#pragma unroll
-          for (int i = 0; i < 4; i++)
-          {
-            acc = __sad(c.pat[k * SIZE + x + 2 * i], (int) (a[i] & 0xffffu), acc);
-            acc = __sad(c.pat[k * SIZE + x + 2 * i + 1], (int) (a[i] >> 16), acc);
-          }
-        }
-        else
-        {
-          const uint4    v    = *reinterpret_cast<const uint4*>(c.patPtr + (ptrdiff_t) r * c.patStride + x);
-          const uint32_t o[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-          for (int i = 0; i < 4; i++)
-          {
-            acc = __sad((int) (o[i] & 0xffffu), (int) (a[i] & 0xffffu), acc);
-            acc = __sad((int) (o[i] >> 16), (int) (a[i] >> 16), acc);
-          }
-        }
+        p0 = c.pat[2 * it];
+        p1 = c.pat[2 * it + 1];
       }
+      else
+      {
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(c.patPtr + (ptrdiff_t) r * c.patStride + (it % CB) * 64 + lx * 2));
+        p0               = (int) (w & 0xffffu);
+        p1               = (int) (w >> 16);
+      }
+      acc = __sad(p0, (int) (a & 0xffffu), acc);
+      acc = __sad(p1, (int) (a >> 16), acc);
     }
     return acc;
+  }
+
+  // Sums s[q] over the 32 lanes for all q at once; afterwards the lane holds the total of probe id(lane):
+  // stage with lane-mask m and `half` live values: a lane whose bit m is set keeps the upper half, sends the lower.
+  static __device__ __forceinline__ uint32_t butterfly(uint32_t (&s)[K], int lane, int& id)
+  {
+    int m = 16;
+    id    = 0;
+#pragma unroll
+    for (int half = K / 2; half >= 1; half >>= 1, m >>= 1)
+    {
+      const bool up = (lane & m) != 0;
+      if (up) id += half;
+#pragma unroll
+      for (int j = 0; j < half; j++)
+      {
+        const uint32_t send = up ? s[j] : s[j + half];
+        const uint32_t keep = up ? s[j + half] : s[j];
+        s[j]                = keep + __shfl_xor_sync(0xffffffffu, send, m);
+      }
+    }
+#pragma unroll
+    for (; m >= 1; m >>= 1) s[0] += __shfl_xor_sync(0xffffffffu, s[0], m);
+    return s[0];
   }
 
   template <class PointFn>
   static __device__ __forceinline__ int eval(const Ctx& c, int n, uint32_t best, uint32_t& costOut, PointFn point)
   {
-    const int lane = threadIdx.x & 31, g = lane / LP, rl = lane % LP;
-    unsigned long long k = ~0ull;
-    for (int i0 = 0; i0 < n; i0 += PPW)
+    const int          lane = threadIdx.x & 31;
+    unsigned long long k    = ~0ull;
+    for (int i0 = 0; i0 < n; i0 += K)
     {
-      const int  i   = i0 + g;
-      const bool act = i < n;
-      int        x = 0, y = 0;
-      if (act) point(i, x, y);
-      uint32_t s = lane_sad(c, c.refAtPU + (ptrdiff_t) y * c.refStride + x, rl);
+      uint32_t s[K];
 #pragma unroll
-      for (int m = LP >> 1; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
-      if (act)
+      for (int q = 0; q < K; q++)
       {
-        const unsigned long long ki = ((unsigned long long) tz_cost(c, x, y, s << SS) << 32) | (uint32_t) i;
+        int x = 0, y = 0;
+        if (i0 + q < n) point(i0 + q, x, y);
+        s[q] = lane_sad(c, c.refAtPU + (ptrdiff_t) y * c.refStride + x);
+      }
+      int            id;
+      const uint32_t sad = butterfly(s, lane, id) << SS;
+      const int      i   = i0 + id;
+      if (i < n)
+      {
+        int x, y;
+        point(i, x, y);
+        const unsigned long long ki = ((unsigned long long) tz_cost(c, x, y, sad) << 32) | (uint32_t) i;
         k = ki < k ? ki : k;
       }
     }
 #pragma unroll
-    for (int m = LP; m < 32; m <<= 1)
+    for (int m = 16; m >= 1; m >>= 1)
     {
       const unsigned long long o = __shfl_xor_sync(0xffffffffu, k, m);
       k                          = o < k ? o : k;

@@ -413,6 +413,7 @@ int vtmme_search_frames_device(vtmme_ctx* ctx, int nPairs, const int32_t* curPic
   tp.imvShift = prm->imvShift;
   tp.lambda   = prm->lambdaMotion;
   const bool prof = ctx->profiling;
+  int        tzLaunches = 0;
   if (prof) VTMME_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
   if (tzFrame)
   {
@@ -430,7 +431,7 @@ int vtmme_search_frames_device(vtmme_ctx* ctx, int nPairs, const int32_t* curPic
     zp.extended        = prm->fastSearch == 3;
     zp.firstSearchStop = prm->tzFirstSearchStop;
     zp.lambda          = prm->lambdaMotion;
-    VTMME_CUDA_CHECK(ctx, launch_tz_frame(zp, nPairs, ctx->stream));
+    VTMME_CUDA_CHECK(ctx, launch_tz_frame(zp, nPairs, ctx->stream, &tzLaunches));
     if (prof) VTMME_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     if (prof) VTMME_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
   }
@@ -461,7 +462,7 @@ int vtmme_search_frames_device(vtmme_ctx* ctx, int nPairs, const int32_t* curPic
     VTMME_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
     ctx->evValid = true;
   }
-  ctx->launches += (tzFrame ? 1 : 2) + fracLaunches;
+  ctx->launches += (tzFrame ? tzLaunches : 2) + fracLaunches;
   return VTMME_OK;
 }
 
