@@ -14,12 +14,15 @@ namespace vtmme {
 
 namespace {
 
+__host__ __device__ constexpr int coop_warps(int size) { return size >= 64 ? 4 : 1; }   // warps per search
+
 template <int SIZE, int SS>
 __device__ __forceinline__ unsigned long long tz_frame_cu(const TzFrameParams& p, const DevPic& cur, const DevPic& ref, int x, int y,
-                                                          short2 pr, const DevTz& t)
+                                                          short2 pr, const DevTz& t, uint32_t* partial)
 {
-  using EV = TzEvalTile<SIZE, SS>;
+  using EV = TzEvalTile<SIZE, SS, coop_warps(SIZE)>;
   typename EV::Ctx c;
+  c.partial   = partial;
   c.patPtr    = cur.origin + (ptrdiff_t) y * cur.stride + x;
   c.patStride = cur.stride;
   c.refAtPU   = ref.origin + (ptrdiff_t) y * ref.stride + x;
@@ -32,13 +35,16 @@ __device__ __forceinline__ unsigned long long tz_frame_cu(const TzFrameParams& p
   return tz_search<EV>(c, t);
 }
 
-// one launch per CU level (its own register budget and occupancy), four searches per CTA
+// one launch per CU level (its own register budget and occupancy); a CTA carries four searches of CUs up to 32x32 or
+// one search of a larger CU, whose rows its four warps share
 template <int SIZE, int SS>
 __global__ void __launch_bounds__(128) me_tz_frame_kernel(TzFrameParams p, int level)
 {
+  __shared__ uint32_t s_partial[8];
+  constexpr int perCta = 4 / coop_warps(SIZE);
   const int warp = threadIdx.x >> 5;
   const int nCU  = p.g.off[5], nLevel = p.g.nx[level] * p.g.ny[level];
-  const int li = blockIdx.x * 4 + warp, pair = blockIdx.y;
+  const int li = blockIdx.x * perCta + (perCta > 1 ? warp : 0), pair = blockIdx.y;
   if (li >= nLevel) return;
   const int cu = p.g.off[level] + li;
   const int x = (li % p.g.nx[level]) * SIZE, y = (li / p.g.nx[level]) * SIZE;
@@ -61,8 +67,8 @@ __global__ void __launch_bounds__(128) me_tz_frame_kernel(TzFrameParams p, int l
   t.picW            = p.g.picW;
   t.picH            = p.g.picH;
   t.maxCuW = t.maxCuH = p.ctu;
-  const unsigned long long key = tz_frame_cu<SIZE, SS>(p, cur, ref, x, y, pr, t);
-  if ((threadIdx.x & 31) == 0) p.keys[(size_t) pair * nCU + cu] = key;
+  const unsigned long long key = tz_frame_cu<SIZE, SS>(p, cur, ref, x, y, pr, t, s_partial);
+  if (threadIdx.x == 0 || (perCta > 1 && (threadIdx.x & 31) == 0)) p.keys[(size_t) pair * nCU + cu] = key;
 }
 
 template <int SIZE, int SS>
@@ -70,7 +76,8 @@ cudaError_t launch_level(const TzFrameParams& p, int level, int nPairs, cudaStre
 {
   const int n = p.g.nx[level] * p.g.ny[level];
   if (n == 0) return cudaSuccess;
-  dim3 grid((n + 3) / 4, nPairs, 1);
+  constexpr int perCta = 4 / coop_warps(SIZE);
+  dim3 grid((n + perCta - 1) / perCta, nPairs, 1);
   me_tz_frame_kernel<SIZE, SS><<<grid, 128, 0, st>>>(p, level);
   return cudaGetLastError();
 }

@@ -151,7 +151,7 @@ struct TzEvalWarps
 // an odd x takes the second half of its word pair from the neighbouring lane.  K probes are in flight at a time; their
 // per-lane partial sums are reduced with a butterfly that halves the number of live values at every stage (about one
 // shuffle per probe) and leaves probe (i0 + id(lane)) in its lane, so the K rate terms are computed in parallel too.
-template <int SIZE, int SS>
+template <int SIZE, int SS, int COOP = 1>   // COOP warps share the rows of every probe (large CUs: one CTA per search)
 struct TzEvalTile
 {
   static constexpr int  WPR    = SIZE / 2;                  // 32-bit words per row
@@ -171,10 +171,13 @@ struct TzEvalTile
     int            refStride;
     int            predQx, predQy, imvShift;
     double         lambda;
+    uint32_t*      partial;     // COOP > 1: shared memory, [2][COOP] per-warp partial sums (double-buffered)
+    mutable int    parity;
   };
 
   static __device__ __forceinline__ void load_pattern(Ctx& c)
   {
+    c.parity = 0;
     if (!PATREG) return;
     const int lane = threadIdx.x & 31, ri = lane / LX, lx = lane % LX;
 #pragma unroll
@@ -194,7 +197,7 @@ struct TzEvalTile
     const unsigned sh   = (reinterpret_cast<uintptr_t>(blk) & 2) ? 16u : 0u;   // odd x (the stride is even: same for all rows)
     uint32_t       acc  = 0;
 #pragma unroll(PATREG ? ITERS : 4)
-    for (int it = 0; it < ITERS; it++)
+    for (int it = (COOP > 1 ? (int) (threadIdx.x >> 5) : 0); it < ITERS; it += COOP)
     {
       const int       r  = ((it / CB) * RPI + ri) << SS;
       const int16_t*  q  = blk + (ptrdiff_t) r * c.refStride + (it % CB) * 64 + lx * 2;
@@ -256,12 +259,29 @@ struct TzEvalTile
 #pragma unroll
       for (int q = 0; q < K; q++)
       {
-        int x = 0, y = 0;
-        if (i0 + q < n) point(i0 + q, x, y);
-        s[q] = lane_sad(c, c.refAtPU + (ptrdiff_t) y * c.refStride + x);
+        s[q] = 0;
+        if (i0 + q < n)   // uniform
+        {
+          int x, y;
+          point(i0 + q, x, y);
+          s[q] = lane_sad(c, c.refAtPU + (ptrdiff_t) y * c.refStride + x);
+        }
       }
-      int            id;
-      const uint32_t sad = butterfly(s, lane, id) << SS;
+      int      id;
+      uint32_t sad = butterfly(s, lane, id);
+      if (COOP > 1)
+      {
+        // K == 1: every lane holds its warp's share of the probe; one barrier per probe (the buffer written now is
+        // read before the barrier of the next probe, which every warp passes before writing it again)
+        uint32_t* buf = c.partial + c.parity * COOP;
+        c.parity ^= 1;
+        if (lane == 0) buf[threadIdx.x >> 5] = sad;
+        __syncthreads();
+        sad = 0;
+#pragma unroll
+        for (int w = 0; w < COOP; w++) sad += buf[w];
+      }
+      sad <<= SS;
       const int      i   = i0 + id;
       if (i < n)
       {
@@ -415,19 +435,21 @@ __device__ inline void tz_raster(const typename EV::Ctx& c, TzState& s, int l, i
 {
   if (r < l || b < t) return;
   const int nx = (r - l) / win + 1, ny = (b - t) / win + 1, n = nx * ny;
+  // g / nx as a multiply-high: exact for g < 2^17 and nx <= 1099 (checked exhaustively), far above any window here
+  const uint32_t inv = 0xffffffffu / (uint32_t) nx + 1u;
   for (int base = 0; base < n; base += kTzChunk)
   {
     uint32_t  cost;
     const int m   = min(kTzChunk, n - base);
     const int idx = EV::eval(c, m, s.best, cost, [&](int i, int& x, int& y) {
-      const int g = base + i;
-      x           = l + (g % nx) * win;
-      y           = t + (g / nx) * win;
+      const int g = base + i, gy = (int) __umulhi((uint32_t) g, inv);
+      x           = l + (g - gy * nx) * win;
+      y           = t + gy * win;
     });
     if (idx >= 0)
     {
-      const int g = base + idx;
-      tz_update(s, cost, l + (g % nx) * win, t + (g / nx) * win, 0, (uint32_t) win);
+      const int g = base + idx, gy = g / nx;
+      tz_update(s, cost, l + (g - gy * nx) * win, t + gy * win, 0, (uint32_t) win);
     }
   }
 }
