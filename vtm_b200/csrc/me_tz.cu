@@ -22,16 +22,12 @@ __device__ __forceinline__ unsigned long long tz_frame_cu(const TzFrameParams& p
 {
   using EV = TzEvalTile<SIZE, SS, coop_warps(SIZE)>;
   typename EV::Ctx c;
-  c.partial   = partial;
-  c.patPtr    = cur.origin + (ptrdiff_t) y * cur.stride + x;
-  c.patStride = cur.stride;
-  c.refAtPU   = ref.origin + (ptrdiff_t) y * ref.stride + x;
-  c.refStride = ref.stride;
-  c.predQx    = pr.x;
-  c.predQy    = pr.y;
-  c.imvShift  = p.imvShift;
-  c.lambda    = p.lambda;
-  EV::load_pattern(c);
+  c.partial  = partial;
+  c.predQx   = pr.x;
+  c.predQy   = pr.y;
+  c.imvShift = p.imvShift;
+  c.lambda   = p.lambda;
+  EV::init(c, cur.origin + (ptrdiff_t) y * cur.stride + x, cur.stride, ref.origin + (ptrdiff_t) y * ref.stride + x, ref.stride);
   return tz_search<EV>(c, t);
 }
 

@@ -159,15 +159,16 @@ struct TzEvalTile
   static constexpr int  CB     = WPR / LX;                  // column blocks per row (128 wide: 2)
   static constexpr int  RPI    = 32 / LX;                   // rows per load instruction
   static constexpr int  ROWS   = SIZE >> SS;                // sampled rows
-  static constexpr int  ITERS  = ROWS / RPI * CB;           // load instructions per probe
+  static constexpr int  RITERS = ROWS / RPI;                // row steps per probe
+  static constexpr int  ITERS  = RITERS * CB;               // load instructions per probe
   static constexpr bool PATREG = ITERS <= 16;               // the lane's pattern samples stay in registers
   static constexpr int  K      = SIZE == 8 ? 16 : (SIZE == 16 ? 8 : 1);
   struct Ctx
   {
     int            pat[PATREG ? ITERS * 2 : 2];
-    const int16_t* patPtr;      // pattern in the current picture (rows 16-byte aligned)
-    int            patStride;
-    const int16_t* refAtPU;
+    const int16_t* patLane;     // pattern (current picture, rows 16-byte aligned) at this lane's first sample
+    const int16_t* refLane;     // reference plane at the PU position + this lane's first sample
+    int            patStep, refStep;   // element offset between two row steps of a lane: (RPI << SS) * stride
     int            refStride;
     int            predQx, predQy, imvShift;
     double         lambda;
@@ -175,63 +176,80 @@ struct TzEvalTile
     mutable int    parity;
   };
 
-  static __device__ __forceinline__ void load_pattern(Ctx& c)
+  static __device__ __forceinline__ void init(Ctx& c, const int16_t* patAtPU, int patStride, const int16_t* refAtPU, int refStride)
   {
-    c.parity = 0;
-    if (!PATREG) return;
     const int lane = threadIdx.x & 31, ri = lane / LX, lx = lane % LX;
-#pragma unroll
-    for (int it = 0; it < ITERS; it++)
+    c.patLane   = patAtPU + (ri << SS) * patStride + lx * 2;
+    c.refLane   = refAtPU + (ri << SS) * refStride + lx * 2;
+    c.patStep   = (RPI << SS) * patStride;
+    c.refStep   = (RPI << SS) * refStride;
+    c.refStride = refStride;
+    c.parity    = 0;
+    if (PATREG)
     {
-      const int      r = ((it / CB) * RPI + ri) << SS;
-      const uint32_t w = *reinterpret_cast<const uint32_t*>(c.patPtr + (ptrdiff_t) r * c.patStride + (it % CB) * 64 + lx * 2);
-      c.pat[2 * it]     = (int) (w & 0xffffu);
-      c.pat[2 * it + 1] = (int) (w >> 16);
+#pragma unroll
+      for (int it = 0; it < ITERS; it++)
+      {
+        const uint32_t w  = *reinterpret_cast<const uint32_t*>(c.patLane + (it / CB) * c.patStep + (it % CB) * 64);
+        c.pat[2 * it]     = (int) (w & 0xffffu);
+        c.pat[2 * it + 1] = (int) (w >> 16);
+      }
     }
   }
 
-  // this lane's share of SAD(pattern, block at blk)
-  static __device__ __forceinline__ uint32_t lane_sad(const Ctx& c, const int16_t* blk)
+  // this lane's share of SAD(pattern, block at element offset `off` from the PU position)
+  static __device__ __forceinline__ uint32_t lane_sad(const Ctx& c, int off)
   {
-    const int      lane = threadIdx.x & 31, ri = lane / LX, lx = lane % LX;
-    const unsigned sh   = (reinterpret_cast<uintptr_t>(blk) & 2) ? 16u : 0u;   // odd x (the stride is even: same for all rows)
+    const int16_t* q    = c.refLane + off;
+    const unsigned sh   = (reinterpret_cast<uintptr_t>(q) & 2) ? 16u : 0u;   // odd x (strides are even: same for all rows)
+    const bool     last = (threadIdx.x & 31) % LX == LX - 1;
     uint32_t       acc  = 0;
-#pragma unroll(PATREG ? ITERS : 4)
-    for (int it = (COOP > 1 ? (int) (threadIdx.x >> 5) : 0); it < ITERS; it += COOP)
+    if (PATREG)
     {
-      const int       r  = ((it / CB) * RPI + ri) << SS;
-      const int16_t*  q  = blk + (ptrdiff_t) r * c.refStride + (it % CB) * 64 + lx * 2;
-      const uint32_t* wa = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(q) & ~(uintptr_t) 3);
-      const uint32_t  w0 = __ldg(wa);
-      uint32_t        w1 = __shfl_down_sync(0xffffffffu, w0, 1);
-      if (lx == LX - 1 && sh) w1 = __ldg(wa + 1);
-      const uint32_t a = __funnelshift_r(w0, w1, sh);
-      int            p0, p1;
-      if (PATREG)
+#pragma unroll
+      for (int it = 0; it < ITERS; it++)
       {
-        p0 = c.pat[2 * it];
-        p1 = c.pat[2 * it + 1];
+        const uint32_t* wa = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(q + (it / CB) * c.refStep + (it % CB) * 64) & ~(uintptr_t) 3);
+        const uint32_t  w0 = __ldg(wa);
+        uint32_t        w1 = __shfl_down_sync(0xffffffffu, w0, 1);
+        if (last && sh) w1 = __ldg(wa + 1);
+        const uint32_t a = __funnelshift_r(w0, w1, sh);
+        acc = __sad(c.pat[2 * it], (int) (a & 0xffffu), acc);
+        acc = __sad(c.pat[2 * it + 1], (int) (a >> 16), acc);
       }
-      else
-      {
-        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(c.patPtr + (ptrdiff_t) r * c.patStride + (it % CB) * 64 + lx * 2));
-        p0               = (int) (w & 0xffffu);
-        p1               = (int) (w >> 16);
-      }
-      acc = __sad(p0, (int) (a & 0xffffu), acc);
-      acc = __sad(p1, (int) (a >> 16), acc);
+    }
+    else
+    {
+      const int       w0i = COOP > 1 ? (int) (threadIdx.x >> 5) : 0;
+      const int16_t*  pr  = q + w0i * c.refStep;
+      const int16_t*  pp  = c.patLane + w0i * c.patStep;
+#pragma unroll 4
+      for (int rit = w0i; rit < RITERS; rit += COOP, pr += COOP * c.refStep, pp += COOP * c.patStep)
+#pragma unroll
+        for (int cb = 0; cb < CB; cb++)
+        {
+          const uint32_t* wa = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(pr + cb * 64) & ~(uintptr_t) 3);
+          const uint32_t  w0 = __ldg(wa);
+          uint32_t        w1 = __shfl_down_sync(0xffffffffu, w0, 1);
+          if (last && sh) w1 = __ldg(wa + 1);
+          const uint32_t a = __funnelshift_r(w0, w1, sh);
+          const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(pp + cb * 64));
+          acc = __sad((int) (w & 0xffffu), (int) (a & 0xffffu), acc);
+          acc = __sad((int) (w >> 16), (int) (a >> 16), acc);
+        }
     }
     return acc;
   }
 
-  // Sums s[q] over the 32 lanes for all q at once; afterwards the lane holds the total of probe id(lane):
+  // Sums s[q] over the 32 lanes for all q < KK at once; afterwards the lane holds the total of probe id(lane):
   // stage with lane-mask m and `half` live values: a lane whose bit m is set keeps the upper half, sends the lower.
-  static __device__ __forceinline__ uint32_t butterfly(uint32_t (&s)[K], int lane, int& id)
+  template <int KK>
+  static __device__ __forceinline__ uint32_t butterfly(uint32_t (&s)[KK], int lane, int& id)
   {
     int m = 16;
     id    = 0;
 #pragma unroll
-    for (int half = K / 2; half >= 1; half >>= 1, m >>= 1)
+    for (int half = KK / 2; half >= 1; half >>= 1, m >>= 1)
     {
       const bool up = (lane & m) != 0;
       if (up) id += half;
@@ -248,57 +266,58 @@ struct TzEvalTile
     return s[0];
   }
 
+  // KK probes i0 .. i0+KK-1 (all valid) in flight; updates the lane's running (cost, index) minimum
+  template <int KK, class PointFn>
+  static __device__ __forceinline__ void phase(const Ctx& c, int i0, uint32_t& bestCost, uint32_t& bestIdx, PointFn point)
+  {
+    const int lane = threadIdx.x & 31;
+    uint32_t  s[KK];
+#pragma unroll
+    for (int q = 0; q < KK; q++)
+    {
+      int x, y;
+      point(i0 + q, x, y);
+      s[q] = lane_sad(c, y * c.refStride + x);
+    }
+    int      id;
+    uint32_t sad = butterfly<KK>(s, lane, id);
+    if (COOP > 1)
+    {
+      // every lane holds its warp's share of the probe; one barrier per probe (the buffer written now is read before
+      // the barrier of the next probe, which every warp passes before writing it again)
+      uint32_t* buf = c.partial + c.parity * COOP;
+      c.parity ^= 1;
+      if (lane == 0) buf[threadIdx.x >> 5] = sad;
+      __syncthreads();
+      sad = 0;
+#pragma unroll
+      for (int w = 0; w < COOP; w++) sad += buf[w];
+    }
+    int x, y;
+    point(i0 + id, x, y);
+    const uint32_t cost = tz_cost(c, x, y, sad << SS);
+    if (cost < bestCost)   // probes of later phases have larger indices: strict
+    {
+      bestCost = cost;
+      bestIdx  = (uint32_t) (i0 + id);
+    }
+  }
+
   template <class PointFn>
   static __device__ __forceinline__ int eval(const Ctx& c, int n, uint32_t best, uint32_t& costOut, PointFn point)
   {
-    const int          lane = threadIdx.x & 31;
-    unsigned long long k    = ~0ull;
-    for (int i0 = 0; i0 < n; i0 += K)
-    {
-      uint32_t s[K];
-#pragma unroll
-      for (int q = 0; q < K; q++)
-      {
-        s[q] = 0;
-        if (i0 + q < n)   // uniform
-        {
-          int x, y;
-          point(i0 + q, x, y);
-          s[q] = lane_sad(c, c.refAtPU + (ptrdiff_t) y * c.refStride + x);
-        }
-      }
-      int      id;
-      uint32_t sad = butterfly(s, lane, id);
-      if (COOP > 1)
-      {
-        // K == 1: every lane holds its warp's share of the probe; one barrier per probe (the buffer written now is
-        // read before the barrier of the next probe, which every warp passes before writing it again)
-        uint32_t* buf = c.partial + c.parity * COOP;
-        c.parity ^= 1;
-        if (lane == 0) buf[threadIdx.x >> 5] = sad;
-        __syncthreads();
-        sad = 0;
-#pragma unroll
-        for (int w = 0; w < COOP; w++) sad += buf[w];
-      }
-      sad <<= SS;
-      const int      i   = i0 + id;
-      if (i < n)
-      {
-        int x, y;
-        point(i, x, y);
-        const unsigned long long ki = ((unsigned long long) tz_cost(c, x, y, sad) << 32) | (uint32_t) i;
-        k = ki < k ? ki : k;
-      }
-    }
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1)
-    {
-      const unsigned long long o = __shfl_xor_sync(0xffffffffu, k, m);
-      k                          = o < k ? o : k;
-    }
-    costOut = (uint32_t) (k >> 32);
-    return (k != ~0ull && costOut < best) ? (int) (uint32_t) k : -1;
+    uint32_t bc = 0xffffffffu, bi = 0xffffffffu;
+    int      i0 = 0;
+    for (; i0 + K <= n; i0 += K) phase<K>(c, i0, bc, bi, point);
+    if (K >= 16 && n - i0 >= 8) { phase<8>(c, i0, bc, bi, point); i0 += 8; }
+    if (K >= 8 && n - i0 >= 4) { phase<4>(c, i0, bc, bi, point); i0 += 4; }
+    if (K >= 4 && n - i0 >= 2) { phase<2>(c, i0, bc, bi, point); i0 += 2; }
+    if (K >= 2 && n - i0 >= 1) { phase<1>(c, i0, bc, bi, point); i0 += 1; }
+    // first strict minimum in probe order over the lanes: smallest cost, then smallest index among its holders
+    const uint32_t mc = __reduce_min_sync(0xffffffffu, bc);
+    const uint32_t mi = __reduce_min_sync(0xffffffffu, bc == mc ? bi : 0xffffffffu);
+    costOut           = mc;
+    return (mi != 0xffffffffu && mc < best) ? (int) mi : -1;
   }
 };
 
