@@ -95,6 +95,69 @@ def test_frame_tiny_and_ragged_pictures(ms, oracle_lib, w, h):
     assert [gpu_tuple(got[0][i]) for i in range(ncu)] == [want[i] for i in range(ncu)]
 
 
+@pytest.mark.parametrize("w,h,sr,fast_search", [(8, 8, 8, 1), (40, 56, 16, 3), (136, 72, 128, 1), (264, 136, 200, 3)])
+def test_frame_tz_tiny_ragged_and_wide_ranges(ms, oracle_lib, w, h, sr, fast_search):
+    """TZ frame search on pictures smaller than a CTU / not multiples of the CU sizes (levels without any CU are
+    skipped), with search ranges up to 200 (diamond distances beyond 128, windows clipped on every side), random
+    predictors far outside the picture, two pairs per call."""
+    from tests.helpers import oracle_frame_tz
+    from vtm_b200 import FrameParams
+    from vtm_b200.synth import make_pair, random_predictors
+    pairs = [make_pair(90 + w + k, w, h, max_global=6, max_local=9, n_rects=1, sigma=3.0) for k in range(2)]
+    refps = [pad_plane(p[1]) for p in pairs]
+    for k in range(2):
+        ms.upload_picture(40 + 2 * k, pairs[k][0])
+        ms.upload_picture(41 + 2 * k, refps[k], MARGIN)
+    ncu = ms.set_frame_size(w, h)
+    pred = np.stack([random_predictors(11 + k, ncu, 300) for k in range(2)])   # up to +-300 px: clipped by clipMv
+    got = ms.search_frames([40, 42], [41, 43], FrameParams(searchRange=sr, lambdaMotion=23.5, fastSearch=fast_search), pred)
+    for k in range(2):
+        want = oracle_frame_tz(oracle_lib, pairs[k][0], refps[k], MARGIN, sr, 23.5, pred[k], fast_search, 1, 0)
+        assert [gpu_tuple(got[k][i]) for i in range(ncu)] == [want[i] for i in range(ncu)]
+
+
+def test_job_tz_signed_pattern_and_amvr(ms, oracle_lib):
+    """Per-call TZ jobs with a bi-pred style pattern (2*org - otherPred, outside the sample range) followed by the
+    integer AMVR refinement: xTZSearch + xPatternSearchIntRefine in one call."""
+    from tests.helpers import int_refine_case, tz_case
+    from vtm_b200 import Amvr, Job, TzSearch
+    rng = np.random.default_rng(91)
+    W, H = 160, 128
+    ref = np.clip(np.rint(rng.normal(512, 200, (H, W))), 0, 1023).astype(np.int16)
+    cur = np.ascontiguousarray(np.roll(ref, (1, 2), (0, 1)))
+    refp = pad_plane(ref)
+    ms.upload_picture(44, cur)
+    ms.upload_picture(45, refp, MARGIN)
+    stride = refp.shape[1]
+    jobs, want, keep = [], [], []
+    for (w, h) in [(8, 8), (16, 32), (32, 32), (64, 16), (128, 64), (4, 16)]:
+        for imv in (1, 2):
+            x, y = int(rng.integers(0, (W - w) // 4 + 1)) * 4, int(rng.integers(0, (H - h) // 4 + 1)) * 4
+            org = (2 * cur[y:y + h, x:x + w].astype(np.int32) - rng.integers(0, 1024, (h, w))).astype(np.int16)
+            org = np.ascontiguousarray(org)
+            keep.append(org)
+            io = int_refine_case(rng, imv, x, y, w, h, W, H, max_pel=6)
+            pred16 = (io.candX[io.mvpIdx], io.candY[io.mvpIdx])
+            pq = tuple((v + 1) >> 2 if v >= 0 else (v + 2) >> 2 for v in pred16)
+            t = tz_case(rng, x, y, W, H, 32, 0, 0, max_pel=10)
+            t.startX, t.startY = pred16
+            tz = TzSearch(pred16, 32, W, H, tuple((t.seedX[i], t.seedY[i]) for i in range(t.nSeeds)), None, 0, 0, 1)
+            t.hasInt2Nx2N = 0
+            am = Amvr(imv, ((io.candX[0], io.candY[0]), (io.candX[1], io.candY[1])), io.numCand, io.mvpIdx,
+                      (io.mvpIdxBits[0], io.mvpIdxBits[1]), io.bits, W, H, io.fWeight)
+            jobs.append(Job(44, 45, x, y, w, h, (0, 0, 0, 0), pq, imv << 1, 0, 10, 1, 0, 2, 19.0, org, am, tz))
+            oj = B.make_job(org, refp, stride, (MARGIN + y) * stride + MARGIN + x, w, h, (0, 0, 0, 0), pq, imv << 1, 0, 10, 1,
+                            0, 0, 19.0)
+            mx, my, sad = C.c_int(), C.c_int(), C.c_uint64()
+            oracle_lib.vo_tz_search(C.byref(oj), C.byref(t), C.byref(mx), C.byref(my), C.byref(sad), None)
+            io.mvX, io.mvY = mx.value * 16, my.value * 16
+            oracle_lib.vo_int_refine(C.byref(oj), C.byref(io))
+            want.append((mx.value, my.value, sad.value) + io.tuple())
+    pick = lambda t: t[:3] + t[8:]
+    assert [pick(t) for t in ms.search(jobs)] == want
+    assert [pick(ms.search([j])[0]) for j in jobs] == want
+
+
 def test_frame_batch_is_independent_per_pair(ms, oracle_lib):
     """A batch of three different pairs gives, pair by pair, what each pair gives alone (and what the oracle gives);
     running it twice gives identical results."""
