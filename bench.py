@@ -287,7 +287,9 @@ def run_ours(args, rank, world, local_rank):
     # ---- e2e: host buffers through the C ABI (upload both planes of every pair, search, results back to the host)
     e2e_steps = max(1, min(K, args.e2e_steps))
     npool = len(host_cur)
-    h_res = np.zeros((B, ncu), dtype=CU_RESULT_DTYPE)
+    # results land in page-locked host memory owned by the caller (one DMA per step, no staging copy)
+    h_res_t = torch.empty(B * ncu * CU_RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    h_res = h_res_t.numpy().view(CU_RESULT_DTYPE).reshape(B, ncu)
 
     def e2e_upload(s):
         """queue the H2D copies of step s (pipelined on the library's copy stream); picture ids double-buffered"""
@@ -299,7 +301,7 @@ def run_ours(args, rank, world, local_rank):
 
     def e2e_search(s):
         base = 100000 + (s & 1) * 2 * B
-        return ms.search_frames([base + 2 * i for i in range(B)], [base + 2 * i + 1 for i in range(B)], prm, h_pred)
+        return ms.search_frames([base + 2 * i for i in range(B)], [base + 2 * i + 1 for i in range(B)], prm, h_pred, out=h_res)
 
     # every timed step uploads the NEXT step's pictures while it searches its own (uploaded during the previous step)
     # and reads its results back to the host: per step, one full set of H2D copies and one D2H of all results

@@ -396,6 +396,89 @@ __global__ void __launch_bounds__(128) me_job_frac_finish_kernel(const DevJob* _
 }
 
 
+// Refinement of a pattern of at most 32x32 samples by one CTA of kFracThreads threads, the pattern already in shared
+// memory (row stride patStride): the xPatternSearchFracDIF body (fracMode 1) or xPatternSearchIntRefine (fracMode 2)
+// at the integer MV held by `key`, and the result record (`out`: mapped pinned host memory).
+__device__ __forceinline__ void job_refine_single(const DevJob& j, unsigned long long key, const int16_t* s_pat, int patStride,
+                                                  FracSmem& fsm, IntRefSmem& irs, DevJobResult* out)
+{
+  const int    dx = key_dx(key), dy = key_dy(key);
+  DevJobResult res;
+  res.mvX    = dx;
+  res.mvY    = dy;
+  res.intSad = key_cost(key) - mv_cost(j.lambda, mv_bits_q(dx * 4, dy * 4, j.predQx, j.predQy, j.imvShift));
+  res.halfX = res.halfY = res.qterX = res.qterY = 0;
+  res.fracCost = res.intSad;
+  res.amvrMvX = res.amvrMvY = res.mvpIdx = 0;
+  res.bits = 0;
+  res.cost = 0;
+  if (j.fracMode == 2)
+  {
+    intrefine_accumulate<kFracThreads>(irs, j, s_pat, patStride, dx, dy, 0, 1);
+    if (threadIdx.x == 0) intrefine_decide(j, dx, dy, irs.acc, res);
+  }
+  else if (j.fracMode)
+  {
+    FracJob f   = make_frac_job(j, dx, dy);
+    f.org       = s_pat;
+    f.orgStride = patStride;
+    if (j.imvShift > 1)
+    {
+      frac_stage(fsm, f, 0, 0, 2, false);
+      res.fracCost = fsm.centre + mv_cost(j.lambda, mv_bits_q(dx * 4, dy * 4, j.predQx, j.predQy, j.imvShift));
+    }
+    else
+    {
+      const FracOut o = frac_refine_cta(fsm, f);
+      res.halfX    = o.halfX;
+      res.halfY    = o.halfY;
+      res.qterX    = o.qterX;
+      res.qterY    = o.qterY;
+      res.fracCost = o.cost;
+    }
+  }
+  if (threadIdx.x == 0)
+  {
+    *out = res;
+    __threadfence_system();
+  }
+}
+
+// TZ search of one small job with its refinement, one launch (the in-loop encoder's FastSearch=1 call)
+__global__ void __launch_bounds__(kTzThreads) me_job_tz_fused_kernel(const DevJob* __restrict__ jobs, const DevTz* __restrict__ tz,
+                                                                     DevJobResult* __restrict__ result)
+{
+  static_assert(kTzThreads == kFracThreads, "the refinement code is written for CTAs of kFracThreads threads");
+  __shared__ TzSmem                sm;
+  __shared__ FracSmem              fsm;
+  __shared__ IntRefSmem            irs;
+  __shared__ __align__(16) int16_t s_pat[32 * 32];
+  const DevJob j = jobs[0];
+  const DevTz  t = tz[0];
+  for (int i = threadIdx.x; i < j.w * j.h; i += kTzThreads)
+  {
+    const int y = i / j.w, x = i - y * j.w;
+    s_pat[i]    = j.org[(size_t) y * j.orgStride + x];
+  }
+  __syncthreads();
+  TzCtx c;
+  c.pat       = s_pat;
+  c.patStride = j.w;
+  c.refAtPU   = j.refAtPU;
+  c.refStride = j.refStride;
+  c.w         = j.w;
+  c.h         = j.h;
+  c.subShift  = j.subShift;
+  c.predQx    = j.predQx;
+  c.predQy    = j.predQy;
+  c.imvShift  = j.imvShift;
+  c.lambda    = j.lambda;
+  c.sm        = &sm;
+  const unsigned long long key = tz_search<TzEvalWarps<kTzThreads / 32>>(c, t);
+  __syncthreads();
+  job_refine_single(j, key, s_pat, j.w, fsm, irs, result);
+}
+
 // ---- single small job, one launch (the in-loop encoder's call: one PU, pattern <= 32x32) ----------------------------
 // Job descriptor and pattern travel as kernel parameters (no upload, no dependent global reads at kernel start); every
 // CTA searches one band of window rows, the last CTA to finish (ticket) runs the fractional refinement and writes the
@@ -516,45 +599,7 @@ __global__ void __launch_bounds__(kFusedThreads) me_job_fused_kernel(const __gri
   __syncthreads();
   const unsigned long long key = hdr->best;
   const int                dx = key_dx(key), dy = key_dy(key);
-  DevJobResult             res;
-  res.mvX    = dx;
-  res.mvY    = dy;
-  res.intSad = key_cost(key) - mv_cost(j.lambda, mv_bits_q(dx * 4, dy * 4, j.predQx, j.predQy, j.imvShift));
-  res.halfX = res.halfY = res.qterX = res.qterY = 0;
-  res.fracCost = res.intSad;
-  res.amvrMvX = res.amvrMvY = res.mvpIdx = 0;
-  res.bits = 0;
-  res.cost = 0;
-  if (j.fracMode == 2)
-  {
-    intrefine_accumulate<kFusedThreads>(irs, j, s_pat, rw, dx, dy, 0, 1);
-    if (tid == 0) intrefine_decide(j, dx, dy, irs.acc, res);
-  }
-  else if (j.fracMode)
-  {
-    FracJob f   = make_frac_job(j, dx, dy);
-    f.org       = s_pat;
-    f.orgStride = rw;
-    if (j.imvShift > 1)
-    {
-      frac_stage(fsm, f, 0, 0, 2, false);
-      res.fracCost = fsm.centre + mv_cost(j.lambda, mv_bits_q(dx * 4, dy * 4, j.predQx, j.predQy, j.imvShift));
-    }
-    else
-    {
-      const FracOut o = frac_refine_cta(fsm, f);
-      res.halfX    = o.halfX;
-      res.halfY    = o.halfY;
-      res.qterX    = o.qterX;
-      res.qterY    = o.qterY;
-      res.fracCost = o.cost;
-    }
-  }
-  if (tid == 0)
-  {
-    *a.result = res;   // mapped pinned host memory
-    __threadfence_system();
-  }
+  job_refine_single(j, key, s_pat, rw, fsm, irs, a.result);
 }
 
 }   // namespace
@@ -567,6 +612,13 @@ cudaError_t launch_job_search_impl(const DevJob* dJobs, unsigned long long* dKey
                                    int* launches, const DevTz* dTz, int maxPatternSamples)
 {
   cudaError_t e;
+  if (dTz && n == 1 && maxPatternSamples <= 32 * 32 && maxRegions == 1)
+  {
+    // one small TZ job: search and refinement in one launch
+    me_job_tz_fused_kernel<<<1, kTzThreads, 0, st>>>(dJobs, dTz, dResults);
+    *launches += 1;
+    return cudaGetLastError();
+  }
   if (dTz)
   {
     me_job_tz_kernel<<<n, kTzThreads, (size_t) maxPatternSamples * 2, st>>>(dJobs, dTz, dKeys);

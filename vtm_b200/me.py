@@ -220,14 +220,18 @@ class MotionSearch:
         return [r.tuple() + (r.amvr_tuple() if j.fracMode == 2 else ()) for r, j in zip(res, jobs)]
 
     # ---- batched frame search --------------------------------------------------------------------------------
-    def search_frames(self, cur_ids, ref_ids, params, pred_q=None):
-        """Host buffers.  pred_q: int16 [nPairs, nCU, 2] or None.  Returns a structured array [nPairs, nCU]."""
+    def search_frames(self, cur_ids, ref_ids, params, pred_q=None, out=None):
+        """Host buffers.  pred_q: int16 [nPairs, nCU, 2] or None.  Returns a structured array [nPairs, nCU]; `out`
+        (optional) is a caller-owned array of that shape to receive the results — page-locked memory makes the
+        device-to-host copy a single DMA instead of a staged one."""
         n = len(cur_ids)
         cur = (C.c_int32 * n)(*cur_ids)
         ref = (C.c_int32 * n)(*ref_ids)
         prm = params.c()
         ncu = self._ncu
-        out = np.zeros((n, ncu), dtype=CU_RESULT_DTYPE)
+        if out is None:
+            out = np.zeros((n, ncu), dtype=CU_RESULT_DTYPE)
+        assert out.dtype == CU_RESULT_DTYPE and out.shape == (n, ncu) and out.flags["C_CONTIGUOUS"]
         pp = None
         if pred_q is not None:
             pred_q = np.ascontiguousarray(pred_q, dtype=np.int16)
