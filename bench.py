@@ -284,39 +284,71 @@ def run_ours(args, rank, world, local_rank):
     elapsed_ms = max_over_ranks(elapsed_ms, dev)
     value = world * B * K * cands_pair / (elapsed_ms * 1e-3)
 
-    # ---- e2e: host buffers through the C ABI (upload both planes of every pair, search, results back to the host)
+    # ---- e2e: host buffers through the C ABI.  Every step uploads both planes of its pairs from page-locked host
+    # memory (vtmme_upload_picture_async), searches them (vtmme_search_frames_device, asynchronous) and copies all
+    # results back to page-locked host memory.  The three stages of consecutive steps overlap: pictures are
+    # triple-buffered, results double-buffered; the timed region ends when the last result is on the host.
     e2e_steps = max(1, min(K, args.e2e_steps))
     npool = len(host_cur)
-    # results land in page-locked host memory owned by the caller (one DMA per step, no staging copy)
-    h_res_t = torch.empty(B * ncu * CU_RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
-    h_res = h_res_t.numpy().view(CU_RESULT_DTYPE).reshape(B, ncu)
+    res_bytes = B * ncu * CU_RESULT_DTYPE.itemsize
+    d_res2 = [torch.zeros(res_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+    h_res2 = [torch.empty(res_bytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    searched = [torch.cuda.Event() for _ in range(3)]
+    copied = [torch.cuda.Event() for _ in range(2)]
+    h_pred_pinned, d_pred_e2e = None, None
+    if h_pred is not None:
+        h_pred_pinned = torch.from_numpy(h_pred).pin_memory()
+        d_pred_e2e = torch.zeros_like(h_pred_pinned, device=dev)
 
     def e2e_upload(s):
-        """queue the H2D copies of step s (pipelined on the library's copy stream); picture ids double-buffered"""
-        base = 100000 + (s & 1) * 2 * B
+        """queue the H2D copies of step s on the library's copy stream; picture ids triple-buffered"""
+        if s >= 3:
+            searched[s % 3].synchronize()      # the search that last used this slot (step s-3) is done
+        base = 100000 + (s % 3) * 2 * B
         for i in range(B):
             p = (s * B + i) % npool
             ms.upload_picture_async(base + 2 * i, host_cur[p].data_ptr(), WIDTH, WIDTH, HEIGHT)
             ms.upload_picture_async(base + 2 * i + 1, host_ref[p].data_ptr(), WIDTH, WIDTH, HEIGHT)
 
     def e2e_search(s):
-        base = 100000 + (s & 1) * 2 * B
-        return ms.search_frames([base + 2 * i for i in range(B)], [base + 2 * i + 1 for i in range(B)], prm, h_pred, out=h_res)
+        k = s & 1
+        base = 100000 + (s % 3) * 2 * B
+        if s >= 2:
+            copied[k].synchronize()            # the results of step s-2 have left this buffer
+        pp = 0
+        if h_pred_pinned is not None:
+            d_pred_e2e.copy_(h_pred_pinned, non_blocking=True)
+            pp = d_pred_e2e.data_ptr()
+        ms.search_frames_device([base + 2 * i for i in range(B)], [base + 2 * i + 1 for i in range(B)], prm, pp,
+                                d_res2[k].data_ptr())
+        searched[s % 3].record(stream)
+        copy_stream.wait_event(searched[s % 3])
+        with torch.cuda.stream(copy_stream):
+            h_res2[k].copy_(d_res2[k], non_blocking=True)
+            copied[k].record(copy_stream)
 
-    # every timed step uploads the NEXT step's pictures while it searches its own (uploaded during the previous step)
-    # and reads its results back to the host: per step, one full set of H2D copies and one D2H of all results
     e2e_upload(0)
     e2e_search(0)
     e2e_upload(1)
     barrier()
+    copy_stream.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for s in range(1, e2e_steps + 1):
         e2e_upload(s + 1)
-        h_res = e2e_search(s)
+        e2e_search(s)
+    copy_stream.synchronize()                  # the last results are on the host
     ms.synchronize()
+    stream.wait_stream(copy_stream)
     e1.record(stream)
     barrier()
+    h_res = h_res2[e2e_steps & 1].numpy().view(CU_RESULT_DTYPE).reshape(B, ncu)
+    # untimed: the pipelined path delivered what the synchronous host call gives for the same pictures
+    base = 100000 + (e2e_steps % 3) * 2 * B
+    chk = ms.search_frames([base + 2 * i for i in range(B)], [base + 2 * i + 1 for i in range(B)], prm, h_pred)
+    if not np.array_equal(h_res, chk):
+        raise RuntimeError("e2e: pipelined results differ from the synchronous call")
     e2e_ms = max_over_ranks(e0.elapsed_time(e1), dev)
     e2e_value = world * B * e2e_steps * cands_pair / (e2e_ms * 1e-3)
     h2d = B * 2 * WIDTH * HEIGHT * 2

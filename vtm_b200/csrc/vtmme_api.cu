@@ -64,6 +64,13 @@ struct vtmme_ctx
   size_t         hMcTilesCap = 0;
   cudaEvent_t    mcUploaded = nullptr;      // recorded after the tile upload: the next call waits before re-filling
 
+  // picture descriptors of a frame call: page-locked staging, two slots, so that the call returns without
+  // waiting for the copy (vtmme_search_frames_device is asynchronous)
+  DevPic*     hPairs = nullptr;
+  size_t      hPairsCap = 0;            // DevPic entries per slot
+  cudaEvent_t pairsCopied[2] = { nullptr, nullptr };
+  int         pairsSlot = 0;
+
   bool        profiling = false;
   cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
   bool        evValid = false;
@@ -244,6 +251,9 @@ void vtmme_destroy(vtmme_ctx* ctx)
   cudaFree(ctx->dJobKeys);
   cudaFree(ctx->dJobFracAcc);
   if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
+  if (ctx->hPairs) cudaFreeHost(ctx->hPairs);
+  for (int i = 0; i < 2; i++)
+    if (ctx->pairsCopied[i]) cudaEventDestroy(ctx->pairsCopied[i]);
   for (int i = 0; i < 4; i++)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   cudaStreamDestroy(ctx->ownStream);
@@ -346,7 +356,30 @@ int vtmme_search_frames_device(vtmme_ctx* ctx, int nPairs, const int32_t* curPic
   const bool tzFrame = prm->fastSearch != 0;
   VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
 
-  std::vector<DevPic> hc(nPairs), hr(nPairs);
+  // page-locked staging slot for the descriptors (the previous user of the slot is two calls back)
+  if ((size_t) 2 * nPairs > ctx->hPairsCap)
+  {
+    VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->hPairs) cudaFreeHost(ctx->hPairs);
+    ctx->hPairs    = nullptr;
+    ctx->hPairsCap = 0;
+    void* hp       = nullptr;
+    if (cudaHostAlloc(&hp, (size_t) 2 * 2 * nPairs * sizeof(DevPic), cudaHostAllocDefault) != cudaSuccess)
+    {
+      cudaGetLastError();
+      return vtmme_set_error(ctx, VTMME_ERR_NOMEM, "cudaHostAlloc", "out of pinned host memory");
+    }
+    ctx->hPairs    = reinterpret_cast<DevPic*>(hp);
+    ctx->hPairsCap = (size_t) 2 * nPairs;
+  }
+  const int slot = ctx->pairsSlot;
+  ctx->pairsSlot ^= 1;
+  if (!ctx->pairsCopied[slot])
+    VTMME_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&ctx->pairsCopied[slot], cudaEventDisableTiming));
+  else
+    VTMME_CUDA_CHECK(ctx, cudaEventSynchronize(ctx->pairsCopied[slot]));
+  DevPic* hc = ctx->hPairs + (size_t) slot * ctx->hPairsCap;
+  DevPic* hr = hc + nPairs;
   for (int i = 0; i < nPairs; i++)
   {
     auto a = ctx->pics.find(curPics[i]), b = ctx->pics.find(refPics[i]);
@@ -387,10 +420,9 @@ int vtmme_search_frames_device(vtmme_ctx* ctx, int nPairs, const int32_t* curPic
   if ((rc = ensure(ctx, ctx->dRegInfo, ctx->regInfoCap, (size_t) nPairs * nReg * sizeof(int4))) != VTMME_OK) return rc;
   if ((rc = ensure(ctx, ctx->dFracAcc, ctx->fracAccCap, frac_frame_acc_bytes(g, nPairs))) != VTMME_OK) return rc;
 
-  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dCur, hc.data(), nPairs * sizeof(DevPic), cudaMemcpyHostToDevice, ctx->stream));
-  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dRef, hr.data(), nPairs * sizeof(DevPic), cudaMemcpyHostToDevice, ctx->stream));
-  // the pageable staging vectors above must outlive the copies
-  VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dCur, hc, nPairs * sizeof(DevPic), cudaMemcpyHostToDevice, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dRef, hr, nPairs * sizeof(DevPic), cudaMemcpyHostToDevice, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, cudaEventRecord(ctx->pairsCopied[slot], ctx->stream));
   VTMME_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dKeys, 0xff, (size_t) nPairs * nCU * 8, ctx->stream));
 
   TreeParams tp;
