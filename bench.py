@@ -328,14 +328,17 @@ def run_ours(args, rank, world, local_rank):
             h_res2[k].copy_(d_res2[k], non_blocking=True)
             copied[k].record(copy_stream)
 
+    # warm-up: every picture slot and result buffer is used once (device allocations happen here)
     e2e_upload(0)
     e2e_search(0)
     e2e_upload(1)
+    e2e_search(1)
+    e2e_upload(2)
     barrier()
     copy_stream.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for s in range(1, e2e_steps + 1):
+    for s in range(2, e2e_steps + 2):
         e2e_upload(s + 1)
         e2e_search(s)
     copy_stream.synchronize()                  # the last results are on the host
@@ -343,9 +346,10 @@ def run_ours(args, rank, world, local_rank):
     stream.wait_stream(copy_stream)
     e1.record(stream)
     barrier()
-    h_res = h_res2[e2e_steps & 1].numpy().view(CU_RESULT_DTYPE).reshape(B, ncu)
+    last = e2e_steps + 1
+    h_res = h_res2[last & 1].numpy().view(CU_RESULT_DTYPE).reshape(B, ncu)
     # untimed: the pipelined path delivered what the synchronous host call gives for the same pictures
-    base = 100000 + (e2e_steps % 3) * 2 * B
+    base = 100000 + (last % 3) * 2 * B
     chk = ms.search_frames([base + 2 * i for i in range(B)], [base + 2 * i + 1 for i in range(B)], prm, h_pred)
     if not np.array_equal(h_res, chk):
         raise RuntimeError("e2e: pipelined results differ from the synchronous call")
