@@ -338,6 +338,9 @@ def run_ours(args, rank, world, local_rank):
     copy_stream.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
+    e2e_prof = os.environ.get("BENCH_E2E_PROFILE") == "1"   # development: kernel times of the last pipelined step
+    if e2e_prof:
+        ms.set_profiling(True)
     for s in range(2, e2e_steps + 2):
         e2e_upload(s + 1)
         e2e_search(s)
@@ -346,6 +349,10 @@ def run_ours(args, rank, world, local_rank):
     stream.wait_stream(copy_stream)
     e1.record(stream)
     barrier()
+    if e2e_prof:
+        sys.stderr.write("e2e kernel ms of the last step (tree, upper, frac): %s; step %.2f ms\n"
+                         % (ms.frame_kernel_ms(), e0.elapsed_time(e1) / e2e_steps))
+        ms.set_profiling(False)
     last = e2e_steps + 1
     h_res = h_res2[last & 1].numpy().view(CU_RESULT_DTYPE).reshape(B, ncu)
     # untimed: the pipelined path delivered what the synchronous host call gives for the same pictures

@@ -192,6 +192,7 @@ cudaError_t launch_filter_batch(int taps, int vertical, int isFirst, int isLast,
                                 long long srcBlockStride, int16_t* dst, int dstStride, long long dstBlockStride, int w, int h,
                                 const int16_t* coeff, int bitDepth, int n, cudaStream_t st);
 cudaError_t launch_extend_border(DevPic pic, cudaStream_t st);
+cudaError_t launch_scatter_extend(DevPic pic, const int16_t* staging, int srcStride, cudaStream_t st);
 
 // Motion compensation (mc_kernels.cu): a block is cut into tiles of at most 16x16 outputs, one warp each
 struct McTile

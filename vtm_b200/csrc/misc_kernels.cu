@@ -18,6 +18,20 @@ __global__ void extend_border_kernel(DevPic p)
   }
 }
 
+// Same replication, the picture area coming from a contiguous staging copy of the caller's plane (row stride
+// srcStride): one pass writes the whole padded plane.  Used by the host uploads — a 2-D DMA of 1080 narrow rows is an
+// order of magnitude slower than one contiguous transfer.
+__global__ void scatter_extend_kernel(DevPic p, const int16_t* __restrict__ staging, int srcStride)
+{
+  const int W = p.width + 2 * p.margin, H = p.height + 2 * p.margin;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < W * H; i += gridDim.x * blockDim.x)
+  {
+    const int y = i / W - p.margin, x = i % W - p.margin;
+    const int sx = min(max(x, 0), p.width - 1), sy = min(max(y, 0), p.height - 1);
+    p.origin[(ptrdiff_t) y * p.stride + x] = staging[(size_t) sy * srcStride + sx];
+  }
+}
+
 // ---- SAD: RdCost::xGetSAD (RdCost.cpp:493-528) / xGetSAD_NxN_SIMD (x86/RdCostX86.h:341-456) ----
 // Generic layout: one warp per block, scalar loads.
 __global__ void __launch_bounds__(256) sad_batch_kernel(const int16_t* __restrict__ org, int orgStride, long long orgBlk,
@@ -326,6 +340,12 @@ const int16_t h_chroma[32][4] = {
 };
 
 }   // namespace
+
+cudaError_t launch_scatter_extend(DevPic pic, const int16_t* staging, int srcStride, cudaStream_t st)
+{
+  scatter_extend_kernel<<<592, 256, 0, st>>>(pic, staging, srcStride);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_extend_border(DevPic pic, cudaStream_t st)
 {

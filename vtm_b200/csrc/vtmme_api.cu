@@ -64,6 +64,10 @@ struct vtmme_ctx
   size_t         hMcTilesCap = 0;
   cudaEvent_t    mcUploaded = nullptr;      // recorded after the tile upload: the next call waits before re-filling
 
+  // contiguous landing zones of host uploads (one per stream that uploads; stream order makes reuse safe)
+  int16_t* dUpStage[2] = { nullptr, nullptr };
+  size_t   upStageCap[2] = { 0, 0 };
+
   // picture descriptors of a frame call: page-locked staging, two slots, so that the call returns without
   // waiting for the copy (vtmme_search_frames_device is asynchronous)
   DevPic*     hPairs = nullptr;
@@ -182,11 +186,24 @@ int upload_common(vtmme_ctx* ctx, int picId, const int16_t* origin, int stride, 
       ctx->picReady.erase(it);
     }
   }
-  VTMME_CUDA_CHECK(ctx, cudaMemcpy2DAsync(p.origin - (ptrdiff_t) cm * p.stride - cm, (size_t) p.stride * 2,
-                                          origin - (ptrdiff_t) cm * stride - cm, (size_t) stride * 2,
-                                          (size_t) (width + 2 * cm) * 2, height + 2 * cm, kind, st));
-  // everything beyond is edge replication (Picture::extendPicBorder, Picture.cpp:1050-1096)
-  VTMME_CUDA_CHECK(ctx, launch_extend_border(p, st));
+  if (kind == cudaMemcpyHostToDevice && cm == 0 && stride - width < 64)
+  {
+    // (nearly) contiguous host plane: ONE transfer into a landing zone, then one kernel writes the padded plane —
+    // picture area and replicated border (Picture::extendPicBorder, Picture.cpp:1050-1096) — in a single pass
+    const int    k     = async ? 1 : 0;
+    const size_t bytes = ((size_t) stride * (height - 1) + width) * 2;
+    if ((rc = ensure(ctx, ctx->dUpStage[k], ctx->upStageCap[k], bytes)) != VTMME_OK) return rc;
+    VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dUpStage[k], origin, bytes, kind, st));
+    VTMME_CUDA_CHECK(ctx, launch_scatter_extend(p, ctx->dUpStage[k], stride, st));
+  }
+  else
+  {
+    VTMME_CUDA_CHECK(ctx, cudaMemcpy2DAsync(p.origin - (ptrdiff_t) cm * p.stride - cm, (size_t) p.stride * 2,
+                                            origin - (ptrdiff_t) cm * stride - cm, (size_t) stride * 2,
+                                            (size_t) (width + 2 * cm) * 2, height + 2 * cm, kind, st));
+    // everything beyond is edge replication (Picture::extendPicBorder, Picture.cpp:1050-1096)
+    VTMME_CUDA_CHECK(ctx, launch_extend_border(p, st));
+  }
   ctx->launches += 1;
   if (async) VTMME_CUDA_CHECK(ctx, cudaEventRecord(ctx->picReady[picId], st));
   else if (kind == cudaMemcpyHostToDevice) VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -252,6 +269,8 @@ void vtmme_destroy(vtmme_ctx* ctx)
   cudaFree(ctx->dJobFracAcc);
   if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
   if (ctx->hPairs) cudaFreeHost(ctx->hPairs);
+  cudaFree(ctx->dUpStage[0]);
+  cudaFree(ctx->dUpStage[1]);
   for (int i = 0; i < 2; i++)
     if (ctx->pairsCopied[i]) cudaEventDestroy(ctx->pairsCopied[i]);
   for (int i = 0; i < 4; i++)
@@ -361,6 +380,8 @@ int vtmme_search_frames_device(vtmme_ctx* ctx, int nPairs, const int32_t* curPic
   {
     VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->hPairs) cudaFreeHost(ctx->hPairs);
+  cudaFree(ctx->dUpStage[0]);
+  cudaFree(ctx->dUpStage[1]);
     ctx->hPairs    = nullptr;
     ctx->hPairsCap = 0;
     void* hp       = nullptr;
