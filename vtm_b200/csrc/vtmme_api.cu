@@ -64,9 +64,9 @@ struct vtmme_ctx
   size_t         hMcTilesCap = 0;
   cudaEvent_t    mcUploaded = nullptr;      // recorded after the tile upload: the next call waits before re-filling
 
-  // contiguous landing zones of host uploads (one per stream that uploads; stream order makes reuse safe)
-  int16_t* dUpStage[2] = { nullptr, nullptr };
-  size_t   upStageCap[2] = { 0, 0 };
+  // contiguous landing zone of the pipelined host uploads (copy stream)
+  int16_t* dUpStage = nullptr;
+  size_t   upStageCap = 0;
 
   // picture descriptors of a frame call: page-locked staging, two slots, so that the call returns without
   // waiting for the copy (vtmme_search_frames_device is asynchronous)
@@ -186,15 +186,15 @@ int upload_common(vtmme_ctx* ctx, int picId, const int16_t* origin, int stride, 
       ctx->picReady.erase(it);
     }
   }
-  if (kind == cudaMemcpyHostToDevice && cm == 0 && stride - width < 64)
+  if (async && kind == cudaMemcpyHostToDevice && cm == 0 && stride - width < 64)
   {
-    // (nearly) contiguous host plane: ONE transfer into a landing zone, then one kernel writes the padded plane —
-    // picture area and replicated border (Picture::extendPicBorder, Picture.cpp:1050-1096) — in a single pass
-    const int    k     = async ? 1 : 0;
+    // pipelined upload of a (nearly) contiguous page-locked plane: ONE transfer into a landing zone, then one kernel
+    // writes the padded plane — picture area and replicated border (Picture::extendPicBorder, Picture.cpp:1050-1096) —
+    // in a single pass.  (Stream order on the copy stream makes the reuse of the landing zone safe.)
     const size_t bytes = ((size_t) stride * (height - 1) + width) * 2;
-    if ((rc = ensure(ctx, ctx->dUpStage[k], ctx->upStageCap[k], bytes)) != VTMME_OK) return rc;
-    VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dUpStage[k], origin, bytes, kind, st));
-    VTMME_CUDA_CHECK(ctx, launch_scatter_extend(p, ctx->dUpStage[k], stride, st));
+    if ((rc = ensure(ctx, ctx->dUpStage, ctx->upStageCap, bytes)) != VTMME_OK) return rc;
+    VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dUpStage, origin, bytes, kind, st));
+    VTMME_CUDA_CHECK(ctx, launch_scatter_extend(p, ctx->dUpStage, stride, st));
   }
   else
   {
@@ -269,8 +269,7 @@ void vtmme_destroy(vtmme_ctx* ctx)
   cudaFree(ctx->dJobFracAcc);
   if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
   if (ctx->hPairs) cudaFreeHost(ctx->hPairs);
-  cudaFree(ctx->dUpStage[0]);
-  cudaFree(ctx->dUpStage[1]);
+  cudaFree(ctx->dUpStage);
   for (int i = 0; i < 2; i++)
     if (ctx->pairsCopied[i]) cudaEventDestroy(ctx->pairsCopied[i]);
   for (int i = 0; i < 4; i++)
@@ -380,8 +379,7 @@ int vtmme_search_frames_device(vtmme_ctx* ctx, int nPairs, const int32_t* curPic
   {
     VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->hPairs) cudaFreeHost(ctx->hPairs);
-  cudaFree(ctx->dUpStage[0]);
-  cudaFree(ctx->dUpStage[1]);
+  cudaFree(ctx->dUpStage);
     ctx->hPairs    = nullptr;
     ctx->hPairsCap = 0;
     void* hp       = nullptr;
