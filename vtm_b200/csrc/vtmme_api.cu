@@ -168,7 +168,14 @@ int upload_common(vtmme_ctx* ctx, int picId, const int16_t* origin, int stride, 
   cudaStream_t st = ctx->stream;
   if (async)
   {
-    if (!ctx->copyStream) VTMME_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+    if (!ctx->copyStream)
+    {
+      // highest priority: the short border kernels of an upload must not queue behind the CTAs of a running search
+      // (with equal priority 64 uploads took longer than the 79 ms search they overlap with)
+      int lo = 0, hi = 0;
+      VTMME_CUDA_CHECK(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      VTMME_CUDA_CHECK(ctx, cudaStreamCreateWithPriority(&ctx->copyStream, cudaStreamNonBlocking, hi));
+    }
     st = ctx->copyStream;
     // the copy must not overtake searches already queued on the compute stream that still read this picture
     cudaEvent_t& ev = ctx->picReady[picId];
