@@ -301,14 +301,10 @@ def run_ours(args, rank, world, local_rank):
         h_pred_pinned = torch.from_numpy(h_pred).pin_memory()
         d_pred_e2e = torch.zeros_like(h_pred_pinned, device=dev)
 
-    e2e_skip = os.environ.get("BENCH_E2E_SKIP", "")   # development: leave a stage out to see what it costs
-
     def e2e_upload(s):
         """queue the H2D copies of step s on the library's copy stream; picture ids triple-buffered"""
         if s >= 3:
             searched[s % 3].synchronize()      # the search that last used this slot (step s-3) is done
-        if e2e_skip == "upload" and s >= 3:
-            return
         base = 100000 + (s % 3) * 2 * B
         for i in range(B):
             p = (s * B + i) % npool
@@ -329,8 +325,7 @@ def run_ours(args, rank, world, local_rank):
         searched[s % 3].record(stream)
         copy_stream.wait_event(searched[s % 3])
         with torch.cuda.stream(copy_stream):
-            if e2e_skip != "d2h":
-                h_res2[k].copy_(d_res2[k], non_blocking=True)
+            h_res2[k].copy_(d_res2[k], non_blocking=True)
             copied[k].record(copy_stream)
 
     # warm-up: every picture slot and result buffer is used once (device allocations happen here)
@@ -363,7 +358,7 @@ def run_ours(args, rank, world, local_rank):
     # untimed: the pipelined path delivered what the synchronous host call gives for the same pictures
     base = 100000 + (last % 3) * 2 * B
     chk = ms.search_frames([base + 2 * i for i in range(B)], [base + 2 * i + 1 for i in range(B)], prm, h_pred)
-    if not e2e_skip and not np.array_equal(h_res, chk):
+    if not np.array_equal(h_res, chk):
         raise RuntimeError("e2e: pipelined results differ from the synchronous call")
     e2e_ms = max_over_ranks(e0.elapsed_time(e1), dev)
     e2e_value = world * B * e2e_steps * cands_pair / (e2e_ms * 1e-3)
