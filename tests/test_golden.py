@@ -122,3 +122,82 @@ def test_oracle_bipred_helpers_golden():
         t = np.ascontiguousarray(GM["hf_org"]).copy()
         L.vo_remove_high_freq(B.ptr(t), B.ptr(pred), t.size, clip, 10)
         assert np.array_equal(t, GM["hf_out%d" % clip])
+
+
+# ---- TZ search / AMVR refinement fixtures (tests/golden/amvr_tz_golden.npz, make_golden_amvr_tz.py) -------------------
+GA = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "amvr_tz_golden.npz"))
+GA_W, GA_H = 192, 128
+
+
+def iter_tz():
+    """(w, h, x, y, predQ, subShiftMode, oracle TzParams, lambda, want (mvX, mvY, sad, hx, hy, qx, qy, fracCost))"""
+    from oracle import bindings as B
+    for row, lam, res in zip(GA["tz_int"], GA["tz_lambda"], GA["tz_res"]):
+        row = [int(v) for v in row]
+        w, h, x, y, pqx, pqy, ssm = row[:7]
+        t = B.TzParams()
+        t.startX, t.startY, t.hasInt2Nx2N, t.int2Nx2NX, t.int2Nx2NY, t.nSeeds = row[7:13]
+        for i in range(16):
+            t.seedX[i], t.seedY[i] = row[13 + i], row[29 + i]
+        t.searchRange, t.extended, t.fast, t.firstSearchStop = row[45:49]
+        t.posX, t.posY, t.picW, t.picH, t.maxCuW, t.maxCuH = x, y, GA_W, GA_H, 128, 128
+        yield w, h, x, y, (pqx, pqy), ssm, t, float(lam), tuple(int(v) for v in res)
+
+
+def iter_amvr():
+    """(w, h, x, y, predQ, window, imv, useHad, oracle IntRefine state (mv not set), lambda,
+    want (intX, intY, intSad, mvX, mvY, mvpIdx, bits, cost))"""
+    from oracle import bindings as B
+    for row, f, res in zip(GA["ir_int"], GA["ir_f"], GA["ir_res"]):
+        row = [int(v) for v in row]
+        w, h, x, y, pqx, pqy = row[:6]
+        io = B.IntRefine()
+        io.imv, io.numCand = row[10], row[12]
+        io.candX[0], io.candY[0], io.candX[1], io.candY[1] = row[13:17]
+        io.mvpIdx, io.mvpIdxBits[0], io.mvpIdxBits[1], io.bits = row[17:21]
+        io.fWeight = float(f[1])
+        io.posX, io.posY, io.picW, io.picH, io.maxCuW, io.maxCuH = x, y, GA_W, GA_H, 128, 128
+        yield w, h, x, y, (pqx, pqy), tuple(row[6:10]), row[10], row[11], io, float(f[0]), tuple(int(v) for v in res)
+
+
+def _ga_planes():
+    from tests.helpers import MARGIN, pad_plane
+    cur = np.ascontiguousarray(GA["cur"])
+    refp = pad_plane(np.ascontiguousarray(GA["ref"]))
+    return cur, refp, MARGIN
+
+
+def test_tz_golden(oracle_lib):
+    """oracle xTZSearch + fractional refinement == the reference's (60 cases: FastSearch=1, enhanced, fast re-search)"""
+    from oracle import bindings as B
+    cur, refp, m = _ga_planes()
+    stride = refp.shape[1]
+    n = 0
+    for w, h, x, y, pq, ssm, t, lam, want in iter_tz():
+        j = B.make_job(cur, refp, stride, (m + y) * stride + m + x, w, h, (0, 0, 0, 0), pq, 0, ssm, 10, 1, 0, 1, lam,
+                       org_off=y * GA_W + x, org_stride=GA_W)
+        mx, my, sad = C.c_int(), C.c_int(), C.c_uint64()
+        oracle_lib.vo_tz_search(C.byref(j), C.byref(t), C.byref(mx), C.byref(my), C.byref(sad), None)
+        hx, hy, qx, qy, cost = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_uint64()
+        oracle_lib.vo_frac_direct(C.byref(j), mx.value, my.value, C.byref(hx), C.byref(hy), C.byref(qx), C.byref(qy), C.byref(cost))
+        assert (mx.value, my.value, sad.value, hx.value, hy.value, qx.value, qy.value, cost.value) == want, (w, h, x, y)
+        n += 1
+    assert n == 60
+
+
+def test_amvr_golden(oracle_lib):
+    """oracle xPatternSearch + xPatternSearchIntRefine == the reference's (40 cases: FPEL / 4PEL, SATD / SAD)"""
+    from oracle import bindings as B
+    cur, refp, m = _ga_planes()
+    stride = refp.shape[1]
+    n = 0
+    for w, h, x, y, pq, win, imv, use_had, io, lam, want in iter_amvr():
+        j = B.make_job(cur, refp, stride, (m + y) * stride + m + x, w, h, win, pq, imv << 1, 0, 10, use_had, 0, 0, lam,
+                       org_off=y * GA_W + x, org_stride=GA_W)
+        r = B.Result()
+        oracle_lib.vo_search(C.byref(j), C.byref(r), 0)
+        io.mvX, io.mvY = r.mvX * 16, r.mvY * 16
+        oracle_lib.vo_int_refine(C.byref(j), C.byref(io))
+        assert (r.mvX, r.mvY, r.intSad) + io.tuple() == want, (w, h, x, y)
+        n += 1
+    assert n == 40

@@ -43,3 +43,39 @@ def test_gpu_search_golden(ms):
         want.append(res)
     got = ms.search(jobs)
     assert got == want
+
+
+def test_gpu_tz_golden(ms):
+    """vtmme_search with vtmme_tz against the reference's own xTZSearch + fractional refinement (committed fixtures)."""
+    from tests.test_golden import GA_H, GA_W, _ga_planes, iter_tz
+    from vtm_b200 import Job, TzSearch
+    cur, refp, m = _ga_planes()
+    ms.upload_picture(60, cur)
+    ms.upload_picture(61, refp, m)
+    jobs, want = [], []
+    for w, h, x, y, pq, ssm, t, lam, res in iter_tz():
+        ss = 1 if (ssm == 2 and h > 8 and w <= 64) else 0
+        tz = TzSearch((t.startX, t.startY), t.searchRange, GA_W, GA_H, tuple((t.seedX[i], t.seedY[i]) for i in range(t.nSeeds)),
+                      (t.int2Nx2NX, t.int2Nx2NY) if t.hasInt2Nx2N else None, t.extended, t.fast, t.firstSearchStop)
+        jobs.append(Job(60, 61, x, y, w, h, (0, 0, 0, 0), pq, 0, ss, 10, 1, 0, 1, lam, None, None, tz))
+        want.append(res)
+    assert ms.search(jobs) == want
+    assert [ms.search([j])[0] for j in jobs] == want
+
+
+def test_gpu_amvr_golden(ms):
+    """vtmme_search fracMode 2 against the reference's own xPatternSearch + xPatternSearchIntRefine (committed fixtures)."""
+    from tests.test_golden import GA_H, GA_W, _ga_planes, iter_amvr
+    from vtm_b200 import Amvr, Job
+    cur, refp, m = _ga_planes()
+    ms.upload_picture(60, cur)
+    ms.upload_picture(61, refp, m)
+    jobs, want = [], []
+    for w, h, x, y, pq, win, imv, use_had, io, lam, res in iter_amvr():
+        am = Amvr(imv, ((io.candX[0], io.candY[0]), (io.candX[1], io.candY[1])), io.numCand, io.mvpIdx,
+                  (io.mvpIdxBits[0], io.mvpIdxBits[1]), io.bits, GA_W, GA_H, io.fWeight)
+        jobs.append(Job(60, 61, x, y, w, h, win, pq, imv << 1, 0, 10, use_had, 0, 2, lam, None, am))
+        want.append(res)
+    pick = lambda t: t[:3] + t[8:]
+    assert [pick(t) for t in ms.search(jobs)] == want
+    assert [pick(ms.search([j])[0]) for j in jobs] == want
