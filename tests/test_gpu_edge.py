@@ -200,6 +200,22 @@ def test_error_codes(ms):
         ms.search_frames([50], [50], FrameParams(searchRange=8, predSpread=0), pred)
     with pytest.raises(vtm_b200.VtmmeError, match="NOPIC"):
         ms.release_picture(12345)
+    # TZ search / AMVR refinement descriptors
+    from vtm_b200 import Amvr, TzSearch
+    tz = TzSearch((0, 0), 16, 32, 32)
+    good = Job(50, 50, 8, 8, 8, 8, (-2, 2, -2, 2), (0, 0), tz=tz)
+    assert len(ms.search([good])) == 1
+    with pytest.raises(vtm_b200.VtmmeError, match="ARG"):                        # TZ and full-search jobs in one call
+        ms.search([good, Job(50, 50, 8, 8, 8, 8, (-2, 2, -2, 2), (0, 0))])
+    with pytest.raises(vtm_b200.VtmmeError, match="ARG"):                        # clip rectangle is not the picture's
+        ms.search([Job(50, 50, 8, 8, 8, 8, (-2, 2, -2, 2), (0, 0), tz=TzSearch((0, 0), 16, 64, 32))])
+    with pytest.raises(vtm_b200.VtmmeError, match="ARG"):                        # fracMode 2 without its state
+        ms.search([Job(50, 50, 8, 8, 8, 8, (-2, 2, -2, 2), (0, 0), imvShift=2, fracMode=2)])
+    with pytest.raises(vtm_b200.VtmmeError, match="ARG"):                        # quarter-pel CUs have no integer refinement
+        ms.search([Job(50, 50, 8, 8, 8, 8, (-2, 2, -2, 2), (0, 0), imvShift=2, fracMode=2,
+                       amvr=Amvr(0, ((0, 0), (0, 0)), 1, 0, (0, 0), 3, 32, 32))])
+    with pytest.raises(vtm_b200.VtmmeError, match="ARG"):
+        ms.search_frames([50], [50], FrameParams(searchRange=8, fastSearch=2))  # the selective search is not built
 
 
 def test_full_size_properties(ms, oracle_lib):
