@@ -31,6 +31,7 @@
 #include "CommonLib/CodingStructure.h"
 #include "EncoderLib/EncCfg.h"
 #include "EncoderLib/InterSearch.h"
+#include "EncoderLib/EncTemporalFilter.h"
 
 namespace {
 
@@ -520,6 +521,49 @@ double ref_tz_batch(const RefSearchJob* jobs, const RefTzParams* tz, int n, int 
     for (auto& t : th) t.join();
   }
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// ---- EncTemporalFilter::motionEstimation (EncTemporalFilter.cpp:448-466), the reference's own member ----------------
+// org / ref: sample (0,0) of planes carrying `margin` (>= 0) valid border samples; the shim copies the picture area
+// into PelStorage buffers with the filter's own padding (128) and extends the border as EncTemporalFilter::filter does
+// (:169-204).  mv: (width/4) x (height/4) entries {x, y, error}.  Returns the seconds spent in motionEstimation.
+double ref_mctf_me(const int16_t* org, int orgStride, const int16_t* ref, int refStride, int width, int height, int bitDepth,
+                   int32_t* mv)
+{
+  EncTemporalFilter tf;
+  tf.m_chromaFormatIDC = CHROMA_400;
+  tf.m_sourceWidth     = width;
+  tf.m_sourceHeight    = height;
+  for (int i = 0; i < MAX_NUM_CHANNEL_TYPE; i++) tf.m_internalBitDepth[i] = bitDepth;
+  const int  pad = EncTemporalFilter::m_padding;
+  const Area area(0, 0, width, height);
+  PelStorage o, b, o2, o4;
+  o.create(CHROMA_400, area, 0, pad);
+  b.create(CHROMA_400, area, 0, pad);
+  for (int y = 0; y < height; y++)
+  {
+    memcpy(o.Y().buf + (ptrdiff_t) y * o.Y().stride, org + (ptrdiff_t) y * orgStride, sizeof(int16_t) * width);
+    memcpy(b.Y().buf + (ptrdiff_t) y * b.Y().stride, ref + (ptrdiff_t) y * refStride, sizeof(int16_t) * width);
+  }
+  o.extendBorderPel(pad, pad);
+  b.extendBorderPel(pad, pad);
+  tf.subsampleLuma(o, o2);
+  tf.subsampleLuma(o2, o4);
+  Array2D<MotionVector> mvs;
+  mvs.allocate(width / 4, height / 4);
+  auto t0 = std::chrono::steady_clock::now();
+  tf.motionEstimation(mvs, o, b, o2, o4);
+  const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  for (int y = 0; y < height / 4; y++)
+    for (int x = 0; x < width / 4; x++)
+    {
+      const MotionVector& m = mvs.get(x, y);
+      int32_t*            d = mv + 3 * ((size_t) y * (width / 4) + x);
+      d[0] = m.x;
+      d[1] = m.y;
+      d[2] = m.error;
+    }
+  return sec;
 }
 
 // Batch driver used as the CPU baseline: nThreads workers over disjoint job ranges.

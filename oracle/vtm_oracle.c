@@ -1016,3 +1016,226 @@ void vo_tz_search(const vo_job* j, const vo_tz_params* p, int* mvx, int* mvy, ui
   *sadOut = s.bestSad - vo_mv_cost(j->lambdaMotion, vo_mv_bits(s.bestX, s.bestY, j->predQx, j->predQy, 2, j->imvShift));
   if (nProbes) *nProbes = s.probes;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * GOP-based temporal filter: motion estimation
+ * ---------------------------------------------------------------------------------------------- */
+
+#define VO_MCTF_PAD 128 /* EncTemporalFilter::m_padding */
+
+static const int vo_mctf_filter[16][8] = { /* EncTemporalFilter::m_interpolationFilter — EncTemporalFilter.cpp:50-68 */
+  { 0, 0, 0, 64, 0, 0, 0, 0 },    { 0, 1, -3, 64, 4, -2, 0, 0 },   { 0, 1, -6, 62, 9, -3, 1, 0 },   { 0, 2, -8, 60, 14, -5, 1, 0 },
+  { 0, 2, -9, 57, 19, -7, 2, 0 }, { 0, 3, -10, 53, 24, -8, 2, 0 }, { 0, 3, -11, 50, 29, -9, 2, 0 }, { 0, 3, -11, 44, 35, -10, 3, 0 },
+  { 0, 1, -7, 38, 38, -7, 1, 0 }, { 0, 3, -10, 35, 44, -11, 3, 0 }, { 0, 2, -9, 29, 50, -11, 3, 0 }, { 0, 2, -8, 24, 53, -10, 3, 0 },
+  { 0, 2, -7, 19, 57, -9, 2, 0 }, { 0, 1, -5, 14, 60, -8, 2, 0 },  { 0, 1, -3, 9, 62, -6, 1, 0 },   { 0, 0, -2, 4, 64, -3, 1, 0 }
+};
+
+/* EncTemporalFilter::motionErrorLuma — EncTemporalFilter.cpp:268-361 */
+int vo_mctf_error(const vo_pel* org, int orgStride, const vo_pel* ref, int refStride, int x, int y, int dx, int dy, int bs,
+                  int bestError, int bitDepth)
+{
+  int error = 0, x1, y1;
+  if (((dx | dy) & 0xF) == 0)
+  {
+    dx /= 16;
+    dy /= 16;
+    for (y1 = 0; y1 < bs; y1++)
+    {
+      const vo_pel* o = org + (ptrdiff_t) (y + y1) * orgStride + x;
+      const vo_pel* b = ref + (ptrdiff_t) (y + y1 + dy) * refStride + (x + dx);
+      for (x1 = 0; x1 < bs; x1++)
+      {
+        const int diff = o[x1] - b[x1];
+        error += diff * diff;
+      }
+      if (error > bestError) return error;
+    }
+  }
+  else
+  {
+    const int* xf = vo_mctf_filter[dx & 0xF];
+    const int* yf = vo_mctf_filter[dy & 0xF];
+    const int  maxv = (1 << bitDepth) - 1;
+    int        tmp[64 + 8][64];
+    for (y1 = 1; y1 < bs + 7; y1++)
+    {
+      const vo_pel* row = ref + (ptrdiff_t) (y + y1 + (dy >> 4) - 3) * refStride;
+      for (x1 = 0; x1 < bs; x1++)
+      {
+        const vo_pel* p   = row + (x + x1 + (dx >> 4) - 3);
+        int           sum = 0, k;
+        for (k = 1; k <= 6; k++) sum += xf[k] * p[k];
+        tmp[y1][x1] = sum;
+      }
+    }
+    for (y1 = 0; y1 < bs; y1++)
+    {
+      const vo_pel* o = org + (ptrdiff_t) (y + y1) * orgStride;
+      for (x1 = 0; x1 < bs; x1++)
+      {
+        int sum = 0, k;
+        for (k = 1; k <= 6; k++) sum += yf[k] * tmp[y1 + k][x1];
+        sum = (sum + (1 << 11)) >> 12;
+        sum = sum < 0 ? 0 : (sum > maxv ? maxv : sum);
+        error += (sum - o[x + x1]) * (sum - o[x + x1]);
+      }
+      if (error > bestError) return error;
+    }
+  }
+  return error;
+}
+
+typedef struct
+{
+  vo_pel* base;
+  vo_pel* origin;
+  int     stride, width, height;
+} vo_plane;
+
+static void vo_plane_alloc(vo_plane* p, int width, int height)
+{
+  p->width  = width;
+  p->height = height;
+  p->stride = width + 2 * VO_MCTF_PAD;
+  p->base   = (vo_pel*) malloc(sizeof(vo_pel) * (size_t) p->stride * (height + 2 * VO_MCTF_PAD));
+  p->origin = p->base + (size_t) VO_MCTF_PAD * p->stride + VO_MCTF_PAD;
+}
+
+/* EncTemporalFilter::subsampleLuma — EncTemporalFilter.cpp:241-266 (2x2 mean, then extendBorderPel) */
+static void vo_mctf_subsample(const vo_pel* in, int inStride, int inW, int inH, vo_plane* out)
+{
+  int x, y;
+  vo_plane_alloc(out, inW / 2, inH / 2);
+  for (y = 0; y < out->height; y++)
+    for (x = 0; x < out->width; x++)
+    {
+      const vo_pel* a = in + (ptrdiff_t) (2 * y) * inStride + 2 * x;
+      out->origin[(ptrdiff_t) y * out->stride + x] = (vo_pel) ((a[0] + a[inStride] + a[1] + a[inStride + 1] + 2) >> 2);
+    }
+  for (y = -VO_MCTF_PAD; y < out->height + VO_MCTF_PAD; y++)
+    for (x = -VO_MCTF_PAD; x < out->width + VO_MCTF_PAD; x++)
+    {
+      const int sx = x < 0 ? 0 : (x >= out->width ? out->width - 1 : x);
+      const int sy = y < 0 ? 0 : (y >= out->height ? out->height - 1 : y);
+      out->origin[(ptrdiff_t) y * out->stride + x] = out->origin[(ptrdiff_t) sy * out->stride + sx];
+    }
+}
+
+typedef struct
+{
+  int x, y, error;
+} vo_mctf_mv;
+
+/* EncTemporalFilter::motionEstimationLuma — EncTemporalFilter.cpp:363-446.  mvs / previous: arrays of mvW entries per row */
+static void vo_mctf_level(vo_mctf_mv* mvs, int mvW, const vo_pel* org, int os, const vo_pel* buf, int bstride, int origWidth,
+                          int origHeight, int blockSize, const vo_mctf_mv* previous, int prevW, int factor, int doubleRes, int bd)
+{
+  int range = 5, blockX, blockY, px, py, x2, y2;
+  for (blockY = 0; blockY + blockSize < origHeight; blockY += blockSize)
+    for (blockX = 0; blockX + blockSize < origWidth; blockX += blockSize)
+    {
+      vo_mctf_mv best = { 0, 0, INT32_MAX }, prev;
+      if (!previous)
+        range = 8;
+      else
+        for (py = -2; py <= 2; py++)
+        {
+          const int testy = blockY / (2 * blockSize) + py;
+          for (px = -2; px <= 2; px++)
+          {
+            const int testx = blockX / (2 * blockSize) + px;
+            if (testx >= 0 && testx < origWidth / (2 * blockSize) && testy >= 0 && testy < origHeight / (2 * blockSize))
+            {
+              const vo_mctf_mv old = previous[testy * prevW + testx];
+              const int        e   = vo_mctf_error(org, os, buf, bstride, blockX, blockY, old.x * factor, old.y * factor, blockSize, best.error, bd);
+              if (e < best.error)
+              {
+                best.x     = old.x * factor;
+                best.y     = old.y * factor;
+                best.error = e;
+              }
+            }
+          }
+        }
+      prev = best;
+      for (y2 = prev.y / 16 - range; y2 <= prev.y / 16 + range; y2++)
+        for (x2 = prev.x / 16 - range; x2 <= prev.x / 16 + range; x2++)
+        {
+          const int e = vo_mctf_error(org, os, buf, bstride, blockX, blockY, x2 * 16, y2 * 16, blockSize, best.error, bd);
+          if (e < best.error)
+          {
+            best.x     = x2 * 16;
+            best.y     = y2 * 16;
+            best.error = e;
+          }
+        }
+      if (doubleRes)
+      {
+        int pass;
+        for (pass = 0; pass < 2; pass++) /* +-12 in steps of 4, then +-3 in steps of 1 (1/16 sample) */
+        {
+          const int dr = pass ? 3 : 12, st = pass ? 1 : 4;
+          prev = best;
+          for (y2 = prev.y - dr; y2 <= prev.y + dr; y2 += st)
+            for (x2 = prev.x - dr; x2 <= prev.x + dr; x2 += st)
+            {
+              const int e = vo_mctf_error(org, os, buf, bstride, blockX, blockY, x2, y2, blockSize, best.error, bd);
+              if (e < best.error)
+              {
+                best.x     = x2;
+                best.y     = y2;
+                best.error = e;
+              }
+            }
+        }
+      }
+      mvs[(blockY / blockSize) * mvW + blockX / blockSize] = best;
+    }
+}
+
+/* EncTemporalFilter::motionEstimation — EncTemporalFilter.cpp:448-466 */
+void vo_mctf_me(const vo_pel* org, int orgStride, const vo_pel* ref, int refStride, int width, int height, int bitDepth,
+                int32_t* mvOut)
+{
+  const int   lw = width / 16, lh = height / 16; /* the three intermediate fields are (width/16) x (height/16) */
+  const int   fw = width / 4, fh = height / 4;
+  vo_plane    o2, o4, b2, b4;
+  vo_mctf_mv *mv0, *mv1, *mv2, *mv;
+  int         i;
+  mv0 = (vo_mctf_mv*) malloc(sizeof(vo_mctf_mv) * (size_t) lw * lh);
+  mv1 = (vo_mctf_mv*) malloc(sizeof(vo_mctf_mv) * (size_t) lw * lh);
+  mv2 = (vo_mctf_mv*) malloc(sizeof(vo_mctf_mv) * (size_t) lw * lh);
+  mv  = (vo_mctf_mv*) malloc(sizeof(vo_mctf_mv) * (size_t) fw * fh);
+  for (i = 0; i < lw * lh; i++)
+  {
+    const vo_mctf_mv d = { 0, 0, INT32_MAX };
+    mv0[i] = mv1[i] = mv2[i] = d;
+  }
+  for (i = 0; i < fw * fh; i++)
+  {
+    const vo_mctf_mv d = { 0, 0, INT32_MAX };
+    mv[i] = d;
+  }
+  vo_mctf_subsample(org, orgStride, width, height, &o2);
+  vo_mctf_subsample(o2.origin, o2.stride, o2.width, o2.height, &o4);
+  vo_mctf_subsample(ref, refStride, width, height, &b2);
+  vo_mctf_subsample(b2.origin, b2.stride, b2.width, b2.height, &b4);
+  vo_mctf_level(mv0, lw, o4.origin, o4.stride, b4.origin, b4.stride, o4.width, o4.height, 16, NULL, 0, 1, 0, bitDepth);
+  vo_mctf_level(mv1, lw, o2.origin, o2.stride, b2.origin, b2.stride, o2.width, o2.height, 16, mv0, lw, 2, 0, bitDepth);
+  vo_mctf_level(mv2, lw, org, orgStride, ref, refStride, width, height, 16, mv1, lw, 2, 0, bitDepth);
+  vo_mctf_level(mv, fw, org, orgStride, ref, refStride, width, height, 8, mv2, lw, 1, 1, bitDepth);
+  for (i = 0; i < fw * fh; i++)
+  {
+    mvOut[3 * i]     = mv[i].x;
+    mvOut[3 * i + 1] = mv[i].y;
+    mvOut[3 * i + 2] = mv[i].error;
+  }
+  free(mv0);
+  free(mv1);
+  free(mv2);
+  free(mv);
+  free(o2.base);
+  free(o4.base);
+  free(b2.base);
+  free(b4.base);
+}

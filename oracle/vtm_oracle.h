@@ -128,6 +128,19 @@ typedef struct
 /* mvx,mvy: rcMv (integer pel); sad: ruiSAD; nProbes (optional): number of xTZSearchHelp + seed distortions */
 void vo_tz_search(const vo_job* j, const vo_tz_params* p, int* mvx, int* mvy, uint64_t* sad, int* nProbes);
 
+/* GOP-based temporal filter: hierarchical motion estimation of one reference frame against the original,
+ * EncTemporalFilter::motionEstimation (EncoderLib/EncTemporalFilter.cpp:448-466) with motionEstimationLuma (:363-446),
+ * motionErrorLuma (:268-361) and subsampleLuma (:241-266).
+ * org / ref: sample (0,0) of planes that carry at least 128 replicated border samples on every side.
+ * mv: (width/4) x (height/4) entries of {x, y, error} (x, y in 1/16 sample), row stride width/4 entries, as
+ * TemporalFilterSourcePicInfo::mvs is allocated (:205); block (bx, by) of the final 8x8 level is entry (bx, by);
+ * entries no block writes keep {0, 0, INT32_MAX}. */
+void vo_mctf_me(const vo_pel* org, int orgStride, const vo_pel* ref, int refStride, int width, int height, int bitDepth,
+                int32_t* mv);
+/* one distortion probe (motionErrorLuma): block bs x bs at (x, y), displacement (dx, dy) in 1/16 sample */
+int  vo_mctf_error(const vo_pel* org, int orgStride, const vo_pel* ref, int refStride, int x, int y, int dx, int dy, int bs,
+                   int bestError, int bitDepth);
+
 #ifdef __cplusplus
 }
 #endif

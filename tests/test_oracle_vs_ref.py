@@ -344,3 +344,24 @@ def test_tz_search(oracle_lib, ref_lib, extended, fast):
                 n += 1
                 probes += a[3].value
     assert n > 300 and probes / n > 20
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("w,h,bd", [(208, 120, 10), (176, 144, 8), (96, 64, 10)])
+def test_mctf_motion_estimation(oracle_lib, ref_lib, w, h, bd):
+    """EncTemporalFilter::motionEstimation (EncTemporalFilter.cpp:448-466): the reference's own member against the
+    restatement — the whole pyramid (1/4, 1/2, full 16x16, full 8x8 with 1/16-sample refinement), every MV and error."""
+    from tests.helpers import pad_plane
+    from vtm_b200.synth import make_pair
+    cur, ref, _ = make_pair(300 + w, w, h, max_global=9, max_local=14, n_rects=3, sigma=5.0, bit_depth=bd)
+    curp, refp = pad_plane(cur, 128), pad_plane(ref, 128)
+    stride = curp.shape[1]
+    off = 128 * stride + 128
+    a = np.zeros((h // 4, w // 4, 3), np.int32)
+    b = np.zeros_like(a)
+    oracle_lib.vo_mctf_me(B.ptr(curp, off), stride, B.ptr(refp, off), stride, w, h, bd, C.c_void_p(a.ctypes.data))
+    ref_lib.ref_mctf_me(B.ptr(curp, off), stride, B.ptr(refp, off), stride, w, h, bd, C.c_void_p(b.ctypes.data))
+    assert np.array_equal(a, b), np.argwhere(a != b)[:5]
+    n_blocks = int((a[:, :, 2] != np.iinfo(np.int32).max).sum())
+    assert n_blocks == ((h - 1) // 8) * ((w - 1) // 8)          # blocks with blockX + 8 < width, blockY + 8 < height
+    assert (a[:, :, :2][a[:, :, 2] != np.iinfo(np.int32).max] % 16 != 0).any()   # fractional MVs occur
