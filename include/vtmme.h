@@ -22,6 +22,8 @@
  *   InterPrediction::xPredInterBlk (CommonLib/InterPrediction.cpp   vtmme_mc_batch / vtmme_mc_host
  *     :660-830), AreaBuf::addAvg (Buffer.cpp:467-507),              vtmme_add_avg
  *     AreaBuf::removeHighFreq (Buffer.h:474-517)                    vtmme_remove_high_freq
+ *   EncTemporalFilter::motionEstimation (EncoderLib/                vtmme_mctf_me
+ *     EncTemporalFilter.cpp:448-466)
  *   distortion of InterSearch::xGetTemplateCost and of the ME      vtmme_cand_sad
  *     seeds (EncoderLib/InterSearch.cpp:3235-3270, 3388-3426)
  *   Picture::getRecoBuf / getOrigBuf planes handed to ME            vtmme_upload_picture / vtmme_release_picture
@@ -282,6 +284,17 @@ typedef struct vtmme_cand_job
   int32_t        reserved;   /* 0 */
 } vtmme_cand_job;
 int vtmme_cand_sad(vtmme_ctx* ctx, int bitDepth, int useAltHpel, int nJobs, const vtmme_cand_job* jobs, uint64_t* out);
+
+/* ---- GOP-based temporal filter: motion estimation ---------------------------------
+ * EncTemporalFilter::motionEstimation (EncoderLib/EncTemporalFilter.cpp:448-466): the four-level hierarchical block
+ * search of a reference frame against the original (16x16 blocks on the 1/4, 1/2 and full resolution pictures, then
+ * 8x8 blocks with a 1/16-sample refinement; squared error, 6-tap interpolation — motionEstimationLuma :363-446,
+ * motionErrorLuma :268-361, subsampleLuma :241-266).  Pair i searches picture refPics[i] ("buffer") against
+ * orgPics[i]; both uploaded luma planes of the same size (the library replicates / keeps their border; the filter's
+ * own padding is 128 samples).  mv: HOST array, per pair (height/4) x (width/4) entries {x, y, error} (x, y in 1/16
+ * sample, row stride width/4 entries) exactly as TemporalFilterSourcePicInfo::mvs is filled (:205): block (bx, by) of
+ * the 8x8 level at entry (bx, by), entries no block writes {0, 0, INT32_MAX}.  Synchronous. */
+int vtmme_mctf_me(vtmme_ctx* ctx, int nPairs, const int32_t* orgPics, const int32_t* refPics, int bitDepth, int32_t* mv);
 
 /* ---- measurement helpers ------------------------------------------------------------------------
  * Per-kernel timing of the frame path: when enabled, vtmme_search_frames[_device] brackets each of its

@@ -201,3 +201,18 @@ def test_amvr_golden(oracle_lib):
         assert (r.mvX, r.mvY, r.intSad) + io.tuple() == want, (w, h, x, y)
         n += 1
     assert n == 40
+
+
+def test_mctf_golden(oracle_lib):
+    """oracle EncTemporalFilter::motionEstimation == the reference's (tests/golden/mctf_golden.npz)"""
+    from oracle import bindings as B
+    from tests.helpers import pad_plane
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mctf_golden.npz"))
+    cur, ref = np.ascontiguousarray(g["cur"]), np.ascontiguousarray(g["ref"])
+    h, w = cur.shape
+    curp, refp = pad_plane(cur, 128), pad_plane(ref, 128)
+    stride = curp.shape[1]
+    off = 128 * stride + 128
+    out = np.zeros((h // 4, w // 4, 3), np.int32)
+    oracle_lib.vo_mctf_me(B.ptr(curp, off), stride, B.ptr(refp, off), stride, w, h, 10, C.c_void_p(out.ctypes.data))
+    assert np.array_equal(out, g["mv"])

@@ -1,0 +1,58 @@
+"""GPU: motion estimation of the GOP-based temporal filter (vtmme_mctf_me) against the oracle — which is pinned on the
+reference's own EncTemporalFilter::motionEstimation — and against committed vectors of the reference."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import bindings as B  # noqa: E402
+from tests.helpers import pad_plane  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ms():
+    import vtm_b200
+    m = vtm_b200.MotionSearch(0)
+    yield m
+    m.close()
+
+
+def oracle_mctf(L, cur, ref, bd):
+    h, w = cur.shape
+    curp, refp = pad_plane(cur, 128), pad_plane(ref, 128)
+    stride = curp.shape[1]
+    off = 128 * stride + 128
+    out = np.zeros((h // 4, w // 4, 3), np.int32)
+    L.vo_mctf_me(B.ptr(curp, off), stride, B.ptr(refp, off), stride, w, h, bd, C.c_void_p(out.ctypes.data))
+    return out
+
+
+@pytest.mark.parametrize("w,h,bd", [(208, 120, 10), (176, 144, 8), (64, 48, 10), (416, 240, 10)])
+def test_mctf_me_matches_oracle(ms, oracle_lib, w, h, bd):
+    """Whole pyramid, every vector and error; three references against one original in one call; sizes that are not
+    multiples of 16 / 32 (partial last blocks are skipped like the reference skips them)."""
+    from vtm_b200.synth import make_pair
+    pairs = [make_pair(400 + w + k, w, h, max_global=9, max_local=14, n_rects=3, sigma=5.0, bit_depth=bd) for k in range(3)]
+    cur = pairs[0][0]
+    ms.upload_picture(70, cur)
+    for k in range(3):
+        ms.upload_picture(71 + k, pairs[k][1] if k == 0 else pairs[k][0])   # reference frames: one true, two unrelated
+    got = ms.mctf_me([70, 70, 70], [71, 72, 73], w, h, bd)
+    refs = [pairs[0][1], pairs[1][0], pairs[2][0]]
+    for k in range(3):
+        want = oracle_mctf(oracle_lib, cur, refs[k], bd)
+        assert np.array_equal(got[k], want), (k, np.argwhere(got[k] != want)[:4])
+    assert (got[0][:, :, 2] != np.iinfo(np.int32).max).sum() == ((h - 1) // 8) * ((w - 1) // 8)
+
+
+def test_mctf_me_golden(ms):
+    """Committed vectors of the reference itself (tests/golden/mctf_golden.npz, make_golden_mctf.py)."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mctf_golden.npz"))
+    cur, ref = np.ascontiguousarray(g["cur"]), np.ascontiguousarray(g["ref"])
+    h, w = cur.shape
+    ms.upload_picture(74, cur)
+    ms.upload_picture(75, ref)
+    assert np.array_equal(ms.mctf_me([74], [75], w, h, 10)[0], g["mv"])

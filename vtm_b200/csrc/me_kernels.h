@@ -221,4 +221,20 @@ cudaError_t launch_mc_batch(int comp, const McTile* dTiles, int nTiles, int bi, 
 cudaError_t launch_add_avg(const int16_t* a, const int16_t* b, int16_t* d, long long n, int bitDepth, cudaStream_t st);
 cudaError_t launch_remove_high_freq(int16_t* d, const int16_t* s, long long n, int clip, int bitDepth, cudaStream_t st);
 
+// GOP-based temporal filter motion estimation (mctf_kernels.cu)
+struct MctfLevelParams
+{
+  const DevPic* org;        // [nPairs] original picture of this level
+  const DevPic* ref;        // [nPairs] reference ("buffer") picture of this level
+  int           width, height;   // picture size of this level
+  const int3*   previous;   // [nPairs][prevH][prevW] vectors of the coarser level, or nullptr
+  int           prevW, prevH, factor;
+  int3*         mvs;        // [nPairs][mvH][mvW] {x, y, error}
+  int           mvW, mvH;
+  int           maxv;       // (1 << bitDepth) - 1
+};
+cudaError_t launch_mctf_subsample(DevPic in, DevPic out, cudaStream_t st);
+cudaError_t launch_mctf_init_mv(int3* mv, int n, cudaStream_t st);
+cudaError_t launch_mctf_level(const MctfLevelParams& p, int blockSize, bool doubleRes, int nPairs, cudaStream_t st);
+
 }   // namespace vtmme

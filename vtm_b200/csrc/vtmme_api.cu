@@ -68,6 +68,10 @@ struct vtmme_ctx
   int16_t* dUpStage = nullptr;
   size_t   upStageCap = 0;
 
+  // scratch of vtmme_mctf_me: sub-sampled planes, vector fields, picture descriptors
+  unsigned char* dMctf = nullptr;
+  size_t         mctfCap = 0;
+
   // picture descriptors of a frame call: page-locked staging, two slots, so that the call returns without
   // waiting for the copy (vtmme_search_frames_device is asynchronous)
   DevPic*     hPairs = nullptr;
@@ -277,6 +281,7 @@ void vtmme_destroy(vtmme_ctx* ctx)
   if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
   if (ctx->hPairs) cudaFreeHost(ctx->hPairs);
   cudaFree(ctx->dUpStage);
+  cudaFree(ctx->dMctf);
   for (int i = 0; i < 2; i++)
     if (ctx->pairsCopied[i]) cudaEventDestroy(ctx->pairsCopied[i]);
   for (int i = 0; i < 4; i++)
@@ -387,6 +392,7 @@ int vtmme_search_frames_device(vtmme_ctx* ctx, int nPairs, const int32_t* curPic
     VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->hPairs) cudaFreeHost(ctx->hPairs);
   cudaFree(ctx->dUpStage);
+  cudaFree(ctx->dMctf);
     ctx->hPairs    = nullptr;
     ctx->hPairsCap = 0;
     void* hp       = nullptr;
@@ -924,6 +930,96 @@ extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_
     g_timing.wait += tEnd - tEnq;
     g_timing.calls++;
   }
+  return VTMME_OK;
+}
+
+// ---- GOP-based temporal filter: motion estimation -------------------------------------------------------------------
+extern "C" int vtmme_mctf_me(vtmme_ctx* ctx, int nPairs, const int32_t* orgPics, const int32_t* refPics, int bitDepth,
+                             int32_t* mv)
+{
+  if (!ctx) return VTMME_ERR_ARG;
+  if (nPairs <= 0 || !orgPics || !refPics || !mv || bitDepth < 8 || bitDepth > 12)
+    return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_mctf_me", "bad argument");
+  VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  std::vector<DevPic> pics((size_t) 6 * nPairs);   // [level 0,1,2][org, ref][pair]
+  int W = 0, H = 0;
+  for (int i = 0; i < nPairs; i++)
+  {
+    auto a = ctx->pics.find(orgPics[i]), b = ctx->pics.find(refPics[i]);
+    if (a == ctx->pics.end() || b == ctx->pics.end())
+      return vtmme_set_error(ctx, VTMME_ERR_NOPIC, "vtmme_mctf_me", "unknown picture id");
+    if (i == 0)
+    {
+      W = a->second.width;
+      H = a->second.height;
+    }
+    if (a->second.width != W || a->second.height != H || b->second.width != W || b->second.height != H)
+      return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_mctf_me", "all pictures must have the same size");
+    int wrc;
+    if ((wrc = wait_picture(ctx, orgPics[i])) != VTMME_OK || (wrc = wait_picture(ctx, refPics[i])) != VTMME_OK) return wrc;
+    pics[(size_t) 0 * nPairs + i] = a->second;
+    pics[(size_t) 1 * nPairs + i] = b->second;
+  }
+  if (W < 32 || H < 32) return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_mctf_me", "picture smaller than 32x32");
+  // scratch layout: descriptors | sub-sampled planes (margin 128, the filter's own padding) | vector fields
+  const int    pad = 128;
+  const int    w2 = W / 2, h2 = H / 2, w4 = w2 / 2, h4 = h2 / 2;
+  const int    s2 = round_up(w2 + 2 * pad, 64), s4 = round_up(w4 + 2 * pad, 64);
+  const size_t plane2 = align256((size_t) s2 * (h2 + 2 * pad) * 2), plane4 = align256((size_t) s4 * (h4 + 2 * pad) * 2);
+  const int    lw = W / 16, lh = H / 16, fw = W / 4, fh = H / 4;
+  const size_t offDesc = 0, offPlanes = align256(pics.size() * sizeof(DevPic));
+  const size_t offMv = offPlanes + (size_t) nPairs * 2 * (plane2 + plane4);
+  const size_t lowBytes = align256((size_t) nPairs * lw * lh * sizeof(int3)), finBytes = (size_t) nPairs * fw * fh * sizeof(int3);
+  const size_t total = offMv + 3 * lowBytes + finBytes;
+  int rc;
+  if ((rc = ensure(ctx, ctx->dMctf, ctx->mctfCap, total)) != VTMME_OK) return rc;
+  auto sub = [&](size_t off, int w, int h, int stride) {
+    DevPic p;
+    p.base   = reinterpret_cast<int16_t*>(ctx->dMctf + off);
+    p.stride = stride;
+    p.width  = w;
+    p.height = h;
+    p.margin = pad;
+    p.origin = p.base + (size_t) pad * stride + pad;
+    return p;
+  };
+  for (int i = 0; i < nPairs; i++)
+    for (int k = 0; k < 2; k++)   // 0 original, 1 reference
+    {
+      const size_t o = offPlanes + ((size_t) i * 2 + k) * (plane2 + plane4);
+      pics[(size_t) (2 + k) * nPairs + i] = sub(o, w2, h2, s2);
+      pics[(size_t) (4 + k) * nPairs + i] = sub(o + plane2, w4, h4, s4);
+      VTMME_CUDA_CHECK(ctx, launch_mctf_subsample(pics[(size_t) k * nPairs + i], pics[(size_t) (2 + k) * nPairs + i], ctx->stream));
+      VTMME_CUDA_CHECK(ctx, launch_mctf_subsample(pics[(size_t) (2 + k) * nPairs + i], pics[(size_t) (4 + k) * nPairs + i], ctx->stream));
+      ctx->launches += 2;
+    }
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dMctf + offDesc, pics.data(), pics.size() * sizeof(DevPic), cudaMemcpyHostToDevice, ctx->stream));
+  int3* mv0  = reinterpret_cast<int3*>(ctx->dMctf + offMv);
+  int3* mv1  = reinterpret_cast<int3*>(ctx->dMctf + offMv + lowBytes);
+  int3* mv2  = reinterpret_cast<int3*>(ctx->dMctf + offMv + 2 * lowBytes);
+  int3* mvF  = reinterpret_cast<int3*>(ctx->dMctf + offMv + 3 * lowBytes);
+  VTMME_CUDA_CHECK(ctx, launch_mctf_init_mv(mv0, (int) ((3 * lowBytes + finBytes) / sizeof(int3)), ctx->stream));
+  const DevPic* d = reinterpret_cast<const DevPic*>(ctx->dMctf + offDesc);
+  MctfLevelParams p;
+  p.maxv = (1 << bitDepth) - 1;
+  // motionEstimationLuma(mv_0, origSubsampled4, bufferSub4, 16)                      (:461)
+  p.org = d + (size_t) 4 * nPairs;  p.ref = d + (size_t) 5 * nPairs;  p.width = w4;  p.height = h4;
+  p.previous = nullptr;  p.prevW = p.prevH = 0;  p.factor = 1;  p.mvs = mv0;  p.mvW = lw;  p.mvH = lh;
+  VTMME_CUDA_CHECK(ctx, launch_mctf_level(p, 16, false, nPairs, ctx->stream));
+  // motionEstimationLuma(mv_1, origSubsampled2, bufferSub2, 16, &mv_0, 2)             (:462)
+  p.org = d + (size_t) 2 * nPairs;  p.ref = d + (size_t) 3 * nPairs;  p.width = w2;  p.height = h2;
+  p.previous = mv0;  p.prevW = lw;  p.prevH = lh;  p.factor = 2;  p.mvs = mv1;
+  VTMME_CUDA_CHECK(ctx, launch_mctf_level(p, 16, false, nPairs, ctx->stream));
+  // motionEstimationLuma(mv_2, orgPic, buffer, 16, &mv_1, 2)                          (:463)
+  p.org = d;  p.ref = d + (size_t) nPairs;  p.width = W;  p.height = H;
+  p.previous = mv1;  p.mvs = mv2;
+  VTMME_CUDA_CHECK(ctx, launch_mctf_level(p, 16, false, nPairs, ctx->stream));
+  // motionEstimationLuma(mv, orgPic, buffer, 8, &mv_2, 1, true)                       (:465)
+  p.previous = mv2;  p.factor = 1;  p.mvs = mvF;  p.mvW = fw;  p.mvH = fh;
+  VTMME_CUDA_CHECK(ctx, launch_mctf_level(p, 8, true, nPairs, ctx->stream));
+  ctx->launches += 5;
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(mv, mvF, finBytes, cudaMemcpyDeviceToHost, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   return VTMME_OK;
 }
 

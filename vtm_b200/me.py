@@ -333,6 +333,16 @@ class MotionSearch:
         self._check(self.L.vtmme_remove_high_freq(self.ctx, C.c_void_p(d_org), C.c_void_p(d_pred), count, clip, bit_depth),
                     "vtmme_remove_high_freq")
 
+    # ---- GOP-based temporal filter ---------------------------------------------------------------------------
+    def mctf_me(self, org_ids, ref_ids, width, height, bit_depth=10):
+        """EncTemporalFilter::motionEstimation for every (original, reference) pair of uploaded pictures.
+        Returns int32 [nPairs, height/4, width/4, 3] = {x, y, error}, x / y in 1/16 sample."""
+        n = len(org_ids)
+        out = np.zeros((n, height // 4, width // 4, 3), np.int32)
+        self._check(self.L.vtmme_mctf_me(self.ctx, n, (C.c_int32 * n)(*org_ids), (C.c_int32 * n)(*ref_ids), bit_depth,
+                                         C.c_void_p(out.ctypes.data)), "vtmme_mctf_me")
+        return out
+
     # ---- candidate distortion (AMVP template cost / ME seeds) ----------------------------------------------
     def cand_sad(self, jobs, bit_depth=10, use_alt_hpel=0):
         """jobs: list of dicts {curPic, refPic, x, y, w, h, mv: [(mvX, mvY), ...] in 1/16 sample, subShift=0, org=None}
