@@ -969,7 +969,8 @@ extern "C" int vtmme_mctf_me(vtmme_ctx* ctx, int nPairs, const int32_t* orgPics,
   const int    lw = W / 16, lh = H / 16, fw = W / 4, fh = H / 4;
   const size_t offDesc = 0, offPlanes = align256(pics.size() * sizeof(DevPic));
   const size_t offMv = offPlanes + (size_t) nPairs * 2 * (plane2 + plane4);
-  const size_t lowBytes = align256((size_t) nPairs * lw * lh * sizeof(int3)), finBytes = (size_t) nPairs * fw * fh * sizeof(int3);
+  // (the four vector fields are contiguous, unpadded: one kernel initialises them as a single int3 array)
+  const size_t lowBytes = (size_t) nPairs * lw * lh * sizeof(int3), finBytes = (size_t) nPairs * fw * fh * sizeof(int3);
   const size_t total = offMv + 3 * lowBytes + finBytes;
   int rc;
   if ((rc = ensure(ctx, ctx->dMctf, ctx->mctfCap, total)) != VTMME_OK) return rc;
