@@ -27,11 +27,12 @@ constexpr int kPlaneElems = kPatchW * kPlaneStride;   // rows [-4, ch+4) x cols 
 
 struct __align__(16) ItemSmem
 {
-  int32_t  plane[3][kPlaneElems];   // 14-bit horizontal intermediates, widened
+  uint32_t plane[3][kPlaneElems];   // 14-bit horizontal intermediates as VERTICAL pairs: word (r, c) = rows r (low half)
+                                    // and r + 1 (high half) of column c — the operand layout of the 2-way dot product
   int16_t  org[kChunk * kChunk];
   uint16_t patch[kPatchW * kPatchW];
   uint32_t acc[12];
-  int32_t  cf[4][8];                // luma filter taps of the four quarter-pel phases
+  uint32_t cfp[4][2];               // luma filter taps of the four quarter-pel phases, four signed bytes per word
 };
 
 struct ItemGeom
@@ -92,7 +93,12 @@ __device__ __forceinline__ void item_stage(ItemSmem& sm, const int16_t* __restri
   const int hr   = max(2, 14 - bitDepth);
   const int maxv = (1 << bitDepth) - 1;
   if (lane < 12) sm.acc[lane] = 0;
-  sm.cf[lane >> 3][lane & 7] = c_lumaFilter[(lane >> 3) * 4][lane & 7];
+  if (lane < 8)
+  {
+    const int16_t* cfs = c_lumaFilter[(lane >> 1) * 4] + (lane & 1) * 4;
+    sm.cfp[lane >> 1][lane & 1] = (uint32_t) (cfs[0] & 0xff) | ((uint32_t) (cfs[1] & 0xff) << 8) | ((uint32_t) (cfs[2] & 0xff) << 16) |
+                                  ((uint32_t) (cfs[3] & 0xff) << 24);
+  }
   // 1. original chunk and reference patch rows/cols [-4, +4)
 #pragma unroll
   for (int i = lane; i < cw * ch; i += 32)
@@ -108,47 +114,100 @@ __device__ __forceinline__ void item_stage(ItemSmem& sm, const int16_t* __restri
   }
   __syncwarp();
   // 2. horizontal pass: lane r filters patch row r (picture row r-4) once for the three planes
-  //    dqx = cqx + (p-1)*step: plane[p][r][c], 14-bit intermediates (filter<8,false,true,false> / filterCopy<true,false>)
-  if (lane < ch + 8)
+  //    dqx = cqx + (p-1)*step, 14-bit intermediates (filter<8,false,true,false> / filterCopy<true,false>).  The eight
+  //    taps of an output are four 2-way dot products (IDP.2A: two 16-bit samples x two 8-bit taps) on sample pairs —
+  //    the even pairs are the row's own words, the odd pairs one funnel shift each.  A lane packs its row with the next
+  //    lane's into vertical pairs for the second pass.
   {
-    int s[pw];
-    const uint16_t* prow = sm.patch + lane * kPatchW;
+    const int       rowl = min(lane, ch + 7);
+    const uint32_t* prow = reinterpret_cast<const uint32_t*>(sm.patch + rowl * kPatchW);
+    uint32_t        w[pw / 2], o[pw / 2];
 #pragma unroll
-    for (int i = 0; i < pw; i += 2)
-    {
-      const uint32_t w = *reinterpret_cast<const uint32_t*>(prow + i);
-      s[i]     = (int) (w & 0xffffu);
-      s[i + 1] = (int) (w >> 16);
-    }
+    for (int j = 0; j < pw / 2; j++) w[j] = prow[j];
+#pragma unroll
+    for (int j = 0; j < pw / 2 - 1; j++) o[j] = __funnelshift_r(w[j], w[j + 1], 16);
+    o[pw / 2 - 1] = 0;
 #pragma unroll
     for (int p = 0; p < 3; p++)
     {
       const int dq = cqx + (p - 1) * step;
       const int ix = dq >> 2, px = dq & 3;   // ix in {-1, 0}
-      int32_t*  dst = sm.plane[p] + lane * kPlaneStride;
+      int       v[cw];
       if (px == 0)
       {
 #pragma unroll
         for (int c = 0; c < cw; c++)
         {
-          const int v0 = ix ? s[c + 3] : s[c + 4];
-          dst[c]       = (v0 << hr) - 8192;
+          const int s3 = (int) ((w[(c + 3) >> 1] >> (16 * ((c + 3) & 1))) & 0xffffu);
+          const int s4 = (int) ((w[(c + 4) >> 1] >> (16 * ((c + 4) & 1))) & 0xffffu);
+          v[c]         = ((ix ? s3 : s4) << hr) - 8192;
         }
       }
       else
       {
-        int cf[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) cf[k] = sm.cf[px][k];
+        const int cA = (int) sm.cfp[px][0], cB = (int) sm.cfp[px][1];
         const int shift = 6 - hr, off = 8192 << shift;
-#pragma unroll
-        for (int c = 0; c < cw; c++)
+        if (ix)
         {
-          int sum = 0;
+          // taps at samples c .. c+7: pairs starting at c (even c: own words, odd c: shifted words)
 #pragma unroll
-          for (int k = 0; k < 8; k++) sum += (ix ? s[c + k] : s[c + k + 1]) * cf[k];
-          dst[c] = (sum - off) >> shift;
+          for (int c = 0; c < cw; c++)
+          {
+            int sum = 0;
+            if ((c & 1) == 0)
+            {
+              sum = __dp2a_lo((int) w[c / 2], cA, sum);
+              sum = __dp2a_hi((int) w[c / 2 + 1], cA, sum);
+              sum = __dp2a_lo((int) w[c / 2 + 2], cB, sum);
+              sum = __dp2a_hi((int) w[c / 2 + 3], cB, sum);
+            }
+            else
+            {
+              sum = __dp2a_lo((int) o[c / 2], cA, sum);
+              sum = __dp2a_hi((int) o[c / 2 + 1], cA, sum);
+              sum = __dp2a_lo((int) o[c / 2 + 2], cB, sum);
+              sum = __dp2a_hi((int) o[c / 2 + 3], cB, sum);
+            }
+            v[c] = (sum - off) >> shift;
+          }
         }
+        else
+        {
+          // taps at samples c+1 .. c+8
+#pragma unroll
+          for (int c = 0; c < cw; c++)
+          {
+            int sum = 0;
+            if ((c & 1) == 1)
+            {
+              sum = __dp2a_lo((int) w[(c + 1) / 2], cA, sum);
+              sum = __dp2a_hi((int) w[(c + 1) / 2 + 1], cA, sum);
+              sum = __dp2a_lo((int) w[(c + 1) / 2 + 2], cB, sum);
+              sum = __dp2a_hi((int) w[(c + 1) / 2 + 3], cB, sum);
+            }
+            else
+            {
+              sum = __dp2a_lo((int) o[c / 2], cA, sum);
+              sum = __dp2a_hi((int) o[c / 2 + 1], cA, sum);
+              sum = __dp2a_lo((int) o[c / 2 + 2], cB, sum);
+              sum = __dp2a_hi((int) o[c / 2 + 3], cB, sum);
+            }
+            v[c] = (sum - off) >> shift;
+          }
+        }
+      }
+      uint32_t* dst = sm.plane[p] + rowl * kPlaneStride;
+#pragma unroll
+      for (int c = 0; c < cw; c += 4)
+      {
+        uint32_t q[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+          const int nxt = __shfl_down_sync(0xffffffffu, v[c + i], 1);
+          q[i]          = ((uint32_t) v[c + i] & 0xffffu) | ((uint32_t) nxt << 16);
+        }
+        if (lane < ch + 7) *reinterpret_cast<uint4*>(dst + c) = make_uint4(q[0], q[1], q[2], q[3]);
       }
     }
   }
@@ -166,33 +225,38 @@ __device__ __forceinline__ void item_stage(ItemSmem& sm, const int16_t* __restri
     const int  dqy = cqy + tab[c][1] * step;
     const int  iy = dqy >> 2, py = dqy & 3;
     const int  y = ty + lit;
-    const int32_t* pp = sm.plane[tab[c][0] + 1] + (y + iy + 4) * kPlaneStride + tx;
+    const uint32_t* pp = sm.plane[tab[c][0] + 1] + (y + iy + 4) * kPlaneStride + tx;   // pair row r: picture rows r-4, r-3
     int d[8];
     if (py == 0)
     {
-      const int4 a = *reinterpret_cast<const int4*>(pp), b = *reinterpret_cast<const int4*>(pp + 4);
-      const int  s[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+      const uint4    a = *reinterpret_cast<const uint4*>(pp), b = *reinterpret_cast<const uint4*>(pp + 4);
+      const uint32_t s[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
 #pragma unroll
       for (int i = 0; i < 8; i++)
       {
-        const int v = (s[i] + 8192 + (1 << (hr - 1))) >> hr;
+        const int v = ((int) (short) (s[i] & 0xffffu) + 8192 + (1 << (hr - 1))) >> hr;
         d[i]        = min(max(v, 0), maxv);
       }
     }
     else
     {
-      const int32_t* cfp = sm.cf[py];
-      int            sum[8];
+      // taps 0..7 at picture rows y+iy-3 .. y+iy+4 = pair rows (y+iy+1), +2, +4, +6: four 2-way dot products per sample
+      const int cA = (int) sm.cfp[py][0], cB = (int) sm.cfp[py][1];
+      int       sum[8];
 #pragma unroll
-      for (int i = 0; i < 8; i++) sum[i] = 0;
-#pragma unroll
-      for (int k = 0; k < 8; k++)
+      for (int m = 0; m < 4; m++)
       {
-        const int32_t* row = pp + (k - 3) * kPlaneStride;
-        const int4     a = *reinterpret_cast<const int4*>(row), b = *reinterpret_cast<const int4*>(row + 4);
-        const int      cf = cfp[k];
-        sum[0] += a.x * cf; sum[1] += a.y * cf; sum[2] += a.z * cf; sum[3] += a.w * cf;
-        sum[4] += b.x * cf; sum[5] += b.y * cf; sum[6] += b.z * cf; sum[7] += b.w * cf;
+        const uint32_t* row = pp + (2 * m - 3) * kPlaneStride;
+        const uint4     a = *reinterpret_cast<const uint4*>(row), b = *reinterpret_cast<const uint4*>(row + 4);
+        const uint32_t  s[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+        {
+          if (m == 0) sum[i] = __dp2a_lo((int) s[i], cA, 0);
+          else if (m == 1) sum[i] = __dp2a_hi((int) s[i], cA, sum[i]);
+          else if (m == 2) sum[i] = __dp2a_lo((int) s[i], cB, sum[i]);
+          else sum[i] = __dp2a_hi((int) s[i], cB, sum[i]);
+        }
       }
       const int shift = 6 + hr, offset = (1 << (shift - 1)) + (8192 << 6);
 #pragma unroll
