@@ -295,6 +295,13 @@ int vtmme_cand_sad(vtmme_ctx* ctx, int bitDepth, int useAltHpel, int nJobs, cons
  * sample, row stride width/4 entries) exactly as TemporalFilterSourcePicInfo::mvs is filled (:205): block (bx, by) of
  * the 8x8 level at entry (bx, by), entries no block writes {0, 0, INT32_MAX}.  Synchronous. */
 int vtmme_mctf_me(vtmme_ctx* ctx, int nPairs, const int32_t* orgPics, const int32_t* refPics, int bitDepth, int32_t* mv);
+/* EncTemporalFilter::applyMotion (EncTemporalFilter.cpp:470-552) for one component: the uploaded plane srcPic
+ * (luma, or a chroma plane uploaded as a picture of its own with csx / csy = 1 for 4:2:0) motion-compensated block
+ * by block — (8 >> csx) x (8 >> csy) samples per luma 8x8 block — with the vectors of vtmme_mctf_me (HOST, mvStride
+ * entries per row).  dst: HOST, plane width x height samples, packed; samples outside whole blocks are returned 0
+ * (the reference leaves them unwritten).  Synchronous. */
+int vtmme_mctf_apply_motion(vtmme_ctx* ctx, int srcPic, int csx, int csy, const int32_t* mv, int mvStride, int mvRows,
+                            int bitDepth, int16_t* dst);
 
 /* ---- measurement helpers ------------------------------------------------------------------------
  * Per-kernel timing of the frame path: when enabled, vtmme_search_frames[_device] brackets each of its

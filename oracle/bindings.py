@@ -103,6 +103,7 @@ def oracle():
         L.vo_int_refine.argtypes = [C.POINTER(Job), C.POINTER(IntRefine)]
         L.vo_tz_search.argtypes = [C.POINTER(Job), C.POINTER(TzParams), C.POINTER(_I), C.POINTER(_I),
                                    C.POINTER(C.c_uint64), C.POINTER(_I)]
+        L.vo_mctf_apply_motion.argtypes = [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _I]
         L.vo_mctf_me.argtypes = [_P, _I, _P, _I, _I, _I, _I, _P]
         L.vo_mctf_error.argtypes = [_P, _I, _P, _I] + [_I] * 7
         L.vo_mctf_error.restype = _I
@@ -142,6 +143,7 @@ def ref():
                                     C.POINTER(C.c_uint64)]
         L.ref_tz_batch.restype = C.c_double
         L.ref_tz_batch.argtypes = [C.POINTER(Job), C.POINTER(TzParams), _I, _I, _P, _P]
+        L.ref_mctf_apply_motion.argtypes = [_P, _P, _I, _I, _I, _P, _P, _P]
         L.ref_mctf_me.restype = C.c_double
         L.ref_mctf_me.argtypes = [_P, _I, _P, _I, _I, _I, _I, _P]
         L.ref_mc_blocks.argtypes = [_I, _P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, C.POINTER(C.c_double)]

@@ -566,6 +566,51 @@ double ref_mctf_me(const int16_t* org, int orgStride, const int16_t* ref, int re
   return sec;
 }
 
+// ---- EncTemporalFilter::applyMotion (EncTemporalFilter.cpp:470-552), the reference's own member ---------------------
+// luma: lumaW x lumaH plane, chroma: (lumaW/2) x (lumaH/2) plane used for Cb and Cr (4:2:0); both without border (the
+// shim pads them like EncTemporalFilter::filter).  mv: the (lumaW/4) x (lumaH/4) field of ref_mctf_me.
+// dstY / dstC: packed outputs (row stride = component width); samples the reference does not write are zero.
+void ref_mctf_apply_motion(const int16_t* luma, const int16_t* chroma, int lumaW, int lumaH, int bitDepth, const int32_t* mv,
+                           int16_t* dstY, int16_t* dstC)
+{
+  EncTemporalFilter tf;
+  tf.m_chromaFormatIDC = CHROMA_420;
+  tf.m_sourceWidth     = lumaW;
+  tf.m_sourceHeight    = lumaH;
+  for (int i = 0; i < MAX_NUM_CHANNEL_TYPE; i++) tf.m_internalBitDepth[i] = bitDepth;
+  const int  pad = EncTemporalFilter::m_padding;
+  const Area area(0, 0, lumaW, lumaH);
+  PelStorage in, out;
+  in.create(CHROMA_420, area, 0, pad);
+  out.create(CHROMA_420, area, 0, pad);
+  for (int c = 0; c < 3; c++)
+  {
+    const int      w = c ? lumaW / 2 : lumaW, h = c ? lumaH / 2 : lumaH;
+    const int16_t* s = c ? chroma : luma;
+    for (int y = 0; y < h; y++)
+    {
+      memcpy(in.bufs[c].buf + (ptrdiff_t) y * in.bufs[c].stride, s + (ptrdiff_t) y * w, sizeof(int16_t) * w);
+      memset(out.bufs[c].buf + (ptrdiff_t) y * out.bufs[c].stride, 0, sizeof(int16_t) * w);
+    }
+  }
+  in.extendBorderPel(pad, pad);
+  Array2D<MotionVector> mvs;
+  mvs.allocate(lumaW / 4, lumaH / 4);
+  for (int y = 0; y < lumaH / 4; y++)
+    for (int x = 0; x < lumaW / 4; x++)
+    {
+      const int32_t* m = mv + 3 * ((size_t) y * (lumaW / 4) + x);
+      mvs.get(x, y).set(m[0], m[1], m[2]);
+    }
+  tf.applyMotion(mvs, in, out);
+  for (int c = 0; c < 2; c++)
+  {
+    const int w = c ? lumaW / 2 : lumaW, h = c ? lumaH / 2 : lumaH;
+    int16_t*  d = c ? dstC : dstY;
+    for (int y = 0; y < h; y++) memcpy(d + (ptrdiff_t) y * w, out.bufs[c].buf + (ptrdiff_t) y * out.bufs[c].stride, sizeof(int16_t) * w);
+  }
+}
+
 // Batch driver used as the CPU baseline: nThreads workers over disjoint job ranges.
 // Returns wall seconds spent in the searches (steady_clock around the work only).
 double ref_search_batch(const RefSearchJob* jobs, RefSearchResult* res, int n, int nThreads)

@@ -1239,3 +1239,40 @@ void vo_mctf_me(const vo_pel* org, int orgStride, const vo_pel* ref, int refStri
   free(b2.base);
   free(b4.base);
 }
+
+/* EncTemporalFilter::applyMotion — EncTemporalFilter.cpp:470-552, one component */
+void vo_mctf_apply_motion(const vo_pel* src, int srcStride, int compW, int compH, int csx, int csy, const int32_t* mv,
+                          int mvStride, int bitDepth, vo_pel* dst, int dstStride)
+{
+  const int bsx = 8 >> csx, bsy = 8 >> csy, maxv = (1 << bitDepth) - 1;
+  int       x, y, bnx, bny, bx, by, k;
+  for (y = 0, bny = 0; y + bsy <= compH; y += bsy, bny++)
+    for (x = 0, bnx = 0; x + bsx <= compW; x += bsx, bnx++)
+    {
+      const int32_t* m    = mv + 3 * ((size_t) bny * mvStride + bnx);
+      const int      dx = m[0] >> csx, dy = m[1] >> csy;
+      const int      xInt = m[0] >> (4 + csx), yInt = m[1] >> (4 + csy);
+      const int*     xf = vo_mctf_filter[dx & 0xf];
+      const int*     yf = vo_mctf_filter[dy & 0xf];
+      int            tmp[8 + 7][8];
+      for (by = 1; by < bsy + 7; by++)
+      {
+        const vo_pel* row = src + (ptrdiff_t) (y + by + yInt - 3) * srcStride;
+        for (bx = 0; bx < bsx; bx++)
+        {
+          const vo_pel* p   = row + (x + bx + xInt - 3);
+          int           sum = 0;
+          for (k = 1; k <= 6; k++) sum += xf[k] * p[k];
+          tmp[by][bx] = sum;
+        }
+      }
+      for (by = 0; by < bsy; by++)
+        for (bx = 0; bx < bsx; bx++)
+        {
+          int sum = 0;
+          for (k = 1; k <= 6; k++) sum += yf[k] * tmp[by + k][bx];
+          sum = (sum + (1 << 11)) >> 12;
+          dst[(ptrdiff_t) (y + by) * dstStride + x + bx] = (vo_pel) (sum < 0 ? 0 : (sum > maxv ? maxv : sum));
+        }
+    }
+}

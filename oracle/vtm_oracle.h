@@ -137,6 +137,12 @@ void vo_tz_search(const vo_job* j, const vo_tz_params* p, int* mvx, int* mvy, ui
  * entries no block writes keep {0, 0, INT32_MAX}. */
 void vo_mctf_me(const vo_pel* org, int orgStride, const vo_pel* ref, int refStride, int width, int height, int bitDepth,
                 int32_t* mv);
+/* EncTemporalFilter::applyMotion (EncoderLib/EncTemporalFilter.cpp:470-552) for one component: the reference frame
+ * motion-compensated block by block (8x8 luma blocks, i.e. (8>>csx) x (8>>csy) samples of the component) with the
+ * vectors of vo_mctf_me.  src: sample (0,0) of the component's plane (>= 128>>cs border samples); mv: the luma field,
+ * mvStride entries per row; dst: compW x compH samples, row stride dstStride (samples outside whole blocks untouched). */
+void vo_mctf_apply_motion(const vo_pel* src, int srcStride, int compW, int compH, int csx, int csy, const int32_t* mv,
+                          int mvStride, int bitDepth, vo_pel* dst, int dstStride);
 /* one distortion probe (motionErrorLuma): block bs x bs at (x, y), displacement (dx, dy) in 1/16 sample */
 int  vo_mctf_error(const vo_pel* org, int orgStride, const vo_pel* ref, int refStride, int x, int y, int dx, int dy, int bs,
                    int bestError, int bitDepth);

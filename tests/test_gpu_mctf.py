@@ -56,3 +56,31 @@ def test_mctf_me_golden(ms):
     ms.upload_picture(74, cur)
     ms.upload_picture(75, ref)
     assert np.array_equal(ms.mctf_me([74], [75], w, h, 10)[0], g["mv"])
+
+
+@pytest.mark.parametrize("w,h,bd", [(208, 120, 10), (100, 68, 8)])
+def test_mctf_apply_motion(ms, oracle_lib, w, h, bd):
+    """applyMotion for luma and 4:2:0 chroma with the GPU's own vectors and with random 1/16-sample vectors; a size with
+    partial blocks at the right / bottom edge."""
+    from vtm_b200.synth import make_pair
+    rng = np.random.default_rng(600 + w)
+    cur, ref, _ = make_pair(320 + w, w, h, max_global=9, max_local=14, n_rects=3, sigma=5.0, bit_depth=bd)
+    ref = np.ascontiguousarray(ref)
+    chroma = np.ascontiguousarray(rng.integers(0, 1 << bd, (h // 2, w // 2), dtype=np.int16))
+    ms.upload_picture(76, np.ascontiguousarray(cur))
+    ms.upload_picture(77, ref)
+    ms.upload_picture(78, chroma)
+    mv = ms.mctf_me([76], [77], w, h, bd)[0]
+    refp, chp = pad_plane(ref, 128), pad_plane(chroma, 64)
+    for variant in range(2):
+        if variant:
+            mv = mv.copy()
+            mv[:, :, 0] = rng.integers(-300, 301, mv.shape[:2])
+            mv[:, :, 1] = rng.integers(-300, 301, mv.shape[:2])
+        want_y, want_c = np.zeros((h, w), np.int16), np.zeros((h // 2, w // 2), np.int16)
+        oracle_lib.vo_mctf_apply_motion(B.ptr(refp, 128 * refp.shape[1] + 128), refp.shape[1], w, h, 0, 0,
+                                        C.c_void_p(mv.ctypes.data), mv.shape[1], bd, B.ptr(want_y), w)
+        oracle_lib.vo_mctf_apply_motion(B.ptr(chp, 64 * chp.shape[1] + 64), chp.shape[1], w // 2, h // 2, 1, 1,
+                                        C.c_void_p(mv.ctypes.data), mv.shape[1], bd, B.ptr(want_c), w // 2)
+        assert np.array_equal(ms.mctf_apply_motion(77, w, h, mv, 0, 0, bd), want_y), variant
+        assert np.array_equal(ms.mctf_apply_motion(78, w // 2, h // 2, mv, 1, 1, bd), want_c), variant

@@ -365,3 +365,33 @@ def test_mctf_motion_estimation(oracle_lib, ref_lib, w, h, bd):
     n_blocks = int((a[:, :, 2] != np.iinfo(np.int32).max).sum())
     assert n_blocks == ((h - 1) // 8) * ((w - 1) // 8)          # blocks with blockX + 8 < width, blockY + 8 < height
     assert (a[:, :, :2][a[:, :, 2] != np.iinfo(np.int32).max] % 16 != 0).any()   # fractional MVs occur
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("w,h,bd", [(208, 120, 10), (96, 64, 8)])
+def test_mctf_apply_motion(oracle_lib, ref_lib, w, h, bd):
+    """EncTemporalFilter::applyMotion (EncTemporalFilter.cpp:470-552), luma and 4:2:0 chroma, with the vectors of the
+    reference's own motion estimation plus random 1/16-sample vectors (every filter phase, negative vectors)."""
+    from tests.helpers import pad_plane
+    from vtm_b200.synth import make_pair
+    rng = np.random.default_rng(500 + w)
+    cur, ref, _ = make_pair(310 + w, w, h, max_global=9, max_local=14, n_rects=3, sigma=5.0, bit_depth=bd)
+    chroma = np.ascontiguousarray(rng.integers(0, 1 << bd, (h // 2, w // 2), dtype=np.int16))
+    curp, refp = pad_plane(cur, 128), pad_plane(ref, 128)
+    stride = curp.shape[1]
+    off = 128 * stride + 128
+    mv = np.zeros((h // 4, w // 4, 3), np.int32)
+    ref_lib.ref_mctf_me(B.ptr(curp, off), stride, B.ptr(refp, off), stride, w, h, bd, C.c_void_p(mv.ctypes.data))
+    for variant in range(2):
+        if variant:
+            mv[:, :, 0] = rng.integers(-300, 301, mv.shape[:2])
+            mv[:, :, 1] = rng.integers(-300, 301, mv.shape[:2])
+        want_y, want_c = np.zeros((h, w), np.int16), np.zeros((h // 2, w // 2), np.int16)
+        ref_lib.ref_mctf_apply_motion(B.ptr(np.ascontiguousarray(ref)), B.ptr(chroma), w, h, bd, C.c_void_p(mv.ctypes.data),
+                                      B.ptr(want_y), B.ptr(want_c))
+        got_y, got_c = np.zeros_like(want_y), np.zeros_like(want_c)
+        chp = pad_plane(chroma, 64)
+        oracle_lib.vo_mctf_apply_motion(B.ptr(refp, off), stride, w, h, 0, 0, C.c_void_p(mv.ctypes.data), w // 4, bd, B.ptr(got_y), w)
+        oracle_lib.vo_mctf_apply_motion(B.ptr(chp, 64 * chp.shape[1] + 64), chp.shape[1], w // 2, h // 2, 1, 1,
+                                        C.c_void_p(mv.ctypes.data), w // 4, bd, B.ptr(got_c), w // 2)
+        assert np.array_equal(got_y, want_y) and np.array_equal(got_c, want_c), variant

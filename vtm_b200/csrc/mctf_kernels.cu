@@ -43,6 +43,40 @@ __global__ void mctf_init_mv_kernel(int3* mv, int n)
   if (i < n) mv[i] = make_int3(0, 0, 0x7fffffff);   // MotionVector() (EncTemporalFilter.h:50-56)
 }
 
+// EncTemporalFilter::applyMotion (:470-552) for one component: one thread per output sample.  The two passes of the
+// reference keep exact integer sums between them, so a thread evaluates its own 6 x 6 support directly.
+__global__ void mctf_apply_motion_kernel(DevPic src, int csx, int csy, const int3* __restrict__ mv, int mvStride, int maxv,
+                                         int16_t* __restrict__ dst)
+{
+  const int bsx = 8 >> csx, bsy = 8 >> csy;
+  const int wBlk = src.width / bsx * bsx, hBlk = src.height / bsy * bsy;   // whole blocks only (:492-494)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < src.width * src.height; i += gridDim.x * blockDim.x)
+  {
+    const int y = i / src.width, x = i - y * src.width;
+    if (x >= wBlk || y >= hBlk)
+    {
+      dst[i] = 0;
+      continue;
+    }
+    const int3 m  = mv[(size_t) (y / bsy) * mvStride + x / bsx];
+    const int  dx = m.x >> csx, dy = m.y >> csy;
+    const int8_t* xf = c_mctfFilter[dx & 15];
+    const int8_t* yf = c_mctfFilter[dy & 15];
+    const int16_t* p = src.origin + (ptrdiff_t) (y + (m.y >> (4 + csy)) - 2) * src.stride + (x + (m.x >> (4 + csx)) - 2);
+    int sum = 0;
+#pragma unroll
+    for (int ky = 0; ky < 6; ky++)
+    {
+      int h = 0;
+#pragma unroll
+      for (int kx = 0; kx < 6; kx++) h += xf[kx + 1] * p[(ptrdiff_t) ky * src.stride + kx];
+      sum += yf[ky + 1] * h;
+    }
+    sum    = (sum + (1 << 11)) >> 12;
+    dst[i] = (int16_t) min(max(sum, 0), maxv);
+  }
+}
+
 constexpr int kMctfWarps = 4;
 
 template <int BS>
@@ -264,6 +298,13 @@ __global__ void __launch_bounds__(kMctfWarps * 32) mctf_level_kernel(MctfLevelPa
 cudaError_t launch_mctf_subsample(DevPic in, DevPic out, cudaStream_t st)
 {
   mctf_subsample_kernel<<<296, 256, 0, st>>>(in, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mctf_apply_motion(DevPic src, int csx, int csy, const int3* mv, int mvStride, int maxv, int16_t* dst,
+                                     cudaStream_t st)
+{
+  mctf_apply_motion_kernel<<<592, 256, 0, st>>>(src, csx, csy, mv, mvStride, maxv, dst);
   return cudaGetLastError();
 }
 

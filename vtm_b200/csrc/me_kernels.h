@@ -235,6 +235,8 @@ struct MctfLevelParams
 };
 cudaError_t launch_mctf_subsample(DevPic in, DevPic out, cudaStream_t st);
 cudaError_t launch_mctf_init_mv(int3* mv, int n, cudaStream_t st);
+cudaError_t launch_mctf_apply_motion(DevPic src, int csx, int csy, const int3* mv, int mvStride, int maxv, int16_t* dst,
+                                     cudaStream_t st);
 cudaError_t launch_mctf_level(const MctfLevelParams& p, int blockSize, bool doubleRes, int nPairs, cudaStream_t st);
 
 }   // namespace vtmme

@@ -1024,6 +1024,42 @@ extern "C" int vtmme_mctf_me(vtmme_ctx* ctx, int nPairs, const int32_t* orgPics,
   return VTMME_OK;
 }
 
+extern "C" int vtmme_mctf_apply_motion(vtmme_ctx* ctx, int srcPic, int csx, int csy, const int32_t* mv, int mvStride,
+                                       int mvRows, int bitDepth, int16_t* dst)
+{
+  if (!ctx) return VTMME_ERR_ARG;
+  if (!mv || !dst || csx < 0 || csx > 1 || csy < 0 || csy > 1 || mvStride <= 0 || mvRows <= 0 || bitDepth < 8 || bitDepth > 12)
+    return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_mctf_apply_motion", "bad argument");
+  VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  auto it = ctx->pics.find(srcPic);
+  if (it == ctx->pics.end()) return vtmme_set_error(ctx, VTMME_ERR_NOPIC, "vtmme_mctf_apply_motion", "unknown picture id");
+  int rc;
+  if ((rc = wait_picture(ctx, srcPic)) != VTMME_OK) return rc;
+  const DevPic& sp = it->second;
+  const int bsx = 8 >> csx, bsy = 8 >> csy;
+  if (sp.width / bsx > mvStride || sp.height / bsy > mvRows)
+    return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_mctf_apply_motion", "vector field smaller than the block grid");
+  // vectors are bounded by the pyramid's ranges; anything that would leave the padded plane is refused
+  const int lim = (sp.margin - 4) << 4;
+  for (int y = 0; y < sp.height / bsy; y++)
+    for (int x = 0; x < sp.width / bsx; x++)
+    {
+      const int32_t* m = mv + 3 * ((size_t) y * mvStride + x);
+      if ((m[0] >> csx) > lim || (m[0] >> csx) < -lim || (m[1] >> csy) > lim || (m[1] >> csy) < -lim)
+        return vtmme_set_error(ctx, VTMME_ERR_RANGE, "vtmme_mctf_apply_motion", "motion vector leaves the padded plane");
+    }
+  const size_t mvBytes = (size_t) mvStride * mvRows * sizeof(int3), outBytes = (size_t) sp.width * sp.height * 2;
+  if ((rc = ensure(ctx, ctx->dMctf, ctx->mctfCap, align256(mvBytes) + outBytes)) != VTMME_OK) return rc;
+  int3*    dMv  = reinterpret_cast<int3*>(ctx->dMctf);
+  int16_t* dOut = reinterpret_cast<int16_t*>(ctx->dMctf + align256(mvBytes));
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(dMv, mv, mvBytes, cudaMemcpyHostToDevice, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, launch_mctf_apply_motion(sp, csx, csy, dMv, mvStride, (1 << bitDepth) - 1, dOut, ctx->stream));
+  ctx->launches += 1;
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, dOut, outBytes, cudaMemcpyDeviceToHost, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return VTMME_OK;
+}
+
 // ---- table-level entry points -------------------------------------------------------------------------------
 extern "C" int vtmme_dist_batch(vtmme_ctx* ctx, int kind, const int16_t* dOrg, int orgStride, int64_t orgBlockStride,
                                 const int16_t* dCur, int curStride, int64_t curBlockStride, int w, int h, int subShift,

@@ -343,6 +343,16 @@ class MotionSearch:
                                          C.c_void_p(out.ctypes.data)), "vtmme_mctf_me")
         return out
 
+    def mctf_apply_motion(self, src_id, comp_w, comp_h, mv, csx=0, csy=0, bit_depth=10):
+        """EncTemporalFilter::applyMotion for one component plane (uploaded as src_id) with the luma vector field
+        `mv` (int32 [rows, cols, 3] as returned by mctf_me).  Returns int16 [comp_h, comp_w]."""
+        mv = np.ascontiguousarray(mv, dtype=np.int32)
+        out = np.zeros((comp_h, comp_w), np.int16)
+        self._check(self.L.vtmme_mctf_apply_motion(self.ctx, src_id, csx, csy, C.c_void_p(mv.ctypes.data), mv.shape[1],
+                                                   mv.shape[0], bit_depth, C.c_void_p(out.ctypes.data)),
+                    "vtmme_mctf_apply_motion")
+        return out
+
     # ---- candidate distortion (AMVP template cost / ME seeds) ----------------------------------------------
     def cand_sad(self, jobs, bit_depth=10, use_alt_hpel=0):
         """jobs: list of dicts {curPic, refPic, x, y, w, h, mv: [(mvX, mvY), ...] in 1/16 sample, subShift=0, org=None}
