@@ -22,8 +22,8 @@
  *   InterPrediction::xPredInterBlk (CommonLib/InterPrediction.cpp   vtmme_mc_batch / vtmme_mc_host
  *     :660-830), AreaBuf::addAvg (Buffer.cpp:467-507),              vtmme_add_avg
  *     AreaBuf::removeHighFreq (Buffer.h:474-517)                    vtmme_remove_high_freq
- *   EncTemporalFilter::motionEstimation (EncoderLib/                vtmme_mctf_me
- *     EncTemporalFilter.cpp:448-466)
+ *   EncTemporalFilter::motionEstimation / applyMotion (EncoderLib/  vtmme_mctf_me / vtmme_mctf_apply_motion
+ *     EncTemporalFilter.cpp:448-466, 470-552)
  *   distortion of InterSearch::xGetTemplateCost and of the ME      vtmme_cand_sad
  *     seeds (EncoderLib/InterSearch.cpp:3235-3270, 3388-3426)
  *   Picture::getRecoBuf / getOrigBuf planes handed to ME            vtmme_upload_picture / vtmme_release_picture
