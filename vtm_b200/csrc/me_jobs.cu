@@ -400,7 +400,8 @@ __global__ void __launch_bounds__(128) me_job_frac_finish_kernel(const DevJob* _
 // memory (row stride patStride): the xPatternSearchFracDIF body (fracMode 1) or xPatternSearchIntRefine (fracMode 2)
 // at the integer MV held by `key`, and the result record (`out`: mapped pinned host memory).
 __device__ __forceinline__ void job_refine_single(const DevJob& j, unsigned long long key, const int16_t* s_pat, int patStride,
-                                                  FracSmem& fsm, IntRefSmem& irs, DevJobResult* out)
+                                                  FracSmem& fsm, IntRefSmem& irs, DevJobResult* out, unsigned int* done,
+                                                  unsigned int seq)
 {
   const int    dx = key_dx(key), dy = key_dy(key);
   DevJobResult res;
@@ -441,12 +442,15 @@ __device__ __forceinline__ void job_refine_single(const DevJob& j, unsigned long
   {
     *out = res;
     __threadfence_system();
+    // the host polls this word instead of waiting for the stream: the result above is visible before it
+    if (done) *reinterpret_cast<volatile unsigned int*>(done) = seq;
   }
 }
 
 // TZ search of one small job with its refinement, one launch (the in-loop encoder's FastSearch=1 call)
 __global__ void __launch_bounds__(kTzThreads) me_job_tz_fused_kernel(const DevJob* __restrict__ jobs, const DevTz* __restrict__ tz,
-                                                                     DevJobResult* __restrict__ result)
+                                                                     DevJobResult* __restrict__ result, unsigned int* done,
+                                                                     unsigned int seq)
 {
   static_assert(kTzThreads == kFracThreads, "the refinement code is written for CTAs of kFracThreads threads");
   __shared__ TzSmem                sm;
@@ -476,7 +480,7 @@ __global__ void __launch_bounds__(kTzThreads) me_job_tz_fused_kernel(const DevJo
   c.sm        = &sm;
   const unsigned long long key = tz_search<TzEvalWarps<kTzThreads / 32>>(c, t);
   __syncthreads();
-  job_refine_single(j, key, s_pat, j.w, fsm, irs, result);
+  job_refine_single(j, key, s_pat, j.w, fsm, irs, result, done, seq);
 }
 
 // ---- single small job, one launch (the in-loop encoder's call: one PU, pattern <= 32x32) ----------------------------
@@ -599,7 +603,7 @@ __global__ void __launch_bounds__(kFusedThreads) me_job_fused_kernel(const __gri
   __syncthreads();
   const unsigned long long key = hdr->best;
   const int                dx = key_dx(key), dy = key_dy(key);
-  job_refine_single(j, key, s_pat, rw, fsm, irs, a.result);
+  job_refine_single(j, key, s_pat, rw, fsm, irs, a.result, a.done, a.seq);
 }
 
 }   // namespace
@@ -609,13 +613,16 @@ __global__ void __launch_bounds__(kFusedThreads) me_job_fused_kernel(const __gri
 cudaError_t launch_job_search_impl(const DevJob* dJobs, unsigned long long* dKeys, DevJobResult* dResults, int n,
                                    int maxRegions, int nSplit, int bandRows, int maxGx, bool anyMulti, uint32_t* dSurf,
                                    const long long* dSurfOff, uint32_t* dFracAcc, int maxFracChunks, cudaStream_t st,
-                                   int* launches, const DevTz* dTz, int maxPatternSamples)
+                                   int* launches, const DevTz* dTz, int maxPatternSamples, unsigned int* done,
+                                   unsigned int seq, bool* fusedTz)
 {
   cudaError_t e;
+  if (fusedTz) *fusedTz = false;
   if (dTz && n == 1 && maxPatternSamples <= 32 * 32 && maxRegions == 1)
   {
     // one small TZ job: search and refinement in one launch
-    me_job_tz_fused_kernel<<<1, kTzThreads, 0, st>>>(dJobs, dTz, dResults);
+    if (fusedTz) *fusedTz = true;
+    me_job_tz_fused_kernel<<<1, kTzThreads, 0, st>>>(dJobs, dTz, dResults, done, seq);
     *launches += 1;
     return cudaGetLastError();
   }

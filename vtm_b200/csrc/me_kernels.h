@@ -165,7 +165,8 @@ struct DevJobResult
 cudaError_t launch_job_search_impl(const DevJob* dJobs, unsigned long long* dKeys, DevJobResult* dResults, int n,
                                    int maxRegions, int nSplit, int bandRows, int maxGx, bool anyMulti, uint32_t* dSurf,
                                    const long long* dSurfOff, uint32_t* dFracAcc, int maxFracChunks, cudaStream_t st,
-                                   int* launches, const DevTz* dTz = nullptr, int maxPatternSamples = 0);
+                                   int* launches, const DevTz* dTz = nullptr, int maxPatternSamples = 0,
+                                   unsigned int* done = nullptr, unsigned int seq = 0, bool* fusedTz = nullptr);
 
 // One small job per launch (me_job_fused_kernel): descriptor and pattern as kernel parameters
 struct FusedJobArgs
@@ -174,6 +175,8 @@ struct FusedJobArgs
   unsigned long long* key;             // persistent slot, all-ones between calls
   DevJobResult*       result;          // mapped pinned host memory
   unsigned int*       ticket;          // zero between calls
+  unsigned int*       done;            // mapped pinned host memory: set to `seq` after the result is visible (or nullptr)
+  unsigned int        seq;
   int                 bandRows;        // window rows per CTA pass
   int                 inlinePattern;
   int16_t             pattern[32 * 32];   // row stride job.w

@@ -1,5 +1,6 @@
 // C ABI of libvtmme.so (include/vtmme.h): context, device pictures, and the orchestration of the kernels.
 // There is no CPU implementation of anything behind these entry points: a failing CUDA call is an error.
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -55,6 +56,7 @@ struct vtmme_ctx
   size_t         jobKeysCap = 0;
   uint32_t*      dJobFracAcc = nullptr;     // persistent, all-zero between calls (18 sums per job slot)
   size_t         jobFracAccCap = 0;
+  unsigned int   jobSeq = 0;                // sequence number of the polled completion word (single-launch jobs)
   unsigned char* dPinnedAlias = nullptr;    // device address of hPinned (mapped, zero-copy result write-back)
   unsigned int*  dJobTicket = nullptr;      // CTA ticket of the single-launch small-job path, zero between calls
   size_t         jobTicketCap = 0;
@@ -588,6 +590,7 @@ static int ensure_pinned(vtmme_ctx* ctx, size_t bytes)
     cudaFreeHost(p);
     return vtmme_set_error(ctx, VTMME_ERR_CUDA, "cudaHostGetDevicePointer", "mapped pinned memory unavailable");
   }
+  memset(p, 0, bytes);
   ctx->hPinned      = reinterpret_cast<unsigned char*>(p);
   ctx->dPinnedAlias = reinterpret_cast<unsigned char*>(dp);
   ctx->hPinnedCap   = bytes;
@@ -597,6 +600,32 @@ static int ensure_pinned(vtmme_ctx* ctx, size_t bytes)
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t) 255; }
 
 namespace {
+// Completion of a single-launch job: the kernel's last store is a sequence number into mapped pinned memory, which the
+// host polls — cudaStreamSynchronize costs several microseconds more per call on this platform.  VTMME_POLL=0 turns the
+// polling off; a kernel that never reports (a fault) falls back to the stream wait, which returns its error.
+const bool g_poll = !(getenv("VTMME_POLL") && getenv("VTMME_POLL")[0] == '0');
+constexpr size_t kDoneOffset = 256;   // byte offset of the completion word in the pinned block (results start at 0)
+
+inline cudaError_t wait_done(vtmme_ctx* ctx, unsigned int seq, size_t doneOffset = kDoneOffset)
+{
+  if (g_poll)
+  {
+    volatile unsigned int* f = reinterpret_cast<volatile unsigned int*>(ctx->hPinned + doneOffset);
+    for (long spins = 0; spins < (1L << 26); spins++)
+    {
+      if (*f == seq)
+      {
+        std::atomic_thread_fence(std::memory_order_acquire);
+        return cudaSuccess;
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+  }
+  return cudaStreamSynchronize(ctx->stream);
+}
+
 DevAmvr make_dev_amvr(const vtmme_job& j)
 {
   DevAmvr d;
@@ -779,13 +808,16 @@ extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_
       a.key    = ctx->dJobKeys;
       a.ticket = ctx->dJobTicket;
       a.result = reinterpret_cast<DevJobResult*>(ctx->dPinnedAlias);
+      a.seq    = ++ctx->jobSeq;
+      a.done   = g_poll ? reinterpret_cast<unsigned int*>(ctx->dPinnedAlias + kDoneOffset) : nullptr;
+      *reinterpret_cast<volatile unsigned int*>(ctx->hPinned + kDoneOffset) = 0;   // the block is shared with the batch path
       int grid = (nrows + a.bandRows - 1) / a.bandRows;
       if (grid > 4 * 148) grid = 4 * 148;
       const double tPrep = g_timing.on ? now_s() : 0;
       VTMME_CUDA_CHECK(ctx, launch_job_fused(a, grid, ctx->stream));
       ctx->launches += 1;
       const double tEnq = g_timing.on ? now_s() : 0;
-      VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+      VTMME_CUDA_CHECK(ctx, wait_done(ctx, a.seq));
       memcpy(results, ctx->hPinned, sizeof(vtmme_result));
       if (g_timing.on)
       {
@@ -812,7 +844,8 @@ extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_
   const size_t offOrg = align256(offTz + (tzCall ? (size_t) n * sizeof(DevTz) : 0));
   const size_t upBytes = offOrg + orgBytes;
   const size_t offKeys = align256(upBytes), offRes = align256(offKeys + (size_t) n * 8);
-  const size_t devBytes = offRes + (size_t) n * sizeof(DevJobResult);
+  const size_t offDone  = align256(offRes + (size_t) n * sizeof(DevJobResult));   // completion word of a single-launch TZ job
+  const size_t devBytes = offDone + 256;
   int rc;
   if ((rc = ensure_pinned(ctx, devBytes)) != VTMME_OK) return rc;
   if ((rc = ensure(ctx, ctx->dJobBuf, ctx->jobBufCap, devBytes)) != VTMME_OK) return rc;
@@ -908,7 +941,10 @@ extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_
     if ((rc = ensure(ctx, ctx->dJobFracAcc, ctx->jobFracAccCap, want / 8 * 18 * 4)) != VTMME_OK) return rc;
     VTMME_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dJobFracAcc, 0, want / 8 * 18 * 4, ctx->stream));
   }
-  int launches = 0;
+  int                launches = 0;
+  bool               fusedTz  = false;
+  const unsigned int seq      = ++ctx->jobSeq;
+  *reinterpret_cast<volatile unsigned int*>(ctx->hPinned + offDone) = 0;
   VTMME_CUDA_CHECK(ctx, launch_job_search_impl(reinterpret_cast<const DevJob*>(dIn + offJobs),
                                                ctx->dJobKeys,
                                                reinterpret_cast<DevJobResult*>(ctx->dPinnedAlias + offRes), n, maxRegions,
@@ -916,11 +952,16 @@ extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_
                                                reinterpret_cast<const long long*>(dIn + offSurfOff),
                                                ctx->dJobFracAcc, maxFracChunks, ctx->stream, &launches,
                                                tzCall ? reinterpret_cast<const DevTz*>(dIn + offTz) : nullptr,
-                                               maxPatternSamples));
+                                               maxPatternSamples,
+                                               g_poll ? reinterpret_cast<unsigned int*>(ctx->dPinnedAlias + offDone) : nullptr, seq,
+                                               &fusedTz));
   ctx->launches += launches;
   // the frac kernel wrote the results straight into the mapped pinned block: no device-to-host copy
   const double tEnq = g_timing.on ? now_s() : 0;
-  VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (fusedTz)
+    VTMME_CUDA_CHECK(ctx, wait_done(ctx, seq, offDone));
+  else
+    VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   memcpy(results, ctx->hPinned + offRes, (size_t) n * sizeof(vtmme_result));
   if (g_timing.on)
   {
