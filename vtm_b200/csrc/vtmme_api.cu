@@ -393,8 +393,6 @@ int vtmme_search_frames_device(vtmme_ctx* ctx, int nPairs, const int32_t* curPic
   {
     VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->hPairs) cudaFreeHost(ctx->hPairs);
-  cudaFree(ctx->dUpStage);
-  cudaFree(ctx->dMctf);
     ctx->hPairs    = nullptr;
     ctx->hPairsCap = 0;
     void* hp       = nullptr;
