@@ -78,3 +78,21 @@ def test_struct_layouts_match_the_header(tmp_path):
         assert int(got[cname]) == C.sizeof(cls), cname
         for f in cls._fields_:
             assert int(got["%s.%s" % (cname, f[0])]) == getattr(cls, f[0]).offset, (cname, f[0])
+
+
+def test_vtm_patch_applies(tmp_path):
+    """integration/apply_patch.py finds every anchor in the reference and inserts the hooks (needs /root/reference;
+    compiling the patched tree is __graft_entry__.build()'s job)."""
+    import subprocess
+    import sys
+    if not os.path.isdir("/root/reference/source"):
+        pytest.skip("/root/reference not present")
+    dst = tmp_path / "patched"
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "integration", "apply_patch.py"), "/root/reference", str(dst)],
+                          stdout=subprocess.DEVNULL)
+    src = open(dst / "source" / "Lib" / "EncoderLib" / "InterSearch.cpp").read()
+    for needle in ("cudaSearch( false, false, Mv() )", "cudaSearch( true, true, rcMv )", "cudaSearch( true, false, rcMv )",
+                   "if( cudaFracDone )", "if( cudaIntRefineDone )"):
+        assert src.count(needle) == 1, needle
+    assert "initRdCostCUDA();" in open(dst / "source" / "Lib" / "CommonLib" / "RdCost.cpp").read()
+    assert os.path.exists(dst / "source" / "Lib" / "CommonLib" / "cuda" / "VtmCudaME.cpp")
