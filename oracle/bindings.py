@@ -55,7 +55,7 @@ class TzParams(C.Structure):
                 ("int2Nx2NY", C.c_int), ("nSeeds", C.c_int), ("seedX", C.c_int * 16), ("seedY", C.c_int * 16),
                 ("searchRange", C.c_int), ("extended", C.c_int), ("fast", C.c_int), ("firstSearchStop", C.c_int),
                 ("posX", C.c_int), ("posY", C.c_int), ("picW", C.c_int), ("picH", C.c_int),
-                ("maxCuW", C.c_int), ("maxCuH", C.c_int)]
+                ("maxCuW", C.c_int), ("maxCuH", C.c_int), ("selective", C.c_int)]
 
 
 def build_oracle():

@@ -418,6 +418,7 @@ struct RefTzParams
   int searchRange;
   int extended, fast, firstSearchStop;
   int posX, posY, picW, picH, maxCuW, maxCuH;
+  int selective;   // xTZSearchSelective (MESEARCH_SELECTIVE) instead of xTZSearch
 };
 
 // per-thread environment of the xTZSearch calls: parameter sets and the CodingStructure shell are built once
@@ -490,7 +491,10 @@ void ref_tz_search(const RefSearchJob* j, const RefTzParams* t, int* mvx, int* m
   Mv         mv(t->startX, t->startY);
   Mv         int2Nx2N(t->int2Nx2NX, t->int2Nx2NY);
   Distortion cost = 0;
-  p.xTZSearch(pu, REF_PIC_LIST_0, 0, st, mv, cost, t->hasInt2Nx2N ? &int2Nx2N : nullptr, t->extended != 0, t->fast != 0);
+  if (t->selective)
+    p.xTZSearchSelective(pu, REF_PIC_LIST_0, 0, st, mv, cost, t->hasInt2Nx2N ? &int2Nx2N : nullptr);
+  else
+    p.xTZSearch(pu, REF_PIC_LIST_0, 0, st, mv, cost, t->hasInt2Nx2N ? &int2Nx2N : nullptr, t->extended != 0, t->fast != 0);
   p.m_uniMvList = nullptr;
   *mvx = mv.hor;
   *mvy = mv.ver;

@@ -791,11 +791,58 @@ typedef struct
   int           probes;
 } vo_tz;
 
-/* xTZSearchHelp, subShiftMode != 1 branch — InterSearch.cpp:394-416 */
+/* xTZSearchHelp, subShiftMode == 1 branch — InterSearch.cpp:340-391 (the selective search's staged SAD): the rows
+ * 0, 2^S, 2*2^S ... first, scaled up by 2^S as an estimate of the whole SAD; then the rows half-way between those
+ * already summed, stage by stage, each time testing the scaled partial sum against the best cost.  Only a probe that
+ * survives every stage (and so has its exact SAD) can become the best.  The tests are estimates: a probe whose exact
+ * cost is below the best can be rejected, so the outcome depends on the best cost at the time of the probe. */
+static void vo_tz_probe_staged(vo_tz* s, int x, int y, int pointNr, unsigned dist)
+{
+  const vo_job*  j       = s->j;
+  const vo_pel*  cur     = j->refAtPU + (ptrdiff_t) y * j->refStride + x;
+  const uint64_t bitCost = vo_mv_cost(j->lambdaMotion, vo_mv_bits(x, y, j->predQx, j->predQy, 2, j->imvShift));
+  int            sub     = s->subShift;
+  uint64_t       tmp, sad = 0;
+  if (!(bitCost < s->bestSad)) return; /* :346 */
+  s->probes++;
+  tmp = vo_sad(j->org, j->orgStride, cur, j->refStride, j->w, j->h, sub); /* = (sum over rows 0 mod 2^sub) << sub */
+  if (!(tmp + bitCost < s->bestSad)) return; /* :350 */
+  sad += tmp >> sub;
+  while (sub > 0) /* :357-371 */
+  {
+    const int isub = sub - 1;
+    tmp = vo_sad(j->org + ((ptrdiff_t) j->orgStride << isub), j->orgStride, cur + ((ptrdiff_t) j->refStride << isub), j->refStride,
+                 j->w, j->h, sub); /* distFunc walks h >> sub rows from the offset row: rows 2^isub mod 2^sub */
+    sad += tmp >> sub;
+    if ((sad << isub) + bitCost > s->bestSad) break;
+    sub--;
+  }
+  if (sub == 0)
+  {
+    sad += bitCost;
+    if (sad < s->bestSad)
+    {
+      s->bestSad      = sad;
+      s->bestX        = x;
+      s->bestY        = y;
+      s->bestDistance = dist;
+      s->bestRound    = 0;
+      s->pointNr      = pointNr;
+    }
+  }
+}
+
+/* xTZSearchHelp — InterSearch.cpp:330-417 */
 static void vo_tz_probe(vo_tz* s, int x, int y, int pointNr, unsigned dist)
 {
-  const vo_job* j   = s->j;
-  uint64_t      sad = vo_sad(j->org, j->orgStride, j->refAtPU + (ptrdiff_t) y * j->refStride + x, j->refStride, j->w, j->h, s->subShift);
+  const vo_job* j = s->j;
+  uint64_t      sad;
+  if (j->subShiftMode == 1)
+  {
+    vo_tz_probe_staged(s, x, y, pointNr, dist);
+    return;
+  }
+  sad = vo_sad(j->org, j->orgStride, j->refAtPU + (ptrdiff_t) y * j->refStride + x, j->refStride, j->w, j->h, s->subShift);
   s->probes++;
   if (sad < s->bestSad)
   {
@@ -904,6 +951,101 @@ static void vo_tz_to_int(const vo_tz_params* p, int* x, int* y)
   *y = vo_div_pow2(vo_change_prec(*y, -2), 2);
 }
 
+/* History MVs of xTZSearch (:3734-3765) and xTZSearchSelective (:4042-4074): duplicates of a newer entry are skipped;
+ * the distortion is distFunc's own (sub-sampled rows scaled up, also for subShiftMode 1); only position and cost change */
+static void vo_tz_seeds(vo_tz* s, const vo_tz_params* p)
+{
+  const vo_job* j = s->j;
+  int           i, k;
+  for (i = 0; i < p->nSeeds; i++)
+  {
+    int      x = p->seedX[i], y = p->seedY[i];
+    uint64_t sad;
+    for (k = 0; k < i; k++)
+      if (p->seedX[k] == x && p->seedY[k] == y) break;
+    if (k < i) continue;
+    vo_clip_mv(&x, &y, p->posX, p->posY, p->picW, p->picH, p->maxCuW, p->maxCuH);
+    x   = vo_change_prec(x, -4);
+    y   = vo_change_prec(y, -4);
+    sad = vo_sad(j->org, j->orgStride, j->refAtPU + (ptrdiff_t) y * j->refStride + x, j->refStride, j->w, j->h, s->subShift);
+    s->probes++;
+    sad += vo_mv_cost(j->lambdaMotion, vo_mv_bits(x, y, j->predQx, j->predQy, 2, j->imvShift));
+    if (sad < s->bestSad)
+    {
+      s->bestSad = sad;
+      s->bestX   = x;
+      s->bestY   = y;
+    }
+  }
+}
+
+/* InterSearch::xTZSearchSelective — EncoderLib/InterSearch.cpp:3979-4170 (FastSearch=2, MESEARCH_SELECTIVE; no hash ME) */
+static void vo_tz_search_selective(const vo_job* j, const vo_tz_params* p, int* mvx, int* mvy, uint64_t* sadOut, int* nProbes)
+{
+  const int range = p->searchRange, rangeInitial = p->searchRange >> 2, step = 4, distThresh = 8;
+  vo_tz     s;
+  int       sx, sy, d, x, y, bx, by, l, r, t, b;
+  memset(&s, 0, sizeof(s));
+  s.j        = j;
+  s.subShift = vo_subshift(j->subShiftMode, j->w, j->h);
+  s.bestSad  = UINT64_MAX;
+
+  sx = p->startX;
+  sy = p->startY;
+  vo_tz_to_int(p, &sx, &sy);       /* :4003-4005 */
+  vo_tz_probe(&s, sx, sy, 0, 0);   /* :4017 */
+  vo_tz_probe(&s, 0, 0, 0, 0);     /* :4020-4023, bTestZeroVector: unconditional here */
+  if (p->hasInt2Nx2N)              /* :4027-4038: no duplicate test either */
+  {
+    int ix = p->int2Nx2NX * 16, iy = p->int2Nx2NY * 16;
+    vo_tz_to_int(p, &ix, &iy);
+    vo_tz_probe(&s, ix, iy, 0, 0);
+  }
+  vo_tz_seeds(&s, p);              /* :4040-4074 */
+  /* :4076-4081 — the reference shifts the integer position by 2, not by MV_FRACTIONAL_BITS_INTERNAL, before handing it to
+   * xSetSearchRange as a 1/16-sample vector: the window is centred on a quarter of the best start point.  Restated as is. */
+  vo_set_search_range(s.bestX * 4, s.bestY * 4, p->posX, p->posY, p->picW, p->picH, p->maxCuW, p->maxCuH, range, &s.l, &s.r,
+                      &s.t, &s.b);
+
+  bx = s.bestX; /* initial search: a grid of step 4 around the best start point, each point with its two smallest diamonds, :4104-4120 */
+  by = s.bestY;
+  l  = bx - rangeInitial > s.l ? bx - rangeInitial : s.l;
+  t  = by - rangeInitial > s.t ? by - rangeInitial : s.t;
+  r  = bx + rangeInitial < s.r ? bx + rangeInitial : s.r;
+  b  = by + rangeInitial < s.b ? by + rangeInitial : s.b;
+  for (y = t; y <= b; y += step)
+    for (x = l; x <= r; x += step)
+    {
+      vo_tz_probe(&s, x, y, 0, 0);
+      vo_tz_diamond(&s, x, y, 1, 0);
+      vo_tz_diamond(&s, x, y, 2, 0);
+    }
+
+  if (abs(s.bestX - bx) > distThresh || abs(s.bestY - by) > distThresh) /* far from the predictors: full search, :4122-4134 */
+  {
+    for (y = s.t; y <= s.b; y++)
+      for (x = s.l; x <= s.r; x++) vo_tz_probe(&s, x, y, 0, 1);
+  }
+  else /* star refinement without a stop criterion, :4136-4165 */
+    while (s.bestDistance > 0)
+    {
+      sx             = s.bestX;
+      sy             = s.bestY;
+      s.bestDistance = 0;
+      s.pointNr      = 0;
+      for (d = 1; d < range + 1; d *= 2) vo_tz_diamond(&s, sx, sy, d, 0);
+      if (s.bestDistance == 1)
+      {
+        s.bestDistance = 0;
+        if (s.pointNr != 0) vo_tz_two_points(&s);
+      }
+    }
+  *mvx    = s.bestX;
+  *mvy    = s.bestY;
+  *sadOut = s.bestSad - vo_mv_cost(j->lambdaMotion, vo_mv_bits(s.bestX, s.bestY, j->predQx, j->predQy, 2, j->imvShift));
+  if (nProbes) *nProbes = s.probes;
+}
+
 /* InterSearch::xTZSearch — EncoderLib/InterSearch.cpp:3640-3974 */
 void vo_tz_search(const vo_job* j, const vo_tz_params* p, int* mvx, int* mvy, uint64_t* sadOut, int* nProbes)
 {
@@ -911,7 +1053,12 @@ void vo_tz_search(const vo_job* j, const vo_tz_params* p, int* mvx, int* mvy, ui
   const int firstRounds = 3;                             /* uiFirstSearchRounds (both settings) */
   const int range       = p->searchRange;
   vo_tz     s;
-  int       sx, sy, d, i, k, bestIsZero;
+  int       sx, sy, d, bestIsZero;
+  if (p->selective)
+  {
+    vo_tz_search_selective(j, p, mvx, mvy, sadOut, nProbes);
+    return;
+  }
   memset(&s, 0, sizeof(s));
   s.j        = j;
   s.subShift = vo_subshift(j->subShiftMode, j->w, j->h);
@@ -930,26 +1077,7 @@ void vo_tz_search(const vo_job* j, const vo_tz_params* p, int* mvx, int* mvy, ui
     if ((sx != ix || sy != iy) && (ix != s.bestX || iy != s.bestY)) vo_tz_probe(&s, ix, iy, 0, 0);
   }
 
-  for (i = 0; i < p->nSeeds; i++) /* :3734-3765: history MVs; only the position and cost are updated */
-  {
-    int      x = p->seedX[i], y = p->seedY[i];
-    uint64_t sad;
-    for (k = 0; k < i; k++)
-      if (p->seedX[k] == x && p->seedY[k] == y) break;
-    if (k < i) continue;
-    vo_clip_mv(&x, &y, p->posX, p->posY, p->picW, p->picH, p->maxCuW, p->maxCuH);
-    x   = vo_change_prec(x, -4);
-    y   = vo_change_prec(y, -4);
-    sad = vo_sad(j->org, j->orgStride, j->refAtPU + (ptrdiff_t) y * j->refStride + x, j->refStride, j->w, j->h, s.subShift);
-    s.probes++;
-    sad += vo_mv_cost(j->lambdaMotion, vo_mv_bits(x, y, j->predQx, j->predQy, 2, j->imvShift));
-    if (sad < s.bestSad)
-    {
-      s.bestSad = sad;
-      s.bestX   = x;
-      s.bestY   = y;
-    }
-  }
+  vo_tz_seeds(&s, p); /* :3734-3765 */
 
   vo_set_search_range(s.bestX * 16, s.bestY * 16, p->posX, p->posY, p->picW, p->picH, p->maxCuW, p->maxCuH,
                       range >> (p->fast ? 1 : 0), &s.l, &s.r, &s.t, &s.b); /* :3767-3772 */

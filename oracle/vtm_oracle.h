@@ -112,7 +112,7 @@ void vo_int_refine(const vo_job* j, vo_int_refine_io* io);
  * xTZ2PointSearch (:420-446) and xTZ8PointDiamondSearch (:503-705): the integer search of FastSearch=1
  * (MESEARCH_DIAMOND: extended 0, fast 0), FastSearch=3 (MESEARCH_DIAMOND_ENHANCED: extended 1) and of the cached-MV
  * re-search (fast 1, :3445).  Same field layout as RefTzParams in oracle/ref_harness.cpp.  No hash ME, no MCTS, no
- * composite reference; subShiftMode 0 or 2 (mode 1 belongs to the selective search). */
+ * composite reference; subShiftMode 0, 1 or 2. */
 typedef struct
 {
   int startX, startY;       /* rcMv on entry, 1/16 sample                                                  */
@@ -124,6 +124,9 @@ typedef struct
   int extended, fast;       /* bExtendedSettings, bFastSettings                                            */
   int firstSearchStop;      /* EncCfg::getFastMEAssumingSmootherMVEnabled                                  */
   int posX, posY, picW, picH, maxCuW, maxCuH;
+  int selective;            /* 1: xTZSearchSelective (:3979-4170, FastSearch=2) instead of xTZSearch; extended, fast and  */
+                            /*    firstSearchStop are then unused.  With vo_job.subShiftMode 1 the probes of either search */
+                            /*    use xTZSearchHelp's staged SAD (:340-391)                                                 */
 } vo_tz_params;
 /* mvx,mvy: rcMv (integer pel); sad: ruiSAD; nProbes (optional): number of xTZSearchHelp + seed distortions */
 void vo_tz_search(const vo_job* j, const vo_tz_params* p, int* mvx, int* mvy, uint64_t* sad, int* nProbes);

@@ -347,6 +347,49 @@ def test_tz_search(oracle_lib, ref_lib, extended, fast):
 
 
 @pytest.mark.ref
+@pytest.mark.parametrize("selective,fast", [(1, 0), (0, 1), (0, 0)])
+def test_tz_search_selective(oracle_lib, ref_lib, selective, fast):
+    """xTZSearchSelective (InterSearch.cpp:3979-4170, FastSearch=2) and xTZSearchHelp's staged SAD of subShiftMode 1
+    (:340-391), which the selective method also switches on for the cached-MV re-search through xTZSearch (:3438-3441):
+    the reference's own members against the restatement.  Large motion so that the full-search branch runs, small motion
+    for the star refinement; all CU shapes (sub-shifts 1-4), border positions, sub-sampling modes 1 / 0 / 2."""
+    from tests.helpers import MARGIN, pad_plane, tz_case
+    from vtm_b200.synth import make_pair
+    rng = np.random.default_rng(700 + 2 * selective + fast)
+    pic_w, pic_h = 256, 192
+    n = probes = far = 0
+    for seed in range(3):
+        cur, ref, _ = make_pair(80 + seed, pic_w, pic_h, max_global=[3, 14, 24][seed], max_local=30, n_rects=4, sigma=6.0)
+        refp = pad_plane(ref)
+        stride = refp.shape[1]
+        for w, h in [(a, b) for a in (4, 8, 16, 32, 64, 128) for b in (4, 8, 16, 32, 64, 128) if a * b > 16]:
+            for rep in range(3):
+                x = int(rng.integers(0, (pic_w - w) // 4 + 1)) * 4
+                y = int(rng.integers(0, (pic_h - h) // 4 + 1)) * 4
+                if rep == 2:
+                    x, y = [0, pic_w - w][int(rng.integers(0, 2))], [0, pic_h - h][int(rng.integers(0, 2))]
+                sr = [64, 32, 96][rep]
+                t = tz_case(rng, x, y, pic_w, pic_h, sr, 0, fast, first_stop=int(rep != 1), max_pel=20 if rep < 2 else 160)
+                t.selective = selective
+                pq = (int(rng.integers(-80, 81)), int(rng.integers(-80, 81)))
+                mode = [1, 1, 2 * selective][rep] if (selective or fast) else 1
+                j = B.make_job(cur, refp, stride, (MARGIN + y) * stride + MARGIN + x, w, h, (0, 0, 0, 0), pq,
+                               [0, 2, 0][rep], mode, 10, 1, 0, 0, 31.33 if rep else 8.5, org_off=y * pic_w + x,
+                               org_stride=pic_w)
+                a = (C.c_int(), C.c_int(), C.c_uint64(), C.c_int())
+                b = (C.c_int(), C.c_int(), C.c_uint64())
+                oracle_lib.vo_tz_search(C.byref(j), C.byref(t), *[C.byref(v) for v in a])
+                ref_lib.ref_tz_search(C.byref(j), C.byref(t), *[C.byref(v) for v in b])
+                assert [v.value for v in a[:3]] == [v.value for v in b], (w, h, rep, seed)
+                n += 1
+                probes += a[3].value
+                far += a[3].value > 2000
+    assert n > 300 and probes / n > 20
+    if selective:
+        assert far > 10          # the full-search branch ran
+
+
+@pytest.mark.ref
 @pytest.mark.parametrize("w,h,bd", [(208, 120, 10), (176, 144, 8), (96, 64, 10)])
 def test_mctf_motion_estimation(oracle_lib, ref_lib, w, h, bd):
     """EncTemporalFilter::motionEstimation (EncTemporalFilter.cpp:448-466): the reference's own member against the
