@@ -19,6 +19,7 @@
  *     (EncoderLib/InterSearch.cpp:3566-3608, 4284-4339)             vtmme_search_frames   (batched, per CTU tree)
  *   InterSearch::xPatternSearchIntRefine (:4172-4282)               vtmme_search with fracMode 2 + vtmme_amvr
  *   InterSearch::xTZSearch (:3640-3974, FastSearch=1/3)             vtmme_search with vtmme_tz
+ *   InterSearch::xTZSearchSelective (:3979-4170, FastSearch=2)      vtmme_search with vtmme_tz.selective
  *   InterPrediction::xPredInterBlk (CommonLib/InterPrediction.cpp   vtmme_mc_batch / vtmme_mc_host
  *     :660-830), AreaBuf::addAvg (Buffer.cpp:467-507),              vtmme_add_avg
  *     AreaBuf::removeHighFreq (Buffer.h:474-517)                    vtmme_remove_high_freq
@@ -104,9 +105,10 @@ typedef struct
 
 /* State of a TZ search call, InterSearch::xTZSearch (InterSearch.cpp:3640-3974): when a job carries one, its
  * integer search is the TZ search of FastSearch=1 (MESEARCH_DIAMOND: extended 0, fast 0), FastSearch=3
- * (MESEARCH_DIAMOND_ENHANCED: extended 1) or of the cached-MV re-search (:3445, fast 1) instead of the full
+ * (MESEARCH_DIAMOND_ENHANCED: extended 1), of the cached-MV re-search (:3445, fast 1) or the selective search of
+ * FastSearch=2 (xTZSearchSelective :3979-4170, selective 1) instead of the full
  * search; the job's srLeft..srBottom are ignored (xTZSearch sets its own window around the best start point).
- * No hash ME, MCTS or composite reference; subShift as RdCost::setDistParam gives it for subShiftMode 0 or 2. */
+ * No hash ME, MCTS or composite reference; subShift as RdCost::setDistParam gives it for subShiftMode 0, 1 or 2. */
 typedef struct
 {
   int32_t startX, startY;       /* rcMv on entry (the AMVP predictor, or the cached integer MV), 1/16 sample      */
@@ -120,6 +122,12 @@ typedef struct
   int32_t firstSearchStop;      /* EncCfg::getFastMEAssumingSmootherMVEnabled                                     */
   int32_t picW, picH;           /* clipMvInPic / xClipMv rectangle = size of refPic                               */
   int32_t maxCu;                /* sps.getMaxCUWidth() == getMaxCUHeight(), <= 128                                */
+  int32_t selective;            /* 1: xTZSearchSelective (:3979-4170, FastSearch=2 / MESEARCH_SELECTIVE) instead of */
+                                /*   xTZSearch; extended, fast, firstSearchStop unused; searchRange <= 128         */
+  int32_t stagedSad;            /* 1: cStruct.subShiftMode == 1 (what MESEARCH_SELECTIVE sets without               */
+                                /*   RestrictMESampling, :3438-3445): every probe is xTZSearchHelp's staged SAD     */
+                                /*   (:340-391) and the job's subShift is setDistParam's mode-1 value               */
+                                /*   (RdCost.cpp:291-309: 4 for h > 32, 3 for h 32, 2 for h 16, else 1)             */
 } vtmme_tz;
 
 typedef struct

@@ -122,6 +122,7 @@ def main():
     {
       in.tzExtended        = !tzFast && m_motionEstimationSearchMethod == MESEARCH_DIAMOND_ENHANCED;
       in.tzFast            = tzFast;
+      in.tzSelective       = !tzFast && m_motionEstimationSearchMethod == MESEARCH_SELECTIVE;   // xTZSearchSelective (FastSearch=2)
       in.tzFirstSearchStop = m_pcEncCfg->getFastMEAssumingSmootherMVEnabled();
       in.tzStartX          = tzStart.getHor();
       in.tzStartY          = tzStart.getVer();
@@ -140,11 +141,11 @@ def main():
     cudaFracDone      = in.doFrac == 1;
     cudaIntRefineDone = in.doFrac == 2;
   };
-  // the TZ search runs on the GPU for the diamond methods without hash ME / MCTS / composite reference
+  // the TZ searches (diamond, enhanced diamond, selective) run on the GPU without hash ME / MCTS / composite reference
   const bool cudaTzUsable = cudaUsable && clipMv == clipMvInPic && !m_pcEncCfg->getMCTSEncConstraint() && !m_pcEncCfg->getUseHashME()
                             && !cStruct.inCtuSearch
-                            && ( m_motionEstimationSearchMethod == MESEARCH_DIAMOND || m_motionEstimationSearchMethod == MESEARCH_DIAMOND_ENHANCED )
-                            && ( m_pcEncCfg->getRestrictMESampling() || m_pcEncCfg->getMotionEstimationSearchMethod() != MESEARCH_SELECTIVE );
+                            && ( m_motionEstimationSearchMethod == MESEARCH_DIAMOND || m_motionEstimationSearchMethod == MESEARCH_DIAMOND_ENHANCED
+                                 || ( m_motionEstimationSearchMethod == MESEARCH_SELECTIVE && m_iSearchRange <= 128 ) );
 """ + s[second:]
         s = once(s, "    xPatternSearch( cStruct, rcMv, ruiCost);\n", """\
     if( cudaUsable && ( clipMv == clipMvInPic || ( pu.cu->imv == 0 || pu.cu->imv == IMV_HPEL ) ) )

@@ -18,7 +18,7 @@ namespace
 vtmme_ctx* g_ctx        = nullptr;
 uint64_t   g_calls      = 0;
 uint64_t   g_uploads    = 0;
-uint64_t   g_tzSearches = 0;   // searches whose integer stage was xTZSearch (FastSearch=1/3)
+uint64_t   g_tzSearches = 0;   // searches whose integer stage was xTZSearch / xTZSearchSelective (FastSearch=1/2/3)
 uint64_t   g_intRefines = 0;   // searches whose xPatternSearchIntRefine ran on the GPU too
 double     g_searchSec  = 0;   // wall time spent inside vtmme_search (upload of the pattern, kernels, sync)
 int        g_nextPicId  = 1;
@@ -98,10 +98,15 @@ void search( const SearchIn& in, SearchOut& out )
   j.predQx   = in.predQx;
   j.predQy   = in.predQy;
   j.imvShift = in.imvShift;
-  // DistParam::subShift as RdCost::setDistParam derives it (RdCost.cpp:289-323); full search uses mode 0 or 2
+  // DistParam::subShift as RdCost::setDistParam derives it (RdCost.cpp:289-323); the full search uses mode 0 or 2, the
+  // TZ searches of MESEARCH_SELECTIVE mode 1 (staged SAD, InterSearch.cpp:3438-3445)
   j.subShift = 0;
   if( in.subShiftMode == 2 && in.h > 8 && in.w <= 64 ) j.subShift = 1;
-  CHECK( in.subShiftMode != 0 && in.subShiftMode != 2, "unexpected subShiftMode on the full-search path" );
+  if( in.subShiftMode == 1 )
+  {
+    j.subShift = ( in.h > 32 && ( in.h & 15 ) == 0 ) ? 4 : ( in.h > 16 && ( in.h & 7 ) == 0 ) ? 3 : ( in.h > 8 && ( in.h & 3 ) == 0 ) ? 2 : ( ( in.h & 1 ) == 0 ? 1 : 0 );
+  }
+  CHECK( in.subShiftMode != 0 && in.subShiftMode != 2 && !( in.subShiftMode == 1 && in.tzSearch ), "unexpected subShiftMode" );
   j.bitDepth     = in.bitDepth;
   j.useHad       = in.useHad;
   j.useAltHpel   = in.useAltHpel;
@@ -149,6 +154,8 @@ void search( const SearchIn& in, SearchOut& out )
     t.picW            = in.picW;
     t.picH            = in.picH;
     t.maxCu           = in.maxCuW;
+    t.selective       = in.tzSelective;
+    t.stagedSad       = in.subShiftMode == 1;
     j.tz              = &t;
     g_tzSearches++;
   }

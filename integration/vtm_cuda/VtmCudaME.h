@@ -24,7 +24,7 @@ struct SearchIn
   int            srLeft, srRight, srTop, srBottom;   // cStruct.searchRange
   int            predQx, predQy;                     // predictor, quarter-pel
   int            imvShift;
-  int            subShiftMode;  // cStruct.subShiftMode (0 or 2)
+  int            subShiftMode;  // cStruct.subShiftMode (0 or 2; 1 for the TZ searches of MESEARCH_SELECTIVE)
   int            bitDepth;
   bool           useHad, useAltHpel;
   int            doFrac;        // 0 integer search only, 1 + xPatternSearchFracDIF, 2 + xPatternSearchIntRefine (AMVR)
@@ -34,8 +34,9 @@ struct SearchIn
   uint32_t       mvpIdxBits[2], bits;
   int            picW, picH, maxCuW, maxCuH;
   double         fWeight;
-  // tzSearch: the integer search is xTZSearch (FastSearch=1/3) instead of the full search; sr* are ignored
-  bool           tzSearch, tzExtended, tzFast, tzFirstSearchStop;
+  // tzSearch: the integer search is xTZSearch (FastSearch=1/3) or xTZSearchSelective (FastSearch=2, tzSelective) instead
+  // of the full search; sr* are ignored
+  bool           tzSearch, tzExtended, tzFast, tzFirstSearchStop, tzSelective;
   int            tzStartX, tzStartY;       // rcMv on entry, MV_PRECISION_INTERNAL
   int            tzSearchRange;            // m_iSearchRange
   int            tzNumSeeds, tzSeedX[16], tzSeedY[16];   // m_uniMvList entries of (list, ref), newest first

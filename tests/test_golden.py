@@ -129,10 +129,15 @@ GA = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", 
 GA_W, GA_H = 192, 128
 
 
-def iter_tz():
+# selective search / staged SAD fixtures (tests/golden/tz_selective_golden.npz, make_golden_tz_selective.py); same pictures
+GS = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tz_selective_golden.npz"))
+
+
+def iter_tz(G=None):
     """(w, h, x, y, predQ, subShiftMode, oracle TzParams, lambda, want (mvX, mvY, sad, hx, hy, qx, qy, fracCost))"""
     from oracle import bindings as B
-    for row, lam, res in zip(GA["tz_int"], GA["tz_lambda"], GA["tz_res"]):
+    G = GA if G is None else G
+    for row, lam, res in zip(G["tz_int"], G["tz_lambda"], G["tz_res"]):
         row = [int(v) for v in row]
         w, h, x, y, pqx, pqy, ssm = row[:7]
         t = B.TzParams()
@@ -140,6 +145,7 @@ def iter_tz():
         for i in range(16):
             t.seedX[i], t.seedY[i] = row[13 + i], row[29 + i]
         t.searchRange, t.extended, t.fast, t.firstSearchStop = row[45:49]
+        t.selective = row[49] if len(row) > 49 else 0
         t.posX, t.posY, t.picW, t.picH, t.maxCuW, t.maxCuH = x, y, GA_W, GA_H, 128, 128
         yield w, h, x, y, (pqx, pqy), ssm, t, float(lam), tuple(int(v) for v in res)
 
@@ -167,13 +173,15 @@ def _ga_planes():
     return cur, refp, MARGIN
 
 
-def test_tz_golden(oracle_lib):
-    """oracle xTZSearch + fractional refinement == the reference's (60 cases: FastSearch=1, enhanced, fast re-search)"""
+@pytest.mark.parametrize("which", ["tz", "selective"])
+def test_tz_golden(oracle_lib, which):
+    """oracle xTZSearch + fractional refinement == the reference's (60 cases: FastSearch=1, enhanced, fast re-search);
+    oracle xTZSearchSelective / staged SAD + refinement == the reference's (60 cases: FastSearch=2)"""
     from oracle import bindings as B
     cur, refp, m = _ga_planes()
     stride = refp.shape[1]
     n = 0
-    for w, h, x, y, pq, ssm, t, lam, want in iter_tz():
+    for w, h, x, y, pq, ssm, t, lam, want in iter_tz(GA if which == "tz" else GS):
         j = B.make_job(cur, refp, stride, (m + y) * stride + m + x, w, h, (0, 0, 0, 0), pq, 0, ssm, 10, 1, 0, 1, lam,
                        org_off=y * GA_W + x, org_stride=GA_W)
         mx, my, sad = C.c_int(), C.c_int(), C.c_uint64()

@@ -63,6 +63,26 @@ def test_gpu_tz_golden(ms):
     assert [ms.search([j])[0] for j in jobs] == want
 
 
+def test_gpu_tz_selective_golden(ms):
+    """vtmme_search with vtmme_tz.selective / stagedSad against the reference's own xTZSearchSelective, resp. xTZSearch
+    under subShiftMode 1, + fractional refinement (committed fixtures)."""
+    from tests.test_golden import GA_H, GA_W, GS, _ga_planes, iter_tz
+    from vtm_b200 import Job, TzSearch
+    cur, refp, m = _ga_planes()
+    ms.upload_picture(60, cur)
+    ms.upload_picture(61, refp, m)
+    jobs, want = [], []
+    for w, h, x, y, pq, ssm, t, lam, res in iter_tz(GS):
+        ss = (4 if h > 32 else 3 if h > 16 else 2 if h > 8 else 1) if ssm == 1 else (1 if (ssm == 2 and h > 8 and w <= 64) else 0)
+        tz = TzSearch((t.startX, t.startY), t.searchRange, GA_W, GA_H, tuple((t.seedX[i], t.seedY[i]) for i in range(t.nSeeds)),
+                      (t.int2Nx2NX, t.int2Nx2NY) if t.hasInt2Nx2N else None, t.extended, t.fast, t.firstSearchStop, 128,
+                      t.selective, int(ssm == 1))
+        jobs.append(Job(60, 61, x, y, w, h, (0, 0, 0, 0), pq, 0, ss, 10, 1, 0, 1, lam, None, None, tz))
+        want.append(res)
+    assert ms.search(jobs) == want
+    assert [ms.search([j])[0] for j in jobs] == want
+
+
 def test_gpu_amvr_golden(ms):
     """vtmme_search fracMode 2 against the reference's own xPatternSearch + xPatternSearchIntRefine (committed fixtures)."""
     from tests.test_golden import GA_H, GA_W, _ga_planes, iter_amvr

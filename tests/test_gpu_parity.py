@@ -270,6 +270,61 @@ def test_job_tz_search(ms, oracle_lib, extended, fast):
     assert got1 == want[::7]
 
 
+@pytest.mark.parametrize("selective,fast", [(1, 0), (0, 1), (0, 0)])
+def test_tz_selective_jobs(ms, oracle_lib, selective, fast):
+    """vtmme_search with vtmme_tz.selective / stagedSad: xTZSearchSelective (InterSearch.cpp:3979-4170, FastSearch=2) and
+    the staged SAD of subShiftMode 1 (xTZSearchHelp :340-391; also what the cached-MV re-search through xTZSearch uses
+    under FastSearch=2) followed by the fractional refinement, against the oracle (pinned on the reference's own
+    members): all shapes (sub-shifts 1-4), border positions, far motion (the exhaustive branch) and near motion (star
+    refinement), history seeds, sub-sampling modes 1 / 2 / 0."""
+    from tests.helpers import tz_case
+    from vtm_b200 import Job, TzSearch
+    from vtm_b200.synth import make_pair
+    rng = np.random.default_rng(800 + 2 * selective + fast)
+    W, H = 256, 192
+    jobs, want = [], []
+    for seed in range(2):
+        cur, ref, _ = make_pair(90 + seed, W, H, max_global=[3, 24][seed], max_local=30, n_rects=4, sigma=6.0)
+        refp = pad_plane(ref)
+        ms.upload_picture(40 + 2 * seed, cur)
+        ms.upload_picture(41 + 2 * seed, refp, MARGIN)
+        stride = refp.shape[1]
+        for w in SIZES:
+            for h in SIZES:
+                if w == 4 and h == 4:
+                    continue
+                for rep in range(3):
+                    x = int(rng.integers(0, (W - w) // 4 + 1)) * 4
+                    y = int(rng.integers(0, (H - h) // 4 + 1)) * 4
+                    if rep == 2:
+                        x, y = [0, W - w][int(rng.integers(0, 2))], [0, H - h][int(rng.integers(0, 2))]
+                    sr = [64, 32, 96][rep]
+                    t = tz_case(rng, x, y, W, H, sr, 0, fast, first_stop=int(rep != 1), max_pel=20 if rep < 2 else 160)
+                    t.selective = selective
+                    pq = (int(rng.integers(-80, 81)), int(rng.integers(-80, 81)))
+                    ssm = [1, 1, 2 * selective][rep] if (selective or fast) else 1
+                    ss = oracle_lib.vo_subshift(ssm, w, h)
+                    lam = 31.33 if rep else 8.5
+                    tz = TzSearch((t.startX, t.startY), sr, W, H, tuple((t.seedX[i], t.seedY[i]) for i in range(t.nSeeds)),
+                                  (t.int2Nx2NX, t.int2Nx2NY) if t.hasInt2Nx2N else None, 0, fast, t.firstSearchStop, 128,
+                                  selective, int(ssm == 1))
+                    jobs.append(Job(40 + 2 * seed, 41 + 2 * seed, x, y, w, h, (0, 0, 0, 0), pq, 0, ss, 10, 1, 0, 1, lam, None,
+                                    None, tz))
+                    oj = B.make_job(cur, refp, stride, (MARGIN + y) * stride + MARGIN + x, w, h, (0, 0, 0, 0), pq, 0, ssm, 10,
+                                    1, 0, 1, lam, org_off=y * W + x, org_stride=W)
+                    mx, my, sad = C.c_int(), C.c_int(), C.c_uint64()
+                    oracle_lib.vo_tz_search(C.byref(oj), C.byref(t), C.byref(mx), C.byref(my), C.byref(sad), None)
+                    hx, hy, qx, qy, cost = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_uint64()
+                    oracle_lib.vo_frac_direct(C.byref(oj), mx.value, my.value, C.byref(hx), C.byref(hy), C.byref(qx),
+                                              C.byref(qy), C.byref(cost))
+                    want.append((mx.value, my.value, sad.value, hx.value, hy.value, qx.value, qy.value, cost.value))
+    got = ms.search(jobs)
+    bad = [(i, jobs[i].w, jobs[i].h, got[i], want[i]) for i in range(len(jobs)) if got[i] != want[i]]
+    assert not bad, "%d of %d jobs differ, first: %s" % (len(bad), len(jobs), bad[:3])
+    got1 = [ms.search([j])[0] for j in jobs[::11]]     # the single-launch path
+    assert got1 == want[::11]
+
+
 @pytest.mark.parametrize("fast_search,ssm,spread", [(1, 0, 0), (1, 2, 9), (3, 0, 9), (3, 2, 0)])
 def test_frame_tz_search(ms, oracle_lib, fast_search, ssm, spread):
     """vtmme_search_frames with fastSearch 1 / 3: every CU's integer search is xTZSearch started at its predictor."""

@@ -220,7 +220,9 @@ __global__ void __launch_bounds__(kTzThreads) me_job_tz_kernel(const DevJob* __r
   c.imvShift  = j.imvShift;
   c.lambda    = j.lambda;
   c.sm        = &sm;
-  const unsigned long long key = tz_search<TzEvalWarps<kTzThreads / 32>>(c, t);
+  c.staged    = t.staged;
+  const unsigned long long key = t.selective ? tz_search_selective<TzEvalWarps<kTzThreads / 32>>(c, t)
+                                             : tz_search<TzEvalWarps<kTzThreads / 32>>(c, t);
   if (threadIdx.x == 0) keys[blockIdx.x] = key;
 }
 
@@ -478,7 +480,9 @@ __global__ void __launch_bounds__(kTzThreads) me_job_tz_fused_kernel(const DevJo
   c.imvShift  = j.imvShift;
   c.lambda    = j.lambda;
   c.sm        = &sm;
-  const unsigned long long key = tz_search<TzEvalWarps<kTzThreads / 32>>(c, t);
+  c.staged    = t.staged;
+  const unsigned long long key = t.selective ? tz_search_selective<TzEvalWarps<kTzThreads / 32>>(c, t)
+                                             : tz_search<TzEvalWarps<kTzThreads / 32>>(c, t);
   __syncthreads();
   job_refine_single(j, key, s_pat, j.w, fsm, irs, result, done, seq);
 }

@@ -135,6 +135,8 @@ struct DevTz
   int searchRange;
   int extended, fast, firstSearchStop;
   int posX, posY, picW, picH, maxCuW, maxCuH;
+  int selective;   // xTZSearchSelective instead of xTZSearch
+  int staged;      // cStruct.subShiftMode == 1: the probes use xTZSearchHelp's staged SAD
 };
 
 // Generic per-call jobs (vtmme_search)

@@ -32,6 +32,7 @@ struct TzState
 struct TzSmem
 {
   unsigned long long key;
+  uint32_t           gate[kTzChunk], full[kTzChunk];   // staged probes of a batch: acceptance threshold, exact cost
 };
 
 // SAD of the pattern (row stride patStride, 8-byte aligned rows) against the reference block at `cur`, rows r with
@@ -85,6 +86,7 @@ struct TzCtx
   int            predQx, predQy, imvShift;
   double         lambda;
   TzSmem*        sm;
+  int            staged;    // cStruct.subShiftMode == 1: xTZSearchHelp's staged SAD (tz_eval_staged)
 };
 
 template <class CTX>
@@ -132,13 +134,118 @@ __device__ __forceinline__ int tz_eval(const TzCtx& c, int n, uint32_t best, uin
   return (k != ~0ull && costOut < best) ? (int) (uint32_t) k : -1;
 }
 
+// Row sums of |pattern - block| binned by the stage of xTZSearchHelp's staged SAD (subShiftMode 1, :340-391) that reads the
+// row: with S = subShift, stage 0 holds the rows 0 mod 2^S, stage k >= 1 the rows 2^(S-k) mod 2^(S-k+1).  One warp; the
+// sums are returned in every lane.
+__device__ __forceinline__ void tz_warp_sad_stages(const int16_t* pat, int patStride, int w, int h, const int16_t* cur,
+                                                   int refStride, int S, uint32_t (&sum)[5])
+{
+  const int lane = threadIdx.x & 31;
+  const int q = w >> 2, units = q * h;
+#pragma unroll
+  for (int k = 0; k < 5; k++) sum[k] = 0;
+  for (int u = lane; u < units; u += 32)
+  {
+    const int      r = u / q, c = (u % q) << 2;
+    const int      low   = r & ((1 << S) - 1);
+    const int      stage = low == 0 ? 0 : S - (__ffs(low) - 1);
+    const uint2    o = *reinterpret_cast<const uint2*>(pat + r * patStride + c);
+    const int16_t* p = cur + (ptrdiff_t) r * refStride + c;
+    uint32_t       v = 0;
+    v = __sad((int) (short) (o.x & 0xffffu), (int) p[0], v);
+    v = __sad((int) o.x >> 16, (int) p[1], v);
+    v = __sad((int) (short) (o.y & 0xffffu), (int) p[2], v);
+    v = __sad((int) o.y >> 16, (int) p[3], v);
+#pragma unroll
+    for (int k = 0; k < 5; k++) sum[k] += stage == k ? v : 0u;
+  }
+#pragma unroll
+  for (int k = 0; k < 5; k++)
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) sum[k] += __shfl_xor_sync(0xffffffffu, sum[k], m);
+}
+
+// A batch of probes under the staged SAD of subShiftMode 1.  The reference accepts a probe only if the scaled-up partial
+// sums of every stage pass against the best cost of that moment: (R0 << S) + bits < best, then ((R0 + .. + Rk) << (S-k))
+// + bits <= best for the stages in between, and the exact cost F < best at the end.  These are estimates, so a probe is
+// not characterised by its cost alone but by the pair (gate, F): it is accepted iff best > gate, gate = max(first
+// estimate, the later ones - 1, F), and then best becomes F.  Gates and costs of the batch are computed in parallel —
+// a probe whose first estimate already fails against the best cost at the start of the batch (the best only falls) stops
+// there, which is the selective search's own saving — and one thread replays the sequential acceptance over them.
+template <int WARPS, class PointFn>
+__device__ __forceinline__ int tz_eval_staged(const TzCtx& c, int n, uint32_t best, uint32_t& costOut, PointFn point)
+{
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = c.subShift;
+  __syncthreads();   // the previous batch's key has been read by everybody
+  for (int i = warp; i < n; i += WARPS)
+  {
+    int x, y;
+    point(i, x, y);
+    const int16_t* cur  = c.refAtPU + (ptrdiff_t) y * c.refStride + x;
+    const uint32_t bits = mv_cost(c.lambda, mv_bits_q(x * 4, y * 4, c.predQx, c.predQy, c.imvShift));
+    uint32_t       gate = 0xffffffffu, full = 0xffffffffu;
+    const uint32_t e0   = tz_warp_sad(c.pat, c.patStride, c.w, c.h, cur, c.refStride, S) + bits;   // (R0 << S) + bits
+    if (e0 < best)
+    {
+      uint32_t r[5];
+      tz_warp_sad_stages(c.pat, c.patStride, c.w, c.h, cur, c.refStride, S, r);
+      uint32_t part = r[0];
+      gate          = e0;
+      for (int k = 1; k <= S; k++)
+      {
+        part += r[k];
+        const uint32_t e = (part << (S - k)) + bits;
+        if (k == S)
+          full = e;
+        else if (e > 0 && e - 1 > gate)
+          gate = e - 1;
+      }
+      if (S == 0) full = e0;
+      if (full > gate) gate = full;
+    }
+    if (lane == 0)
+    {
+      c.sm->gate[i] = gate;
+      c.sm->full[i] = full;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    uint32_t b = best, win = 0xffffffffu;
+    for (int i = 0; i < n; i++)
+    {
+      const uint32_t g = c.sm->gate[i];
+      if (b > g)
+      {
+        b   = c.sm->full[i];
+        win = (uint32_t) i;
+      }
+    }
+    c.sm->key = ((unsigned long long) b << 32) | win;
+  }
+  __syncthreads();
+  const unsigned long long k = c.sm->key;
+  costOut = (uint32_t) (k >> 32);
+  return (int) (uint32_t) k;   // 0xffffffff -> -1
+}
+
 // evaluator of the generic path: WARPS warps per search, any block size, pattern and reference read from memory
 template <int WARPS>
 struct TzEvalWarps
 {
   using Ctx = TzCtx;
+  static constexpr int kBatch = kTzChunk;   // largest batch one eval call may take
   template <class PointFn>
   static __device__ __forceinline__ int eval(const Ctx& c, int n, uint32_t best, uint32_t& costOut, PointFn point)
+  {
+    if (c.staged) return tz_eval_staged<WARPS>(c, n, best, costOut, point);
+    return tz_eval<WARPS>(c, n, best, costOut, point);
+  }
+  // distFunc as it stands (sub-sampled rows scaled up), first strict minimum: the history seeds
+  template <class PointFn>
+  static __device__ __forceinline__ int eval_plain(const Ctx& c, int n, uint32_t best, uint32_t& costOut, PointFn point)
   {
     return tz_eval<WARPS>(c, n, best, costOut, point);
   }
@@ -303,6 +410,11 @@ struct TzEvalTile
     }
   }
 
+  template <class PointFn>
+  static __device__ __forceinline__ int eval_plain(const Ctx& c, int n, uint32_t best, uint32_t& costOut, PointFn point)
+  {
+    return eval(c, n, best, costOut, point);
+  }
   template <class PointFn>
   static __device__ __forceinline__ int eval(const Ctx& c, int n, uint32_t best, uint32_t& costOut, PointFn point)
   {
@@ -486,6 +598,37 @@ __device__ __forceinline__ void tz_to_int(const DevTz& t, int& x, int& y)
   y = div_pow2_round(y, 2);
 }
 
+// history MVs (xTZSearch :3734-3765, xTZSearchSelective :4040-4074): duplicates of an earlier entry are skipped; the
+// distortion is distFunc's own, also under subShiftMode 1; only position and cost are updated
+template <class EV>
+__device__ inline void tz_seeds(const typename EV::Ctx& c, const DevTz& t, TzState& s)
+{
+  if (t.nSeeds <= 0) return;
+  TzPoints  p;
+  const int horMax = (t.picW + 8 - t.posX - 1) * 16, horMin = (-t.maxCuW - 8 - t.posX + 1) * 16;
+  const int verMax = (t.picH + 8 - t.posY - 1) * 16, verMin = (-t.maxCuH - 8 - t.posY + 1) * 16;
+  p.n = 0;
+  for (int i = 0; i < t.nSeeds; i++)
+  {
+    int k = 0;
+    for (; k < i; k++)
+      if (t.seedX[k] == t.seedX[i] && t.seedY[k] == t.seedY[i]) break;
+    if (k < i) continue;
+    const int x = clampi(t.seedX[i], horMin, horMax), y = clampi(t.seedY[i], verMin, verMax);
+    p.x[p.n] = (short) (x >= 0 ? (x + 7) >> 4 : (x + 8) >> 4);   // changePrecision(INTERNAL -> INT)
+    p.y[p.n] = (short) (y >= 0 ? (y + 7) >> 4 : (y + 8) >> 4);
+    p.n++;
+  }
+  uint32_t  cost;
+  const int win = EV::eval_plain(c, p.n, s.best, cost, [&](int i, int& x, int& y) { x = p.x[i]; y = p.y[i]; });
+  if (win >= 0)
+  {
+    s.best = cost;
+    s.bx   = p.x[win];
+    s.by   = p.y[win];
+  }
+}
+
 // The whole xTZSearch.  Returns the best key (cost, position) to every thread of the cooperating warps.
 template <class EV>
 __device__ inline unsigned long long tz_search(const typename EV::Ctx& c, const DevTz& t)
@@ -527,33 +670,7 @@ __device__ inline unsigned long long tz_search(const typename EV::Ctx& c, const 
       }
     }
   }
-  if (t.nSeeds > 0)
-  {
-    // history MVs (:3734-3765): duplicates of an earlier entry are skipped; only position and cost are updated
-    TzPoints  p;
-    const int horMax = (t.picW + 8 - t.posX - 1) * 16, horMin = (-t.maxCuW - 8 - t.posX + 1) * 16;
-    const int verMax = (t.picH + 8 - t.posY - 1) * 16, verMin = (-t.maxCuH - 8 - t.posY + 1) * 16;
-    p.n = 0;
-    for (int i = 0; i < t.nSeeds; i++)
-    {
-      int k = 0;
-      for (; k < i; k++)
-        if (t.seedX[k] == t.seedX[i] && t.seedY[k] == t.seedY[i]) break;
-      if (k < i) continue;
-      const int x = clampi(t.seedX[i], horMin, horMax), y = clampi(t.seedY[i], verMin, verMax);
-      p.x[p.n] = (short) (x >= 0 ? (x + 7) >> 4 : (x + 8) >> 4);   // changePrecision(INTERNAL -> INT)
-      p.y[p.n] = (short) (y >= 0 ? (y + 7) >> 4 : (y + 8) >> 4);
-      p.n++;
-    }
-    uint32_t  cost;
-    const int win = EV::eval(c, p.n, s.best, cost, [&](int i, int& x, int& y) { x = p.x[i]; y = p.y[i]; });
-    if (win >= 0)
-    {
-      s.best = cost;
-      s.bx   = p.x[win];
-      s.by   = p.y[win];
-    }
-  }
+  tz_seeds<EV>(c, t, s);
   {
     // xSetSearchRange around the best start point (:3767-3772)
     const Window w = search_window(s.bx * 4, s.by * 4, t.posX, t.posY, t.picW, t.picH, t.maxCuW, range >> (t.fast ? 1 : 0));
@@ -613,6 +730,122 @@ __device__ inline unsigned long long tz_search(const typename EV::Ctx& c, const 
       if (s.pnr != 0) tz_two_points<EV>(c, s);
     }
   }
+  return make_key(s.best, s.bx, s.by);
+}
+
+// The whole xTZSearchSelective (:3979-4170, FastSearch=2 / MESEARCH_SELECTIVE; no hash ME).  Start points, then a grid of
+// step 4 within +-range/4 of the best start point, every grid point with its diamonds of distance 1 and 2 — 13 fixed
+// probes per grid point, one batch — then either the exhaustive scan of the window (the best moved more than 8 samples
+// away) or the star refinement without a stop criterion.
+template <class EV>
+__device__ inline unsigned long long tz_search_selective(const typename EV::Ctx& c, const DevTz& t)
+{
+  const int range = t.searchRange, rangeInitial = t.searchRange >> 2;
+  TzState   s;
+  s.best = 0xffffffffu;
+  s.bx = s.by = 0;
+  s.dist = s.round = 0;
+  s.pnr = 0;
+  s.l = s.r = s.t = s.b = 0;
+  {
+    // median predictor, zero vector, 2Nx2N integer MV: unconditional here (:4017-4038); a repeated position costs the
+    // same and cannot win again
+    TzPoints p;
+    int      sx = t.startX, sy = t.startY;
+    tz_to_int(t, sx, sy);
+    p.n = 2;
+    p.x[0] = (short) sx;
+    p.y[0] = (short) sy;
+    p.x[1] = p.y[1] = 0;
+    if (t.hasInt2Nx2N)
+    {
+      int ix = t.int2Nx2NX * 16, iy = t.int2Nx2NY * 16;
+      tz_to_int(t, ix, iy);
+      p.x[2] = (short) ix;
+      p.y[2] = (short) iy;
+      p.n    = 3;
+    }
+    for (int i = 0; i < p.n; i++)
+    {
+      p.pnr[i]  = 0;
+      p.dist[i] = 0;
+    }
+    tz_run_points<EV>(c, s, p);
+  }
+  tz_seeds<EV>(c, t, s);
+  {
+    // :4076-4081 — the reference shifts the integer position by 2 (not by MV_FRACTIONAL_BITS_INTERNAL) before
+    // xSetSearchRange reads it as a 1/16-sample vector: the window is centred on a quarter of the best start point
+    const Window w = search_window(s.bx, s.by, t.posX, t.posY, t.picW, t.picH, t.maxCuW, range);
+    s.l = w.l;
+    s.r = w.r;
+    s.t = w.t;
+    s.b = w.b;
+  }
+  const int bx0 = s.bx, by0 = s.by;
+  {
+    // initial search (:4104-4120)
+    const int l = max(bx0 - rangeInitial, s.l), r = min(bx0 + rangeInitial, s.r);
+    const int tt = max(by0 - rangeInitial, s.t), b = min(by0 + rangeInitial, s.b);
+    if (l <= r && tt <= b)
+    {
+      // probe order of one grid point: itself, xTZ8PointDiamondSearch(1) = up, left, right, down, then (2) = the eight
+      // points of tz_diamond's d <= 8 branch; packed as (dx + 2) | (dy + 2) << 3 | dist << 6
+      constexpr int kPer = 13;
+      constexpr int kGridPerBatch = EV::kBatch / kPer;
+      const int nx = (r - l) / 4 + 1, ny = (b - tt) / 4 + 1, nGrid = nx * ny;
+      auto      offset = [](int k, int& dx, int& dy, int& dist) {
+        const int dxs[kPer] = { 0, 0, -1, 1, 0, 0, -1, 1, -2, 2, -1, 1, 0 };
+        const int dys[kPer] = { 0, -1, 0, 0, 1, -2, -1, -1, 0, 0, 1, 1, 2 };
+        const int dst[kPer] = { 0, 1, 1, 1, 1, 2, 1, 1, 2, 2, 1, 1, 2 };
+        dx   = dxs[k];
+        dy   = dys[k];
+        dist = dst[k];
+      };
+      for (int g0 = 0; g0 < nGrid; g0 += kGridPerBatch)
+      {
+        const int m     = min(kGridPerBatch, nGrid - g0) * kPer;
+        auto      point = [&](int i, int& x, int& y) {
+          const int g = g0 + i / kPer, k = i % kPer, gy = g / nx, gx = g - gy * nx;
+          int       dx, dy, dist;
+          offset(k, dx, dy, dist);
+          const int cx = l + 4 * gx, cy = tt + 4 * gy;
+          x = cx + dx;
+          y = cy + dy;
+          // a point outside the window is not probed (tz_add's rule); here it repeats the grid point, which cannot win
+          if ((dx < 0 && x < s.l) || (dx > 0 && x > s.r) || (dy < 0 && y < s.t) || (dy > 0 && y > s.b))
+          {
+            x = cx;
+            y = cy;
+          }
+        };
+        uint32_t  cost;
+        const int win = EV::eval(c, m, s.best, cost, point);
+        if (win >= 0)
+        {
+          int x, y, dx, dy, dist;
+          point(win, x, y);
+          offset(win % kPer, dx, dy, dist);
+          tz_update(s, cost, x, y, 0, (uint32_t) dist);
+        }
+      }
+    }
+  }
+  if (abs(s.bx - bx0) > 8 || abs(s.by - by0) > 8)   // :4122-4134
+    tz_raster<EV>(c, s, s.l, s.r, s.t, s.b, 1);
+  else
+    while (s.dist > 0)   // :4136-4165
+    {
+      const int sx = s.bx, sy = s.by;
+      s.dist = 0;
+      s.pnr  = 0;
+      for (int d = 1; d < range + 1; d *= 2) tz_diamond<EV>(c, s, sx, sy, d, false);
+      if (s.dist == 1)
+      {
+        s.dist = 0;
+        if (s.pnr != 0) tz_two_points<EV>(c, s);
+      }
+    }
   return make_key(s.best, s.bx, s.by);
 }
 

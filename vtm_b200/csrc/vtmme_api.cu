@@ -597,6 +597,9 @@ static int ensure_pinned(vtmme_ctx* ctx, size_t bytes)
 
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t) 255; }
 
+// DistParam::subShift of subShiftMode 1 (RdCost.cpp:291-309) for a power-of-two height
+static inline int mode1_subshift(int h) { return h > 32 ? 4 : (h > 16 ? 3 : (h > 8 ? 2 : 1)); }
+
 namespace {
 // Completion of a single-launch job: the kernel's last store is a sequence number into mapped pinned memory, which the
 // host polls — cudaStreamSynchronize costs several microseconds more per call on this platform.  VTMME_POLL=0 turns the
@@ -704,6 +707,11 @@ extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_
       if (t.picW != rp.width || t.picH != rp.height || t.maxCu < 1 || t.maxCu > 128 || t.nSeeds < 0 || t.nSeeds > 15 ||
           t.searchRange < 1 || t.searchRange > 512)
         return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search", "invalid vtmme_tz (picture size of refPic, maxCu <= 128, <= 15 seeds, range 1..512)");
+      // the exhaustive scan of the selective search indexes its window with a 17-bit multiply-high division (tz_raster)
+      if (t.selective && t.searchRange > 128)
+        return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search", "the selective TZ search takes a searchRange of at most 128");
+      if (t.stagedSad && mode1_subshift(j.h) != j.subShift)
+        return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search", "stagedSad needs the subShift of subShiftMode 1 (RdCost.cpp:291-309)");
       if (j.org) orgBytes += align256((size_t) j.w * j.h * 2);
       const int nReg = ((j.w + 31) >> 5) * ((j.h + 31) >> 5);
       if (j.fracMode && nReg > maxFracChunks) maxFracChunks = nReg;
@@ -918,6 +926,8 @@ extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_
       z.picW            = t.picW;
       z.picH            = t.picH;
       z.maxCuW = z.maxCuH = t.maxCu;
+      z.selective = t.selective != 0;
+      z.staged    = t.stagedSad != 0;
       d.l = d.r = d.t = d.b = 0;
     }
     hj[i]   = d;

@@ -35,7 +35,8 @@ class CTz(C.Structure):
     _fields_ = [("startX", C.c_int32), ("startY", C.c_int32), ("hasInt2Nx2N", C.c_int32), ("int2Nx2NX", C.c_int32),
                 ("int2Nx2NY", C.c_int32), ("nSeeds", C.c_int32), ("seedX", C.c_int32 * 16), ("seedY", C.c_int32 * 16),
                 ("searchRange", C.c_int32), ("extended", C.c_int32), ("fast", C.c_int32), ("firstSearchStop", C.c_int32),
-                ("picW", C.c_int32), ("picH", C.c_int32), ("maxCu", C.c_int32)]
+                ("picW", C.c_int32), ("picH", C.c_int32), ("maxCu", C.c_int32), ("selective", C.c_int32),
+                ("stagedSad", C.c_int32)]
 
 
 class CJob(C.Structure):

@@ -61,7 +61,8 @@ class Job:
 
 @dataclass
 class TzSearch:
-    """vtmme_tz: what xTZSearch (EncoderLib/InterSearch.cpp:3640-3974) receives; MVs in 1/16 sample."""
+    """vtmme_tz: what xTZSearch (EncoderLib/InterSearch.cpp:3640-3974) or xTZSearchSelective (:3979-4170) receives;
+    MVs in 1/16 sample."""
     start: tuple              # rcMv on entry
     searchRange: int
     picW: int
@@ -72,6 +73,8 @@ class TzSearch:
     fast: int = 0
     firstSearchStop: int = 1
     maxCu: int = 128
+    selective: int = 0        # xTZSearchSelective (:3979-4170, FastSearch=2) instead of xTZSearch
+    stagedSad: int = 0        # subShiftMode 1: xTZSearchHelp's staged SAD (:340-391); Job.subShift = the mode-1 value
 
     def c(self):
         t = CTz()
@@ -84,6 +87,7 @@ class TzSearch:
             t.seedX[i], t.seedY[i] = x, y
         t.searchRange, t.extended, t.fast, t.firstSearchStop = self.searchRange, self.extended, self.fast, self.firstSearchStop
         t.picW, t.picH, t.maxCu = self.picW, self.picH, self.maxCu
+        t.selective, t.stagedSad = self.selective, self.stagedSad
         return t
 
 
