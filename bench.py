@@ -28,8 +28,8 @@ sys.path.insert(0, ROOT)
 
 WIDTH, HEIGHT, SR, CTU, LAMBDA = 1920, 1080, 64, 128, 31.33
 # dram__bytes_read.sum + dram__bytes_write.sum of me_tree_sad_kernel from one `ncu --set full` capture of a 4-pair launch
-# (profiles/r01f_tree_sad_ncu.md: 40.1 MB + 487.7 MB), per pair
-NCU_DRAM_BYTES_PER_PAIR = (40.087040e6 + 487.701760e6) / 4
+# (profiles/r01i_tree_sad_ncu.md: 40.1 MB + 489.8 MB), per pair
+NCU_DRAM_BYTES_PER_PAIR = (40.096256e6 + 489.766656e6) / 4
 METRIC = "ME block-candidates/s (SAD+SATD), 1080p SR=64 full search + quarter-pel"
 UNIT = "block-candidates/s"
 
@@ -394,7 +394,7 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "roofline": {"bound": "int_alu", "kernel": "me_tree_sad_kernel", "achieved": achieved / 1e12,
                          "peak": peak_ops / 1e12, "unit": "Tiop/s", "frac": achieved / peak_ops, "traffic": B * NCU_DRAM_BYTES_PER_PAIR,
-                         "traffic_note": "DRAM bytes per launch scaled from the ncu capture in profiles/r01f_tree_sad_ncu.md; "
+                         "traffic_note": "DRAM bytes per launch scaled from the ncu capture in profiles/r01i_tree_sad_ncu.md; "
                                          "algorithmic bytes per launch: %d" % hbm_bytes,
                          "peak_source": "measured in this run: VABSDIFF.U32 issue rate %.1f lanes/clk/SM x %d SMs x %.0f MHz, "
                                         "fused |a-b|+c = 2 ops" % (pk["lane_instr_per_clk_per_sm"], sms, pk["sm_mhz"]),
