@@ -185,10 +185,13 @@ typedef struct
   int32_t useHad;        /* 1: SATD in the fractional stage                                         */
   int32_t fracMode;      /* 0 integer only, 1 half + quarter                                        */
   int32_t predSpread;    /* max |pred_a - pred_b| (integer pel, per component) among CUs of one CTU  */
-  int32_t subShiftMode;  /* 0: every row; 2 (FEN=1/3): CUs with H > 8 and W <= 64 use even rows only, x2 (RdCost.cpp:310-316) */
+  int32_t subShiftMode;  /* 0: every row; 2 (FEN=1/3): CUs with H > 8 and W <= 64 use even rows only, x2 (RdCost.cpp:310-316); */
+                         /*   1 (fastSearch 2 only): xTZSearchHelp's staged SAD (InterSearch.cpp:340-391), what FastSearch=2 */
+                         /*   selects without RestrictMESampling                                                          */
   double  lambdaMotion;
   int32_t fastSearch;    /* integer search, like --FastSearch: 0 full search (xPatternSearch); 1 TZ search (xTZSearch,  */
-                         /*   MESEARCH_DIAMOND) started at the predictor; 3 enhanced TZ search (MESEARCH_DIAMOND_ENHANCED) */
+                         /*   MESEARCH_DIAMOND) started at the predictor; 3 enhanced TZ search (MESEARCH_DIAMOND_ENHANCED); */
+                         /*   2 selective TZ search (xTZSearchSelective, MESEARCH_SELECTIVE; searchRange <= 128)            */
   int32_t tzFirstSearchStop; /* EncCfg::getFastMEAssumingSmootherMVEnabled (VTM default 1); fastSearch 1 / 3 only */
 } vtmme_frame_params;
 

@@ -164,6 +164,7 @@ def oracle_frame_tz(L, cur, ref_padded, margin, sr, lam, pred_q=None, fast_searc
                 t = B.TzParams()
                 t.startX, t.startY = pq[0] * 4, pq[1] * 4
                 t.searchRange, t.extended, t.fast, t.firstSearchStop = sr, int(fast_search == 3), 0, first_stop
+                t.selective = int(fast_search == 2)
                 t.posX, t.posY, t.picW, t.picH, t.maxCuW, t.maxCuH = x, y, w, h, 128, 128
                 j = B.make_job(cur, ref_padded, stride, (margin + y) * stride + margin + x, s, s, (0, 0, 0, 0), pq, 0,
                                sub_shift_mode, 10, 1, 0, 1, lam, org_off=y * w + x, org_stride=w)

@@ -215,7 +215,9 @@ def test_error_codes(ms):
         ms.search([Job(50, 50, 8, 8, 8, 8, (-2, 2, -2, 2), (0, 0), imvShift=2, fracMode=2,
                        amvr=Amvr(0, ((0, 0), (0, 0)), 1, 0, (0, 0), 3, 32, 32))])
     with pytest.raises(vtm_b200.VtmmeError, match="ARG"):
-        ms.search_frames([50], [50], FrameParams(searchRange=8, fastSearch=2))  # the selective search exists per call only
+        ms.search_frames([50], [50], FrameParams(searchRange=8, subShiftMode=1))   # the staged SAD belongs to fastSearch 2
+    with pytest.raises(vtm_b200.VtmmeError, match="ARG"):
+        ms.search_frames([50], [50], FrameParams(searchRange=200, fastSearch=2))   # selective: range <= 128
     sel = Job(50, 50, 8, 8, 8, 8, (0, 0, 0, 0), (0, 0), subShift=1, tz=TzSearch((0, 0), 16, 32, 32, selective=1, stagedSad=1))
     assert len(ms.search([sel])) == 1
     with pytest.raises(vtm_b200.VtmmeError, match="ARG"):                        # window index of the exhaustive branch

@@ -325,9 +325,11 @@ def test_tz_selective_jobs(ms, oracle_lib, selective, fast):
     assert got1 == want[::11]
 
 
-@pytest.mark.parametrize("fast_search,ssm,spread", [(1, 0, 0), (1, 2, 9), (3, 0, 9), (3, 2, 0)])
+@pytest.mark.parametrize("fast_search,ssm,spread", [(1, 0, 0), (1, 2, 9), (3, 0, 9), (3, 2, 0), (2, 1, 9), (2, 2, 0), (2, 0, 30)])
 def test_frame_tz_search(ms, oracle_lib, fast_search, ssm, spread):
-    """vtmme_search_frames with fastSearch 1 / 3: every CU's integer search is xTZSearch started at its predictor."""
+    """vtmme_search_frames with fastSearch 1 / 3: every CU's integer search is xTZSearch started at its predictor;
+    fastSearch 2: xTZSearchSelective, with the staged SAD when subShiftMode is 1 (spread 30: far predictors, so that the
+    exhaustive branch runs)."""
     from tests.helpers import oracle_frame_tz
     from vtm_b200 import FrameParams
     from vtm_b200.synth import make_pair, random_predictors

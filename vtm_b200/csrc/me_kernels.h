@@ -94,6 +94,7 @@ struct TzFrameParams
   unsigned long long* keys;
   int                 sr, ctu, imvShift, subShiftMode;
   int                 extended, firstSearchStop;
+  int                 selective;   // FastSearch=2: xTZSearchSelective; subShiftMode 1 = staged SAD
   double              lambda;
 };
 cudaError_t launch_tz_frame(const TzFrameParams& p, int nPairs, cudaStream_t st, int* launches);

@@ -1,4 +1,5 @@
-// Batched TZ search of the frame path (vtmme_search_frames with fastSearch 1 or 3): every grid-aligned square CU of
+// Batched TZ search of the frame path (vtmme_search_frames with fastSearch 1 or 3; 2 = the selective search, see
+// me_tz_frame_selective_kernel): every grid-aligned square CU of
 // every picture pair runs InterSearch::xTZSearch (EncoderLib/InterSearch.cpp:3640-3974, me_tz.cuh) from its own
 // predictor and leaves the (cost, position) key the fractional refinement (me_frac.cu) starts from — the same
 // hand-over as the full search's tree kernels.
@@ -67,6 +68,57 @@ __global__ void __launch_bounds__(128) me_tz_frame_kernel(TzFrameParams p, int l
   if (threadIdx.x == 0 || (perCta > 1 && (threadIdx.x & 31) == 0)) p.keys[(size_t) pair * nCU + cu] = key;
 }
 
+// FastSearch=2: xTZSearchSelective (InterSearch.cpp:3979-4170) per CU, one warp per search on the generic evaluator
+// (pattern read from the current picture); subShiftMode 1 = the staged SAD of xTZSearchHelp (:340-391)
+__global__ void __launch_bounds__(128) me_tz_frame_selective_kernel(TzFrameParams p, int level)
+{
+  const int size = 8 << level;
+  const int nCU  = p.g.off[5], nLevel = p.g.nx[level] * p.g.ny[level];
+  const int li = blockIdx.x * 4 + (threadIdx.x >> 5), pair = blockIdx.y;
+  if (li >= nLevel) return;
+  const int cu = p.g.off[level] + li;
+  const int x = (li % p.g.nx[level]) * size, y = (li / p.g.nx[level]) * size;
+  const DevPic cur = p.cur[pair], ref = p.ref[pair];
+  short2       pr  = make_short2(0, 0);
+  if (p.predQ) pr = p.predQ[(size_t) pair * nCU + cu];
+
+  DevTz t;
+  t.startX = pr.x * 4;
+  t.startY = pr.y * 4;
+  t.hasInt2Nx2N = 0;
+  t.int2Nx2NX = t.int2Nx2NY = 0;
+  t.nSeeds          = 0;
+  t.searchRange     = p.sr;
+  t.extended        = 0;
+  t.fast            = 0;
+  t.firstSearchStop = 0;
+  t.posX            = x;
+  t.posY            = y;
+  t.picW            = p.g.picW;
+  t.picH            = p.g.picH;
+  t.maxCuW = t.maxCuH = p.ctu;
+  t.selective       = 1;
+  t.staged          = p.subShiftMode == 1;
+
+  TzCtx c;
+  c.pat       = cur.origin + (ptrdiff_t) y * cur.stride + x;   // rows 16-byte aligned (x is a multiple of 8 samples)
+  c.patStride = cur.stride;
+  c.refAtPU   = ref.origin + (ptrdiff_t) y * ref.stride + x;
+  c.refStride = ref.stride;
+  c.w = c.h   = size;
+  // DistParam::subShift (RdCost.cpp:289-323): mode 1 by height, mode 2 for 16..64 rows
+  c.subShift  = p.subShiftMode == 1 ? (size > 32 ? 4 : (size > 16 ? 3 : (size > 8 ? 2 : 1)))
+                                    : (p.subShiftMode == 2 && size > 8 && size <= 64 ? 1 : 0);
+  c.predQx    = pr.x;
+  c.predQy    = pr.y;
+  c.imvShift  = p.imvShift;
+  c.lambda    = p.lambda;
+  c.sm        = nullptr;
+  c.staged    = t.staged;
+  const unsigned long long key = tz_search_selective<TzEvalWarps<1>>(c, t);
+  if ((threadIdx.x & 31) == 0) p.keys[(size_t) pair * nCU + cu] = key;
+}
+
 template <int SIZE, int SS>
 cudaError_t launch_level(const TzFrameParams& p, int level, int nPairs, cudaStream_t st)
 {
@@ -86,6 +138,18 @@ cudaError_t launch_tz_frame(const TzFrameParams& p, int nPairs, cudaStream_t st,
 {
   const bool  ss = p.subShiftMode == 2;
   cudaError_t e;
+  if (p.selective)
+  {
+    for (int l = 4; l >= 0; l--)
+    {
+      const int n = p.g.nx[l] * p.g.ny[l];
+      if (n == 0) continue;
+      me_tz_frame_selective_kernel<<<dim3((n + 3) / 4, nPairs, 1), 128, 0, st>>>(p, l);
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+      *launches += 1;
+    }
+    return cudaSuccess;
+  }
   if ((e = launch_level<128, 0>(p, 4, nPairs, st)) != cudaSuccess) return e;
   if ((e = ss ? launch_level<64, 1>(p, 3, nPairs, st) : launch_level<64, 0>(p, 3, nPairs, st)) != cudaSuccess) return e;
   if ((e = ss ? launch_level<32, 1>(p, 2, nPairs, st) : launch_level<32, 0>(p, 2, nPairs, st)) != cudaSuccess) return e;

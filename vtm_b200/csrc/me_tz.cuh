@@ -172,11 +172,60 @@ __device__ __forceinline__ void tz_warp_sad_stages(const int16_t* pat, int patSt
 // estimate, the later ones - 1, F), and then best becomes F.  Gates and costs of the batch are computed in parallel —
 // a probe whose first estimate already fails against the best cost at the start of the batch (the best only falls) stops
 // there, which is the selective search's own saving — and one thread replays the sequential acceptance over them.
+// gate and exact cost of one staged probe whose first estimate e0 = (R0 << S) + bits passed (one warp)
+__device__ __forceinline__ void tz_staged_gate(const TzCtx& c, const int16_t* cur, uint32_t bits, uint32_t e0, uint32_t& gate,
+                                               uint32_t& full)
+{
+  const int S = c.subShift;
+  uint32_t  r[5];
+  tz_warp_sad_stages(c.pat, c.patStride, c.w, c.h, cur, c.refStride, S, r);
+  uint32_t part = r[0];
+  gate          = e0;
+  full          = e0;   // S == 0: the first sum is the exact one
+  for (int k = 1; k <= S; k++)
+  {
+    part += r[k];
+    const uint32_t e = (part << (S - k)) + bits;
+    if (k == S)
+      full = e;
+    else if (e > 0 && e - 1 > gate)
+      gate = e - 1;
+  }
+  if (full > gate) gate = full;
+}
+
 template <int WARPS, class PointFn>
 __device__ __forceinline__ int tz_eval_staged(const TzCtx& c, int n, uint32_t best, uint32_t& costOut, PointFn point)
 {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = c.subShift;
+  if (WARPS == 1)
+  {
+    // one warp per search (batched frame search): the warp walks the probes in order against the running best cost,
+    // exactly the reference's flow
+    uint32_t b   = best;
+    int      win = -1;
+    for (int i = 0; i < n; i++)
+    {
+      int x, y;
+      point(i, x, y);
+      const int16_t* cur  = c.refAtPU + (ptrdiff_t) y * c.refStride + x;
+      const uint32_t bits = mv_cost(c.lambda, mv_bits_q(x * 4, y * 4, c.predQx, c.predQy, c.imvShift));
+      const uint32_t e0   = tz_warp_sad(c.pat, c.patStride, c.w, c.h, cur, c.refStride, S) + bits;
+      if (e0 < b)
+      {
+        uint32_t gate, full;
+        tz_staged_gate(c, cur, bits, e0, gate, full);
+        if (b > gate)
+        {
+          b   = full;
+          win = i;
+        }
+      }
+    }
+    costOut = b;
+    return win;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __syncthreads();   // the previous batch's key has been read by everybody
   for (int i = warp; i < n; i += WARPS)
   {
@@ -186,24 +235,7 @@ __device__ __forceinline__ int tz_eval_staged(const TzCtx& c, int n, uint32_t be
     const uint32_t bits = mv_cost(c.lambda, mv_bits_q(x * 4, y * 4, c.predQx, c.predQy, c.imvShift));
     uint32_t       gate = 0xffffffffu, full = 0xffffffffu;
     const uint32_t e0   = tz_warp_sad(c.pat, c.patStride, c.w, c.h, cur, c.refStride, S) + bits;   // (R0 << S) + bits
-    if (e0 < best)
-    {
-      uint32_t r[5];
-      tz_warp_sad_stages(c.pat, c.patStride, c.w, c.h, cur, c.refStride, S, r);
-      uint32_t part = r[0];
-      gate          = e0;
-      for (int k = 1; k <= S; k++)
-      {
-        part += r[k];
-        const uint32_t e = (part << (S - k)) + bits;
-        if (k == S)
-          full = e;
-        else if (e > 0 && e - 1 > gate)
-          gate = e - 1;
-      }
-      if (S == 0) full = e0;
-      if (full > gate) gate = full;
-    }
+    if (e0 < best) tz_staged_gate(c, cur, bits, e0, gate, full);
     if (lane == 0)
     {
       c.sm->gate[i] = gate;

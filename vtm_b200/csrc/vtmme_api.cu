@@ -383,7 +383,9 @@ int vtmme_search_frames_device(vtmme_ctx* ctx, int nPairs, const int32_t* curPic
   if (nPairs <= 0 || !curPics || !refPics || !prm || !dResults)
     return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search_frames", "null argument");
   if (prm->searchRange < 1 || prm->searchRange > 512 || prm->bitDepth < 8 || prm->bitDepth > 10 || prm->predSpread < 0 ||
-      (prm->subShiftMode != 0 && prm->subShiftMode != 2) || (prm->fastSearch != 0 && prm->fastSearch != 1 && prm->fastSearch != 3))
+      prm->fastSearch < 0 || prm->fastSearch > 3 ||
+      (prm->subShiftMode != 0 && prm->subShiftMode != 2 && !(prm->subShiftMode == 1 && prm->fastSearch == 2)) ||
+      (prm->fastSearch == 2 && prm->searchRange > 128))   // tz_raster's window index (see vtmme_search)
     return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search_frames", "unsupported parameters");
   const bool tzFrame = prm->fastSearch != 0;
   VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
@@ -493,6 +495,7 @@ int vtmme_search_frames_device(vtmme_ctx* ctx, int nPairs, const int32_t* curPic
     zp.imvShift        = prm->imvShift;
     zp.subShiftMode    = prm->subShiftMode;
     zp.extended        = prm->fastSearch == 3;
+    zp.selective       = prm->fastSearch == 2;
     zp.firstSearchStop = prm->tzFirstSearchStop;
     zp.lambda          = prm->lambdaMotion;
     VTMME_CUDA_CHECK(ctx, launch_tz_frame(zp, nPairs, ctx->stream, &tzLaunches));
