@@ -410,6 +410,9 @@ def run_ours(args, rank, world, local_rank):
             rate, sec, desc, kind, threads = cpu_reference_rate(cur0, ref0, args.cpu_every, os.cpu_count() or 1)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind, "sample": desc,
                                     "seconds": sec}
+            if kind == "reference":   # the single-thread number next to the all-cores one (sparser sample)
+                r1, s1, d1, _, _ = cpu_reference_rate(cur0, ref0, 8 * args.cpu_every, 1)
+                line["cpu_baseline"]["single_core"] = {"value": r1, "unit": UNIT, "cores": 1, "sample": d1, "seconds": s1}
         emit(line)
     ms.close()
     if world > 1:

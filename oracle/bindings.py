@@ -105,6 +105,8 @@ def oracle():
                                    C.POINTER(C.c_uint64), C.POINTER(_I)]
         L.vo_mctf_apply_motion.argtypes = [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _I]
         L.vo_mctf_me.argtypes = [_P, _I, _P, _I, _I, _I, _I, _P]
+        L.vo_dmvr_block.restype = None
+        L.vo_dmvr_block.argtypes = [_P, _P, _I] + [_I] * 13 + [_P]
         L.vo_mctf_error.argtypes = [_P, _I, _P, _I] + [_I] * 7
         L.vo_mctf_error.restype = _I
         L.vo_mc_block.argtypes = [_I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I]
@@ -147,6 +149,7 @@ def ref():
         L.ref_mctf_me.restype = C.c_double
         L.ref_mctf_me.argtypes = [_P, _I, _P, _I, _I, _I, _I, _P]
         L.ref_mc_blocks.argtypes = [_I, _P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, C.POINTER(C.c_double)]
+        L.ref_dmvr_blocks.argtypes = [_P, _P, _I, _I, _I, _I, _I, _P, _I, _P]
         L.ref_add_avg.argtypes = [_P, _P, _P, _I, _I, _I]
         L.ref_remove_high_freq.argtypes = [_P, _I, _P, _I, _I, _I, _I, _I]
         _ref = L

@@ -320,6 +320,107 @@ int ref_mc_blocks(int comp, const int16_t* plane, int planeStride, int lumaW, in
   return 0;
 }
 
+// ---- decoder-side MV refinement: the reference's own members InterPrediction::xPrefetch (InterPrediction.cpp:1664-1708),
+// xinitMC (:1949-1995: bilinear prediction of the (w+4) x (h+4) neighbourhood of both lists), xDMVRCost (:1919-1927),
+// xBIPMVRefine (:1820-1843) and the free function xDMVRSubPixelErrorSurface (:1929-1947), driven per sub-block the way
+// xProcessDMVR does (:2098-2154).  plane0 / plane1: luma planes of the two reference pictures (`margin` border samples on
+// each side already extended).  blk: n x 8 int32 {x, y, w, h, mvL0x, mvL0y, mvL1x, mvL1y}, w,h <= 16, MVs in 1/16 sample.
+// out: n x 4 int32 {mvdL0SubPu.hor, .ver (1/16 sample), minCost, notZeroCost}.  Returns 0, or -1 when the margin does not fit.
+extern "C++" void xDMVRSubPixelErrorSurface(bool notZeroCost, int16_t* totalDeltaMV, int16_t* deltaMV, uint64_t* pSADsArray);   // InterPrediction.cpp:1929
+int ref_dmvr_blocks(const int16_t* plane0, const int16_t* plane1, int planeStride, int lumaW, int lumaH, int margin, int n,
+                               const int32_t* blk, int bitDepth, int32_t* out)
+{
+  Probe&  p = probe();
+  Picture pics[2];
+  for (int l = 0; l < 2; l++)
+  {
+    Picture& pic = pics[l];
+    pic.create(CHROMA_420, Size(lumaW, lumaH), 128, 128 + 16, false, 0);
+    pic.unscaledPic = &pic;
+    PelBuf reco = pic.getRecoBuf(COMPONENT_Y);
+    if (margin > (int) pic.margin) return -1;
+    const int16_t* plane = l ? plane1 : plane0;
+    for (int y = -margin; y < lumaH + margin; y++)
+      memcpy(reco.buf + (ptrdiff_t) y * reco.stride - margin, plane + (ptrdiff_t) (y + margin) * planeStride,
+             sizeof(int16_t) * (lumaW + 2 * margin));
+  }
+  PPS pps;
+  pps.setPicWidthInLumaSamples(lumaW);
+  pps.setPicHeightInLumaSamples(lumaH);
+  SPS sps;
+  std::vector<uint64_t> shell((sizeof(CodingStructure) + 7) / 8, 0);
+  CodingStructure* cs = reinterpret_cast<CodingStructure*>(shell.data());
+  cs->sps = &sps;
+  cs->pps = &pps;
+  Slice* slice = new Slice();
+  for (int l = 0; l < 2; l++)
+  {
+    slice->m_apcRefPicList[l][0] = &pics[l];
+    slice->m_scalingRatio[l][0]  = SCALE_1X;
+  }
+  clipMv = clipMvInPic;
+  ClpRngs clps;
+  for (int c = 0; c < MAX_NUM_COMPONENT; c++) clps.comp[c] = makeClp(bitDepth);
+  const int side = 2 * DMVR_NUM_ITERATION + 1;
+  for (int i = 0; i < n; i++)
+  {
+    const int32_t* b = blk + 8 * i;
+    const int dx = b[2], dy = b[3];
+    CodingUnit cu;
+    cu.imv    = IMV_OFF;
+    cu.affine = false;
+    cu.slice  = slice;
+    PredictionUnit pu(CHROMA_420, Area(b[0], b[1], dx, dy));
+    pu.cu = &cu;
+    pu.cs = cs;
+    pu.refIdx[0] = pu.refIdx[1] = 0;
+    pu.mv[0] = Mv(b[4], b[5]);
+    pu.mv[1] = Mv(b[6], b[7]);
+    // buffers as xProcessDMVR sets them up (:2063-2078)
+    p.m_biLinearBufStride = dx + 2 * DMVR_NUM_ITERATION;
+    p.m_cYuvRefBuffDMVRL0 = PelUnitBuf(CHROMA_400, PelBuf(p.m_cRefSamplesDMVRL0[0], dx, dx, dy));
+    p.m_cYuvRefBuffDMVRL1 = PelUnitBuf(CHROMA_400, PelBuf(p.m_cRefSamplesDMVRL1[0], dx, dx, dy));
+    Pel* predL0 = p.m_cYuvPredTempDMVRL0 + DMVR_NUM_ITERATION * p.m_biLinearBufStride + DMVR_NUM_ITERATION;
+    Pel* predL1 = p.m_cYuvPredTempDMVRL1 + DMVR_NUM_ITERATION * p.m_biLinearBufStride + DMVR_NUM_ITERATION;
+    p.xPrefetch(pu, p.m_cYuvRefBuffDMVRL0, REF_PIC_LIST_0, 1);
+    p.xPrefetch(pu, p.m_cYuvRefBuffDMVRL1, REF_PIC_LIST_1, 1);
+    p.xinitMC(pu, clps);
+    uint64_t sads[side * side];
+    for (int k = 0; k < side * side; k++) sads[k] = MAX_UINT64;
+    uint64_t* centre = sads + (side * side) / 2;
+    int16_t   total[2] = { 0, 0 }, delta[2] = { 0, 0 };
+    bool      notZero  = true;
+    uint64_t  minCost  = p.xDMVRCost(bitDepth, predL0, p.m_biLinearBufStride, predL1, p.m_biLinearBufStride, dx, dy);
+    minCost -= minCost >> 2;
+    if (minCost < (uint64_t) (dx * dy))
+      notZero = false;
+    else
+    {
+      centre[0] = minCost;
+      if (!minCost)
+        notZero = false;
+      else
+      {
+        p.xBIPMVRefine(bitDepth, predL0, predL1, minCost, delta, centre, dx, dy);
+        total[0] = delta[0];
+        total[1] = delta[1];
+        centre += delta[1] * side + delta[0];
+      }
+    }
+    total[0] = total[0] << MV_FRACTIONAL_BITS_INTERNAL;
+    total[1] = total[1] << MV_FRACTIONAL_BITS_INTERNAL;
+    xDMVRSubPixelErrorSurface(notZero, total, delta, centre);
+    out[4 * i + 0] = total[0];
+    out[4 * i + 1] = total[1];
+    out[4 * i + 2] = (int32_t) minCost;
+    out[4 * i + 3] = notZero;
+  }
+  delete slice;
+  pics[0].destroy();
+  pics[1].destroy();
+  return 0;
+}
+
 // AreaBuf<Pel>::removeHighFreq (Buffer.h:474-517): dst = 2*dst - src, optionally clipped (bi-pred ME target)
 void ref_remove_high_freq(int16_t* dst, int dstStride, const int16_t* src, int srcStride, int w, int h, int clip, int bd)
 {

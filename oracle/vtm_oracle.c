@@ -1146,6 +1146,141 @@ void vo_tz_search(const vo_job* j, const vo_tz_params* p, int* mvx, int* mvy, ui
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * Decoder-side MV refinement (DMVR): the search of one sub-block
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Bilinear prediction of the (w+4) x (h+4) neighbourhood of the block the merge MV points at — xPrefetch
+ * (InterPrediction.cpp:1664-1708: the reference samples are fetched at the integer part of clip(mv - 3 samples)),
+ * xinitMC (:1949-1995: the fraction comes from clip(mv), the block starts 2 samples up and left) and xPredInterBlk with
+ * bilinearMC (:660-768) on the 2-tap filter m_bilinearFilterPrec4 (InterpolationFilter.cpp:312-330) with the
+ * biMCForDMVR rounding (:424-452, :600-612): 10-bit intermediates whatever the bit depth.  ref: sample (0,0) of the
+ * reference plane (border extended).  dst stride w + 4. */
+static void vo_dmvr_bilinear(const vo_pel* ref, int refStride, int x, int y, int w, int h, int mvx, int mvy, int picW, int picH,
+                             int maxCuW, int maxCuH, int bd, vo_pel* dst)
+{
+  const int W2 = w + 4, H2 = h + 4;
+  int       cx = mvx - 48, cy = mvy - 48, fx = mvx, fy = mvy, r, c;
+  int       tmp[21][20];
+  vo_clip_mv(&cx, &cy, x, y, picW, picH, maxCuW, maxCuH);
+  vo_clip_mv(&fx, &fy, x, y, picW, picH, maxCuW, maxCuH);
+  {
+    const vo_pel* src  = ref + (ptrdiff_t) (y + (cy >> 4) + 1) * refStride + x + (cx >> 4) + 1;
+    const int     xf   = fx & 15, yf = fy & 15;
+    const int     sh1  = 4 - (10 - bd), off1 = 1 << (sh1 - 1); /* first pass: IF_FILTER_PREC_BILINEAR - (10 - bd) */
+    if (yf == 0 && xf == 0) /* filterCopy, isFirst && !isLast */
+    {
+      for (r = 0; r < H2; r++)
+        for (c = 0; c < W2; c++) dst[r * W2 + c] = (vo_pel) (src[(ptrdiff_t) r * refStride + c] << (10 - bd));
+    }
+    else if (yf == 0)
+    {
+      for (r = 0; r < H2; r++)
+        for (c = 0; c < W2; c++)
+          dst[r * W2 + c] = (vo_pel) ((src[(ptrdiff_t) r * refStride + c] * (16 - xf) + src[(ptrdiff_t) r * refStride + c + 1] * xf + off1) >> sh1);
+    }
+    else if (xf == 0)
+    {
+      for (r = 0; r < H2; r++)
+        for (c = 0; c < W2; c++)
+          dst[r * W2 + c] = (vo_pel) ((src[(ptrdiff_t) r * refStride + c] * (16 - yf) + src[(ptrdiff_t) (r + 1) * refStride + c] * yf + off1) >> sh1);
+    }
+    else
+    {
+      for (r = 0; r < H2 + 1; r++)
+        for (c = 0; c < W2; c++)
+          tmp[r][c] = (vo_pel) ((src[(ptrdiff_t) r * refStride + c] * (16 - xf) + src[(ptrdiff_t) r * refStride + c + 1] * xf + off1) >> sh1);
+      for (r = 0; r < H2; r++)
+        for (c = 0; c < W2; c++) dst[r * W2 + c] = (vo_pel) ((tmp[r][c] * (16 - yf) + tmp[r + 1][c] * yf + 8) >> 4);
+    }
+  }
+}
+
+/* div_for_maxq7 — InterPrediction.cpp:1731-1763 */
+static int vo_div_maxq7(int64_t num, int64_t den)
+{
+  int sign = 0, q = 0;
+  if (num < 0)
+  {
+    sign = 1;
+    num  = -num;
+  }
+  den <<= 3;
+  if (num >= den)
+  {
+    num -= den;
+    q++;
+  }
+  q <<= 1;
+  den >>= 1;
+  if (num >= den)
+  {
+    num -= den;
+    q++;
+  }
+  q <<= 1;
+  if (num >= (den >> 1)) q++;
+  return sign ? -q : q;
+}
+
+/* One sub-block of xProcessDMVR (InterPrediction.cpp:2098-2154): cost at the merge MVs (even rows, xDMVRCost :1919-1927),
+ * biased by 1/4; if it reaches w*h, the 25 mirrored integer offsets (xBIPMVRefine :1820-1843, first strict minimum in
+ * the order of m_pSearchOffset) and the parametric sub-sample step (xDMVRSubPixelErrorSurface :1929-1947,
+ * xSubPelErrorSrfc :1766-1818).  out: {mvdL0SubPu.hor, .ver (1/16 sample), minCost, notZeroCost}. */
+void vo_dmvr_block(const vo_pel* ref0, const vo_pel* ref1, int refStride, int x, int y, int w, int h, int mv0x, int mv0y, int mv1x,
+                   int mv1y, int picW, int picH, int maxCuW, int maxCuH, int bd, int32_t* out)
+{
+  vo_pel    p0[20 * 20], p1[20 * 20];
+  uint64_t  sad[25], minCost;
+  const int W2 = w + 4;
+  int       k, r, c, bestK = 12, notZero = 1, totalX = 0, totalY = 0;
+  vo_dmvr_bilinear(ref0, refStride, x, y, w, h, mv0x, mv0y, picW, picH, maxCuW, maxCuH, bd, p0);
+  vo_dmvr_bilinear(ref1, refStride, x, y, w, h, mv1x, mv1y, picW, picH, maxCuW, maxCuH, bd, p1);
+  for (k = 0; k < 25; k++)
+  {
+    /* offset (ox, oy) on list 0, mirrored on list 1; rows 0, 2, 4 ... (subShift 1, the << 1 of the SAD undone by xDMVRCost) */
+    const int ox = k % 5 - 2, oy = k / 5 - 2;
+    uint64_t  s = 0;
+    for (r = 0; r < h; r += 2)
+      for (c = 0; c < w; c++) s += (uint64_t) abs(p0[(2 + oy + r) * W2 + 2 + ox + c] - p1[(2 - oy + r) * W2 + 2 - ox + c]);
+    sad[k] = s;
+  }
+  minCost = sad[12] - (sad[12] >> 2);
+  if (minCost < (uint64_t) (w * h))
+    notZero = 0;
+  else
+  {
+    sad[12] = minCost;
+    if (!minCost)
+      notZero = 0;
+    else
+      for (k = 0; k < 25; k++)
+        if (sad[k] < minCost)
+        {
+          minCost = sad[k];
+          bestK   = k;
+        }
+  }
+  totalX = (bestK % 5 - 2) * 16;
+  totalY = (bestK / 5 - 2) * 16;
+  if (notZero && abs(totalX) != 32 && abs(totalY) != 32)
+  {
+    /* centre, left, top, right, bottom */
+    const uint64_t e0 = sad[bestK], e1 = sad[bestK - 1], e2 = sad[bestK - 5], e3 = sad[bestK + 1], e4 = sad[bestK + 5];
+    int64_t        num, den;
+    num = (int64_t) ((e1 - e3) << 4);
+    den = (int64_t) (e1 + e3 - (e0 << 1));
+    if (den != 0) totalX += (e1 != e0 && e3 != e0) ? vo_div_maxq7(num, den) : (e1 == e0 ? -8 : 8);
+    num = (int64_t) ((e2 - e4) << 4);
+    den = (int64_t) (e2 + e4 - (e0 << 1));
+    if (den != 0) totalY += (e2 != e0 && e4 != e0) ? vo_div_maxq7(num, den) : (e2 == e0 ? -8 : 8);
+  }
+  out[0] = totalX;
+  out[1] = totalY;
+  out[2] = (int32_t) minCost;
+  out[3] = notZero;
+}
+
+/* ------------------------------------------------------------------------------------------------
  * GOP-based temporal filter: motion estimation
  * ---------------------------------------------------------------------------------------------- */
 

@@ -150,6 +150,13 @@ void vo_mctf_apply_motion(const vo_pel* src, int srcStride, int compW, int compH
 int  vo_mctf_error(const vo_pel* org, int orgStride, const vo_pel* ref, int refStride, int x, int y, int dx, int dy, int bs,
                    int bestError, int bitDepth);
 
+/* Decoder-side MV refinement, one sub-block of InterPrediction::xProcessDMVR (CommonLib/InterPrediction.cpp:2098-2154):
+ * bilinear predictions of both lists around the merge MVs, cost at the centre, 25 mirrored integer offsets, parametric
+ * sub-sample step.  ref0 / ref1: sample (0,0) of the two reference planes (border extended); w, h in {8, 16}; MVs in 1/16
+ * sample.  out: {mvdL0SubPu.hor, .ver, minCost, notZeroCost}. */
+void vo_dmvr_block(const vo_pel* ref0, const vo_pel* ref1, int refStride, int x, int y, int w, int h, int mv0x, int mv0y, int mv1x,
+                   int mv1y, int picW, int picH, int maxCuW, int maxCuH, int bd, int32_t* out);
+
 #ifdef __cplusplus
 }
 #endif

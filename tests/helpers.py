@@ -177,3 +177,34 @@ def oracle_frame_tz(L, cur, ref_padded, margin, sr, lam, pred_q=None, fast_searc
                             my.value, int(sad.value), int(cost.value))
                 idx += 1
     return out
+
+
+def dmvr_cases(rng, pic_w, pic_h, n, max_pel=24, same=False):
+    """n random DMVR sub-blocks {x, y, w, h, mvL0, mvL1} (int32 [n, 8]): sizes 8 / 16, merge MVs in 1/16 sample around a
+    mirrored pair (DMVR's bi-prediction with equal POC distances) plus a small mismatch, some integer / half-sample MVs,
+    some blocks at the picture border with MVs pointing far outside (the MV clip of xPrefetch / xinitMC)."""
+    blk = np.zeros((n, 8), np.int32)
+    for i in range(n):
+        w, h = int(rng.choice([8, 16])), int(rng.choice([8, 16]))
+        x = int(rng.integers(0, (pic_w - w) // 4 + 1)) * 4
+        y = int(rng.integers(0, (pic_h - h) // 4 + 1)) * 4
+        mx, my = (int(rng.integers(-max_pel * 16, max_pel * 16 + 1)) for _ in range(2))
+        kind = i % 8
+        if kind == 1:
+            mx, my = mx & ~15, my & ~15
+        elif kind == 2:
+            mx = mx & ~15
+        elif kind == 3:
+            my = (my & ~15) | 8
+        ex, ey = (int(rng.integers(-40, 41)) for _ in range(2))
+        if kind == 7:
+            x, y = [0, pic_w - w][int(rng.integers(0, 2))], [0, pic_h - h][int(rng.integers(0, 2))]
+            mx, my = (int(rng.integers(-200 * 16, 200 * 16 + 1)) for _ in range(2))
+        blk[i] = (x, y, w, h, mx, my, -mx + ex, -my + ey)
+        if same:
+            # both lists read the same picture: list 1 = list 0 displaced by 2*(ox, oy) samples makes offset (ox, oy) exact
+            ox, oy = (int(rng.integers(-2, 3)) for _ in range(2))
+            if kind in (0, 4):
+                ox = oy = 0          # identical predictions: the early exit below w*h
+            blk[i, 6:8] = (mx + 32 * ox, my + 32 * oy)
+    return blk

@@ -390,6 +390,43 @@ def test_tz_search_selective(oracle_lib, ref_lib, selective, fast):
 
 
 @pytest.mark.ref
+@pytest.mark.parametrize("bd", [10, 8])
+def test_dmvr_blocks(oracle_lib, ref_lib, bd):
+    """The DMVR search of a sub-block (InterPrediction.cpp:2098-2154): the reference's own xPrefetch, xinitMC (bilinear
+    prediction), xDMVRCost, xBIPMVRefine and xDMVRSubPixelErrorSurface against the restatement — all phases of the
+    bilinear filter, the early exit below w*h, integer and sub-sample outcomes, MVs clipped at the picture border."""
+    from tests.helpers import MARGIN, dmvr_cases, pad_plane
+    from vtm_b200.synth import make_pair
+    rng = np.random.default_rng(900 + bd)
+    pic_w, pic_h = 256, 192
+    n = moved = sub = skipped = 0
+    for seed in range(4):
+        # the two references are the two sides of a pair: true motion between them, so that refinements are found;
+        # seed 3: both lists read the same picture (exact matches: early exit, zero costs on the error surface)
+        r0, r1, _ = make_pair(120 + seed, pic_w, pic_h, max_global=[1, 2, 6, 2][seed], max_local=3, n_rects=4,
+                              sigma=[1.0, 4.0, 6.0, 3.0][seed], bit_depth=bd)
+        if seed == 3:
+            r1 = r0
+        p0, p1 = pad_plane(r0), pad_plane(r1)
+        stride = p0.shape[1]
+        blk = dmvr_cases(rng, pic_w, pic_h, 400, same=seed == 3)
+        want = np.zeros((len(blk), 4), np.int32)
+        assert ref_lib.ref_dmvr_blocks(B.ptr(p0), B.ptr(p1), stride, pic_w, pic_h, MARGIN, len(blk), C.c_void_p(blk.ctypes.data), bd,
+                                       C.c_void_p(want.ctypes.data)) == 0
+        got = np.zeros(4, np.int32)
+        off = MARGIN * stride + MARGIN
+        for i, b in enumerate(blk):
+            oracle_lib.vo_dmvr_block(B.ptr(p0, off), B.ptr(p1, off), stride, *[int(v) for v in b], pic_w, pic_h, 128, 128, bd,
+                                     C.c_void_p(got.ctypes.data))
+            assert got.tolist() == want[i].tolist(), (seed, i, b.tolist())
+        n += len(blk)
+        moved += int(((want[:, 0] != 0) | (want[:, 1] != 0)).sum())
+        sub += int(((want[:, 0] % 16 != 0) | (want[:, 1] % 16 != 0)).sum())
+        skipped += int((want[:, 3] == 0).sum())
+    assert n == 1600 and moved > 100 and sub > 50 and skipped > 20
+
+
+@pytest.mark.ref
 @pytest.mark.parametrize("w,h,bd", [(208, 120, 10), (176, 144, 8), (96, 64, 10)])
 def test_mctf_motion_estimation(oracle_lib, ref_lib, w, h, bd):
     """EncTemporalFilter::motionEstimation (EncTemporalFilter.cpp:448-466): the reference's own member against the
