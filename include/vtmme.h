@@ -25,6 +25,8 @@
  *     AreaBuf::removeHighFreq (Buffer.h:474-517)                    vtmme_remove_high_freq
  *   EncTemporalFilter::motionEstimation / applyMotion (EncoderLib/  vtmme_mctf_me / vtmme_mctf_apply_motion
  *     EncTemporalFilter.cpp:448-466, 470-552)
+ *   InterPrediction::xProcessDMVR, the search (CommonLib/           vtmme_dmvr_refine
+ *     InterPrediction.cpp:2098-2154)
  *   distortion of InterSearch::xGetTemplateCost and of the ME      vtmme_cand_sad
  *     seeds (EncoderLib/InterSearch.cpp:3235-3270, 3388-3426)
  *   Picture::getRecoBuf / getOrigBuf planes handed to ME            vtmme_upload_picture / vtmme_release_picture
@@ -295,6 +297,32 @@ typedef struct vtmme_cand_job
   int32_t        reserved;   /* 0 */
 } vtmme_cand_job;
 int vtmme_cand_sad(vtmme_ctx* ctx, int bitDepth, int useAltHpel, int nJobs, const vtmme_cand_job* jobs, uint64_t* out);
+
+/* ---- decoder-side MV refinement (DMVR), SURVEY 8(f) rank 4 ---------------------------------------------------------
+ * The search of InterPrediction::xProcessDMVR for a batch of sub-blocks (CommonLib/InterPrediction.cpp:2098-2154):
+ * bilinear prediction of both lists around the merge MVs (xPrefetch :1664-1708, xinitMC :1949-1995), the cost at the
+ * merge MVs with its 1/4 bias and the early exit below w*h, the 25 mirrored integer offsets (xDMVRCost :1919-1927,
+ * xBIPMVRefine :1820-1843) and the parametric sub-sample step (xDMVRSubPixelErrorSurface :1929-1947).  The result is
+ * what xProcessDMVR stores in pu.mvdL0SubPu[] (list 0 moves by +mvd, list 1 by -mvd); the final motion compensation
+ * with the refined MVs is vtmme_mc_batch's job.  Plain DMVR only: no wrap-around, no reference scaling. */
+typedef struct
+{
+  int32_t x, y, w, h;         /* sub-block (luma samples); w, h in {8, 16} (DMVR_SUBCU_WIDTH / HEIGHT, PU::checkDMVRCondition) */
+  int32_t mvL0x, mvL0y;       /* merge MV of list 0, 1/16 sample                                                      */
+  int32_t mvL1x, mvL1y;       /* merge MV of list 1                                                                   */
+} vtmme_dmvr_block;
+
+typedef struct
+{
+  int32_t  mvdX, mvdY;        /* pu.mvdL0SubPu[i], 1/16 sample                                                        */
+  uint32_t minCost;           /* minCost after the integer stage (the BDOF switch compares it with 2*w*h, :2146)      */
+  int32_t  notZeroCost;       /* 0: the search stopped at the centre (cost below w*h, or zero)                        */
+} vtmme_dmvr_result;
+
+/* refPic0 / refPic1: uploaded reference pictures of list 0 / list 1 (same size); blocks, results: HOST arrays of n entries;
+ * maxCu: sps.getMaxCUWidth() (== Height) of the MV clip, <= 128.  Synchronous. */
+int vtmme_dmvr_refine(vtmme_ctx* ctx, int refPic0, int refPic1, int bitDepth, int maxCu, int n, const vtmme_dmvr_block* blocks,
+                      vtmme_dmvr_result* results);
 
 /* ---- GOP-based temporal filter: motion estimation ---------------------------------
  * EncTemporalFilter::motionEstimation (EncoderLib/EncTemporalFilter.cpp:448-466): the four-level hierarchical block

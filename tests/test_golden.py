@@ -224,3 +224,29 @@ def test_mctf_golden(oracle_lib):
     out = np.zeros((h // 4, w // 4, 3), np.int32)
     oracle_lib.vo_mctf_me(B.ptr(curp, off), stride, B.ptr(refp, off), stride, w, h, 10, C.c_void_p(out.ctypes.data))
     assert np.array_equal(out, g["mv"])
+
+
+# ---- DMVR fixtures (tests/golden/dmvr_golden.npz, make_golden_dmvr.py); pictures of amvr_tz_golden.npz -----------------
+GD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dmvr_golden.npz"))
+
+
+def iter_dmvr():
+    """(padded list-0 plane, padded list-1 plane, margin, blocks int32 [n, 8], want int32 [n, 4])"""
+    from tests.helpers import MARGIN, pad_plane
+    p0, p1 = pad_plane(np.ascontiguousarray(GA["ref"])), pad_plane(np.ascontiguousarray(GA["cur"]))
+    yield p0, p1, MARGIN, GD["pair_blk"], GD["pair_res"]
+    yield p0, p0, MARGIN, GD["same_blk"], GD["same_res"]
+
+
+def test_dmvr_golden(oracle_lib):
+    """oracle DMVR sub-block search == the reference's own members (320 cases)"""
+    n = 0
+    for p0, p1, m, blk, want in iter_dmvr():
+        stride, off = p0.shape[1], m * p0.shape[1] + m
+        got = np.zeros(4, np.int32)
+        for b, w in zip(blk, want):
+            oracle_lib.vo_dmvr_block(B.ptr(p0, off), B.ptr(p1, off), stride, *[int(v) for v in b], GA_W, GA_H, 128, 128, 10,
+                                     C.c_void_p(got.ctypes.data))
+            assert got.tolist() == w.tolist(), b.tolist()
+            n += 1
+    assert n == 320

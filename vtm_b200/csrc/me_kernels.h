@@ -245,4 +245,19 @@ cudaError_t launch_mctf_apply_motion(DevPic src, int csx, int csy, const int3* m
                                      cudaStream_t st);
 cudaError_t launch_mctf_level(const MctfLevelParams& p, int blockSize, bool doubleRes, int nPairs, cudaStream_t st);
 
+// Decoder-side MV refinement of a batch of sub-blocks (dmvr_kernels.cu); same layouts as vtmme_dmvr_block / _result
+struct DevDmvrBlock
+{
+  int x, y, w, h;
+  int mv0x, mv0y, mv1x, mv1y;
+};
+struct DevDmvrResult
+{
+  int      mvdX, mvdY;
+  uint32_t minCost;
+  int      notZeroCost;
+};
+cudaError_t launch_dmvr_refine(const DevPic& ref0, const DevPic& ref1, const DevDmvrBlock* blocks, int n, int bitDepth, int maxCu,
+                               DevDmvrResult* results, cudaStream_t st);
+
 }   // namespace vtmme

@@ -1397,6 +1397,45 @@ extern "C" int vtmme_remove_high_freq(vtmme_ctx* ctx, int16_t* dOrg, const int16
 }
 
 // ---- candidate distortion (template cost / seeds) -------------------------------------------------------------------
+static_assert(sizeof(vtmme_dmvr_block) == sizeof(DevDmvrBlock) && sizeof(vtmme_dmvr_result) == sizeof(DevDmvrResult),
+              "DMVR layouts must match");
+
+extern "C" int vtmme_dmvr_refine(vtmme_ctx* ctx, int refPic0, int refPic1, int bitDepth, int maxCu, int n,
+                                 const vtmme_dmvr_block* blocks, vtmme_dmvr_result* results)
+{
+  if (!ctx) return VTMME_ERR_ARG;
+  const char* who = "vtmme_dmvr_refine";
+  if (!blocks || !results || n <= 0 || n > (1 << 22) || bitDepth < 8 || bitDepth > 10 || maxCu < 8 || maxCu > 128)
+    return vtmme_set_error(ctx, VTMME_ERR_ARG, who, "bad argument (bitDepth 8..10, maxCu 8..128)");
+  VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  if (ctx->pics.find(refPic0) == ctx->pics.end() || ctx->pics.find(refPic1) == ctx->pics.end())
+    return vtmme_set_error(ctx, VTMME_ERR_NOPIC, who, "unknown picture id");
+  const DevPic r0 = ctx->pics[refPic0], r1 = ctx->pics[refPic1];
+  if (r0.width != r1.width || r0.height != r1.height) return vtmme_set_error(ctx, VTMME_ERR_ARG, who, "the two reference pictures differ in size");
+  for (int i = 0; i < n; i++)
+  {
+    const vtmme_dmvr_block& b = blocks[i];
+    if ((b.w != 8 && b.w != 16) || (b.h != 8 && b.h != 16) || b.x < 0 || b.y < 0 || b.x + b.w > r0.width || b.y + b.h > r0.height)
+      return vtmme_set_error(ctx, VTMME_ERR_ARG, who, "bad sub-block (w,h in {8,16}, inside the picture)");
+  }
+  // the MV clip keeps every fetched sample within maxCu + 8 + 16 + 7 samples of the picture: inside the device margin
+  int rc;
+  if ((rc = wait_picture(ctx, refPic0)) != VTMME_OK || (rc = wait_picture(ctx, refPic1)) != VTMME_OK) return rc;
+  const size_t inBytes = align256((size_t) n * sizeof(DevDmvrBlock)), total = inBytes + align256((size_t) n * sizeof(DevDmvrResult));
+  VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));   // the staging blocks are shared with the other synchronous calls
+  if ((rc = ensure_pinned(ctx, total)) != VTMME_OK) return rc;
+  if ((rc = ensure(ctx, ctx->dJobBuf, ctx->jobBufCap, total)) != VTMME_OK) return rc;
+  memcpy(ctx->hPinned, blocks, (size_t) n * sizeof(DevDmvrBlock));
+  DevDmvrResult* dRes = reinterpret_cast<DevDmvrResult*>(ctx->dJobBuf + inBytes);
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dJobBuf, ctx->hPinned, (size_t) n * sizeof(DevDmvrBlock), cudaMemcpyHostToDevice, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, launch_dmvr_refine(r0, r1, reinterpret_cast<const DevDmvrBlock*>(ctx->dJobBuf), n, bitDepth, maxCu, dRes, ctx->stream));
+  ctx->launches += 1;
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->hPinned + inBytes, dRes, (size_t) n * sizeof(DevDmvrResult), cudaMemcpyDeviceToHost, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(results, ctx->hPinned + inBytes, (size_t) n * sizeof(DevDmvrResult));
+  return VTMME_OK;
+}
+
 extern "C" int vtmme_cand_sad(vtmme_ctx* ctx, int bitDepth, int useAltHpel, int nJobs, const vtmme_cand_job* jobs, uint64_t* out)
 {
   if (!ctx) return VTMME_ERR_ARG;

@@ -9,7 +9,8 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .lib import CAmvr, CCandJob, CTz, CFrameParams, CJob, CMcBlock, CResult, ERR_NAMES, VtmmeError, load_library
+from .lib import (CAmvr, CCandJob, CDmvrBlock, CDmvrResult, CTz, CFrameParams, CJob, CMcBlock, CResult, ERR_NAMES, VtmmeError,
+                  load_library)
 
 # vtmme_cu_result
 CU_RESULT_DTYPE = np.dtype([("mvQx", "<i2"), ("mvQy", "<i2"), ("intX", "<i2"), ("intY", "<i2"),
@@ -355,6 +356,18 @@ class MotionSearch:
         self._check(self.L.vtmme_mctf_apply_motion(self.ctx, src_id, csx, csy, C.c_void_p(mv.ctypes.data), mv.shape[1],
                                                    mv.shape[0], bit_depth, C.c_void_p(out.ctypes.data)),
                     "vtmme_mctf_apply_motion")
+        return out
+
+    # ---- decoder-side MV refinement ------------------------------------------------------------------------
+    def dmvr_refine(self, ref_pic0, ref_pic1, blocks, bit_depth=10, max_cu=128):
+        """The search of InterPrediction::xProcessDMVR (CommonLib/InterPrediction.cpp:2098-2154) for a batch of sub-blocks.
+        blocks: int32 [n, 8] {x, y, w, h, mvL0x, mvL0y, mvL1x, mvL1y} (MVs in 1/16 sample).
+        Returns int32 [n, 4] {mvdL0SubPu.hor, .ver, minCost, notZeroCost}."""
+        blk = np.ascontiguousarray(np.asarray(blocks, dtype=np.int32).reshape(-1, 8))
+        out = np.zeros((len(blk), 4), np.int32)
+        self._check(self.L.vtmme_dmvr_refine(self.ctx, ref_pic0, ref_pic1, bit_depth, max_cu, len(blk),
+                                             C.cast(blk.ctypes.data, C.POINTER(CDmvrBlock)),
+                                             C.cast(out.ctypes.data, C.POINTER(CDmvrResult))), "vtmme_dmvr_refine")
         return out
 
     # ---- candidate distortion (AMVP template cost / ME seeds) ----------------------------------------------
