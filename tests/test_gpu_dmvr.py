@@ -79,9 +79,9 @@ def test_dmvr_full_picture(ms, oracle_lib):
     mv = rng.integers(-6 * 16, 6 * 16 + 1, (n, 2))
     blk = np.stack([xs.ravel(), ys.ravel(), np.full(n, 16), np.full(n, 16), mv[:, 0], mv[:, 1], -mv[:, 0] + rng.integers(-24, 25, n),
                     -mv[:, 1] + rng.integers(-24, 25, n)], axis=1).astype(np.int32)
-    launches = ms.launches()
+    launches = ms.launches
     got = ms.dmvr_refine(74, 75, blk)
-    assert ms.launches() - launches == 1
+    assert ms.launches - launches == 1
     pick = rng.choice(n, 300, replace=False)
     want = oracle_dmvr(oracle_lib, pad_plane(r0), pad_plane(r1), MARGIN, blk[pick], W, H, 10)
     assert np.array_equal(got[pick], want)
