@@ -320,7 +320,8 @@ typedef struct
 } vtmme_dmvr_result;
 
 /* refPic0 / refPic1: uploaded reference pictures of list 0 / list 1 (same size); blocks, results: HOST arrays of n entries;
- * maxCu: sps.getMaxCUWidth() (== Height) of the MV clip, <= 128.  Synchronous. */
+ * maxCu: sps.getMaxCUWidth() (== Height) of the MV clip, <= 128; n <= 2^20 (an 8K picture has 129,600 sub-blocks).
+ * Synchronous. */
 int vtmme_dmvr_refine(vtmme_ctx* ctx, int refPic0, int refPic1, int bitDepth, int maxCu, int n, const vtmme_dmvr_block* blocks,
                       vtmme_dmvr_result* results);
 

@@ -1405,8 +1405,8 @@ extern "C" int vtmme_dmvr_refine(vtmme_ctx* ctx, int refPic0, int refPic1, int b
 {
   if (!ctx) return VTMME_ERR_ARG;
   const char* who = "vtmme_dmvr_refine";
-  if (!blocks || !results || n <= 0 || n > (1 << 22) || bitDepth < 8 || bitDepth > 10 || maxCu < 8 || maxCu > 128)
-    return vtmme_set_error(ctx, VTMME_ERR_ARG, who, "bad argument (bitDepth 8..10, maxCu 8..128)");
+  if (!blocks || !results || n <= 0 || n > (1 << 20) || bitDepth < 8 || bitDepth > 10 || maxCu < 8 || maxCu > 128)
+    return vtmme_set_error(ctx, VTMME_ERR_ARG, who, "bad argument (at most 2^20 sub-blocks per call, bitDepth 8..10, maxCu 8..128)");
   VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
   if (ctx->pics.find(refPic0) == ctx->pics.end() || ctx->pics.find(refPic1) == ctx->pics.end())
     return vtmme_set_error(ctx, VTMME_ERR_NOPIC, who, "unknown picture id");
