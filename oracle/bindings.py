@@ -49,6 +49,18 @@ class IntRefine(C.Structure):
         return (self.mvX, self.mvY, self.mvpIdx, self.bits, self.cost)
 
 
+class SmvdIo(C.Structure):
+    """vo_smvd_io / RefSmvdIo (identical layout): state of an xSymmetricMotionEstimation call."""
+    _fields_ = [("x", C.c_int), ("y", C.c_int), ("w", C.c_int), ("h", C.c_int), ("picW", C.c_int), ("picH", C.c_int),
+                ("maxCuW", C.c_int), ("maxCuH", C.c_int), ("bd", C.c_int), ("imv", C.c_int),
+                ("curPredX", C.c_int), ("curPredY", C.c_int), ("tarPredX", C.c_int), ("tarPredY", C.c_int),
+                ("curMvX", C.c_int), ("curMvY", C.c_int), ("tarMvX", C.c_int), ("tarMvY", C.c_int),
+                ("clipBiPred", C.c_int), ("useHad", C.c_int), ("lambda_", C.c_double), ("cost", C.c_uint64)]
+
+    def tuple(self):
+        return (self.curMvX, self.curMvY, self.tarMvX, self.tarMvY, self.cost)
+
+
 class TzParams(C.Structure):
     """vo_tz_params / RefTzParams (identical layout): what xTZSearch receives besides the job."""
     _fields_ = [("startX", C.c_int), ("startY", C.c_int), ("hasInt2Nx2N", C.c_int), ("int2Nx2NX", C.c_int),
@@ -105,6 +117,8 @@ def oracle():
                                    C.POINTER(C.c_uint64), C.POINTER(_I)]
         L.vo_mctf_apply_motion.argtypes = [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _I]
         L.vo_mctf_me.argtypes = [_P, _I, _P, _I, _I, _I, _I, _P]
+        L.vo_smvd_search.restype = None
+        L.vo_smvd_search.argtypes = [_P, _I, _P, _P, _I, C.POINTER(SmvdIo)]
         L.vo_dmvr_block.restype = None
         L.vo_dmvr_block.argtypes = [_P, _P, _I] + [_I] * 13 + [_P]
         L.vo_mctf_error.argtypes = [_P, _I, _P, _I] + [_I] * 7
@@ -149,6 +163,7 @@ def ref():
         L.ref_mctf_me.restype = C.c_double
         L.ref_mctf_me.argtypes = [_P, _I, _P, _I, _I, _I, _I, _P]
         L.ref_mc_blocks.argtypes = [_I, _P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, C.POINTER(C.c_double)]
+        L.ref_smvd_search.argtypes = [_P, _I, _P, _P, _I, _I, _I, C.POINTER(SmvdIo)]
         L.ref_dmvr_blocks.argtypes = [_P, _P, _I, _I, _I, _I, _I, _P, _I, _P]
         L.ref_add_avg.argtypes = [_P, _P, _P, _I, _I, _I]
         L.ref_remove_high_freq.argtypes = [_P, _I, _P, _I, _I, _I, _I, _I]

@@ -421,6 +421,100 @@ int ref_dmvr_blocks(const int16_t* plane0, const int16_t* plane1, int planeStrid
   return 0;
 }
 
+// ---- symmetric MVD search: the reference's own InterSearch::xSymmetricMotionEstimation (InterSearch.cpp:4506-4518) ------
+// planeCur / planeTar: luma planes of the reference pictures of eRefPicList (list 0 here) and of the other list (`margin`
+// border samples on each side already extended); org: the original block.  Same field layout as vo_smvd_io.
+struct RefSmvdIo
+{
+  int      x, y, w, h, picW, picH, maxCuW, maxCuH, bd, imv;
+  int      curPredX, curPredY, tarPredX, tarPredY, curMvX, curMvY, tarMvX, tarMvY;
+  int      clipBiPred, useHad;
+  double   lambda;
+  uint64_t cost;
+};
+int ref_smvd_search(const int16_t* org, int orgStride, const int16_t* planeCur, const int16_t* planeTar, int planeStride, int margin,
+                    int n, RefSmvdIo* ios)
+{
+  Probe&  p = probe();
+  if (n <= 0) return 0;
+  const int lumaW = ios[0].picW, lumaH = ios[0].picH;
+  Picture pics[2];
+  for (int l = 0; l < 2; l++)
+  {
+    Picture& pic = pics[l];
+    pic.create(CHROMA_420, Size(lumaW, lumaH), 128, 128 + 16, false, 0);
+    pic.unscaledPic = &pic;
+    PelBuf reco = pic.getRecoBuf(COMPONENT_Y);
+    if (margin > (int) pic.margin) return -1;
+    const int16_t* plane = l ? planeTar : planeCur;
+    for (int y = -margin; y < lumaH + margin; y++)
+      memcpy(reco.buf + (ptrdiff_t) y * reco.stride - margin, plane + (ptrdiff_t) (y + margin) * planeStride,
+             sizeof(int16_t) * (lumaW + 2 * margin));
+  }
+  if (p.m_tmpStorageLCU.bufs.empty())   // what InterSearch::init creates (InterSearch.cpp:254-258)
+  {
+    for (int i = 0; i < NUM_REF_PIC_LIST_01; i++) p.m_tmpPredStorage[i].create(UnitArea(CHROMA_420, Area(0, 0, MAX_CU_SIZE, MAX_CU_SIZE)));
+    p.m_tmpStorageLCU.create(UnitArea(CHROMA_420, Area(0, 0, MAX_CU_SIZE, MAX_CU_SIZE)));
+  }
+  PPS pps;
+  pps.setPicWidthInLumaSamples(lumaW);
+  pps.setPicHeightInLumaSamples(lumaH);
+  SPS sps;
+  std::vector<uint64_t> shell((sizeof(CodingStructure) + 7) / 8, 0);
+  CodingStructure* cs = reinterpret_cast<CodingStructure*>(shell.data());
+  cs->sps = &sps;
+  cs->pps = &pps;
+  Slice* slice = new Slice();
+  for (int l = 0; l < 2; l++)
+  {
+    slice->m_apcRefPicList[l][0] = &pics[l];
+    slice->m_scalingRatio[l][0]  = SCALE_1X;
+  }
+  slice->setSPS(&sps);
+  clipMv = clipMvInPic;
+  p.cfg.setMCTSEncConstraint(false);
+  PelStorage orgStore;
+  orgStore.create(UnitArea(CHROMA_420, Area(0, 0, MAX_CU_SIZE, MAX_CU_SIZE)));
+  for (int i = 0; i < n; i++)
+  {
+    RefSmvdIo& io = ios[i];
+    sps.setBitDepth(CHANNEL_TYPE_LUMA, io.bd);
+    sps.setBitDepth(CHANNEL_TYPE_CHROMA, io.bd);
+    sps.setMaxCUWidth(io.maxCuW);
+    sps.setMaxCUHeight(io.maxCuH);
+    for (int c = 0; c < MAX_NUM_COMPONENT; c++) slice->m_clpRngs.comp[c] = makeClp(io.bd);
+    slice->setDisableSATDForRD(!io.useHad);
+    p.cfg.setClipForBiPredMeEnabled(io.clipBiPred != 0);
+    p.rd.m_motionLambda = io.lambda;
+    CodingUnit cu(CHROMA_420, Area(io.x, io.y, io.w, io.h));
+    cu.imv    = io.imv;
+    cu.affine = false;
+    cu.BcwIdx = BCW_DEFAULT;
+    cu.slice  = slice;
+    PredictionUnit pu(CHROMA_420, Area(io.x, io.y, io.w, io.h));
+    pu.cu = &cu;
+    pu.cs = cs;
+    cs->slice = slice;
+    const UnitArea rel(CHROMA_420, Area(0, 0, io.w, io.h));
+    PelUnitBuf orgBuf = orgStore.getBuf(rel);
+    for (int y = 0; y < io.h; y++) memcpy(orgBuf.Y().buf + (ptrdiff_t) y * orgBuf.Y().stride, org + (ptrdiff_t) (io.y + y) * orgStride + io.x, sizeof(int16_t) * io.w);
+    Mv         curPred(io.curPredX, io.curPredY), tarPred(io.tarPredX, io.tarPredY);
+    MvField    cur(Mv(io.curMvX, io.curMvY), 0), tar(Mv(io.tarMvX, io.tarMvY), 0);
+    Distortion cost = io.cost;
+    p.xSymmetricMotionEstimation(pu, orgBuf, curPred, tarPred, REF_PIC_LIST_0, cur, tar, cost, BCW_DEFAULT);
+    io.curMvX = cur.mv.hor;
+    io.curMvY = cur.mv.ver;
+    io.tarMvX = tar.mv.hor;
+    io.tarMvY = tar.mv.ver;
+    io.cost   = cost;
+  }
+  orgStore.destroy();
+  delete slice;
+  pics[0].destroy();
+  pics[1].destroy();
+  return 0;
+}
+
 // AreaBuf<Pel>::removeHighFreq (Buffer.h:474-517): dst = 2*dst - src, optionally clipped (bi-pred ME target)
 void ref_remove_high_freq(int16_t* dst, int dstStride, const int16_t* src, int srcStride, int w, int h, int clip, int bd)
 {

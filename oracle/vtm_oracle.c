@@ -1146,6 +1146,80 @@ void vo_tz_search(const vo_job* j, const vo_tz_params* p, int* mvx, int* mvy, ui
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * Symmetric MVD search (SMVD)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* InterSearch::xGetSymmetricCost — EncoderLib/InterSearch.cpp:4341-4391 (default BCW weights): both predictions with the
+ * 8-tap filter at the clipped MVs (an integer MV reads the picture directly, which is what the filter's copy gives),
+ * 2*org - predA (removeHighFreq), SATD or SAD against predB, weighted by 0.5. */
+static uint64_t vo_smvd_cost(const vo_pel* org, int orgStride, const vo_pel* refA, const vo_pel* refB, int refStride,
+                             const vo_smvd_io* io, int mvAx, int mvAy, int mvBx, int mvBy)
+{
+  vo_pel   predA[VO_MAX_CU * VO_MAX_CU], predB[VO_MAX_CU * VO_MAX_CU], tmp[VO_MAX_CU * VO_MAX_CU];
+  uint64_t dist;
+  int      r;
+  vo_clip_mv(&mvAx, &mvAy, io->x, io->y, io->picW, io->picH, io->maxCuW, io->maxCuH);
+  vo_clip_mv(&mvBx, &mvBy, io->x, io->y, io->picW, io->picH, io->maxCuW, io->maxCuH);
+  vo_mc_block(0, refA + (ptrdiff_t) io->y * refStride + io->x, refStride, io->w, io->h, mvAx, mvAy, 0, io->bd, io->imv == 3, predA, io->w);
+  vo_mc_block(0, refB + (ptrdiff_t) io->y * refStride + io->x, refStride, io->w, io->h, mvBx, mvBy, 0, io->bd, io->imv == 3, predB, io->w);
+  for (r = 0; r < io->h; r++) memcpy(tmp + r * io->w, org + (ptrdiff_t) r * orgStride, sizeof(vo_pel) * io->w);
+  vo_remove_high_freq(tmp, predA, io->w * io->h, io->clipBiPred, io->bd);
+  dist = io->useHad ? vo_satd(tmp, io->w, predB, io->w, io->w, io->h) : vo_sad(tmp, io->w, predB, io->w, io->w, io->h, 0);
+  return (uint64_t) floor(0.5 * (double) dist); /* xGetMEDistortionWeight(BCW_DEFAULT) */
+}
+
+/* InterSearch::xSymmeticRefineMvSearch — EncoderLib/InterSearch.cpp:4393-4503 (patterns 2 = diamond and 0 = cross, the two
+ * xSymmetricMotionEstimation uses; no MCTS constraint) */
+static void vo_smvd_refine(const vo_pel* org, int orgStride, const vo_pel* refCur, const vo_pel* refTar, int refStride, vo_smvd_io* io,
+                           int pattern, int stepShift, int maxRounds)
+{
+  static const int cross[4][2]   = { { 0, 1 }, { 1, 0 }, { 0, -1 }, { -1, 0 } };
+  static const int diamond[8][2] = { { 0, 2 }, { 1, 1 }, { 2, 0 }, { 1, -1 }, { 0, -2 }, { -1, -1 }, { -2, 0 }, { -1, 1 } };
+  const int down = io->imv == 0 ? -2 : (io->imv == 1 ? -4 : (io->imv == 2 ? -6 : -3)); /* Mv::m_amvrPrecision, Mv.cpp:43 */
+  const int predX = vo_change_prec(io->curPredX, down), predY = vo_change_prec(io->curPredY, down);
+  int       start = 0, end = pattern == 0 ? 3 : 7, rounding = pattern == 0 ? 4 : 8, mask = pattern == 0 ? 3 : 7;
+  int       round, idx;
+  for (round = 0; round < maxRounds; round++)
+  {
+    const int cx = io->curMvX, cy = io->curMvY; /* mvCurCenter */
+    int       bestDirect = -1;
+    for (idx = start; idx <= end; idx++)
+    {
+      const int direct = (idx + rounding) & mask;
+      const int ox = (pattern == 0 ? cross[direct][0] : diamond[direct][0]) * (1 << stepShift);
+      const int oy = (pattern == 0 ? cross[direct][1] : diamond[direct][1]) * (1 << stepShift);
+      const int mx = cx + ox, my = cy + oy;
+      const int px = io->tarPredX - (mx - io->curPredX), py = io->tarPredY - (my - io->curPredY); /* the mirrored MVD */
+      uint64_t  cost = vo_mv_cost(io->lambda, vo_mv_bits(vo_change_prec(mx, down), vo_change_prec(my, down), predX, predY, 0, 0));
+      cost += vo_smvd_cost(org, orgStride, refCur, refTar, refStride, io, mx, my, px, py);
+      if (cost < io->cost)
+      {
+        io->cost   = cost;
+        io->curMvX = mx;
+        io->curMvY = my;
+        io->tarMvX = px;
+        io->tarMvY = py;
+        bestDirect = direct;
+      }
+    }
+    if (bestDirect == -1) break;
+    {
+      const int step = pattern == 2 ? 2 - (bestDirect & 1) : 1;
+      start = bestDirect - step;
+      end   = bestDirect + step;
+    }
+  }
+}
+
+/* InterSearch::xSymmetricMotionEstimation — EncoderLib/InterSearch.cpp:4506-4518 */
+void vo_smvd_search(const vo_pel* org, int orgStride, const vo_pel* refCur, const vo_pel* refTar, int refStride, vo_smvd_io* io)
+{
+  const int stepShift = 2 + (io->imv == 3 ? 1 : (io->imv << 1)); /* MV_FRACTIONAL_BITS_DIFF + ... */
+  vo_smvd_refine(org, orgStride, refCur, refTar, refStride, io, 2, stepShift, 8 >> io->imv);
+  vo_smvd_refine(org, orgStride, refCur, refTar, refStride, io, 0, stepShift, 1);
+}
+
+/* ------------------------------------------------------------------------------------------------
  * Decoder-side MV refinement (DMVR): the search of one sub-block
  * ---------------------------------------------------------------------------------------------- */
 

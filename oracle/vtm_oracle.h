@@ -150,6 +150,27 @@ void vo_mctf_apply_motion(const vo_pel* src, int srcStride, int compW, int compH
 int  vo_mctf_error(const vo_pel* org, int orgStride, const vo_pel* ref, int refStride, int x, int y, int dx, int dy, int bs,
                    int bestError, int bitDepth);
 
+/* Symmetric MVD search, InterSearch::xSymmetricMotionEstimation (EncoderLib/InterSearch.cpp:4506-4518) with
+ * xSymmeticRefineMvSearch (:4393-4503) and xGetSymmetricCost (:4341-4391); default BCW weights, no MCTS constraint.
+ * Same field layout as RefSmvdIo in oracle/ref_harness.cpp. */
+typedef struct
+{
+  int      x, y, w, h;                 /* PU (= CU) luma rectangle                                              */
+  int      picW, picH, maxCuW, maxCuH; /* clipMv (clipMvInPic) arguments                                        */
+  int      bd;                         /* internal bit depth                                                    */
+  int      imv;                        /* cu.imv: 0 quarter, 1 integer, 2 four-sample, 3 half (alt. filter)     */
+  int      curPredX, curPredY;         /* rcMvCurPred, 1/16 sample                                              */
+  int      tarPredX, tarPredY;         /* rcMvTarPred                                                           */
+  int      curMvX, curMvY;             /* in/out rCurMvField.mv                                                 */
+  int      tarMvX, tarMvY;             /* in/out rTarMvField.mv                                                 */
+  int      clipBiPred;                 /* EncCfg::getClipForBiPredMeEnabled                                     */
+  int      useHad;                     /* !slice->getDisableSATDForRD()                                         */
+  double   lambda;                     /* RdCost::m_motionLambda                                                */
+  uint64_t cost;                       /* in/out ruiCost                                                        */
+} vo_smvd_io;
+/* refCur / refTar: sample (0,0) of the reference planes of eRefPicList and of the other list (border extended) */
+void vo_smvd_search(const vo_pel* org, int orgStride, const vo_pel* refCur, const vo_pel* refTar, int refStride, vo_smvd_io* io);
+
 /* Decoder-side MV refinement, one sub-block of InterPrediction::xProcessDMVR (CommonLib/InterPrediction.cpp:2098-2154):
  * bilinear predictions of both lists around the merge MVs, cost at the centre, 25 mirrored integer offsets, parametric
  * sub-sample step.  ref0 / ref1: sample (0,0) of the two reference planes (border extended); w, h in {8, 16}; MVs in 1/16

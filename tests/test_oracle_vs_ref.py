@@ -390,6 +390,58 @@ def test_tz_search_selective(oracle_lib, ref_lib, selective, fast):
 
 
 @pytest.mark.ref
+@pytest.mark.parametrize("imv", [0, 1, 2, 3])
+def test_smvd_search(oracle_lib, ref_lib, imv):
+    """xSymmetricMotionEstimation (InterSearch.cpp:4506-4518): the reference's own member against the restatement — every
+    AMVR precision (the half-sample one with the alternative filter), SATD and SAD, clipped bi-prediction targets, PU
+    shapes 8x8 .. 64x64, positions at the picture border with MVs that the clip moves, start costs that let the diamond
+    run several rounds."""
+    from tests.helpers import MARGIN, pad_plane
+    from vtm_b200.synth import make_pair
+    rng = np.random.default_rng(1000 + imv)
+    pic_w, pic_h = 256, 192
+    n = moved = 0
+    for seed in range(2):
+        cur, ref0, _ = make_pair(140 + seed, pic_w, pic_h, max_global=4, max_local=6, n_rects=4, sigma=4.0)
+        _, ref1, _ = make_pair(150 + seed, pic_w, pic_h, max_global=4, max_local=6, n_rects=4, sigma=4.0)
+        cur = np.ascontiguousarray(cur)
+        p0, p1 = pad_plane(ref0), pad_plane(ref1)
+        stride = p0.shape[1]
+        off = MARGIN * stride + MARGIN
+        ios = []
+        for w, h in [(8, 8), (16, 16), (32, 32), (64, 64), (16, 8), (8, 32), (64, 16), (32, 8)]:
+            for rep in range(4):
+                x = int(rng.integers(0, (pic_w - w) // 4 + 1)) * 4
+                y = int(rng.integers(0, (pic_h - h) // 4 + 1)) * 4
+                span = 12 * 16
+                if rep == 3:
+                    x, y = [0, pic_w - w][int(rng.integers(0, 2))], [0, pic_h - h][int(rng.integers(0, 2))]
+                    span = 170 * 16
+                io = B.SmvdIo()
+                io.x, io.y, io.w, io.h, io.picW, io.picH, io.maxCuW, io.maxCuH = x, y, w, h, pic_w, pic_h, 128, 128
+                io.bd, io.imv = 10, imv
+                unit = [4, 16, 64, 8][imv]                      # MVs and predictors on the AMVR grid, as the encoder has them
+                io.curPredX, io.curPredY, io.tarPredX, io.tarPredY = (int(rng.integers(-span, span + 1)) // unit * unit for _ in range(4))
+                dx, dy = (int(rng.integers(-6, 7)) * unit for _ in range(2))
+                io.curMvX, io.curMvY = io.curPredX + dx, io.curPredY + dy
+                io.tarMvX, io.tarMvY = io.tarPredX - dx, io.tarPredY - dy
+                io.clipBiPred, io.useHad = int(rep == 1), int(rep != 2)
+                io.lambda_ = [31.33, 8.5, 57.9, 31.33][rep]
+                io.cost = [2 ** 40, w * h * 12, w * h * 5, 2 ** 40][rep]      # finite start costs: some rounds find nothing better
+                ios.append(io)
+        arr = (B.SmvdIo * len(ios))(*ios)
+        want = (B.SmvdIo * len(ios))(*ios)
+        assert ref_lib.ref_smvd_search(B.ptr(cur), pic_w, B.ptr(p0), B.ptr(p1), stride, MARGIN, len(ios), want) == 0
+        for i in range(len(ios)):
+            start = arr[i].tuple()
+            oracle_lib.vo_smvd_search(B.ptr(cur, arr[i].y * pic_w + arr[i].x), pic_w, B.ptr(p0, off), B.ptr(p1, off), stride, C.byref(arr[i]))
+            assert arr[i].tuple() == want[i].tuple(), (seed, i, arr[i].w, arr[i].h, start)
+            n += 1
+            moved += arr[i].tuple()[:2] != start[:2]
+    assert n == 64 and moved > 30
+
+
+@pytest.mark.ref
 @pytest.mark.parametrize("bd", [10, 8])
 def test_dmvr_blocks(oracle_lib, ref_lib, bd):
     """The DMVR search of a sub-block (InterPrediction.cpp:2098-2154): the reference's own xPrefetch, xinitMC (bilinear
