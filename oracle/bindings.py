@@ -55,7 +55,7 @@ class SmvdIo(C.Structure):
                 ("maxCuW", C.c_int), ("maxCuH", C.c_int), ("bd", C.c_int), ("imv", C.c_int),
                 ("curPredX", C.c_int), ("curPredY", C.c_int), ("tarPredX", C.c_int), ("tarPredY", C.c_int),
                 ("curMvX", C.c_int), ("curMvY", C.c_int), ("tarMvX", C.c_int), ("tarMvY", C.c_int),
-                ("clipBiPred", C.c_int), ("useHad", C.c_int), ("lambda_", C.c_double), ("cost", C.c_uint64)]
+                ("clipBiPred", C.c_int), ("useHad", C.c_int), ("bcwIdx", C.c_int), ("lambda_", C.c_double), ("cost", C.c_uint64)]
 
     def tuple(self):
         return (self.curMvX, self.curMvY, self.tarMvX, self.tarMvY, self.cost)

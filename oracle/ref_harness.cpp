@@ -428,7 +428,7 @@ struct RefSmvdIo
 {
   int      x, y, w, h, picW, picH, maxCuW, maxCuH, bd, imv;
   int      curPredX, curPredY, tarPredX, tarPredY, curMvX, curMvY, tarMvX, tarMvY;
-  int      clipBiPred, useHad;
+  int      clipBiPred, useHad, bcwIdx;
   double   lambda;
   uint64_t cost;
 };
@@ -489,7 +489,7 @@ int ref_smvd_search(const int16_t* org, int orgStride, const int16_t* planeCur, 
     CodingUnit cu(CHROMA_420, Area(io.x, io.y, io.w, io.h));
     cu.imv    = io.imv;
     cu.affine = false;
-    cu.BcwIdx = BCW_DEFAULT;
+    cu.BcwIdx = (uint8_t) io.bcwIdx;
     cu.slice  = slice;
     PredictionUnit pu(CHROMA_420, Area(io.x, io.y, io.w, io.h));
     pu.cu = &cu;
@@ -501,7 +501,7 @@ int ref_smvd_search(const int16_t* org, int orgStride, const int16_t* planeCur, 
     Mv         curPred(io.curPredX, io.curPredY), tarPred(io.tarPredX, io.tarPredY);
     MvField    cur(Mv(io.curMvX, io.curMvY), 0), tar(Mv(io.tarMvX, io.tarMvY), 0);
     Distortion cost = io.cost;
-    p.xSymmetricMotionEstimation(pu, orgBuf, curPred, tarPred, REF_PIC_LIST_0, cur, tar, cost, BCW_DEFAULT);
+    p.xSymmetricMotionEstimation(pu, orgBuf, curPred, tarPred, REF_PIC_LIST_0, cur, tar, cost, io.bcwIdx);
     io.curMvX = cur.mv.hor;
     io.curMvY = cur.mv.ver;
     io.tarMvX = tar.mv.hor;

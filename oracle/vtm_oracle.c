@@ -1149,9 +1149,24 @@ void vo_tz_search(const vo_job* j, const vo_tz_params* p, int* mvx, int* mvy, ui
  * Symmetric MVD search (SMVD)
  * ---------------------------------------------------------------------------------------------- */
 
-/* InterSearch::xGetSymmetricCost — EncoderLib/InterSearch.cpp:4341-4391 (default BCW weights): both predictions with the
+/* AreaBuf<T>::removeWeightHighFreq — CommonLib/Buffer.h:418-472: the bi-prediction search target under a BCW weight,
+ * (org * 8 - other * (8 - w)) / w in 16-bit fixed point (g_BcwWeightBase = 8, Rom.cpp:188-190) */
+void vo_remove_weight_high_freq(vo_pel* dst, const vo_pel* src, int n, int clip, int bd, int bcwWeight)
+{
+  const int normalizer = ((1 << 16) + (bcwWeight > 0 ? (bcwWeight >> 1) : -(bcwWeight >> 1))) / bcwWeight;
+  const int weight0 = normalizer * 8, weight1 = (8 - bcwWeight) * normalizer, maxv = (1 << bd) - 1;
+  for (int i = 0; i < n; i++)
+  {
+    int v = (dst[i] * weight0 - src[i] * weight1 + (1 << 15)) >> 16;
+    if (clip) v = v < 0 ? 0 : (v > maxv ? maxv : v);
+    dst[i] = (vo_pel) v;
+  }
+}
+
+/* InterSearch::xGetSymmetricCost — EncoderLib/InterSearch.cpp:4341-4391: both predictions with the
  * 8-tap filter at the clipped MVs (an integer MV reads the picture directly, which is what the filter's copy gives),
- * 2*org - predA (removeHighFreq), SATD or SAD against predB, weighted by 0.5. */
+ * 2*org - predA (removeHighFreq; removeWeightHighFreq under a BCW weight), SATD or SAD against predB, weighted by
+ * xGetMEDistortionWeight (:7666-7676).  The searched list is list 0, so the target list's weight is g_BcwWeights[bcwIdx]. */
 static uint64_t vo_smvd_cost(const vo_pel* org, int orgStride, const vo_pel* refA, const vo_pel* refB, int refStride,
                              const vo_smvd_io* io, int mvAx, int mvAy, int mvBx, int mvBy)
 {
@@ -1163,9 +1178,17 @@ static uint64_t vo_smvd_cost(const vo_pel* org, int orgStride, const vo_pel* ref
   vo_mc_block(0, refA + (ptrdiff_t) io->y * refStride + io->x, refStride, io->w, io->h, mvAx, mvAy, 0, io->bd, io->imv == 3, predA, io->w);
   vo_mc_block(0, refB + (ptrdiff_t) io->y * refStride + io->x, refStride, io->w, io->h, mvBx, mvBy, 0, io->bd, io->imv == 3, predB, io->w);
   for (r = 0; r < io->h; r++) memcpy(tmp + r * io->w, org + (ptrdiff_t) r * orgStride, sizeof(vo_pel) * io->w);
-  vo_remove_high_freq(tmp, predA, io->w * io->h, io->clipBiPred, io->bd);
-  dist = io->useHad ? vo_satd(tmp, io->w, predB, io->w, io->w, io->h) : vo_sad(tmp, io->w, predB, io->w, io->w, io->h, 0);
-  return (uint64_t) floor(0.5 * (double) dist); /* xGetMEDistortionWeight(BCW_DEFAULT) */
+  {
+    static const int bcwWeights[5] = { -2, 3, 4, 5, 10 }; /* g_BcwWeights, BCW_DEFAULT = 2 */
+    const int        wTar          = bcwWeights[io->bcwIdx];
+    const double     fWeight       = io->bcwIdx == 2 ? 0.5 : fabs((double) wTar / 8.0);
+    if (io->bcwIdx == 2)
+      vo_remove_high_freq(tmp, predA, io->w * io->h, io->clipBiPred, io->bd);
+    else
+      vo_remove_weight_high_freq(tmp, predA, io->w * io->h, io->clipBiPred, io->bd, wTar);
+    dist = io->useHad ? vo_satd(tmp, io->w, predB, io->w, io->w, io->h) : vo_sad(tmp, io->w, predB, io->w, io->w, io->h, 0);
+    return (uint64_t) floor(fWeight * (double) dist);
+  }
 }
 
 /* InterSearch::xSymmeticRefineMvSearch — EncoderLib/InterSearch.cpp:4393-4503 (patterns 2 = diamond and 0 = cross, the two

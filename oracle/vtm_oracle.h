@@ -86,6 +86,7 @@ void vo_mc_block(int comp, const vo_pel* refAtBlk, int refStride, int w, int h, 
                  int useAltHpel, vo_pel* dst, int dstStride);
 void vo_add_avg(const vo_pel* s0, const vo_pel* s1, vo_pel* dst, int n, int bd);
 void vo_remove_high_freq(vo_pel* dst, const vo_pel* src, int n, int clip, int bd);
+void vo_remove_weight_high_freq(vo_pel* dst, const vo_pel* src, int n, int clip, int bd, int bcwWeight);
 
 /* tail of xMotionEstimation (InterSearch.cpp:3477-3484): final MV (quarter-pel), bits and cost */
 void vo_me_finish(const vo_job* j, const vo_result* r, double fWeight, uint32_t bitsIn, int* mvQx, int* mvQy,
@@ -151,7 +152,7 @@ int  vo_mctf_error(const vo_pel* org, int orgStride, const vo_pel* ref, int refS
                    int bestError, int bitDepth);
 
 /* Symmetric MVD search, InterSearch::xSymmetricMotionEstimation (EncoderLib/InterSearch.cpp:4506-4518) with
- * xSymmeticRefineMvSearch (:4393-4503) and xGetSymmetricCost (:4341-4391); default BCW weights, no MCTS constraint.
+ * xSymmeticRefineMvSearch (:4393-4503) and xGetSymmetricCost (:4341-4391); the searched list is list 0; no MCTS constraint.
  * Same field layout as RefSmvdIo in oracle/ref_harness.cpp. */
 typedef struct
 {
@@ -165,6 +166,7 @@ typedef struct
   int      tarMvX, tarMvY;             /* in/out rTarMvField.mv                                                 */
   int      clipBiPred;                 /* EncCfg::getClipForBiPredMeEnabled                                     */
   int      useHad;                     /* !slice->getDisableSATDForRD()                                         */
+  int      bcwIdx;                     /* cu.BcwIdx, 0..4 (2 = BCW_DEFAULT, equal weights)                       */
   double   lambda;                     /* RdCost::m_motionLambda                                                */
   uint64_t cost;                       /* in/out ruiCost                                                        */
 } vo_smvd_io;

@@ -393,7 +393,8 @@ def test_tz_search_selective(oracle_lib, ref_lib, selective, fast):
 @pytest.mark.parametrize("imv", [0, 1, 2, 3])
 def test_smvd_search(oracle_lib, ref_lib, imv):
     """xSymmetricMotionEstimation (InterSearch.cpp:4506-4518): the reference's own member against the restatement — every
-    AMVR precision (the half-sample one with the alternative filter), SATD and SAD, clipped bi-prediction targets, PU
+    AMVR precision (the half-sample one with the alternative filter), SATD and SAD, clipped bi-prediction targets, all five
+    BCW weights (removeWeightHighFreq, scalar with clipping and SIMD without), PU
     shapes 8x8 .. 64x64, positions at the picture border with MVs that the clip moves, start costs that let the diamond
     run several rounds."""
     from tests.helpers import MARGIN, pad_plane
@@ -426,6 +427,7 @@ def test_smvd_search(oracle_lib, ref_lib, imv):
                 io.curMvX, io.curMvY = io.curPredX + dx, io.curPredY + dy
                 io.tarMvX, io.tarMvY = io.tarPredX - dx, io.tarPredY - dy
                 io.clipBiPred, io.useHad = int(rep == 1), int(rep != 2)
+                io.bcwIdx = [2, 2, 2, 2, 0, 1, 3, 4][len(ios) % 8]           # BCW_DEFAULT and the four unequal weights
                 io.lambda_ = [31.33, 8.5, 57.9, 31.33][rep]
                 io.cost = [2 ** 40, w * h * 12, w * h * 5, 2 ** 40][rep]      # finite start costs: some rounds find nothing better
                 ios.append(io)
