@@ -117,6 +117,10 @@ def oracle():
                                    C.POINTER(C.c_uint64), C.POINTER(_I)]
         L.vo_mctf_apply_motion.argtypes = [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _I]
         L.vo_mctf_me.argtypes = [_P, _I, _P, _I, _I, _I, _I, _P]
+        L.vo_mctf_bilateral_weights.restype = None
+        L.vo_mctf_bilateral_weights.argtypes = [_I, _I, C.c_double, _I, _I, _I, _P]
+        L.vo_mctf_bilateral.restype = None
+        L.vo_mctf_bilateral.argtypes = [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, C.c_double, _I, _P, _I]
         L.vo_smvd_search.restype = None
         L.vo_smvd_search.argtypes = [_P, _I, _P, _P, _I, C.POINTER(SmvdIo)]
         L.vo_dmvr_block.restype = None
@@ -160,6 +164,8 @@ def ref():
         L.ref_tz_batch.restype = C.c_double
         L.ref_tz_batch.argtypes = [C.POINTER(Job), C.POINTER(TzParams), _I, _I, _P, _P]
         L.ref_mctf_apply_motion.argtypes = [_P, _P, _I, _I, _I, _P, _P, _P]
+        L.ref_mctf_bilateral.restype = None
+        L.ref_mctf_bilateral.argtypes = [_P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, C.c_double, _P, _P]
         L.ref_mctf_me.restype = C.c_double
         L.ref_mctf_me.argtypes = [_P, _I, _P, _I, _I, _I, _I, _P]
         L.ref_mc_blocks.argtypes = [_I, _P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, C.POINTER(C.c_double)]

@@ -27,6 +27,7 @@
 #include "CommonLib/InterPrediction.h"
 #include "CommonLib/Buffer.h"
 #include "CommonLib/Picture.h"
+#include <deque>
 #include "CommonLib/Slice.h"
 #include "CommonLib/CodingStructure.h"
 #include "EncoderLib/EncCfg.h"
@@ -802,6 +803,59 @@ void ref_mctf_apply_motion(const int16_t* luma, const int16_t* chroma, int lumaW
       mvs.get(x, y).set(m[0], m[1], m[2]);
     }
   tf.applyMotion(mvs, in, out);
+  for (int c = 0; c < 2; c++)
+  {
+    const int w = c ? lumaW / 2 : lumaW, h = c ? lumaH / 2 : lumaH;
+    int16_t*  d = c ? dstC : dstY;
+    for (int y = 0; y < h; y++) memcpy(d + (ptrdiff_t) y * w, out.bufs[c].buf + (ptrdiff_t) y * out.bufs[c].stride, sizeof(int16_t) * w);
+  }
+}
+
+// ---- EncTemporalFilter::bilateralFilter (EncTemporalFilter.cpp:555-623), the reference's own member ------------------
+// org / neighbours: luma (lumaW x lumaH) and chroma ((lumaW/2) x (lumaH/2), used for Cb and Cr) planes without border; mv:
+// numRefs vector fields of (lumaW/4) x (lumaH/4) entries {x, y, error} (ref_mctf_me); offsets: POC distances.
+// dstY / dstC: packed filtered planes (Cb).
+void ref_mctf_bilateral(const int16_t* orgY, const int16_t* orgC, const int16_t* const* refY, const int16_t* const* refC, int numRefs,
+                        const int32_t* mv, const int* offsets, int lumaW, int lumaH, int bitDepth, int qp, double overallStrength,
+                        int16_t* dstY, int16_t* dstC)
+{
+  EncTemporalFilter tf;
+  tf.m_chromaFormatIDC = CHROMA_420;
+  tf.m_sourceWidth     = lumaW;
+  tf.m_sourceHeight    = lumaH;
+  tf.m_QP              = qp;
+  tf.m_area            = Area(0, 0, lumaW, lumaH);
+  for (int i = 0; i < MAX_NUM_CHANNEL_TYPE; i++) tf.m_internalBitDepth[i] = bitDepth;
+  const int  pad = EncTemporalFilter::m_padding;
+  const Area area(0, 0, lumaW, lumaH);
+  auto load = [&](PelStorage& st, const int16_t* y, const int16_t* c) {
+    st.create(CHROMA_420, area, 0, pad);
+    for (int k = 0; k < 3; k++)
+    {
+      const int      w = k ? lumaW / 2 : lumaW, h = k ? lumaH / 2 : lumaH;
+      const int16_t* s = k ? c : y;
+      for (int r = 0; r < h; r++) memcpy(st.bufs[k].buf + (ptrdiff_t) r * st.bufs[k].stride, s + (ptrdiff_t) r * w, sizeof(int16_t) * w);
+    }
+    st.extendBorderPel(pad, pad);
+  };
+  PelStorage org, out;
+  load(org, orgY, orgC);
+  out.create(CHROMA_420, area, 0, pad);
+  std::deque<TemporalFilterSourcePicInfo> infos(numRefs);
+  const size_t fieldSize = (size_t) (lumaW / 4) * (lumaH / 4) * 3;
+  for (int i = 0; i < numRefs; i++)
+  {
+    load(infos[i].picBuffer, refY[i], refC[i]);
+    infos[i].origOffset = offsets[i];
+    infos[i].mvs.allocate(lumaW / 4, lumaH / 4);
+    for (int y = 0; y < lumaH / 4; y++)
+      for (int x = 0; x < lumaW / 4; x++)
+      {
+        const int32_t* m = mv + i * fieldSize + 3 * ((size_t) y * (lumaW / 4) + x);
+        infos[i].mvs.get(x, y).set(m[0], m[1], m[2]);
+      }
+  }
+  tf.bilateralFilter(org, infos, out, overallStrength);
   for (int c = 0; c < 2; c++)
   {
     const int w = c ? lumaW / 2 : lumaW, h = c ? lumaH / 2 : lumaH;

@@ -1145,6 +1145,70 @@ void vo_tz_search(const vo_job* j, const vo_tz_params* p, int* mvx, int* mvy, ui
   if (nProbes) *nProbes = s.probes;
 }
 
+/* EncTemporalFilter::bilateralFilter, the weighting of one component — EncoderLib/EncTemporalFilter.cpp:568-621.
+ * corrected[i]: the i-th neighbouring picture after applyMotion (vo_mctf_apply_motion), same geometry as org.
+ * The weight of a reference sample depends only on the integer difference refVal - orgVal, the component class and the
+ * POC distance class: w = (weightScaling * refStrength) * exp(-(diff * 1024 / 2^bd)^2 / (2 sigma^2)); the sums run in
+ * reference order in double precision, without contraction (the reference is built without FMA), one division, round(). */
+void vo_mctf_bilateral(const vo_pel* org, int orgStride, const vo_pel* const* corrected, int corrStride, const int* origOffset,
+                       int numRefs, int w, int h, int isChroma, int qp, double overallStrength, int bitDepth, vo_pel* dst, int dstStride)
+{
+  static const double refStrengths[3][2] = { { 0.85, 0.60 }, { 1.20, 1.00 }, { 0.30, 0.30 } }; /* m_refStrengths, :72-78 */
+  const int           range = 2;                                                             /* m_range */
+  const int           row   = numRefs == range * 2 ? 0 : (numRefs == range ? 1 : 2);
+  const double lumaSigmaSq = (qp - 10.0) * (qp - 10.0) * 9.0, chromaSigmaSq = 30 * 30;      /* m_sigmaZeroPoint, m_sigmaMultiplier */
+  const double sigmaSq = isChroma ? chromaSigmaSq : lumaSigmaSq;
+  const double weightScaling = overallStrength * (isChroma ? 0.55 : 0.4);                    /* m_chromaFactor */
+  const int    maxv = (1 << bitDepth) - 1;
+  const double bitDepthDiffWeighting = 1024.0 / (maxv + 1);
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++)
+    {
+      const int       orgVal = org[(ptrdiff_t) y * orgStride + x];
+      volatile double sum = 1.0, newVal = (double) orgVal; /* volatile: every product and sum rounded to double on its own */
+      for (int i = 0; i < numRefs; i++)
+      {
+        const int    refVal = corrected[i][(ptrdiff_t) y * corrStride + x];
+        double       diff   = (double) (refVal - orgVal);
+        int          a      = origOffset[i] < 0 ? -origOffset[i] : origOffset[i];
+        const int    index  = a - 1 < 1 ? a - 1 : 1;
+        double       diffSq, weight;
+        volatile double prod;
+        diff *= bitDepthDiffWeighting;
+        diffSq = diff * diff;
+        weight = weightScaling * refStrengths[row][index] * exp(-diffSq / (2 * sigmaSq));
+        prod   = weight * refVal;
+        newVal = newVal + prod;
+        sum    = sum + weight;
+      }
+      {
+        const double q = newVal / sum;
+        int          v = (int) (vo_pel) round(q);
+        dst[(ptrdiff_t) y * dstStride + x] = (vo_pel) (v < 0 ? 0 : (v > maxv ? maxv : v));
+      }
+    }
+}
+
+/* The weights of vo_mctf_bilateral as a table over |refVal - orgVal| (they depend on nothing else within a component and a
+ * POC-distance class): what a device implementation receives from the host instead of evaluating exp() itself, so that
+ * its double-precision sums are those of the reference bit for bit.  table: 1 << bitDepth entries. */
+void vo_mctf_bilateral_weights(int isChroma, int qp, double overallStrength, int bitDepth, int numRefs, int index, double* table)
+{
+  static const double refStrengths[3][2] = { { 0.85, 0.60 }, { 1.20, 1.00 }, { 0.30, 0.30 } };
+  const int    row = numRefs == 4 ? 0 : (numRefs == 2 ? 1 : 2);
+  const double sigmaSq = isChroma ? 30 * 30 : (qp - 10.0) * (qp - 10.0) * 9.0;
+  const double weightScaling = overallStrength * (isChroma ? 0.55 : 0.4);
+  const double bitDepthDiffWeighting = 1024.0 / (1 << bitDepth);
+  for (int d = 0; d < (1 << bitDepth); d++)
+  {
+    double diff = (double) d;
+    double diffSq;
+    diff *= bitDepthDiffWeighting;
+    diffSq   = diff * diff; /* (-d)^2 == d^2 exactly */
+    table[d] = weightScaling * refStrengths[row][index] * exp(-diffSq / (2 * sigmaSq));
+  }
+}
+
 /* ------------------------------------------------------------------------------------------------
  * Symmetric MVD search (SMVD)
  * ---------------------------------------------------------------------------------------------- */

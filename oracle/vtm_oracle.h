@@ -151,6 +151,14 @@ void vo_mctf_apply_motion(const vo_pel* src, int srcStride, int compW, int compH
 int  vo_mctf_error(const vo_pel* org, int orgStride, const vo_pel* ref, int refStride, int x, int y, int dx, int dy, int bs,
                    int bestError, int bitDepth);
 
+/* EncTemporalFilter::bilateralFilter (EncoderLib/EncTemporalFilter.cpp:555-623), the weighting of one component over the
+ * motion-compensated neighbours (corrected[i], from vo_mctf_apply_motion); origOffset[i]: POC distance of neighbour i */
+void vo_mctf_bilateral(const vo_pel* org, int orgStride, const vo_pel* const* corrected, int corrStride, const int* origOffset,
+                       int numRefs, int w, int h, int isChroma, int qp, double overallStrength, int bitDepth, vo_pel* dst, int dstStride);
+
+/* the same weights as a table over |refVal - orgVal| for one POC-distance class (index = min(1, |origOffset| - 1)) */
+void vo_mctf_bilateral_weights(int isChroma, int qp, double overallStrength, int bitDepth, int numRefs, int index, double* table);
+
 /* Symmetric MVD search, InterSearch::xSymmetricMotionEstimation (EncoderLib/InterSearch.cpp:4506-4518) with
  * xSymmeticRefineMvSearch (:4393-4503) and xGetSymmetricCost (:4341-4391); the searched list is list 0; no MCTS constraint.
  * Same field layout as RefSmvdIo in oracle/ref_harness.cpp. */

@@ -390,6 +390,75 @@ def test_tz_search_selective(oracle_lib, ref_lib, selective, fast):
 
 
 @pytest.mark.ref
+@pytest.mark.parametrize("num_refs,bd,qp,strength", [(4, 10, 32, 0.95), (2, 10, 27, 1.5), (3, 8, 37, 0.95), (1, 10, 22, 1.5)])
+def test_mctf_bilateral(oracle_lib, ref_lib, num_refs, bd, qp, strength):
+    """EncTemporalFilter::bilateralFilter (EncTemporalFilter.cpp:555-623): the reference's own member (applyMotion of every
+    neighbour + the weighting, luma and 4:2:0 chroma) against vo_mctf_apply_motion + vo_mctf_bilateral — every sample equal.
+    The weights are double-precision exp() values; the restatement sums them in the reference's order."""
+    from tests.helpers import pad_plane
+    from vtm_b200.synth import make_pair
+    w, h = 208, 120
+    rng = np.random.default_rng(1100 + num_refs)
+    org, _, _ = make_pair(160, w, h, max_global=5, max_local=8, n_rects=3, sigma=5.0, bit_depth=bd)
+    org = np.ascontiguousarray(org)
+    org_c = np.ascontiguousarray(rng.integers(0, 1 << bd, (h // 2, w // 2), dtype=np.int16))
+    offsets = [[-1], [-1, 1], [-2, -1, 1], [-2, -1, 1, 2]][num_refs - 1]
+    refs_y, refs_c, fields = [], [], []
+    orgp = pad_plane(org, 128)
+    stride = orgp.shape[1]
+    off = 128 * stride + 128
+    for k in range(num_refs):
+        r = np.clip(np.roll(org.astype(np.int32), (k + 1, -2 * k - 1), (0, 1)) + np.rint(rng.normal(0, 3 + 2 * k, org.shape)).astype(np.int32),
+                    0, (1 << bd) - 1).astype(np.int16)
+        c = np.clip(org_c.astype(np.int32) + np.rint(rng.normal(0, 6, org_c.shape)).astype(np.int32), 0, (1 << bd) - 1).astype(np.int16)
+        refs_y.append(np.ascontiguousarray(r))
+        refs_c.append(np.ascontiguousarray(c))
+        mv = np.zeros((h // 4, w // 4, 3), np.int32)
+        rp = pad_plane(refs_y[-1], 128)
+        ref_lib.ref_mctf_me(B.ptr(orgp, off), stride, B.ptr(rp, off), stride, w, h, bd, C.c_void_p(mv.ctypes.data))
+        fields.append(mv)
+    mvs = np.ascontiguousarray(np.stack(fields))
+    ptrs_y = (C.c_void_p * num_refs)(*[a.ctypes.data for a in refs_y])
+    ptrs_c = (C.c_void_p * num_refs)(*[a.ctypes.data for a in refs_c])
+    offs = (C.c_int * num_refs)(*offsets)
+    want_y, want_c = np.zeros((h, w), np.int16), np.zeros((h // 2, w // 2), np.int16)
+    ref_lib.ref_mctf_bilateral(B.ptr(org), B.ptr(org_c), ptrs_y, ptrs_c, num_refs, C.c_void_p(mvs.ctypes.data), offs, w, h, bd, qp,
+                               strength, B.ptr(want_y), B.ptr(want_c))
+    # restatement: motion-compensate every neighbour, then weight
+    for comp, (o, planes, cw, ch, cs) in enumerate([(org, refs_y, w, h, 0), (org_c, refs_c, w // 2, h // 2, 1)]):
+        corr = []
+        for k in range(num_refs):
+            pp = pad_plane(planes[k], 128 >> cs)
+            m = 128 >> cs
+            d = np.zeros((ch, cw), np.int16)
+            oracle_lib.vo_mctf_apply_motion(B.ptr(pp, m * pp.shape[1] + m), pp.shape[1], cw, ch, cs, cs, C.c_void_p(mvs[k].ctypes.data),
+                                            w // 4, bd, B.ptr(d), cw)
+            corr.append(d)
+        cptrs = (C.c_void_p * num_refs)(*[a.ctypes.data for a in corr])
+        got = np.zeros((ch, cw), np.int16)
+        oracle_lib.vo_mctf_bilateral(B.ptr(o), cw, cptrs, cw, offs, num_refs, cw, ch, comp, qp, strength, bd, B.ptr(got), cw)
+        want = want_y if comp == 0 else want_c
+        assert np.array_equal(got, want), (comp, np.argwhere(got != want)[:5])
+        assert (got != o).mean() > 0.2          # the filter does change the picture
+        # the table-driven form a device implementation would run (weights looked up by |ref - org|, IEEE double products and
+        # sums in reference order, one division, round half away from zero) gives the same samples
+        tables = []
+        for index in (0, 1):
+            tb = np.zeros(1 << bd, np.float64)
+            oracle_lib.vo_mctf_bilateral_weights(comp, qp, strength, bd, num_refs, index, C.c_void_p(tb.ctypes.data))
+            tables.append(tb)
+        new_val, wsum = o.astype(np.float64), np.ones(o.shape, np.float64)
+        for k in range(num_refs):
+            wk = tables[min(1, abs(offsets[k]) - 1)][np.abs(corr[k].astype(np.int32) - o.astype(np.int32))]
+            new_val = new_val + wk * corr[k].astype(np.float64)
+            wsum = wsum + wk
+        q = new_val / wsum
+        t = np.trunc(q)
+        lut = np.clip(t + (q - t >= 0.5), 0, (1 << bd) - 1).astype(np.int16)
+        assert np.array_equal(lut, want), comp
+
+
+@pytest.mark.ref
 @pytest.mark.parametrize("imv", [0, 1, 2, 3])
 def test_smvd_search(oracle_lib, ref_lib, imv):
     """xSymmetricMotionEstimation (InterSearch.cpp:4506-4518): the reference's own member against the restatement — every
