@@ -422,6 +422,104 @@ int ref_dmvr_blocks(const int16_t* plane0, const int16_t* plane1, int planeStrid
   return 0;
 }
 
+// ---- luma prediction after DMVR: the reference's own xPrefetch, xPad and xFinalPaddedMCForDMVR (InterPrediction.cpp:1664-1730,
+// 1845-1917) per sub-block, as xProcessDMVR drives them (:2156-2181).  blk as ref_dmvr_blocks; mvd: n x 2 (mvdL0SubPu, 1/16
+// sample).  dst0 / dst1: the two lists' predictions (14-bit intermediates), blocks packed back to back (row stride = w).
+int ref_dmvr_final_luma(const int16_t* plane0, const int16_t* plane1, int planeStride, int lumaW, int lumaH, int margin, int n,
+                        const int32_t* blk, const int32_t* mvd, int bitDepth, int16_t* dst0, int16_t* dst1)
+{
+  Probe&  p = probe();
+  Picture pics[2];
+  for (int l = 0; l < 2; l++)
+  {
+    Picture& pic = pics[l];
+    pic.create(CHROMA_420, Size(lumaW, lumaH), 128, 128 + 16, false, 0);
+    pic.unscaledPic = &pic;
+    PelBuf reco = pic.getRecoBuf(COMPONENT_Y);
+    if (margin > (int) pic.margin) return -1;
+    const int16_t* plane = l ? plane1 : plane0;
+    for (int y = -margin; y < lumaH + margin; y++)
+      memcpy(reco.buf + (ptrdiff_t) y * reco.stride - margin, plane + (ptrdiff_t) (y + margin) * planeStride,
+             sizeof(int16_t) * (lumaW + 2 * margin));
+    for (int c = 1; c < 3; c++)   // chroma is predicted too (and ignored here): defined samples
+    {
+      PelBuf cb = pic.getRecoBuf(ComponentID(c));
+      for (int y = -(int) (pic.margin >> 1); y < lumaH / 2 + (int) (pic.margin >> 1); y++)
+        memset(cb.buf + (ptrdiff_t) y * cb.stride - (pic.margin >> 1), 0, sizeof(int16_t) * (lumaW / 2 + pic.margin));
+    }
+  }
+  PPS pps;
+  pps.setPicWidthInLumaSamples(lumaW);
+  pps.setPicHeightInLumaSamples(lumaH);
+  SPS sps;
+  std::vector<uint64_t> shell((sizeof(CodingStructure) + 7) / 8, 0);
+  CodingStructure* cs = reinterpret_cast<CodingStructure*>(shell.data());
+  cs->sps = &sps;
+  cs->pps = &pps;
+  Slice* slice = new Slice();
+  for (int l = 0; l < 2; l++)
+  {
+    slice->m_apcRefPicList[l][0] = &pics[l];
+    slice->m_scalingRatio[l][0]  = SCALE_1X;
+  }
+  for (int c = 0; c < MAX_NUM_COMPONENT; c++) slice->m_clpRngs.comp[c] = makeClp(bitDepth);
+  cs->slice = slice;
+  clipMv = clipMvInPic;
+  PelStorage pred[2];
+  for (int l = 0; l < 2; l++) pred[l].create(UnitArea(CHROMA_420, Area(0, 0, 16, 16)));
+  for (int i = 0; i < n; i++)
+  {
+    const int32_t* b = blk + 8 * i;
+    const int dx = b[2], dy = b[3];
+    CodingUnit cu;
+    cu.imv    = IMV_OFF;
+    cu.affine = false;
+    cu.slice  = slice;
+    PredictionUnit pu(CHROMA_420, Area(b[0], b[1], dx, dy));
+    pu.cu = &cu;
+    pu.cs = cs;
+    pu.refIdx[0] = pu.refIdx[1] = 0;
+    const Mv mergeMv[2] = { Mv(b[4], b[5]), Mv(b[6], b[7]) };
+    pu.mv[0] = mergeMv[0];
+    pu.mv[1] = mergeMv[1];
+    // the prefetch buffers as xProcessDMVR sets them up (:2063-2078), all three components
+    p.m_cYuvRefBuffDMVRL0 = PelUnitBuf(CHROMA_420, PelBuf(p.m_cRefSamplesDMVRL0[0], dx, dx, dy), PelBuf(p.m_cRefSamplesDMVRL0[1], dx / 2, dx / 2, dy / 2),
+                                       PelBuf(p.m_cRefSamplesDMVRL0[2], dx / 2, dx / 2, dy / 2));
+    p.m_cYuvRefBuffDMVRL1 = PelUnitBuf(CHROMA_420, PelBuf(p.m_cRefSamplesDMVRL1[0], dx, dx, dy), PelBuf(p.m_cRefSamplesDMVRL1[1], dx / 2, dx / 2, dy / 2),
+                                       PelBuf(p.m_cRefSamplesDMVRL1[2], dx / 2, dx / 2, dy / 2));
+    p.xPrefetch(pu, p.m_cYuvRefBuffDMVRL0, REF_PIC_LIST_0, 1);
+    p.xPrefetch(pu, p.m_cYuvRefBuffDMVRL1, REF_PIC_LIST_1, 1);
+    const Mv   d(mvd[2 * i], mvd[2 * i + 1]);
+    const bool moved = d != Mv(0, 0);
+    if (moved)
+    {
+      p.xPrefetch(pu, p.m_cYuvRefBuffDMVRL0, REF_PIC_LIST_0, 0);
+      p.xPrefetch(pu, p.m_cYuvRefBuffDMVRL1, REF_PIC_LIST_1, 0);
+      p.xPad(pu, p.m_cYuvRefBuffDMVRL0, REF_PIC_LIST_0);
+      p.xPad(pu, p.m_cYuvRefBuffDMVRL1, REF_PIC_LIST_1);
+    }
+    pu.mv[0] = mergeMv[0] + d;
+    pu.mv[1] = mergeMv[1] - d;
+    pu.mv[0].clipToStorageBitDepth();
+    pu.mv[1].clipToStorageBitDepth();
+    const UnitArea rel(CHROMA_420, Area(0, 0, dx, dy));
+    PelUnitBuf s0 = pred[0].getBuf(rel), s1 = pred[1].getBuf(rel);
+    p.xFinalPaddedMCForDMVR(pu, s0, s1, p.m_cYuvRefBuffDMVRL0, p.m_cYuvRefBuffDMVRL1, false, mergeMv, moved);
+    for (int y = 0; y < dy; y++)
+    {
+      memcpy(dst0 + (ptrdiff_t) y * dx, s0.Y().buf + (ptrdiff_t) y * s0.Y().stride, sizeof(int16_t) * dx);
+      memcpy(dst1 + (ptrdiff_t) y * dx, s1.Y().buf + (ptrdiff_t) y * s1.Y().stride, sizeof(int16_t) * dx);
+    }
+    dst0 += dx * dy;
+    dst1 += dx * dy;
+  }
+  for (int l = 0; l < 2; l++) pred[l].destroy();
+  delete slice;
+  pics[0].destroy();
+  pics[1].destroy();
+  return 0;
+}
+
 // ---- symmetric MVD search: the reference's own InterSearch::xSymmetricMotionEstimation (InterSearch.cpp:4506-4518) ------
 // planeCur / planeTar: luma planes of the reference pictures of eRefPicList (list 0 here) and of the other list (`margin`
 // border samples on each side already extended); org: the original block.  Same field layout as vo_smvd_io.

@@ -1441,6 +1441,34 @@ void vo_dmvr_block(const vo_pel* ref0, const vo_pel* ref1, int refStride, int x,
   out[3] = notZero;
 }
 
+/* The luma prediction of one list after DMVR — xFinalPaddedMCForDMVR (InterPrediction.cpp:1845-1917) over the buffer xPrefetch
+ * filled (:1664-1708: the (w+7) x (h+7) window at the integer part of clip(mergeMv - 3 samples)) and xPad extended by two
+ * replicated samples on every side (:1710-1730, paddingCore Buffer.cpp:340-364): the 8-tap filter of xPredInterBlk (bi = true,
+ * 14-bit intermediates) at the fraction of clip(refinedMv), reading the window with clamped coordinates instead of the
+ * picture.  ref: sample (0,0) of the reference plane; dst stride w. */
+void vo_dmvr_final_luma(const vo_pel* ref, int refStride, int x, int y, int w, int h, int mergeX, int mergeY, int refinedX,
+                        int refinedY, int picW, int picH, int maxCuW, int maxCuH, int bd, vo_pel* dst)
+{
+  vo_pel    patch[(16 + 7) * (16 + 7)];
+  const int pw = w + 7, ph = h + 7;
+  int       cx = mergeX - 48, cy = mergeY - 48, fx = refinedX, fy = refinedY, r, c;
+  vo_clip_mv(&cx, &cy, x, y, picW, picH, maxCuW, maxCuH); /* xPrefetch */
+  vo_clip_mv(&fx, &fy, x, y, picW, picH, maxCuW, maxCuH); /* cMvClipped: only its fraction is used */
+  {
+    const vo_pel* win = ref + (ptrdiff_t) (y + (cy >> 4)) * refStride + x + (cx >> 4); /* window origin */
+    const int     bx = 3 + ((refinedX >> 4) - (mergeX >> 4)), by = 3 + ((refinedY >> 4) - (mergeY >> 4)); /* block origin in the window */
+    for (r = 0; r < ph; r++)
+      for (c = 0; c < pw; c++)
+      {
+        int wr = by - 3 + r, wc = bx - 3 + c; /* window coordinates of the filter's support */
+        wr = wr < 0 ? 0 : (wr > h + 6 ? h + 6 : wr);
+        wc = wc < 0 ? 0 : (wc > w + 6 ? w + 6 : wc);
+        patch[r * pw + c] = win[(ptrdiff_t) wr * refStride + wc];
+      }
+  }
+  vo_mc_block(0, patch + 3 * pw + 3, pw, w, h, fx & 15, fy & 15, 1, bd, 0, dst, w);
+}
+
 /* ------------------------------------------------------------------------------------------------
  * GOP-based temporal filter: motion estimation
  * ---------------------------------------------------------------------------------------------- */

@@ -188,6 +188,11 @@ void vo_smvd_search(const vo_pel* org, int orgStride, const vo_pel* refCur, cons
 void vo_dmvr_block(const vo_pel* ref0, const vo_pel* ref1, int refStride, int x, int y, int w, int h, int mv0x, int mv0y, int mv1x,
                    int mv1y, int picW, int picH, int maxCuW, int maxCuH, int bd, int32_t* out);
 
+/* luma prediction (14-bit intermediates, bi = true) of one list after DMVR: xPrefetch + xPad + xFinalPaddedMCForDMVR
+ * (CommonLib/InterPrediction.cpp:1664-1730, 1845-1917); merge MV and refined MV (merge +- mvdL0SubPu) in 1/16 sample */
+void vo_dmvr_final_luma(const vo_pel* ref, int refStride, int x, int y, int w, int h, int mergeX, int mergeY, int refinedX,
+                        int refinedY, int picW, int picH, int maxCuW, int maxCuH, int bd, vo_pel* dst);
+
 #ifdef __cplusplus
 }
 #endif

@@ -390,6 +390,42 @@ def test_tz_search_selective(oracle_lib, ref_lib, selective, fast):
 
 
 @pytest.mark.ref
+@pytest.mark.parametrize("bd", [10, 8])
+def test_dmvr_final_luma(oracle_lib, ref_lib, bd):
+    """The luma prediction of both lists after DMVR (xPrefetch + xPad + xFinalPaddedMCForDMVR, InterPrediction.cpp:1664-1730,
+    1845-1917): the reference's own members against the restatement (8-tap filter over the prefetched window with clamped
+    coordinates), with the refinements the reference's own search found — integer moves of up to two samples, sub-sample
+    steps, unmoved blocks — and MVs the clip moves at the picture border."""
+    from tests.helpers import MARGIN, dmvr_cases, pad_plane
+    from vtm_b200.synth import make_pair
+    rng = np.random.default_rng(1200 + bd)
+    pic_w, pic_h = 256, 192
+    r0, r1, _ = make_pair(170, pic_w, pic_h, max_global=3, max_local=3, n_rects=4, sigma=4.0, bit_depth=bd)
+    p0, p1 = pad_plane(r0), pad_plane(r1)
+    stride = p0.shape[1]
+    blk = dmvr_cases(rng, pic_w, pic_h, 500)
+    res = np.zeros((len(blk), 4), np.int32)
+    assert ref_lib.ref_dmvr_blocks(B.ptr(p0), B.ptr(p1), stride, pic_w, pic_h, MARGIN, len(blk), C.c_void_p(blk.ctypes.data), bd,
+                                   C.c_void_p(res.ctypes.data)) == 0
+    mvd = np.ascontiguousarray(res[:, :2])
+    mvd[::5] = 0                                                   # unmoved blocks: no padding, luma still read from the window
+    total = int((blk[:, 2] * blk[:, 3]).sum())
+    want0, want1 = np.zeros(total, np.int16), np.zeros(total, np.int16)
+    assert ref_lib.ref_dmvr_final_luma(B.ptr(p0), B.ptr(p1), stride, pic_w, pic_h, MARGIN, len(blk), C.c_void_p(blk.ctypes.data),
+                                       C.c_void_p(mvd.ctypes.data), bd, B.ptr(want0), B.ptr(want1)) == 0
+    off, pos = MARGIN * stride + MARGIN, 0
+    for b, d in zip(blk, mvd):
+        x, y, w, h, m0x, m0y, m1x, m1y = (int(v) for v in b)
+        got = np.zeros(w * h, np.int16)
+        for plane, want, (mx, my), sgn in ((p0, want0, (m0x, m0y), 1), (p1, want1, (m1x, m1y), -1)):
+            oracle_lib.vo_dmvr_final_luma(B.ptr(plane, off), stride, x, y, w, h, mx, my, mx + sgn * int(d[0]), my + sgn * int(d[1]),
+                                          pic_w, pic_h, 128, 128, bd, B.ptr(got))
+            assert np.array_equal(got, want[pos:pos + w * h]), (b.tolist(), d.tolist(), sgn)
+        pos += w * h
+    assert (np.abs(mvd) >= 16).any(axis=1).sum() > 50 and (mvd % 16 != 0).any(axis=1).sum() > 50
+
+
+@pytest.mark.ref
 @pytest.mark.parametrize("num_refs,bd,qp,strength", [(4, 10, 32, 0.95), (2, 10, 27, 1.5), (3, 8, 37, 0.95), (1, 10, 22, 1.5)])
 def test_mctf_bilateral(oracle_lib, ref_lib, num_refs, bd, qp, strength):
     """EncTemporalFilter::bilateralFilter (EncTemporalFilter.cpp:555-623): the reference's own member (applyMotion of every
