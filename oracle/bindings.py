@@ -123,6 +123,8 @@ def oracle():
         L.vo_mctf_bilateral.argtypes = [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, C.c_double, _I, _P, _I]
         L.vo_smvd_search.restype = None
         L.vo_smvd_search.argtypes = [_P, _I, _P, _P, _I, C.POINTER(SmvdIo)]
+        L.vo_dmvr_final_chroma.restype = None
+        L.vo_dmvr_final_chroma.argtypes = [_P, _I] + [_I] * 13 + [_P]
         L.vo_dmvr_final_luma.restype = None
         L.vo_dmvr_final_luma.argtypes = [_P, _I] + [_I] * 13 + [_P]
         L.vo_dmvr_block.restype = None
@@ -172,6 +174,7 @@ def ref():
         L.ref_mctf_me.argtypes = [_P, _I, _P, _I, _I, _I, _I, _P]
         L.ref_mc_blocks.argtypes = [_I, _P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, C.POINTER(C.c_double)]
         L.ref_smvd_search.argtypes = [_P, _I, _P, _P, _I, _I, _I, C.POINTER(SmvdIo)]
+        L.ref_dmvr_final.argtypes = [_P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P]
         L.ref_dmvr_final_luma.argtypes = [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P]
         L.ref_dmvr_blocks.argtypes = [_P, _P, _I, _I, _I, _I, _I, _P, _I, _P]
         L.ref_add_avg.argtypes = [_P, _P, _P, _I, _I, _I]

@@ -425,8 +425,19 @@ int ref_dmvr_blocks(const int16_t* plane0, const int16_t* plane1, int planeStrid
 // ---- luma prediction after DMVR: the reference's own xPrefetch, xPad and xFinalPaddedMCForDMVR (InterPrediction.cpp:1664-1730,
 // 1845-1917) per sub-block, as xProcessDMVR drives them (:2156-2181).  blk as ref_dmvr_blocks; mvd: n x 2 (mvdL0SubPu, 1/16
 // sample).  dst0 / dst1: the two lists' predictions (14-bit intermediates), blocks packed back to back (row stride = w).
+// chroma0 / chroma1 (optional): Cb planes of the two pictures with margin/2 border samples, row stride chromaStride;
+// dstC0 / dstC1: their predictions ((w/2) x (h/2) per block).
+int ref_dmvr_final(const int16_t* plane0, const int16_t* plane1, int planeStride, const int16_t* chroma0, const int16_t* chroma1,
+                   int chromaStride, int lumaW, int lumaH, int margin, int n, const int32_t* blk, const int32_t* mvd, int bitDepth,
+                   int16_t* dst0, int16_t* dst1, int16_t* dstC0, int16_t* dstC1);
 int ref_dmvr_final_luma(const int16_t* plane0, const int16_t* plane1, int planeStride, int lumaW, int lumaH, int margin, int n,
                         const int32_t* blk, const int32_t* mvd, int bitDepth, int16_t* dst0, int16_t* dst1)
+{
+  return ref_dmvr_final(plane0, plane1, planeStride, nullptr, nullptr, 0, lumaW, lumaH, margin, n, blk, mvd, bitDepth, dst0, dst1, nullptr, nullptr);
+}
+int ref_dmvr_final(const int16_t* plane0, const int16_t* plane1, int planeStride, const int16_t* chroma0, const int16_t* chroma1,
+                   int chromaStride, int lumaW, int lumaH, int margin, int n, const int32_t* blk, const int32_t* mvd, int bitDepth,
+                   int16_t* dst0, int16_t* dst1, int16_t* dstC0, int16_t* dstC1)
 {
   Probe&  p = probe();
   Picture pics[2];
@@ -441,11 +452,16 @@ int ref_dmvr_final_luma(const int16_t* plane0, const int16_t* plane1, int planeS
     for (int y = -margin; y < lumaH + margin; y++)
       memcpy(reco.buf + (ptrdiff_t) y * reco.stride - margin, plane + (ptrdiff_t) (y + margin) * planeStride,
              sizeof(int16_t) * (lumaW + 2 * margin));
-    for (int c = 1; c < 3; c++)   // chroma is predicted too (and ignored here): defined samples
+    for (int c = 1; c < 3; c++)   // chroma is predicted too: defined samples (zero without chroma planes)
     {
       PelBuf cb = pic.getRecoBuf(ComponentID(c));
       for (int y = -(int) (pic.margin >> 1); y < lumaH / 2 + (int) (pic.margin >> 1); y++)
         memset(cb.buf + (ptrdiff_t) y * cb.stride - (pic.margin >> 1), 0, sizeof(int16_t) * (lumaW / 2 + pic.margin));
+      const int16_t* cp = l ? chroma1 : chroma0;
+      const int      cm = margin / 2;
+      if (cp)
+        for (int y = -cm; y < lumaH / 2 + cm; y++)
+          memcpy(cb.buf + (ptrdiff_t) y * cb.stride - cm, cp + (ptrdiff_t) (y + cm) * chromaStride, sizeof(int16_t) * (lumaW / 2 + 2 * cm));
     }
   }
   PPS pps;
@@ -512,6 +528,16 @@ int ref_dmvr_final_luma(const int16_t* plane0, const int16_t* plane1, int planeS
     }
     dst0 += dx * dy;
     dst1 += dx * dy;
+    if (dstC0 && dstC1)
+    {
+      for (int y = 0; y < dy / 2; y++)
+      {
+        memcpy(dstC0 + (ptrdiff_t) y * (dx / 2), s0.Cb().buf + (ptrdiff_t) y * s0.Cb().stride, sizeof(int16_t) * (dx / 2));
+        memcpy(dstC1 + (ptrdiff_t) y * (dx / 2), s1.Cb().buf + (ptrdiff_t) y * s1.Cb().stride, sizeof(int16_t) * (dx / 2));
+      }
+      dstC0 += (dx / 2) * (dy / 2);
+      dstC1 += (dx / 2) * (dy / 2);
+    }
   }
   for (int l = 0; l < 2; l++) pred[l].destroy();
   delete slice;

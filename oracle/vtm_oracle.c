@@ -1469,6 +1469,32 @@ void vo_dmvr_final_luma(const vo_pel* ref, int refStride, int x, int y, int w, i
   vo_mc_block(0, patch + 3 * pw + 3, pw, w, h, fx & 15, fy & 15, 1, bd, 0, dst, w);
 }
 
+/* The same for a 4:2:0 chroma component when the block moved (an unmoved block reads the picture directly, which is the
+ * plain xPredInterBlk): window of (w/2+3) x (h/2+3) chroma samples at the integer part (1/32 units) of clip(mergeMv - 1
+ * chroma sample), padded by one sample, 4-tap filter.  x, y, w, h: the LUMA rectangle; ref: sample (0,0) of the chroma plane. */
+void vo_dmvr_final_chroma(const vo_pel* ref, int refStride, int x, int y, int w, int h, int mergeX, int mergeY, int refinedX,
+                          int refinedY, int picW, int picH, int maxCuW, int maxCuH, int bd, vo_pel* dst)
+{
+  vo_pel    patch[(8 + 3) * (8 + 3)];
+  const int cw = w >> 1, ch = h >> 1, pw = cw + 3, ph = ch + 3;
+  int       cx = mergeX - 32, cy = mergeY - 32, fx = refinedX, fy = refinedY, r, c;
+  vo_clip_mv(&cx, &cy, x, y, picW, picH, maxCuW, maxCuH);
+  vo_clip_mv(&fx, &fy, x, y, picW, picH, maxCuW, maxCuH);
+  {
+    const vo_pel* win = ref + (ptrdiff_t) ((y >> 1) + (cy >> 5)) * refStride + (x >> 1) + (cx >> 5);
+    const int     bx = 1 + ((refinedX >> 5) - (mergeX >> 5)), by = 1 + ((refinedY >> 5) - (mergeY >> 5));
+    for (r = 0; r < ph; r++)
+      for (c = 0; c < pw; c++)
+      {
+        int wr = by - 1 + r, wc = bx - 1 + c;
+        wr = wr < 0 ? 0 : (wr > ch + 2 ? ch + 2 : wr);
+        wc = wc < 0 ? 0 : (wc > cw + 2 ? cw + 2 : wc);
+        patch[r * pw + c] = win[(ptrdiff_t) wr * refStride + wc];
+      }
+  }
+  vo_mc_block(1, patch + pw + 1, pw, cw, ch, fx & 31, fy & 31, 1, bd, 0, dst, cw);
+}
+
 /* ------------------------------------------------------------------------------------------------
  * GOP-based temporal filter: motion estimation
  * ---------------------------------------------------------------------------------------------- */

@@ -192,6 +192,9 @@ void vo_dmvr_block(const vo_pel* ref0, const vo_pel* ref1, int refStride, int x,
  * (CommonLib/InterPrediction.cpp:1664-1730, 1845-1917); merge MV and refined MV (merge +- mvdL0SubPu) in 1/16 sample */
 void vo_dmvr_final_luma(const vo_pel* ref, int refStride, int x, int y, int w, int h, int mergeX, int mergeY, int refinedX,
                         int refinedY, int picW, int picH, int maxCuW, int maxCuH, int bd, vo_pel* dst);
+/* the same for a 4:2:0 chroma plane of a MOVED block (x, y, w, h: the luma rectangle; ref: the chroma plane; dst stride w/2) */
+void vo_dmvr_final_chroma(const vo_pel* ref, int refStride, int x, int y, int w, int h, int mergeX, int mergeY, int refinedX,
+                          int refinedY, int picW, int picH, int maxCuW, int maxCuH, int bd, vo_pel* dst);
 
 #ifdef __cplusplus
 }

@@ -391,8 +391,8 @@ def test_tz_search_selective(oracle_lib, ref_lib, selective, fast):
 
 @pytest.mark.ref
 @pytest.mark.parametrize("bd", [10, 8])
-def test_dmvr_final_luma(oracle_lib, ref_lib, bd):
-    """The luma prediction of both lists after DMVR (xPrefetch + xPad + xFinalPaddedMCForDMVR, InterPrediction.cpp:1664-1730,
+def test_dmvr_final_prediction(oracle_lib, ref_lib, bd):
+    """The luma (and, for moved blocks, 4:2:0 chroma) prediction of both lists after DMVR (xPrefetch + xPad + xFinalPaddedMCForDMVR, InterPrediction.cpp:1664-1730,
     1845-1917): the reference's own members against the restatement (8-tap filter over the prefetched window with clamped
     coordinates), with the refinements the reference's own search found — integer moves of up to two samples, sub-sample
     steps, unmoved blocks — and MVs the clip moves at the picture border."""
@@ -423,6 +423,28 @@ def test_dmvr_final_luma(oracle_lib, ref_lib, bd):
             assert np.array_equal(got, want[pos:pos + w * h]), (b.tolist(), d.tolist(), sgn)
         pos += w * h
     assert (np.abs(mvd) >= 16).any(axis=1).sum() > 50 and (mvd % 16 != 0).any(axis=1).sum() > 50
+    # 4:2:0 chroma of the moved blocks (an unmoved block is the plain motion compensation)
+    c0, c1 = (np.ascontiguousarray(rng.integers(0, 1 << bd, (pic_h // 2, pic_w // 2), dtype=np.int16)) for _ in range(2))
+    cp0, cp1 = pad_plane(c0, MARGIN // 2), pad_plane(c1, MARGIN // 2)
+    cstride = cp0.shape[1]
+    ctotal = total // 4
+    wc0, wc1 = np.zeros(ctotal, np.int16), np.zeros(ctotal, np.int16)
+    assert ref_lib.ref_dmvr_final(B.ptr(p0), B.ptr(p1), stride, B.ptr(cp0), B.ptr(cp1), cstride, pic_w, pic_h, MARGIN, len(blk),
+                                  C.c_void_p(blk.ctypes.data), C.c_void_p(mvd.ctypes.data), bd, B.ptr(want0), B.ptr(want1), B.ptr(wc0),
+                                  B.ptr(wc1)) == 0
+    coff, pos, n_chroma = (MARGIN // 2) * cstride + MARGIN // 2, 0, 0
+    for b, d in zip(blk, mvd):
+        x, y, w, h, m0x, m0y, m1x, m1y = (int(v) for v in b)
+        sz = (w // 2) * (h // 2)
+        if d.any():
+            got = np.zeros(sz, np.int16)
+            for plane, want, (mx, my), sgn in ((cp0, wc0, (m0x, m0y), 1), (cp1, wc1, (m1x, m1y), -1)):
+                oracle_lib.vo_dmvr_final_chroma(B.ptr(plane, coff), cstride, x, y, w, h, mx, my, mx + sgn * int(d[0]), my + sgn * int(d[1]),
+                                                pic_w, pic_h, 128, 128, bd, B.ptr(got))
+                assert np.array_equal(got, want[pos:pos + sz]), (b.tolist(), d.tolist(), sgn)
+            n_chroma += 1
+        pos += sz
+    assert n_chroma > 200
 
 
 @pytest.mark.ref
