@@ -121,6 +121,10 @@ def oracle():
         L.vo_mctf_bilateral_weights.argtypes = [_I, _I, C.c_double, _I, _I, _I, _P]
         L.vo_mctf_bilateral.restype = None
         L.vo_mctf_bilateral.argtypes = [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, C.c_double, _I, _P, _I]
+        L.vo_add_weighted_avg.restype = None
+        L.vo_add_weighted_avg.argtypes = [_P, _P, _P, _I, _I, _I]
+        L.vo_remove_weight_high_freq.restype = None
+        L.vo_remove_weight_high_freq.argtypes = [_P, _P, _I, _I, _I, _I]
         L.vo_smvd_search.restype = None
         L.vo_smvd_search.argtypes = [_P, _I, _P, _P, _I, C.POINTER(SmvdIo)]
         L.vo_dmvr_final_chroma.restype = None
@@ -178,6 +182,8 @@ def ref():
         L.ref_dmvr_final_luma.argtypes = [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P]
         L.ref_dmvr_blocks.argtypes = [_P, _P, _I, _I, _I, _I, _I, _P, _I, _P]
         L.ref_add_avg.argtypes = [_P, _P, _P, _I, _I, _I]
+        L.ref_add_weighted_avg.argtypes = [_P, _P, _P, _I, _I, _I, _I]
+        L.ref_remove_weight_high_freq.argtypes = [_P, _P, _I, _I, _I, _I, _I]
         L.ref_remove_high_freq.argtypes = [_P, _I, _P, _I, _I, _I, _I, _I]
         _ref = L
     return _ref

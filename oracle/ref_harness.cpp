@@ -656,6 +656,20 @@ void ref_add_avg(const int16_t* s0, const int16_t* s1, int16_t* dst, int w, int 
   d.addAvg(a, b, makeClp(bd));
 }
 
+// AreaBuf<Pel>::addWeightedAvg (Buffer.cpp:365-396) / AreaBuf<T>::removeWeightHighFreq (Buffer.h:418-472): the BCW forms
+void ref_add_weighted_avg(const int16_t* s0, const int16_t* s1, int16_t* dst, int w, int h, int bd, int bcwIdx)
+{
+  PelBuf  d(dst, w, w, h);
+  CPelBuf a(s0, w, w, h), b(s1, w, w, h);
+  d.addWeightedAvg(a, b, makeClp(bd), (int8_t) bcwIdx);
+}
+void ref_remove_weight_high_freq(int16_t* dst, const int16_t* src, int w, int h, int clip, int bd, int bcwWeight)
+{
+  PelBuf d(dst, w, w, h);
+  PelBuf s(const_cast<int16_t*>(src), w, w, h);
+  d.removeWeightHighFreq(s, clip != 0, makeClp(bd), (int8_t) bcwWeight);
+}
+
 // ---- InterSearch::xPatternSearchIntRefine (InterSearch.cpp:4172-4282), the reference's own member -----------------
 // Same layout as vo_int_refine_io (oracle/vtm_oracle.h).
 struct RefIntRefine

@@ -668,6 +668,22 @@ void vo_add_avg(const vo_pel* s0, const vo_pel* s1, vo_pel* dst, int n, int bd)
   }
 }
 
+/* AreaBuf<Pel>::addWeightedAvg — CommonLib/Buffer.cpp:365-396: the bi-prediction average under BCW weights
+ * (w1 = g_BcwWeights[bcwIdx], w0 = 8 - w1; Rom.cpp:188-200) of two bi=1 predictions */
+void vo_add_weighted_avg(const vo_pel* s0, const vo_pel* s1, vo_pel* dst, int n, int bd, int bcwIdx)
+{
+  static const int bcwWeights[5] = { -2, 3, 4, 5, 10 };
+  const int w1 = bcwWeights[bcwIdx], w0 = 8 - w1;
+  const int shift  = ((VO_IF_INTERNAL_PREC - bd) > 2 ? (VO_IF_INTERNAL_PREC - bd) : 2) + 3;
+  const int offset = (1 << (shift - 1)) + (VO_IF_INTERNAL_OFFS << 3);
+  const int maxv   = (1 << bd) - 1;
+  for (int i = 0; i < n; i++)
+  {
+    int v  = (s0[i] * w0 + s1[i] * w1 + offset) >> shift;
+    dst[i] = (vo_pel) (v < 0 ? 0 : (v > maxv ? maxv : v));
+  }
+}
+
 /* AreaBuf<T>::removeHighFreq — CommonLib/Buffer.h:474-517: the bi-prediction search target 2*org - otherPred */
 void vo_remove_high_freq(vo_pel* dst, const vo_pel* src, int n, int clip, int bd)
 {

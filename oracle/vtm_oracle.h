@@ -85,6 +85,7 @@ double vo_search_batch(const vo_job* jobs, vo_result* res, int n, int literal);
 void vo_mc_block(int comp, const vo_pel* refAtBlk, int refStride, int w, int h, int mvX, int mvY, int bi, int bd,
                  int useAltHpel, vo_pel* dst, int dstStride);
 void vo_add_avg(const vo_pel* s0, const vo_pel* s1, vo_pel* dst, int n, int bd);
+void vo_add_weighted_avg(const vo_pel* s0, const vo_pel* s1, vo_pel* dst, int n, int bd, int bcwIdx);
 void vo_remove_high_freq(vo_pel* dst, const vo_pel* src, int n, int clip, int bd);
 void vo_remove_weight_high_freq(vo_pel* dst, const vo_pel* src, int n, int clip, int bd, int bcwWeight);
 

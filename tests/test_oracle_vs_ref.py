@@ -391,6 +391,34 @@ def test_tz_search_selective(oracle_lib, ref_lib, selective, fast):
 
 @pytest.mark.ref
 @pytest.mark.parametrize("bd", [10, 8])
+def test_bcw_average_and_target(oracle_lib, ref_lib, bd):
+    """The BCW forms of the bi-prediction helpers: AreaBuf::addWeightedAvg (Buffer.cpp:365-396) over 14-bit intermediates and
+    AreaBuf::removeWeightHighFreq (Buffer.h:418-472; SIMD without clipping, scalar with), all five weights."""
+    rng = np.random.default_rng(1300 + bd)
+    for w, h in [(8, 8), (16, 4), (4, 8), (64, 32), (128, 128)]:
+        n = w * h
+        lo, hi = -8192, ((1 << bd) - 1 << (14 - bd)) - 8192                 # range of the bi = 1 predictions
+        s0 = np.ascontiguousarray(rng.integers(lo, hi + 1, n).astype(np.int16))
+        s1 = np.ascontiguousarray(rng.integers(lo, hi + 1, n).astype(np.int16))
+        org = np.ascontiguousarray(rng.integers(0, 1 << bd, n).astype(np.int16))
+        pred = np.ascontiguousarray(rng.integers(0, 1 << bd, n).astype(np.int16))
+        for idx, wt in enumerate([-2, 3, 4, 5, 10]):
+            a, b = np.zeros(n, np.int16), np.zeros(n, np.int16)
+            oracle_lib.vo_add_weighted_avg(B.ptr(s0), B.ptr(s1), B.ptr(a), n, bd, idx)
+            ref_lib.ref_add_weighted_avg(B.ptr(s0), B.ptr(s1), B.ptr(b), w, h, bd, idx)
+            assert np.array_equal(a, b), (w, h, idx)
+            for wsel in (wt, 8 - wt):                                       # the weight of either list
+                if wsel == 4:
+                    continue
+                for clip in (0, 1):
+                    a, b = org.copy(), org.copy()
+                    oracle_lib.vo_remove_weight_high_freq(B.ptr(a), B.ptr(pred), n, clip, bd, wsel)
+                    ref_lib.ref_remove_weight_high_freq(B.ptr(b), B.ptr(pred), w, h, clip, bd, wsel)
+                    assert np.array_equal(a, b), (w, h, wsel, clip)
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("bd", [10, 8])
 def test_dmvr_final_prediction(oracle_lib, ref_lib, bd):
     """The luma (and, for moved blocks, 4:2:0 chroma) prediction of both lists after DMVR (xPrefetch + xPad + xFinalPaddedMCForDMVR, InterPrediction.cpp:1664-1730,
     1845-1917): the reference's own members against the restatement (8-tap filter over the prefetched window with clamped
