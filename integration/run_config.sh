@@ -1,8 +1,9 @@
 #!/bin/bash
 # Encoder-level parity run (BASELINE configs 1-3): patched VTM (oracle/_ref/EncoderAppCUDA) with the GPU motion
 # search against the golden md5 of the unmodified CPU encoder (tests/golden/encoder_md5.json).
-#   bash integration/run_config.sh <1|2|3|4|5|6|7|8> [gpu|cpu] [frames]   (4 = random access, 5 = LD-B with SearchRange 128, both on the small clip;
-#   6 / 7 = configs 1 / 4 with FastSearch=1, the TZ search: xTZSearch on the GPU; 8 = config 1 with FastSearch=2, the selective search)
+#   bash integration/run_config.sh <1..11> [gpu|cpu] [frames]   (4 = random access, 5 = LD-B with SearchRange 128, both on the small clip;
+#   6 / 7 = configs 1 / 4 with FastSearch=1, the TZ search: xTZSearch on the GPU; 8 = config 1 with FastSearch=2, the selective search;
+#   9 = config 1 with FastSearch=3; 10 / 11 = config 4 with FastSearch=2 / 3)
 set -e
 CFGN=${1:-1}; MODE=${2:-gpu}; FS=0; ROOT=$(cd "$(dirname "$0")/.." && pwd); W=$ROOT/gpurun_out/enc_c$CFGN; mkdir -p $W; cd $W
 case $CFGN in
@@ -13,6 +14,9 @@ case $CFGN in
   6) WD=416; HT=240; FR=${3:-8}; BITS=8; CFG=encoder_lowdelay_P_vtm.cfg; SR=64; EXTRA="-q 32"; FS=1;;   # config 1 with the TZ search
   7) WD=416; HT=240; FR=${3:-9}; BITS=8; CFG=encoder_randomaccess_vtm.cfg; SR=64; EXTRA="-q 32 --IntraPeriod=32"; FS=1;;   # small RA with the TZ search
   8) WD=416; HT=240; FR=${3:-4}; BITS=8; CFG=encoder_lowdelay_P_vtm.cfg; SR=64; EXTRA="-q 32"; FS=2;;   # config 1 with the selective TZ search (xTZSearchSelective, staged SAD)
+  9) WD=416; HT=240; FR=${3:-8}; BITS=8; CFG=encoder_lowdelay_P_vtm.cfg; SR=64; EXTRA="-q 32"; FS=3;;   # config 1 with the enhanced TZ search
+  10) WD=416; HT=240; FR=${3:-9}; BITS=8; CFG=encoder_randomaccess_vtm.cfg; SR=64; EXTRA="-q 32 --IntraPeriod=32"; FS=2;;   # small RA with the selective search
+  11) WD=416; HT=240; FR=${3:-9}; BITS=8; CFG=encoder_randomaccess_vtm.cfg; SR=64; EXTRA="-q 32 --IntraPeriod=32"; FS=3;;   # small RA with the enhanced TZ search
   3) WD=3840; HT=2160; FR=${3:-16}; BITS=10; CFG=encoder_lowdelay_vtm.cfg; SR=128; EXTRA="-q 32";;
 esac
 python $ROOT/integration/make_yuv.py in.yuv --width $WD --height $HT --frames $FR --bits $BITS
