@@ -1,9 +1,9 @@
 #!/bin/bash
 # Encoder-level parity run (BASELINE configs 1-3): patched VTM (oracle/_ref/EncoderAppCUDA) with the GPU motion
 # search against the golden md5 of the unmodified CPU encoder (tests/golden/encoder_md5.json).
-#   bash integration/run_config.sh <1..11> [gpu|cpu] [frames]   (4 = random access, 5 = LD-B with SearchRange 128, both on the small clip;
+#   bash integration/run_config.sh <1..12> [gpu|cpu] [frames]   (4 = random access, 5 = LD-B with SearchRange 128, both on the small clip;
 #   6 / 7 = configs 1 / 4 with FastSearch=1, the TZ search: xTZSearch on the GPU; 8 = config 1 with FastSearch=2, the selective search;
-#   9 = config 1 with FastSearch=3; 10 / 11 = config 4 with FastSearch=2 / 3)
+#   9 = config 1 with FastSearch=3; 10 / 11 = config 4 with FastSearch=2 / 3; 12 = config 2 (first 3 pictures) with FastSearch=1)
 set -e
 CFGN=${1:-1}; MODE=${2:-gpu}; FS=0; ROOT=$(cd "$(dirname "$0")/.." && pwd); W=$ROOT/gpurun_out/enc_c$CFGN; mkdir -p $W; cd $W
 case $CFGN in
@@ -17,6 +17,7 @@ case $CFGN in
   9) WD=416; HT=240; FR=${3:-8}; BITS=8; CFG=encoder_lowdelay_P_vtm.cfg; SR=64; EXTRA="-q 32"; FS=3;;   # config 1 with the enhanced TZ search
   10) WD=416; HT=240; FR=${3:-9}; BITS=8; CFG=encoder_randomaccess_vtm.cfg; SR=64; EXTRA="-q 32 --IntraPeriod=32"; FS=2;;   # small RA with the selective search
   11) WD=416; HT=240; FR=${3:-9}; BITS=8; CFG=encoder_randomaccess_vtm.cfg; SR=64; EXTRA="-q 32 --IntraPeriod=32"; FS=3;;   # small RA with the enhanced TZ search
+  12) WD=1920; HT=1080; FR=${3:-3}; BITS=10; CFG=encoder_randomaccess_vtm.cfg; SR=64; EXTRA="-q 32 --IntraPeriod=32"; FS=1;;   # config 2's picture size with the TZ search (CTC default)
   3) WD=3840; HT=2160; FR=${3:-16}; BITS=10; CFG=encoder_lowdelay_vtm.cfg; SR=128; EXTRA="-q 32";;
 esac
 python $ROOT/integration/make_yuv.py in.yuv --width $WD --height $HT --frames $FR --bits $BITS
