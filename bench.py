@@ -27,9 +27,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WIDTH, HEIGHT, SR, CTU, LAMBDA = 1920, 1080, 64, 128, 31.33
-# dram__bytes_read.sum + dram__bytes_write.sum of me_tree_sad_kernel from one `ncu --set full` capture of a 4-pair launch
-# (profiles/r01i_tree_sad_ncu.md: 40.1 MB + 489.8 MB), per pair
-NCU_DRAM_BYTES_PER_PAIR = (40.096256e6 + 489.766656e6) / 4
+TOTAL_PAIRS = 256          # BASELINE config 4: 256 frame pairs, pair p on rank p % world
 METRIC = "ME block-candidates/s (SAD+SATD), 1080p SR=64 full search + quarter-pel"
 UNIT = "block-candidates/s"
 
@@ -84,6 +82,32 @@ def workload_counts(pred_q=None):
     return cands, ops, ncu
 
 
+def frac_ops_per_pair():
+    """Algorithmic integer ops of the half + quarter-pel refinement of every CU of a pair (16 ops per 8-tap
+    output sample, SATD n*(3+log2 n) per 8x8 tile of n = 64 samples, 9 candidates per stage).  Half-pel stage: 2 horizontal
+    planes of (W+1)x(H+8), 4 vertical planes (W x H .. (W+1)x(H+1)); quarter-pel stage: 2 horizontal planes of W x (H+8),
+    8 vertical planes of W x H; the frac-0 'filters' of the reference are copies and count as nothing."""
+    ops = 0
+    for level in range(5):
+        s = 8 << level
+        n = (WIDTH // s) * (HEIGHT // s)
+        half = 16 * (1 * (s + 1) * (s + 8) + (s * (s + 1) + (s + 1) * (s + 1)))         # hor: frac 8; ver: the 2 frac-8 planes
+        qter = 16 * (2 * s * (s + 8) + 8 * s * s)
+        satd = 18 * (s // 8) * (s // 8) * 64 * (3 + 6)
+        ops += n * (half + qter + satd)
+    return ops
+
+
+def ncu_traffic_per_pair():
+    """DRAM bytes of the dominant kernel per frame pair from the committed `ncu --set full` capture (profiles/ncu_traffic.json,
+    written by scripts/ncu_summary.py) -> (bytes per pair, source) or (None, reason)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["pairs_per_launch"], t["source"]
+    except (OSError, ValueError, KeyError) as e:
+        return None, "profiles/ncu_traffic.json unreadable: %s" % e
+
+
 # ---- clocks -------------------------------------------------------------------------------------------------------
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -128,7 +152,7 @@ class ClockSampler:
 
 
 # ---- reference arm / cpu baseline: VTM's own xPatternSearch + fractional refinement on the host cores -------------------
-def cpu_reference_rate(cur, ref, every, threads, steps=1, warmup=0):
+def cpu_reference_rate(cur, ref, every, threads, steps=1, warmup=0, want_results=False, pred_q=None):
     """Runs oracle/_ref (unmodified VTM behind a C shim) on every `every`-th CU of each level of one pair.
     -> (block-candidates/s, seconds per step, description, kind, threads)"""
     import ctypes as C
@@ -140,15 +164,20 @@ def cpu_reference_rate(cur, ref, every, threads, steps=1, warmup=0):
     margin = 192
     refp = np.ascontiguousarray(np.pad(ref, margin, mode="edge"))
     stride = refp.shape[1]
-    jobs, cands = [], 0
+    jobs, cands, cu_index = [], 0, []
+    off = level_slices()
+    if kind == "port":
+        every = max(every, 20)   # the scalar oracle port: a bounded sample (about 2,150 CUs)
     for level in range(5):
         s = 8 << level
         nx = WIDTH // s
-        l, r, t, b = windows(level)
+        l, r, t, b = windows(level, None if pred_q is None else pred_q[off[level]:off[level + 1]])
         for i in range(0, len(l), every):
+            cu_index.append(off[level] + i)
             x, y = (i % nx) * s, (i // nx) * s
+            pq = (0, 0) if pred_q is None else (int(pred_q[off[level] + i][0]), int(pred_q[off[level] + i][1]))
             jobs.append(B.make_job(cur, refp, stride, (margin + y) * stride + margin + x, s, s,
-                                   (int(l[i]), int(r[i]), int(t[i]), int(b[i])), (0, 0), 0, 0, 10, 1, 0, 1, LAMBDA,
+                                   (int(l[i]), int(r[i]), int(t[i]), int(b[i])), pq, 0, 0, 10, 1, 0, 1, LAMBDA,
                                    org_off=y * WIDTH + x, org_stride=WIDTH))
             cands += int((r[i] - l[i] + 1) * (b[i] - t[i] + 1)) + 18
     n = len(jobs)
@@ -164,6 +193,11 @@ def cpu_reference_rate(cur, ref, every, threads, steps=1, warmup=0):
             times.append(dt)
     sec = float(np.mean(times))
     desc = "pair 0, every %d-th CU of each level (%d CUs, %.3g block-candidates) per step" % (every, n, cands)
+    if want_results:
+        # (CU index in the frame API's level-major order, (mvQx, mvQy, intX, intY, intSad, fracCost))
+        out = [(cu_index[k], (4 * r.mvX + 2 * r.halfX + r.qterX, 4 * r.mvY + 2 * r.halfY + r.qterY, r.mvX, r.mvY,
+                              int(r.intSad), int(r.fracCost))) for k, r in enumerate(res)]
+        return cands / sec, sec, desc, kind, threads, out
     return cands / sec, sec, desc, kind, threads
 
 
@@ -171,6 +205,17 @@ def host_pair0():
     from vtm_b200.synth import make_pair
     cur, ref, _ = make_pair(0, WIDTH, HEIGHT)
     return cur, ref
+
+
+WORKLOAD = ("config4: %d synthetic 1080p 10-bit frame pairs (pair p on rank p %% world), every grid-aligned square CU "
+            "8..128 (43,020 per pair), full search SR=64 + half/quarter-pel SATD refinement, zero predictors (run A)" % TOTAL_PAIRS)
+
+
+def shared_config():
+    """The `config` object both arms print: names the workload, nothing run-specific."""
+    return {"workload": WORKLOAD, "search_range": SR, "pairs": TOTAL_PAIRS, "cus_per_pair": 43020,
+            "l2": "a step's inputs (32 pairs: 411 MB of planes, 4.2 GB of SAD surfaces) exceed the 126 MB L2 and steps cycle "
+                  "through distinct pairs"}
 
 
 def run_reference(args, rank):
@@ -181,9 +226,8 @@ def run_reference(args, rank):
     rate, sec, desc, kind, threads = cpu_reference_rate(cur, ref, args.cpu_every, threads, args.steps, min(args.warmup, 1))
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int16/int32", "data": "synthetic",
-            "config": {"workload": "config4: 1080p pairs, CUs 8..128, full search SR=64 + quarter-pel (bounded sample)",
-                       "search_range": SR, "sample": desc},
+            "vs_baseline": None, "dtype": "int16 samples, int32 SAD/SATD arithmetic", "data": "synthetic",
+            "config": shared_config(),
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": kind, "sample": desc},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -199,14 +243,13 @@ def run_ours(args, rank, world, local_rank):
     from vtm_b200.me import CU_RESULT_DTYPE
     from vtm_b200.peaks import int_peak
     from vtm_b200.shard import max_over_ranks, pairs_for_rank
-    from vtm_b200.synth import make_pairs_torch
+    from vtm_b200.synth import make_pairs_torch, random_predictors
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, K, W = args.pairs_per_step, args.steps, args.warmup
-    pool = max(args.pool, B)
     cands_pair, ops_pair, ncu = workload_counts()
 
     ms = vtm_b200.MotionSearch(local_rank)
@@ -217,32 +260,39 @@ def run_ours(args, rank, world, local_rank):
     ms.set_stream(stream.cuda_stream)
     ms.set_frame_size(WIDTH, HEIGHT)
 
-    # synthetic pairs of this rank: distinct seeds per rank, generated on the GPU, uploaded as library pictures
-    ids = pairs_for_rank(world * pool, world, rank)   # pair p of the job belongs to rank p % world
-    host_cur, host_ref = [], []
+    # The rank's share of the job's pairs (pair p -> rank p % world): resident on the device as library pictures (the
+    # `value` leg) and in page-locked host memory (the e2e leg).  Pair 0 is the host-generated pair the CPU leg searches,
+    # so the parity check below compares the e2e leg's delivered results with the reference's on the same samples.
+    ids = pairs_for_rank(args.pool, world, rank)
+    pool = len(ids)
+    if pool < 1:
+        raise SystemExit("fewer pairs than ranks")
+    host_cur, host_ref = [None] * pool, [None] * pool
+    pair0 = host_pair0() if (rank == 0 and not args.no_cpu) else None
     for c0 in range(0, pool, 8):
         cur, ref = make_pairs_torch(ids[c0:c0 + 8], dev, WIDTH, HEIGHT)
         for i in range(cur.shape[0]):
             p = c0 + i
+            if p == 0 and pair0 is not None:
+                host_cur[0] = torch.from_numpy(pair0[0]).pin_memory()
+                host_ref[0] = torch.from_numpy(pair0[1]).pin_memory()
+                ms.upload_picture(0, pair0[0])
+                ms.upload_picture(1, pair0[1])
+                continue
             ms.upload_picture_device(2 * p, cur[i].data_ptr(), WIDTH, WIDTH, HEIGHT)
             ms.upload_picture_device(2 * p + 1, ref[i].data_ptr(), WIDTH, WIDTH, HEIGHT)
-            if p < args.e2e_pool:
-                host_cur.append(cur[i].cpu().pin_memory())
-                host_ref.append(ref[i].cpu().pin_memory())
+            host_cur[p] = cur[i].cpu().pin_memory()
+            host_ref[p] = ref[i].cpu().pin_memory()
         ms.synchronize()
         del cur, ref
-    prm = FrameParams(searchRange=SR, bitDepth=10, ctuSize=CTU, lambdaMotion=LAMBDA, predSpread=0)
+    prm_a = FrameParams(searchRange=SR, bitDepth=10, ctuSize=CTU, lambdaMotion=LAMBDA, predSpread=0)
+    # run B of config 4: seeded random quarter-pel predictors within +-16 px, one set per pair slot of a step
+    h_pred = np.stack([random_predictors(7000 + i, ncu, 16) for i in range(B)])
+    d_pred = torch.from_numpy(h_pred).to(dev)
+    prm_b = FrameParams(searchRange=SR, bitDepth=10, ctuSize=CTU, lambdaMotion=LAMBDA, predSpread=33)
+    cands_b = int(np.mean([workload_counts(h_pred[i])[0] for i in range(min(B, 4))]))
+    ops_b = int(np.mean([workload_counts(h_pred[i])[1] for i in range(min(B, 4))]))
     d_res = torch.zeros(B * ncu * CU_RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
-    d_pred_ptr, h_pred = 0, None
-    if args.run == "B":
-        # run B of config 4: seeded random quarter-pel predictors within +-16 px, one set per pair slot of a step
-        from vtm_b200.synth import random_predictors
-        h_pred = np.stack([random_predictors(7000 + i, ncu, 16) for i in range(B)])
-        d_pred = torch.from_numpy(h_pred).to(dev)
-        d_pred_ptr = d_pred.data_ptr()
-        prm.predSpread = 33
-        cands_pair = int(np.mean([workload_counts(h_pred[i])[0] for i in range(min(B, 4))]))
-        ops_pair = int(np.mean([workload_counts(h_pred[i])[1] for i in range(min(B, 4))]))
 
     def step_ids(s):
         sel = [(s * B + i) % pool for i in range(B)]
@@ -259,37 +309,54 @@ def run_ours(args, rank, world, local_rank):
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     peak_ops = 2.0 * pk["lane_instr_per_clk_per_sm"] * sms * pk["sm_mhz"] * 1e6
 
-    for s in range(W):
-        c, r = step_ids(s)
-        ms.search_frames_device(c, r, prm, d_pred_ptr, d_res.data_ptr())
-    ms.set_profiling(True)
-    sampler = ClockSampler(local_rank)
-    launches0 = ms.launches
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.time()
-    ev0.record(stream)
-    kms = []
-    for s in range(W, W + K):
-        c, r = step_ids(s)
-        ms.search_frames_device(c, r, prm, d_pred_ptr, d_res.data_ptr())
-        kms.append(ms.frame_kernel_ms())
-    ev1.record(stream)
-    barrier()
-    t_wall1 = time.time()
-    clocks = sampler.stop(t_wall0, t_wall1)
-    launches = ms.launches - launches0
-    ms.set_profiling(False)
-    elapsed_ms = ev0.elapsed_time(ev1)
-    elapsed_ms = max_over_ranks(elapsed_ms, dev)
+    def timed_resident(prm, pred_ptr, steps, warm):
+        """`steps` batched searches over device-resident pairs -> (ms over all steps [max over ranks], per-step kernel ms,
+        launches, clocks)."""
+        for s in range(warm):
+            c, r = step_ids(s)
+            ms.search_frames_device(c, r, prm, pred_ptr, d_res.data_ptr())
+        ms.set_profiling(True)
+        sampler = ClockSampler(local_rank)
+        launches0 = ms.launches
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall0 = time.time()
+        ev0.record(stream)
+        kms = []
+        for s in range(warm, warm + steps):
+            c, r = step_ids(s)
+            ms.search_frames_device(c, r, prm, pred_ptr, d_res.data_ptr())
+            kms.append(ms.frame_kernel_ms())
+        ev1.record(stream)
+        barrier()
+        t_wall1 = time.time()
+        clocks = sampler.stop(t_wall0, t_wall1)
+        launches = ms.launches - launches0
+        ms.set_profiling(False)
+        return max_over_ranks(ev0.elapsed_time(ev1), dev), np.array(kms), launches, clocks
+
+    run_b_headline = args.run == "B"
+    prm, pred_ptr = (prm_b, d_pred.data_ptr()) if run_b_headline else (prm_a, 0)
+    if run_b_headline:
+        cands_pair, ops_pair = cands_b, ops_b
+    elapsed_ms, kms, launches, clocks = timed_resident(prm, pred_ptr, K, W)
     value = world * B * K * cands_pair / (elapsed_ms * 1e-3)
+    other = None
+    if not run_b_headline:      # run B of SURVEY 8(d) beside run A: same pairs, predictor-centred windows
+        b_ms, b_kms, _, _ = timed_resident(prm_b, d_pred.data_ptr(), max(2, min(K, 4)), 2)
+        nb = max(2, min(K, 4))
+        other = {"predictors": "seeded random quarter-pel predictors within +-16 px per CU",
+                 "value": world * B * nb * cands_b / (b_ms * 1e-3), "unit": UNIT, "ms_per_step": b_ms / nb, "steps": nb,
+                 "block_candidates_per_pair": cands_b,
+                 "roofline_frac": B * ops_b / (float(b_kms[:, 0].mean()) * 1e-3) / peak_ops,
+                 "kernel_ms": {"me_tree_sad": float(b_kms[:, 0].mean()), "me_tree_upper": float(b_kms[:, 1].mean()),
+                               "me_frac_frame": float(b_kms[:, 2].mean())}}
 
     # ---- e2e: host buffers through the C ABI.  Every step uploads both planes of its pairs from page-locked host
     # memory (vtmme_upload_picture_async), searches them (vtmme_search_frames_device, asynchronous) and copies all
     # results back to page-locked host memory.  The three stages of consecutive steps overlap: pictures are
     # triple-buffered, results double-buffered; the timed region ends when the last result is on the host.
-    e2e_steps = max(1, min(K, args.e2e_steps))
-    npool = len(host_cur)
+    e2e_steps = K
     res_bytes = B * ncu * CU_RESULT_DTYPE.itemsize
     d_res2 = [torch.zeros(res_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
     h_res2 = [torch.empty(res_bytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
@@ -297,9 +364,13 @@ def run_ours(args, rank, world, local_rank):
     searched = [torch.cuda.Event() for _ in range(3)]
     copied = [torch.cuda.Event() for _ in range(2)]
     h_pred_pinned, d_pred_e2e = None, None
-    if h_pred is not None:
+    if run_b_headline:
         h_pred_pinned = torch.from_numpy(h_pred).pin_memory()
         d_pred_e2e = torch.zeros_like(h_pred_pinned, device=dev)
+    last = e2e_steps + 1          # index of the last pipelined step: it searches pool pairs 0..B-1, pair 0 in slot 0
+
+    def e2e_pair(s, i):
+        return ((s - last) * B + i) % pool
 
     def e2e_upload(s):
         """queue the H2D copies of step s on the library's copy stream; picture ids triple-buffered"""
@@ -307,7 +378,7 @@ def run_ours(args, rank, world, local_rank):
             searched[s % 3].synchronize()      # the search that last used this slot (step s-3) is done
         base = 100000 + (s % 3) * 2 * B
         for i in range(B):
-            p = (s * B + i) % npool
+            p = e2e_pair(s, i)
             ms.upload_picture_async(base + 2 * i, host_cur[p].data_ptr(), WIDTH, WIDTH, HEIGHT)
             ms.upload_picture_async(base + 2 * i + 1, host_ref[p].data_ptr(), WIDTH, WIDTH, HEIGHT)
 
@@ -338,36 +409,24 @@ def run_ours(args, rank, world, local_rank):
     copy_stream.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    e2e_prof = os.environ.get("BENCH_E2E_PROFILE") == "1"   # development: kernel times of the last pipelined step
-    if e2e_prof:
-        ms.set_profiling(True)
     for s in range(2, e2e_steps + 2):
-        e2e_upload(s + 1)
+        if s + 1 <= last:
+            e2e_upload(s + 1)
         e2e_search(s)
     copy_stream.synchronize()                  # the last results are on the host
     ms.synchronize()
     stream.wait_stream(copy_stream)
     e1.record(stream)
     barrier()
-    if e2e_prof:
-        sys.stderr.write("e2e kernel ms of the last step (tree, upper, frac): %s; step %.2f ms\n"
-                         % (ms.frame_kernel_ms(), e0.elapsed_time(e1) / e2e_steps))
-        ms.set_profiling(False)
-    last = e2e_steps + 1
     h_res = h_res2[last & 1].numpy().view(CU_RESULT_DTYPE).reshape(B, ncu)
-    # untimed: the pipelined path delivered what the synchronous host call gives for the same pictures
-    base = 100000 + (last % 3) * 2 * B
-    chk = ms.search_frames([base + 2 * i for i in range(B)], [base + 2 * i + 1 for i in range(B)], prm, h_pred)
-    if not np.array_equal(h_res, chk):
-        raise RuntimeError("e2e: pipelined results differ from the synchronous call")
     e2e_ms = max_over_ranks(e0.elapsed_time(e1), dev)
     e2e_value = world * B * e2e_steps * cands_pair / (e2e_ms * 1e-3)
     h2d = B * 2 * WIDTH * HEIGHT * 2
     d2h = B * ncu * CU_RESULT_DTYPE.itemsize
 
     if rank == 0:
-        kms = np.array(kms)                       # [K, 3] per-step kernel durations on this rank
         k1_ms = float(kms[:, 0].mean())
+        k2_ms, k3_ms = float(kms[:, 1].mean()), float(kms[:, 2].mean())
         achieved = B * ops_pair / (k1_ms * 1e-3)
         # algorithmic HBM bytes of the dominant kernel per launch: both planes once + the 32x32 SAD surfaces out
         surf_bytes = B * (WIDTH // 32) * (HEIGHT // 32) * (2 * SR + 1) * (2 * SR + 8) * 4
@@ -378,42 +437,68 @@ def run_ours(args, rank, world, local_rank):
         except (OSError, ValueError):
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic_pair, traffic_src = ncu_traffic_per_pair()
+        fops = B * frac_ops_per_pair()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int16 samples, int32 SAD/SATD arithmetic", "data": "synthetic",
-            "config": {"workload": "config4: synthetic 1080p 10-bit pairs, CUs 8..128 (43,020/pair), full search SR=64 "
-                                   "+ half/quarter-pel SATD refinement, " + ("zero predictors (run A)" if args.run == "A" else "random quarter-pel predictors within +-16 px (run B)"),
-                       "pairs_per_step_per_gpu": B, "pool_pairs_per_gpu": pool, "search_range": SR,
-                       "block_candidates_per_pair": cands_pair, "frame_pairs_per_s": world * B * K / (elapsed_ms * 1e-3),
-                       "l2": "inputs of a step (%d MB of planes + %d MB of SAD surfaces) exceed the 126 MB L2; steps cycle "
-                             "through a pool of distinct pairs" % (B * 2 * 2304 * 1464 * 2 >> 20, surf_bytes >> 20)},
+            "config": shared_config(),
+            "run": {"predictors": "zero (run A)" if not run_b_headline else "random within +-16 px (run B)",
+                    "pairs_per_step_per_gpu": B, "pool_pairs_per_gpu": pool, "block_candidates_per_pair": cands_pair,
+                    "frame_pairs_per_s": world * B * K / (elapsed_ms * 1e-3)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps},
+                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "pinned_pool_pairs": pool},
             "gpu_launches": int(launches),
             "roofline": {"bound": "int_alu", "kernel": "me_tree_sad_kernel", "achieved": achieved / 1e12,
-                         "peak": peak_ops / 1e12, "unit": "Tiop/s", "frac": achieved / peak_ops, "traffic": B * NCU_DRAM_BYTES_PER_PAIR,
-                         "traffic_note": "DRAM bytes per launch scaled from the ncu capture in profiles/r01i_tree_sad_ncu.md; "
-                                         "algorithmic bytes per launch: %d" % hbm_bytes,
+                         "peak": peak_ops / 1e12, "unit": "Tiop/s", "frac": achieved / peak_ops,
+                         "traffic": None if traffic_pair is None else B * traffic_pair,
+                         "traffic_note": "DRAM bytes per launch = pairs per launch x the per-pair figure of %s; algorithmic bytes "
+                                         "per launch: %d" % (traffic_src, hbm_bytes),
                          "peak_source": "measured in this run: VABSDIFF.U32 issue rate %.1f lanes/clk/SM x %d SMs x %.0f MHz, "
                                         "fused |a-b|+c = 2 ops" % (pk["lane_instr_per_clk_per_sm"], sms, pk["sm_mhz"]),
                          "algorithmic_ops_per_launch": B * ops_pair, "kernel_ms": k1_ms,
                          "kernel_share_of_step": float(kms[:, 0].sum() / elapsed_ms),
-                         "other_kernels_ms": {"me_tree_upper": float(kms[:, 1].mean()), "me_frac_frame": float(kms[:, 2].mean())},
+                         "whole_step_frac": B * ops_pair / (elapsed_ms / K * 1e-3) / peak_ops,
+                         "other_kernels": {
+                             "me_tree_upper": {"ms": k2_ms, "bound": "hbm", "algorithmic_bytes": surf_bytes,
+                                               "achieved_gbs": surf_bytes / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else None,
+                                               "frac": surf_bytes / (k2_ms * 1e-3) / 1e9 / hbm_peak if k2_ms > 0 else None},
+                             "me_frac_frame": {"ms": k3_ms, "bound": "int_alu", "algorithmic_ops": fops,
+                                               "achieved_tiops": fops / (k3_ms * 1e-3) / 1e12,
+                                               "frac": fops / (k3_ms * 1e-3) / peak_ops}},
                          "hbm": {"achieved_gbs": hbm_bytes / (k1_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                                  "frac": hbm_bytes / (k1_ms * 1e-3) / 1e9 / hbm_peak,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"}},
         }
-        if world == 1 and not args.no_cpu:
-            cur0, ref0 = host_pair0()
-            rate, sec, desc, kind, threads = cpu_reference_rate(cur0, ref0, args.cpu_every, os.cpu_count() or 1)
+        if other is not None:
+            line["run_b"] = other
+        if pair0 is not None:
+            every = args.cpu_every
+            rate, sec, desc, kind, threads, want = cpu_reference_rate(pair0[0], pair0[1], every, os.cpu_count() or 1,
+                                                                      want_results=True)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind, "sample": desc,
                                     "seconds": sec}
+            # parity of what the timed e2e leg delivered for pair 0 (slot 0 of its last step) with the CPU leg's results
+            # for the same host samples: every CU the CPU leg searched, all six result fields
+            got0 = h_res[0]
+            bad = [i for i, t in want if (int(got0["mvQx"][i]), int(got0["mvQy"][i]), int(got0["intX"][i]),
+                                          int(got0["intY"][i]), int(got0["intSad"][i]), int(got0["fracCost"][i])) != t]
+            line["parity"] = {"cus": len(want), "equal": not bad, "mismatches": len(bad), "against": kind,
+                              "what": "e2e leg's results for host pair 0 vs the CPU leg's (MV quarter-pel, integer MV, SAD, "
+                                      "refined cost)"}
+            if run_b_headline:
+                line["parity"] = {"cus": 0, "equal": None, "what": "run B headline: the CPU leg searches zero predictors; see "
+                                                                   "tests/test_gpu_fullsize.py"}
             if kind == "reference":   # the single-thread number next to the all-cores one (sparser sample)
-                r1, s1, d1, _, _ = cpu_reference_rate(cur0, ref0, 8 * args.cpu_every, 1)
+                r1, s1, d1, _, _ = cpu_reference_rate(pair0[0], pair0[1], 8 * every, 1)
                 line["cpu_baseline"]["single_core"] = {"value": r1, "unit": UNIT, "cores": 1, "sample": d1, "seconds": s1}
         emit(line)
+        if line.get("parity", {}).get("equal") is False:
+            sys.stderr.write("PARITY FAILURE: %d of %d CUs differ from the %s\n" % (len(bad), len(want), kind))
+            ms.close()
+            sys.exit(3)
     ms.close()
     if world > 1:
         dist.destroy_process_group()
@@ -440,9 +525,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs-per-step", type=int, default=32)
-    ap.add_argument("--pool", type=int, default=64, help="distinct resident pairs per GPU")
-    ap.add_argument("--e2e-pool", type=int, default=16, help="pairs kept in pinned host memory for the e2e pass")
-    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--pool", type=int, default=TOTAL_PAIRS, help="distinct frame pairs of the whole job (sharded p %% world)")
     ap.add_argument("--cpu-every", type=int, default=1, help="CPU baseline sample: every n-th CU of pair 0")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--run", default="A", choices=["A", "B"], help="config 4 run A (zero predictors) or B (random predictors)")

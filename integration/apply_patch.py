@@ -69,7 +69,12 @@ def main():
   vtmcuda::SearchOut cudaOut;
   bool cudaFracDone      = false;
   bool cudaIntRefineDone = false;
+  // not on the GPU: weighted prediction, wrap-around / scaled references, and the two cases in which VTM rewrites a
+  // reference's reconstruction plane in place after it was uploaded — sub-pictures treated as pictures
+  // (extendSubPicBorder, EncSlice.cpp:1556; clipMv is then clipMvInSubpic) and the composite long-term reference
+  // (EncGOP::updateCompositeReference; also the zeroMV / in-CTU branch of xPatternSearchFracDIF, InterSearch.cpp:4311)
   const bool cudaUsable  = vtmcuda::enabled() && !m_cDistParam.applyWeight && m_lumaClpRng.bd <= 10 && !wrap
+                           && clipMv == clipMvInPic && !m_useCompositeRef && !cStruct.inCtuSearch
                            && !pu.cu->slice->getRefPic( eRefPicList, iRefIdxPred )->isRefScaled( pu.cs->pps )
                            && !pu.cs->sps->getWrapAroundEnabledFlag();
   auto cudaSearch = [&]( const bool tz, const bool tzFast, const Mv& tzStart )
@@ -142,13 +147,12 @@ def main():
     cudaIntRefineDone = in.doFrac == 2;
   };
   // the TZ searches (diamond, enhanced diamond, selective) run on the GPU without hash ME / MCTS / composite reference
-  const bool cudaTzUsable = cudaUsable && clipMv == clipMvInPic && !m_pcEncCfg->getMCTSEncConstraint() && !m_pcEncCfg->getUseHashME()
-                            && !cStruct.inCtuSearch
+  const bool cudaTzUsable = cudaUsable && !m_pcEncCfg->getMCTSEncConstraint() && !m_pcEncCfg->getUseHashME()
                             && ( m_motionEstimationSearchMethod == MESEARCH_DIAMOND || m_motionEstimationSearchMethod == MESEARCH_DIAMOND_ENHANCED
                                  || ( m_motionEstimationSearchMethod == MESEARCH_SELECTIVE && m_iSearchRange <= 128 ) );
 """ + s[second:]
         s = once(s, "    xPatternSearch( cStruct, rcMv, ruiCost);\n", """\
-    if( cudaUsable && ( clipMv == clipMvInPic || ( pu.cu->imv == 0 || pu.cu->imv == IMV_HPEL ) ) )
+    if( cudaUsable )
     {
       cudaSearch( false, false, Mv() );   // libvtmme: integer full search + refinement
     }

@@ -9,6 +9,15 @@ import argparse
 import numpy as np
 
 
+def paste(y, rect, x, y0):
+    """rect into y at (x, y0), clipped to the picture (any picture size, rectangles may leave it on every side)"""
+    H, W = y.shape
+    h, w = rect.shape
+    xa, xb, ya, yb = max(x, 0), min(x + w, W), max(y0, 0), min(y0 + h, H)
+    if xa < xb and ya < yb:
+        y[ya:yb, xa:xb] = rect[ya - y0:yb - y0, xa - x:xb - x]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("out")
@@ -36,9 +45,9 @@ def main():
             ox, oy = pad + 2 * t, pad + t                      # global pan (+2, +1) px per frame
             y = base[oy:oy + H, ox:ox + W].copy()
             x1, y1 = 40 + 5 * t, 30 + 3 * t                    # rectangle 1: (+5, +3)
-            y[y1:y1 + 64, x1:x1 + 64] = sq1[:max(0, min(64, H - y1)), :max(0, min(64, W - x1))]
+            paste(y, sq1, x1, y1)
             x2, y2 = W - 140 - 7 * t, H - 70 - 2 * t           # rectangle 2: (-7, -2)
-            y[y2:y2 + 40, x2:x2 + 96] = sq2[:max(0, min(40, H - y2)), :max(0, min(96, W - x2))]
+            paste(y, sq2, x2, y2)
             y = np.clip(np.rint(y + rng.normal(0, 0.004 * maxv * 3, y.shape)), 0, maxv)
             u = np.clip(np.rint(maxv / 2 + 0.1 * (y[::2, ::2] - maxv / 2)), 0, maxv)
             v = np.clip(np.rint(maxv / 2 - 0.1 * (y[::2, ::2] - maxv / 2)), 0, maxv)

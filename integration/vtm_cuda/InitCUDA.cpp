@@ -12,22 +12,38 @@
 #include "CommonLib/RdCost.h"
 #include "VtmCudaME.h"
 
+#include <cstdio>
+#include <cstdlib>
+
 namespace
 {
 FpDistFunc s_prevDist[DF_TOTAL_FUNCTIONS];
+// calls answered by the GPU / handed to the entry that was replaced; printed at exit (VTMME_TABLE_HOOKS=2: count
+// only — every call is delegated, which sizes a run without a GPU)
+unsigned long long s_distGpu = 0, s_distPrev = 0, s_filtGpu = 0, s_filtPrev = 0;
+bool               s_countOnly = false;
+
+void printHookStats()
+{
+  fprintf( stderr, "[vtmcuda] table hooks: distortion %llu on the GPU / %llu delegated, filters %llu on the GPU / %llu delegated%s\n",
+           s_distGpu, s_distPrev, s_filtGpu, s_filtPrev, s_countOnly ? " (count only)" : "" );
+}
 
 template<int DF> Distortion distCuda( const DistParam& dp )
 {
   const int w = dp.org.width, h = dp.org.height;
   if( dp.applyWeight || dp.bitDepth > 10 || dp.useMR || w < 2 || h < 2 || w > 128 || h > 128 || ( w & 1 ) || ( h & 1 ) || dp.step != 1 )
   {
+    s_distPrev++;
     return s_prevDist[DF]( dp );
   }
   const bool had = DF >= DF_HAD && DF <= DF_HAD16N;
-  if( !had && ( h >> dp.subShift ) < 1 )
+  if( ( !had && ( h >> dp.subShift ) < 1 ) || s_countOnly )
   {
+    s_distPrev++;
     return s_prevDist[DF]( dp );
   }
+  s_distGpu++;
   return vtmcuda::distHost( had ? 1 : 0, dp.org.buf, dp.org.stride, dp.cur.buf, dp.cur.stride, w, h, had ? 0 : dp.subShift );
 }
 
@@ -40,11 +56,13 @@ template<int T, bool VER, bool FIRST, bool LAST>
 void filterCuda( const ClpRng& clpRng, Pel const* src, int srcStride, Pel* dst, int dstStride, int width, int height,
                  TFilterCoeff const* coeff, bool biMCForDMVR )
 {
-  if( biMCForDMVR || clpRng.bd > 10 || clpRng.bd < 8 || width > 256 || height > 256 || clpRng.min != 0 || clpRng.max != ( 1 << clpRng.bd ) - 1 )
+  if( biMCForDMVR || clpRng.bd > 10 || clpRng.bd < 8 || width > 256 || height > 256 || clpRng.min != 0 || clpRng.max != ( 1 << clpRng.bd ) - 1 || s_countOnly )
   {
+    s_filtPrev++;
     ( VER ? s_prevVer : s_prevHor )[T][FIRST][LAST]( clpRng, src, srcStride, dst, dstStride, width, height, coeff, biMCForDMVR );
     return;
   }
+  s_filtGpu++;
   const int taps = T == 0 ? 8 : ( T == 1 ? 4 : 2 );
   int16_t   c[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
   for( int k = 0; k < taps; k++ ) c[k] = coeff[k];
@@ -54,11 +72,13 @@ void filterCuda( const ClpRng& clpRng, Pel const* src, int srcStride, Pel* dst, 
 template<bool FIRST, bool LAST>
 void copyCuda( const ClpRng& clpRng, Pel const* src, int srcStride, Pel* dst, int dstStride, int width, int height, bool biMCForDMVR )
 {
-  if( biMCForDMVR || clpRng.bd > 10 || clpRng.bd < 8 || width > 256 || height > 256 || clpRng.min != 0 || clpRng.max != ( 1 << clpRng.bd ) - 1 )
+  if( biMCForDMVR || clpRng.bd > 10 || clpRng.bd < 8 || width > 256 || height > 256 || clpRng.min != 0 || clpRng.max != ( 1 << clpRng.bd ) - 1 || s_countOnly )
   {
+    s_filtPrev++;
     s_prevCopy[FIRST][LAST]( clpRng, src, srcStride, dst, dstStride, width, height, biMCForDMVR );
     return;
   }
+  s_filtGpu++;
   vtmcuda::filterHost( 8, 0, FIRST, LAST, 1, src, srcStride, dst, dstStride, width, height, nullptr, clpRng.bd );
 }
 }   // namespace
@@ -71,6 +91,9 @@ void RdCost::initRdCostCUDA()
   {
     for( int i = 0; i < DF_TOTAL_FUNCTIONS; i++ ) s_prevDist[i] = m_afpDistortFunc[i];
     done = true;
+    const char* e = getenv( "VTMME_TABLE_HOOKS" );
+    s_countOnly   = e && e[0] == '2';
+    atexit( printHookStats );
   }
 #define VTMCUDA_DIST( DF ) m_afpDistortFunc[DF] = distCuda<DF>;
   VTMCUDA_DIST( DF_SAD ) VTMCUDA_DIST( DF_SAD2 ) VTMCUDA_DIST( DF_SAD4 ) VTMCUDA_DIST( DF_SAD8 ) VTMCUDA_DIST( DF_SAD16 )

@@ -710,6 +710,9 @@ extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_
       if (t.picW != rp.width || t.picH != rp.height || t.maxCu < 1 || t.maxCu > 128 || t.nSeeds < 0 || t.nSeeds > 15 ||
           t.searchRange < 1 || t.searchRange > 512)
         return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search", "invalid vtmme_tz (picture size of refPic, maxCu <= 128, <= 15 seeds, range 1..512)");
+      // ... and when the PU itself lies inside that picture
+      if (j.x < 0 || j.y < 0 || j.x + j.w > rp.width || j.y + j.h > rp.height)
+        return vtmme_set_error(ctx, VTMME_ERR_RANGE, "vtmme_search", "PU outside the reference picture");
       // the exhaustive scan of the selective search indexes its window with a 17-bit multiply-high division (tz_raster)
       if (t.selective && t.searchRange > 128)
         return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_search", "the selective TZ search takes a searchRange of at most 128");
@@ -817,7 +820,8 @@ extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_
       a.key    = ctx->dJobKeys;
       a.ticket = ctx->dJobTicket;
       a.result = reinterpret_cast<DevJobResult*>(ctx->dPinnedAlias);
-      a.seq    = ++ctx->jobSeq;
+      if (++ctx->jobSeq == 0) ++ctx->jobSeq;   // 0 is the reset value of the polled word: never a sequence number
+      a.seq    = ctx->jobSeq;
       a.done   = g_poll ? reinterpret_cast<unsigned int*>(ctx->dPinnedAlias + kDoneOffset) : nullptr;
       *reinterpret_cast<volatile unsigned int*>(ctx->hPinned + kDoneOffset) = 0;   // the block is shared with the batch path
       int grid = (nrows + a.bandRows - 1) / a.bandRows;
@@ -954,7 +958,8 @@ extern "C" int vtmme_search(vtmme_ctx* ctx, const vtmme_job* jobs, int n, vtmme_
   }
   int                launches = 0;
   bool               fusedTz  = false;
-  const unsigned int seq      = ++ctx->jobSeq;
+  if (++ctx->jobSeq == 0) ++ctx->jobSeq;   // 0 is the reset value of the polled word
+  const unsigned int seq      = ctx->jobSeq;
   *reinterpret_cast<volatile unsigned int*>(ctx->hPinned + offDone) = 0;
   VTMME_CUDA_CHECK(ctx, launch_job_search_impl(reinterpret_cast<const DevJob*>(dIn + offJobs),
                                                ctx->dJobKeys,
