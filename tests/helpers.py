@@ -21,7 +21,7 @@ def oracle_window(L, pred_q, x, y, pic_w, pic_h, sr, ctu=128):
 
 
 def oracle_frame_search(L, cur, ref_padded, margin, sr, lam, pred_q=None, frac=1, use_had=1, levels=range(5),
-                        only=None, literal=0, sub_shift_mode=0):
+                        only=None, literal=0, sub_shift_mode=0, bit_depth=10):
     """Every grid-aligned square CU (level-major, raster) through vo_search.  Returns list of result tuples
     (mvQx, mvQy, intX, intY, intSad, fracCost) indexed like the frame API; `only` = subset of CU indices."""
     h, w = cur.shape
@@ -37,7 +37,7 @@ def oracle_frame_search(L, cur, ref_padded, margin, sr, lam, pred_q=None, frac=1
                     pq = (0, 0) if pred_q is None else (int(pred_q[idx][0]), int(pred_q[idx][1]))
                     win = oracle_window(L, pq, x, y, w, h, sr)
                     j = B.make_job(cur, ref_padded, stride, (margin + y) * stride + margin + x, s, s, win, pq, 0,
-                                   sub_shift_mode, 10, use_had, 0, frac, lam, org_off=y * w + x, org_stride=w)
+                                   sub_shift_mode, bit_depth, use_had, 0, frac, lam, org_off=y * w + x, org_stride=w)
                     r = B.Result()
                     L.vo_search(C.byref(j), C.byref(r), literal)
                     out[idx] = (4 * r.mvX + 2 * r.halfX + r.qterX, 4 * r.mvY + 2 * r.halfY + r.qterY, r.mvX, r.mvY,

@@ -73,6 +73,26 @@ def test_frame_search_row_subsampling(ms, oracle_lib):
         assert not bad, "%dx%d: %d of %d CUs differ, first: %s" % (w, h, len(bad), ncu, bad[:3])
 
 
+def test_frame_search_8bit_and_every_level(ms, oracle_lib):
+    """8-bit samples (headroom 6: the first filter stage does not shift) on a picture with 128x128 CUs, and a second
+    pair in the same call (the refinement kernels index pictures, keys and results per pair)."""
+    from vtm_b200 import FrameParams
+    from vtm_b200.synth import make_pair, random_predictors
+    w, h, sr = 256, 136, 10
+    pairs = [make_pair(21 + i, w, h, max_global=7, max_local=8, n_rects=3, sigma=3.0, bit_depth=8) for i in range(2)]
+    for i, (cur, ref, _) in enumerate(pairs):
+        ms.upload_picture(10 + 2 * i, cur)
+        ms.upload_picture(11 + 2 * i, pad_plane(ref), MARGIN)
+    ncu = ms.set_frame_size(w, h)
+    pred = np.stack([random_predictors(30 + i, ncu, 5) for i in range(2)])
+    prm = FrameParams(searchRange=sr, bitDepth=8, predSpread=11, lambdaMotion=9.5)
+    got = ms.search_frames([10, 12], [11, 13], prm, pred)
+    for i, (cur, ref, _) in enumerate(pairs):
+        want = oracle_frame_search(oracle_lib, cur, pad_plane(ref), MARGIN, sr, 9.5, pred[i], bit_depth=8)
+        bad = [(k, gpu_tuple(got[i][k]), want[k]) for k in range(ncu) if gpu_tuple(got[i][k]) != want[k]]
+        assert not bad, "pair %d: %d of %d CUs differ, first: %s" % (i, len(bad), ncu, bad[:3])
+
+
 def test_frame_search_sr64(ms, oracle_lib):
     # the BASELINE search range on a picture the oracle finishes in seconds
     _frame_case(ms, oracle_lib, 256, 256, 64, 6, 0)

@@ -10,6 +10,8 @@
 //     me_frac_items_kernel<0>  half-pel stage of every chunk            -> acc[cu][0..8]
 //     me_frac_items_kernel<1>  decision from acc, quarter-pel stage      -> acc[cu][9..17]
 //     me_frac_finish_kernel    decisions from acc, result
+#include <cstdlib>
+
 #include "me_frac.cuh"
 #include "me_kernels.h"
 
@@ -460,6 +462,9 @@ cudaError_t launch_frac_frame(const FracFrameParams& p, uint32_t* acc, int nPair
     *launches += 1;
     return cudaGetLastError();
   }
+  // default: one thread per 8x8 tile (me_frac_tile.cu); VTMME_FRAC_VARIANT=items keeps the warp-per-chunk kernels below
+  static const bool useItems = [] { const char* v = getenv("VTMME_FRAC_VARIANT"); return v && v[0] == 'i'; }();
+  if (!useItems) return launch_frac_frame_tiles(p, nPairs, st, launches);
   if ((e = cudaMemsetAsync(acc, 0, frac_frame_acc_bytes(p.g, nPairs), st)) != cudaSuccess) return e;
   const int nAll = frame_items(p.g), nSmall = frame_items_small(p.g);
   ip.nItems   = nAll;

@@ -113,6 +113,8 @@ struct FracFrameParams
 };
 size_t      frac_frame_acc_bytes(const FrameGeom& g, int nPairs);
 cudaError_t launch_frac_frame(const FracFrameParams& p, uint32_t* acc, int nPairs, cudaStream_t st, int* launches);
+// me_frac_tile.cu: one thread per 8x8 SATD tile, one launch per CU level (what launch_frac_frame uses when fracMode != 0)
+cudaError_t launch_frac_frame_tiles(const FracFrameParams& p, int nPairs, cudaStream_t st, int* launches);
 
 // State of an xPatternSearchIntRefine call (InterSearch.cpp:4172-4282), MVs in 1/16 sample
 struct DevAmvr
