@@ -82,6 +82,58 @@ def workload_counts(pred_q=None):
     return cands, ops, ncu
 
 
+def _union_area(rects):
+    """Exact area of the union of k inclusive integer rectangles per row: rects int64 [n, k, 4] = (l, r, t, b); empty
+    rectangles have r < l.  Sweep over the (at most 2k - 1) x-intervals between sorted edges."""
+    n, k, _ = rects.shape
+    l, r, t, b = rects[..., 0], rects[..., 1] + 1, rects[..., 2], rects[..., 3] + 1     # half-open
+    ok = (r > l) & (b > t)
+    xs = np.sort(np.concatenate([np.where(ok, l, 0), np.where(ok, r, 0)], axis=1), axis=1)   # [n, 2k]
+    area = np.zeros(n, dtype=np.int64)
+    for i in range(2 * k - 1):
+        x0, x1 = xs[:, i], xs[:, i + 1]
+        cover = ok & (l <= x0[:, None]) & (r >= x1[:, None])                                # rectangles spanning the interval
+        # union of the y-intervals of the covering rectangles: sort by start, sweep
+        ts = np.where(cover, t, np.iinfo(np.int64).max // 2)
+        order = np.argsort(ts, axis=1)
+        ts = np.take_along_axis(ts, order, axis=1)
+        bs = np.take_along_axis(np.where(cover, b, np.iinfo(np.int64).min // 2), order, axis=1)
+        length = np.zeros(n, dtype=np.int64)
+        cur_end = np.full(n, np.iinfo(np.int64).min // 2)
+        for j in range(k):
+            live = bs[:, j] > ts[:, j]
+            start = np.maximum(ts[:, j], cur_end)
+            length += np.where(live & (bs[:, j] > start), bs[:, j] - start, 0)
+            cur_end = np.where(live, np.maximum(cur_end, bs[:, j]), cur_end)
+        area += length * (x1 - x0)
+    return area
+
+
+def tree_needed_ops(pred_q):
+    """Integer ops the quad-tree reuse cannot avoid with per-CU predictors (run B): the SAD of an 8x8 block is needed at
+    every displacement in the window of the block OR of any of its four ancestors (their SADs are sums over it), i.e. on
+    the union of five windows instead of one; plus the one add per parent block-candidate of workload_counts()."""
+    off = level_slices()
+    nx0, ny0 = WIDTH // 8, HEIGHT // 8
+    cx = np.tile(np.arange(nx0), ny0)
+    cy = np.repeat(np.arange(ny0), nx0)
+    rects = np.zeros((nx0 * ny0, 5, 4), dtype=np.int64)
+    rects[:, :, 1] = -1
+    adds = 0
+    for level in range(5):
+        s = 8 << level
+        nx, ny = WIDTH // s, HEIGHT // s
+        l, r, t, b = windows(level, None if pred_q is None else pred_q[off[level]:off[level + 1]])
+        if level:
+            adds += int(((r - l + 1) * (b - t + 1)).sum())
+        ax, ay = cx >> level, cy >> level
+        ok = (ax < nx) & (ay < ny)
+        idx = np.where(ok, ay * nx + ax, 0)
+        for k, arr in enumerate((l, r, t, b)):
+            rects[:, level, k] = np.where(ok, arr[idx], rects[:, level, k])
+    return 2 * 64 * int(_union_area(rects).sum()) + adds
+
+
 def frac_ops_per_pair():
     """Algorithmic integer ops of the half + quarter-pel refinement of every CU of a pair (16 ops per 8-tap
     output sample, SATD n*(3+log2 n) per 8x8 tile of n = 64 samples, 9 candidates per stage).  Half-pel stage: 2 horizontal
@@ -292,6 +344,7 @@ def run_ours(args, rank, world, local_rank):
     prm_b = FrameParams(searchRange=SR, bitDepth=10, ctuSize=CTU, lambdaMotion=LAMBDA, predSpread=33)
     cands_b = int(np.mean([workload_counts(h_pred[i])[0] for i in range(min(B, 4))]))
     ops_b = int(np.mean([workload_counts(h_pred[i])[1] for i in range(min(B, 4))]))
+    needed_b = int(np.mean([tree_needed_ops(h_pred[i]) for i in range(min(B, 2))]))
     d_res = torch.zeros(B * ncu * CU_RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
 
     def step_ids(s):
@@ -349,6 +402,10 @@ def run_ours(args, rank, world, local_rank):
                  "value": world * B * nb * cands_b / (b_ms * 1e-3), "unit": UNIT, "ms_per_step": b_ms / nb, "steps": nb,
                  "block_candidates_per_pair": cands_b,
                  "roofline_frac": B * ops_b / (float(b_kms[:, 0].mean()) * 1e-3) / peak_ops,
+                 "roofline_frac_needed_ops": B * needed_b / (float(b_kms[:, 0].mean()) * 1e-3) / peak_ops,
+                 "needed_ops_note": "per-CU-window ops (roofline_frac) undercount what a quad-tree search must do with "
+                                    "independent predictors: an 8x8 SAD is needed on the union of the windows of the block and "
+                                    "its four ancestors (tree_needed_ops: %.3g ops per pair vs %.3g)" % (needed_b, ops_b),
                  "kernel_ms": {"me_tree_sad": float(b_kms[:, 0].mean()), "me_tree_upper": float(b_kms[:, 1].mean()),
                                "me_frac_frame": float(b_kms[:, 2].mean())}}
 

@@ -275,6 +275,17 @@ int vtmme_add_avg(vtmme_ctx* ctx, const int16_t* dSrc0, const int16_t* dSrc1, in
  * clip != 0) — how the pattern of a bi-predictive search is formed from the original block and the other
  * direction's prediction (InterSearch.cpp:3317-3325).  DEVICE pointers, asynchronous. */
 int vtmme_remove_high_freq(vtmme_ctx* ctx, int16_t* dOrg, const int16_t* dPred, int64_t count, int clip, int bitDepth);
+/* BCW (bi-prediction with CU-level weights, `BCW : 1` in the random-access and low-delay-B configurations):
+ * AreaBuf<Pel>::addWeightedAvg (CommonLib/Buffer.cpp:87-121): dDst = clip((dSrc0*w0 + dSrc1*w1 + offset) >> shift) with
+ * w1 = g_BcwWeights[bcwIdx] = {-2, 3, 4, 5, 10}, w0 = 8 - w1;
+ * AreaBuf<Pel>::removeWeightHighFreq (CommonLib/Buffer.h:78-79,124; Buffer.cpp:123-140): dOrg = (dOrg*weight0 -
+ * dPred*weight1 + 2^15) >> 16 with normalizer = ((1 << 16) + |bcwWeight| / 2) / bcwWeight, weight0 = 8 * normalizer,
+ * weight1 = (8 - bcwWeight) * normalizer — the pattern of a bi-predictive search under a BCW weight
+ * (InterSearch.cpp:3317-3325 with getBcwWeight).  DEVICE pointers, asynchronous. */
+int vtmme_add_weighted_avg(vtmme_ctx* ctx, const int16_t* dSrc0, const int16_t* dSrc1, int16_t* dDst, int64_t count, int bitDepth,
+                           int bcwIdx);
+int vtmme_remove_weight_high_freq(vtmme_ctx* ctx, int16_t* dOrg, const int16_t* dPred, int64_t count, int clip, int bitDepth,
+                                  int bcwWeight);
 
 /* ---- candidate distortion (the step BEFORE the search: AMVP template cost and ME seeds) ----------
  * For one PU and a list of candidate MVs: SAD(org, xPredInterBlk(ref, mv)) per candidate, without

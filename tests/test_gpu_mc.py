@@ -6,6 +6,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
+from oracle import bindings as B  # noqa: E402
 from tests.helpers import mc_cases, oracle_mc  # noqa: E402
 from tests.test_golden import GM, iter_mc  # noqa: E402
 
@@ -108,6 +109,40 @@ def test_bipred_helpers_golden(ms):
         ms.remove_high_freq(t.data_ptr(), pred.data_ptr(), t.numel(), clip)
         ms.synchronize()
         assert np.array_equal(t.cpu().numpy(), GM["hf_out%d" % clip])
+
+
+def test_bcw_helpers(ms, oracle_lib):
+    """BCW forms of the bi-prediction helpers: addWeightedAvg for the five weights, removeWeightHighFreq for the weights a
+    search can see (g_BcwWeights and 8 - g_BcwWeights), clipped and unclipped, 8 and 10 bit — against the oracle, which is
+    pinned on the reference's own AreaBuf members (tests/test_oracle_vs_ref.py)."""
+    import torch
+    rng = np.random.default_rng(77)
+    n = 4096 + 5
+    for bd in (8, 10):
+        lo, hi = -8192, ((1 << bd) - 1 << (14 - bd)) - 8192        # range of 14-bit intermediate predictions
+        a = rng.integers(lo, hi + 1, n).astype(np.int16)
+        b = rng.integers(lo, hi + 1, n).astype(np.int16)
+        da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+        for idx in range(5):
+            d = torch.zeros_like(da)
+            torch.cuda.synchronize()
+            ms.add_weighted_avg(da.data_ptr(), db.data_ptr(), d.data_ptr(), n, idx, bd)
+            ms.synchronize()
+            want = np.zeros(n, np.int16)
+            oracle_lib.vo_add_weighted_avg(B.ptr(a), B.ptr(b), B.ptr(want), n, bd, idx)
+            assert np.array_equal(d.cpu().numpy(), want), (bd, idx)
+        org = rng.integers(0, 1 << bd, n).astype(np.int16)
+        pred = rng.integers(0, 1 << bd, n).astype(np.int16)
+        dpred = torch.from_numpy(pred).cuda()
+        for w in (-2, 3, 5, 10, 4):
+            for clip in (0, 1):
+                t = torch.from_numpy(org.copy()).cuda()
+                torch.cuda.synchronize()
+                ms.remove_weight_high_freq(t.data_ptr(), dpred.data_ptr(), n, w, clip, bd)
+                ms.synchronize()
+                want = org.copy()
+                oracle_lib.vo_remove_weight_high_freq(B.ptr(want), B.ptr(pred), n, clip, bd, w)
+                assert np.array_equal(t.cpu().numpy(), want), (bd, w, clip)
 
 
 def test_mc_errors(ms):

@@ -232,6 +232,32 @@ __global__ void __launch_bounds__(256) remove_high_freq_kernel(int16_t* __restri
   }
 }
 
+// BCW forms (Buffer.cpp addWeightedAvg / Buffer.h:124 removeWeightHighFreq).  addWeightedAvg: (a*w0 + b*w1 + offset) >> shift,
+// clipped; removeWeightHighFreq: (org*weight0 - pred*weight1 + 2^15) >> 16 with the 16-bit normaliser of the BCW weight.
+__global__ void __launch_bounds__(256) add_weighted_avg_kernel(const int16_t* __restrict__ a, const int16_t* __restrict__ b,
+                                                               int16_t* __restrict__ d, long long n, int w0, int w1, int shift,
+                                                               int offset, int maxv)
+{
+  const long long stride = (long long) gridDim.x * blockDim.x;
+  for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    const int v = ((int) a[i] * w0 + (int) b[i] * w1 + offset) >> shift;
+    d[i]        = (int16_t) min(max(v, 0), maxv);
+  }
+}
+
+__global__ void __launch_bounds__(256) remove_weight_high_freq_kernel(int16_t* __restrict__ d, const int16_t* __restrict__ s,
+                                                                      long long n, int clip, int maxv, int weight0, int weight1)
+{
+  const long long stride = (long long) gridDim.x * blockDim.x;
+  for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    int v = ((int) d[i] * weight0 - (int) s[i] * weight1 + (1 << 15)) >> 16;
+    if (clip) v = min(max(v, 0), maxv);
+    d[i] = (int16_t) v;
+  }
+}
+
 int elementwise_grid(long long n)
 {
   long long g = (n + 255) / 256;
@@ -269,6 +295,25 @@ cudaError_t launch_add_avg(const int16_t* a, const int16_t* b, int16_t* d, long 
   if (n - nVec * 8)
     add_avg_kernel<<<elementwise_grid(n - nVec * 8), 256, 0, st>>>(a + nVec * 8, b + nVec * 8, d + nVec * 8, n - nVec * 8, shift,
                                                                     offset, maxv);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_add_weighted_avg(const int16_t* a, const int16_t* b, int16_t* d, long long n, int bitDepth, int bcwIdx,
+                                    cudaStream_t st)
+{
+  static const int bcwWeights[5] = { -2, 3, 4, 5, 10 };   // g_BcwWeights (CommonLib/Rom.cpp), BCW_DEFAULT = 2
+  const int w1 = bcwWeights[bcwIdx], w0 = 8 - w1;
+  const int hr = 14 - bitDepth > 2 ? 14 - bitDepth : 2, shift = hr + 3, offset = (1 << (shift - 1)) + (8192 << 3);
+  add_weighted_avg_kernel<<<elementwise_grid(n), 256, 0, st>>>(a, b, d, n, w0, w1, shift, offset, (1 << bitDepth) - 1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_remove_weight_high_freq(int16_t* d, const int16_t* s, long long n, int clip, int bitDepth, int bcwWeight,
+                                           cudaStream_t st)
+{
+  const int normalizer = ((1 << 16) + (bcwWeight > 0 ? (bcwWeight >> 1) : -(bcwWeight >> 1))) / bcwWeight;
+  remove_weight_high_freq_kernel<<<elementwise_grid(n), 256, 0, st>>>(d, s, n, clip, (1 << bitDepth) - 1, normalizer * 8,
+                                                                      (8 - bcwWeight) * normalizer);
   return cudaGetLastError();
 }
 

@@ -36,13 +36,13 @@ __host__ __device__ constexpr uint32_t pack4(int a, int b, int c, int d)
 }
 // luma taps of the quarter-pel phases 0, 1/4, 1/2, 3/4 (c_lumaFilter rows 0, 4, 8, 12; InterpolationFilter.cpp:77-95),
 // four signed bytes per word: [phase][0] = taps 0..3, [phase][1] = taps 4..7
-__device__ const uint32_t c_tapW[4][2] = { { pack4(0, 0, 0, 64), pack4(0, 0, 0, 0) },
+__constant__ uint32_t c_tapW[4][2] = { { pack4(0, 0, 0, 64), pack4(0, 0, 0, 0) },
                                            { pack4(-1, 4, -10, 58), pack4(17, -5, 1, 0) },
                                            { pack4(-1, 4, -11, 40), pack4(40, -11, 4, -1) },
                                            { pack4(0, 1, -5, 17), pack4(58, -10, 4, -1) } };
 // (dx + 1) * 3 + (dy + 1) -> position in s_acMvRefineH / s_acMvRefineQ (me_frac.cuh c_refineH / c_refineQ)
-__device__ const int8_t c_orderH[9] = { 5, 3, 7, 1, 0, 2, 6, 4, 8 };
-__device__ const int8_t c_orderQ[9] = { 3, 5, 7, 1, 0, 2, 4, 6, 8 };
+__constant__ int8_t c_orderH[9] = { 5, 3, 7, 1, 0, 2, 6, 4, 8 };
+__constant__ int8_t c_orderQ[9] = { 3, 5, 7, 1, 0, 2, 4, 6, 8 };
 
 template <int LEVEL>
 struct TileCfg
@@ -138,7 +138,7 @@ __device__ __forceinline__ void tile_hpass(const uint32_t* __restrict__ patchTil
   const int      cA = (int) c_tapW[px][0], cB = (int) c_tapW[px][1];
   const int      shift = 6 - hr, negOff = -(8192 << shift);
   const uint32_t sh = (uint32_t) (ix + 1) * 16u;   // window = patch columns ix+1 ..: 0 or one sample to the right
-#pragma unroll
+#pragma unroll 4   // not 16: the kernel's code should stay well inside the instruction cache
   for (int r = 0; r < 16; r++)
   {
     const uint4    a = *reinterpret_cast<const uint4*>(patchTile + r * rowWords);
@@ -209,7 +209,7 @@ __device__ __forceinline__ uint32_t tile_candidate(const uint4* __restrict__ str
 #pragma unroll
   for (int i = 0; i < 64; i++)
   {
-    const int v = min(max(sum[i] >> shift, 0), maxv);
+    const int v = __vimin_s32_relu(sum[i] >> shift, maxv);   // clip to [0, maxv] in one instruction
     f[i]        = org[i] - __int_as_float(v);   // exact: both are integers below 2^24 carried as (de)normal floats
   }
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -274,31 +274,13 @@ __global__ void __launch_bounds__(TileCfg<LEVEL>::THREADS) me_frac_tile_kernel(F
     if (cuBase + t < nLevel)
     {
       const unsigned long long key = p.keys[(size_t) pair * nCU + p.g.off[LEVEL] + cuBase + t];
-      mv = make_int2(key_dx(key), key_dy(key));
+      if (key != ~0ull) mv = make_int2(key_dx(key), key_dy(key));   // ~0: no candidate (the search reported an error)
     }
     sMv[t] = mv;
   }
   if (LEVEL >= 3)
     for (int i = t; i < Cfg::CPC * 18; i += Cfg::THREADS) sAcc[i] = 0;
   __syncthreads();
-  // reference patches: rows -4 .. S+3, columns -4 .. S+3 around the block at the integer MV, 16-bit pairs; a patch that
-  // starts at an odd sample is assembled from aligned words
-  for (int i = t; i < Cfg::CPC * Cfg::ROWS * Cfg::PWW; i += Cfg::THREADS)
-  {
-    const int c = i / (Cfg::ROWS * Cfg::PWW), rem = i - c * (Cfg::ROWS * Cfg::PWW);
-    const int row = rem / Cfg::PWW, wj = rem - row * Cfg::PWW;
-    const int li = cuBase + c;
-    if (li >= nLevel) continue;
-    const int2 mv = sMv[c];
-    const int  x = (li % p.g.nx[LEVEL]) * Cfg::S, y = (li / p.g.nx[LEVEL]) * Cfg::S;
-    const int16_t*  g  = ref.origin + (ptrdiff_t) (y + mv.y - 4 + row) * ref.stride + (x + mv.x - 4) + 2 * wj;
-    const uint32_t* gw = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(g) & ~(uintptr_t) 3);
-    uint32_t w = gw[0];
-    if (reinterpret_cast<uintptr_t>(g) & 2) w = __funnelshift_r(w, gw[1], 16);
-    sPatch[c * Cfg::CU_WORDS + row * Cfg::PWW + wj] = w;
-  }
-  __syncthreads();
-
   int cu, tx, ty;
   tile_of_thread<LEVEL>(t, cu, tx, ty);
   const int  li    = cuBase + cu;
@@ -306,25 +288,50 @@ __global__ void __launch_bounds__(TileCfg<LEVEL>::THREADS) me_frac_tile_kernel(F
   const int  liC   = valid ? li : 0;
   const int  x = (liC % p.g.nx[LEVEL]) * Cfg::S, y = (liC / p.g.nx[LEVEL]) * Cfg::S;
   const int  cuIdx = p.g.off[LEVEL] + liC;
-  const int2 mv    = sMv[cu];
   short2 pr = make_short2(0, 0);
   if (p.predQ) pr = p.predQ[(size_t) pair * nCU + cuIdx];
-
-  // the thread's original tile as integer-valued floats (samples of a picture are >= 0)
-  float org[64];
+  // the thread's original tile as integer-valued floats (samples of a picture are >= 0); the loads are issued before the
+  // patch is staged so that their latency is hidden behind it
+  uint4 orgRaw[8];
   {
     const int16_t* o = cur.origin + (size_t) (y + ty * 8) * cur.stride + x + tx * 8;
 #pragma unroll
-    for (int r = 0; r < 8; r++)
+    for (int r = 0; r < 8; r++) orgRaw[r] = *reinterpret_cast<const uint4*>(o + (size_t) r * cur.stride);
+  }
+  // reference patches: rows -4 .. S+3, columns -4 .. S+3 around the block at the integer MV, 16-bit pairs.  One unit = 16
+  // bytes of a patch row, assembled from five aligned words (a patch may start at an odd sample); several units in flight
+  // per thread.
+  {
+    constexpr int UPR = Cfg::PWW / 4, UNITS = Cfg::CPC * Cfg::ROWS * UPR;
+    const int lastCu = nLevel - 1 - cuBase;   // CUs past the end of the level re-read the last one (never used)
+#pragma unroll 4
+    for (int i = t; i < UNITS; i += Cfg::THREADS)
     {
-      const uint4    v = *reinterpret_cast<const uint4*>(o + (size_t) r * cur.stride);
-      const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+      const int c = i / (Cfg::ROWS * UPR), rem = i - c * (Cfg::ROWS * UPR);
+      const int row = rem / UPR, u = rem - row * UPR;
+      const int cc = min(c, lastCu), lj = cuBase + cc;
+      const int2 cmv = sMv[cc];
+      const int  px = (lj % p.g.nx[LEVEL]) * Cfg::S, py = (lj / p.g.nx[LEVEL]) * Cfg::S;
+      const int16_t*  g  = ref.origin + (ptrdiff_t) (py + cmv.y - 4 + row) * ref.stride + (px + cmv.x - 4) + 8 * u;
+      const uint32_t* gw = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(g) & ~(uintptr_t) 3);
+      const uint32_t  sh = (uint32_t) (reinterpret_cast<uintptr_t>(g) & 2) * 8u;
+      const uint32_t  w0 = gw[0], w1 = gw[1], w2 = gw[2], w3 = gw[3], w4 = gw[4];
+      *reinterpret_cast<uint4*>(sPatch + c * Cfg::CU_WORDS + row * Cfg::PWW + 4 * u) =
+        make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+    }
+  }
+  __syncthreads();
+  const int2 mv = sMv[cu];
+  float org[64];
 #pragma unroll
-      for (int j = 0; j < 4; j++)
-      {
-        org[r * 8 + 2 * j]     = __uint_as_float(w[j] & 0xffffu);
-        org[r * 8 + 2 * j + 1] = __uint_as_float(w[j] >> 16);
-      }
+  for (int r = 0; r < 8; r++)
+  {
+    const uint32_t w[4] = { orgRaw[r].x, orgRaw[r].y, orgRaw[r].z, orgRaw[r].w };
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+    {
+      org[r * 8 + 2 * j]     = __uint_as_float(w[j] & 0xffffu);
+      org[r * 8 + 2 * j + 1] = __uint_as_float(w[j] >> 16);
     }
   }
   const uint32_t* patchTile = sPatch + cu * Cfg::CU_WORDS + (ty * 8) * Cfg::PWW + tx * 4;

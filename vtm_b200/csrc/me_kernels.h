@@ -228,6 +228,8 @@ cudaError_t launch_mc_sad(const McSadTile* dTiles, int nTiles, int bitDepth, int
 cudaError_t launch_mc_batch(int comp, const McTile* dTiles, int nTiles, int bi, int bitDepth, int useAltHpel, cudaStream_t st);
 cudaError_t launch_add_avg(const int16_t* a, const int16_t* b, int16_t* d, long long n, int bitDepth, cudaStream_t st);
 cudaError_t launch_remove_high_freq(int16_t* d, const int16_t* s, long long n, int clip, int bitDepth, cudaStream_t st);
+cudaError_t launch_add_weighted_avg(const int16_t* a, const int16_t* b, int16_t* d, long long n, int bitDepth, int bcwIdx, cudaStream_t st);
+cudaError_t launch_remove_weight_high_freq(int16_t* d, const int16_t* s, long long n, int clip, int bitDepth, int bcwWeight, cudaStream_t st);
 
 // GOP-based temporal filter motion estimation (mctf_kernels.cu)
 struct MctfLevelParams

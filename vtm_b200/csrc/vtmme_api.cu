@@ -1401,6 +1401,30 @@ extern "C" int vtmme_remove_high_freq(vtmme_ctx* ctx, int16_t* dOrg, const int16
   return VTMME_OK;
 }
 
+extern "C" int vtmme_add_weighted_avg(vtmme_ctx* ctx, const int16_t* dSrc0, const int16_t* dSrc1, int16_t* dDst, int64_t count,
+                                      int bitDepth, int bcwIdx)
+{
+  if (!ctx) return VTMME_ERR_ARG;
+  if (!dSrc0 || !dSrc1 || !dDst || count <= 0 || bitDepth < 8 || bitDepth > 10 || bcwIdx < 0 || bcwIdx > 4)
+    return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_add_weighted_avg", "bad argument");
+  VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  VTMME_CUDA_CHECK(ctx, launch_add_weighted_avg(dSrc0, dSrc1, dDst, count, bitDepth, bcwIdx, ctx->stream));
+  ctx->launches += 1;
+  return VTMME_OK;
+}
+
+extern "C" int vtmme_remove_weight_high_freq(vtmme_ctx* ctx, int16_t* dOrg, const int16_t* dPred, int64_t count, int clip,
+                                             int bitDepth, int bcwWeight)
+{
+  if (!ctx) return VTMME_ERR_ARG;
+  if (!dOrg || !dPred || count <= 0 || bitDepth < 8 || bitDepth > 10 || bcwWeight == 0 || bcwWeight < -8 || bcwWeight > 16)
+    return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_remove_weight_high_freq", "bad argument");
+  VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  VTMME_CUDA_CHECK(ctx, launch_remove_weight_high_freq(dOrg, dPred, count, clip, bitDepth, bcwWeight, ctx->stream));
+  ctx->launches += 1;
+  return VTMME_OK;
+}
+
 // ---- candidate distortion (template cost / seeds) -------------------------------------------------------------------
 static_assert(sizeof(vtmme_dmvr_block) == sizeof(DevDmvrBlock) && sizeof(vtmme_dmvr_result) == sizeof(DevDmvrResult),
               "DMVR layouts must match");

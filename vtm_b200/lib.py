@@ -19,7 +19,7 @@ SYMBOLS = ["vtmme_create", "vtmme_destroy", "vtmme_last_error", "vtmme_set_strea
            "vtmme_launch_count", "vtmme_set_profiling", "vtmme_frame_kernel_ms", "vtmme_upload_picture", "vtmme_upload_picture_async", "vtmme_upload_picture_device", "vtmme_release_picture",
            "vtmme_search", "vtmme_frame_cu_count", "vtmme_search_frames", "vtmme_search_frames_device",
            "vtmme_dist_batch", "vtmme_dist_host", "vtmme_interp_batch", "vtmme_interp_host", "vtmme_filter_host",
-           "vtmme_mc_batch", "vtmme_mc_host", "vtmme_add_avg", "vtmme_remove_high_freq", "vtmme_cand_sad", "vtmme_dmvr_refine", "vtmme_mctf_me", "vtmme_mctf_apply_motion", "vtmme_int_peak"]
+           "vtmme_mc_batch", "vtmme_mc_host", "vtmme_add_avg", "vtmme_remove_high_freq", "vtmme_add_weighted_avg", "vtmme_remove_weight_high_freq", "vtmme_cand_sad", "vtmme_dmvr_refine", "vtmme_mctf_me", "vtmme_mctf_apply_motion", "vtmme_int_peak"]
 
 
 class CAmvr(C.Structure):
@@ -147,6 +147,8 @@ def load_library():
     L.vtmme_mc_host.argtypes = [P, I, I, I, I, I, C.POINTER(CMcBlock), P]
     L.vtmme_add_avg.argtypes = [P, P, P, P, I64, I]
     L.vtmme_remove_high_freq.argtypes = [P, P, P, I64, I, I]
+    L.vtmme_add_weighted_avg.argtypes = [P, P, P, P, I64, I, I]
+    L.vtmme_remove_weight_high_freq.argtypes = [P, P, P, I64, I, I, I]
     L.vtmme_cand_sad.argtypes = [P, I, I, I, C.POINTER(CCandJob), C.POINTER(C.c_uint64)]
     L.vtmme_dmvr_refine.argtypes = [P, I, I, I, I, I, C.POINTER(CDmvrBlock), C.POINTER(CDmvrResult)]
     L.vtmme_mctf_me.argtypes = [P, I, C.POINTER(C.c_int32), C.POINTER(C.c_int32), I, P]

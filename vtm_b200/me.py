@@ -338,6 +338,14 @@ class MotionSearch:
         self._check(self.L.vtmme_remove_high_freq(self.ctx, C.c_void_p(d_org), C.c_void_p(d_pred), count, clip, bit_depth),
                     "vtmme_remove_high_freq")
 
+    def add_weighted_avg(self, d_src0, d_src1, d_dst, count, bcw_idx, bit_depth=10):
+        self._check(self.L.vtmme_add_weighted_avg(self.ctx, C.c_void_p(d_src0), C.c_void_p(d_src1), C.c_void_p(d_dst), count,
+                                                  bit_depth, bcw_idx), "vtmme_add_weighted_avg")
+
+    def remove_weight_high_freq(self, d_org, d_pred, count, bcw_weight, clip=0, bit_depth=10):
+        self._check(self.L.vtmme_remove_weight_high_freq(self.ctx, C.c_void_p(d_org), C.c_void_p(d_pred), count, clip, bit_depth,
+                                                         bcw_weight), "vtmme_remove_weight_high_freq")
+
     # ---- GOP-based temporal filter ---------------------------------------------------------------------------
     def mctf_me(self, org_ids, ref_ids, width, height, bit_depth=10):
         """EncTemporalFilter::motionEstimation for every (original, reference) pair of uploaded pictures.
