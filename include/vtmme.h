@@ -336,6 +336,54 @@ typedef struct
 int vtmme_dmvr_refine(vtmme_ctx* ctx, int refPic0, int refPic1, int bitDepth, int maxCu, int n, const vtmme_dmvr_block* blocks,
                       vtmme_dmvr_result* results);
 
+/* ---- symmetric-MVD search -------------------------------------------------------------------------
+ * InterSearch::xSymmetricMotionEstimation (EncoderLib/InterSearch.cpp:4506-4518): the MV of the searched list moves on a
+ * diamond (at most 8 >> imv rounds) and once on a cross (xSymmeticRefineMvSearch :4393-4503), the MV of the other list
+ * mirrors the MV difference; every candidate costs the MVD rate plus xGetSymmetricCost (:4341-4391): both 8-tap
+ * predictions at the clipped MVs, 2*org - predCur (removeHighFreq, or removeWeightHighFreq under a BCW weight), SATD
+ * (HadamardME) or SAD against predTar, weighted by xGetMEDistortionWeight.  MVs in 1/16 sample. */
+typedef struct
+{
+  int32_t        curPic;               /* uploaded original picture (ignored when org != NULL)                        */
+  int32_t        refPicCur, refPicTar; /* uploaded reference pictures of the searched list and of the other list       */
+  int32_t        x, y, w, h;           /* PU luma rectangle, w and h powers of two in 8..128                           */
+  const int16_t* org;                  /* optional HOST pattern (w x h at orgStride) instead of the block of curPic    */
+  int32_t        orgStride;
+  int32_t        maxCu;                /* sps.getMaxCUWidth() of the MV clip (clipMvInPic), <= 128                     */
+  int32_t        bitDepth;
+  int32_t        imv;                  /* cu.imv: 0 quarter, 1 integer, 2 four-sample, 3 half sample (alt. filter)     */
+  int32_t        curPredX, curPredY;   /* rcMvCurPred                                                                  */
+  int32_t        tarPredX, tarPredY;   /* rcMvTarPred                                                                  */
+  int32_t        curMvX, curMvY;       /* rCurMvField.mv on entry                                                      */
+  int32_t        tarMvX, tarMvY;       /* rTarMvField.mv on entry                                                      */
+  int32_t        clipBiPred;           /* EncCfg::getClipForBiPredMeEnabled()                                          */
+  int32_t        useHad;               /* !slice->getDisableSATDForRD()                                                */
+  int32_t        bcwIdx;               /* cu.BcwIdx, 0..4 (2 = BCW_DEFAULT)                                            */
+  double         lambdaMotion;         /* RdCost::m_motionLambda (selectMotionLambda)                                  */
+  uint64_t       cost;                 /* ruiCost on entry                                                             */
+} vtmme_smvd;
+
+typedef struct
+{
+  int32_t  curMvX, curMvY, tarMvX, tarMvY;   /* rCurMvField.mv / rTarMvField.mv on return */
+  uint64_t cost;                             /* ruiCost on return                         */
+} vtmme_smvd_result;
+
+/* jobs, results: HOST arrays of n entries (n <= 65536); one launch for all of them.  Synchronous. */
+int vtmme_smvd_search(vtmme_ctx* ctx, int n, const vtmme_smvd* jobs, vtmme_smvd_result* results);
+
+/* The prediction of ONE list after DMVR — InterPrediction::xFinalPaddedMCForDMVR (CommonLib/InterPrediction.cpp:1845-1917) over the
+ * buffer xPrefetch (:1664-1708) filled and xPad (:1710-1730) extended: the 8-tap (comp 0) / 4-tap (comp 1, 4:2:0 chroma
+ * plane uploaded as a picture of its own) filter of xPredInterBlk with bi = true (14-bit intermediates for
+ * vtmme_add_avg) at the fraction of clip(refined MV), reading the (w + taps - 1) x (h + taps - 1) window at the integer
+ * part of clip(merge MV - (taps/2 - 1) samples) with replicated borders instead of the picture.  blocks[i]: {x, y, w, h} =
+ * the LUMA rectangle of the sub-block, mvL0 = the list's merge MV, mvL1 = the list's refined MV (merge MV +- mvdL0SubPu),
+ * both 1/16 luma sample.  A chroma block that did not move is the plain vtmme_mc_batch prediction (the reference reads
+ * the picture then, :1871).  dst: HOST, predictions packed (block i at the sum of earlier (w*h) >> (2*comp)).
+ * Synchronous. */
+int vtmme_dmvr_final_mc(vtmme_ctx* ctx, int comp, int refPic, int bitDepth, int maxCu, int n, const vtmme_dmvr_block* blocks,
+                        int16_t* dst);
+
 /* ---- GOP-based temporal filter: motion estimation ---------------------------------
  * EncTemporalFilter::motionEstimation (EncoderLib/EncTemporalFilter.cpp:448-466): the four-level hierarchical block
  * search of a reference frame against the original (16x16 blocks on the 1/4, 1/2 and full resolution pictures, then
@@ -353,6 +401,17 @@ int vtmme_mctf_me(vtmme_ctx* ctx, int nPairs, const int32_t* orgPics, const int3
  * (the reference leaves them unwritten).  Synchronous. */
 int vtmme_mctf_apply_motion(vtmme_ctx* ctx, int srcPic, int csx, int csy, const int32_t* mv, int mvStride, int mvRows,
                             int bitDepth, int16_t* dst);
+
+/* EncTemporalFilter::bilateralFilter (EncTemporalFilter.cpp:555-622), the weighting of one component: every sample of the
+ * uploaded original plane orgPic is replaced by the weighted mean of itself (weight 1) and the co-located samples of the
+ * numRefs (<= 8) uploaded planes corrPics[i] — the neighbouring pictures after vtmme_mctf_apply_motion.  The weight of a
+ * neighbouring sample depends only on |refVal - orgVal| and the picture: weights = HOST array of numRefs tables of
+ * (1 << bitDepth) doubles, weights[i][d] = weightScaling * m_refStrengths[row][min(1, |origOffset_i| - 1)] *
+ * exp(-(d * 1024 / 2^bitDepth)^2 / (2 * sigmaSq)) as the caller's own libm evaluates it (:595-610) — the device then only
+ * multiplies, adds and divides IEEE doubles in the reference's order, and every output sample equals the reference's.
+ * dst: HOST, width x height samples, packed.  Synchronous. */
+int vtmme_mctf_bilateral(vtmme_ctx* ctx, int orgPic, int numRefs, const int32_t* corrPics, const double* weights, int bitDepth,
+                         int16_t* dst);
 
 /* ---- measurement helpers ------------------------------------------------------------------------
  * Per-kernel timing of the frame path: when enabled, vtmme_search_frames[_device] brackets each of its

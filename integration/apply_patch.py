@@ -80,6 +80,7 @@ def main():
   auto cudaSearch = [&]( const bool tz, const bool tzFast, const Mv& tzStart )
   {
     vtmcuda::SearchIn in;
+    memset( &in, 0, sizeof( in ) );   // identical inputs = identical bytes (the per-PU batching compares requests)
     in.refPic       = pu.cu->slice->getRefPic( eRefPicList, iRefIdxPred );
     in.x            = pu.Y().x;
     in.y            = pu.Y().y;
@@ -150,11 +151,20 @@ def main():
   const bool cudaTzUsable = cudaUsable && !m_pcEncCfg->getMCTSEncConstraint() && !m_pcEncCfg->getUseHashME()
                             && ( m_motionEstimationSearchMethod == MESEARCH_DIAMOND || m_motionEstimationSearchMethod == MESEARCH_DIAMOND_ENHANCED
                                  || ( m_motionEstimationSearchMethod == MESEARCH_SELECTIVE && m_iSearchRange <= 128 ) );
+  if( vtmcuda::collecting() )   // collect pass: a search the GPU does not take is left to the real pass
+  {
+    const bool cudaFull = ( m_motionEstimationSearchMethod == MESEARCH_FULL ) || bBi || bQTBTMV;
+    if( cudaFull ? !cudaUsable : !cudaTzUsable )
+    {
+      return;
+    }
+  }
 """ + s[second:]
         s = once(s, "    xPatternSearch( cStruct, rcMv, ruiCost);\n", """\
     if( cudaUsable )
     {
       cudaSearch( false, false, Mv() );   // libvtmme: integer full search + refinement
+      if( vtmcuda::collecting() ) return;   // collect pass of predInterSearch: the search runs in the PU's batch
     }
     else
     {
@@ -165,6 +175,7 @@ def main():
     if( cudaTzUsable )
     {
       cudaSearch( true, true, rcMv );   // libvtmme: xTZSearch with the fast settings + refinement
+      if( vtmcuda::collecting() ) return;
     }
     else
     {
@@ -175,6 +186,7 @@ def main():
     if( cudaTzUsable )
     {
       cudaSearch( true, false, rcMv );   // libvtmme: xTZSearch (FastSearch=1/3) + refinement
+      if( vtmcuda::collecting() ) return;
     }
     else
     {
@@ -209,6 +221,44 @@ def main():
       xPatternSearchIntRefine( pu, cStruct, rcMv, rcMvPred, riMVPIdx, ruiBits, ruiCost, amvpInfo, fWeight);
     }
 """)
+        # 5. predInterSearch: before its (list, reference) loop of uni-predictive searches, the same loop in collect mode —
+        # the searches of all reference pictures of the PU then run in ONE vtmme_search call (VtmCudaME.h)
+        anchor = "      //  Uni-directional prediction\n      for ( int iRefList = 0; iRefList < iNumPredDir; iRefList++ )\n"
+        pos = s.index(anchor, s.index("void InterSearch::predInterSearch("))
+        s = s[:pos] + """\
+      if( vtmcuda::enabled() && vtmcuda::batching() )   // libvtmme: collect the uni-predictive searches of this PU
+      {
+        vtmcuda::beginCollect();
+        for( int cList = 0; cList < iNumPredDir; cList++ )
+        {
+          const RefPicList cRefPicList = cList ? REF_PIC_LIST_1 : REF_PIC_LIST_0;
+          for( int cRefIdx = 0; cRefIdx < cs.slice->getNumRefIdx( cRefPicList ); cRefIdx++ )
+          {
+            if( m_pcEncCfg->getFastMEForGenBLowDelayEnabled() && cList == 1 && cs.slice->getList1IdxToList0Idx( cRefIdx ) >= 0 )
+            {
+              continue;   // the loop below copies list 0's result for this picture
+            }
+            uint32_t cBits = uiMbBits[cList];
+            if( cs.slice->getNumRefIdx( cRefPicList ) > 1 )
+            {
+              cBits += cRefIdx + 1;
+              if( cRefIdx == cs.slice->getNumRefIdx( cRefPicList ) - 1 )
+              {
+                cBits--;
+              }
+            }
+            Mv         cPred, cMvOut;
+            AMVPInfo   cAmvp;
+            Distortion cDist = 0, cCost = 0;
+            xEstimateMvPredAMVP( pu, origBuf, cRefPicList, cRefIdx, cPred, cAmvp, false, &cDist );
+            int cMvpIdx = pu.mvpIdx[cRefPicList];
+            cBits += m_auiMVPIdxCost[cMvpIdx][AMVP_MAX_NUM_CANDS];
+            xMotionEstimation( pu, origBuf, cRefPicList, cPred, cRefIdx, cMvOut, cMvpIdx, cBits, cCost, cAmvp );
+          }
+        }
+        vtmcuda::endCollect();
+      }
+""" + s[pos:]
         return s
     edit(os.path.join(lib, "EncoderLib", "InterSearch.cpp"), inter)
     print("patched tree:", dst)

@@ -5,7 +5,9 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <map>
+#include <vector>
 
 #include "CommonLib/CommonDef.h"
 #include "CommonLib/Picture.h"
@@ -22,6 +24,19 @@ uint64_t   g_tzSearches = 0;   // searches whose integer stage was xTZSearch / x
 uint64_t   g_intRefines = 0;   // searches whose xPatternSearchIntRefine ran on the GPU too
 double     g_searchSec  = 0;   // wall time spent inside vtmme_search (upload of the pattern, kernels, sync)
 int        g_nextPicId  = 1;
+uint64_t   g_batchCalls = 0;   // vtmme_search calls that carried the collected searches of a PU
+uint64_t   g_batchJobs  = 0;   // searches run in such calls
+uint64_t   g_batchHits  = 0;   // requests answered from a batch
+bool       g_collecting = false;
+
+struct Prefetched
+{
+  alignas( 8 ) unsigned char raw[sizeof( vtmcuda::SearchIn )];   // the request byte for byte (the caller zero-fills it first)
+  vtmcuda::SearchOut         out;
+  bool                       valid;
+  const vtmcuda::SearchIn&   in() const { return *reinterpret_cast<const vtmcuda::SearchIn*>( raw ); }
+};
+std::vector<Prefetched> g_prefetched;
 
 struct Uploaded
 {
@@ -80,9 +95,11 @@ bool tableHooksEnabled()
   return e != 0;
 }
 
-void search( const SearchIn& in, SearchOut& out )
+namespace
 {
-  vtmme_job j;
+// SearchIn -> vtmme_job (+ the AMVR / TZ descriptors it points at)
+void fillJob( const SearchIn& in, vtmme_job& j, vtmme_amvr& a, vtmme_tz& t )
+{
   j.curPic   = 0;
   j.refPic   = pictureId( in.refPic );
   j.x        = in.x;
@@ -112,7 +129,6 @@ void search( const SearchIn& in, SearchOut& out )
   j.useAltHpel   = in.useAltHpel;
   j.fracMode     = in.doFrac;
   j.lambdaMotion = in.lambdaMotion;
-  vtmme_amvr a;
   j.amvr = nullptr;
   if( in.doFrac == 2 )
   {
@@ -133,7 +149,6 @@ void search( const SearchIn& in, SearchOut& out )
     a.fWeight = in.fWeight;
     j.amvr    = &a;
   }
-  vtmme_tz t;
   j.tz = nullptr;
   if( in.tzSearch )
   {
@@ -157,14 +172,11 @@ void search( const SearchIn& in, SearchOut& out )
     t.selective       = in.tzSelective;
     t.stagedSad       = in.subShiftMode == 1;
     j.tz              = &t;
-    g_tzSearches++;
   }
-  vtmme_result r;
-  vtmme_ctx*   c  = ctx();
-  const auto   t0 = std::chrono::steady_clock::now();
-  const int    rc = vtmme_search( c, &j, 1, &r );
-  g_searchSec += std::chrono::duration<double>( std::chrono::steady_clock::now() - t0 ).count();
-  CHECK( rc != VTMME_OK, vtmme_last_error( g_ctx ) );
+}
+
+void fillOut( const vtmme_result& r, SearchOut& out )
+{
   out.mvX      = r.mvX;
   out.mvY      = r.mvY;
   out.intSad   = r.intSad;
@@ -178,6 +190,97 @@ void search( const SearchIn& in, SearchOut& out )
   out.mvpIdx   = r.mvpIdx;
   out.bits     = r.bits;
   out.cost     = r.cost;
+}
+}   // namespace
+
+bool batching()
+{
+  static int e = -1;
+  if( e < 0 )
+  {
+    const char* v = getenv( "VTMME_BATCH" );
+    e             = ( v && v[0] == '0' ) ? 0 : 1;
+  }
+  return e != 0;
+}
+
+bool collecting() { return g_collecting; }
+
+void beginCollect()
+{
+  g_prefetched.clear();
+  g_collecting = true;
+}
+
+void endCollect()
+{
+  g_collecting = false;
+  // the library takes full-search and TZ jobs in separate calls
+  for( int kind = 0; kind < 2; kind++ )
+  {
+    std::vector<int> idx;
+    for( size_t i = 0; i < g_prefetched.size(); i++ )
+      if( (int) g_prefetched[i].in().tzSearch == kind ) idx.push_back( (int) i );
+    if( idx.size() < 2 ) continue;   // a single search gains nothing from being early
+    const int                 n = (int) idx.size();
+    std::vector<vtmme_job>    jobs( n );
+    std::vector<vtmme_amvr>   amvr( n );
+    std::vector<vtmme_tz>     tz( n );
+    std::vector<vtmme_result> res( n );
+    for( int k = 0; k < n; k++ ) fillJob( g_prefetched[idx[k]].in(), jobs[k], amvr[k], tz[k] );
+    vtmme_ctx* c  = ctx();
+    const auto t0 = std::chrono::steady_clock::now();
+    const int  rc = vtmme_search( c, jobs.data(), n, res.data() );
+    g_searchSec += std::chrono::duration<double>( std::chrono::steady_clock::now() - t0 ).count();
+    CHECK( rc != VTMME_OK, vtmme_last_error( g_ctx ) );
+    for( int k = 0; k < n; k++ )
+    {
+      fillOut( res[k], g_prefetched[idx[k]].out );
+      g_prefetched[idx[k]].valid = true;
+    }
+    g_batchCalls++;
+    g_batchJobs += n;
+  }
+}
+
+void search( const SearchIn& in, SearchOut& out )
+{
+  if( g_collecting )
+  {
+    Prefetched p;
+    memcpy( p.raw, &in, sizeof( SearchIn ) );
+    p.valid = false;
+    memset( &p.out, 0, sizeof( p.out ) );
+    out = p.out;
+    g_prefetched.push_back( p );
+    return;
+  }
+  for( size_t i = 0; i < g_prefetched.size(); i++ )
+  {
+    // the caller zero-fills SearchIn before setting its fields: identical inputs are identical bytes
+    if( g_prefetched[i].valid && memcmp( g_prefetched[i].raw, &in, sizeof( SearchIn ) ) == 0 )
+    {
+      out                   = g_prefetched[i].out;
+      g_prefetched[i].valid = false;
+      g_batchHits++;
+      g_calls++;
+      if( in.tzSearch ) g_tzSearches++;
+      if( in.doFrac == 2 ) g_intRefines++;
+      return;
+    }
+  }
+  vtmme_job  j;
+  vtmme_amvr a;
+  vtmme_tz   t;
+  fillJob( in, j, a, t );
+  if( in.tzSearch ) g_tzSearches++;
+  vtmme_result r;
+  vtmme_ctx*   c  = ctx();
+  const auto   t0 = std::chrono::steady_clock::now();
+  const int    rc = vtmme_search( c, &j, 1, &r );
+  g_searchSec += std::chrono::duration<double>( std::chrono::steady_clock::now() - t0 ).count();
+  CHECK( rc != VTMME_OK, vtmme_last_error( g_ctx ) );
+  fillOut( r, out );
   g_calls++;
   if( in.doFrac == 2 ) g_intRefines++;
 }
@@ -210,10 +313,15 @@ void printStats()
 {
   if( g_ctx )
   {
+    const uint64_t libCalls = g_calls - g_batchHits + g_batchCalls;   // vtmme_search calls actually made
     fprintf( stderr, "[vtmcuda] GPU motion searches: %llu (%llu TZ searches, %llu with AMVR integer refinement; %.1f s inside vtmme_search, %.1f us per "
-                     "call), reference pictures uploaded: %llu, kernel launches: %llu\n",
+                     "search), reference pictures uploaded: %llu, kernel launches: %llu\n",
              (unsigned long long) g_calls, (unsigned long long) g_tzSearches, (unsigned long long) g_intRefines, g_searchSec, g_calls ? 1e6 * g_searchSec / g_calls : 0.0,
              (unsigned long long) g_uploads, (unsigned long long) vtmme_launch_count( g_ctx ) );
+    fprintf( stderr, "[vtmcuda] per-PU batching: %llu vtmme_search calls in all, %llu of them batches carrying %llu searches, %llu searches answered "
+                     "from a batch (%llu collected searches were never asked for)\n",
+             (unsigned long long) libCalls, (unsigned long long) g_batchCalls, (unsigned long long) g_batchJobs, (unsigned long long) g_batchHits,
+             (unsigned long long) ( g_batchJobs - g_batchHits ) );
   }
 }
 }   // namespace vtmcuda

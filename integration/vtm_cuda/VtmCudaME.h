@@ -53,6 +53,16 @@ struct SearchOut
   uint64_t cost;                       //   ruiCost
 };
 
+// Per-PU batching: InterSearch::predInterSearch first walks its (list, reference) loop in *collect* mode — xMotionEstimation runs
+// up to the point where it would search and hands the search's inputs to collect mode instead — then endCollect() runs all
+// collected searches in ONE vtmme_search call.  The real loop that follows asks search() as before; a request whose inputs are
+// identical, field by field, to a collected one is answered from that batch (anything else is searched on its own), so the
+// results cannot depend on the batching.  VTMME_BATCH=0 disables it.
+bool batching();
+bool collecting();
+void beginCollect();
+void endCollect();
+
 // Runs one xMotionEstimation search on the GPU.  Any failure of the CUDA path is fatal (THROW): there is no
 // CPU fallback once the GPU path is enabled.
 void search( const SearchIn& in, SearchOut& out );

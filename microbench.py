@@ -35,6 +35,12 @@ def main():
     torch.cuda.set_stream(stream)
     ms.set_stream(stream.cuda_stream)
     rows = []
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        peak_src = "MEASURED_PEAKS.json"
+    except (OSError, ValueError, KeyError):
+        hbm_peak, peak_src = 6650.0, "fallback of B200_PROFILING.md"
+    L2_BYTES = 126e6
     shapes = [(w, h) for w in SIZES for h in SIZES]
     if a.quick:
         shapes = [(8, 8), (16, 16), (32, 8), (64, 64), (128, 128), (4, 4)]
@@ -80,8 +86,11 @@ def main():
                     mask[::997] = False
                     got[mask] = 0
                 equal = bool(np.array_equal(got, ref_out))
+                # algorithmic bytes: the sampled rows of both blocks in, one 8-byte distortion out
+                nbytes = n * (2 * w * (h >> ss) * 2 + 8)
                 rows.append({"op": label, "w": w, "h": h, "data": dist_name, "n": n, "gpu_blocks_per_s": n / t_gpu,
-                             "cpu_blocks_per_s": n / t_cpu, "gpu_GBps": 2 * n * w * h * 2 / t_gpu / 1e9, "equal": equal, "cpu": src})
+                             "cpu_blocks_per_s": n / t_cpu, "gpu_GBps": nbytes / t_gpu / 1e9, "hbm_frac": nbytes / t_gpu / 1e9 / hbm_peak,
+                             "l2_resident": 2 * n * w * h * 2 < L2_BYTES, "equal": equal, "cpu": src})
                 print(json.dumps(rows[-1]))
                 assert equal, (label, w, h, dist_name)
         # interpolation: luma H / V / HV(second stage) and chroma, all phases summed into one timing
@@ -101,6 +110,10 @@ def main():
             s_np, s_d = (src, d_src) if first else (mid, d_mid)
             t_gpu = t_cpu = 0.0
             equal = True
+            fracs = list(fracs)
+            taps = 8 if comp == 0 else 4
+            # algorithmic bytes per block: the block plus its tap halo along the filtered axis in, the block out
+            blk_bytes = ((w + taps - 1) * h if not vert else w * (h + taps - 1)) * 2 + w * h * 2
             for frac in fracs:
                 t_gpu += gpu_time(lambda: ms.interp_batch(comp, vert, s_d.data_ptr() + 2 * off, w + 8, (w + 8) * (h + 8), d_dst.data_ptr(), w, w * h, w, h, frac, first, last, 10, 0, nf), reps=2)
                 got = d_dst.cpu().numpy()
@@ -110,6 +123,8 @@ def main():
                     equal &= bool(np.array_equal(got, want))
             rows.append({"op": label, "w": w, "h": h, "data": "uniform", "n": nf * len(list(fracs)), "gpu_blocks_per_s": nf * len(list(fracs)) / t_gpu,
                          "cpu_blocks_per_s": (nf * len(list(fracs)) / t_cpu) if t_cpu else float("nan"), "equal": equal,
+                         "gpu_GBps": nf * len(fracs) * blk_bytes / t_gpu / 1e9, "hbm_frac": nf * len(fracs) * blk_bytes / t_gpu / 1e9 / hbm_peak,
+                         "l2_resident": nf * (w + 8) * (h + 8) * 2 < L2_BYTES,
                          "cpu": "reference AVX2, 1 core" if R is not None else "n/a"})
             print(json.dumps(rows[-1]))
             assert equal, (label, w, h)
@@ -119,10 +134,15 @@ def main():
             f.write("# Distortion / interpolation micro-benchmark (BASELINE config 5)\n\n")
             f.write("GPU: libvtmme table-level batch kernels, blocks resident in HBM, CUDA-event timed.  CPU: the reference's own "
                     "dispatch-table entries (AVX2) on ONE host core.  Every output compared for exact equality.\n\n")
-            f.write("| op | WxH | data | blocks | GPU blocks/s | CPU blocks/s (1 core) | ratio | equal |\n|---|---|---|---|---|---|---|---|\n")
+            f.write("Roofline: these kernels are HBM-bound by design (a few integer ops per byte).  `GB/s` = algorithmic bytes (operand "
+                    "blocks in — sampled rows only for SAD, with the tap halo for filters — plus results out) / kernel time; `frac` = "
+                    "that over the measured HBM peak of %.0f GB/s (%s).  Batches whose operands fit the 126 MB L2 are marked `L2`: "
+                    "their repeated timing runs out of L2, so `frac` can exceed 1 there and is not an HBM figure.\n\n" % (hbm_peak, peak_src))
+            f.write("| op | WxH | data | blocks | GPU blocks/s | CPU blocks/s (1 core) | ratio | GB/s | frac | equal |\n|---|---|---|---|---|---|---|---|---|---|\n")
             for r in rows:
-                f.write("| %s | %dx%d | %s | %d | %.3g | %.3g | %.1f | %s |\n" % (r["op"], r["w"], r["h"], r["data"], r["n"], r["gpu_blocks_per_s"],
-                                                                                r["cpu_blocks_per_s"], r["gpu_blocks_per_s"] / r["cpu_blocks_per_s"], r["equal"]))
+                f.write("| %s | %dx%d | %s | %d | %.3g | %.3g | %.1f | %.0f | %.2f%s | %s |\n" % (
+                    r["op"], r["w"], r["h"], r["data"], r["n"], r["gpu_blocks_per_s"], r["cpu_blocks_per_s"],
+                    r["gpu_blocks_per_s"] / r["cpu_blocks_per_s"], r["gpu_GBps"], r["hbm_frac"], " (L2)" if r["l2_resident"] else "", r["equal"]))
             if mc_rows:
                 f.write("\n## Motion compensation of a whole 1080p picture (xPredInterBlk, uni-directional, random fractional MVs)\n\n"
                         "GPU: `vtmme_mc_batch` (host block list -> device prediction, wall time per call incl. the host-side tile "

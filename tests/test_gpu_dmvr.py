@@ -109,3 +109,45 @@ def test_dmvr_errors(ms):
         ms.dmvr_refine(76, 76, np.array([[56, 8, 16, 8, 0, 0, 0, 0]], np.int32))    # outside the picture
     with pytest.raises(vtm_b200.VtmmeError, match="ARG"):
         ms.dmvr_refine(76, 76, ok, 12)
+
+
+@pytest.mark.parametrize("bd", [10, 8])
+def test_dmvr_final_prediction(ms, oracle_lib, bd):
+    """The padded prediction after DMVR (xPrefetch + xPad + xFinalPaddedMCForDMVR) of both lists, luma and 4:2:0 chroma, with
+    the refinements the GPU's own search found (integer moves of up to two samples, sub-sample steps), some blocks left
+    unmoved, MVs the clip moves at the picture border — against the oracle (pinned on the reference's own members)."""
+    from vtm_b200.synth import make_pair
+    rng = np.random.default_rng(1200 + bd)
+    W, H = 256, 192
+    r0, r1, _ = make_pair(170, W, H, max_global=3, max_local=3, n_rects=4, sigma=4.0, bit_depth=bd)
+    p0, p1 = pad_plane(r0), pad_plane(r1)
+    c0, c1 = (np.ascontiguousarray(rng.integers(0, 1 << bd, (H // 2, W // 2), dtype=np.int16)) for _ in range(2))
+    cp0, cp1 = pad_plane(c0, MARGIN // 2), pad_plane(c1, MARGIN // 2)
+    ms.upload_picture(80, p0, MARGIN)
+    ms.upload_picture(81, p1, MARGIN)
+    ms.upload_picture(82, cp0, MARGIN // 2)
+    ms.upload_picture(83, c1)                                   # chroma border of list 1 replicated on the device
+    blk = dmvr_cases(rng, W, H, 500)
+    mvd = np.ascontiguousarray(ms.dmvr_refine(80, 81, blk, bd)[:, :2])
+    mvd[::5] = 0
+    assert (np.abs(mvd) >= 16).any(axis=1).sum() > 50 and (mvd % 16 != 0).any(axis=1).sum() > 50
+    stride, off = p0.shape[1], MARGIN * p0.shape[1] + MARGIN
+    cstride, coff = cp0.shape[1], (MARGIN // 2) * cp0.shape[1] + MARGIN // 2
+    for lst, (pid, cid, plane, cplane, sgn) in enumerate([(80, 82, p0, cp0, 1), (81, 83, p1, cp1, -1)]):
+        jobs = blk.copy()
+        jobs[:, 4:6] = blk[:, 4 + 2 * lst:6 + 2 * lst]                       # the list's merge MV
+        jobs[:, 6:8] = jobs[:, 4:6] + sgn * mvd                              # its refined MV
+        got_y = ms.dmvr_final_mc(0, pid, jobs, bd)
+        got_c = ms.dmvr_final_mc(1, cid, jobs, bd)
+        py = pc = 0
+        for b in jobs:
+            x, y, w, h, mx, my, fx, fy = (int(v) for v in b)
+            want = np.zeros(w * h, np.int16)
+            oracle_lib.vo_dmvr_final_luma(B.ptr(plane, off), stride, x, y, w, h, mx, my, fx, fy, W, H, 128, 128, bd, B.ptr(want))
+            assert np.array_equal(got_y[py:py + w * h], want), (lst, b.tolist())
+            py += w * h
+            sz = (w // 2) * (h // 2)
+            wantc = np.zeros(sz, np.int16)
+            oracle_lib.vo_dmvr_final_chroma(B.ptr(cplane, coff), cstride, x, y, w, h, mx, my, fx, fy, W, H, 128, 128, bd, B.ptr(wantc))
+            assert np.array_equal(got_c[pc:pc + sz], wantc), (lst, b.tolist())
+            pc += sz

@@ -84,3 +84,44 @@ def test_mctf_apply_motion(ms, oracle_lib, w, h, bd):
                                         C.c_void_p(mv.ctypes.data), mv.shape[1], bd, B.ptr(want_c), w // 2)
         assert np.array_equal(ms.mctf_apply_motion(77, w, h, mv, 0, 0, bd), want_y), variant
         assert np.array_equal(ms.mctf_apply_motion(78, w // 2, h // 2, mv, 1, 1, bd), want_c), variant
+
+
+@pytest.mark.parametrize("num_refs,bd,qp,strength", [(4, 10, 32, 0.95), (2, 10, 27, 1.5), (3, 8, 37, 0.95), (1, 10, 22, 1.5)])
+def test_mctf_bilateral(ms, oracle_lib, num_refs, bd, qp, strength):
+    """The whole filter of one picture on the GPU — motion estimation against every neighbour, applyMotion, bilateral
+    weighting (luma and 4:2:0 chroma) — against the oracle's vo_mctf_bilateral, which is pinned on the reference's own
+    EncTemporalFilter::bilateralFilter (tests/test_oracle_vs_ref.py).  The weight tables come from the host's exp()."""
+    from vtm_b200.synth import make_pair
+    w, h = 208, 120
+    rng = np.random.default_rng(1100 + num_refs)
+    org, _, _ = make_pair(160, w, h, max_global=5, max_local=8, n_rects=3, sigma=5.0, bit_depth=bd)
+    org = np.ascontiguousarray(org)
+    org_c = np.ascontiguousarray(rng.integers(0, 1 << bd, (h // 2, w // 2), dtype=np.int16))
+    offsets = [[-1], [-1, 1], [-2, -1, 1], [-2, -1, 1, 2]][num_refs - 1]
+    ms.upload_picture(500, org)
+    ms.upload_picture(501, org_c)
+    corr_y, corr_c = [], []
+    for k in range(num_refs):
+        r = np.clip(np.roll(org.astype(np.int32), (k + 1, -2 * k - 1), (0, 1)) + np.rint(rng.normal(0, 3 + 2 * k, org.shape)).astype(np.int32),
+                    0, (1 << bd) - 1).astype(np.int16)
+        c = np.clip(org_c.astype(np.int32) + np.rint(rng.normal(0, 6, org_c.shape)).astype(np.int32), 0, (1 << bd) - 1).astype(np.int16)
+        ms.upload_picture(510 + k, np.ascontiguousarray(r))
+        ms.upload_picture(520 + k, np.ascontiguousarray(c))
+        mv = ms.mctf_me([500], [510 + k], w, h, bd)[0]
+        corr_y.append(ms.mctf_apply_motion(510 + k, w, h, mv, 0, 0, bd))
+        corr_c.append(ms.mctf_apply_motion(520 + k, w // 2, h // 2, mv, 1, 1, bd))
+        ms.upload_picture(530 + k, corr_y[-1])
+        ms.upload_picture(540 + k, corr_c[-1])
+    offs = (C.c_int * num_refs)(*offsets)
+    for comp, (o, oid, corr, base, cw, ch) in enumerate([(org, 500, corr_y, 530, w, h), (org_c, 501, corr_c, 540, w // 2, h // 2)]):
+        tables = []
+        for k in range(num_refs):
+            tb = np.zeros(1 << bd, np.float64)
+            oracle_lib.vo_mctf_bilateral_weights(comp, qp, strength, bd, num_refs, min(1, abs(offsets[k]) - 1), C.c_void_p(tb.ctypes.data))
+            tables.append(tb)
+        got = ms.mctf_bilateral(oid, [base + k for k in range(num_refs)], np.stack(tables), cw, ch, bd)
+        cptrs = (C.c_void_p * num_refs)(*[a.ctypes.data for a in corr])
+        want = np.zeros((ch, cw), np.int16)
+        oracle_lib.vo_mctf_bilateral(B.ptr(o), cw, cptrs, cw, offs, num_refs, cw, ch, comp, qp, strength, bd, B.ptr(want), cw)
+        assert np.array_equal(got, want), (comp, np.argwhere(got != want)[:5])
+        assert (got != o).mean() > 0.2

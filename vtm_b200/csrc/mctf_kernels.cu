@@ -293,7 +293,58 @@ __global__ void __launch_bounds__(kMctfWarps * 32) mctf_level_kernel(MctfLevelPa
   if (lane == 0) p.mvs[(size_t) pair * p.mvW * p.mvH + (size_t) by * p.mvW + bx] = make_int3(bestX, bestY, bestE);
 }
 
+// EncTemporalFilter::bilateralFilter, the weighting of one component (EncoderLib/EncTemporalFilter.cpp:591-618).  The weight
+// of a neighbouring sample, weightScaling * refStrength * exp(-(diff * 1024 / 2^bd)^2 / (2 sigma^2)), depends only on
+// |refVal - orgVal| and the picture's POC-distance class, so the host hands over one table of 2^bd doubles per neighbouring
+// picture (computed with its own exp(), the reference's libm); products and sums are IEEE doubles in the reference's order,
+// never contracted into FMAs, one division, round() half away from zero: every output equals the reference's.
+struct MctfBilateralParams
+{
+  DevPic        org;
+  DevPic        corr[8];
+  const double* weights;   // [numRefs][1 << bitDepth]
+  int           numRefs, tableSize, maxv;
+  int16_t*      dst;       // packed width x height
+};
+
+__global__ void __launch_bounds__(256) mctf_bilateral_kernel(MctfBilateralParams p)
+{
+  const int       w = p.org.width, h = p.org.height;
+  const long long n = (long long) w * h, stride = (long long) gridDim.x * blockDim.x;
+  for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    const int y = (int) (i / w), x = (int) (i - (long long) y * w);
+    const int orgVal = p.org.origin[(size_t) y * p.org.stride + x];
+    double    sum = 1.0, newVal = (double) orgVal;
+    for (int r = 0; r < p.numRefs; r++)
+    {
+      const int    refVal = p.corr[r].origin[(size_t) y * p.corr[r].stride + x];
+      const int    d      = min(abs(refVal - orgVal), p.tableSize - 1);
+      const double wgt    = p.weights[(size_t) r * p.tableSize + d];
+      newVal = __dadd_rn(newVal, __dmul_rn(wgt, (double) refVal));
+      sum    = __dadd_rn(sum, wgt);
+    }
+    const int v = (int) (short) (int) round(__ddiv_rn(newVal, sum));
+    p.dst[i]    = (int16_t) min(max(v, 0), p.maxv);
+  }
+}
+
 }   // namespace
+
+cudaError_t launch_mctf_bilateral(DevPic org, const DevPic* corr, int numRefs, const double* dWeights, int bitDepth, int16_t* dst,
+                                  cudaStream_t st)
+{
+  MctfBilateralParams p;
+  p.org = org;
+  for (int i = 0; i < numRefs; i++) p.corr[i] = corr[i];
+  p.weights   = dWeights;
+  p.numRefs   = numRefs;
+  p.tableSize = 1 << bitDepth;
+  p.maxv      = (1 << bitDepth) - 1;
+  p.dst       = dst;
+  mctf_bilateral_kernel<<<592, 256, 0, st>>>(p);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_mctf_subsample(DevPic in, DevPic out, cudaStream_t st)
 {

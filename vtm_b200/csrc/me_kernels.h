@@ -211,7 +211,11 @@ struct McTile
   uint8_t        tw, th;       // 1..16
   uint8_t        xFrac, yFrac; // 1/16 (luma) or 1/32 (chroma) phase
   uint8_t        q4Hor, q4Ver; // the 4x4 coefficient table applies to the horizontal / vertical pass
-  uint8_t        pad[2];
+  // DMVR's padded prediction (xFinalPaddedMCForDMVR): winMaxX != 0 makes src the origin of the prefetched window, the tile
+  // starts at window coordinates (winX, winY) and every read is clamped to [0, winMaxX] x [0, winMaxY] (xPad's replication)
+  uint8_t        winMaxX, winMaxY;
+  int8_t         winX, winY;
+  uint8_t        pad2[4];
 };
 // the same tile with the original block it is compared against (candidate SAD, mc_sad_kernel)
 struct McSadTile
@@ -231,6 +235,27 @@ cudaError_t launch_remove_high_freq(int16_t* d, const int16_t* s, long long n, i
 cudaError_t launch_add_weighted_avg(const int16_t* a, const int16_t* b, int16_t* d, long long n, int bitDepth, int bcwIdx, cudaStream_t st);
 cudaError_t launch_remove_weight_high_freq(int16_t* d, const int16_t* s, long long n, int clip, int bitDepth, int bcwWeight, cudaStream_t st);
 
+// Symmetric-MVD search (smvd_kernels.cu): state of one InterSearch::xSymmetricMotionEstimation call, MVs in 1/16 sample
+struct DevSmvd
+{
+  const int16_t*     org;          // original block at the PU position (device)
+  const int16_t*     refCur;       // sample (0,0) of the searched list's reference plane
+  const int16_t*     refTar;       // ... of the other list's
+  int                orgStride, refStride;
+  int                x, y, w, h, picW, picH, maxCu, bd, imv;
+  int                curPredX, curPredY, tarPredX, tarPredY;
+  int                curMvX, curMvY, tarMvX, tarMvY;
+  int                clipBiPred, useHad, bcwIdx;
+  double             lambda;
+  unsigned long long cost;
+};
+struct DevSmvdResult
+{
+  int                curMvX, curMvY, tarMvX, tarMvY;
+  unsigned long long cost;
+};
+cudaError_t launch_smvd_search(const DevSmvd* dJobs, DevSmvdResult* dOut, int n, cudaStream_t st);
+
 // GOP-based temporal filter motion estimation (mctf_kernels.cu)
 struct MctfLevelParams
 {
@@ -248,6 +273,8 @@ cudaError_t launch_mctf_init_mv(int3* mv, int n, cudaStream_t st);
 cudaError_t launch_mctf_apply_motion(DevPic src, int csx, int csy, const int3* mv, int mvStride, int maxv, int16_t* dst,
                                      cudaStream_t st);
 cudaError_t launch_mctf_level(const MctfLevelParams& p, int blockSize, bool doubleRes, int nPairs, cudaStream_t st);
+cudaError_t launch_mctf_bilateral(DevPic org, const DevPic* corr, int numRefs, const double* dWeights, int bitDepth, int16_t* dst,
+                                  cudaStream_t st);
 
 // Decoder-side MV refinement of a batch of sub-blocks (dmvr_kernels.cu); same layouts as vtmme_dmvr_block / _result
 struct DevDmvrBlock

@@ -1117,6 +1117,40 @@ extern "C" int vtmme_mctf_apply_motion(vtmme_ctx* ctx, int srcPic, int csx, int 
   return VTMME_OK;
 }
 
+extern "C" int vtmme_mctf_bilateral(vtmme_ctx* ctx, int orgPic, int numRefs, const int32_t* corrPics, const double* weights,
+                                    int bitDepth, int16_t* dst)
+{
+  if (!ctx) return VTMME_ERR_ARG;
+  if (numRefs < 1 || numRefs > 8 || !corrPics || !weights || !dst || bitDepth < 8 || bitDepth > 12)
+    return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_mctf_bilateral", "bad argument (1..8 neighbouring pictures, bit depth 8..12)");
+  VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  auto it = ctx->pics.find(orgPic);
+  if (it == ctx->pics.end()) return vtmme_set_error(ctx, VTMME_ERR_NOPIC, "vtmme_mctf_bilateral", "unknown picture id");
+  int rc;
+  if ((rc = wait_picture(ctx, orgPic)) != VTMME_OK) return rc;
+  const DevPic op = it->second;
+  DevPic       corr[8];
+  for (int i = 0; i < numRefs; i++)
+  {
+    auto c = ctx->pics.find(corrPics[i]);
+    if (c == ctx->pics.end()) return vtmme_set_error(ctx, VTMME_ERR_NOPIC, "vtmme_mctf_bilateral", "unknown picture id");
+    if (c->second.width != op.width || c->second.height != op.height)
+      return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_mctf_bilateral", "pictures differ in size");
+    if ((rc = wait_picture(ctx, corrPics[i])) != VTMME_OK) return rc;
+    corr[i] = c->second;
+  }
+  const size_t tabBytes = (size_t) numRefs * ((size_t) 1 << bitDepth) * sizeof(double), outBytes = (size_t) op.width * op.height * 2;
+  if ((rc = ensure(ctx, ctx->dMctf, ctx->mctfCap, align256(tabBytes) + outBytes)) != VTMME_OK) return rc;
+  double*  dTab = reinterpret_cast<double*>(ctx->dMctf);
+  int16_t* dOut = reinterpret_cast<int16_t*>(ctx->dMctf + align256(tabBytes));
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(dTab, weights, tabBytes, cudaMemcpyHostToDevice, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, launch_mctf_bilateral(op, corr, numRefs, dTab, bitDepth, dOut, ctx->stream));
+  ctx->launches += 1;
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, dOut, outBytes, cudaMemcpyDeviceToHost, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return VTMME_OK;
+}
+
 // ---- table-level entry points -------------------------------------------------------------------------------
 extern "C" int vtmme_dist_batch(vtmme_ctx* ctx, int kind, const int16_t* dOrg, int orgStride, int64_t orgBlockStride,
                                 const int16_t* dCur, int curStride, int64_t curBlockStride, int w, int h, int subShift,
@@ -1250,8 +1284,8 @@ extern "C" int vtmme_filter_host(vtmme_ctx* ctx, int nTaps, int vertical, int is
 // ---- motion compensation -------------------------------------------------------------------------------------------
 // Validates the blocks, cuts them into <=16x16 tiles in the pinned staging block, uploads the tiles to *dTiles (device
 // scratch) and launches the kernel writing to dDst (block i packed at the running sum of w*h).
-static int mc_launch(vtmme_ctx* ctx, const char* who, int comp, int bi, int bitDepth, int useAltHpel, int n,
-                     const vtmme_mc_block* blocks, int nTiles, int16_t* dDst)
+// page-locked staging of nTiles tile descriptors (waits until the previous upload out of it has completed)
+static int mc_tiles_begin(vtmme_ctx* ctx, int nTiles)
 {
   const size_t tileBytes = align256((size_t) nTiles * sizeof(McTile));
   int rc;
@@ -1277,6 +1311,25 @@ static int mc_launch(vtmme_ctx* ctx, const char* who, int comp, int bi, int bitD
     VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     if ((rc = ensure(ctx, ctx->dMcTiles, ctx->mcTilesCap, tileBytes)) != VTMME_OK) return rc;
   }
+  return VTMME_OK;
+}
+
+// uploads the staged descriptors and launches the kernel
+static int mc_tiles_launch(vtmme_ctx* ctx, int comp, int nTiles, int bi, int bitDepth, int useAltHpel)
+{
+  McTile* dTiles = reinterpret_cast<McTile*>(ctx->dMcTiles);
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(dTiles, ctx->hMcTiles, (size_t) nTiles * sizeof(McTile), cudaMemcpyHostToDevice, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, cudaEventRecord(ctx->mcUploaded, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, launch_mc_batch(comp, dTiles, nTiles, bi, bitDepth, useAltHpel, ctx->stream));
+  ctx->launches += 1;
+  return VTMME_OK;
+}
+
+static int mc_launch(vtmme_ctx* ctx, const char* who, int comp, int bi, int bitDepth, int useAltHpel, int n,
+                     const vtmme_mc_block* blocks, int nTiles, int16_t* dDst)
+{
+  int rc;
+  if ((rc = mc_tiles_begin(ctx, nTiles)) != VTMME_OK) return rc;
   const int shift = 4 + (comp ? 1 : 0), taps = comp ? 4 : 8, before = taps / 2 - 1, after = taps / 2;
   McTile* ht = reinterpret_cast<McTile*>(ctx->hMcTiles);
   int     k = 0;
@@ -1310,17 +1363,13 @@ static int mc_launch(vtmme_ctx* ctx, const char* who, int comp, int bi, int bitD
         t.yFrac = (uint8_t) yFrac;
         t.q4Hor = q4Hor;
         t.q4Ver = q4Ver;
-        t.pad[0] = t.pad[1] = 0;
+        t.winMaxX = t.winMaxY = 0;
+        t.winX = t.winY = 0;
       }
     off += (size_t) b.w * b.h;
   }
   if (k != nTiles) return vtmme_set_error(ctx, VTMME_ERR_ARG, who, "internal: tile count");
-  McTile* dTiles = reinterpret_cast<McTile*>(ctx->dMcTiles);
-  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(dTiles, ht, (size_t) nTiles * sizeof(McTile), cudaMemcpyHostToDevice, ctx->stream));
-  VTMME_CUDA_CHECK(ctx, cudaEventRecord(ctx->mcUploaded, ctx->stream));
-  VTMME_CUDA_CHECK(ctx, launch_mc_batch(comp, dTiles, nTiles, bi, bitDepth, useAltHpel, ctx->stream));
-  ctx->launches += 1;
-  return VTMME_OK;
+  return mc_tiles_launch(ctx, comp, nTiles, bi, bitDepth, useAltHpel);
 }
 
 // shared argument check; returns the tile count and the packed output size
@@ -1372,6 +1421,161 @@ extern "C" int vtmme_mc_host(vtmme_ctx* ctx, int comp, int bi, int bitDepth, int
                       reinterpret_cast<int16_t*>(ctx->dJobBuf))) != VTMME_OK)
     return rc;
   VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->hPinned, ctx->dJobBuf, elems * 2, cudaMemcpyDeviceToHost, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(dst, ctx->hPinned, elems * 2);
+  return VTMME_OK;
+}
+
+// ---- symmetric-MVD search ------------------------------------------------------------------------------------------
+static_assert(sizeof(vtmme_smvd_result) == sizeof(DevSmvdResult), "result layout");
+extern "C" int vtmme_smvd_search(vtmme_ctx* ctx, int n, const vtmme_smvd* jobs, vtmme_smvd_result* results)
+{
+  static const char* who = "vtmme_smvd_search";
+  if (!ctx) return VTMME_ERR_ARG;
+  if (!jobs || !results || n <= 0 || n > 65536) return vtmme_set_error(ctx, VTMME_ERR_ARG, who, "bad argument");
+  VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  size_t orgBytes = 0;
+  int    rc;
+  for (int i = 0; i < n; i++)
+  {
+    const vtmme_smvd& j = jobs[i];
+    const bool pow2w = j.w >= 8 && j.w <= 128 && (j.w & (j.w - 1)) == 0, pow2h = j.h >= 8 && j.h <= 128 && (j.h & (j.h - 1)) == 0;
+    if (!pow2w || !pow2h || j.bitDepth < 8 || j.bitDepth > 10 || j.imv < 0 || j.imv > 3 || j.bcwIdx < 0 || j.bcwIdx > 4 ||
+        j.maxCu < 1 || j.maxCu > 128 || (j.org && j.orgStride < j.w))
+      return vtmme_set_error(ctx, VTMME_ERR_ARG, who, "invalid job (w, h powers of two in 8..128, bit depth 8..10, imv 0..3, bcwIdx 0..4)");
+    auto a = ctx->pics.find(j.refPicCur), b = ctx->pics.find(j.refPicTar);
+    if (a == ctx->pics.end() || b == ctx->pics.end() || (!j.org && ctx->pics.find(j.curPic) == ctx->pics.end()))
+      return vtmme_set_error(ctx, VTMME_ERR_NOPIC, who, "unknown picture id");
+    const DevPic& pa = a->second;
+    const DevPic& pb = b->second;
+    if (pa.width != pb.width || pa.height != pb.height || pa.stride != pb.stride || pa.margin < 144 || pb.margin < 144)
+      return vtmme_set_error(ctx, VTMME_ERR_ARG, who, "the two reference pictures must have the same size");
+    if (j.x < 0 || j.y < 0 || j.x + j.w > pa.width || j.y + j.h > pa.height)
+      return vtmme_set_error(ctx, VTMME_ERR_RANGE, who, "PU outside the picture");
+    if ((rc = wait_picture(ctx, j.refPicCur)) != VTMME_OK || (rc = wait_picture(ctx, j.refPicTar)) != VTMME_OK) return rc;
+    if (!j.org && (rc = wait_picture(ctx, j.curPic)) != VTMME_OK) return rc;
+    if (j.org) orgBytes += align256((size_t) j.w * j.h * 2);
+  }
+  const size_t jobBytes = align256((size_t) n * sizeof(DevSmvd)), resBytes = align256((size_t) n * sizeof(DevSmvdResult));
+  const size_t total = jobBytes + resBytes + orgBytes;
+  if ((rc = ensure_pinned(ctx, total)) != VTMME_OK) return rc;
+  if ((rc = ensure(ctx, ctx->dJobBuf, ctx->jobBufCap, total)) != VTMME_OK) return rc;
+  DevSmvd* hj  = reinterpret_cast<DevSmvd*>(ctx->hPinned);
+  size_t   off = jobBytes + resBytes;
+  for (int i = 0; i < n; i++)
+  {
+    const vtmme_smvd& j = jobs[i];
+    const DevPic& pa = ctx->pics[j.refPicCur];
+    const DevPic& pb = ctx->pics[j.refPicTar];
+    DevSmvd& d = hj[i];
+    if (j.org)
+    {
+      int16_t* ho = reinterpret_cast<int16_t*>(ctx->hPinned + off);
+      for (int y = 0; y < j.h; y++) memcpy(ho + (size_t) y * j.w, j.org + (ptrdiff_t) y * j.orgStride, (size_t) j.w * 2);
+      d.org       = reinterpret_cast<const int16_t*>(ctx->dJobBuf + off);
+      d.orgStride = j.w;
+      off += align256((size_t) j.w * j.h * 2);
+    }
+    else
+    {
+      const DevPic& cp = ctx->pics[j.curPic];
+      d.org       = cp.origin + (ptrdiff_t) j.y * cp.stride + j.x;
+      d.orgStride = cp.stride;
+    }
+    d.refCur = pa.origin;
+    d.refTar = pb.origin;
+    d.refStride = pa.stride;
+    d.x = j.x; d.y = j.y; d.w = j.w; d.h = j.h;
+    d.picW = pa.width; d.picH = pa.height; d.maxCu = j.maxCu; d.bd = j.bitDepth; d.imv = j.imv;
+    d.curPredX = j.curPredX; d.curPredY = j.curPredY; d.tarPredX = j.tarPredX; d.tarPredY = j.tarPredY;
+    d.curMvX = j.curMvX; d.curMvY = j.curMvY; d.tarMvX = j.tarMvX; d.tarMvY = j.tarMvY;
+    d.clipBiPred = j.clipBiPred; d.useHad = j.useHad; d.bcwIdx = j.bcwIdx;
+    d.lambda = j.lambdaMotion;
+    d.cost   = j.cost;
+  }
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dJobBuf, ctx->hPinned, total, cudaMemcpyHostToDevice, ctx->stream));
+  DevSmvdResult* dRes = reinterpret_cast<DevSmvdResult*>(ctx->dJobBuf + jobBytes);
+  VTMME_CUDA_CHECK(ctx, launch_smvd_search(reinterpret_cast<const DevSmvd*>(ctx->dJobBuf), dRes, n, ctx->stream));
+  ctx->launches += 1;
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->hPinned + jobBytes, dRes, (size_t) n * sizeof(DevSmvdResult), cudaMemcpyDeviceToHost, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(results, ctx->hPinned + jobBytes, (size_t) n * sizeof(vtmme_smvd_result));
+  return VTMME_OK;
+}
+
+// Mv clipping of clipMvInPic (CommonLib/Mv.cpp:53-71), 1/16 sample
+static void clip_mv_in_pic(int& mx, int& my, int x, int y, int picW, int picH, int maxCu)
+{
+  const int horMax = (picW + 8 - x - 1) << 4, horMin = (-maxCu - 8 - x + 1) * 16;
+  const int verMax = (picH + 8 - y - 1) << 4, verMin = (-maxCu - 8 - y + 1) * 16;
+  mx = mx > horMax ? horMax : (mx < horMin ? horMin : mx);
+  my = my > verMax ? verMax : (my < verMin ? verMin : my);
+}
+
+// The prediction of one list after DMVR: xFinalPaddedMCForDMVR (CommonLib/InterPrediction.cpp:1845-1917).  xPrefetch (:1664-1708)
+// copied the (w + taps - 1) x (h + taps - 1) window at the integer part of clip(mergeMv - (taps/2 - 1) samples), xPad
+// (:1710-1730) replicated its border, and xPredInterBlk (bi = true) filters out of that buffer at the refined MV: the same
+// tile routine as vtmme_mc_batch reading the window with clamped coordinates.
+extern "C" int vtmme_dmvr_final_mc(vtmme_ctx* ctx, int comp, int refPic, int bitDepth, int maxCu, int n,
+                                   const vtmme_dmvr_block* blocks, int16_t* dst)
+{
+  static const char* who = "vtmme_dmvr_final_mc";
+  if (!ctx) return VTMME_ERR_ARG;
+  if (!blocks || !dst || n <= 0 || n > (1 << 20) || (comp != 0 && comp != 1) || bitDepth < 8 || bitDepth > 10 || maxCu < 1 || maxCu > 128)
+    return vtmme_set_error(ctx, VTMME_ERR_ARG, who, "bad argument");
+  VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  auto it = ctx->pics.find(refPic);
+  if (it == ctx->pics.end()) return vtmme_set_error(ctx, VTMME_ERR_NOPIC, who, "unknown picture id");
+  int rc;
+  if ((rc = wait_picture(ctx, refPic)) != VTMME_OK) return rc;
+  const DevPic rp = it->second;
+  const int cs = comp ? 1 : 0, taps = comp ? 4 : 8, before = taps / 2 - 1, sh = 4 + cs;
+  const int picW = rp.width << cs, picH = rp.height << cs;   // the luma picture the MV clip refers to
+  size_t elems = 0;
+  for (int i = 0; i < n; i++)
+  {
+    const vtmme_dmvr_block& b = blocks[i];
+    if ((b.w != 8 && b.w != 16) || (b.h != 8 && b.h != 16) || b.x < 0 || b.y < 0 || b.x + b.w > picW || b.y + b.h > picH)
+      return vtmme_set_error(ctx, VTMME_ERR_ARG, who, "sub-blocks are 8 or 16 luma samples wide / high and lie inside the picture");
+    elems += (size_t) (b.w >> cs) * (b.h >> cs);
+  }
+  if ((rc = mc_tiles_begin(ctx, n)) != VTMME_OK) return rc;
+  if ((rc = ensure(ctx, ctx->dJobBuf, ctx->jobBufCap, elems * 2)) != VTMME_OK) return rc;
+  if ((rc = ensure_pinned(ctx, elems * 2)) != VTMME_OK) return rc;
+  int16_t* dDst = reinterpret_cast<int16_t*>(ctx->dJobBuf);
+  McTile*  ht   = reinterpret_cast<McTile*>(ctx->hMcTiles);
+  size_t   off  = 0;
+  for (int i = 0; i < n; i++)
+  {
+    const vtmme_dmvr_block& b = blocks[i];
+    const int w = b.w >> cs, h = b.h >> cs;
+    int cx = b.mvL0x - (before << sh), cy = b.mvL0y - (before << sh), fx = b.mvL1x, fy = b.mvL1y;   // merge MV -> window, refined MV -> phase
+    clip_mv_in_pic(cx, cy, b.x, b.y, picW, picH, maxCu);
+    clip_mv_in_pic(fx, fy, b.x, b.y, picW, picH, maxCu);
+    const int wx0 = (b.x >> cs) + (cx >> sh), wy0 = (b.y >> cs) + (cy >> sh);   // window origin in the plane
+    if (wx0 < -rp.margin || wy0 < -rp.margin || wx0 + w + taps - 1 > rp.width + rp.margin || wy0 + h + taps - 1 > rp.height + rp.margin)
+      return vtmme_set_error(ctx, VTMME_ERR_RANGE, who, "prefetch window leaves the padded reference plane");
+    const int bx = before + ((b.mvL1x >> sh) - (b.mvL0x >> sh)), by = before + ((b.mvL1y >> sh) - (b.mvL0y >> sh));
+    if (bx < -100 || bx > 100 || by < -100 || by > 100)
+      return vtmme_set_error(ctx, VTMME_ERR_ARG, who, "refined MV too far from the merge MV (DMVR moves a block by at most 2 samples)");
+    McTile& t = ht[i];
+    t.src = rp.origin + (ptrdiff_t) wy0 * rp.stride + wx0;
+    t.dst = dDst + off;
+    t.srcStride = rp.stride;
+    t.dstStride = w;
+    t.tw = (uint8_t) w;
+    t.th = (uint8_t) h;
+    t.xFrac = (uint8_t) (fx & ((1 << sh) - 1));
+    t.yFrac = (uint8_t) (fy & ((1 << sh) - 1));
+    t.q4Hor = t.q4Ver = 0;
+    t.winMaxX = (uint8_t) (w + taps - 2);
+    t.winMaxY = (uint8_t) (h + taps - 2);
+    t.winX = (int8_t) bx;
+    t.winY = (int8_t) by;
+    off += (size_t) w * h;
+  }
+  if ((rc = mc_tiles_launch(ctx, comp, n, 1, bitDepth, 0)) != VTMME_OK) return rc;
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->hPinned, dDst, elems * 2, cudaMemcpyDeviceToHost, ctx->stream));
   VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   memcpy(dst, ctx->hPinned, elems * 2);
   return VTMME_OK;
@@ -1544,7 +1748,8 @@ extern "C" int vtmme_cand_sad(vtmme_ctx* ctx, int bitDepth, int useAltHpel, int 
           t.mc.yFrac = (uint8_t) yFrac;
           t.mc.q4Hor = q4Hor;
           t.mc.q4Ver = q4Ver;
-          t.mc.pad[0] = t.mc.pad[1] = 0;
+          t.mc.winMaxX = t.mc.winMaxY = 0;
+          t.mc.winX = t.mc.winY = 0;
           t.org = dOrg + (ptrdiff_t) ty * orgStride + tx;
           t.orgStride = orgStride;
           t.outIdx = slot;

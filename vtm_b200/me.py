@@ -9,7 +9,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .lib import (CAmvr, CCandJob, CDmvrBlock, CDmvrResult, CTz, CFrameParams, CJob, CMcBlock, CResult, ERR_NAMES, VtmmeError,
+from .lib import (CAmvr, CCandJob, CDmvrBlock, CDmvrResult, CSmvd, CSmvdResult, CTz, CFrameParams, CJob, CMcBlock, CResult, ERR_NAMES, VtmmeError,
                   load_library)
 
 # vtmme_cu_result
@@ -366,6 +366,18 @@ class MotionSearch:
                     "vtmme_mctf_apply_motion")
         return out
 
+    def mctf_bilateral(self, org_id, corr_ids, weights, width, height, bit_depth=10):
+        """EncTemporalFilter::bilateralFilter for one component: uploaded original plane org_id, uploaded motion-compensated
+        neighbours corr_ids, weights float64 [len(corr_ids), 1 << bit_depth] (weight by |ref - org|).  Returns int16
+        [height, width]."""
+        n = len(corr_ids)
+        wt = np.ascontiguousarray(weights, dtype=np.float64)
+        assert wt.shape == (n, 1 << bit_depth)
+        out = np.zeros((height, width), np.int16)
+        self._check(self.L.vtmme_mctf_bilateral(self.ctx, org_id, n, (C.c_int32 * n)(*corr_ids), C.c_void_p(wt.ctypes.data),
+                                                bit_depth, C.c_void_p(out.ctypes.data)), "vtmme_mctf_bilateral")
+        return out
+
     # ---- decoder-side MV refinement ------------------------------------------------------------------------
     def dmvr_refine(self, ref_pic0, ref_pic1, blocks, bit_depth=10, max_cu=128):
         """The search of InterPrediction::xProcessDMVR (CommonLib/InterPrediction.cpp:2098-2154) for a batch of sub-blocks.
@@ -377,6 +389,40 @@ class MotionSearch:
                                              C.cast(blk.ctypes.data, C.POINTER(CDmvrBlock)),
                                              C.cast(out.ctypes.data, C.POINTER(CDmvrResult))), "vtmme_dmvr_refine")
         return out
+
+    def dmvr_final_mc(self, comp, ref_pic, blocks, bit_depth=10, max_cu=128):
+        """InterPrediction::xFinalPaddedMCForDMVR for a batch of sub-blocks of one list: blocks int32 [n, 8] {x, y, w, h (luma),
+        merge MV x, y, refined MV x, y}.  Returns the packed int16 14-bit predictions (comp 1: the 4:2:0 chroma plane)."""
+        blk = np.ascontiguousarray(np.asarray(blocks, dtype=np.int32).reshape(-1, 8))
+        cs = 1 if comp else 0
+        total = int(((blk[:, 2] >> cs) * (blk[:, 3] >> cs)).sum())
+        out = np.zeros(total, np.int16)
+        self._check(self.L.vtmme_dmvr_final_mc(self.ctx, comp, ref_pic, bit_depth, max_cu, len(blk),
+                                               C.cast(blk.ctypes.data, C.POINTER(CDmvrBlock)), C.c_void_p(out.ctypes.data)),
+                    "vtmme_dmvr_final_mc")
+        return out
+
+    # ---- symmetric-MVD search -----------------------------------------------------------------------------
+    def smvd_search(self, jobs):
+        """InterSearch::xSymmetricMotionEstimation for a batch of PUs.  jobs: list of dicts with the fields of vtmme_smvd
+        (org: optional int16 2-D array).  Returns a list of (curMvX, curMvY, tarMvX, tarMvY, cost)."""
+        n = len(jobs)
+        arr = (CSmvd * n)()
+        keep = []
+        for i, j in enumerate(jobs):
+            org = j.get("org")
+            if org is not None:
+                org = np.ascontiguousarray(org, dtype=np.int16)
+                keep.append(org)
+            arr[i] = CSmvd(int(j.get("curPic", 0)), int(j["refPicCur"]), int(j["refPicTar"]), int(j["x"]), int(j["y"]), int(j["w"]),
+                           int(j["h"]), org.ctypes.data if org is not None else None, org.shape[1] if org is not None else 0,
+                           int(j.get("maxCu", 128)), int(j.get("bitDepth", 10)), int(j["imv"]), int(j["curPred"][0]),
+                           int(j["curPred"][1]), int(j["tarPred"][0]), int(j["tarPred"][1]), int(j["curMv"][0]), int(j["curMv"][1]),
+                           int(j["tarMv"][0]), int(j["tarMv"][1]), int(j.get("clipBiPred", 0)), int(j.get("useHad", 1)),
+                           int(j.get("bcwIdx", 2)), float(j["lambdaMotion"]), int(j["cost"]))
+        res = (CSmvdResult * n)()
+        self._check(self.L.vtmme_smvd_search(self.ctx, n, arr, res), "vtmme_smvd_search")
+        return [(r.curMvX, r.curMvY, r.tarMvX, r.tarMvY, int(r.cost)) for r in res]
 
     # ---- candidate distortion (AMVP template cost / ME seeds) ----------------------------------------------
     def cand_sad(self, jobs, bit_depth=10, use_alt_hpel=0):
