@@ -261,6 +261,85 @@ def main():
 """ + s[pos:]
         return s
     edit(os.path.join(lib, "EncoderLib", "InterSearch.cpp"), inter)
+
+    # 6. EncTemporalFilter::filter: motion estimation of every neighbouring picture, applyMotion and the bilateral weighting on
+    # the GPU (vtmcuda::temporalFilter); the weight tables are computed here, with the encoder's own exp()
+    def tfilter(s):
+        s = once(s, '#include "EncTemporalFilter.h"\n', '#include "EncTemporalFilter.h"\n#include "CommonLib/cuda/VtmCudaME.h"   // libvtmme\n#include <vector>\n')
+        s = once(s, "      motionEstimation(srcPic.mvs, origPadded, srcPic.picBuffer, origSubsampled2, origSubsampled4);\n", """\
+      if( !vtmcuda::enabled() )   // libvtmme: with the GPU path every neighbour is searched in one batch below
+      {
+        motionEstimation(srcPic.mvs, origPadded, srcPic.picBuffer, origSubsampled2, origSubsampled4);
+      }
+""")
+        s = once(s, "    bilateralFilter(origPadded, srcFrameInfo, newOrgPic, overallStrength);\n", """\
+    if( vtmcuda::enabled() && !srcFrameInfo.empty() && srcFrameInfo.size() <= 8 )   // libvtmme
+    {
+      const int numRefs = int( srcFrameInfo.size() ), numComp = getNumberValidComponents( m_chromaFormatIDC );
+      int refStrengthRow = 2;
+      if( numRefs == m_range * 2 )
+      {
+        refStrengthRow = 0;
+      }
+      else if( numRefs == m_range )
+      {
+        refStrengthRow = 1;
+      }
+      const double lumaSigmaSq = ( m_QP - m_sigmaZeroPoint ) * ( m_QP - m_sigmaZeroPoint ) * m_sigmaMultiplier;
+      const double chromaSigmaSq = 30 * 30;
+      std::vector<vtmcuda::TfPlane> org( numComp ), refs( numRefs * numComp );
+      std::vector<std::vector<double>> tables( numComp );
+      std::vector<const double*> weights( numComp );
+      std::vector<int16_t*> dst( numComp );
+      std::vector<int> dstStride( numComp ), bitDepth( numComp );
+      for( int c = 0; c < numComp; c++ )
+      {
+        const ComponentID compID = ComponentID( c );
+        org[c] = vtmcuda::TfPlane{ origPadded.bufs[c].buf, int( origPadded.bufs[c].stride ), int( origPadded.bufs[c].width ), int( origPadded.bufs[c].height ) };
+        for( int i = 0; i < numRefs; i++ )
+        {
+          const PelBuf& rb = srcFrameInfo[i].picBuffer.bufs[c];
+          refs[i * numComp + c] = vtmcuda::TfPlane{ rb.buf, int( rb.stride ), int( rb.width ), int( rb.height ) };
+        }
+        dst[c]       = newOrgPic.bufs[c].buf;
+        dstStride[c] = int( newOrgPic.bufs[c].stride );
+        bitDepth[c]  = m_internalBitDepth[toChannelType( compID )];
+        // the weight of a neighbouring sample as a function of |refVal - orgVal| — the expressions of bilateralFilter
+        const double sigmaSq = isChroma( compID ) ? chromaSigmaSq : lumaSigmaSq;
+        const double weightScaling = overallStrength * ( isChroma( compID ) ? m_chromaFactor : 0.4 );
+        const Pel maxSampleValue = ( 1 << bitDepth[c] ) - 1;
+        const double bitDepthDiffWeighting = 1024.0 / ( maxSampleValue + 1 );
+        tables[c].resize( size_t( numRefs ) << bitDepth[c] );
+        for( int i = 0; i < numRefs; i++ )
+        {
+          const int index = std::min( 1, std::abs( srcFrameInfo[i].origOffset ) - 1 );
+          for( int d = 0; d <= maxSampleValue; d++ )
+          {
+            double diff = (double) d;
+            diff *= bitDepthDiffWeighting;
+            double diffSq = diff * diff;
+            tables[c][( size_t( i ) << bitDepth[c] ) + d] = weightScaling * m_refStrengths[refStrengthRow][index] * exp( -diffSq / ( 2 * sigmaSq ) );
+          }
+        }
+        weights[c] = tables[c].data();
+      }
+      vtmcuda::temporalFilter( numRefs, numComp, org.data(), refs.data(), getComponentScaleX( COMPONENT_Cb, m_chromaFormatIDC ),
+                               getComponentScaleY( COMPONENT_Cb, m_chromaFormatIDC ), bitDepth.data(), weights.data(), dst.data(), dstStride.data() );
+    }
+    else
+    {
+      if( vtmcuda::enabled() )   // not taken by the GPU path: the motion estimation skipped above
+      {
+        for( auto& srcPic : srcFrameInfo )
+        {
+          motionEstimation( srcPic.mvs, origPadded, srcPic.picBuffer, origSubsampled2, origSubsampled4 );
+        }
+      }
+      bilateralFilter(origPadded, srcFrameInfo, newOrgPic, overallStrength);
+    }
+""")
+        return s
+    edit(os.path.join(lib, "EncoderLib", "EncTemporalFilter.cpp"), tfilter)
     print("patched tree:", dst)
 
 

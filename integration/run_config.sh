@@ -4,7 +4,8 @@
 #   bash integration/run_config.sh <1..12> [gpu|cpu] [frames]   (4 = random access, 5 = LD-B with SearchRange 128, both on the small clip;
 #   6 / 7 = configs 1 / 4 with FastSearch=1, the TZ search: xTZSearch on the GPU; 8 = config 1 with FastSearch=2, the selective search;
 #   9 = config 1 with FastSearch=3; 10 / 11 = config 4 with FastSearch=2 / 3; 12 = config 2 (first 3 pictures) with FastSearch=1;
-#   13 = 64x64, 2 pictures, low delay P: small enough for MODE=hooks)
+#   13 = 64x64, 2 pictures, low delay P: small enough for MODE=hooks; 14 = small RA clip, FastSearch=1, with the GOP-based temporal
+#   filter: EncTemporalFilter::filter on the GPU)
 # MODE: gpu = VTMME_ENABLE=1; hooks = VTMME_ENABLE=1 VTMME_TABLE_HOOKS=1 (distortion / interpolation dispatch tables on the
 # GPU too, one launch per table call); cpu = the unmodified encoder (regenerates a golden).
 # Exit status: 0 only when the bitstream md5 equals the golden and the decoder's picture hashes are all OK.
@@ -24,6 +25,7 @@ case $CFGN in
   11) WD=416; HT=240; FR=${3:-9}; BITS=8; CFG=encoder_randomaccess_vtm.cfg; SR=64; EXTRA="-q 32 --IntraPeriod=32"; FS=3;;   # small RA with the enhanced TZ search
   12) WD=1920; HT=1080; FR=${3:-3}; BITS=10; CFG=encoder_randomaccess_vtm.cfg; SR=64; EXTRA="-q 32 --IntraPeriod=32"; FS=1;;   # config 2's picture size with the TZ search (CTC default)
   3) WD=3840; HT=2160; FR=${3:-16}; BITS=10; CFG=encoder_lowdelay_vtm.cfg; SR=128; EXTRA="-q 32";;
+  14) WD=416; HT=240; FR=${3:-11}; BITS=8; CFG=encoder_randomaccess_vtm.cfg; SR=64; EXTRA="-q 32 --IntraPeriod=32 --TemporalFilter=1"; FS=1;;   # small RA clip with the GOP-based temporal filter (pictures 0 and 8 filtered)
   13) WD=64; HT=64; FR=${3:-2}; BITS=8; CFG=encoder_lowdelay_P_vtm.cfg; SR=64; EXTRA="-q 32";;   # tiny clip for the table hooks
   *) echo "unknown configuration $CFGN"; exit 2;;
 esac

@@ -28,6 +28,9 @@ uint64_t   g_batchCalls = 0;   // vtmme_search calls that carried the collected 
 uint64_t   g_batchJobs  = 0;   // searches run in such calls
 uint64_t   g_batchHits  = 0;   // requests answered from a batch
 bool       g_collecting = false;
+uint64_t   g_tfPics     = 0;   // pictures filtered by the GOP-based temporal filter on the GPU
+uint64_t   g_tfRefs     = 0;   // neighbouring pictures searched for them
+double     g_tfSec      = 0;
 
 struct Prefetched
 {
@@ -285,6 +288,49 @@ void search( const SearchIn& in, SearchOut& out )
   if( in.doFrac == 2 ) g_intRefines++;
 }
 
+void temporalFilter( int numRefs, int numComp, const TfPlane* org, const TfPlane* refs, int csx, int csy, const int* bitDepth,
+                     const double* const* weights, int16_t* const* dst, const int* dstStride )
+{
+  vtmme_ctx* c = ctx();
+  const auto t0 = std::chrono::steady_clock::now();
+  // picture ids of the temporal filter live above the reference-picture cache's
+  const int idOrg = 1 << 20, idRef = idOrg + 16, idCorr = idRef + 256;
+  CHECK( numRefs < 1 || numRefs > 8 || numComp < 1 || numComp > 3, "temporal filter: 1..8 neighbouring pictures, 1..3 components" );
+  for( int k = 0; k < numComp; k++ )
+  {
+    CHECK( vtmme_upload_picture( c, idOrg + k, org[k].buf, org[k].stride, org[k].width, org[k].height, 0, 0 ) != VTMME_OK, vtmme_last_error( c ) );
+    for( int r = 0; r < numRefs; r++ )
+    {
+      const TfPlane& p = refs[r * numComp + k];
+      CHECK( vtmme_upload_picture( c, idRef + r * 4 + k, p.buf, p.stride, p.width, p.height, 0, 0 ) != VTMME_OK, vtmme_last_error( c ) );
+    }
+  }
+  // EncTemporalFilter::motionEstimation of every neighbour (:207), one call
+  const int            w = org[0].width, h = org[0].height, mvW = w / 4, mvH = h / 4;
+  std::vector<int32_t> orgIds( numRefs, idOrg ), refIds( numRefs ), mv( (size_t) numRefs * mvW * mvH * 3 );
+  for( int r = 0; r < numRefs; r++ ) refIds[r] = idRef + r * 4;
+  CHECK( vtmme_mctf_me( c, numRefs, orgIds.data(), refIds.data(), bitDepth[0], mv.data() ) != VTMME_OK, vtmme_last_error( c ) );
+  // applyMotion (:564-567) and the weighting (:580-621) per component
+  for( int k = 0; k < numComp; k++ )
+  {
+    const int            cw = org[k].width, ch = org[k].height, sx = k ? csx : 0, sy = k ? csy : 0;
+    std::vector<int16_t> corr( (size_t) cw * ch ), out( (size_t) cw * ch );
+    std::vector<int32_t> corrIds( numRefs );
+    for( int r = 0; r < numRefs; r++ )
+    {
+      CHECK( vtmme_mctf_apply_motion( c, idRef + r * 4 + k, sx, sy, mv.data() + (size_t) r * mvW * mvH * 3, mvW, mvH, bitDepth[k], corr.data() ) != VTMME_OK,
+             vtmme_last_error( c ) );
+      corrIds[r] = idCorr + r * 4 + k;
+      CHECK( vtmme_upload_picture( c, corrIds[r], corr.data(), cw, cw, ch, 0, 0 ) != VTMME_OK, vtmme_last_error( c ) );
+    }
+    CHECK( vtmme_mctf_bilateral( c, idOrg + k, numRefs, corrIds.data(), weights[k], bitDepth[k], out.data() ) != VTMME_OK, vtmme_last_error( c ) );
+    for( int y = 0; y < ch; y++ ) memcpy( dst[k] + (ptrdiff_t) y * dstStride[k], out.data() + (size_t) y * cw, (size_t) cw * 2 );
+  }
+  g_tfSec += std::chrono::duration<double>( std::chrono::steady_clock::now() - t0 ).count();
+  g_tfPics++;
+  g_tfRefs += numRefs;
+}
+
 uint64_t distHost( int kind, const int16_t* org, int orgStride, const int16_t* cur, int curStride, int w, int h, int subShift )
 {
   uint64_t  v  = 0;
@@ -322,6 +368,9 @@ void printStats()
                      "from a batch (%llu collected searches were never asked for)\n",
              (unsigned long long) libCalls, (unsigned long long) g_batchCalls, (unsigned long long) g_batchJobs, (unsigned long long) g_batchHits,
              (unsigned long long) ( g_batchJobs - g_batchHits ) );
+    if( g_tfPics )
+      fprintf( stderr, "[vtmcuda] temporal filter: %llu pictures filtered on the GPU against %llu neighbouring pictures, %.2f s\n",
+               (unsigned long long) g_tfPics, (unsigned long long) g_tfRefs, g_tfSec );
   }
 }
 }   // namespace vtmcuda

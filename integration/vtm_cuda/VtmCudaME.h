@@ -67,6 +67,21 @@ void endCollect();
 // CPU fallback once the GPU path is enabled.
 void search( const SearchIn& in, SearchOut& out );
 
+// GOP-based temporal filter (EncTemporalFilter::filter, EncoderLib/EncTemporalFilter.cpp:133-236) on the GPU: the motion
+// estimation of every neighbouring picture against the original (one batched vtmme_mctf_me call), applyMotion and the
+// bilateral weighting of each component.  Planes are plain pointers (sample (0,0), row stride in samples); the library
+// re-makes the replicated border the filter pads its pictures with.  weights: per component numRefs tables of
+// (1 << bitDepth[c]) doubles, computed by the caller with its own exp() (EncTemporalFilter.cpp:595-610), so the filtered
+// samples are the reference's bit for bit.
+struct TfPlane
+{
+  const int16_t* buf;
+  int            stride, width, height;
+};
+void temporalFilter( int numRefs, int numComp, const TfPlane* org /*[numComp]*/, const TfPlane* refs /*[numRefs][numComp]*/, int csx, int csy,
+                     const int* bitDepth /*[numComp]*/, const double* const* weights /*[numComp]*/, int16_t* const* dst /*[numComp]*/,
+                     const int* dstStride );
+
 // per-block table entries (used by InitCUDA.cpp)
 uint64_t distHost( int kind, const int16_t* org, int orgStride, const int16_t* cur, int curStride, int w, int h, int subShift );
 void     interpHost( int comp, int vertical, const int16_t* src, int srcStride, int16_t* dst, int dstStride, int w, int h,
