@@ -712,27 +712,35 @@ __global__ void __launch_bounds__(kUpperThreads) me_tree_upper_kernel(TreeParams
       any |= bits[s] < 256;
     }
     if (!any) continue;
-    // s64: what the 64x64 CUs compare (even rows x2 in subShiftMode 2); s64f: all rows, summed into the 128x128 CU
+    // s64: what the 64x64 CUs compare (even rows x2 in subShiftMode 2); s64f: all rows, summed into the 128x128 CU.
+    // All (up to 16, in subShiftMode 2 32) surface reads of a displacement are issued before any is used — the kernel is
+    // bound by HBM latency x bytes in flight; a surface this displacement lies outside of reads its first element instead.
+    uint32_t f[16], e[16];
+#pragma unroll
+    for (int ri = 0; ri < 16; ri++)
+    {
+      const int4      info = s_reg[ri];
+      const uint32_t* sp   = s_surf[ri];
+      const int       j    = ((ri >> 3) << 1) | ((ri >> 1) & 1);   // the 64x64 CU this region belongs to
+      const bool      need = sp != nullptr && (bits[j] < 256 || bits[4] < 256);
+      const size_t    o    = need ? (size_t) (dy - info.y) * (info.z * 8) + (dx - info.x) : 0;
+      const uint32_t* pf   = need ? sp : p.surf;
+      f[ri] = __ldg(pf + o);
+      if (TWO) e[ri] = __ldg((need ? s_surfE[ri] : p.surf) + o);
+      if (!need) f[ri] = 0;
+      if (TWO && !need) e[ri] = 0;
+    }
     uint32_t   s64[4], s64f[4];
 #pragma unroll
     for (int j = 0; j < 4; j++)
     {
       s64[j] = s64f[j] = 0;
-      if (bits[j] < 256 || bits[4] < 256)
-      {
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-        {
-          const int  ri   = ((j >> 1) * 2 + (k >> 1)) * 4 + (j & 1) * 2 + (k & 1);
-          const int4 info = s_reg[ri];
-          if (s_surf[ri])
-          {
-            const size_t o = (size_t) (dy - info.y) * (info.z * 8) + (dx - info.x);
-            const uint32_t f = s_surf[ri][o];
-            s64f[j] += f;
-            if (TWO) s64[j] += s_surfE[ri][o];
-          }
-        }
+      for (int k = 0; k < 4; k++)
+      {
+        const int ri = ((j >> 1) * 2 + (k >> 1)) * 4 + (j & 1) * 2 + (k & 1);
+        s64f[j] += f[ri];
+        if (TWO) s64[j] += e[ri];
       }
     }
 #pragma unroll
