@@ -320,7 +320,7 @@ def run_ours(args, rank, world, local_rank):
     if pool < 1:
         raise SystemExit("fewer pairs than ranks")
     host_cur, host_ref = [None] * pool, [None] * pool
-    pair0 = host_pair0() if (rank == 0 and not args.no_cpu) else None
+    pair0 = host_pair0() if (rank == 0 and world == 1 and not args.no_cpu) else None   # CPU leg + parity: N=1 only
     for c0 in range(0, pool, 8):
         cur, ref = make_pairs_torch(ids[c0:c0 + 8], dev, WIDTH, HEIGHT)
         for i in range(cur.shape[0]):

@@ -1,7 +1,7 @@
 # usage: bash scripts/prof_tree.sh "<variant> ..."  : parity tests with the default variant, then one ncu --set full capture per variant
 set -x
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
-SMALL="--steps 1 --warmup 1 --pairs-per-step 4 --pool 4 --e2e-pool 1 --e2e-steps 1 --no-cpu"
+SMALL="--steps 1 --warmup 1 --pairs-per-step 4 --pool 4 --no-cpu"
 for v in $1; do
   tag=$(echo $v | tr ',' '_')
   VTMME_TREE_VARIANT=$v timeout 600 python bench.py $SMALL > gpurun_out/plain_$tag.log 2>&1 &&

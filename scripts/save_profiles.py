@@ -29,7 +29,7 @@ tot_ours = sum(agg[k][1] for k in ours)
 share = sum(agg[k][1] for k in ours if "me_tree_sad" in k) / tot_ours
 with open("profiles/%s_launches_summary.md" % pre, "w") as f:
     f.write("# %s launch list (ncu --metrics gpu__time_duration.sum --clock-control none)\n\n" % pre)
-    f.write("command: `python bench.py --steps 1 --warmup 1 --pairs-per-step 4 --pool 4 --e2e-pool 4 --e2e-steps 1 --no-cpu` "
+    f.write("command: `python bench.py --steps 1 --warmup 1 --pairs-per-step 4 --pool 4 --no-cpu` "
             "(cold-cache, serialised: compare shares).\n\n")
     f.write("Share of `me_tree_sad_kernel` among the search kernels: **%.2f** here, **%.2f** live in the timed step of the full "
             "bench (`%s_bench.json`, roofline.kernel_share_of_step; the live figure also contains the host gaps of a step).\n\n"
