@@ -97,7 +97,9 @@ struct TzFrameParams
   int                 selective;   // FastSearch=2: xTZSearchSelective; subShiftMode 1 = staged SAD
   double              lambda;
 };
-cudaError_t launch_tz_frame(const TzFrameParams& p, int nPairs, cudaStream_t st, int* launches);
+cudaError_t launch_tz_frame(const TzFrameParams& p, int nPairs, int predSpread, cudaStream_t st, int* launches);
+// me_tz_smem.cu: one level (0 .. 3) with the search windows staged in shared memory; *done = false when they do not fit
+cudaError_t launch_tz_frame_smem(const TzFrameParams& p, int level, int nPairs, int predSpread, cudaStream_t st, bool* done);
 
 // Fractional refinement + result write-out for the frame path.
 struct FracFrameParams

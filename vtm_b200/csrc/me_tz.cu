@@ -9,6 +9,8 @@
 // CU has sampled rows (TzEvalTile in me_tz.cuh: four 8x8 probes per warp at a time), the lane's pattern row stays in
 // registers, the probes are read from the reference picture through L1/L2 — a search touches a few hundred
 // scattered blocks of a window that neighbouring CUs share.  Largest CUs are scheduled first.
+#include <cstdlib>
+
 #include "me_tz.cuh"
 
 namespace vtmme {
@@ -134,10 +136,14 @@ cudaError_t launch_level(const TzFrameParams& p, int level, int nPairs, cudaStre
 
 // DistParam::subShift of the integer search is 1 for CUs of 16..64 rows when subShiftMode is 2 (RdCost.cpp:310-316).
 // Largest CUs first.  Returns the number of kernels launched in *launches.
-cudaError_t launch_tz_frame(const TzFrameParams& p, int nPairs, cudaStream_t st, int* launches)
+cudaError_t launch_tz_frame(const TzFrameParams& p, int nPairs, int predSpread, cudaStream_t st, int* launches)
 {
   const bool  ss = p.subShiftMode == 2;
   cudaError_t e;
+  // levels 8x8 .. 64x64: windows staged in shared memory (me_tz_smem.cu) when they fit; VTMME_TZ_VARIANT=global keeps the
+  // kernels below (probes read from the picture) for all levels
+  static const bool useSmem = [] { const char* v = getenv("VTMME_TZ_VARIANT"); return !(v && v[0] == 'g'); }();
+  bool viaSmem[4] = { false, false, false, false };
   if (p.selective)
   {
     for (int l = 4; l >= 0; l--)
@@ -151,10 +157,15 @@ cudaError_t launch_tz_frame(const TzFrameParams& p, int nPairs, cudaStream_t st,
     return cudaSuccess;
   }
   if ((e = launch_level<128, 0>(p, 4, nPairs, st)) != cudaSuccess) return e;
-  if ((e = ss ? launch_level<64, 1>(p, 3, nPairs, st) : launch_level<64, 0>(p, 3, nPairs, st)) != cudaSuccess) return e;
-  if ((e = ss ? launch_level<32, 1>(p, 2, nPairs, st) : launch_level<32, 0>(p, 2, nPairs, st)) != cudaSuccess) return e;
-  if ((e = ss ? launch_level<16, 1>(p, 1, nPairs, st) : launch_level<16, 0>(p, 1, nPairs, st)) != cudaSuccess) return e;
-  if ((e = launch_level<8, 0>(p, 0, nPairs, st)) != cudaSuccess) return e;
+  // measured per level (32 pairs of 1080p, SR=64, profiles/r02k_tz_levels.md): staged windows win at 8x8, 16x16 and 64x64
+  // (38.7 / 22.9 / 19.3 ms against 46.5 / 26.5 / 26.2), the picture-read kernel at 32x32 (18.0 against 21.7)
+  if (useSmem)
+    for (int l = 3; l >= 0; l--)
+      if (l != 2 && (e = launch_tz_frame_smem(p, l, nPairs, predSpread, st, &viaSmem[l])) != cudaSuccess) return e;
+  if (!viaSmem[3] && (e = ss ? launch_level<64, 1>(p, 3, nPairs, st) : launch_level<64, 0>(p, 3, nPairs, st)) != cudaSuccess) return e;
+  if (!viaSmem[2] && (e = ss ? launch_level<32, 1>(p, 2, nPairs, st) : launch_level<32, 0>(p, 2, nPairs, st)) != cudaSuccess) return e;
+  if (!viaSmem[1] && (e = ss ? launch_level<16, 1>(p, 1, nPairs, st) : launch_level<16, 0>(p, 1, nPairs, st)) != cudaSuccess) return e;
+  if (!viaSmem[0] && (e = launch_level<8, 0>(p, 0, nPairs, st)) != cudaSuccess) return e;
   for (int l = 0; l < 5; l++) *launches += p.g.nx[l] * p.g.ny[l] > 0;
   return cudaSuccess;
 }

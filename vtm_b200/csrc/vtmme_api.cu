@@ -498,7 +498,7 @@ int vtmme_search_frames_device(vtmme_ctx* ctx, int nPairs, const int32_t* curPic
     zp.selective       = prm->fastSearch == 2;
     zp.firstSearchStop = prm->tzFirstSearchStop;
     zp.lambda          = prm->lambdaMotion;
-    VTMME_CUDA_CHECK(ctx, launch_tz_frame(zp, nPairs, ctx->stream, &tzLaunches));
+    VTMME_CUDA_CHECK(ctx, launch_tz_frame(zp, nPairs, prm->predSpread, ctx->stream, &tzLaunches));
     if (prof) VTMME_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     if (prof) VTMME_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
   }
