@@ -336,6 +336,30 @@ typedef struct
 int vtmme_dmvr_refine(vtmme_ctx* ctx, int refPic0, int refPic1, int bitDepth, int maxCu, int n, const vtmme_dmvr_block* blocks,
                       vtmme_dmvr_result* results);
 
+/* ---- affine motion estimation: AffineGradientSearch's dispatch-table primitives ------------------------------
+ * The three function pointers every iteration of InterSearch::xAffineMotionEstimation calls (EncoderLib/InterSearch.cpp:5486-5526;
+ * CommonLib/AffineGradientSearch.h:52-54, scalar :64-174, SIMD x86/AffineGradientSearchX86.h):
+ *   m_HorizontalSobelFilter / m_VerticalSobelFilter   3x3 Sobel of the prediction into int derivatives, border = nearest interior value
+ *   m_EqualCoeffComputer                              sums of products of the per-sample model vector (4- or 6-parameter) and of its
+ *                                                     product with the residual (<< 3), int64, accumulated into coeff[7][7]
+ * Table flavour (HOST pointers, one block per call — what initAffineGradientSearchCUDA installs, cf. initRdCostCUDA): */
+int vtmme_affine_sobel_host(vtmme_ctx* ctx, int vertical, const int16_t* pred, int predStride, int w, int h, int32_t* deriv, int derivStride);
+int vtmme_affine_equal_coeff_host(vtmme_ctx* ctx, const int16_t* residue, int residueStride, const int32_t* d0, const int32_t* d1,
+                                  int derivStride, int w, int h, int sixParam, int64_t* coeff /* [7][7], accumulated */);
+/* Batched flavour: one gradient step — error = org - pred, both derivatives, the sums — for n blocks in ONE launch.
+ * coeff: HOST, n * 49 entries, block i's matrix (rows 1..p, columns 0..p; p = 4 or 6) starting from zero. */
+typedef struct
+{
+  const int16_t* org;        /* HOST: original block (for bi-prediction: 2*org - other prediction)  */
+  int32_t        orgStride;
+  const int16_t* pred;       /* HOST: current affine prediction of the block (xPredAffineBlk)       */
+  int32_t        predStride;
+  int32_t        w, h;       /* 4..128                                                              */
+  int32_t        sixParam;   /* cu.affineType == AFFINEMODEL_6PARAM                                 */
+  int32_t        reserved;   /* 0                                                                   */
+} vtmme_affine_block;
+int vtmme_affine_gradient_step(vtmme_ctx* ctx, int n, const vtmme_affine_block* blocks, int64_t* coeff);
+
 /* ---- symmetric-MVD search -------------------------------------------------------------------------
  * InterSearch::xSymmetricMotionEstimation (EncoderLib/InterSearch.cpp:4506-4518): the MV of the searched list moves on a
  * diamond (at most 8 >> imv rounds) and once on a cross (xSymmeticRefineMvSearch :4393-4503), the MV of the other list

@@ -58,6 +58,13 @@ def main():
         r"(void InterpolationFilter::initInterpolationFilter\( bool enable \)\n\{\n(?:.*\n)*?#endif\n#endif\n)\}",
         r"\1  if ( enable )\n  {\n    initInterpolationFilterCUDA();   // libvtmme\n  }\n}", s, count=1))
 
+    # 3b. AffineGradientSearch: the third dispatch table (Sobel filters and xEqualCoeffComputer of the affine ME)
+    edit(os.path.join(lib, "CommonLib", "AffineGradientSearch.h"), lambda s: once(
+        s, "  void initAffineGradientSearchX86();", "  void initAffineGradientSearchX86();\n  void initAffineGradientSearchCUDA();   // libvtmme"))
+    edit(os.path.join(lib, "CommonLib", "AffineGradientSearch.cpp"), lambda s: re.sub(
+        r"(AffineGradientSearch::AffineGradientSearch\(\)\n\{\n(?:.*\n)*?#endif\n#endif\n)\}",
+        r"\1  initAffineGradientSearchCUDA();   // libvtmme: after the X86 entries\n}", s, count=1))
+
     # 4. InterSearch.cpp: xMotionEstimation calls the GPU entry instead of xPatternSearch / xTZSearch (+ the refinement)
     def inter(s):
         s = once(s, '#include "InterSearch.h"\n', '#include "InterSearch.h"\n#include "CommonLib/cuda/VtmCudaME.h"   // libvtmme\n')

@@ -7,6 +7,7 @@
 // One block per call with host pointers is launch-bound by construction (SURVEY.md §7 "hard parts" 3): these
 // hooks exist for table-level parity and the micro-benchmark; encoder throughput comes from vtmcuda::search().
 // They are only installed when VTMME_TABLE_HOOKS=1.
+#include "CommonLib/AffineGradientSearch.h"
 #include "CommonLib/CommonDef.h"
 #include "CommonLib/InterpolationFilter.h"
 #include "CommonLib/RdCost.h"
@@ -20,13 +21,14 @@ namespace
 FpDistFunc s_prevDist[DF_TOTAL_FUNCTIONS];
 // calls answered by the GPU / handed to the entry that was replaced; printed at exit (VTMME_TABLE_HOOKS=2: count
 // only — every call is delegated, which sizes a run without a GPU)
-unsigned long long s_distGpu = 0, s_distPrev = 0, s_filtGpu = 0, s_filtPrev = 0;
+unsigned long long s_distGpu = 0, s_distPrev = 0, s_filtGpu = 0, s_filtPrev = 0, s_affGpu = 0, s_affPrev = 0;
 bool               s_countOnly = false;
 
 void printHookStats()
 {
-  fprintf( stderr, "[vtmcuda] table hooks: distortion %llu on the GPU / %llu delegated, filters %llu on the GPU / %llu delegated%s\n",
-           s_distGpu, s_distPrev, s_filtGpu, s_filtPrev, s_countOnly ? " (count only)" : "" );
+  fprintf( stderr, "[vtmcuda] table hooks: distortion %llu on the GPU / %llu delegated, filters %llu on the GPU / %llu delegated, "
+                   "affine gradient entries %llu on the GPU / %llu delegated%s\n",
+           s_distGpu, s_distPrev, s_filtGpu, s_filtPrev, s_affGpu, s_affPrev, s_countOnly ? " (count only)" : "" );
 }
 
 template<int DF> Distortion distCuda( const DistParam& dp )
@@ -131,4 +133,51 @@ void InterpolationFilter::initInterpolationFilterCUDA()
   m_filterVer[1][1][1] = filterCuda<1, true, true, true>;
   m_filterCopy[0][1]   = copyCuda<false, true>;
   m_filterCopy[1][0]   = copyCuda<true, false>;
+}
+
+// AffineGradientSearch::initAffineGradientSearchCUDA(): the CUDA sibling of initAffineGradientSearchX86()
+// (x86/AffineGradientSearchX86.h:311-317) — the Sobel filters and xEqualCoeffComputer of the affine motion estimation.
+namespace
+{
+typedef void ( *SobelFn )( Pel* const, const int, int* const, const int, const int, const int );
+typedef void ( *EqualFn )( Pel*, int, int**, int, int64_t ( * )[7], int, int, bool );
+SobelFn s_prevSobelH = nullptr, s_prevSobelV = nullptr;
+EqualFn s_prevEqual  = nullptr;
+
+bool affineOnGpu( int w, int h ) { return !s_countOnly && w >= 4 && h >= 4 && w <= 128 && h <= 128; }
+
+void sobelHCuda( Pel* const pPred, const int predStride, int* const pDerivate, const int derivateBufStride, const int width, const int height )
+{
+  if( !affineOnGpu( width, height ) ) { s_affPrev++; s_prevSobelH( pPred, predStride, pDerivate, derivateBufStride, width, height ); return; }
+  s_affGpu++;
+  vtmcuda::affineSobelHost( 0, pPred, predStride, width, height, pDerivate, derivateBufStride );
+}
+
+void sobelVCuda( Pel* const pPred, const int predStride, int* const pDerivate, const int derivateBufStride, const int width, const int height )
+{
+  if( !affineOnGpu( width, height ) ) { s_affPrev++; s_prevSobelV( pPred, predStride, pDerivate, derivateBufStride, width, height ); return; }
+  s_affGpu++;
+  vtmcuda::affineSobelHost( 1, pPred, predStride, width, height, pDerivate, derivateBufStride );
+}
+
+void equalCoeffCuda( Pel* pResidue, int residueStride, int** ppDerivate, int derivateBufStride, int64_t ( *pEqualCoeff )[7], int width, int height, bool b6Param )
+{
+  if( !affineOnGpu( width, height ) ) { s_affPrev++; s_prevEqual( pResidue, residueStride, ppDerivate, derivateBufStride, pEqualCoeff, width, height, b6Param ); return; }
+  s_affGpu++;
+  vtmcuda::affineEqualCoeffHost( pResidue, residueStride, ppDerivate[0], ppDerivate[1], derivateBufStride, width, height, b6Param ? 1 : 0, &pEqualCoeff[0][0] );
+}
+}   // namespace
+
+void AffineGradientSearch::initAffineGradientSearchCUDA()
+{
+  if( !vtmcuda::tableHooksEnabled() ) return;
+  if( !s_prevEqual )   // the entries every instance starts from are the same: remember them once
+  {
+    s_prevSobelH = m_HorizontalSobelFilter;
+    s_prevSobelV = m_VerticalSobelFilter;
+    s_prevEqual  = m_EqualCoeffComputer;
+  }
+  m_HorizontalSobelFilter = sobelHCuda;
+  m_VerticalSobelFilter   = sobelVCuda;
+  m_EqualCoeffComputer    = equalCoeffCuda;
 }

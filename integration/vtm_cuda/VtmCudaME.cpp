@@ -355,6 +355,19 @@ void filterHost( int taps, int vertical, int isFirst, int isLast, int copy, cons
   CHECK( rc != VTMME_OK, vtmme_last_error( g_ctx ) );
 }
 
+void affineSobelHost( int vertical, const int16_t* pred, int predStride, int w, int h, int* deriv, int derivStride )
+{
+  const int rc = vtmme_affine_sobel_host( ctx(), vertical, pred, predStride, w, h, deriv, derivStride );
+  CHECK( rc != VTMME_OK, vtmme_last_error( g_ctx ) );
+}
+
+void affineEqualCoeffHost( const int16_t* residue, int residueStride, const int* d0, const int* d1, int derivStride, int w, int h, int sixParam,
+                           int64_t* coeff )
+{
+  const int rc = vtmme_affine_equal_coeff_host( ctx(), residue, residueStride, d0, d1, derivStride, w, h, sixParam, coeff );
+  CHECK( rc != VTMME_OK, vtmme_last_error( g_ctx ) );
+}
+
 void printStats()
 {
   if( g_ctx )

@@ -89,5 +89,9 @@ void     interpHost( int comp, int vertical, const int16_t* src, int srcStride, 
 // table-entry flavour of the filters: explicit taps (what m_filterHor/m_filterVer/m_filterCopy entries receive)
 void     filterHost( int taps, int vertical, int isFirst, int isLast, int copy, const int16_t* src, int srcStride, int16_t* dst,
                      int dstStride, int w, int h, const int16_t* coeff, int bitDepth );
+// AffineGradientSearch's table entries (InitCUDA.cpp)
+void     affineSobelHost( int vertical, const int16_t* pred, int predStride, int w, int h, int* deriv, int derivStride );
+void     affineEqualCoeffHost( const int16_t* residue, int residueStride, const int* d0, const int* d1, int derivStride, int w, int h, int sixParam,
+                               int64_t* coeff );
 void     printStats();
 }   // namespace vtmcuda

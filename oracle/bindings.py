@@ -115,6 +115,10 @@ def oracle():
         L.vo_int_refine.argtypes = [C.POINTER(Job), C.POINTER(IntRefine)]
         L.vo_tz_search.argtypes = [C.POINTER(Job), C.POINTER(TzParams), C.POINTER(_I), C.POINTER(_I),
                                    C.POINTER(C.c_uint64), C.POINTER(_I)]
+        L.vo_affine_sobel.restype = None
+        L.vo_affine_sobel.argtypes = [_I, _P, _I, _P, _I, _I, _I]
+        L.vo_affine_equal_coeff.restype = None
+        L.vo_affine_equal_coeff.argtypes = [_P, _I, _P, _P, _I, _P, _I, _I, _I]
         L.vo_mctf_apply_motion.argtypes = [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _I]
         L.vo_mctf_me.argtypes = [_P, _I, _P, _I, _I, _I, _I, _P]
         L.vo_mctf_bilateral_weights.restype = None
@@ -160,6 +164,10 @@ def ref():
         L.ref_filter_hor.argtypes = [_I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I]
         L.ref_filter_ver.argtypes = [_I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I]
         L.ref_search.argtypes = [C.POINTER(Job), C.POINTER(Result)]
+        L.ref_affine_sobel.restype = None
+        L.ref_affine_sobel.argtypes = [_I, _P, _I, _P, _I, _I, _I]
+        L.ref_affine_equal_coeff.restype = None
+        L.ref_affine_equal_coeff.argtypes = [_P, _I, _P, _P, _I, _P, _I, _I, _I]
         L.ref_search_batch.argtypes = [C.POINTER(Job), C.POINTER(Result), _I, _I]
         L.ref_search_batch.restype = C.c_double
         L.ref_dist_batch.restype = C.c_double

@@ -22,6 +22,7 @@
 #include <atomic>
 
 #include "CommonLib/CommonDef.h"
+#include "CommonLib/AffineGradientSearch.h"
 #include "CommonLib/RdCost.h"
 #include "CommonLib/InterpolationFilter.h"
 #include "CommonLib/InterPrediction.h"
@@ -1030,6 +1031,21 @@ double ref_search_batch(const RefSearchJob* jobs, RefSearchResult* res, int n, i
   }
   auto t1 = std::chrono::steady_clock::now();
   return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// AffineGradientSearch's own table entries (SIMD where the reference installs them): Sobel filters and xEqualCoeffComputer
+void ref_affine_sobel(int vertical, const int16_t* pred, int predStride, int* deriv, int derivStride, int w, int h)
+{
+  static AffineGradientSearch ags;
+  (vertical ? ags.m_VerticalSobelFilter : ags.m_HorizontalSobelFilter)(const_cast<Pel*>(pred), predStride, deriv, derivStride, w, h);
+}
+
+void ref_affine_equal_coeff(const int16_t* residue, int residueStride, int* d0, int* d1, int derivStride, int64_t* coeff, int w, int h,
+                            int sixParam)
+{
+  static AffineGradientSearch ags;
+  int* dd[2] = { d0, d1 };
+  ags.m_EqualCoeffComputer(const_cast<Pel*>(residue), residueStride, dd, derivStride, reinterpret_cast<int64_t(*)[7]>(coeff), w, h, sixParam != 0);
 }
 
 }   // extern "C"

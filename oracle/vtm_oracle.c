@@ -1770,3 +1770,65 @@ void vo_mctf_apply_motion(const vo_pel* src, int srcStride, int compW, int compH
         }
     }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Affine motion estimation: the three dispatch-table primitives of AffineGradientSearch
+ * (CommonLib/AffineGradientSearch.cpp:64-174; SIMD x86/AffineGradientSearchX86.h), called once per iteration of
+ * InterSearch::xAffineMotionEstimation (EncoderLib/InterSearch.cpp:5501-5526)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* xHorizontalSobelFilter / xVerticalSobelFilter: 3x3 Sobel of the prediction; the border takes the nearest interior value */
+void vo_affine_sobel(int vertical, const vo_pel* pred, int predStride, int* deriv, int derivStride, int w, int h)
+{
+  int j, k;
+  for (j = 0; j < h; j++)
+    for (k = 0; k < w; k++)
+    {
+      const int jj = j < 1 ? 1 : (j > h - 2 ? h - 2 : j), kk = k < 1 ? 1 : (k > w - 2 ? w - 2 : k);
+      const vo_pel* c = pred + (ptrdiff_t) jj * predStride + kk;
+      int v;
+      if (!vertical)
+        v = c[1 - predStride] - c[-1 - predStride] + (c[1] << 1) - (c[-1] << 1) + c[1 + predStride] - c[-1 + predStride];
+      else
+        v = c[predStride - 1] - c[-predStride - 1] + (c[predStride] << 1) - (c[-predStride] << 1) + c[predStride + 1] - c[-predStride + 1];
+      deriv[(ptrdiff_t) j * derivStride + k] = v;
+    }
+}
+
+/* xEqualCoeffComputer: accumulates into coeff[7][7] (rows 1..n, columns 0..n; n = 4 or 6 affine parameters) */
+void vo_affine_equal_coeff(const vo_pel* residue, int residueStride, const int* d0, const int* d1, int derivStride, int64_t coeff[7][7],
+                           int w, int h, int sixParam)
+{
+  const int n = sixParam ? 6 : 4;
+  int j, k, col, row;
+  for (j = 0; j < h; j++)
+  {
+    const int cy = ((j >> 2) << 2) + 2;
+    for (k = 0; k < w; k++)
+    {
+      const int cx = ((k >> 2) << 2) + 2, gx = d0[(ptrdiff_t) j * derivStride + k], gy = d1[(ptrdiff_t) j * derivStride + k];
+      int c[6];
+      if (!sixParam)
+      {
+        c[0] = gx;
+        c[1] = cx * gx + cy * gy;
+        c[2] = gy;
+        c[3] = cy * gx - cx * gy;
+      }
+      else
+      {
+        c[0] = gx;
+        c[1] = cx * gx;
+        c[2] = gy;
+        c[3] = cx * gy;
+        c[4] = cy * gx;
+        c[5] = cy * gy;
+      }
+      for (col = 0; col < n; col++)
+      {
+        for (row = 0; row < n; row++) coeff[col + 1][row] += (int64_t) c[col] * c[row];
+        coeff[col + 1][n] += ((int64_t) c[col] * residue[(ptrdiff_t) j * residueStride + k]) << 3;
+      }
+    }
+  }
+}

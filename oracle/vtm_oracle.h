@@ -200,4 +200,9 @@ void vo_dmvr_final_chroma(const vo_pel* ref, int refStride, int x, int y, int w,
 #ifdef __cplusplus
 }
 #endif
+/* Affine ME: AffineGradientSearch's dispatch-table primitives (CommonLib/AffineGradientSearch.cpp:64-174) */
+void vo_affine_sobel(int vertical, const vo_pel* pred, int predStride, int* deriv, int derivStride, int w, int h);
+void vo_affine_equal_coeff(const vo_pel* residue, int residueStride, const int* d0, const int* d1, int derivStride, int64_t coeff[7][7],
+                           int w, int h, int sixParam);
+
 #endif

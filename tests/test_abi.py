@@ -64,7 +64,7 @@ def test_struct_layouts_match_the_header(tmp_path):
     pairs = {"vtmme_job": lib.CJob, "vtmme_result": lib.CResult, "vtmme_amvr": lib.CAmvr, "vtmme_tz": lib.CTz,
              "vtmme_frame_params": lib.CFrameParams, "vtmme_mc_block": lib.CMcBlock, "vtmme_cand_job": lib.CCandJob,
              "vtmme_dmvr_block": lib.CDmvrBlock, "vtmme_dmvr_result": lib.CDmvrResult, "vtmme_smvd": lib.CSmvd,
-             "vtmme_smvd_result": lib.CSmvdResult}
+             "vtmme_smvd_result": lib.CSmvdResult, "vtmme_affine_block": lib.CAffineBlock}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "vtmme.h"', 'int main(void){']
     for cname, cls in pairs.items():
         lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))

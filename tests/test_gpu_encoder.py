@@ -48,7 +48,9 @@ def test_encoder_md5_with_gpu_search(tmp_path):
 @pytest.mark.skipif(not os.path.exists(ENC), reason="oracle/_ref/EncoderAppCUDA was not built (needs /root/reference at build time)")
 def test_encoder_md5_with_table_hooks(tmp_path):
     gold, out, err = _encode(tmp_path, {"VTMME_ENABLE": "1", "VTMME_TABLE_HOOKS": "1"}, "hooks")
-    m = re.search(r"table hooks: distortion (\d+) on the GPU / (\d+) delegated, filters (\d+) on the GPU", err)
+    m = re.search(r"table hooks: distortion (\d+) on the GPU / (\d+) delegated, filters (\d+) on the GPU / \d+ delegated, "
+                  r"affine gradient entries (\d+) on the GPU", err)
     assert m, err[-500:]
-    assert int(m.group(1)) > 10000 and int(m.group(3)) > 10000      # the table entries really ran on the GPU
+    # the entries of all three dispatch tables (RdCost, InterpolationFilter, AffineGradientSearch) really ran on the GPU
+    assert int(m.group(1)) > 10000 and int(m.group(3)) > 10000 and int(m.group(4)) > 1000
     assert hashlib.md5(out.read_bytes()).hexdigest() == gold["bitstream_md5"]

@@ -684,3 +684,31 @@ def test_mctf_apply_motion(oracle_lib, ref_lib, w, h, bd):
         oracle_lib.vo_mctf_apply_motion(B.ptr(chp, 64 * chp.shape[1] + 64), chp.shape[1], w // 2, h // 2, 1, 1,
                                         C.c_void_p(mv.ctypes.data), w // 4, bd, B.ptr(got_c), w // 2)
         assert np.array_equal(got_y, want_y) and np.array_equal(got_c, want_c), variant
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("six", [0, 1])
+def test_affine_gradient_primitives(oracle_lib, ref_lib, six):
+    """AffineGradientSearch's three dispatch-table entries (CommonLib/AffineGradientSearch.cpp:64-174, the reference's SIMD
+    versions where it installs them): Sobel derivatives of a prediction with their replicated border, and the normal-equation
+    sums of xEqualCoeffComputer (4- and 6-parameter model) — every derivative and every int64 coefficient equal."""
+    rng = np.random.default_rng(1300 + six)
+    for (w, h) in [(16, 16), (32, 16), (16, 64), (64, 64), (128, 32), (128, 128)]:
+        stride = w + 8
+        pred = rng.integers(0, 1024, (h, stride)).astype(np.int16)
+        # the residual has the row stride of the derivatives, as in xAffineMotionEstimation (both `width`; the reference's SIMD
+        # entry indexes it with the derivatives' index)
+        res = rng.integers(-1023, 1024, (h, w)).astype(np.int16)
+        got, want = [np.zeros((h, w), np.int32) for _ in range(2)], [np.zeros((h, w), np.int32) for _ in range(2)]
+        for v in (0, 1):
+            oracle_lib.vo_affine_sobel(v, B.ptr(pred), stride, C.c_void_p(got[v].ctypes.data), w, w, h)
+            ref_lib.ref_affine_sobel(v, B.ptr(pred), stride, C.c_void_p(want[v].ctypes.data), w, w, h)
+            assert np.array_equal(got[v], want[v]), (w, h, v)
+        cg, cw = np.zeros((7, 7), np.int64), np.zeros((7, 7), np.int64)
+        cg[1, 0] = cw[1, 0] = 12345                     # the entries accumulate
+        oracle_lib.vo_affine_equal_coeff(B.ptr(res), w, C.c_void_p(got[0].ctypes.data), C.c_void_p(got[1].ctypes.data), w,
+                                         C.c_void_p(cg.ctypes.data), w, h, six)
+        ref_lib.ref_affine_equal_coeff(B.ptr(res), w, C.c_void_p(want[0].ctypes.data), C.c_void_p(want[1].ctypes.data), w,
+                                       C.c_void_p(cw.ctypes.data), w, h, six)
+        assert np.array_equal(cg, cw), (w, h)
+        assert np.abs(cg).max() > 1 << 32

@@ -258,6 +258,18 @@ struct DevSmvdResult
 };
 cudaError_t launch_smvd_search(const DevSmvd* dJobs, DevSmvdResult* dOut, int n, cudaStream_t st);
 
+// Affine ME primitives (affine_kernels.cu)
+struct DevAffineBlock
+{
+  const int16_t* org;
+  const int16_t* pred;
+  int            orgStride, predStride, w, h, sixParam, pad;
+};
+cudaError_t launch_affine_sobel(const int16_t* pred, int stride, int w, int h, int vertical, int* deriv, cudaStream_t st);
+cudaError_t launch_affine_equal_coeff(const int16_t* residue, int residueStride, const int* d0, const int* d1, int derivStride, int w, int h,
+                                      int sixParam, long long* coeff, cudaStream_t st);
+cudaError_t launch_affine_step(const DevAffineBlock* dBlocks, int n, long long* dCoeff, cudaStream_t st);
+
 // GOP-based temporal filter motion estimation (mctf_kernels.cu)
 struct MctfLevelParams
 {

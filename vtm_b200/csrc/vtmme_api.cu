@@ -1426,6 +1426,117 @@ extern "C" int vtmme_mc_host(vtmme_ctx* ctx, int comp, int bi, int bitDepth, int
   return VTMME_OK;
 }
 
+// ---- affine ME primitives (AffineGradientSearch's table entries) ---------------------------------------------------------
+static int affine_dims_ok(int w, int h) { return w >= 4 && h >= 4 && w <= 128 && h <= 128; }
+
+extern "C" int vtmme_affine_sobel_host(vtmme_ctx* ctx, int vertical, const int16_t* pred, int predStride, int w, int h, int32_t* deriv,
+                                       int derivStride)
+{
+  if (!ctx) return VTMME_ERR_ARG;
+  if (!pred || !deriv || !affine_dims_ok(w, h) || predStride < w || derivStride < w)
+    return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_affine_sobel_host", "bad argument (4 <= w, h <= 128)");
+  VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  const size_t inBytes = align256((size_t) w * h * 2), outBytes = (size_t) w * h * 4;
+  int rc;
+  if ((rc = ensure_pinned(ctx, inBytes + outBytes)) != VTMME_OK) return rc;
+  if ((rc = ensure(ctx, ctx->dJobBuf, ctx->jobBufCap, inBytes + outBytes)) != VTMME_OK) return rc;
+  int16_t* hp = reinterpret_cast<int16_t*>(ctx->hPinned);
+  for (int y = 0; y < h; y++) memcpy(hp + (size_t) y * w, pred + (ptrdiff_t) y * predStride, (size_t) w * 2);
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dJobBuf, ctx->hPinned, inBytes, cudaMemcpyHostToDevice, ctx->stream));
+  int* dD = reinterpret_cast<int*>(ctx->dJobBuf + inBytes);
+  VTMME_CUDA_CHECK(ctx, launch_affine_sobel(reinterpret_cast<const int16_t*>(ctx->dJobBuf), w, w, h, vertical, dD, ctx->stream));
+  ctx->launches += 1;
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->hPinned + inBytes, dD, outBytes, cudaMemcpyDeviceToHost, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  const int32_t* ho = reinterpret_cast<const int32_t*>(ctx->hPinned + inBytes);
+  for (int y = 0; y < h; y++) memcpy(deriv + (ptrdiff_t) y * derivStride, ho + (size_t) y * w, (size_t) w * 4);
+  return VTMME_OK;
+}
+
+extern "C" int vtmme_affine_equal_coeff_host(vtmme_ctx* ctx, const int16_t* residue, int residueStride, const int32_t* d0, const int32_t* d1,
+                                             int derivStride, int w, int h, int sixParam, int64_t* coeff)
+{
+  if (!ctx) return VTMME_ERR_ARG;
+  if (!residue || !d0 || !d1 || !coeff || !affine_dims_ok(w, h) || residueStride < w || derivStride < w)
+    return vtmme_set_error(ctx, VTMME_ERR_ARG, "vtmme_affine_equal_coeff_host", "bad argument (4 <= w, h <= 128)");
+  VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  const size_t rBytes = align256((size_t) w * h * 2), dBytes = align256((size_t) w * h * 4), cBytes = 49 * 8;
+  const size_t total = rBytes + 2 * dBytes + align256(cBytes);
+  int rc;
+  if ((rc = ensure_pinned(ctx, total)) != VTMME_OK) return rc;
+  if ((rc = ensure(ctx, ctx->dJobBuf, ctx->jobBufCap, total)) != VTMME_OK) return rc;
+  int16_t* hr = reinterpret_cast<int16_t*>(ctx->hPinned);
+  int32_t* h0 = reinterpret_cast<int32_t*>(ctx->hPinned + rBytes);
+  int32_t* h1 = reinterpret_cast<int32_t*>(ctx->hPinned + rBytes + dBytes);
+  for (int y = 0; y < h; y++)
+  {
+    memcpy(hr + (size_t) y * w, residue + (ptrdiff_t) y * residueStride, (size_t) w * 2);
+    memcpy(h0 + (size_t) y * w, d0 + (ptrdiff_t) y * derivStride, (size_t) w * 4);
+    memcpy(h1 + (size_t) y * w, d1 + (ptrdiff_t) y * derivStride, (size_t) w * 4);
+  }
+  memcpy(ctx->hPinned + rBytes + 2 * dBytes, coeff, cBytes);   // the entries accumulate (the reference's caller zeroes them)
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dJobBuf, ctx->hPinned, rBytes + 2 * dBytes + cBytes, cudaMemcpyHostToDevice, ctx->stream));
+  long long* dC = reinterpret_cast<long long*>(ctx->dJobBuf + rBytes + 2 * dBytes);
+  VTMME_CUDA_CHECK(ctx, launch_affine_equal_coeff(reinterpret_cast<const int16_t*>(ctx->dJobBuf), w, reinterpret_cast<const int*>(ctx->dJobBuf + rBytes),
+                                                  reinterpret_cast<const int*>(ctx->dJobBuf + rBytes + dBytes), w, w, h, sixParam, dC, ctx->stream));
+  ctx->launches += 1;
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->hPinned + rBytes + 2 * dBytes, dC, cBytes, cudaMemcpyDeviceToHost, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(coeff, ctx->hPinned + rBytes + 2 * dBytes, cBytes);
+  return VTMME_OK;
+}
+
+extern "C" int vtmme_affine_gradient_step(vtmme_ctx* ctx, int n, const vtmme_affine_block* blocks, int64_t* coeff)
+{
+  static const char* who = "vtmme_affine_gradient_step";
+  if (!ctx) return VTMME_ERR_ARG;
+  if (!blocks || !coeff || n <= 0 || n > 65536) return vtmme_set_error(ctx, VTMME_ERR_ARG, who, "bad argument");
+  VTMME_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  size_t sampleBytes = 0;
+  for (int i = 0; i < n; i++)
+  {
+    const vtmme_affine_block& b = blocks[i];
+    if (!b.org || !b.pred || !affine_dims_ok(b.w, b.h) || b.orgStride < b.w || b.predStride < b.w)
+      return vtmme_set_error(ctx, VTMME_ERR_ARG, who, "bad block (4 <= w, h <= 128)");
+    sampleBytes += 2 * align256((size_t) b.w * b.h * 2);
+  }
+  const size_t descBytes = align256((size_t) n * sizeof(DevAffineBlock)), outBytes = align256((size_t) n * 49 * 8);
+  const size_t total = descBytes + sampleBytes + outBytes;
+  int rc;
+  if ((rc = ensure_pinned(ctx, total)) != VTMME_OK) return rc;
+  if ((rc = ensure(ctx, ctx->dJobBuf, ctx->jobBufCap, total)) != VTMME_OK) return rc;
+  DevAffineBlock* hd = reinterpret_cast<DevAffineBlock*>(ctx->hPinned);
+  size_t off = descBytes;
+  for (int i = 0; i < n; i++)
+  {
+    const vtmme_affine_block& b = blocks[i];
+    const size_t blk = align256((size_t) b.w * b.h * 2);
+    int16_t* ho = reinterpret_cast<int16_t*>(ctx->hPinned + off);
+    int16_t* hp = reinterpret_cast<int16_t*>(ctx->hPinned + off + blk);
+    for (int y = 0; y < b.h; y++)
+    {
+      memcpy(ho + (size_t) y * b.w, b.org + (ptrdiff_t) y * b.orgStride, (size_t) b.w * 2);
+      memcpy(hp + (size_t) y * b.w, b.pred + (ptrdiff_t) y * b.predStride, (size_t) b.w * 2);
+    }
+    hd[i].org  = reinterpret_cast<const int16_t*>(ctx->dJobBuf + off);
+    hd[i].pred = reinterpret_cast<const int16_t*>(ctx->dJobBuf + off + blk);
+    hd[i].orgStride = hd[i].predStride = b.w;
+    hd[i].w = b.w;
+    hd[i].h = b.h;
+    hd[i].sixParam = b.sixParam != 0;
+    hd[i].pad = 0;
+    off += 2 * blk;
+  }
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dJobBuf, ctx->hPinned, off, cudaMemcpyHostToDevice, ctx->stream));
+  long long* dC = reinterpret_cast<long long*>(ctx->dJobBuf + off);
+  VTMME_CUDA_CHECK(ctx, launch_affine_step(reinterpret_cast<const DevAffineBlock*>(ctx->dJobBuf), n, dC, ctx->stream));
+  ctx->launches += 1;
+  VTMME_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->hPinned + off, dC, (size_t) n * 49 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  VTMME_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(coeff, ctx->hPinned + off, (size_t) n * 49 * 8);
+  return VTMME_OK;
+}
+
 // ---- symmetric-MVD search ------------------------------------------------------------------------------------------
 static_assert(sizeof(vtmme_smvd_result) == sizeof(DevSmvdResult), "result layout");
 extern "C" int vtmme_smvd_search(vtmme_ctx* ctx, int n, const vtmme_smvd* jobs, vtmme_smvd_result* results)

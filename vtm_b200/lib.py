@@ -17,6 +17,12 @@ class CSmvd(C.Structure):
                 ("bcwIdx", C.c_int32), ("lambdaMotion", C.c_double), ("cost", C.c_uint64)]
 
 
+class CAffineBlock(C.Structure):
+    """vtmme_affine_block"""
+    _fields_ = [("org", C.c_void_p), ("orgStride", C.c_int32), ("pred", C.c_void_p), ("predStride", C.c_int32), ("w", C.c_int32),
+                ("h", C.c_int32), ("sixParam", C.c_int32), ("reserved", C.c_int32)]
+
+
 class CSmvdResult(C.Structure):
     """vtmme_smvd_result"""
     _fields_ = [("curMvX", C.c_int32), ("curMvY", C.c_int32), ("tarMvX", C.c_int32), ("tarMvY", C.c_int32), ("cost", C.c_uint64)]
@@ -34,7 +40,7 @@ SYMBOLS = ["vtmme_create", "vtmme_destroy", "vtmme_last_error", "vtmme_set_strea
            "vtmme_launch_count", "vtmme_set_profiling", "vtmme_frame_kernel_ms", "vtmme_upload_picture", "vtmme_upload_picture_async", "vtmme_upload_picture_device", "vtmme_release_picture",
            "vtmme_search", "vtmme_frame_cu_count", "vtmme_search_frames", "vtmme_search_frames_device",
            "vtmme_dist_batch", "vtmme_dist_host", "vtmme_interp_batch", "vtmme_interp_host", "vtmme_filter_host",
-           "vtmme_mc_batch", "vtmme_mc_host", "vtmme_add_avg", "vtmme_remove_high_freq", "vtmme_add_weighted_avg", "vtmme_remove_weight_high_freq", "vtmme_cand_sad", "vtmme_dmvr_refine", "vtmme_dmvr_final_mc", "vtmme_smvd_search", "vtmme_mctf_me", "vtmme_mctf_apply_motion", "vtmme_mctf_bilateral", "vtmme_int_peak"]
+           "vtmme_mc_batch", "vtmme_mc_host", "vtmme_add_avg", "vtmme_remove_high_freq", "vtmme_add_weighted_avg", "vtmme_remove_weight_high_freq", "vtmme_cand_sad", "vtmme_dmvr_refine", "vtmme_dmvr_final_mc", "vtmme_smvd_search", "vtmme_affine_sobel_host", "vtmme_affine_equal_coeff_host", "vtmme_affine_gradient_step", "vtmme_mctf_me", "vtmme_mctf_apply_motion", "vtmme_mctf_bilateral", "vtmme_int_peak"]
 
 
 class CAmvr(C.Structure):
@@ -168,6 +174,9 @@ def load_library():
     L.vtmme_dmvr_refine.argtypes = [P, I, I, I, I, I, C.POINTER(CDmvrBlock), C.POINTER(CDmvrResult)]
     L.vtmme_dmvr_final_mc.argtypes = [P, I, I, I, I, I, C.POINTER(CDmvrBlock), P]
     L.vtmme_smvd_search.argtypes = [P, I, C.POINTER(CSmvd), C.POINTER(CSmvdResult)]
+    L.vtmme_affine_sobel_host.argtypes = [P, I, P, I, I, I, P, I]
+    L.vtmme_affine_equal_coeff_host.argtypes = [P, P, I, P, P, I, I, I, I, P]
+    L.vtmme_affine_gradient_step.argtypes = [P, I, C.POINTER(CAffineBlock), P]
     L.vtmme_mctf_me.argtypes = [P, I, C.POINTER(C.c_int32), C.POINTER(C.c_int32), I, P]
     L.vtmme_mctf_apply_motion.argtypes = [P, I, I, I, P, I, I, I, P]
     L.vtmme_mctf_bilateral.argtypes = [P, I, I, C.POINTER(C.c_int32), P, I, P]

@@ -9,7 +9,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .lib import (CAmvr, CCandJob, CDmvrBlock, CDmvrResult, CSmvd, CSmvdResult, CTz, CFrameParams, CJob, CMcBlock, CResult, ERR_NAMES, VtmmeError,
+from .lib import (CAffineBlock, CAmvr, CCandJob, CDmvrBlock, CDmvrResult, CSmvd, CSmvdResult, CTz, CFrameParams, CJob, CMcBlock, CResult, ERR_NAMES, VtmmeError,
                   load_library)
 
 # vtmme_cu_result
@@ -400,6 +400,37 @@ class MotionSearch:
         self._check(self.L.vtmme_dmvr_final_mc(self.ctx, comp, ref_pic, bit_depth, max_cu, len(blk),
                                                C.cast(blk.ctypes.data, C.POINTER(CDmvrBlock)), C.c_void_p(out.ctypes.data)),
                     "vtmme_dmvr_final_mc")
+        return out
+
+    # ---- affine ME primitives ----------------------------------------------------------------------------
+    def affine_sobel(self, vertical, pred):
+        """AffineGradientSearch's Sobel entries on one prediction block (int16 2-D, views ok) -> int32 [h, w]."""
+        assert pred.dtype == np.int16
+        h, w = pred.shape
+        out = np.zeros((h, w), np.int32)
+        self._check(self.L.vtmme_affine_sobel_host(self.ctx, vertical, C.c_void_p(pred.ctypes.data), pred.strides[0] // 2, w, h,
+                                                   C.c_void_p(out.ctypes.data), w), "vtmme_affine_sobel_host")
+        return out
+
+    def affine_equal_coeff(self, residue, d0, d1, six, coeff=None):
+        """xEqualCoeffComputer: residue int16 [h, w], derivatives int32 [h, w]; accumulates into coeff (int64 [7, 7])."""
+        h, w = residue.shape
+        if coeff is None:
+            coeff = np.zeros((7, 7), np.int64)
+        self._check(self.L.vtmme_affine_equal_coeff_host(self.ctx, C.c_void_p(residue.ctypes.data), residue.strides[0] // 2,
+                                                         C.c_void_p(d0.ctypes.data), C.c_void_p(d1.ctypes.data), d0.strides[0] // 4, w, h,
+                                                         int(six), C.c_void_p(coeff.ctypes.data)), "vtmme_affine_equal_coeff_host")
+        return coeff
+
+    def affine_gradient_step(self, blocks):
+        """blocks: list of (org, pred, sixParam) with int16 2-D arrays of equal shape.  Returns int64 [n, 7, 7]."""
+        n = len(blocks)
+        arr = (CAffineBlock * n)()
+        for i, (o, p, six) in enumerate(blocks):
+            assert o.dtype == np.int16 and p.dtype == np.int16 and o.shape == p.shape
+            arr[i] = CAffineBlock(o.ctypes.data, o.strides[0] // 2, p.ctypes.data, p.strides[0] // 2, o.shape[1], o.shape[0], int(six), 0)
+        out = np.zeros((n, 7, 7), np.int64)
+        self._check(self.L.vtmme_affine_gradient_step(self.ctx, n, arr, C.c_void_p(out.ctypes.data)), "vtmme_affine_gradient_step")
         return out
 
     # ---- symmetric-MVD search -----------------------------------------------------------------------------
