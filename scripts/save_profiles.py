@@ -42,3 +42,16 @@ title = "%s — ncu --set full of the dominant kernel me_tree_sad_kernel<NFP=2,F
 subprocess.check_call([sys.executable, "scripts/ncu_summary.py", "gpurun_out/prof_tree_%s.ncu-rep" % tag,
                        "profiles/%s_tree_sad_ncu.md" % pre, title], stdout=subprocess.DEVNULL)
 print(open("profiles/%s_launches_summary.md" % pre).read()[:900])
+
+# DRAM traffic of the dominant kernel for bench.py's roofline.traffic (read from this file, not pasted into the bench)
+import csv as _csv, io as _io, json as _json
+raw = subprocess.run(["ncu", "-i", "gpurun_out/prof_tree_%s.ncu-rep" % tag, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rr = list(_csv.reader(_io.StringIO(raw)))
+col = {h: i for i, h in enumerate(rr[0])}
+def _bytes(name):
+    v, u = float(rr[2][col[name]].replace(",", "")), rr[1][col[name]]
+    return int(v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u])
+_json.dump({"kernel": "me_tree_sad_kernel", "source": "profiles/%s_tree_sad_ncu.md (ncu --set full, one launch of 4 pairs of 1080p, SR=64)" % pre,
+            "pairs_per_launch": 4, "dram_bytes_read": _bytes("dram__bytes_read.sum"), "dram_bytes_write": _bytes("dram__bytes_write.sum")},
+           open("profiles/ncu_traffic.json", "w"), indent=2)
+print(open("profiles/ncu_traffic.json").read())
