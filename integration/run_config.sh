@@ -29,7 +29,7 @@ case $CFGN in
   13) WD=64; HT=64; FR=${3:-2}; BITS=8; CFG=encoder_lowdelay_P_vtm.cfg; SR=64; EXTRA="-q 32";;   # tiny clip for the table hooks
   *) echo "unknown configuration $CFGN"; exit 2;;
 esac
-W=$ROOT/gpurun_out/enc_c${CFGN}_${FR}f_$MODE; mkdir -p $W; cd $W
+W=$ROOT/gpurun_out/enc_c${CFGN}_${FR}f_$MODE${WD_SUFFIX:-}; mkdir -p $W; cd $W
 python $ROOT/integration/make_yuv.py in.yuv --width $WD --height $HT --frames $FR --bits $BITS
 echo "input md5: $(md5sum in.yuv | cut -d' ' -f1)"
 ARGS="-c $ROOT/oracle/_ref/cfg/$CFG -i in.yuv -wdt $WD -hgt $HT -fr 30 -f $FR $EXTRA --InputBitDepth=$BITS --FastSearch=$FS --SearchRange=$SR --SEIDecodedPictureHash=1"

@@ -16,7 +16,34 @@ constexpr int kUnroll = 16;   // independent accumulators per thread
 
 // Variant ids (keep in sync with vtm_b200/peaks.py)
 enum { V_VABSDIFF = 0, V_IADD3, V_IMAD, V_LOP3, V_PRMT, V_VABSDIFF_IMAD, V_FADD_ABS, V_VABSDIFF_FADD, V_VIADD16X2,
-       V_VIADDMNMX16X2, V_VABSDIFF4, V_VABSDIFF_FADD2, V_DP2A, V_DP4A, V_COUNT };
+       V_VIADDMNMX16X2, V_VABSDIFF4, V_VABSDIFF_FADD2, V_DP2A, V_DP4A, V_FADD2P, V_VABSDIFF_FADD2P_88, V_VABSDIFF_FADD2P_610,
+       V_VABSDIFF_FADD2P_106, V_VABSDIFF_FADD2P_124, V_MIX_FADD_124, V_MIX_FADD_106, V_MIX_FADD_88, V_COUNT };
+
+// Packed FP32 (sm_100 add.f32x2 / sub.f32x2 -> FADD2): two |a-b| per instruction pair.  ptxas folds the broadcast of the
+// scalar minuend, the negation and the magnitude into operand modifiers (FADD2 R, Ra.F32, -Rb.F32x2 ; FADD2 R, Racc, |Rd|).
+__device__ __forceinline__ unsigned long long f2_pack(float a, float b)
+{
+  unsigned long long r;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_absdiff_acc(unsigned long long acc, float o, unsigned long long p2)
+{
+  unsigned long long d;
+  const unsigned long long oo = f2_pack(o, o);
+  asm("sub.f32x2 %0, %1, %2;" : "=l"(d) : "l"(oo), "l"(p2));
+  float d0, d1;
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+  const unsigned long long ad = f2_pack(fabsf(d0), fabsf(d1));
+  asm("add.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(ad));
+  return acc;
+}
+__device__ __forceinline__ float f2_lo(unsigned long long v)
+{
+  float a, b;
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+  return a;
+}
 
 template <int V>
 __global__ void __launch_bounds__(256) peak_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int iters,
@@ -33,10 +60,27 @@ __global__ void __launch_bounds__(256) peak_kernel(const uint32_t* __restrict__ 
   float facc[kUnroll];
 #pragma unroll
   for (int i = 0; i < kUnroll; i++) facc[i] = __uint_as_float(acc[i] >> 3);
+  // packed state: slot pair j = slots 2j, 2j+1
+  unsigned long long pacc[kUnroll / 2], pb[kUnroll / 2];
+#pragma unroll
+  for (int j = 0; j < kUnroll / 2; j++)
+  {
+    pacc[j] = f2_pack(facc[2 * j], facc[2 * j + 1]);
+    pb[j]   = f2_pack(__uint_as_float(b[2 * j]), __uint_as_float(b[2 * j + 1]));
+  }
+  // number of leading slots on the ALU pipe in the packed mixes (the rest are FADD2 pairs)
+  // (the older mixed variants V_VABSDIFF_FADD / V_VABSDIFF_FADD2 take their FP minuend from an ALU slot, which makes the
+  // difference loop-invariant: ptxas hoists it and they run ONE FADD per pixel - kept for continuity, not used for peaks)
+  constexpr int kAluSlots = (V == V_VABSDIFF_FADD2P_88 || V == V_MIX_FADD_88) ? 8 : V == V_VABSDIFF_FADD2P_610 ? 6
+                          : (V == V_VABSDIFF_FADD2P_106 || V == V_MIX_FADD_106) ? 10
+                          : (V == V_VABSDIFF_FADD2P_124 || V == V_MIX_FADD_124) ? 12 : 0;
+  constexpr bool kPlainMix = V == V_MIX_FADD_124 || V == V_MIX_FADD_106 || V == V_MIX_FADD_88;
+  constexpr bool kPacked = V >= V_FADD2P && !kPlainMix;
 
   unsigned long long g0 = 0;
   if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
   const long long t0 = clock64();
+#pragma unroll 4
   for (int it = 0; it < iters; it++)
   {
     // operand x is another accumulator (static index), so nothing is loop-invariant and every chain stays
@@ -44,6 +88,27 @@ __global__ void __launch_bounds__(256) peak_kernel(const uint32_t* __restrict__ 
 #pragma unroll
     for (int i = 0; i < kUnroll; i++)
     {
+      if (kPlainMix)
+      {   // honest scalar mix: ALU slots take their operand from ALU slots, FP slots (2 FADD per pixel) from FP slots
+        if (i < kAluSlots) acc[i] = __usad(acc[(i + 3) % kAluSlots], b[i], acc[i]);
+        else
+        {
+          const int ix = kAluSlots + ((i - kAluSlots + 3) % (kUnroll - kAluSlots));
+          float d = __fsub_rn(facc[ix], __uint_as_float(b[i]));
+          facc[i] = __fadd_rn(facc[i], fabsf(d));
+        }
+        continue;
+      }
+      if (kPacked)
+      {
+        if (i < kAluSlots) acc[i] = __usad(acc[(i + 3) % (kAluSlots > 0 ? kAluSlots : 1)], b[i], acc[i]);
+        else if ((i & 1) == 0)
+        {
+          const int j = i / 2, jx = (kAluSlots / 2) + ((j - kAluSlots / 2 + 3) % ((kUnroll - kAluSlots) / 2));
+          pacc[j] = f2_absdiff_acc(pacc[j], f2_lo(pacc[jx]), pb[j]);
+        }
+        continue;
+      }
       const uint32_t x = acc[(i + 5) & (kUnroll - 1)];
       const float    fx = facc[(i + 5) & (kUnroll - 1)];
       if (V == V_VABSDIFF) acc[i] = __usad(x, b[i], acc[i]);
@@ -91,6 +156,8 @@ __global__ void __launch_bounds__(256) peak_kernel(const uint32_t* __restrict__ 
   uint32_t        r  = 0;
 #pragma unroll
   for (int i = 0; i < kUnroll; i++) r += acc[i] + __float_as_uint(facc[i]);
+#pragma unroll
+  for (int j = 0; j < kUnroll / 2; j++) r += (uint32_t) pacc[j] + (uint32_t) (pacc[j] >> 32);
   out[blockIdx.x * blockDim.x + threadIdx.x] = r;
   if (threadIdx.x == 0)
   {
@@ -110,6 +177,9 @@ __host__ double instr_per_slot(int v)
     case V_VABSDIFF_FADD: return (2 * 1.0 + 1 * 2.0) / 4.0;   // slots 0,1 usad; slot 2 idle; slot 3 = 2 FADD
     case V_VIADD16X2: return 2.0;   // VIADD.16x2 + LOP3
     case V_VABSDIFF_FADD2: return 1.5;
+    case V_MIX_FADD_124: return (12 + 2 * 4) / 16.0;
+    case V_MIX_FADD_106: return (10 + 2 * 6) / 16.0;
+    case V_MIX_FADD_88: return (8 + 2 * 8) / 16.0;
     case V_VABSDIFF4: return 1.0;   // ptxas folds the add into VABSDIFF4.U8.ACC
     default: return 1.0;
   }
@@ -178,6 +248,8 @@ extern "C" int vtmme_int_peak(int variant, int iters, double* laneInstrPerClkPer
 #define CASE(V) case V: rc = run_variant<V>(iters, sms, din, dout, dclk, laneInstrPerClkPerSm, ms, smClockMHz, st); break;
     CASE(V_VABSDIFF) CASE(V_IADD3) CASE(V_IMAD) CASE(V_LOP3) CASE(V_PRMT) CASE(V_VABSDIFF_IMAD) CASE(V_FADD_ABS)
     CASE(V_VABSDIFF_FADD) CASE(V_VIADD16X2) CASE(V_VIADDMNMX16X2) CASE(V_VABSDIFF4) CASE(V_VABSDIFF_FADD2) CASE(V_DP2A) CASE(V_DP4A)
+    CASE(V_FADD2P) CASE(V_VABSDIFF_FADD2P_88) CASE(V_VABSDIFF_FADD2P_610) CASE(V_VABSDIFF_FADD2P_106)
+    CASE(V_VABSDIFF_FADD2P_124) CASE(V_MIX_FADD_124) CASE(V_MIX_FADD_106) CASE(V_MIX_FADD_88)
 #undef CASE
     default: rc = -2;
   }

@@ -101,22 +101,76 @@ __device__ __forceinline__ void check8(const uint32_t (&a)[8], uint32_t lb, cons
 // use VABSDIFF.U32 on the ALU pipe; the last NFP use two FADDs on the FP32 pipe: the 10-bit samples and the
 // partial sums are treated as denormal floats (bit pattern == integer below 2^24), for which FADD is exact
 // fixed-point arithmetic, so both halves produce the same integers.
+// Packed FP32 lanes (sm_100 sub.f32x2 / add.f32x2 -> FADD2): NFP codes 12 / 13 / 14 put the displacement lanes {4,6} / {2,4,6} /
+// {0,2,4,6} on FADD2, two PIXELS of one displacement per instruction: {o[i], o[i+1]} - {px[i+k], px[i+k+1]} (aligned register
+// pairs because i and k are even), then acc2 += |d2| (negation and magnitude are operand modifiers).  The two halves of a
+// packed accumulator are the partial sums over the even and the odd pixels; the caller adds them when the block is done.
+template <int NFP>
+__host__ __device__ constexpr int fp2_mask()
+{
+  return NFP == 12 ? 0x50 : NFP == 13 ? 0x54 : NFP == 14 ? 0x55 : 0;
+}
+__device__ __forceinline__ unsigned long long f2_pack(uint32_t lo, uint32_t hi)
+{
+  unsigned long long r;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_absdiff_acc(unsigned long long acc, unsigned long long o2, unsigned long long p2)
+{
+  unsigned long long d;
+  asm("sub.f32x2 %0, %1, %2;" : "=l"(d) : "l"(o2), "l"(p2));
+  float d0, d1;
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+  unsigned long long ad;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(ad) : "f"(fabsf(d0)), "f"(fabsf(d1)));
+  asm("add.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(ad));
+  return acc;
+}
+
+template <int NFP>
+__device__ __forceinline__ void sad_row(uint32_t (&a)[8], uint32_t (&ah)[8], const uint32_t (&o)[8], const uint32_t (&px)[16])
+{
+  constexpr int M2 = fp2_mask<NFP>();
+  constexpr int NF = NFP >= 10 ? 0 : NFP;
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+  {
+    if ((M2 >> k) & 1)
+    {
+      unsigned long long acc = f2_pack(a[k], ah[k]);
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) acc = f2_absdiff_acc(acc, f2_pack(o[i], o[i + 1]), f2_pack(px[i + k], px[i + k + 1]));
+      asm("mov.b64 {%0,%1}, %2;" : "=r"(a[k]), "=r"(ah[k]) : "l"(acc));
+    }
+    else if (k >= 8 - NF)
+    {
+      float acc = __uint_as_float(a[k]);
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+        acc = __fadd_rn(acc, fabsf(__fsub_rn(__uint_as_float(o[i]), __uint_as_float(px[i + k]))));
+      a[k] = __float_as_uint(acc);
+    }
+    else
+    {
+#pragma unroll
+      for (int i = 0; i < 8; i++) a[k] = __usad(o[i], px[i + k], a[k]);
+    }
+  }
+}
 template <int NFP>
 __device__ __forceinline__ void sad_row(uint32_t (&a)[8], const uint32_t (&o)[8], const uint32_t (&px)[16])
 {
+  uint32_t unused[8];   // (paths without the second accumulator half run the packed codes as NFP = 2)
+  sad_row<(NFP >= 10 ? 2 : NFP)>(a, unused, o, px);
+}
+// folds the halves of the packed lanes (exact: integers below 2^24 as denormal / small floats)
+template <int NFP>
+__device__ __forceinline__ void sad_fold(uint32_t (&a)[8], const uint32_t (&ah)[8])
+{
 #pragma unroll
-  for (int k = 0; k < 8 - NFP; k++)
-#pragma unroll
-    for (int i = 0; i < 8; i++) a[k] = __usad(o[i], px[i + k], a[k]);
-#pragma unroll
-  for (int k = 8 - NFP; k < 8; k++)
-  {
-    float acc = __uint_as_float(a[k]);
-#pragma unroll
-    for (int i = 0; i < 8; i++)
-      acc = __fadd_rn(acc, fabsf(__fsub_rn(__uint_as_float(o[i]), __uint_as_float(px[i + k]))));
-    a[k] = __float_as_uint(acc);
-  }
+  for (int k = 0; k < 8; k++)
+    if ((fp2_mask<NFP>() >> k) & 1) a[k] = __float_as_uint(__fadd_rn(__uint_as_float(a[k]), __uint_as_float(ah[k])));
 }
 
 // The staged reference window holds two samples per 32-bit word in 12-bit fields (lo | hi << 12), so that a word
@@ -452,16 +506,23 @@ __global__ void __launch_bounds__(kTreeMaxThreads, (DY == 2 || SS) ? 2 : kTreeMi
             {
               const uint32_t* op = orgRow;
               const uint16_t* rp = refRow;
+              uint32_t        a8h[NACC][8];
+#pragma unroll
+              for (int d = 0; d < NACC; d++)
+#pragma unroll
+                for (int k = 0; k < 8; k++) a8h[d][k] = 0;
 #pragma unroll kRowUnroll
               for (int r = 0; r < 8; r++)
               {
                 uint32_t o[8], px[16];
                 load_org8(op, o);
                 load_ref16<FPU, W32>(rp, px, refStride);
-                sad_row<NFP>(a8[SS ? (r & 1) : 0], o, px);
+                sad_row<NFP>(a8[SS ? (r & 1) : 0], a8h[SS ? (r & 1) : 0], o, px);
                 op += 32;
                 rp += rs;
               }
+#pragma unroll
+              for (int d = 0; d < NACC; d++) sad_fold<NFP>(a8[d], a8h[d]);
             }
             else
             {
@@ -852,6 +913,9 @@ cudaError_t launch_tree_sad(const TreeParams& p, int nPairs, cudaStream_t st)
     if (nfp == 1) return launch_tree_sad_t<1, true, 1, false, true>(p, nPairs, threads, smem, st);
     if (nfp == 2) return launch_tree_sad_t<2, true, 1, false, true>(p, nPairs, threads, smem, st);
     if (nfp == 3) return launch_tree_sad_t<3, true, 1, false, true>(p, nPairs, threads, smem, st);
+    if (nfp == 12) return launch_tree_sad_t<12, true, 1, false, true>(p, nPairs, threads, smem, st);
+    if (nfp == 13) return launch_tree_sad_t<13, true, 1, false, true>(p, nPairs, threads, smem, st);
+    if (nfp == 14) return launch_tree_sad_t<14, true, 1, false, true>(p, nPairs, threads, smem, st);
     return cudaErrorInvalidValue;
   }
 #define VTMME_TREE_CASE(N, F, D) \
@@ -880,16 +944,20 @@ cudaError_t launch_tree_upper(const TreeParams& p, int nPairs, cudaStream_t st)
 // ---- development microbenchmark: the 8x8-block SAD inner loop alone (no staging, no argmin, no tails) ----------
 namespace vtmme {
 namespace {
-template <int NFP, bool FPU, int DY>
+template <int NFP, bool FPU, int DY, bool W32 = false>
 __global__ void __launch_bounds__(kTreeMaxThreads, DY == 2 ? 2 : 3) sad_block_bench_kernel(uint32_t* out, int iters)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   uint32_t* s_org = reinterpret_cast<uint32_t*>(smem);
   uint16_t* s_ref = reinterpret_cast<uint16_t*>(smem + 4096);
   constexpr int refStride = 17 * 8 + 32;
+  constexpr int rs        = W32 ? 2 * refStride : refStride;
   for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_org[i] = (i * 2654435761u) >> 22;
-  for (int i = threadIdx.x; i < 48 * refStride / 2; i += blockDim.x)
-    reinterpret_cast<uint32_t*>(s_ref)[i] = pack12((((i * 40503u) >> 6) & 0x3ffu) | ((((i * 9973u) >> 5) & 0x3ffu) << 16));
+  if (W32)
+    for (int i = threadIdx.x; i < 48 * refStride; i += blockDim.x) reinterpret_cast<uint32_t*>(s_ref)[i] = ((i * 40503u) >> 6) & 0x3ffu;
+  else
+    for (int i = threadIdx.x; i < 48 * refStride / 2; i += blockDim.x)
+      reinterpret_cast<uint32_t*>(s_ref)[i] = pack12((((i * 40503u) >> 6) & 0x3ffu) | ((((i * 9973u) >> 5) & 0x3ffu) << 16));
   __syncthreads();
   uint32_t acc[DY][8];
 #pragma unroll
@@ -897,14 +965,14 @@ __global__ void __launch_bounds__(kTreeMaxThreads, DY == 2 ? 2 : 3) sad_block_be
 #pragma unroll
     for (int k = 0; k < 8; k++) acc[d][k] = 0;
   const int gx = threadIdx.x % 17, tr = (threadIdx.x / 17) % 6;
-  const uint16_t* refTile = s_ref + tr * DY * refStride + gx * 8;
+  const uint16_t* refTile = s_ref + tr * DY * rs + gx * 8;
   for (int it = 0; it < iters; it++)
   {
     for (int blk = 0; blk < 16; blk++)
     {
       const int bx = (blk & 3) * 8, by = (blk >> 2) * 8;
       const uint32_t* orgRow = s_org + by * 32 + bx;
-      const uint16_t* refRow = refTile + by * refStride + bx;
+      const uint16_t* refRow = refTile + by * rs + bx;
       uint32_t a8[DY][8];
 #pragma unroll
       for (int d = 0; d < DY; d++)
@@ -912,14 +980,18 @@ __global__ void __launch_bounds__(kTreeMaxThreads, DY == 2 ? 2 : 3) sad_block_be
         for (int k = 0; k < 8; k++) a8[d][k] = 0;
       if (DY == 1)
       {
-#pragma unroll 2
+        uint32_t a8h[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) a8h[k] = 0;
+#pragma unroll kRowUnroll
         for (int r = 0; r < 8; r++)
         {
           uint32_t o[8], px[16];
           load_org8(orgRow + r * 32, o);
-          load_ref16<FPU>(refRow + r * refStride, px);
-          sad_row<NFP>(a8[0], o, px);
+          load_ref16<FPU, W32>(refRow + r * rs, px, refStride);
+          sad_row<NFP>(a8[0], a8h, o, px);
         }
+        sad_fold<NFP>(a8[0], a8h);
       }
       else
       {
@@ -954,17 +1026,17 @@ __global__ void __launch_bounds__(kTreeMaxThreads, DY == 2 ? 2 : 3) sad_block_be
   out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
-template <int NFP, bool FPU, int DY>
+template <int NFP, bool FPU, int DY, bool W32 = false>
 double run_sad_block_bench(int threads, int ctasPerSm, int iters, int sms, uint32_t* dout, cudaStream_t st)
 {
-  const size_t smem = 4096 + 48 * (17 * 8 + 32) * 2;
-  cudaFuncSetAttribute(sad_block_bench_kernel<NFP, FPU, DY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  const size_t smem = 4096 + 48 * (17 * 8 + 32) * (W32 ? 4 : 2);
+  cudaFuncSetAttribute(sad_block_bench_kernel<NFP, FPU, DY, W32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  sad_block_bench_kernel<NFP, FPU, DY><<<sms * ctasPerSm, threads, smem, st>>>(dout, 2);
+  sad_block_bench_kernel<NFP, FPU, DY, W32><<<sms * ctasPerSm, threads, smem, st>>>(dout, 2);
   cudaEventRecord(e0, st);
-  sad_block_bench_kernel<NFP, FPU, DY><<<sms * ctasPerSm, threads, smem, st>>>(dout, iters);
+  sad_block_bench_kernel<NFP, FPU, DY, W32><<<sms * ctasPerSm, threads, smem, st>>>(dout, iters);
   cudaEventRecord(e1, st);
   cudaStreamSynchronize(st);
   float ms = 0;
@@ -992,6 +1064,10 @@ double sad_block_bench(int nfp, int fpu, int dy, int threads, int ctasPerSm, int
   VTMME_BB_CASE(0, 0, 2) VTMME_BB_CASE(0, 1, 2) VTMME_BB_CASE(1, 1, 2) VTMME_BB_CASE(2, 1, 2) VTMME_BB_CASE(3, 1, 2)
   VTMME_BB_CASE(2, 0, 2) VTMME_BB_CASE(2, 0, 1)
 #undef VTMME_BB_CASE
+  // fpu == 2: the one-sample-per-word window of the product path (incl. the packed FADD2 lane codes 12-14)
+#define VTMME_BB_W32(N) if (nfp == N && fpu == 2 && dy == 1) r = run_sad_block_bench<N, true, 1, true>(threads, ctasPerSm, iters, sms, dout, st);
+  VTMME_BB_W32(0) VTMME_BB_W32(1) VTMME_BB_W32(2) VTMME_BB_W32(3) VTMME_BB_W32(12) VTMME_BB_W32(13) VTMME_BB_W32(14)
+#undef VTMME_BB_W32
   cudaStreamDestroy(st);
   cudaFree(dout);
   return r;
