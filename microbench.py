@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--n", type=int, default=65536)
     ap.add_argument("--out", default=None)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time direct launches (host call overhead included)")
     a = ap.parse_args()
     R = B.ref()
     O = B.oracle()
@@ -46,13 +47,34 @@ def main():
         shapes = [(8, 8), (16, 16), (32, 8), (64, 64), (128, 128), (4, 4)]
 
     def gpu_time(fn, reps=5):
+        """Kernel time per call: the calls are captured into a CUDA graph (a ctypes call costs ~10 us of host time, more than a
+        small batch takes on the device) and the graph is replayed between two events; direct launches if capture fails."""
         fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(reps):
-            fn()
-        e1.record(stream)
+        graph = None
+        if not a.no_graph:
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=stream):
+                    for _ in range(reps):
+                        fn()
+                graph = g
+            except Exception as exc:      # noqa: BLE001 - fall back to plain launches
+                print("graph capture failed (%s): timing direct launches" % exc, file=sys.stderr)
+                torch.cuda.synchronize()
+        torch.cuda.set_stream(stream)
+        if graph is not None:
+            graph.replay()
+            torch.cuda.synchronize()
+            e0.record(stream)
+            graph.replay()
+            e1.record(stream)
+        else:
+            e0.record(stream)
+            for _ in range(reps):
+                fn()
+            e1.record(stream)
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) * 1e-3 / reps
 
@@ -132,8 +154,10 @@ def main():
     if a.out:
         with open(a.out, "w") as f:
             f.write("# Distortion / interpolation micro-benchmark (BASELINE config 5)\n\n")
-            f.write("GPU: libvtmme table-level batch kernels, blocks resident in HBM, CUDA-event timed.  CPU: the reference's own "
-                    "dispatch-table entries (AVX2) on ONE host core.  Every output compared for exact equality.\n\n")
+            f.write("GPU: libvtmme table-level batch kernels, blocks resident in HBM, CUDA-event timed%s.  CPU: the reference's own "
+                    "dispatch-table entries (AVX2) on ONE host core.  Every output compared for exact equality.\n\n"
+                    % ("" if a.no_graph else " (the calls of a timing loop are captured into a CUDA graph and replayed, so the ~10 us of host "
+                       "time per ctypes call does not hide the kernels of small batches)"))
             f.write("Roofline: these kernels are HBM-bound by design (a few integer ops per byte).  `GB/s` = algorithmic bytes (operand "
                     "blocks in — sampled rows only for SAD, with the tap halo for filters — plus results out) / kernel time; `frac` = "
                     "that over the measured HBM peak of %.0f GB/s (%s).  Batches whose operands fit the 126 MB L2 are marked `L2`: "

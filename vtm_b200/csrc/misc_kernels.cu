@@ -1,4 +1,7 @@
 // Table-level kernels (the dispatch-table flavour of the reference's SIMD entries) and picture border extension.
+#include <cstdlib>
+#include <type_traits>
+
 #include "me_kernels.h"
 
 namespace vtmme {
@@ -183,6 +186,105 @@ __global__ void __launch_bounds__(256) satd_batch_kernel(const int16_t* __restri
   if (lane == 0) out[warp] = s;
 }
 
+// ---- SATD, one THREAD per 8x8 sub-tile (blocks with min(w, h) >= 8, power-of-two sizes, 16-byte aligned rows) ----
+// MODE 0: the 8x8 tiling (w == h).  MODE 1 / 2: the 16x8 / 8x16 tilings — the first butterfly stage across the two 8x8 halves
+// of a tile is done on the raw differences (Hadamard stages commute): the thread of half 0 transforms L + R (T + B), the
+// thread of half 1 transforms L - R (T - B), each from both halves' samples; the DC term (>> 2) is coefficient (0,0) of half 0
+// and the tile value (int)(sum / sqrt(128) * 2) is formed from the two threads' sums (RdCost.cpp:2369-2560).  The 2-D
+// transform of a sub-tile is 6 x 64 register butterflies, all integer, exact for any 16-bit input.
+// sign-extended low / high 16-bit half of a word: PRMT with the sign-replicate bit of the selector (which __byte_perm masks off)
+__device__ __forceinline__ int sext_lo(uint32_t w)
+{
+  int r;
+  asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(r) : "r"(w));
+  return r;
+}
+__device__ __forceinline__ int sext_hi(uint32_t w)
+{
+  int r;
+  asm("prmt.b32 %0, %1, 0, 0xbb32;" : "=r"(r) : "r"(w));
+  return r;
+}
+__device__ __forceinline__ void load_diff8x8(const int16_t* __restrict__ o, int os, const int16_t* __restrict__ c, int cs, int (&d)[64])
+{
+#pragma unroll
+  for (int r = 0; r < 8; r++)
+  {
+    const uint4    a = *reinterpret_cast<const uint4*>(o + (size_t) r * os), b = *reinterpret_cast<const uint4*>(c + (size_t) r * cs);
+    const uint32_t aw[4] = { a.x, a.y, a.z, a.w }, bw[4] = { b.x, b.y, b.z, b.w };
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+    {
+      d[r * 8 + 2 * k]     = sext_lo(aw[k]) - sext_lo(bw[k]);
+      d[r * 8 + 2 * k + 1] = sext_hi(aw[k]) - sext_hi(bw[k]);
+    }
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128, 3) satd_tile_thread_kernel(const int16_t* __restrict__ org, int orgStride, long long orgBlk,
+                                                               const int16_t* __restrict__ cur, int curStride, long long curBlk,
+                                                               int w, int h, int n, int log2Units, int log2Ux,
+                                                               unsigned long long* out)
+{
+  const long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x;   // global unit = (block, 8x8 sub-tile)
+  const long long blk = g >> log2Units;
+  const int       u = (int) (g & ((1 << log2Units) - 1)), ux = u & ((1 << log2Ux) - 1), uy = u >> log2Ux;
+  const bool      active = blk < n;
+  uint32_t        v = 0;
+  if (active)
+  {
+    const int16_t* o = org + blk * orgBlk + (size_t) (uy * 8) * orgStride + ux * 8;
+    const int16_t* c = cur + blk * curBlk + (size_t) (uy * 8) * curStride + ux * 8;
+    int d[64];
+    load_diff8x8(o, orgStride, c, curStride, d);
+    const int half = MODE == 1 ? (ux & 1) : MODE == 2 ? (uy & 1) : 0;
+    if (MODE != 0)
+    {
+      // partner half: 8 samples to the right / left (MODE 1), 8 rows below / above (MODE 2)
+      const ptrdiff_t po = MODE == 1 ? (half ? -8 : 8) : (ptrdiff_t) (half ? -8 : 8) * orgStride;
+      const ptrdiff_t pc = MODE == 1 ? (half ? -8 : 8) : (ptrdiff_t) (half ? -8 : 8) * curStride;
+      int e[64];
+      load_diff8x8(o + po, orgStride, c + pc, curStride, e);
+#pragma unroll
+      for (int i = 0; i < 64; i++) d[i] = half ? e[i] - d[i] : d[i] + e[i];
+    }
+#pragma unroll
+    for (int st = 0; st < 6; st++)
+#pragma unroll
+      for (int j = 0; j < 32; j++)
+      {
+        const int len = 1 << st, k = ((j >> st) << (st + 1)) | (j & (len - 1));   // j-th butterfly of the stage
+        const int a = d[k], b = d[k + len];
+        d[k]       = a + b;
+        d[k + len] = a - b;
+      }
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 1; i < 64; i++) s = __sad(d[i], 0, s);
+    const uint32_t dc = (uint32_t) abs(d[0]);
+    s += half ? dc : (dc >> 2);
+    v = s;
+  }
+  if (MODE == 0)
+    v = (v + 2) >> 2;
+  else
+  {
+    // the two halves of a tile sit in lanes that differ in one bit: bit 0 (MODE 1) or bit log2Ux (MODE 2)
+    const uint32_t t = v + __shfl_xor_sync(0xffffffffu, v, MODE == 1 ? 1 : (1 << log2Ux));
+    const int      half = MODE == 1 ? (ux & 1) : (uy & 1);
+    v = half ? 0u : (uint32_t) (int) __dmul_rn(__ddiv_rn((double) (int) t, 0x1.6a09e667f3bcdp+3), 2.0);
+  }
+  // sum over the units of a block: segments of min(units, 32) lanes; more than 32 units -> one atomic per warp
+  const int seg = log2Units < 5 ? (1 << log2Units) : 32;
+  for (int m = seg >> 1; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  if (active && (threadIdx.x & (seg - 1)) == 0)
+  {
+    if (log2Units <= 5) out[blk] = v;
+    else atomicAdd(out + blk, (unsigned long long) v);
+  }
+}
+
 // ---- interpolation: InterpolationFilter::filter<N,...> / filterCopy (InterpolationFilter.cpp:397-656) with the
 //      public dispatch of filterHor/filterVer (:749-895).  One CTA per block. ----
 struct InterpArgs
@@ -300,12 +402,379 @@ __global__ void __launch_bounds__(kInterpThreads) interp_batch_kernel(InterpArgs
   }
 }
 
+// Fast path of the same filters (4 or 8 taps, even width): TWO horizontally adjacent outputs per thread, no shared memory, no
+// barrier — the taps are read straight from global memory / L1 as 32-bit words (neighbouring threads re-read the same lines out
+// of L1), so the kernel is a pure stream with many independent loads in flight per thread.
+//   * the taps are 2-way dot products IDP.2A (two 16-bit samples x two 8-bit coefficients);
+//   * horizontal: outputs x, x+1 need the nine (five) samples s[x .. x+TAPS]: four (two) aligned words and one half-word.  If
+//     s[x] is word-aligned, output x takes the coefficient pairs (c0,c1)(c2,c3).. and output x+1 the pairs shifted by one tap
+//     (0,c0)(c1,c2)..(c7,0) over the same words; if it is not, the roles swap — no sample is ever shifted or unpacked;
+//   * vertical: the words of rows y+k and y+k+1 are interleaved into (row k, row k+1) pairs per column (PRMT), then the same dot
+//     products; a column pair at an odd sample address is assembled from two half-word loads;
+//   * the two results leave as one 32-bit store when the destination allows it.
+// Only samples of the block and its tap halo are read.  Arithmetic is InterpolationFilter::filter's (sum in 32 bits, + offset,
+// >> shift, clip if last, store as Pel).
+__device__ __forceinline__ uint32_t pack_taps(const int16_t* c, int i0)   // bytes: c[i0], c[i0+1], c[i0+2], c[i0+3] (0 outside 0..7)
+{
+  uint32_t r = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+  {
+    const int i = i0 + k;
+    const int v = (i >= 0 && i < 8) ? (int) c[i] : 0;
+    r |= ((uint32_t) v & 0xffu) << (8 * k);
+  }
+  return r;
+}
+
+// x / d for x * d < 2^32: one IMAD.HI with m = floor((2^32 - 1) / d) + 1 (d == 1: m wraps to 0)
+struct FastDiv
+{
+  uint32_t d, m;
+  __host__ FastDiv(int div = 1) : d((uint32_t) div), m((uint32_t) (0xffffffffu / (uint32_t) div) + 1u) {}
+  __device__ __forceinline__ uint32_t div(uint32_t x) const { return d == 1 ? x : __umulhi(x, m); }
+};
+
+__device__ __forceinline__ uint32_t ld_u16(const int16_t* p) { return (uint32_t) * reinterpret_cast<const uint16_t*>(p); }
+
+template <int TAPS, bool VERT>
+__global__ void __launch_bounds__(kInterpThreads) interp_pairs_kernel(InterpArgs a, uint32_t units, int dstWords, FastDiv dHalfW, FastDiv dH)
+{
+  const int hr   = max(2, 14 - a.bitDepth);
+  const int maxv = (1 << a.bitDepth) - 1;
+  int       shift = 6, offset;
+  if (a.isLast)
+  {
+    shift += a.isFirst ? 0 : hr;
+    offset = 1 << (shift - 1);
+    offset += a.isFirst ? 0 : (8192 << 6);
+  }
+  else
+  {
+    shift -= a.isFirst ? hr : 0;
+    offset = a.isFirst ? -(8192 << shift) : 0;
+  }
+  constexpr int  before = TAPS / 2 - 1;
+  const uint32_t cA0 = pack_taps(a.coeff, 0), cA1 = pack_taps(a.coeff, 4);                                  // (c0 c1 c2 c3) (c4 c5 c6 c7)
+  const uint32_t cS0 = pack_taps(a.coeff, -1), cS1 = pack_taps(a.coeff, 3), cS2 = pack_taps(a.coeff, 7);   // (0 c0 c1 c2) (c3 c4 c5 c6) (c7 0 0 0)
+  // persistent grid: a CTA that lives for 256 units is bound by the CTA launch rate, not by memory
+#pragma unroll 2
+  for (uint32_t u = blockIdx.x * kInterpThreads + threadIdx.x; u < units; u += gridDim.x * kInterpThreads)
+  {
+  const uint32_t by = dHalfW.div(u), xp = u - by * dHalfW.d, b = dH.div(by), y = by - b * dH.d;
+  int s0 = offset, s1 = offset;
+  if (!VERT)
+  {
+    const int16_t* s = a.src + (long long) b * a.srcBlk + (ptrdiff_t) y * a.srcStride + (2 * (int) xp - before);   // first tap of output x
+    const bool     odd = (reinterpret_cast<uintptr_t>(s) & 2) != 0;
+    // aligned: W[0..TAPS/2-1] = words (s[0],s[1]).., W[TAPS/2] = s[TAPS] in the low half
+    // odd:     W[0] = s[0] in the HIGH half, W[1..TAPS/2] = words (s[1],s[2])..
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(odd ? s + 1 : s);
+    int             W[TAPS / 2 + 1];
+    if (odd)
+    {
+      W[0] = (int) (ld_u16(s) << 16);
+#pragma unroll
+      for (int k = 0; k < TAPS / 2; k++) W[k + 1] = (int) wp[k];
+    }
+    else
+    {
+#pragma unroll
+      for (int k = 0; k < TAPS / 2; k++) W[k] = (int) wp[k];
+      W[TAPS / 2] = (int) ld_u16(s + TAPS);
+    }
+    int sa = offset, ss = offset;   // sa: aligned coefficient pairs over 4 (2) words; ss: shifted pairs over 5 (3) words
+    const int* A = odd ? W + 1 : W;
+    sa = __dp2a_lo(A[0], (int) cA0, sa);
+    sa = __dp2a_hi(A[1], (int) cA0, sa);
+    ss = __dp2a_lo(W[0], (int) cS0, ss);
+    ss = __dp2a_hi(W[1], (int) cS0, ss);
+    ss = __dp2a_lo(W[2], (int) cS1, ss);
+    if (TAPS == 8)
+    {
+      sa = __dp2a_lo(A[2], (int) cA1, sa);
+      sa = __dp2a_hi(A[3], (int) cA1, sa);
+      ss = __dp2a_hi(W[3], (int) cS1, ss);
+      ss = __dp2a_lo(W[4], (int) cS2, ss);
+    }
+    s0 = odd ? ss : sa;
+    s1 = odd ? sa : ss;
+  }
+  else
+  {
+    const int16_t* s = a.src + (long long) b * a.srcBlk + (ptrdiff_t) ((int) y - before) * a.srcStride + 2 * xp;
+    uint32_t       R[TAPS];
+#pragma unroll
+    for (int k = 0; k < TAPS; k++)
+    {
+      const int16_t* q = s + (ptrdiff_t) k * a.srcStride;
+      if ((reinterpret_cast<uintptr_t>(q) & 2) == 0) R[k] = *reinterpret_cast<const uint32_t*>(q);
+      else R[k] = ld_u16(q) | (ld_u16(q + 1) << 16);
+    }
+#pragma unroll
+    for (int k = 0; k < TAPS; k += 2)
+    {
+      const int lo = (int) __byte_perm(R[k], R[k + 1], 0x5410), hi = (int) __byte_perm(R[k], R[k + 1], 0x7632);
+      const int c  = (int) (k < 4 ? cA0 : cA1);
+      if ((k & 2) == 0)
+      {
+        s0 = __dp2a_lo(lo, c, s0);
+        s1 = __dp2a_lo(hi, c, s1);
+      }
+      else
+      {
+        s0 = __dp2a_hi(lo, c, s0);
+        s1 = __dp2a_hi(hi, c, s1);
+      }
+    }
+  }
+  int v0 = (int16_t) (s0 >> shift), v1 = (int16_t) (s1 >> shift);
+  if (a.isLast)
+  {
+    v0 = min(max(v0, 0), maxv);
+    v1 = min(max(v1, 0), maxv);
+  }
+  int16_t* d = a.dst + (long long) b * a.dstBlk + (size_t) y * a.dstStride + 2 * xp;
+  if (dstWords) *reinterpret_cast<uint32_t*>(d) = (uint32_t) (uint16_t) v0 | ((uint32_t) (uint16_t) v1 << 16);
+  else
+  {
+    d[0] = (int16_t) v0;
+    d[1] = (int16_t) v1;
+  }
+  }
+}
+
+// The same arithmetic with EIGHT (horizontal: 8 adjacent outputs of a row) or SIXTEEN (vertical: 2 columns x 8 rows) outputs per
+// thread: the index arithmetic, the loads and — vertically — the interleaved row pairs are shared between the outputs, which is
+// what makes these filters memory- instead of instruction-bound.  Horizontal needs w % 8 == 0, vertical h % 8 == 0.
+template <int TAPS>
+__global__ void __launch_bounds__(kInterpThreads) interp_hor8_kernel(InterpArgs a, uint32_t units, int dstVec, FastDiv dW8, FastDiv dH)
+{
+  const int hr   = max(2, 14 - a.bitDepth);
+  const int maxv = (1 << a.bitDepth) - 1;
+  int       shift = 6, offset;
+  if (a.isLast)
+  {
+    shift  = 6;                      // filterHor is a first stage: first && last
+    offset = 1 << (shift - 1);
+  }
+  else
+  {
+    shift -= hr;
+    offset = -(8192 << shift);
+  }
+  constexpr int  before = TAPS / 2 - 1, NW = (8 + TAPS) / 2;   // words that hold the 8 + TAPS - 1 samples (+ one half-word)
+  const uint32_t cA0 = pack_taps(a.coeff, 0), cA1 = pack_taps(a.coeff, 4);
+  const uint32_t cS0 = pack_taps(a.coeff, -1), cS1 = pack_taps(a.coeff, 3), cS2 = pack_taps(a.coeff, 7);
+  for (uint32_t u = blockIdx.x * kInterpThreads + threadIdx.x; u < units; u += gridDim.x * kInterpThreads)
+  {
+    const uint32_t by = dW8.div(u), xg = u - by * dW8.d, b = dH.div(by), y = by - b * dH.d;
+    const int16_t* s = a.src + (long long) b * a.srcBlk + (ptrdiff_t) y * a.srcStride + (8 * (int) xg - before);
+    const bool     odd = (reinterpret_cast<uintptr_t>(s) & 2) != 0;
+    // aligned: W[k] = (s[2k], s[2k+1]) for k < NW - 1 ... plus s[8 + TAPS - 2] in the low half of the last word
+    // odd:     W[0] = s[0] in the high half, W[k] = (s[2k-1], s[2k])
+    int W[NW + 1];
+    if (odd)
+    {
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(s + 1);
+      W[0] = (int) (ld_u16(s) << 16);
+#pragma unroll
+      for (int k = 0; k < NW - 1; k++) W[k + 1] = (int) wp[k];
+      W[NW] = 0;
+    }
+    else
+    {
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(s);
+#pragma unroll
+      for (int k = 0; k < NW - 1; k++) W[k] = (int) wp[k];
+      W[NW - 1] = (int) ld_u16(s + 2 * (NW - 1));
+      W[NW]     = 0;
+    }
+    // output i (sample offset i): aligned: even i -> A-set from word i/2, odd i -> S-set from word (i-1)/2
+    //                             odd:     even i -> S-set from word i/2, odd i -> A-set from word (i+1)/2
+    int v[8];
+    auto outputs = [&](auto oddTag) {
+      constexpr bool ODD = decltype(oddTag)::value;
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+      {
+        int acc = offset;
+        if (((i & 1) != 0) == ODD)
+        {
+          const int ia = (i + 1) / 2;
+          acc = __dp2a_lo(W[ia], (int) cA0, acc);
+          acc = __dp2a_hi(W[ia + 1], (int) cA0, acc);
+          if (TAPS == 8)
+          {
+            acc = __dp2a_lo(W[ia + 2], (int) cA1, acc);
+            acc = __dp2a_hi(W[ia + 3], (int) cA1, acc);
+          }
+        }
+        else
+        {
+          const int is = i / 2;
+          acc = __dp2a_lo(W[is], (int) cS0, acc);
+          acc = __dp2a_hi(W[is + 1], (int) cS0, acc);
+          acc = __dp2a_lo(W[is + 2], (int) cS1, acc);
+          if (TAPS == 8)
+          {
+            acc = __dp2a_hi(W[is + 3], (int) cS1, acc);
+            acc = __dp2a_lo(W[is + 4], (int) cS2, acc);
+          }
+        }
+        int r = (int16_t) (acc >> shift);
+        if (a.isLast) r = min(max(r, 0), maxv);
+        v[i] = r;
+      }
+    };
+    if (odd) outputs(std::true_type{});
+    else outputs(std::false_type{});
+    int16_t* d = a.dst + (long long) b * a.dstBlk + (size_t) y * a.dstStride + 8 * xg;
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) o[k] = (uint32_t) (uint16_t) v[2 * k] | ((uint32_t) (uint16_t) v[2 * k + 1] << 16);
+    if (dstVec == 2) *reinterpret_cast<uint4*>(d) = make_uint4(o[0], o[1], o[2], o[3]);
+    else if (dstVec == 1)
+    {
+#pragma unroll
+      for (int k = 0; k < 4; k++) reinterpret_cast<uint32_t*>(d)[k] = o[k];
+    }
+    else
+    {
+#pragma unroll
+      for (int i = 0; i < 8; i++) d[i] = (int16_t) v[i];
+    }
+  }
+}
+
+template <int TAPS>
+__global__ void __launch_bounds__(kInterpThreads) interp_ver8_kernel(InterpArgs a, uint32_t units, int dstWords, FastDiv dHalfW, FastDiv dH8)
+{
+  const int hr   = max(2, 14 - a.bitDepth);
+  const int maxv = (1 << a.bitDepth) - 1;
+  int       shift = 6, offset;
+  if (a.isLast)
+  {
+    shift += a.isFirst ? 0 : hr;
+    offset = 1 << (shift - 1);
+    offset += a.isFirst ? 0 : (8192 << 6);
+  }
+  else
+  {
+    shift -= a.isFirst ? hr : 0;
+    offset = a.isFirst ? -(8192 << shift) : 0;
+  }
+  constexpr int  before = TAPS / 2 - 1, NR = 8 + TAPS - 1;
+  const uint32_t cA0 = pack_taps(a.coeff, 0), cA1 = pack_taps(a.coeff, 4);
+  for (uint32_t u = blockIdx.x * kInterpThreads + threadIdx.x; u < units; u += gridDim.x * kInterpThreads)
+  {
+    // unit = (block, group of 8 rows, column pair); column pairs fastest: a warp reads 128 contiguous bytes per row
+    const uint32_t by = dHalfW.div(u), xp = u - by * dHalfW.d, b = dH8.div(by), yg = by - b * dH8.d;
+    const int16_t* s = a.src + (long long) b * a.srcBlk + (ptrdiff_t) (8 * (int) yg - before) * a.srcStride + 2 * xp;
+    uint32_t       R[NR];
+#pragma unroll
+    for (int k = 0; k < NR; k++)
+    {
+      const int16_t* q = s + (ptrdiff_t) k * a.srcStride;
+      if ((reinterpret_cast<uintptr_t>(q) & 2) == 0) R[k] = *reinterpret_cast<const uint32_t*>(q);
+      else R[k] = ld_u16(q) | (ld_u16(q + 1) << 16);
+    }
+    // P[k]: rows k and k+1 interleaved, column x (lo) / x+1 (hi)
+    int lo[NR - 1], hi[NR - 1];
+#pragma unroll
+    for (int k = 0; k < NR - 1; k++)
+    {
+      lo[k] = (int) __byte_perm(R[k], R[k + 1], 0x5410);
+      hi[k] = (int) __byte_perm(R[k], R[k + 1], 0x7632);
+    }
+    int16_t* d = a.dst + (long long) b * a.dstBlk + (size_t) (8 * yg) * a.dstStride + 2 * xp;
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+    {
+      int s0 = offset, s1 = offset;
+      s0 = __dp2a_lo(lo[r], (int) cA0, s0);
+      s1 = __dp2a_lo(hi[r], (int) cA0, s1);
+      s0 = __dp2a_hi(lo[r + 2], (int) cA0, s0);
+      s1 = __dp2a_hi(hi[r + 2], (int) cA0, s1);
+      if (TAPS == 8)
+      {
+        s0 = __dp2a_lo(lo[r + 4], (int) cA1, s0);
+        s1 = __dp2a_lo(hi[r + 4], (int) cA1, s1);
+        s0 = __dp2a_hi(lo[r + 6], (int) cA1, s0);
+        s1 = __dp2a_hi(hi[r + 6], (int) cA1, s1);
+      }
+      int v0 = (int16_t) (s0 >> shift), v1 = (int16_t) (s1 >> shift);
+      if (a.isLast)
+      {
+        v0 = min(max(v0, 0), maxv);
+        v1 = min(max(v1, 0), maxv);
+      }
+      int16_t* dr = d + (size_t) r * a.dstStride;
+      if (dstWords) *reinterpret_cast<uint32_t*>(dr) = (uint32_t) (uint16_t) v0 | ((uint32_t) (uint16_t) v1 << 16);
+      else
+      {
+        dr[0] = (int16_t) v0;
+        dr[1] = (int16_t) v1;
+      }
+    }
+  }
+}
+
+// VTMME_INTERP_VARIANT=generic keeps every call on interp_batch_kernel (comparison runs)
+static bool interp_generic_only()
+{
+  static int v = -1;
+  if (v < 0)
+  {
+    const char* e = getenv("VTMME_INTERP_VARIANT");
+    v = (e && e[0] == 'g') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 static cudaError_t launch_interp(const InterpArgs& a, int n, cudaStream_t st)
 {
   const int halo = a.copy ? 0 : a.taps - 1;
   const int sw = a.w + (a.vertical ? 0 : halo), sh = a.h + (a.vertical ? halo : 0);
   int bpc = 2048 / (a.w * a.h);
   bpc     = bpc < 1 ? 1 : (bpc > 32 ? 32 : bpc);
+  if (!a.copy && (a.taps == 8 || a.taps == 4) && (a.w & 1) == 0 && !interp_generic_only() &&
+      (long long) n * a.h * (a.w / 2) < (1LL << 31))
+  {
+    const int      dstWords = (reinterpret_cast<uintptr_t>(a.dst) & 3) == 0 && (a.dstStride & 1) == 0 && (a.dstBlk & 1) == 0;
+    if (!a.vertical && (a.w & 7) == 0 && a.isFirst)
+    {
+      const int      dstVec = (reinterpret_cast<uintptr_t>(a.dst) & 15) == 0 && (a.dstStride & 7) == 0 && (a.dstBlk & 7) == 0 ? 2 : dstWords;
+      const uint32_t units8 = (uint32_t) n * (uint32_t) a.h * (uint32_t) (a.w / 8);
+      uint32_t       ctas8  = (units8 + kInterpThreads - 1) / kInterpThreads;
+      if (ctas8 > 148u * 16u) ctas8 = 148u * 16u;
+      const FastDiv dW8(a.w / 8), dH8(a.h);
+      if (a.taps == 8) interp_hor8_kernel<8><<<ctas8, kInterpThreads, 0, st>>>(a, units8, dstVec, dW8, dH8);
+      else interp_hor8_kernel<4><<<ctas8, kInterpThreads, 0, st>>>(a, units8, dstVec, dW8, dH8);
+      return cudaGetLastError();
+    }
+    if (a.vertical && (a.h & 7) == 0)
+    {
+      const uint32_t units8 = (uint32_t) n * (uint32_t) (a.h / 8) * (uint32_t) (a.w / 2);
+      uint32_t       ctas8  = (units8 + kInterpThreads - 1) / kInterpThreads;
+      if (ctas8 > 148u * 16u) ctas8 = 148u * 16u;
+      const FastDiv dHalf(a.w / 2), dHg(a.h / 8);
+      if (a.taps == 8) interp_ver8_kernel<8><<<ctas8, kInterpThreads, 0, st>>>(a, units8, dstWords, dHalf, dHg);
+      else interp_ver8_kernel<4><<<ctas8, kInterpThreads, 0, st>>>(a, units8, dstWords, dHalf, dHg);
+      return cudaGetLastError();
+    }
+    const uint32_t units    = (uint32_t) n * (uint32_t) a.h * (uint32_t) (a.w / 2);
+    uint32_t       ctas     = (units + kInterpThreads - 1) / kInterpThreads;
+    if (ctas > 148u * 16u) ctas = 148u * 16u;   // persistent: 8 CTAs of 256 threads fit an SM, two rounds
+    const FastDiv  dHalfW(a.w / 2), dH(a.h);
+#define VTMME_INTERP_PAIRS(T, V) \
+    { interp_pairs_kernel<T, V><<<ctas, kInterpThreads, 0, st>>>(a, units, dstWords, dHalfW, dH); return cudaGetLastError(); }
+    if (a.taps == 8 && !a.vertical) VTMME_INTERP_PAIRS(8, false)
+    if (a.taps == 8 && a.vertical) VTMME_INTERP_PAIRS(8, true)
+    if (a.taps == 4 && !a.vertical) VTMME_INTERP_PAIRS(4, false)
+    VTMME_INTERP_PAIRS(4, true)
+#undef VTMME_INTERP_PAIRS
+  }
   const size_t smem = (size_t) bpc * sw * sh * sizeof(int16_t);
   static SmemOptIn optIn;
   if (cudaError_t e = optIn.ensure(interp_batch_kernel, smem, 48 * 1024)) return e;
@@ -353,6 +822,18 @@ cudaError_t launch_extend_border(DevPic pic, cudaStream_t st)
   return cudaGetLastError();
 }
 
+// VTMME_SATD_VARIANT=warp keeps every call on satd_batch_kernel (one warp per block; comparison runs)
+static bool satd_warp_only()
+{
+  static int v = -1;
+  if (v < 0)
+  {
+    const char* e = getenv("VTMME_SATD_VARIANT");
+    v = (e && e[0] == 'w') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 static bool aligned_layout(const void* p, int stride, long long blk, int vec)
 {
   return (reinterpret_cast<uintptr_t>(p) % (2 * vec)) == 0 && stride % vec == 0 && blk % vec == 0;
@@ -382,6 +863,23 @@ cudaError_t launch_dist_batch(int kind, const int16_t* org, int orgStride, long 
     return cudaGetLastError();
   }
   const int blocks = (n + 7) / 8;   // 8 warps per CTA
+  if (pow2 && w >= 8 && h >= 8 && !satd_warp_only() && aligned_layout(org, orgStride, orgBlockStride, 8) &&
+      aligned_layout(cur, curStride, curBlockStride, 8))
+  {
+    int log2Ux = 0, log2Units = 0;
+    while ((8 << log2Ux) < w) log2Ux++;
+    while ((64LL << log2Units) < (long long) w * h) log2Units++;
+    const long long units = (long long) n << log2Units;
+    const int       ctas  = (int) ((units + 127) / 128);
+    if (log2Units > 5)
+      if (cudaError_t e = cudaMemsetAsync(out, 0, (size_t) n * sizeof(unsigned long long), st)) return e;
+#define VTMME_SATD_TT(M) satd_tile_thread_kernel<M><<<ctas, 128, 0, st>>>(org, orgStride, orgBlockStride, cur, curStride, curBlockStride, w, h, n, log2Units, log2Ux, out)
+    if (w == h) VTMME_SATD_TT(0);
+    else if (w > h) VTMME_SATD_TT(1);
+    else VTMME_SATD_TT(2);
+#undef VTMME_SATD_TT
+    return cudaGetLastError();
+  }
   if (aligned_layout(org, orgStride, orgBlockStride, 8) && aligned_layout(cur, curStride, curBlockStride, 8))
     satd_batch_kernel<true><<<blocks, 256, 0, st>>>(org, orgStride, orgBlockStride, cur, curStride, curBlockStride, w, h, n, out);
   else
