@@ -427,11 +427,18 @@ __device__ __forceinline__ uint32_t pack_taps(const int16_t* c, int i0)   // byt
   return r;
 }
 
-// x / d for x * d < 2^32: one IMAD.HI with m = floor((2^32 - 1) / d) + 1 (d == 1: m wraps to 0)
+// x / d as one IMAD.HI with m = floor((2^32 - 1) / d) + 1 (d == 1: m wraps to 0).  m * d = 2^32 + e with 0 <= e <= d, and the
+// quotient is exact while x * e < 2^32 — always for a power of two (e = 0); the host checks the largest dividend.
 struct FastDiv
 {
   uint32_t d, m;
   __host__ FastDiv(int div = 1) : d((uint32_t) div), m((uint32_t) (0xffffffffu / (uint32_t) div) + 1u) {}
+  __host__ bool exact_below(unsigned long long maxX) const
+  {
+    if (d == 1) return maxX <= 0xffffffffull;
+    const unsigned long long e = (unsigned long long) m * d - (1ull << 32);
+    return maxX <= 0xffffffffull && (e == 0 || maxX * e < (1ull << 32));
+  }
   __device__ __forceinline__ uint32_t div(uint32_t x) const { return d == 1 ? x : __umulhi(x, m); }
 };
 
@@ -738,42 +745,51 @@ static cudaError_t launch_interp(const InterpArgs& a, int n, cudaStream_t st)
   const int sw = a.w + (a.vertical ? 0 : halo), sh = a.h + (a.vertical ? halo : 0);
   int bpc = 2048 / (a.w * a.h);
   bpc     = bpc < 1 ? 1 : (bpc > 32 ? 32 : bpc);
-  if (!a.copy && (a.taps == 8 || a.taps == 4) && (a.w & 1) == 0 && !interp_generic_only() &&
-      (long long) n * a.h * (a.w / 2) < (1LL << 31))
+  bool tapsFitBytes = true;   // IDP.2A multiplies 16-bit samples by 8-bit coefficients (every VVC filter table fits)
+  for (int k = 0; k < 8; k++) tapsFitBytes = tapsFitBytes && a.coeff[k] >= -128 && a.coeff[k] <= 127;
+  const unsigned long long outPairs = (unsigned long long) n * a.h * (a.w / 2);
+  if (!a.copy && (a.taps == 8 || a.taps == 4) && (a.w & 1) == 0 && !interp_generic_only() && tapsFitBytes && outPairs < (1ULL << 31))
   {
-    const int      dstWords = (reinterpret_cast<uintptr_t>(a.dst) & 3) == 0 && (a.dstStride & 1) == 0 && (a.dstBlk & 1) == 0;
+    const int dstWords = (reinterpret_cast<uintptr_t>(a.dst) & 3) == 0 && (a.dstStride & 1) == 0 && (a.dstBlk & 1) == 0;
+    auto grid = [](uint32_t units) {
+      const uint32_t ctas = (units + kInterpThreads - 1) / kInterpThreads;
+      return ctas > 148u * 16u ? 148u * 16u : ctas;   // persistent: 8 CTAs of 256 threads fit an SM, two rounds
+    };
     if (!a.vertical && (a.w & 7) == 0 && a.isFirst)
     {
       const int      dstVec = (reinterpret_cast<uintptr_t>(a.dst) & 15) == 0 && (a.dstStride & 7) == 0 && (a.dstBlk & 7) == 0 ? 2 : dstWords;
-      const uint32_t units8 = (uint32_t) n * (uint32_t) a.h * (uint32_t) (a.w / 8);
-      uint32_t       ctas8  = (units8 + kInterpThreads - 1) / kInterpThreads;
-      if (ctas8 > 148u * 16u) ctas8 = 148u * 16u;
-      const FastDiv dW8(a.w / 8), dH8(a.h);
-      if (a.taps == 8) interp_hor8_kernel<8><<<ctas8, kInterpThreads, 0, st>>>(a, units8, dstVec, dW8, dH8);
-      else interp_hor8_kernel<4><<<ctas8, kInterpThreads, 0, st>>>(a, units8, dstVec, dW8, dH8);
-      return cudaGetLastError();
+      const uint32_t units  = (uint32_t) n * (uint32_t) a.h * (uint32_t) (a.w / 8);
+      const FastDiv  dW8(a.w / 8), dH(a.h);
+      if (dW8.exact_below(units) && dH.exact_below(units / dW8.d))
+      {
+        if (a.taps == 8) interp_hor8_kernel<8><<<grid(units), kInterpThreads, 0, st>>>(a, units, dstVec, dW8, dH);
+        else interp_hor8_kernel<4><<<grid(units), kInterpThreads, 0, st>>>(a, units, dstVec, dW8, dH);
+        return cudaGetLastError();
+      }
     }
     if (a.vertical && (a.h & 7) == 0)
     {
-      const uint32_t units8 = (uint32_t) n * (uint32_t) (a.h / 8) * (uint32_t) (a.w / 2);
-      uint32_t       ctas8  = (units8 + kInterpThreads - 1) / kInterpThreads;
-      if (ctas8 > 148u * 16u) ctas8 = 148u * 16u;
-      const FastDiv dHalf(a.w / 2), dHg(a.h / 8);
-      if (a.taps == 8) interp_ver8_kernel<8><<<ctas8, kInterpThreads, 0, st>>>(a, units8, dstWords, dHalf, dHg);
-      else interp_ver8_kernel<4><<<ctas8, kInterpThreads, 0, st>>>(a, units8, dstWords, dHalf, dHg);
-      return cudaGetLastError();
+      const uint32_t units = (uint32_t) n * (uint32_t) (a.h / 8) * (uint32_t) (a.w / 2);
+      const FastDiv  dHalf(a.w / 2), dHg(a.h / 8);
+      if (dHalf.exact_below(units) && dHg.exact_below(units / dHalf.d))
+      {
+        if (a.taps == 8) interp_ver8_kernel<8><<<grid(units), kInterpThreads, 0, st>>>(a, units, dstWords, dHalf, dHg);
+        else interp_ver8_kernel<4><<<grid(units), kInterpThreads, 0, st>>>(a, units, dstWords, dHalf, dHg);
+        return cudaGetLastError();
+      }
     }
-    const uint32_t units    = (uint32_t) n * (uint32_t) a.h * (uint32_t) (a.w / 2);
-    uint32_t       ctas     = (units + kInterpThreads - 1) / kInterpThreads;
-    if (ctas > 148u * 16u) ctas = 148u * 16u;   // persistent: 8 CTAs of 256 threads fit an SM, two rounds
+    const uint32_t units = (uint32_t) outPairs;
     const FastDiv  dHalfW(a.w / 2), dH(a.h);
+    if (dHalfW.exact_below(units) && dH.exact_below(units / dHalfW.d))
+    {
 #define VTMME_INTERP_PAIRS(T, V) \
-    { interp_pairs_kernel<T, V><<<ctas, kInterpThreads, 0, st>>>(a, units, dstWords, dHalfW, dH); return cudaGetLastError(); }
-    if (a.taps == 8 && !a.vertical) VTMME_INTERP_PAIRS(8, false)
-    if (a.taps == 8 && a.vertical) VTMME_INTERP_PAIRS(8, true)
-    if (a.taps == 4 && !a.vertical) VTMME_INTERP_PAIRS(4, false)
-    VTMME_INTERP_PAIRS(4, true)
+      { interp_pairs_kernel<T, V><<<grid(units), kInterpThreads, 0, st>>>(a, units, dstWords, dHalfW, dH); return cudaGetLastError(); }
+      if (a.taps == 8 && !a.vertical) VTMME_INTERP_PAIRS(8, false)
+      if (a.taps == 8 && a.vertical) VTMME_INTERP_PAIRS(8, true)
+      if (a.taps == 4 && !a.vertical) VTMME_INTERP_PAIRS(4, false)
+      VTMME_INTERP_PAIRS(4, true)
 #undef VTMME_INTERP_PAIRS
+    }
   }
   const size_t smem = (size_t) bpc * sw * sh * sizeof(int16_t);
   static SmemOptIn optIn;
