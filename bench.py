@@ -287,6 +287,69 @@ def run_reference(args, rank):
 
 
 # ---- this repo's arm ------------------------------------------------------------------------------------------------
+def config5_sample(ms, torch, stream, dev, hbm_peak):
+    """BASELINE config 5 inside the bench run (rank 0, N = 1, after the timed legs): the table-level batch kernels on
+    HBM-resident batches of 64x64 and 128x128 blocks (256 MB per operand, beyond L2), CUDA-event timed, a sample of the
+    outputs compared with the oracle port.  GB/s = algorithmic bytes (operand blocks in, with the tap halo for filters, results
+    out) / kernel time.  The full 36-shape sweep against the reference's AVX2 entries is microbench.py."""
+    from oracle import bindings as B
+    O = B.oracle()
+    out = []
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(5005)
+
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / reps
+
+    for (w, h) in ((64, 64), (128, 128)):
+        n = (1 << 27) // (w * h)
+        org = torch.randint(0, 1024, (n, h, w), device=dev, dtype=torch.int16, generator=gen)
+        cur = torch.randint(0, 1024, (n, h, w), device=dev, dtype=torch.int16, generator=gen)
+        res = torch.zeros(n, dtype=torch.int64, device=dev)
+        sample = list(range(0, n, max(1, n // 16)))[:16]
+        h_org, h_cur = org[sample].cpu().numpy(), cur[sample].cpu().numpy()
+        for kind, name in ((0, "SAD"), (1, "SATD")):
+            t = timed(lambda: ms.dist_batch(kind, org.data_ptr(), w, w * h, cur.data_ptr(), w, w * h, w, h, 0, n, res.data_ptr()))
+            got = res[sample].cpu().numpy()
+            f = O.vo_sad if kind == 0 else O.vo_satd
+            want = [f(B.ptr(h_org[i]), w, B.ptr(h_cur[i]), w, w, h, 0) if kind == 0 else f(B.ptr(h_org[i]), w, B.ptr(h_cur[i]), w, w, h)
+                    for i in range(len(sample))]
+            nbytes = n * (2 * w * h * 2 + 8)
+            out.append({"op": name, "w": w, "h": h, "blocks": n, "gbs": nbytes / t / 1e9, "hbm_frac": nbytes / t / 1e9 / hbm_peak,
+                        "equal": bool([int(x) for x in got] == [int(x) for x in want])})
+        del cur, res
+        src = torch.randint(0, 1024, (n, h + 8, w + 8), device=dev, dtype=torch.int16, generator=gen)
+        dst = torch.zeros((n, h, w), dtype=torch.int16, device=dev)
+        off, ss = 4 * (w + 8) + 4, w + 8
+        h_src = src[sample].cpu().numpy()
+        for vert, last, name in ((0, 0, "luma 8-tap horizontal (first stage)"), (1, 1, "luma 8-tap vertical (single stage)")):
+            frac = 5
+            t = timed(lambda: ms.interp_batch(0, vert, src.data_ptr() + 2 * off, ss, ss * (h + 8), dst.data_ptr(), w, w * h, w, h,
+                                              frac, 1, last, 10, 0, n))
+            got = dst[sample].cpu().numpy()
+            ok = True
+            for i in range(len(sample)):
+                want = np.zeros((h, w), np.int16)
+                if vert:
+                    O.vo_filter_ver(0, B.ptr(h_src[i], off), ss, B.ptr(want), w, w, h, frac, 1, last, 10, 0)
+                else:
+                    O.vo_filter_hor(0, B.ptr(h_src[i], off), ss, B.ptr(want), w, w, h, frac, last, 10, 0)
+                ok = ok and bool(np.array_equal(got[i], want))
+            nbytes = n * (((w + 7) * h if not vert else w * (h + 7)) * 2 + w * h * 2)
+            out.append({"op": name, "w": w, "h": h, "blocks": n, "gbs": nbytes / t / 1e9, "hbm_frac": nbytes / t / 1e9 / hbm_peak,
+                        "equal": ok})
+        del org, src, dst
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -551,9 +614,17 @@ def run_ours(args, rank, world, local_rank):
             if kind == "reference":   # the single-thread number next to the all-cores one (sparser sample)
                 r1, s1, d1, _, _ = cpu_reference_rate(pair0[0], pair0[1], 8 * every, 1)
                 line["cpu_baseline"]["single_core"] = {"value": r1, "unit": UNIT, "cores": 1, "sample": d1, "seconds": s1}
+        if pair0 is not None:
+            line["config5"] = {"what": "table-level batch kernels (SURVEY config 5), HBM-resident batches, sample of outputs vs the "
+                                       "oracle; full sweep vs the reference's AVX2 entries: profiles/*_microbench.md",
+                               "hbm_peak_gbs": hbm_peak, "rows": config5_sample(ms, torch, stream, dev, hbm_peak)}
         emit(line)
         if line.get("parity", {}).get("equal") is False:
             sys.stderr.write("PARITY FAILURE: %d of %d CUs differ from the %s\n" % (len(bad), len(want), kind))
+            ms.close()
+            sys.exit(3)
+        if any(not r["equal"] for r in line.get("config5", {}).get("rows", [])):
+            sys.stderr.write("PARITY FAILURE: table-level kernels differ from the oracle (config5 rows)\n")
             ms.close()
             sys.exit(3)
     ms.close()
