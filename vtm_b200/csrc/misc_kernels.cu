@@ -654,8 +654,10 @@ __global__ void __launch_bounds__(kInterpThreads) interp_hor8_kernel(InterpArgs 
   }
 }
 
+// Requires word-aligned column pairs (source base 4-byte aligned, even strides) and source / destination spans below 2 GB, so
+// that every access is "uniform 64-bit row base + 32-bit thread offset" (no 64-bit address arithmetic per row and thread).
 template <int TAPS>
-__global__ void __launch_bounds__(kInterpThreads) interp_ver8_kernel(InterpArgs a, uint32_t units, int dstWords, FastDiv dHalfW, FastDiv dH8)
+__global__ void __launch_bounds__(kInterpThreads) interp_ver8_kernel(InterpArgs a, uint32_t units, FastDiv dHalfW, FastDiv dH8)
 {
   const int hr   = max(2, 14 - a.bitDepth);
   const int maxv = (1 << a.bitDepth) - 1;
@@ -673,20 +675,20 @@ __global__ void __launch_bounds__(kInterpThreads) interp_ver8_kernel(InterpArgs 
   }
   constexpr int  before = TAPS / 2 - 1, NR = 8 + TAPS - 1;
   const uint32_t cA0 = pack_taps(a.coeff, 0), cA1 = pack_taps(a.coeff, 4);
+  const char*    srcBase = reinterpret_cast<const char*>(a.src - (ptrdiff_t) before * a.srcStride);   // first tap row of output row 0
+  char*          dstBase = reinterpret_cast<char*>(a.dst);
+  const uint32_t srcRowBytes = 2u * (uint32_t) a.srcStride, dstRowBytes = 2u * (uint32_t) a.dstStride;
+  const uint32_t srcBlkBytes = 2u * (uint32_t) a.srcBlk, dstBlkBytes = 2u * (uint32_t) a.dstBlk;
   for (uint32_t u = blockIdx.x * kInterpThreads + threadIdx.x; u < units; u += gridDim.x * kInterpThreads)
   {
     // unit = (block, group of 8 rows, column pair); column pairs fastest: a warp reads 128 contiguous bytes per row
     const uint32_t by = dHalfW.div(u), xp = u - by * dHalfW.d, b = dH8.div(by), yg = by - b * dH8.d;
-    const int16_t* s = a.src + (long long) b * a.srcBlk + (ptrdiff_t) (8 * (int) yg - before) * a.srcStride + 2 * xp;
+    const uint32_t so = b * srcBlkBytes + 8u * yg * srcRowBytes + 4u * xp;
     uint32_t       R[NR];
+    const char*    sp = srcBase + so;   // per-thread base; the row offsets k * srcRowBytes are uniform
 #pragma unroll
-    for (int k = 0; k < NR; k++)
-    {
-      const int16_t* q = s + (ptrdiff_t) k * a.srcStride;
-      if ((reinterpret_cast<uintptr_t>(q) & 2) == 0) R[k] = *reinterpret_cast<const uint32_t*>(q);
-      else R[k] = ld_u16(q) | (ld_u16(q + 1) << 16);
-    }
-    // P[k]: rows k and k+1 interleaved, column x (lo) / x+1 (hi)
+    for (int k = 0; k < NR; k++) R[k] = *reinterpret_cast<const uint32_t*>(sp + (size_t) (k * srcRowBytes));
+    // rows k and k+1 interleaved, column x (lo) / x+1 (hi)
     int lo[NR - 1], hi[NR - 1];
 #pragma unroll
     for (int k = 0; k < NR - 1; k++)
@@ -694,7 +696,7 @@ __global__ void __launch_bounds__(kInterpThreads) interp_ver8_kernel(InterpArgs 
       lo[k] = (int) __byte_perm(R[k], R[k + 1], 0x5410);
       hi[k] = (int) __byte_perm(R[k], R[k + 1], 0x7632);
     }
-    int16_t* d = a.dst + (long long) b * a.dstBlk + (size_t) (8 * yg) * a.dstStride + 2 * xp;
+    char* dp = dstBase + (b * dstBlkBytes + 8u * yg * dstRowBytes + 4u * xp);
 #pragma unroll
     for (int r = 0; r < 8; r++)
     {
@@ -710,19 +712,13 @@ __global__ void __launch_bounds__(kInterpThreads) interp_ver8_kernel(InterpArgs 
         s0 = __dp2a_hi(lo[r + 6], (int) cA1, s0);
         s1 = __dp2a_hi(hi[r + 6], (int) cA1, s1);
       }
-      int v0 = (int16_t) (s0 >> shift), v1 = (int16_t) (s1 >> shift);
-      if (a.isLast)
+      int v0 = s0 >> shift, v1 = s1 >> shift;
+      if (a.isLast)   // ClipPel of the 32-bit value (one instruction), as InterpolationFilter::filter does before it stores a Pel
       {
-        v0 = min(max(v0, 0), maxv);
-        v1 = min(max(v1, 0), maxv);
+        v0 = __vimin_s32_relu(v0, maxv);
+        v1 = __vimin_s32_relu(v1, maxv);
       }
-      int16_t* dr = d + (size_t) r * a.dstStride;
-      if (dstWords) *reinterpret_cast<uint32_t*>(dr) = (uint32_t) (uint16_t) v0 | ((uint32_t) (uint16_t) v1 << 16);
-      else
-      {
-        dr[0] = (int16_t) v0;
-        dr[1] = (int16_t) v1;
-      }
+      *reinterpret_cast<uint32_t*>(dp + (size_t) (r * dstRowBytes)) = __byte_perm((uint32_t) v0, (uint32_t) v1, 0x5410);
     }
   }
 }
@@ -767,14 +763,19 @@ static cudaError_t launch_interp(const InterpArgs& a, int n, cudaStream_t st)
         return cudaGetLastError();
       }
     }
-    if (a.vertical && (a.h & 7) == 0)
+    // byte spans of the batch: the vertical fast path addresses with 32-bit offsets from uniform row bases
+    const unsigned long long srcSpan = 2ull * ((unsigned long long) (n - 1) * (unsigned long long) a.srcBlk + (unsigned long long) (a.h + 8) * a.srcStride + a.w);
+    const unsigned long long dstSpan = 2ull * ((unsigned long long) (n - 1) * (unsigned long long) a.dstBlk + (unsigned long long) a.h * a.dstStride + a.w);
+    const bool srcWords = (reinterpret_cast<uintptr_t>(a.src) & 3) == 0 && (a.srcStride & 1) == 0 && (a.srcBlk & 1) == 0;
+    if (a.vertical && (a.h & 7) == 0 && dstWords && srcWords && a.srcBlk >= 0 && a.dstBlk >= 0 && a.srcStride > 0 && a.dstStride > 0 &&
+        srcSpan < (1ull << 31) && dstSpan < (1ull << 31))
     {
       const uint32_t units = (uint32_t) n * (uint32_t) (a.h / 8) * (uint32_t) (a.w / 2);
       const FastDiv  dHalf(a.w / 2), dHg(a.h / 8);
       if (dHalf.exact_below(units) && dHg.exact_below(units / dHalf.d))
       {
-        if (a.taps == 8) interp_ver8_kernel<8><<<grid(units), kInterpThreads, 0, st>>>(a, units, dstWords, dHalf, dHg);
-        else interp_ver8_kernel<4><<<grid(units), kInterpThreads, 0, st>>>(a, units, dstWords, dHalf, dHg);
+        if (a.taps == 8) interp_ver8_kernel<8><<<grid(units), kInterpThreads, 0, st>>>(a, units, dHalf, dHg);
+        else interp_ver8_kernel<4><<<grid(units), kInterpThreads, 0, st>>>(a, units, dHalf, dHg);
         return cudaGetLastError();
       }
     }
