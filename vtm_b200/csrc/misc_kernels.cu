@@ -554,6 +554,13 @@ __global__ void __launch_bounds__(kInterpThreads) interp_pairs_kernel(InterpArgs
 // The same arithmetic with EIGHT (horizontal: 8 adjacent outputs of a row) or SIXTEEN (vertical: 2 columns x 8 rows) outputs per
 // thread: the index arithmetic, the loads and — vertically — the interleaved row pairs are shared between the outputs, which is
 // what makes these filters memory- instead of instruction-bound.  Horizontal needs w % 8 == 0, vertical h % 8 == 0.
+// Horizontal: the 8 + TAPS - 1 samples of a thread come in as the two or three ALIGNED 16-byte chunks that hold them (LDG.128: the
+// lanes of a warp read 512 contiguous bytes per instruction; with 32-bit loads the lanes were 16 bytes apart and the kernel was
+// bound by the L1 data pipe, 0.71 of the HBM peak).  Where the first sample sits in its chunk (q = 0..7 samples, the same for a
+// whole row) only selects which registers the dot products read: word offset q >> 1 as a compile-time offset into the loaded
+// words, parity q & 1 as the swap of the two coefficient sets — a warp-uniform switch over eight instantiations, no data movement.
+// A chunk is only loaded if it holds at least one sample of the block or its halo (the third one is predicated), so no access
+// leaves the 16-byte granule of a needed sample.
 template <int TAPS>
 __global__ void __launch_bounds__(kInterpThreads) interp_hor8_kernel(InterpArgs a, uint32_t units, int dstVec, FastDiv dW8, FastDiv dH)
 {
@@ -570,37 +577,26 @@ __global__ void __launch_bounds__(kInterpThreads) interp_hor8_kernel(InterpArgs 
     shift -= hr;
     offset = -(8192 << shift);
   }
-  constexpr int  before = TAPS / 2 - 1, NW = (8 + TAPS) / 2;   // words that hold the 8 + TAPS - 1 samples (+ one half-word)
+  constexpr int  before = TAPS / 2 - 1, NW = (8 + TAPS) / 2;   // words that hold the 8 + TAPS - 1 samples of a thread
   const uint32_t cA0 = pack_taps(a.coeff, 0), cA1 = pack_taps(a.coeff, 4);
   const uint32_t cS0 = pack_taps(a.coeff, -1), cS1 = pack_taps(a.coeff, 3), cS2 = pack_taps(a.coeff, 7);
   for (uint32_t u = blockIdx.x * kInterpThreads + threadIdx.x; u < units; u += gridDim.x * kInterpThreads)
   {
     const uint32_t by = dW8.div(u), xg = u - by * dW8.d, b = dH.div(by), y = by - b * dH.d;
-    const int16_t* s = a.src + (long long) b * a.srcBlk + (ptrdiff_t) y * a.srcStride + (8 * (int) xg - before);
-    const bool     odd = (reinterpret_cast<uintptr_t>(s) & 2) != 0;
-    // aligned: W[k] = (s[2k], s[2k+1]) for k < NW - 1 ... plus s[8 + TAPS - 2] in the low half of the last word
-    // odd:     W[0] = s[0] in the high half, W[k] = (s[2k-1], s[2k])
-    int W[NW + 1];
-    if (odd)
-    {
-      const uint32_t* wp = reinterpret_cast<const uint32_t*>(s + 1);
-      W[0] = (int) (ld_u16(s) << 16);
-#pragma unroll
-      for (int k = 0; k < NW - 1; k++) W[k + 1] = (int) wp[k];
-      W[NW] = 0;
-    }
-    else
-    {
-      const uint32_t* wp = reinterpret_cast<const uint32_t*>(s);
-#pragma unroll
-      for (int k = 0; k < NW - 1; k++) W[k] = (int) wp[k];
-      W[NW - 1] = (int) ld_u16(s + 2 * (NW - 1));
-      W[NW]     = 0;
-    }
-    // output i (sample offset i): aligned: even i -> A-set from word i/2, odd i -> S-set from word (i-1)/2
-    //                             odd:     even i -> S-set from word i/2, odd i -> A-set from word (i+1)/2
+    const int16_t* s = a.src + (long long) b * a.srcBlk + (ptrdiff_t) y * a.srcStride + (8 * (int) xg - before);   // first tap of output 8 xg
+    const int      q = (int) ((reinterpret_cast<uintptr_t>(s) >> 1) & 7);   // sample offset of s[0] in its 16-byte chunk
+    const uint4*   cp = reinterpret_cast<const uint4*>(reinterpret_cast<uintptr_t>(s) & ~(uintptr_t) 15);
+    const uint4    c0 = cp[0], c1 = cp[1];
+    uint4          c2 = make_uint4(0, 0, 0, 0);
+    if ((q >> 1) + NW > 8) c2 = cp[2];
+    const int L[12] = { (int) c0.x, (int) c0.y, (int) c0.z, (int) c0.w, (int) c1.x, (int) c1.y, (int) c1.z, (int) c1.w,
+                        (int) c2.x, (int) c2.y, (int) c2.z, (int) c2.w };
     int v[8];
-    auto outputs = [&](auto oddTag) {
+    // W[k] = L[WO + k].  Even parity: W[k] = (s[2k], s[2k+1]): output i even -> pairs (c0,c1).. from word i/2, odd -> shifted pairs
+    // (0,c0)(c1,c2)..(c7,0) from word (i-1)/2.  Odd parity: W[k] = (s[2k-1], s[2k]): even i -> shifted pairs from word i/2, odd i ->
+    // pairs from word (i+1)/2.  A half-word outside the taps always meets a zero coefficient.
+    auto outputs = [&](auto woTag, auto oddTag) {
+      constexpr int  WO  = decltype(woTag)::value;
       constexpr bool ODD = decltype(oddTag)::value;
 #pragma unroll
       for (int i = 0; i < 8; i++)
@@ -608,38 +604,51 @@ __global__ void __launch_bounds__(kInterpThreads) interp_hor8_kernel(InterpArgs 
         int acc = offset;
         if (((i & 1) != 0) == ODD)
         {
-          const int ia = (i + 1) / 2;
-          acc = __dp2a_lo(W[ia], (int) cA0, acc);
-          acc = __dp2a_hi(W[ia + 1], (int) cA0, acc);
+          const int ia = WO + (i + 1) / 2;
+          acc = __dp2a_lo(L[ia], (int) cA0, acc);
+          acc = __dp2a_hi(L[ia + 1], (int) cA0, acc);
           if (TAPS == 8)
           {
-            acc = __dp2a_lo(W[ia + 2], (int) cA1, acc);
-            acc = __dp2a_hi(W[ia + 3], (int) cA1, acc);
+            acc = __dp2a_lo(L[ia + 2], (int) cA1, acc);
+            acc = __dp2a_hi(L[ia + 3], (int) cA1, acc);
           }
         }
         else
         {
-          const int is = i / 2;
-          acc = __dp2a_lo(W[is], (int) cS0, acc);
-          acc = __dp2a_hi(W[is + 1], (int) cS0, acc);
-          acc = __dp2a_lo(W[is + 2], (int) cS1, acc);
+          const int is = WO + i / 2;
+          acc = __dp2a_lo(L[is], (int) cS0, acc);
+          acc = __dp2a_hi(L[is + 1], (int) cS0, acc);
+          acc = __dp2a_lo(L[is + 2], (int) cS1, acc);
           if (TAPS == 8)
           {
-            acc = __dp2a_hi(W[is + 3], (int) cS1, acc);
-            acc = __dp2a_lo(W[is + 4], (int) cS2, acc);
+            acc = __dp2a_hi(L[is + 3], (int) cS1, acc);
+            acc = __dp2a_lo(L[is + 4], (int) cS2, acc);
           }
         }
-        int r = (int16_t) (acc >> shift);
-        if (a.isLast) r = min(max(r, 0), maxv);
+        int r = acc >> shift;
+        if (a.isLast) r = __vimin_s32_relu(r, maxv);   // ClipPel of the 32-bit value, then the store truncates to a Pel
         v[i] = r;
       }
     };
-    if (odd) outputs(std::true_type{});
-    else outputs(std::false_type{});
+    using I0 = std::integral_constant<int, 0>;
+    using I1 = std::integral_constant<int, 1>;
+    using I2 = std::integral_constant<int, 2>;
+    using I3 = std::integral_constant<int, 3>;
+    switch (q)
+    {
+      case 0: outputs(I0{}, std::false_type{}); break;
+      case 1: outputs(I0{}, std::true_type{}); break;
+      case 2: outputs(I1{}, std::false_type{}); break;
+      case 3: outputs(I1{}, std::true_type{}); break;
+      case 4: outputs(I2{}, std::false_type{}); break;
+      case 5: outputs(I2{}, std::true_type{}); break;
+      case 6: outputs(I3{}, std::false_type{}); break;
+      default: outputs(I3{}, std::true_type{}); break;
+    }
     int16_t* d = a.dst + (long long) b * a.dstBlk + (size_t) y * a.dstStride + 8 * xg;
     uint32_t o[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) o[k] = (uint32_t) (uint16_t) v[2 * k] | ((uint32_t) (uint16_t) v[2 * k + 1] << 16);
+    for (int k = 0; k < 4; k++) o[k] = __byte_perm((uint32_t) v[2 * k], (uint32_t) v[2 * k + 1], 0x5410);
     if (dstVec == 2) *reinterpret_cast<uint4*>(d) = make_uint4(o[0], o[1], o[2], o[3]);
     else if (dstVec == 1)
     {
