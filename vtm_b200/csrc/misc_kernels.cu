@@ -222,7 +222,7 @@ __device__ __forceinline__ void load_diff8x8(const int16_t* __restrict__ o, int 
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(128, 3) satd_tile_thread_kernel(const int16_t* __restrict__ org, int orgStride, long long orgBlk,
+__global__ void __launch_bounds__(128, MODE == 0 ? 5 : 3) satd_tile_thread_kernel(const int16_t* __restrict__ org, int orgStride, long long orgBlk,
                                                                const int16_t* __restrict__ cur, int curStride, long long curBlk,
                                                                int w, int h, int n, int log2Units, int log2Ux,
                                                                unsigned long long* out)
