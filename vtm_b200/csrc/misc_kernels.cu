@@ -187,11 +187,12 @@ __global__ void __launch_bounds__(256) satd_batch_kernel(const int16_t* __restri
 }
 
 // ---- SATD, one THREAD per 8x8 sub-tile (blocks with min(w, h) >= 8, power-of-two sizes, 16-byte aligned rows) ----
-// MODE 0: the 8x8 tiling (w == h).  MODE 1 / 2: the 16x8 / 8x16 tilings — the first butterfly stage across the two 8x8 halves
-// of a tile is done on the raw differences (Hadamard stages commute): the thread of half 0 transforms L + R (T + B), the
-// thread of half 1 transforms L - R (T - B), each from both halves' samples; the DC term (>> 2) is coefficient (0,0) of half 0
-// and the tile value (int)(sum / sqrt(128) * 2) is formed from the two threads' sums (RdCost.cpp:2369-2560).  The 2-D
-// transform of a sub-tile is 6 x 64 register butterflies, all integer, exact for any 16-bit input.
+// MODE 0: the 8x8 tiling (w == h).  MODE 1 / 2: the 16x8 / 8x16 tilings, two threads per tile (RdCost.cpp:2369-2560).  Each thread
+// transforms its own 8x8 half (L or R; T or B); the last butterfly stage of the 16-point transform pairs coefficient i of the two
+// halves, and |L_i + R_i| + |L_i - R_i| = 2 max(|L_i|, |R_i|): the threads swap 32 coefficients (the first half of the tile
+// takes i < 32, the second i >= 32), so a tile costs 32 shuffles per thread and no sample is loaded twice.  The DC pair keeps the
+// two terms apart (|L_0 + R_0| >> 2 is the scaled DC of the tile).  The tile value (int)(sum / sqrt(128) * 2) is formed from the
+// two threads' sums in FP64.  The 2-D transform of a sub-tile is 6 x 64 register butterflies, all integer, exact for any 16-bit input.
 // sign-extended low / high 16-bit half of a word: PRMT with the sign-replicate bit of the selector (which __byte_perm masks off)
 __device__ __forceinline__ int sext_lo(uint32_t w)
 {
@@ -222,7 +223,7 @@ __device__ __forceinline__ void load_diff8x8(const int16_t* __restrict__ o, int 
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(128, MODE == 0 ? 5 : 3) satd_tile_thread_kernel(const int16_t* __restrict__ org, int orgStride, long long orgBlk,
+__global__ void __launch_bounds__(128, 5) satd_tile_thread_kernel(const int16_t* __restrict__ org, int orgStride, long long orgBlk,
                                                                const int16_t* __restrict__ cur, int curStride, long long curBlk,
                                                                int w, int h, int n, int log2Units, int log2Ux,
                                                                unsigned long long* out)
@@ -232,23 +233,15 @@ __global__ void __launch_bounds__(128, MODE == 0 ? 5 : 3) satd_tile_thread_kerne
   const int       u = (int) (g & ((1 << log2Units) - 1)), ux = u & ((1 << log2Ux) - 1), uy = u >> log2Ux;
   const bool      active = blk < n;
   uint32_t        v = 0;
+  int             coef[MODE == 0 ? 1 : 64];   // the transformed half of a two-thread tile
+#pragma unroll
+  for (int i = 0; i < (MODE == 0 ? 1 : 64); i++) coef[i] = 0;
   if (active)
   {
     const int16_t* o = org + blk * orgBlk + (size_t) (uy * 8) * orgStride + ux * 8;
     const int16_t* c = cur + blk * curBlk + (size_t) (uy * 8) * curStride + ux * 8;
     int d[64];
     load_diff8x8(o, orgStride, c, curStride, d);
-    const int half = MODE == 1 ? (ux & 1) : MODE == 2 ? (uy & 1) : 0;
-    if (MODE != 0)
-    {
-      // partner half: 8 samples to the right / left (MODE 1), 8 rows below / above (MODE 2)
-      const ptrdiff_t po = MODE == 1 ? (half ? -8 : 8) : (ptrdiff_t) (half ? -8 : 8) * orgStride;
-      const ptrdiff_t pc = MODE == 1 ? (half ? -8 : 8) : (ptrdiff_t) (half ? -8 : 8) * curStride;
-      int e[64];
-      load_diff8x8(o + po, orgStride, c + pc, curStride, e);
-#pragma unroll
-      for (int i = 0; i < 64; i++) d[i] = half ? e[i] - d[i] : d[i] + e[i];
-    }
 #pragma unroll
     for (int st = 0; st < 6; st++)
 #pragma unroll
@@ -259,21 +252,43 @@ __global__ void __launch_bounds__(128, MODE == 0 ? 5 : 3) satd_tile_thread_kerne
         d[k]       = a + b;
         d[k + len] = a - b;
       }
-    uint32_t s = 0;
+    if (MODE == 0)
+    {
+      uint32_t s = 0;
 #pragma unroll
-    for (int i = 1; i < 64; i++) s = __sad(d[i], 0, s);
-    const uint32_t dc = (uint32_t) abs(d[0]);
-    s += half ? dc : (dc >> 2);
-    v = s;
+      for (int i = 1; i < 64; i++) s = __sad(d[i], 0, s);
+      s += (uint32_t) abs(d[0]) >> 2;
+      v = (s + 2) >> 2;
+    }
+    else
+    {
+#pragma unroll
+      for (int i = 0; i < 64; i++) coef[i] = d[i];
+    }
   }
-  if (MODE == 0)
-    v = (v + 2) >> 2;
-  else
+  if (MODE != 0)
   {
-    // the two halves of a tile sit in lanes that differ in one bit: bit 0 (MODE 1) or bit log2Ux (MODE 2)
-    const uint32_t t = v + __shfl_xor_sync(0xffffffffu, v, MODE == 1 ? 1 : (1 << log2Ux));
+    // the two halves of a tile sit in lanes that differ in one bit: bit 0 (MODE 1) or bit log2Ux (MODE 2); inactive lanes
+    // (beyond the batch) only take part in the shuffles
+    const int      pd = MODE == 1 ? 1 : (1 << log2Ux);
     const int      half = MODE == 1 ? (ux & 1) : (uy & 1);
-    v = half ? 0u : (uint32_t) (int) __dmul_rn(__ddiv_rn((double) (int) t, 0x1.6a09e667f3bcdp+3), 2.0);
+    uint32_t       s = 0;
+#pragma unroll
+    for (int i = 0; i < 32; i++)
+    {
+      const int own = half ? coef[32 + i] : coef[i];
+      const int got = __shfl_xor_sync(0xffffffffu, half ? coef[i] : coef[32 + i], pd);
+      if (i == 0)
+      {
+        const uint32_t both = 2u * (uint32_t) max(abs(own), abs(got));                       // coefficient 32 (second half)
+        const uint32_t dc   = ((uint32_t) abs(own + got) >> 2) + (uint32_t) abs(own - got);   // coefficient 0: scaled DC + its pair
+        s += half ? both : dc;
+      }
+      else
+        s += 2u * (uint32_t) max(abs(own), abs(got));
+    }
+    const uint32_t t = s + __shfl_xor_sync(0xffffffffu, s, pd);
+    v = (half || !active) ? 0u : (uint32_t) (int) __dmul_rn(__ddiv_rn((double) (int) t, 0x1.6a09e667f3bcdp+3), 2.0);
   }
   // sum over the units of a block: segments of min(units, 32) lanes; more than 32 units -> one atomic per warp
   const int seg = log2Units < 5 ? (1 << log2Units) : 32;
