@@ -422,6 +422,11 @@ def run_ours(args, rank, world, local_rank):
 
     # INT/ALU-pipe peak of this GPU, measured now (roofline denominator; SURVEY §8d: fused |a-b|+c counts 2 ops)
     pk = int_peak(0, 1 << 16)
+    # the kernel also runs two of its eight lanes on the FP32 pipe: the honest ceiling of that instruction mix (12 VABSDIFF : 4
+    # FADD pairs per 16 pixel-candidates, variant 19 of vtmme_int_peak; profiles/r02p_mixed_pipe_peaks.md) is reported beside the
+    # INT roofline SURVEY 8(d) defines
+    pk_mix = int_peak(19, 1 << 16)
+    mix_px = pk_mix["lane_instr_per_clk_per_sm"] / 1.25       # pixel-candidates per clock and SM
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     peak_ops = 2.0 * pk["lane_instr_per_clk_per_sm"] * sms * pk["sm_mhz"] * 1e6
 
@@ -581,6 +586,10 @@ def run_ours(args, rank, world, local_rank):
                          "algorithmic_ops_per_launch": B * ops_pair, "kernel_ms": k1_ms,
                          "kernel_share_of_step": float(kms[:, 0].sum() / elapsed_ms),
                          "whole_step_frac": B * ops_pair / (elapsed_ms / K * 1e-3) / peak_ops,
+                         "mixed_pipe_ceiling": {"what": "measured in this run: 12 VABSDIFF : 4 FADD-pair stream (the kernel's lane split), "
+                                                        "ALU and FP32 pipes together", "px_cand_per_clk_per_sm": mix_px,
+                                                "vs_int_pipe": mix_px / pk["lane_instr_per_clk_per_sm"],
+                                                "frac": achieved / (2.0 * mix_px * sms * pk["sm_mhz"] * 1e6)},
                          "other_kernels": {
                              "me_tree_upper": {"ms": k2_ms, "bound": "hbm", "algorithmic_bytes": surf_bytes,
                                                "achieved_gbs": surf_bytes / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else None,
