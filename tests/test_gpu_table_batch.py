@@ -88,3 +88,36 @@ def test_satd_batch_every_block(ms, oracle_lib):
             got = out.cpu().numpy()
             want = np.array([oracle_lib.vo_satd(B.ptr(org[i]), w, B.ptr(cur[i]), w, w, h) for i in range(n)], dtype=np.int64)
             assert np.array_equal(got, want), (w, h, lo, hi, np.flatnonzero(got != want)[:5])
+
+
+def test_interp_tight_buffers(ms, oracle_lib):
+    """The source buffer begins with the first sample a filter needs and ends with the last one (the kernels read aligned
+    words / 16-byte chunks around them: whatever shares a chunk with a needed sample must meet a zero coefficient)."""
+    import torch
+    rng = np.random.default_rng(4300)
+    stream = torch.cuda.Stream()
+    ms.set_stream(stream.cuda_stream)
+    for comp, taps in ((0, 8), (1, 4)):
+        before = taps // 2 - 1
+        for (w, h) in [(8, 8), (16, 8), (64, 16), (128, 128), (4, 8)]:
+            for vert in (0, 1):
+                for lead in (0, 1, 3):      # samples in front of the tight buffer inside the allocation: shifts its alignment
+                    ss = w + (0 if vert else taps - 1)
+                    rows = h + (taps - 1 if vert else 0)
+                    flat = rng.integers(0, 1024, lead + rows * ss, dtype=np.int16)
+                    tight = flat[lead:]
+                    off = before * ss if vert else before
+                    frac = 5 if comp == 0 else 11
+                    want = np.zeros((h, w), np.int16)
+                    if vert:
+                        oracle_lib.vo_filter_ver(comp, B.ptr(tight, off), ss, B.ptr(want), w, w, h, frac, 1, 1, 10, 0)
+                    else:
+                        oracle_lib.vo_filter_hor(comp, B.ptr(tight, off), ss, B.ptr(want), w, w, h, frac, 1, 10, 0)
+                    d_src = torch.from_numpy(flat).cuda()
+                    d_dst = torch.zeros((h, w), dtype=torch.int16, device="cuda")
+                    with torch.cuda.stream(stream):
+                        ms.interp_batch(comp, vert, d_src.data_ptr() + 2 * (lead + off), ss, ss * rows, d_dst.data_ptr(), w, w * h, w, h,
+                                        frac, 1, 1, 10, 0, 1)
+                    stream.synchronize()
+                    assert np.array_equal(d_dst.cpu().numpy(), want), (comp, w, h, vert, lead)
+    ms.set_stream(0)
