@@ -300,6 +300,75 @@ __global__ void __launch_bounds__(128, 5) satd_tile_thread_kernel(const int16_t*
   }
 }
 
+// ---- SATD of blocks with a 4-sample side: one THREAD per 8x4 / 4x8 / 4x4 tile (RdCost.cpp:2594-2817, 2166-2265) ----
+// TW x TH samples in registers, the separable Hadamard as log2(TW * TH) stages of register butterflies, DC >> 2, the tile's
+// normalisation ((int)(s / sqrt(32) * 2) in FP64; (s + 1) >> 1 for 4x4), tiles of a block summed over min(tiles, 32) lanes.
+template <int TW, int TH>
+__global__ void __launch_bounds__(128) satd_small_tile_kernel(const int16_t* __restrict__ org, int orgStride, long long orgBlk,
+                                                              const int16_t* __restrict__ cur, int curStride, long long curBlk,
+                                                              int n, int log2Tiles, int log2Tx, unsigned long long* out)
+{
+  constexpr int   N = TW * TH;
+  const long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x;   // global tile
+  const long long blk = g >> log2Tiles;
+  const int       t = (int) (g & ((1 << log2Tiles) - 1)), tx = t & ((1 << log2Tx) - 1), ty = t >> log2Tx;
+  const bool      active = blk < n;
+  uint32_t        v = 0;
+  if (active)
+  {
+    const int16_t* o = org + blk * orgBlk + (size_t) (ty * TH) * orgStride + tx * TW;
+    const int16_t* c = cur + blk * curBlk + (size_t) (ty * TH) * curStride + tx * TW;
+    int d[N];
+#pragma unroll
+    for (int r = 0; r < TH; r++)
+    {
+      uint32_t aw[TW / 2], bw[TW / 2];
+      if (TW == 8)
+      {
+        const uint4 a = *reinterpret_cast<const uint4*>(o + (size_t) r * orgStride), b = *reinterpret_cast<const uint4*>(c + (size_t) r * curStride);
+        aw[0] = a.x; aw[1] = a.y; aw[TW / 2 - 2] = a.z; aw[TW / 2 - 1] = a.w;
+        bw[0] = b.x; bw[1] = b.y; bw[TW / 2 - 2] = b.z; bw[TW / 2 - 1] = b.w;
+      }
+      else
+      {
+        const uint2 a = *reinterpret_cast<const uint2*>(o + (size_t) r * orgStride), b = *reinterpret_cast<const uint2*>(c + (size_t) r * curStride);
+        aw[0] = a.x; aw[1] = a.y;
+        bw[0] = b.x; bw[1] = b.y;
+      }
+#pragma unroll
+      for (int k = 0; k < TW / 2; k++)
+      {
+        d[r * TW + 2 * k]     = sext_lo(aw[k]) - sext_lo(bw[k]);
+        d[r * TW + 2 * k + 1] = sext_hi(aw[k]) - sext_hi(bw[k]);
+      }
+    }
+    constexpr int STAGES = N == 32 ? 5 : 4;
+#pragma unroll
+    for (int st = 0; st < STAGES; st++)
+#pragma unroll
+      for (int j = 0; j < N / 2; j++)
+      {
+        const int len = 1 << st, k = ((j >> st) << (st + 1)) | (j & (len - 1));
+        const int a = d[k], b = d[k + len];
+        d[k]       = a + b;
+        d[k + len] = a - b;
+      }
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 1; i < N; i++) s = __sad(d[i], 0, s);
+    s += (uint32_t) abs(d[0]) >> 2;
+    if (N == 16) v = (s + 1) >> 1;
+    else v = (uint32_t) (int) __dmul_rn(__ddiv_rn((double) (int) s, 0x1.6a09e667f3bcdp+2), 2.0);   // / sqrt(32) * 2
+  }
+  const int seg = log2Tiles < 5 ? (1 << log2Tiles) : 32;
+  for (int m = seg >> 1; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  if (active && (threadIdx.x & (seg - 1)) == 0)
+  {
+    if (log2Tiles <= 5) out[blk] = v;
+    else atomicAdd(out + blk, (unsigned long long) v);
+  }
+}
+
 // ---- interpolation: InterpolationFilter::filter<N,...> / filterCopy (InterpolationFilter.cpp:397-656) with the
 //      public dispatch of filterHor/filterVer (:749-895).  One CTA per block. ----
 struct InterpArgs
@@ -920,6 +989,25 @@ cudaError_t launch_dist_batch(int kind, const int16_t* org, int orgStride, long 
     else VTMME_SATD_TT(2);
 #undef VTMME_SATD_TT
     return cudaGetLastError();
+  }
+  // blocks with a 4-sample side: 8x4 tiles (w > h = 4), 4x8 tiles (h > w = 4), the 4x4 block
+  if (pow2 && (w == 4 || h == 4) && w <= 128 && h <= 128 && !satd_warp_only())
+  {
+    const int tw = (w > h) ? 8 : 4, th = (h > w) ? 8 : 4;
+    if (aligned_layout(org, orgStride, orgBlockStride, tw) && aligned_layout(cur, curStride, curBlockStride, tw))
+    {
+      int log2Tx = 0, log2Tiles = 0;
+      while ((tw << log2Tx) < w) log2Tx++;
+      while (((long long) tw * th << log2Tiles) < (long long) w * h) log2Tiles++;
+      const long long tiles = (long long) n << log2Tiles;
+      const int       ctas  = (int) ((tiles + 127) / 128);
+#define VTMME_SATD_ST(TW_, TH_) satd_small_tile_kernel<TW_, TH_><<<ctas, 128, 0, st>>>(org, orgStride, orgBlockStride, cur, curStride, curBlockStride, n, log2Tiles, log2Tx, out)
+      if (tw == 8) VTMME_SATD_ST(8, 4);
+      else if (th == 8) VTMME_SATD_ST(4, 8);
+      else VTMME_SATD_ST(4, 4);
+#undef VTMME_SATD_ST
+      return cudaGetLastError();
+    }
   }
   if (aligned_layout(org, orgStride, orgBlockStride, 8) && aligned_layout(cur, curStride, curBlockStride, 8))
     satd_batch_kernel<true><<<blocks, 256, 0, st>>>(org, orgStride, orgBlockStride, cur, curStride, curBlockStride, w, h, n, out);
