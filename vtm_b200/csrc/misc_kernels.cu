@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(256) satd_batch_kernel(const int16_t* __restri
 // takes i < 32, the second i >= 32), so a tile costs 32 shuffles per thread and no sample is loaded twice.  The DC pair keeps the
 // two terms apart (|L_0 + R_0| >> 2 is the scaled DC of the tile).  The tile value (int)(sum / sqrt(128) * 2) is formed from the
 // two threads' sums in FP64.  The 2-D transform of a sub-tile is 6 x 64 register butterflies, all integer, exact for any 16-bit input.
+
 // sign-extended low / high 16-bit half of a word: PRMT with the sign-replicate bit of the selector (which __byte_perm masks off)
 __device__ __forceinline__ int sext_lo(uint32_t w)
 {
@@ -370,7 +371,8 @@ __global__ void __launch_bounds__(128) satd_small_tile_kernel(const int16_t* __r
 }
 
 // ---- interpolation: InterpolationFilter::filter<N,...> / filterCopy (InterpolationFilter.cpp:397-656) with the
-//      public dispatch of filterHor/filterVer (:749-895).  One CTA per block. ----
+//      public dispatch of filterHor/filterVer (:749-895).  interp_batch_kernel is the generic form (any width, copies, 2-tap
+//      filters); the fast paths for 4- and 8-tap filters follow it. ----
 struct InterpArgs
 {
   const int16_t* src;
@@ -747,8 +749,8 @@ __global__ void __launch_bounds__(kInterpThreads) interp_hor8_kernel(InterpArgs 
   }
 }
 
-// Requires word-aligned column pairs (source base 4-byte aligned, even strides) and source / destination spans below 2 GB, so
-// that every access is "uniform 64-bit row base + 32-bit thread offset" (no 64-bit address arithmetic per row and thread).
+// Vertical: requires word-aligned column pairs (source base 4-byte aligned, even strides) and source / destination spans below
+// 2 GB: thread offsets are 32-bit, added once to uniform bases (per-row 64-bit index arithmetic cost a quarter of the instructions).
 template <int TAPS>
 __global__ void __launch_bounds__(kInterpThreads) interp_ver8_kernel(InterpArgs a, uint32_t units, FastDiv dHalfW, FastDiv dH8)
 {
